@@ -1,0 +1,139 @@
+"""The named configurations of BASELINE.json as concrete inputs.
+
+A `Case` bundles a mesh, thermo, schemes, solver controls, boundary conditions and initial fields, and can
+`apply()` itself to any object exposing the icsb200 C-ABI wrapper (`capi.Api`): the CUDA product
+(`icsfoam_b200.context.Context`) or the test-only oracle.  Dictionary key names follow the tutorial
+dictionaries (fvSchemes / fvSolution / thermophysicalProperties / 0/*).
+"""
+import numpy as np
+
+from . import capi
+from . import meshtools as mt
+
+RR = 8314.46261815324  # J/(kmol K): OpenFOAM thermodynamic::RR = 1e3 * physicoChemical::R (kept a parameter)
+
+
+class Case:
+    def __init__(self, name, mesh, R, Cp, schemes, controls, bcs, p, U, T, mu=0.0, Pr=1.0, n_iter_default=20):
+        self.name, self.mesh, self.R, self.Cp, self.mu, self.Pr = name, mesh, R, Cp, mu, Pr
+        self.schemes, self.controls, self.bcs = schemes, controls, bcs
+        self.p = np.ascontiguousarray(p, np.float64)
+        self.U = np.ascontiguousarray(U, np.float64)
+        self.T = np.ascontiguousarray(T, np.float64)
+        self.n_iter_default = n_iter_default
+
+    def apply(self, api, mesh=None, cells=None):
+        """Configure `api` with this case.  `mesh`/`cells` select a partition (cells = global cell ids)."""
+        m = mesh or self.mesh
+        api.mesh_set(m)
+        api.thermo_set(self.R, self.Cp, self.mu, self.Pr)
+        api.schemes_set(self.schemes)
+        names = [p["name"] for p in m.patches]
+        for patch, fields in self.bcs.items():
+            if patch not in names:
+                continue
+            for field, (kind, params) in fields.items():
+                api.bc_set(patch, {"p": capi.FIELD_P, "U": capi.FIELD_U, "T": capi.FIELD_T}[field], kind, params)
+        if cells is None:
+            api.state_set(self.p, self.U, self.T)
+        else:
+            api.state_set(self.p[cells], self.U[cells], self.T[cells])
+        return api
+
+    def partition(self, n_parts, mode="x"):
+        """Slab / block decomposition of the structured mesh (decomposePar 'simple' stand-in)."""
+        C = self.mesh.C
+        if mode == "x":
+            order = np.argsort(C[:, 0], kind="stable")
+            part = np.empty(self.mesh.n_cells, np.int32)
+            part[order] = (np.arange(self.mesh.n_cells) * n_parts // self.mesh.n_cells).astype(np.int32)
+        else:  # 2x2x2-style blocks by coordinate medians
+            nx, ny, nz = mode
+            part = np.zeros(self.mesh.n_cells, np.int32)
+            for d, n in enumerate((nx, ny, nz)):
+                q = np.quantile(C[:, d], np.linspace(0, 1, n + 1)[1:-1]) if n > 1 else []
+                part = part * n + np.searchsorted(q, C[:, d]).astype(np.int32)
+        meshes = [self.mesh.extract_part(part, r) for r in range(n_parts)]
+        return part, meshes
+
+
+def _uniform(mesh, p, U, T):
+    N = mesh.n_cells
+    return np.full(N, float(p)), np.tile(np.asarray(U, float), (N, 1)), np.full(N, float(T))
+
+
+def shock_tube(n=500, flux="ROE", transient=True):
+    """C1 tutorials/shockTube: 1-D Sod tube.  ROE as shipped (fvSchemes:19-33) or AUSMPlusUp (BASELINE.json)."""
+    mesh = mt.shock_tube(n)
+    R, Cp = RR / 28.96, 1004.5
+    p, U, T = _uniform(mesh, 1e5, (0, 0, 0), 348.432)
+    right = (mesh.C[:, 0] >= 0.0)  # setFieldsDict:19-37 boxToCell (0 -1 -1) (0.5 1 1)
+    p[right], T[right] = 1e4, 278.746
+    sch = capi.default_schemes(flux_scheme=flux, limiter_rho="vanLeer", limiter_U="vanLeer", limiter_T="vanLeer",
+                               ddt_scheme="backward" if transient else "steadyState", delta_t=1e-6, pseudo_co_num=1.0)
+    ctl = capi.solver_controls("LUSGS", n_directions=5, max_iter=20, tolerance=1e-12, rel_tol=1e-4)
+    zg = ("zeroGradient", ())
+    bcs = {n_: {"p": zg, "T": zg, "U": zg} for n_ in ("side1", "side2")}
+    for n_ in ("wallYmin", "wallYmax", "wallZmin", "wallZmax"):
+        bcs[n_] = {"p": zg, "T": zg, "U": ("slip", ())}
+    return Case("shockTube", mesh, R, Cp, sch, ctl, bcs, p, U, T, n_iter_default=10)
+
+
+def bump(nxb=66, ny=54, co=200.0):
+    """C3 tutorials/circularArcBump/transonic, optionally refined (bump-4M: nxb=1280, ny=1040)."""
+    mesh = mt.bump(nxb, ny)
+    R, Cp = RR / 28.966, 1005.0
+    p, U, T = _uniform(mesh, 74653.0, (218.0, 0, 0), 274.9)
+    sch = capi.default_schemes(flux_scheme="HLLC", limiter_rho="Minmod", limiter_U="Minmod", limiter_T="Minmod",
+                               ddt_scheme="steadyState", pseudo_co_num=co, pseudo_co_num_max=co)
+    ctl = capi.solver_controls("LUSGS", n_directions=5, max_iter=10, tolerance=1e-10, rel_tol=1e-2)
+    zg = ("zeroGradient", ())
+    bcs = {
+        "INLE1": {"p": ("totalPressure", (101300.0, 1.4)), "U": ("pressureInletOutletVelocity", (0, 0, 0)),
+                  "T": ("totalTemperature", (288.15, 1.4))},
+        "PRES2": {"p": ("fixedValue", (74653.0,)), "U": zg, "T": zg},
+        "WALL3": {"p": zg, "U": ("slip", ()), "T": zg},
+        "WALL4": {"p": zg, "U": ("slip", ()), "T": zg},
+    }
+    return Case("bump", mesh, R, Cp, sch, ctl, bcs, p, U, T, n_iter_default=20)
+
+
+def onera_box(n=48, co=100.0, flux="HLLC"):
+    """C4 synthetic stand-in for tutorials/OneraM6Wing (inviscid, HLLC, vanLeer, steady, Co=100)."""
+    mesh = mt.onera_box(n)
+    R, Cp = RR / 28.966, 1005.0
+    Uinf = (285.6, 15.268, 0.0)
+    p, U, T = _uniform(mesh, 101325.0, Uinf, 288.15)
+    sch = capi.default_schemes(flux_scheme=flux, limiter_rho="vanLeer", limiter_U="vanLeer", limiter_T="vanLeer",
+                               ddt_scheme="steadyState", pseudo_co_num=co, pseudo_co_num_max=co)
+    ctl = capi.solver_controls("LUSGS", n_directions=5, max_iter=10, tolerance=1e-6, rel_tol=1e-1)
+    slip = ("slip", ())
+    fs = {"p": ("freestreamPressure", (101325.0,) + Uinf), "U": ("freestream", Uinf), "T": ("inletOutlet", (288.15,))}
+    bcs = {"wing": {"p": slip, "U": slip, "T": slip}, "symmetry": {"p": slip, "U": slip, "T": slip}}
+    for n_ in ("inlet", "outlet", "lateral", "top"):
+        bcs[n_] = dict(fs)
+    return Case("onera-box", mesh, R, Cp, sch, ctl, bcs, p, U, T, n_iter_default=20)
+
+
+def periodic_box(n=8, flux="HLLC", limiter="vanLeer", seed=0, nz=None):
+    """Small randomised box with a translational cyclic pair in x — a parity-test workhorse, not a tutorial."""
+    mesh = mt.structured(1, n, n, nz or n, 0, (0, 0, 0), (1.0, 1.2, 0.9),
+                         patch_kinds=(capi.PATCH, capi.PATCH, capi.WALL, capi.PATCH, capi.SYMMETRYPLANE, capi.PATCH))
+    mesh.set_cyclic("xmin", "xmax")
+    rng = np.random.default_rng(seed)
+    N = mesh.n_cells
+    p = 1e5 * (1 + 0.2 * rng.random(N))
+    T = 300 * (1 + 0.2 * rng.random(N))
+    U = 150 * (rng.random((N, 3)) - 0.3)
+    sch = capi.default_schemes(flux_scheme=flux, limiter_rho=limiter, limiter_U=limiter, limiter_T=limiter,
+                               ddt_scheme="steadyState", pseudo_co_num=5.0, pseudo_co_num_max=50.0)
+    ctl = capi.solver_controls("LUSGS", n_directions=5, max_iter=10, tolerance=1e-10, rel_tol=1e-3)
+    zg, slip = ("zeroGradient", ()), ("slip", ())
+    bcs = {
+        "ymin": {"p": zg, "U": slip, "T": zg},
+        "ymax": {"p": ("fixedValue", (1.05e5,)), "U": ("inletOutlet", (50.0, 10.0, 0.0)), "T": ("inletOutlet", (310.0,))},
+        "zmin": {"p": slip, "U": slip, "T": slip},
+        "zmax": {"p": ("freestreamPressure", (1.0e5, 50.0, 10.0, 20.0)), "U": ("freestream", (50.0, 10.0, 20.0)),
+                 "T": ("fixedValue", (305.0,))},
+    }
+    return Case("periodic-box", mesh, 287.0, 1005.0, sch, ctl, bcs, p, U, T)

@@ -1,0 +1,167 @@
+"""Host-side mesh inputs for the icsb200 hot path (block-structured generator, polyMesh reader, partitioner).
+
+Thin ctypes wrapper over meshtools.cpp (libicsmesh.so, built by icsfoam_b200.build).  Produces the flat
+fvMesh arrays that `icsb200_mesh_set` takes.  Input tooling only — never inside a timed region.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ..capi import CYCLIC, EMPTY, PATCH, PROCESSOR, SYMMETRYPLANE, WALL  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libicsmesh.so")
+        if not os.path.exists(path):
+            from .. import build
+            build.build_meshtools()
+        _LIB = C.CDLL(path)
+        _LIB.icsmesh_structured.restype = C.c_void_p
+        _LIB.icsmesh_read_polymesh.restype = C.c_void_p
+        _LIB.icsmesh_extract_part.restype = C.c_void_p
+        _LIB.icsmesh_error.restype = C.c_char_p
+    return _LIB
+
+
+class Mesh:
+    """fvMesh arrays in OpenFOAM's native AoS layout."""
+
+    def __init__(self, handle):
+        lib = _lib()
+        self._h = C.c_void_p(handle)
+        err = lib.icsmesh_error(self._h)
+        if err:
+            raise RuntimeError("meshtools: " + err.decode())
+        sz = (C.c_int * 7)()
+        lib.icsmesh_sizes(self._h, sz)
+        self.n_cells, self.n_internal_faces, self.n_faces, npatch = sz[0], sz[1], sz[2], sz[3]
+        self.solutionD = [sz[4], sz[5], sz[6]]
+        N, F, FT = self.n_cells, self.n_internal_faces, self.n_faces
+        self.owner = np.empty(FT, np.int32)
+        self.neighbour = np.empty(F, np.int32)
+        self.Sf = np.empty((FT, 3))
+        self.Cf = np.empty((FT, 3))
+        self.magSf = np.empty(FT)
+        self.weights = np.empty(FT)
+        self.deltaCoeffs = np.empty(FT)
+        self.nonOrthDeltaCoeffs = np.empty(FT)
+        self.C = np.empty((N, 3))
+        self.V = np.empty(N)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        lib.icsmesh_arrays(self._h, p(self.owner), p(self.neighbour), p(self.Sf), p(self.Cf), p(self.magSf), p(self.weights),
+                           p(self.deltaCoeffs), p(self.nonOrthDeltaCoeffs), p(self.C), p(self.V))
+        self.patches = []
+        for i in range(npatch):
+            o = (C.c_int * 5)()
+            name = C.create_string_buffer(64)
+            lib.icsmesh_patch(self._h, i, o, name)
+            self.patches.append({"name": name.value.decode(), "kind": o[0], "start": o[1], "size": o[2], "nbr_rank": o[3],
+                                 "nbr_patch": o[4]})
+        self.cell_global = None
+        self.face_global = None
+
+    def patch_index(self, name):
+        return [p["name"] for p in self.patches].index(name)
+
+    def patch_faces(self, name):
+        p = self.patches[self.patch_index(name)]
+        return np.arange(p["start"], p["start"] + p["size"])
+
+    def set_cyclic(self, a, b):
+        """Turn two equally-sized patches into a translational cyclic pair."""
+        ia, ib = self.patch_index(a), self.patch_index(b)
+        lib = _lib()
+        lib.icsmesh_set_patch_kind(self._h, ia, CYCLIC, ib)
+        lib.icsmesh_set_patch_kind(self._h, ib, CYCLIC, ia)
+        self.patches[ia].update(kind=CYCLIC, nbr_patch=ib)
+        self.patches[ib].update(kind=CYCLIC, nbr_patch=ia)
+        # coupled weights: cyclicFvPatch::makeWeights — own/neighbour normal distances
+        for pa, pb in ((self.patches[ia], self.patches[ib]), (self.patches[ib], self.patches[ia])):
+            fa = np.arange(pa["start"], pa["start"] + pa["size"])
+            fb = np.arange(pb["start"], pb["start"] + pb["size"])
+            nfa = self.Sf[fa] / self.magSf[fa, None]
+            nfb = self.Sf[fb] / self.magSf[fb, None]
+            da = np.abs(np.einsum("ij,ij->i", nfa, self.Cf[fa] - self.C[self.owner[fa]]))
+            db = np.abs(np.einsum("ij,ij->i", nfb, self.Cf[fb] - self.C[self.owner[fb]]))
+            self.weights[fa] = db / (da + db)
+            d = (self.Cf[fa] - self.C[self.owner[fa]]) - (self.Cf[fb] - self.C[self.owner[fb]])
+            md = np.linalg.norm(d, axis=1)
+            self.deltaCoeffs[fa] = 1.0 / md
+            self.nonOrthDeltaCoeffs[fa] = 1.0 / np.maximum(np.einsum("ij,ij->i", nfa, d), 0.05 * md)
+
+    def extract_part(self, part, rank):
+        """decomposePar stand-in: sub-mesh of the cells with part[c] == rank (processor patches appended)."""
+        part = np.ascontiguousarray(part, np.int32)
+        sub = Mesh(_lib().icsmesh_extract_part(self._h, part.ctypes.data_as(C.c_void_p), int(rank)))
+        sub.cell_global = np.empty(sub.n_cells, np.int32)
+        sub.face_global = np.empty(sub.n_faces, np.int32)
+        _lib().icsmesh_part_maps(sub._h, sub.cell_global.ctypes.data_as(C.c_void_p), sub.face_global.ctypes.data_as(C.c_void_p))
+        # processor-patch interpolation factors from the parent geometry (processorFvPatch::makeWeights)
+        for p in sub.patches:
+            if p["kind"] != PROCESSOR:
+                continue
+            f = np.arange(p["start"], p["start"] + p["size"])
+            gf = sub.face_global[f]
+            own_is_owner = self.owner[gf] == sub.cell_global[sub.owner[f]]
+            nbr = np.where(own_is_owner, self.neighbour[gf], self.owner[gf])
+            nf = sub.Sf[f] / sub.magSf[f, None]
+            d_own = np.abs(np.einsum("ij,ij->i", nf, sub.Cf[f] - sub.C[sub.owner[f]]))
+            d_nbr = np.abs(np.einsum("ij,ij->i", nf, self.C[nbr] - sub.Cf[f]))
+            sub.weights[f] = d_nbr / (d_own + d_nbr)
+            d = self.C[nbr] - sub.C[sub.owner[f]]
+            md = np.linalg.norm(d, axis=1)
+            sub.deltaCoeffs[f] = 1.0 / md
+            sub.nonOrthDeltaCoeffs[f] = 1.0 / np.maximum(np.einsum("ij,ij->i", nf, d), 0.05 * md)
+        return sub
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib().icsmesh_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def structured(nb, nxb, ny, nz, kind=0, lo=(0, 0, 0), hi=(1, 1, 1), grad_y=1.0, amp=0.0,
+               patch_kinds=(PATCH,) * 6, patch_names=("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")):
+    lo_a = (C.c_double * 3)(*lo)
+    hi_a = (C.c_double * 3)(*hi)
+    kinds = (C.c_int * 6)(*patch_kinds)
+    names = (C.c_char_p * 6)(*[n.encode() for n in patch_names])
+    h = _lib().icsmesh_structured(nb, nxb, ny, nz, kind, lo_a, hi_a, C.c_double(grad_y), C.c_double(amp), kinds, names)
+    return Mesh(h)
+
+
+def read_polymesh(directory):
+    return Mesh(_lib().icsmesh_read_polymesh(directory.encode()))
+
+
+# ---- the named configurations of BASELINE.json (SURVEY.md §8d "Configs as concrete synthetic inputs") ----
+def shock_tube(n=500):
+    """C1: tutorials/shockTube/system/blockMeshDict:17-32 — hex (n 1 1), all six sides 'patch'."""
+    return structured(1, n, 1, 1, 0, (-0.5, -0.25, -0.5), (0.5, 0.25, 0.5),
+                      patch_kinds=(PATCH,) * 6, patch_names=("side1", "side2", "wallYmin", "wallYmax", "wallZmin", "wallZmax"))
+
+
+def bump(nxb=66, ny=54):
+    """C3: tutorials/circularArcBump/transonic/system/blockMeshDict — 3 blocks of (nxb x ny x 1), grading 3.5 in y."""
+    return structured(3, nxb, ny, 1, 1, (-1.5, 0.0, -0.1), (1.5, 1.0, 0.1), grad_y=3.5, amp=0.1,
+                      patch_kinds=(PATCH, PATCH, WALL, WALL, EMPTY, EMPTY),
+                      patch_names=("INLE1", "PRES2", "WALL4", "WALL3", "defaultFacesA", "defaultFacesB"))
+
+
+def onera_box(n=48, nz=None, ny=None):
+    """C4: synthetic 3-D transonic box (the shipped OneraM6 mesh is incomplete — SURVEY §0.5):
+    bump wall on z-min (slip), symmetryPlane on y-min, freestream elsewhere."""
+    ny = ny or n
+    nz = nz or n
+    return structured(1, n, ny, nz, 2, (-1.0, 0.0, 0.0), (2.0, 3.0, 3.0), amp=0.12,
+                      patch_kinds=(PATCH, PATCH, SYMMETRYPLANE, PATCH, WALL, PATCH),
+                      patch_names=("inlet", "outlet", "symmetry", "lateral", "wing", "top"))

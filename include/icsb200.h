@@ -1,0 +1,187 @@
+/* icsb200.h — C ABI of the B200-native ICSFoam implicit pseudo-time iteration hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / OpenFOAM / CUDA
+ * types.  Every entry point names the reference interface it replaces (paths relative to the
+ * ICSFoam tree).  Arrays are caller-owned HOST pointers in OpenFOAM's native AoS layout
+ * (vector = 3 contiguous doubles, tensor = 9 row-major doubles, label = 32-bit int) so that
+ * Field<vector>::cdata() can be passed without a copy; the device layout is private.
+ * Entry points ending in _dev operate on state already resident in HBM (no host transfer).
+ *
+ * All functions return 0 on success or a negative ICSB200_E* code; icsb200_last_error() gives the
+ * message (the OpenFOAM adapter turns non-zero into FatalErrorInFunction, mirroring
+ * coupledMatrixSolver.C:53-61, lusgs.C:82-85).  One context per rank / GPU, one host thread.
+ * There is no CPU fallback: icsb200_create fails if no sm_100 device is present.
+ */
+#ifndef ICSB200_H
+#define ICSB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct icsb200_ctx icsb200_ctx;
+
+enum {
+    ICSB200_OK = 0,
+    ICSB200_EINVAL = -1,   /* bad argument / unknown selector (cf. newConvectiveFluxScheme.C:56-66) */
+    ICSB200_ESTATE = -2,   /* call order violated (mesh/state/matrix not set) */
+    ICSB200_ECUDA = -3,    /* CUDA / NCCL runtime failure */
+    ICSB200_ESINGULAR = -4 /* "All diagonals of coupledMatrix are zero" lusgs.C:118-123 */
+};
+
+/* fvPatch kinds as the hot path distinguishes them (convectiveFluxScheme.C:243, setCoAndDeltaT.H:72-86) */
+enum { ICSB200_PATCH = 0, ICSB200_WALL = 1, ICSB200_EMPTY = 2, ICSB200_SYMMETRYPLANE = 3, ICSB200_CYCLIC = 4, ICSB200_PROCESSOR = 5 };
+
+typedef struct {
+    int kind;           /* ICSB200_PATCH ... */
+    int start, size;    /* face range [start, start+size) in the global face list */
+    int nbr_rank;       /* PROCESSOR: neighbProcNo */
+    int nbr_patch;      /* CYCLIC: index of the neighbour patch */
+    double forwardT[9]; /* CYCLIC: rotation tensor (identity for translational) */
+} icsb200_patch;
+
+/* run-time selectors — same words as the reference dictionaries */
+enum { ICSB200_FLUX_HLLC = 0, ICSB200_FLUX_ROE = 1, ICSB200_FLUX_AUSMPLUSUP = 2 };    /* fvSchemes convectiveFluxScheme/fluxScheme */
+enum { ICSB200_LIM_UPWIND = 0, ICSB200_LIM_VANLEER = 1, ICSB200_LIM_MINMOD = 2, ICSB200_LIM_LINEAR = 3 }; /* interpolationSchemes reconstruct(.) */
+enum { ICSB200_DDT_STEADY = 0, ICSB200_DDT_EULER = 1, ICSB200_DDT_BACKWARD = 2 };       /* ddtSchemes: dualTime rPseudoDeltaT <inner> */
+enum { ICSB200_SOLVER_GMRES = 0 };                                                       /* fvSolution flowSolver/solver */
+enum { ICSB200_PRECOND_LUSGS = 0, ICSB200_PRECOND_JACOBI = 1 };                          /* flowSolver/<solver>/preconditioner */
+
+/* boundary-condition kinds for p, U, T (OpenFOAM fvPatchField type names) */
+enum {
+    ICSB200_BC_ZEROGRADIENT = 0,
+    ICSB200_BC_FIXEDVALUE = 1,                  /* params: value (1 or 3 doubles) */
+    ICSB200_BC_SLIP = 2,                        /* also symmetryPlane (basicSymmetry) */
+    ICSB200_BC_EMPTY = 3,
+    ICSB200_BC_INLETOUTLET = 4,                 /* params: inletValue; also 'freestream' (mixed on phi) */
+    ICSB200_BC_TOTALPRESSURE = 5,               /* params: p0, gamma */
+    ICSB200_BC_TOTALTEMPERATURE = 6,            /* params: T0, gamma */
+    ICSB200_BC_PRESSUREINLETOUTLETVELOCITY = 7, /* params: tangentialVelocity (3) */
+    ICSB200_BC_FREESTREAMPRESSURE = 8,          /* params: freestreamValue, Uinf (3) */
+    ICSB200_BC_COUPLED = 9                      /* cyclic / processor: set automatically */
+};
+enum { ICSB200_FIELD_P = 0, ICSB200_FIELD_U = 1, ICSB200_FIELD_T = 2 };
+
+typedef struct {
+    int flux_scheme;          /* ICSB200_FLUX_*        (newConvectiveFluxScheme.C:50) */
+    int limiter_rho;          /* reconstruct(rho): rho, p  (hllcFluxScheme.C:84-88) */
+    int limiter_U;            /* reconstruct(U)            (hllcFluxScheme.C:92-97) */
+    int limiter_T;            /* reconstruct(T): c, E, H   (hllcFluxScheme.C:105-121) */
+    int low_mach_ausm;        /* lowMachAusm, default 1    (ausmPlusUpFluxScheme.C:61) */
+    double entropy_fix_coeff; /* entropyFixCoeff, default 0.05 (roeFluxScheme.C:255) */
+    int ddt_scheme;           /* ICSB200_DDT_*  inner scheme of 'dualTime rPseudoDeltaT <inner>' (dualTimeDdtScheme.H:109-117) */
+    double delta_t;           /* physical time step (transient) */
+    int local_timestepping;   /* pseudoTime/localTimestepping, default 1 (initialise.H:39-43) */
+    int local_timestepping_bounding; /* default 1 (initialise.H:52-57) */
+    double local_timestepping_lower_bound; /* default 0.95 (initialise.H:59-69) */
+    double pseudo_co_num;     /* pseudoCoNum (createFields.H:218-254) */
+    double pseudo_co_num_min, pseudo_co_num_max;          /* beginTimeStep.H:29-33 */
+    double pseudo_co_num_max_incr, pseudo_co_num_min_decr; /* beginTimeStep.H:35-45 */
+    double rho_min, T_min, T_max;                          /* updateFields.H:11-35 */
+} icsb200_schemes;
+
+typedef struct {
+    int solver;         /* ICSB200_SOLVER_GMRES */
+    int preconditioner; /* ICSB200_PRECOND_*   (coupledMatrixPreconditioner.C:41-64) */
+    int n_directions;   /* nDirections         (gmres.C:81) */
+    int max_iter;       /* maxIter, default 1000 (coupledMatrixSolver.C:81, coupledMatrix.C:40) */
+    int min_iter;       /* minIter, default 0 */
+    double tolerance;   /* tolerance */
+    double rel_tol;     /* relTol */
+} icsb200_solver_controls;
+
+/* residualsIO (residualsIO.H:54-312) for nScalar=2 (rho, rhoE), nVector=1 (rhoU) */
+typedef struct {
+    double s_init[2], v_init[3];
+    double s_final[2], v_final[3];
+    int n_iterations;
+} icsb200_residuals;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* nccl_unique_id: 128-byte ncclUniqueId shared by all ranks (NULL when n_ranks == 1). */
+int icsb200_create(icsb200_ctx** ctx, int device, const void* nccl_unique_id, int rank, int n_ranks);
+int icsb200_destroy(icsb200_ctx* ctx);
+const char* icsb200_last_error(icsb200_ctx* ctx);
+/* fills a 128-byte buffer with a fresh ncclUniqueId (rank 0 calls this, then broadcasts it) */
+int icsb200_nccl_unique_id(void* out128);
+
+/* ---- setup --------------------------------------------------------------------------------- */
+/* fvMesh as the reference reads it: mesh.owner()/neighbour() (lduAddr, lusgs.C:141-156), Sf/magSf
+ * (hllcFluxScheme.C:78), weights (convectiveFluxScheme.C:376), deltaCoeffs/nonOrthDeltaCoeffs
+ * (setCoAndDeltaT.H:61,145), C (limited schemes), V (residualsUpdate.H:81-83), Cf (coupled patch
+ * deltas), boundary patches, solutionD (coupledMatrix.C:371-382).  n_faces includes boundary faces. */
+int icsb200_mesh_set(icsb200_ctx* ctx, int n_cells, int n_internal_faces, int n_faces, const int* owner,
+                     const int* neighbour, const double* Sf, const double* magSf, const double* weights,
+                     const double* deltaCoeffs, const double* nonOrthDeltaCoeffs, const double* C, const double* V,
+                     const double* Cf, int n_patches, const icsb200_patch* patches, const int solutionD[3]);
+/* hePsiThermo<pureMixture<constTransport<hConst<perfectGas>>>>, sensibleInternalEnergy (createFields.H:17-35) */
+int icsb200_thermo_set(icsb200_ctx* ctx, double R, double Cp, double mu, double Pr);
+int icsb200_schemes_set(icsb200_ctx* ctx, const icsb200_schemes* s);
+/* fvPatchField of p, U or T on one patch (0/p, 0/U, 0/T boundaryField entries) */
+int icsb200_bc_set(icsb200_ctx* ctx, int patch, int field, int kind, const double* params, int n_params);
+
+/* ---- state --------------------------------------------------------------------------------- */
+/* internal fields p[N], U[3N], T[N]; evaluates BCs + thermo and builds rho, rhoU, rhoE (createFields.H:75-131) */
+int icsb200_state_set(icsb200_ctx* ctx, const double* p, const double* U, const double* T);
+/* any pointer may be NULL.  Cell arrays [N]/[3N]. */
+int icsb200_state_get(icsb200_ctx* ctx, double* rho, double* rhoU, double* rhoE, double* p, double* U, double* T);
+/* boundary values, indexed by (face - n_internal_faces); any pointer may be NULL */
+int icsb200_boundary_get(icsb200_ctx* ctx, double* rho_b, double* U_b, double* p_b, double* T_b);
+/* transient: shift W -> W.old -> W.oldOld (runTime++ of dbnsFoam.C:103) */
+int icsb200_new_time_step(icsb200_ctx* ctx);
+
+/* ---- the hot path, piecewise (for parity and for partial offload) ---------------------------- */
+/* convectiveFluxScheme::calcFlux(phi, phiUp, phiEp) (convectiveFluxScheme.H:219-224;
+ * hllcFluxScheme.C:70-240, roeFluxScheme.C:276-409, ausmPlusUpFluxScheme.C:73-299).
+ * Outputs sized n_faces / 3 n_faces / n_faces (reference face order); may be NULL to keep on device. */
+int icsb200_calc_flux(icsb200_ctx* ctx, double* phi, double* phiUp, double* phiEp);
+/* residualsUpdate.H:1-83 — sources R*V of the three equations: rhoR[N], rhoUR[3N], rhoER[N] (may be NULL) */
+int icsb200_residual(icsb200_ctx* ctx, double* rhoR, double* rhoUR, double* rhoER);
+/* setCoAndDeltaT.H:1-173 (SER + local pseudo time step); outputs rPseudoDeltaT[N], pseudoCoField[N] (may be NULL) */
+int icsb200_pseudo_dt(icsb200_ctx* ctx, double* rPseudoDeltaT, double* pseudoCo);
+/* convectiveFluxScheme::createConvectiveJacobian (convectiveFluxScheme.C:537-546) [+ viscousFluxScheme::
+ * createViscousJacobian LF branch (viscousFluxScheme.C:220-246) when mu > 0] into device block storage.
+ * ddtCoeff as outerLoop.H:61-64 is computed internally from the current rPseudoDeltaT. */
+int icsb200_assemble(icsb200_ctx* ctx);
+/* read back one LDU sub-block of the coupledMatrix (coupledMatrix.H:399-421) in the reference layout.
+ * block: 0 dSByS(0,0) 1 dSByS(0,1) 2 dSByS(1,0) 3 dSByS(1,1) 4 dSByV(0,0) 5 dSByV(1,0) 6 dVByS(0,0)
+ * 7 dVByS(0,1) 8 dVByV(0,0).  diag[nc*N], upper[nc*F], lower[nc*F] with nc = 1, 3 or 9; NULL skips. */
+int icsb200_matrix_get_ldu(icsb200_ctx* ctx, int block, double* diag, double* upper, double* lower);
+/* accept a HOST-assembled coupledMatrix (solver-only drop-in); NULL upper/lower = no off-diagonal */
+int icsb200_matrix_set_ldu(icsb200_ctx* ctx, int block, const double* diag, const double* upper, const double* lower);
+/* sources of the three equations (dSByS(0,0), dVByV(0,0), dSByS(1,1) .source(); residualsUpdate.H:81-83) */
+int icsb200_source_set(icsb200_ctx* ctx, const double* sRho, const double* sRhoU, const double* sRhoE);
+/* coupledMatrix::matrixMul (coupledMatrix.C:66-123): y = A x for x = (rho[N], rhoU[3N], rhoE[N]) */
+int icsb200_matrix_mul(icsb200_ctx* ctx, const double* xRho, const double* xRhoU, const double* xRhoE, double* yRho,
+                       double* yRhoU, double* yRhoE);
+/* coupledMatrix::preconditioner::precondition in place (coupledMatrix.H:363-367; lusgs.C:220-382, Jacobi.C:55-132) */
+int icsb200_precondition(icsb200_ctx* ctx, int preconditioner, double* xRho, double* xRhoU, double* xRhoE);
+/* coupledMatrix::solveForIncr -> gmres::solveDelta 6-arg (coupledMatrix.C:297-385, gmres.C:772-1110).
+ * W = current conserved state on device; outputs the increment (may be NULL to keep on device). */
+int icsb200_solve_delta(icsb200_ctx* ctx, const icsb200_solver_controls* c, double* dRho, double* dRhoU, double* dRhoE,
+                        icsb200_residuals* res);
+/* boundLocalTimeStep.H:1-98 + updateFields.H:1-104 */
+int icsb200_update_fields(icsb200_ctx* ctx);
+
+/* ---- the hot path, fused: one outer pseudo-time iteration of dbnsFoam (outerLoop.H:51-99 + updateFields.H) -- */
+/* device-resident: flux -> residual -> pseudo dt -> Jacobian -> GMRES/LU-SGS -> update */
+int icsb200_iterate_dev(icsb200_ctx* ctx, const icsb200_solver_controls* c, icsb200_residuals* res);
+/* same through host buffers: uploads p,U,T (6N doubles), iterates once, downloads p,U,T — the call an
+ * OpenFOAM adapter makes when fields live on the host */
+int icsb200_iterate_host(icsb200_ctx* ctx, const icsb200_solver_controls* c, double* p, double* U, double* T,
+                         icsb200_residuals* res);
+
+/* ---- introspection ------------------------------------------------------------------------- */
+/* number of kernels this library launched since create (bench.py "gpu_launches") */
+long long icsb200_launch_count(icsb200_ctx* ctx);
+/* per-kernel-class device time in ms accumulated since the last reset (CUDA events on the compute stream).
+ * names: NUL-separated list written to names_buf; returns the number of classes */
+int icsb200_timers_get(icsb200_ctx* ctx, char* names_buf, int names_len, double* ms, long long* calls, int max_classes);
+int icsb200_timers_reset(icsb200_ctx* ctx, int enable);
+/* LU-SGS level schedule statistics: n_levels_fwd, n_levels_rev, max_width, n_positions */
+int icsb200_schedule_info(icsb200_ctx* ctx, int out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

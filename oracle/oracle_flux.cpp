@@ -1,0 +1,830 @@
+// oracle_flux.cpp — convective flux schemes, residual, pseudo time step, Jacobian assembly, field update.
+// TEST INFRASTRUCTURE ONLY (see oracle.hpp).  PARITY UNPINNED.
+//
+// Follows, expression by expression (same operand order, no FMA contraction — build with -ffp-contract=off):
+//   hllcFluxScheme.C:70-240, roeFluxScheme.C:41-241 + 276-409, ausmPlusUpFluxScheme.C:73-299,
+//   cellFaceFunctions.H:490-660, residualsUpdate.H:1-83, setCoAndDeltaT.H:1-173, outerLoop.H:61-64,
+//   dualTimeDdtScheme.C:111-126, convectiveFluxScheme.C:47-120 + 219-546, blockFvMatrix.C:211-326,
+//   viscousFluxScheme.C:220-246, blockFvOperatorsTemplates.C:499-557, updateFields.H:1-104,
+//   boundLocalTimeStep.H:1-98.
+// The reference evaluates whole-field expressions; this file evaluates the same expressions face by face.
+#include "oracle_internal.hpp"
+
+namespace orc {
+
+namespace {
+
+struct V3 { double x, y, z; };
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline V3 operator*(V3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator/(V3 a, double s) { return {a.x / s, a.y / s, a.z / s}; }
+inline double operator&(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 operator^(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline double magSqr(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+struct T9 { double v[9]; };  // xx xy xz yx yy yz zx zy zz
+inline T9 outer(V3 a, V3 b) { return {{a.x * b.x, a.x * b.y, a.x * b.z, a.y * b.x, a.y * b.y, a.y * b.z, a.z * b.x, a.z * b.y, a.z * b.z}}; }
+inline T9 operator*(T9 a, double s) { T9 r; for (int i = 0; i < 9; i++) r.v[i] = a.v[i] * s; return r; }
+inline T9 operator*(double s, T9 a) { T9 r; for (int i = 0; i < 9; i++) r.v[i] = s * a.v[i]; return r; }
+inline T9 operator+(T9 a, T9 b) { T9 r; for (int i = 0; i < 9; i++) r.v[i] = a.v[i] + b.v[i]; return r; }
+inline T9 operator-(T9 a, T9 b) { T9 r; for (int i = 0; i < 9; i++) r.v[i] = a.v[i] - b.v[i]; return r; }
+inline V3 operator&(T9 t, V3 v) { return {t.v[0] * v.x + t.v[1] * v.y + t.v[2] * v.z, t.v[3] * v.x + t.v[4] * v.y + t.v[5] * v.z, t.v[6] * v.x + t.v[7] * v.y + t.v[8] * v.z}; }
+inline V3 operator&(V3 v, T9 t) { return {v.x * t.v[0] + v.y * t.v[3] + v.z * t.v[6], v.x * t.v[1] + v.y * t.v[4] + v.z * t.v[7], v.x * t.v[2] + v.y * t.v[5] + v.z * t.v[8]}; }
+inline T9 operator&(T9 a, T9 b)
+{
+    T9 r;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) r.v[3 * i + j] = a.v[3 * i] * b.v[j] + a.v[3 * i + 1] * b.v[3 + j] + a.v[3 * i + 2] * b.v[6 + j];
+    return r;
+}
+const T9 I9 = {{1, 0, 0, 0, 1, 0, 0, 0, 1}};
+
+// reconstructed left/right face states + geometry of one face
+struct FaceLR {
+    double rho_l, rho_r, p_l, p_r, c_l, c_r, E_l, E_r, H_l, H_r;
+    V3 U_l, U_r;
+};
+
+// derived vol fields (cells + boundary slots) the schemes reconstruct
+struct Derived {
+    vecd Ux, Uy, Uz, c, E, H;
+};
+
+void derivedFields(Ctx& c, Derived& d, int cKind /*0: max(sqrt(gamma/psi),VSMALL)  1: sqrt(gamma/psi)  2: critical (AUSM)*/)
+{
+    const Mesh& m = c.m;
+    size_t n = (size_t)m.N + m.NB;
+    d.Ux.resize(n); d.Uy.resize(n); d.Uz.resize(n); d.c.resize(n); d.E.resize(n); d.H.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        d.Ux[i] = c.U[3 * i]; d.Uy[i] = c.U[3 * i + 1]; d.Uz[i] = c.U[3 * i + 2];
+        double he = c.Cv * c.T[i];                                            // thermo.he(p, T)
+        d.E[i] = he + 0.5 * (d.Ux[i] * d.Ux[i] + d.Uy[i] * d.Uy[i] + d.Uz[i] * d.Uz[i]);
+        d.H[i] = std::max(d.E[i], SMALL) + std::max(c.p[i] / c.rho[i], SMALL);
+        if (cKind == 2) d.c[i] = std::sqrt(2.0 * (c.gamma - 1.0) / (c.gamma + 1.0) * d.H[i]);
+        else {
+            d.c[i] = std::sqrt(c.gamma / c.psi[i]);
+            if (cKind == 0) d.c[i] = std::max(d.c[i], VSMALL);
+        }
+    }
+    // empty-patch slots hold zeros from initialisation; keep them finite
+    for (auto& p : m.patches)
+        if (m.empty(p))
+            for (int f = p.start; f < p.start + p.size; f++) { size_t s = m.N + f - m.F; d.c[s] = d.E[s] = d.H[s] = 0; }
+}
+
+struct Recon {
+    vecd rho_l, rho_r, p_l, p_r, Ux_l, Ux_r, Uy_l, Uy_r, Uz_l, Uz_r, c_l, c_r, E_l, E_r, H_l, H_r;
+};
+
+void reconstructAll(Ctx& c, const Derived& d, Recon& r, bool needC)
+{
+    interpolateLimitedLR(c, c.rho, c.sch.limiter_rho, r.rho_l, r.rho_r);
+    interpolateLimitedLR(c, c.p, c.sch.limiter_rho, r.p_l, r.p_r);
+    interpolateLimitedLR(c, d.Ux, c.sch.limiter_U, r.Ux_l, r.Ux_r);
+    interpolateLimitedLR(c, d.Uy, c.sch.limiter_U, r.Uy_l, r.Uy_r);
+    interpolateLimitedLR(c, d.Uz, c.sch.limiter_U, r.Uz_l, r.Uz_r);
+    if (needC) interpolateLimitedLR(c, d.c, c.sch.limiter_T, r.c_l, r.c_r);
+    interpolateLimitedLR(c, d.E, c.sch.limiter_T, r.E_l, r.E_r);
+    interpolateLimitedLR(c, d.H, c.sch.limiter_T, r.H_l, r.H_r);
+}
+
+inline bool faceActive(const Mesh& m, int f, const std::vector<char>& emptyFace) { return f < m.F || !emptyFace[f - m.F]; }
+
+std::vector<char> emptyMask(const Mesh& m)
+{
+    std::vector<char> e(m.NB, 0);
+    for (auto& p : m.patches)
+        if (m.empty(p)) for (int f = p.start; f < p.start + p.size; f++) e[f - m.F] = 1;
+    return e;
+}
+
+// ---------------------------------------------------------------------------------------------- HLLC
+void fluxHLLC(const Ctx& c, const FaceLR& s, V3 Sf, double magSf, double mrf, double& phi, V3& phiUp, double& phiEp)
+{
+    V3 n = Sf / magSf;
+    double coefR = std::sqrt(std::max(VSMALL, s.rho_r) / std::max(VSMALL, s.rho_l));
+    V3 uAvg = (coefR * s.U_r + s.U_l) / (coefR + 1.0);
+    double HAvg = (coefR * s.H_r + s.H_l) / (coefR + 1.0);
+    double gammaf = c.gamma;  // fvc::interpolate(gamma) of a uniform field
+    double cAvg = std::sqrt(std::fabs((gammaf - 1.0) * (HAvg - 0.5 * magSqr(uAvg))));
+    double uMag_l = s.U_l & n, uMag_r = s.U_r & n, uMagAvg = uAvg & n;
+    uMagAvg -= mrf; uMag_l -= mrf; uMag_r -= mrf;
+    double Sl = std::min(uMag_l - s.c_l, uMagAvg - cAvg);
+    double Sr = std::max(uMag_r + s.c_r, uMagAvg + cAvg);
+    double Sm = (s.rho_r * uMag_r * (Sr - uMag_r) - s.rho_l * uMag_l * (Sl - uMag_l) + s.p_l - s.p_r) /
+                (s.rho_r * (Sr - uMag_r) - s.rho_l * (Sl - uMag_l));
+    double coefSl = pos0(Sl), coefSr = neg(Sr), coefSm = pos0(Sm);
+    double coefSlm = (1.0 - coefSl) * coefSm;
+    double coefSmr = (1.0 - coefSm) * (1.0 - coefSr);
+    double fluxRhoStar_l = Sm / (Sl - Sm) * ((Sl - uMag_l) * s.rho_l);
+    double fluxRhoStar_r = Sm / (Sr - Sm) * ((Sr - uMag_r) * s.rho_r);
+    phi = (coefSl * s.rho_l * uMag_l + coefSlm * fluxRhoStar_l + coefSmr * fluxRhoStar_r + coefSr * s.rho_r * uMag_r) * magSf;
+    double pStar_l = s.rho_l * (uMag_l - Sl) * (uMag_l - Sm) + s.p_l;
+    double pStar_r = s.rho_r * (uMag_r - Sr) * (uMag_r - Sm) + s.p_r;
+    V3 rhoUStar_l = 1.0 / (Sl - Sm) * ((Sl - uMag_l) * s.rho_l * s.U_l + (pStar_l - s.p_l) * n);
+    V3 rhoUStar_r = 1.0 / (Sr - Sm) * ((Sr - uMag_r) * s.rho_r * s.U_r + (pStar_r - s.p_r) * n);
+    V3 fluxRhoUStar_l = Sm * rhoUStar_l + pStar_l * n;
+    V3 fluxRhoUStar_r = Sm * rhoUStar_r + pStar_r * n;
+    phiUp = (coefSl * (s.rho_l * uMag_l * s.U_l + s.p_l * n) + coefSlm * fluxRhoUStar_l + coefSmr * fluxRhoUStar_r +
+             coefSr * (s.rho_r * uMag_r * s.U_r + s.p_r * n)) * magSf;
+    double rhoEStar_l = 1.0 / (Sl - Sm) * ((Sl - uMag_l) * (s.rho_l * s.E_l) - s.p_l * uMag_l + pStar_l * Sm);
+    double rhoEStar_r = 1.0 / (Sr - Sm) * ((Sr - uMag_r) * (s.rho_r * s.E_r) - s.p_r * uMag_r + pStar_r * Sm);
+    double fluxRhoEStar_l = Sm * (rhoEStar_l + pStar_l) + pStar_l * mrf;
+    double fluxRhoEStar_r = Sm * (rhoEStar_r + pStar_r) + pStar_r * mrf;
+    phiEp = (coefSl * s.rho_l * s.H_l * uMag_l + coefSlm * fluxRhoEStar_l + coefSmr * fluxRhoEStar_r +
+             coefSr * s.rho_r * s.H_r * uMag_r) * magSf;
+}
+
+// ---------------------------------------------------------------------------------------------- ROE
+void fluxROE(const Ctx& c, const FaceLR& s, V3 Sf, double magSf, double mrf, double& phi, V3& phiUp, double& phiEp)
+{
+    V3 n = Sf / magSf;
+    double coefR = std::sqrt(std::max(VSMALL, s.rho_r) / std::max(VSMALL, s.rho_l));
+    double RoeDensity = coefR * s.rho_l;
+    V3 RoeVelocity = (coefR * s.U_r + s.U_l) / (coefR + 1.0);
+    double RoeEnthalpy = (coefR * s.H_r + s.H_l) / (coefR + 1.0);
+    double gammaInterp = c.gamma;
+    double RoeSoundSpeed = std::sqrt(std::fabs((gammaInterp - 1.0) * (RoeEnthalpy - 0.5 * magSqr(RoeVelocity))));
+    double uMag_l = s.U_l & n, uMag_r = s.U_r & n;
+    double uProjRoe = RoeVelocity & n;
+    V3 rhoU_l = s.rho_l * s.U_l, rhoU_r = s.rho_r * s.U_r;
+    double rhoE_l = s.rho_l * s.E_l, rhoE_r = s.rho_r * s.E_r;
+    uProjRoe -= mrf;
+    // getRoeDissipation (roeFluxScheme.C:41-241)
+    double a1 = gammaInterp - 1;
+    double theta = 0.5 * a1 * magSqr(RoeVelocity);
+    double c2 = sqr(RoeSoundSpeed);
+    double a2 = 1 / (RoeDensity * RoeSoundSpeed * std::sqrt(2.0));
+    double a3 = RoeDensity / (RoeSoundSpeed * std::sqrt(2.0));
+    double a4 = (theta + c2) / a1;
+    double a5 = 1 - theta / c2;
+    double a6 = theta / a1;
+    V3 invP11 = (n * a5) - (RoeVelocity ^ n) / RoeDensity;
+    T9 invP12 = outer(a1 / c2 * n, RoeVelocity);
+    invP12.v[1] += n.z / RoeDensity;
+    invP12.v[2] -= n.y / RoeDensity;
+    invP12.v[3] -= n.z / RoeDensity;
+    invP12.v[5] += n.x / RoeDensity;
+    invP12.v[6] += n.y / RoeDensity;
+    invP12.v[7] -= n.x / RoeDensity;
+    V3 invP13 = -a1 / c2 * n;
+    double invP21 = a2 * (theta - RoeSoundSpeed * uProjRoe);
+    V3 invP22 = -a2 * (a1 * RoeVelocity - RoeSoundSpeed * n);
+    double invP23 = a1 * a2;
+    double invP31 = a2 * (theta + RoeSoundSpeed * uProjRoe);
+    V3 invP32 = -a2 * (a1 * RoeVelocity + RoeSoundSpeed * n);
+    double invP33 = a1 * a2;
+    double Lambda1 = std::fabs(uProjRoe);
+    double Lambda2 = std::fabs(uProjRoe + RoeSoundSpeed);
+    double Lambda3 = std::fabs(uProjRoe - RoeSoundSpeed);
+    double epsilon = c.sch.entropy_fix_coeff * std::max(Lambda2, Lambda3);
+    if (Lambda1 < epsilon) Lambda1 = (sqr(Lambda1) + sqr(epsilon)) / (2.0 * epsilon);
+    if (Lambda2 < epsilon) Lambda2 = (sqr(Lambda2) + sqr(epsilon)) / (2.0 * epsilon);
+    if (Lambda3 < epsilon) Lambda3 = (sqr(Lambda3) + sqr(epsilon)) / (2.0 * epsilon);
+    V3 P11 = n;
+    double P12 = a3, P13 = a3;
+    T9 P21 = outer(RoeVelocity, n);
+    P21.v[1] -= n.z * RoeDensity;
+    P21.v[2] += n.y * RoeDensity;
+    P21.v[3] += n.z * RoeDensity;
+    P21.v[5] -= n.x * RoeDensity;
+    P21.v[6] -= n.y * RoeDensity;
+    P21.v[7] += n.x * RoeDensity;
+    V3 P22 = a3 * (RoeVelocity + RoeSoundSpeed * n);
+    V3 P23 = a3 * (RoeVelocity - RoeSoundSpeed * n);
+    V3 P31 = n * a6 + RoeDensity * (RoeVelocity ^ n);
+    double P32 = a3 * (a4 + RoeSoundSpeed * uProjRoe);
+    double P33 = a3 * (a4 - RoeSoundSpeed * uProjRoe);
+    double dissContByRho = ((P11 * Lambda1) & invP11) + (Lambda2 * P12 * invP21) + (Lambda3 * P13 * invP31);
+    V3 dissContByRhoU = ((P11 * Lambda1) & invP12) + (Lambda2 * P12 * invP22) + (Lambda3 * P13 * invP32);
+    double dissContByRhoE = ((P11 * Lambda1) & invP13) + (Lambda2 * P12 * invP23) + (Lambda3 * P13 * invP33);
+    V3 dissMomByRho = ((P21 * Lambda1) & invP11) + (Lambda2 * P22 * invP21) + (Lambda3 * P23 * invP31);
+    T9 dissMomByRhoU = ((P21 * Lambda1) & invP12) + outer(Lambda2 * P22, invP22) + outer(Lambda3 * P23, invP32);
+    V3 dissMomByRhoE = ((P21 * Lambda1) & invP13) + (Lambda2 * P22 * invP23) + (Lambda3 * P23 * invP33);
+    double dissEnergyByRho = ((P31 * Lambda1) & invP11) + (Lambda2 * P32 * invP21) + (Lambda3 * P33 * invP31);
+    V3 dissEnergyByRhoU = ((P31 * Lambda1) & invP12) + (Lambda2 * P32 * invP22) + (Lambda3 * P33 * invP32);
+    double dissEnergyByRhoE = ((P31 * Lambda1) & invP13) + (Lambda2 * P32 * invP23) + (Lambda3 * P33 * invP33);
+    // roeFluxScheme.C:376-408
+    double diffRho = s.rho_r - s.rho_l;
+    V3 diffRhoU = rhoU_r - rhoU_l;
+    double diffRhoE = rhoE_r - rhoE_l;
+    phi = -0.5 * magSf * (dissContByRho * diffRho + (dissContByRhoU & diffRhoU) + dissContByRhoE * diffRhoE);
+    phiUp = (-0.5 * magSf) * (dissMomByRho * diffRho + (dissMomByRhoU & diffRhoU) + dissMomByRhoE * diffRhoE);
+    phiEp = -0.5 * magSf * (dissEnergyByRho * diffRho + (dissEnergyByRhoU & diffRhoU) + dissEnergyByRhoE * diffRhoE);
+    double rhoUNorm_l = s.rho_l * uMag_l, rhoUNorm_r = s.rho_r * uMag_r;
+    phi += 0.5 * magSf * (rhoUNorm_l + rhoUNorm_r);
+    phiUp = phiUp + (0.5 * magSf) * (rhoUNorm_l * s.U_l + rhoUNorm_r * s.U_r + n * (s.p_l + s.p_r));
+    phiEp += 0.5 * magSf * (rhoUNorm_l * s.H_l + rhoUNorm_r * s.H_r);
+    phi -= 0.5 * magSf * mrf * (s.rho_l + s.rho_r);
+    phiUp = phiUp - (0.5 * magSf * mrf) * (rhoU_l + rhoU_r);
+    phiEp -= 0.5 * magSf * mrf * (rhoE_l + rhoE_r);
+}
+
+// ---------------------------------------------------------------------------------------------- AUSM+up
+void fluxAUSM(const Ctx& c, const FaceLR& s, V3 Sf, double magSf, double mrf, double& phi, V3& phiUp, double& phiEp)
+{
+    double phi_L = s.U_l & Sf, phi_R = s.U_r & Sf;
+    double un_L = phi_L / magSf, un_R = phi_R / magSf;
+    un_L -= mrf; un_R -= mrf;
+    double c_L = sqr(s.c_l) / std::max(s.c_l, un_L);
+    double c_R = sqr(s.c_r) / std::max(s.c_r, -un_R);
+    double c_face = std::min(c_L, c_R);
+    double Mach_L = un_L / c_face;
+    double Mach_plus_L, p_plus_L;
+    if (std::fabs(Mach_L) < 1.0) {
+        double ML2p = 0.25 * sqr(Mach_L + 1), ML2m = -0.25 * sqr(Mach_L - 1);
+        Mach_plus_L = ML2p * (1 - 2 * ML2m);
+        p_plus_L = ML2p * (2 - Mach_L - 3 * Mach_L * ML2m);
+    } else {
+        Mach_plus_L = std::max(Mach_L, 0.0);
+        p_plus_L = (Mach_L > 0 ? 1.0 : 0.0);
+    }
+    double Mach_R = un_R / c_face;
+    double Mach_minus_R, p_minus_R;
+    if (std::fabs(Mach_R) < 1.0) {
+        double MR2m = -0.25 * sqr(Mach_R - 1), MR2p = 0.25 * sqr(Mach_R + 1);
+        Mach_minus_R = MR2m * (1 + 2 * MR2p);
+        p_minus_R = MR2m * (-2 - Mach_R + 3 * Mach_R * MR2p);
+    } else {
+        Mach_minus_R = std::min(Mach_R, 0.0);
+        p_minus_R = (Mach_R < 0 ? 1.0 : 0.0);
+    }
+    double Mach_1_2 = Mach_plus_L + Mach_minus_R;
+    double p_1_2 = p_plus_L * s.p_l + p_minus_R * s.p_r;
+    double M_mean = 0.5 * (sqr(un_L) + sqr(un_R)) / sqr(c_face);
+    double MDiff = -0.25 * std::max((1.0 - M_mean), 0.0) * (s.p_r - s.p_l) / (0.5 * (s.rho_l + s.rho_r) * sqr(c_face));
+    if ((Mach_1_2 > 0.0 && Mach_1_2 + MDiff <= 0.0) || (Mach_1_2 < 0.0 && Mach_1_2 + MDiff >= 0.0)) Mach_1_2 += 0.2 * MDiff;
+    else Mach_1_2 += MDiff;
+    if (c.sch.low_mach_ausm) {
+        double pDiff = -0.25 * p_plus_L * p_minus_R * (s.rho_l + s.rho_r) * c_face * (un_R - un_L);
+        p_1_2 += pDiff;
+    }
+    bool left = Mach_1_2 >= 0;
+    V3 U_f = left ? s.U_l : s.U_r;
+    double rhoa_LR = Mach_1_2 * c_face * (left ? s.rho_l : s.rho_r);
+    V3 rhoaU_LR = rhoa_LR * U_f;
+    double rhoah_LR = rhoa_LR * (left ? s.H_l : s.H_r);
+    phi = rhoa_LR * magSf;
+    phiUp = rhoaU_LR * magSf + p_1_2 * Sf;
+    phiEp = rhoah_LR * magSf + p_1_2 * mrf * magSf;
+}
+
+inline FaceLR gatherLR(const Recon& r, int f, bool needC)
+{
+    FaceLR s;
+    s.rho_l = r.rho_l[f]; s.rho_r = r.rho_r[f]; s.p_l = r.p_l[f]; s.p_r = r.p_r[f];
+    s.U_l = {r.Ux_l[f], r.Uy_l[f], r.Uz_l[f]}; s.U_r = {r.Ux_r[f], r.Uy_r[f], r.Uz_r[f]};
+    s.c_l = needC ? r.c_l[f] : 0; s.c_r = needC ? r.c_r[f] : 0;
+    s.E_l = r.E_l[f]; s.E_r = r.E_r[f]; s.H_l = r.H_l[f]; s.H_r = r.H_r[f];
+    return s;
+}
+
+}  // namespace
+
+// convectiveFluxScheme::calcFlux
+void calcFlux(Ctx& c)
+{
+    const Mesh& m = c.m;
+    const int scheme = c.sch.flux_scheme;
+    Derived d;
+    derivedFields(c, d, scheme == ICSB200_FLUX_AUSMPLUSUP ? 2 : 0);
+    Recon r;
+    const bool needC = scheme != ICSB200_FLUX_ROE;
+    reconstructAll(c, d, r, needC);
+    auto em = emptyMask(m);
+    c.phi.assign(m.FT, 0.0); c.phiUp.assign(3 * (size_t)m.FT, 0.0); c.phiEp.assign(m.FT, 0.0);
+    for (int f = 0; f < m.FT; f++) {
+        if (!faceActive(m, f, em)) continue;
+        FaceLR s = gatherLR(r, f, needC);
+        V3 Sf = {m.Sf[3 * f], m.Sf[3 * f + 1], m.Sf[3 * f + 2]};
+        double phi, phiEp;
+        V3 phiUp;
+        const double mrf = 0.0;  // MRFFaceVelocity: zero in every shipped case (out of scope)
+        if (scheme == ICSB200_FLUX_HLLC) fluxHLLC(c, s, Sf, m.magSf[f], mrf, phi, phiUp, phiEp);
+        else if (scheme == ICSB200_FLUX_ROE) fluxROE(c, s, Sf, m.magSf[f], mrf, phi, phiUp, phiEp);
+        else fluxAUSM(c, s, Sf, m.magSf[f], mrf, phi, phiUp, phiEp);
+        c.phi[f] = phi; c.phiEp[f] = phiEp;
+        c.phiUp[3 * (size_t)f] = phiUp.x; c.phiUp[3 * (size_t)f + 1] = phiUp.y; c.phiUp[3 * (size_t)f + 2] = phiUp.z;
+    }
+    c.phiValid = true;
+}
+
+// fvm::ddt(vf) with 'dualTime rPseudoDeltaT <inner>' (dualTimeDdtScheme.C:111-126): scalar diag, source with nc comps
+static void fvmDdt(const Ctx& c, const vecd& vf, const vecd& vf0, const vecd& vf00, int nc, vecd& diag, vecd& source)
+{
+    const Mesh& m = c.m;
+    diag.assign(m.N, 0.0);
+    source.assign((size_t)nc * m.N, 0.0);
+    if (c.sch.ddt_scheme == ICSB200_DDT_EULER) {
+        double rDeltaT = 1.0 / c.sch.delta_t;
+        for (int i = 0; i < m.N; i++) {
+            diag[i] = rDeltaT * m.V[i];
+            for (int d = 0; d < nc; d++) source[(size_t)nc * i + d] = rDeltaT * vf0[(size_t)nc * i + d] * m.V[i];
+        }
+    } else if (c.sch.ddt_scheme == ICSB200_DDT_BACKWARD) {
+        double deltaT = c.sch.delta_t, rDeltaT = 1.0 / deltaT;
+        double deltaT0 = (c.timeIndex < 2) ? GREAT : deltaT;  // backwardDdtScheme::deltaT0_(vf)
+        double coefft = 1 + deltaT / (deltaT + deltaT0);
+        double coefft00 = deltaT * deltaT / (deltaT0 * (deltaT + deltaT0));
+        double coefft0 = coefft + coefft00;
+        for (int i = 0; i < m.N; i++) {
+            diag[i] = (coefft * rDeltaT) * m.V[i];
+            for (int d = 0; d < nc; d++)
+                source[(size_t)nc * i + d] = rDeltaT * m.V[i] * (coefft0 * vf0[(size_t)nc * i + d] - coefft00 * vf00[(size_t)nc * i + d]);
+        }
+    }
+    for (int i = 0; i < m.N; i++) {
+        diag[i] += c.rPseudoDeltaT[i] * m.V[i];
+        for (int d = 0; d < nc; d++) source[(size_t)nc * i + d] += c.rPseudoDeltaT[i] * vf[(size_t)nc * i + d] * m.V[i];
+    }
+}
+
+// residualsUpdate.H (inviscid part; the viscous fvc:: terms are SURVEY §8f rank 1)
+void residualsUpdate(Ctx& c)
+{
+    const Mesh& m = c.m;
+    vecd rhoR, rhoUR, rhoER;
+    surfaceIntegrate(c, c.phi, 1, rhoR);
+    surfaceIntegrate(c, c.phiUp, 3, rhoUR);
+    surfaceIntegrate(c, c.phiEp, 1, rhoER);
+    for (auto& v : rhoR) v = -v;
+    for (auto& v : rhoUR) v = -v;
+    for (auto& v : rhoER) v = -v;
+    if (c.sch.ddt_scheme != ICSB200_DDT_STEADY) {
+        vecd dg, sr;
+        fvmDdt(c, c.rho, c.rho0, c.rho00, 1, dg, sr);
+        for (int i = 0; i < m.N; i++) rhoR[i] -= (dg[i] * c.rho[i] - sr[i]) / m.V[i];
+        fvmDdt(c, c.rhoU, c.rhoU0, c.rhoU00, 3, dg, sr);
+        for (int i = 0; i < m.N; i++)
+            for (int d = 0; d < 3; d++) rhoUR[3 * (size_t)i + d] -= (dg[i] * c.rhoU[3 * (size_t)i + d] - sr[3 * (size_t)i + d]) / m.V[i];
+        fvmDdt(c, c.rhoE, c.rhoE0, c.rhoE00, 1, dg, sr);
+        for (int i = 0; i < m.N; i++) rhoER[i] -= (dg[i] * c.rhoE[i] - sr[i]) / m.V[i];
+    }
+    c.srcRho.resize(m.N); c.srcRhoU.resize(3 * (size_t)m.N); c.srcRhoE.resize(m.N);
+    for (int i = 0; i < m.N; i++) {
+        c.srcRho[i] = rhoR[i] * m.V[i];
+        for (int d = 0; d < 3; d++) c.srcRhoU[3 * (size_t)i + d] = rhoUR[3 * (size_t)i + d] * m.V[i];
+        c.srcRhoE[i] = rhoER[i] * m.V[i];
+    }
+}
+
+// lambda = interpolate(sqrt(gamma/psi)) + mag((interpolate(U) & Sf/magSf) - MRFFaceVelocity)
+static void spectralRadius(Ctx& c, vecd& lambda)
+{
+    const Mesh& m = c.m;
+    size_t n = (size_t)m.N + m.NB;
+    vecd cc(n), comp(n), cf, uf[3];
+    for (size_t i = 0; i < n; i++) cc[i] = std::sqrt(c.gamma / c.psi[i]);
+    for (auto& p : m.patches) if (m.empty(p)) for (int f = p.start; f < p.start + p.size; f++) cc[m.N + f - m.F] = 0;
+    interpolateLinear(c, cc, cf);
+    for (int d = 0; d < 3; d++) {
+        for (size_t i = 0; i < n; i++) comp[i] = c.U[3 * i + d];
+        interpolateLinear(c, comp, uf[d]);
+    }
+    lambda.assign(m.FT, 0.0);
+    auto em = emptyMask(m);
+    for (int f = 0; f < m.FT; f++) {
+        if (!faceActive(m, f, em)) continue;
+        V3 nn = V3{m.Sf[3 * f], m.Sf[3 * f + 1], m.Sf[3 * f + 2]} / m.magSf[f];
+        V3 u = {uf[0][f], uf[1][f], uf[2][f]};
+        lambda[f] = cf[f] + std::fabs((u & nn) - 0.0);
+    }
+}
+
+// setCoAndDeltaT.H
+void setCoAndDeltaT(Ctx& c)
+{
+    const Mesh& m = c.m;
+    if (c.haveInitRes) {
+        if (!c.firstIter && c.havePrevRes) {
+            const icsb200_residuals &ir = c.initRes, &pr = c.prevRes;
+            double normInit = std::sqrt(sqr(ir.s_init[0]) + sqr(ir.s_init[1]) + (ir.v_init[0] * ir.v_init[0] + ir.v_init[1] * ir.v_init[1] + ir.v_init[2] * ir.v_init[2]));
+            double normPrev = std::sqrt(sqr(pr.s_init[0]) + sqr(pr.s_init[1]) + (pr.v_init[0] * pr.v_init[0] + pr.v_init[1] * pr.v_init[1] + pr.v_init[2] * pr.v_init[2]));
+            double coNumRatio = normPrev / normInit;
+            coNumRatio = std::max(std::min(coNumRatio, c.sch.pseudo_co_num_max_incr), c.sch.pseudo_co_num_min_decr);
+            if (c.sch.local_timestepping) {
+                for (auto& v : c.pseudoCoField) { v *= coNumRatio; v = std::max(std::min(v, c.sch.pseudo_co_num_max), c.sch.pseudo_co_num_min); }
+            } else {
+                c.pseudoCoNum *= coNumRatio;
+                c.pseudoCoNum = std::max(std::min(c.pseudoCoNum, c.sch.pseudo_co_num_max), c.sch.pseudo_co_num_min);
+            }
+        }
+        c.prevRes = c.initRes;
+        c.havePrevRes = true;
+    }
+    vecd lambda;
+    spectralRadius(c, lambda);
+    if (c.sch.local_timestepping) {
+        std::fill(c.rPseudoDeltaT.begin(), c.rPseudoDeltaT.end(), 0.0);
+        for (int f = 0; f < m.F; f++) {
+            double frdt = m.nonOrthDeltaCoeffs[f] * lambda[f];
+            int o = m.owner[f], n = m.neighbour[f];
+            c.rPseudoDeltaT[o] = std::max(c.rPseudoDeltaT[o], frdt);
+            c.rPseudoDeltaT[n] = std::max(c.rPseudoDeltaT[n], frdt);
+        }
+        for (auto& p : m.patches) {
+            if (m.coupled(p)) {
+                for (int f = p.start; f < p.start + p.size; f++) {
+                    int o = m.owner[f];
+                    c.rPseudoDeltaT[o] = std::max(c.rPseudoDeltaT[o], m.nonOrthDeltaCoeffs[f] * lambda[f]);
+                }
+            } else if (p.kind == ICSB200_WALL) {
+                for (int f = p.start; f < p.start + p.size; f++) {
+                    int o = m.owner[f];
+                    V3 nn = V3{m.Sf[3 * f], m.Sf[3 * f + 1], m.Sf[3 * f + 2]} / m.magSf[f];
+                    V3 u = {c.U[3 * (size_t)o], c.U[3 * (size_t)o + 1], c.U[3 * (size_t)o + 2]};
+                    double pLambda = 0.5 * m.nonOrthDeltaCoeffs[f] * (std::sqrt(c.gamma / c.psi[o]) + std::fabs((u & nn) - 0.0));
+                    c.rPseudoDeltaT[o] = std::max(c.rPseudoDeltaT[o], pLambda);
+                }
+            }
+        }
+        for (int i = 0; i < m.N; i++) c.rPseudoDeltaT[i] /= c.pseudoCoField[i];
+    } else {
+        double mx = -VGREAT;
+        auto em = emptyMask(m);
+        for (int f = 0; f < m.FT; f++) if (faceActive(m, f, em)) mx = std::max(mx, m.deltaCoeffs[f] * lambda[f]);
+        mx = c.comm->max(mx);
+        for (int i = 0; i < m.N; i++) c.rPseudoDeltaT[i] = mx / c.pseudoCoNum;
+    }
+}
+
+// outerLoop.H:61-64
+void computeDdtCoeff(Ctx& c)
+{
+    const Mesh& m = c.m;
+    vecd d1, d2, d3, s;
+    fvmDdt(c, c.rho, c.rho0, c.rho00, 1, d1, s);
+    fvmDdt(c, c.rhoU, c.rhoU0, c.rhoU00, 3, d2, s);
+    fvmDdt(c, c.rhoE, c.rhoE0, c.rhoE00, 1, d3, s);
+    c.ddtCoeff.resize(m.N);
+    for (int i = 0; i < m.N; i++) c.ddtCoeff[i] = std::max(std::max(d1[i], d2[i]), d3[i]) / m.V[i];
+}
+
+// ---------------------------------------------------------------------------------------------- Jacobian
+namespace {
+
+void blkInit(Blk& b, int nc, const Mesh& m)
+{
+    b.nc = nc; b.exists = true; b.hasOff = false; b.hasInt = false;
+    b.diag.assign((size_t)nc * m.N, 0.0);
+    b.upper.clear(); b.lower.clear(); b.intUpper.clear(); b.intLower.clear();
+    b.source.assign((size_t)(nc == 9 ? 3 : (nc == 3 ? 0 : 1)) * m.N, 0.0);
+}
+
+void ensureOff(Blk& b, const Mesh& m)
+{
+    if (!b.hasOff) { b.upper.assign((size_t)b.nc * m.F, 0.0); b.lower.assign((size_t)b.nc * m.F, 0.0); b.hasOff = true; }
+    if (!b.hasInt) { b.intUpper.assign((size_t)b.nc * m.NB, 0.0); b.intLower.assign((size_t)b.nc * m.NB, 0.0); b.hasInt = true; }
+}
+
+// blockFvMatrix::insertBlock (blockFvMatrix.C:211-268): left/right are [nc*FT] face fields
+void insertBlock(const Mesh& m, Blk& A, const vecd& left, const vecd& right)
+{
+    const int nc = A.nc;
+    vecd upp((size_t)nc * m.F), low((size_t)nc * m.F), diag((size_t)nc * m.N, 0.0);
+    for (int f = 0; f < m.F; f++)
+        for (int k = 0; k < nc; k++) {
+            upp[(size_t)nc * f + k] = 0.5 * m.magSf[f] * right[(size_t)nc * f + k];
+            low[(size_t)nc * f + k] = -0.5 * m.magSf[f] * left[(size_t)nc * f + k];
+        }
+    for (int f = 0; f < m.F; f++)  // negSumDiag
+        for (int k = 0; k < nc; k++) {
+            diag[(size_t)nc * m.owner[f] + k] -= low[(size_t)nc * f + k];
+            diag[(size_t)nc * m.neighbour[f] + k] -= upp[(size_t)nc * f + k];
+        }
+    vecd iu((size_t)nc * m.NB, 0.0), il((size_t)nc * m.NB, 0.0);
+    for (auto& p : m.patches) {
+        if (m.empty(p)) continue;
+        for (int f = p.start; f < p.start + p.size; f++)
+            for (int k = 0; k < nc; k++) {
+                iu[(size_t)nc * (f - m.F) + k] = 0.5 * m.magSf[f] * right[(size_t)nc * f + k];
+                il[(size_t)nc * (f - m.F) + k] = -0.5 * m.magSf[f] * left[(size_t)nc * f + k];
+            }
+        if (m.coupled(p))
+            for (int f = p.start; f < p.start + p.size; f++)
+                for (int k = 0; k < nc; k++) diag[(size_t)nc * m.owner[f] + k] -= il[(size_t)nc * (f - m.F) + k];
+    }
+    ensureOff(A, m);
+    for (size_t i = 0; i < diag.size(); i++) A.diag[i] += diag[i];
+    for (size_t i = 0; i < upp.size(); i++) { A.upper[i] += upp[i]; A.lower[i] += low[i]; }
+    for (size_t i = 0; i < iu.size(); i++) { A.intUpper[i] += iu[i]; A.intLower[i] += il[i]; }
+}
+
+// blockFvMatrix::insertDissipationBlock (blockFvMatrix.C:271-326) for a scalar face field times identity pattern
+// 'pattern' lists the coefficient slots that receive lambda (scalar: {0}; tensor: {0,4,8})
+void insertDissipationBlock(const Mesh& m, Blk& A, const vecd& diss, std::initializer_list<int> pattern)
+{
+    const int nc = A.nc;
+    vecd upp((size_t)nc * m.F, 0.0), low((size_t)nc * m.F, 0.0), diag((size_t)nc * m.N, 0.0);
+    for (int f = 0; f < m.F; f++)
+        for (int k : pattern) {
+            upp[(size_t)nc * f + k] = 0.5 * m.magSf[f] * diss[f];
+            low[(size_t)nc * f + k] = 0.5 * m.magSf[f] * diss[f];
+        }
+    for (int f = 0; f < m.F; f++)
+        for (int k : pattern) {
+            diag[(size_t)nc * m.owner[f] + k] -= low[(size_t)nc * f + k];
+            diag[(size_t)nc * m.neighbour[f] + k] -= upp[(size_t)nc * f + k];
+        }
+    vecd iu((size_t)nc * m.NB, 0.0), il((size_t)nc * m.NB, 0.0);
+    for (auto& p : m.patches) {
+        if (m.empty(p)) continue;
+        for (int f = p.start; f < p.start + p.size; f++)
+            for (int k : pattern) {
+                iu[(size_t)nc * (f - m.F) + k] = 0.5 * m.magSf[f] * diss[f];
+                il[(size_t)nc * (f - m.F) + k] = 0.5 * m.magSf[f] * diss[f];
+                diag[(size_t)nc * m.owner[f] + k] -= il[(size_t)nc * (f - m.F) + k];  // physical boundaries included
+            }
+    }
+    ensureOff(A, m);
+    for (size_t i = 0; i < diag.size(); i++) A.diag[i] -= diag[i];
+    for (size_t i = 0; i < upp.size(); i++) { A.upper[i] -= upp[i]; A.lower[i] -= low[i]; }
+    for (size_t i = 0; i < iu.size(); i++) { A.intUpper[i] -= iu[i]; A.intLower[i] -= il[i]; }
+}
+
+// fvj::laplacian(sf, geometricOneField) (blockFvOperatorsTemplates.C:499-557), then A -= stab [* I]
+void subtractLaplacianOne(const Mesh& m, Blk& A, const vecd& sf, std::initializer_list<int> pattern)
+{
+    const int nc = A.nc;
+    vecd sf2(m.FT, 0.0);
+    for (int f = 0; f < m.FT; f++) sf2[f] = sf[f] * m.magSf[f] * m.deltaCoeffs[f];
+    vecd diag(m.N, 0.0);
+    for (int f = 0; f < m.F; f++) { diag[m.owner[f]] -= sf2[f]; diag[m.neighbour[f]] -= sf2[f]; }
+    for (auto& p : m.patches)
+        if (m.coupled(p)) for (int f = p.start; f < p.start + p.size; f++) diag[m.owner[f]] -= sf2[f];
+    ensureOff(A, m);
+    for (int k : pattern) {
+        for (int i = 0; i < m.N; i++) A.diag[(size_t)nc * i + k] -= diag[i] * 1.0;
+        for (int f = 0; f < m.F; f++) { A.upper[(size_t)nc * f + k] -= sf2[f] * 1.0; A.lower[(size_t)nc * f + k] -= sf2[f] * 1.0; }
+        for (auto& p : m.patches) {
+            if (m.empty(p)) continue;
+            for (int f = p.start; f < p.start + p.size; f++) {
+                A.intUpper[(size_t)nc * (f - m.F) + k] -= sf2[f] * 1.0;
+                A.intLower[(size_t)nc * (f - m.F) + k] -= sf2[f] * 1.0;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// convectiveFluxScheme::createConvectiveJacobian + viscousFluxScheme::createViscousJacobian (LF branch)
+void createJacobian(Ctx& c)
+{
+    const Mesh& m = c.m;
+    // coupledMatrix eqSystem(mesh, 2, 1, true)  (outerLoop.H:53) — fresh every iteration
+    Blk& dContByRho = c.blk[0]; Blk& dContByRhoE = c.blk[1]; Blk& dEnergyByRho = c.blk[2]; Blk& dEnergyByRhoE = c.blk[3];
+    Blk& dContByRhoU = c.blk[4]; Blk& dEnergyByRhoU = c.blk[5]; Blk& dMomByRho = c.blk[6]; Blk& dMomByRhoE = c.blk[7];
+    Blk& dMomByRhoU = c.blk[8];
+    blkInit(dContByRho, 1, m); blkInit(dContByRhoE, 1, m); blkInit(dEnergyByRho, 1, m); blkInit(dEnergyByRhoE, 1, m);
+    blkInit(dContByRhoU, 3, m); blkInit(dEnergyByRhoU, 3, m); blkInit(dMomByRho, 3, m); blkInit(dMomByRhoE, 3, m);
+    blkInit(dMomByRhoU, 9, m);
+
+    // ---- addFluxTerms (convectiveFluxScheme.C:374-484)
+    Derived d;
+    derivedFields(c, d, 1);
+    vecd Ux_l, Ux_r, Uy_l, Uy_r, Uz_l, Uz_r, E_l, E_r;
+    interpolateLimitedLR(c, d.Ux, c.sch.limiter_U, Ux_l, Ux_r);
+    interpolateLimitedLR(c, d.Uy, c.sch.limiter_U, Uy_l, Uy_r);
+    interpolateLimitedLR(c, d.Uz, c.sch.limiter_U, Uz_l, Uz_r);
+    interpolateLimitedLR(c, d.E, c.sch.limiter_T, E_l, E_r);
+    const size_t FT = m.FT;
+    vecd nL(3 * FT, 0), momRho_l(3 * FT, 0), momRho_r(3 * FT, 0), momRhoU_l(9 * FT, 0), momRhoU_r(9 * FT, 0), momRhoE_l(3 * FT, 0),
+        momRhoE_r(3 * FT, 0), enRho_l(FT, 0), enRho_r(FT, 0), enRhoU_l(3 * FT, 0), enRhoU_r(3 * FT, 0), enRhoE_l(FT, 0), enRhoE_r(FT, 0);
+    auto em = emptyMask(m);
+    auto put3 = [](vecd& a, size_t f, V3 v) { a[3 * f] = v.x; a[3 * f + 1] = v.y; a[3 * f + 2] = v.z; };
+    for (size_t f = 0; f < FT; f++) {
+        if (!faceActive(m, (int)f, em)) continue;
+        double gamma_interp = c.gamma;
+        V3 U_l = {Ux_l[f], Uy_l[f], Uz_l[f]}, U_r = {Ux_r[f], Uy_r[f], Uz_r[f]};
+        double theta_l = 0.5 * (gamma_interp - 1) * magSqr(U_l), theta_r = 0.5 * (gamma_interp - 1) * magSqr(U_r);
+        double a1_l = gamma_interp * E_l[f] - theta_l, a1_r = gamma_interp * E_r[f] - theta_r;
+        double a2_l = gamma_interp - 1, a2_r = gamma_interp - 1;
+        V3 n = V3{m.Sf[3 * f], m.Sf[3 * f + 1], m.Sf[3 * f + 2]} / m.magSf[f];
+        double projU_l = U_l & n, projU_r = U_r & n;
+        put3(nL, f, n);
+        put3(momRho_l, f, n * theta_l - U_l * projU_l);
+        put3(momRho_r, f, n * theta_r - U_r * projU_r);
+        T9 tl = outer(U_l, n) - outer(a2_l * n, U_l) + projU_l * I9;
+        T9 tr = outer(U_r, n) - outer(a2_r * n, U_r) + projU_r * I9;
+        for (int k = 0; k < 9; k++) { momRhoU_l[9 * f + k] = tl.v[k]; momRhoU_r[9 * f + k] = tr.v[k]; }
+        put3(momRhoE_l, f, n * a2_l);
+        put3(momRhoE_r, f, n * a2_r);
+        enRho_l[f] = projU_l * (theta_l - a1_l);
+        enRho_r[f] = projU_r * (theta_r - a1_r);
+        put3(enRhoU_l, f, n * a1_l - a2_l * U_l * projU_l);
+        put3(enRhoU_r, f, n * a1_r - a2_r * U_r * projU_r);
+        enRhoE_l[f] = gamma_interp * projU_l;
+        enRhoE_r[f] = gamma_interp * projU_r;
+    }
+    insertBlock(m, dContByRhoU, nL, nL);
+    insertBlock(m, dMomByRho, momRho_l, momRho_r);
+    insertBlock(m, dMomByRhoU, momRhoU_l, momRhoU_r);
+    insertBlock(m, dMomByRhoE, momRhoE_l, momRhoE_r);
+    insertBlock(m, dEnergyByRho, enRho_l, enRho_r);
+    insertBlock(m, dEnergyByRhoU, enRhoU_l, enRhoU_r);
+    insertBlock(m, dEnergyByRhoE, enRhoE_l, enRhoE_r);
+    // (moving-mesh and MRF fvj::div terms are identically zero here: MRFFaceVelocity == 0, static mesh)
+
+    // ---- addDissipationJacobian (convectiveFluxScheme.C:487-534)
+    vecd lambdaConv;
+    spectralRadius(c, lambdaConv);
+    insertDissipationBlock(m, dContByRho, lambdaConv, {0});
+    insertDissipationBlock(m, dMomByRhoU, lambdaConv, {0, 4, 8});
+    insertDissipationBlock(m, dEnergyByRhoE, lambdaConv, {0});
+
+    // ---- addBoundaryTerms + boundaryJacobian (convectiveFluxScheme.C:47-120, 219-355)
+    for (size_t pi = 0; pi < m.patches.size(); pi++) {
+        auto& p = m.patches[pi];
+        if (m.coupled(p) || m.empty(p)) continue;
+        for (int f = p.start; f < p.start + p.size; f++) {
+            int s = m.N + f - m.F, iIntCell = m.owner[f];
+            const int bf = f - m.F;
+            double pVIC = c.vicP[bf], tVIC = c.vicT[bf];
+            V3 uVIC = {c.vicU[3 * (size_t)bf], c.vicU[3 * (size_t)bf + 1], c.vicU[3 * (size_t)bf + 2]};
+            V3 SfB = {m.Sf[3 * f], m.Sf[3 * f + 1], m.Sf[3 * f + 2]};
+            double rhoB = c.rho[s];
+            V3 UB = {c.U[3 * (size_t)s], c.U[3 * (size_t)s + 1], c.U[3 * (size_t)s + 2]};
+            double UrelBdotSf = UB & SfB;
+            UrelBdotSf -= 0.0 * m.magSf[f];
+            double pB = c.p[s], TB = c.T[s];
+            // rhoEn = rho*(he(p,T) + 0.5 magSqr(U)) evaluated on the boundary
+            double rhoEB = rhoB * (c.Cv * TB + 0.5 * magSqr(UB));
+            double cvB = c.Cv;
+            auto cm = [](V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; };
+            double dContFluxdp = rhoB / pB * UrelBdotSf * pVIC;
+            V3 dContFluxdU = rhoB * cm(SfB, uVIC);
+            double dContFluxdT = -rhoB / TB * UrelBdotSf * tVIC;
+            V3 dMomFluxdp = (rhoB / pB * UB * UrelBdotSf + SfB) * pVIC;
+            T9 dMomFluxdU = outer(rhoB * UB, cm(SfB, uVIC));
+            V3 dMomFluxdUDiag = rhoB * UrelBdotSf * uVIC;
+            V3 dMomFluxdT = -rhoB / TB * UB * UrelBdotSf * tVIC;
+            double dEnergyFluxdp = (rhoEB / pB * UrelBdotSf + (UB & SfB)) * pVIC;
+            V3 dEnergyFluxdU = cm(SfB, uVIC) * (rhoEB + pB) + rhoB * UrelBdotSf * cm(UB, uVIC);
+            double dEnergyFluxdT = UrelBdotSf * (rhoB * cvB - rhoEB / TB) * tVIC;
+            dMomFluxdU.v[0] = dMomFluxdU.v[0] + dMomFluxdUDiag.x;
+            dMomFluxdU.v[4] = dMomFluxdU.v[4] + dMomFluxdUDiag.y;
+            dMomFluxdU.v[8] = dMomFluxdU.v[8] + dMomFluxdUDiag.z;
+            // internal-cell derivatives of (p, U, T) w.r.t. the conserved variables
+            double rhoI = c.rho[iIntCell];
+            V3 UI = {c.U[3 * (size_t)iIntCell], c.U[3 * (size_t)iIntCell + 1], c.U[3 * (size_t)iIntCell + 2]};
+            double rhoEI = rhoI * (c.Cv * c.T[iIntCell] + 0.5 * magSqr(UI));
+            double gammaI = c.gamma, cvI = c.Cv;
+            double dPdRho = 0.5 * (gammaI - 1) * magSqr(UI);
+            V3 dUdRho = -1.0 * UI / rhoI;
+            double dTdRho = -1.0 / (cvI * rhoI) * (rhoEI / rhoI - magSqr(UI));
+            V3 dPdRhoU = -(gammaI - 1) * UI;
+            double dUdRhoU = 1.0 / rhoI * 1.0;  // sphericalTensor ii component
+            V3 dTdRhoU = -1.0 * UI / (cvI * rhoI);
+            double dPdRhoE = gammaI - 1;
+            V3 dUdRhoE = {0, 0, 0};
+            double dTdRhoE = 1.0 / (cvI * rhoI);
+            auto add3 = [](vecd& a, int i, V3 v) { a[3 * (size_t)i] += v.x; a[3 * (size_t)i + 1] += v.y; a[3 * (size_t)i + 2] += v.z; };
+            // vector & sphericalTensor = vector * ii ; tensor & sphericalTensor = tensor * ii
+            dContByRho.diag[iIntCell] += dContFluxdp * dPdRho;
+            dContByRho.diag[iIntCell] += dContFluxdU & dUdRho;
+            dContByRho.diag[iIntCell] += dContFluxdT * dTdRho;
+            add3(dContByRhoU.diag, iIntCell, dContFluxdp * dPdRhoU);
+            add3(dContByRhoU.diag, iIntCell, dContFluxdU * dUdRhoU);
+            add3(dContByRhoU.diag, iIntCell, dContFluxdT * dTdRhoU);
+            dContByRhoE.diag[iIntCell] += dContFluxdp * dPdRhoE;
+            dContByRhoE.diag[iIntCell] += dContFluxdU & dUdRhoE;
+            dContByRhoE.diag[iIntCell] += dContFluxdT * dTdRhoE;
+            add3(dMomByRho.diag, iIntCell, dMomFluxdp * dPdRho);
+            add3(dMomByRho.diag, iIntCell, dMomFluxdU & dUdRho);
+            add3(dMomByRho.diag, iIntCell, dMomFluxdT * dTdRho);
+            T9 t1 = outer(dMomFluxdp, dPdRhoU), t2 = dMomFluxdU * dUdRhoU, t3 = outer(dMomFluxdT, dTdRhoU);
+            for (int k = 0; k < 9; k++) dMomByRhoU.diag[9 * (size_t)iIntCell + k] += t1.v[k];
+            for (int k = 0; k < 9; k++) dMomByRhoU.diag[9 * (size_t)iIntCell + k] += t2.v[k];
+            for (int k = 0; k < 9; k++) dMomByRhoU.diag[9 * (size_t)iIntCell + k] += t3.v[k];
+            add3(dMomByRhoE.diag, iIntCell, dMomFluxdp * dPdRhoE);
+            add3(dMomByRhoE.diag, iIntCell, dMomFluxdU & dUdRhoE);
+            add3(dMomByRhoE.diag, iIntCell, dMomFluxdT * dTdRhoE);
+            dEnergyByRho.diag[iIntCell] += dEnergyFluxdp * dPdRho;
+            dEnergyByRho.diag[iIntCell] += dEnergyFluxdU & dUdRho;
+            dEnergyByRho.diag[iIntCell] += dEnergyFluxdT * dTdRho;
+            add3(dEnergyByRhoU.diag, iIntCell, dEnergyFluxdp * dPdRhoU);
+            add3(dEnergyByRhoU.diag, iIntCell, dEnergyFluxdU * dUdRhoU);
+            add3(dEnergyByRhoU.diag, iIntCell, dEnergyFluxdT * dTdRhoU);
+            dEnergyByRhoE.diag[iIntCell] += dEnergyFluxdp * dPdRhoE;
+            dEnergyByRhoE.diag[iIntCell] += dEnergyFluxdU & dUdRhoE;
+            dEnergyByRhoE.diag[iIntCell] += dEnergyFluxdT * dTdRhoE;
+        }
+    }
+
+    // ---- addTemporalTerms (convectiveFluxScheme.C:358-369)
+    for (int i = 0; i < m.N; i++) {
+        double diagCoeff = c.ddtCoeff[i] * m.V[i];
+        dContByRho.diag[i] += diagCoeff;
+        for (int k = 0; k < 9; k++) dMomByRhoU.diag[9 * (size_t)i + k] += diagCoeff * I9.v[k];
+        dEnergyByRhoE.diag[i] += diagCoeff;
+    }
+    // addMRFSource: MRFOmega == 0 (out of scope)
+
+    // ---- viscousFluxScheme::addFluxTerms, LaxFriedrichJacobian branch (viscousFluxScheme.C:220-246)
+    if (c.mu > 0) {
+        size_t n = (size_t)m.N + m.NB;
+        vecd muEff(n, c.mu), alphaEff(n, c.gamma * (c.mu / c.Pr)), muf, alf, rhof, half(m.FT, 0.0);
+        interpolateLinear(c, muEff, muf);
+        interpolateLinear(c, alphaEff, alf);
+        interpolateLinear(c, c.rho, rhof);
+        for (int f = 0; f < m.FT; f++) if (faceActive(m, f, em)) half[f] = 0.5 * ((muf[f] + alf[f]) / rhof[f]);
+        subtractLaplacianOne(m, dContByRho, half, {0});
+        subtractLaplacianOne(m, dMomByRhoU, half, {0, 4, 8});
+        subtractLaplacianOne(m, dEnergyByRhoE, half, {0});
+    }
+    // sources (residualsUpdate.H:81-83)
+    dContByRho.source = c.srcRho;
+    dMomByRhoU.source = c.srcRhoU;
+    dEnergyByRhoE.source = c.srcRhoE;
+    c.matrixSet = true;
+}
+
+// ---------------------------------------------------------------------------------------------- update
+// boundLocalTimeStep.H (executed before updateFields, i.e. on the not-yet-updated state — outerLoop.H:99)
+void boundLocalTimeStep(Ctx& c)
+{
+    if (!(c.sch.local_timestepping && c.sch.local_timestepping_bounding)) return;
+    const Mesh& m = c.m;
+    const double lb = c.sch.local_timestepping_lower_bound;
+    vecd rhoMin(m.N), eMin(m.N), eTemp(m.N), factor(m.N, 1.0);
+    std::vector<char> bad(m.N);
+    for (int i = 0; i < m.N; i++) {
+        rhoMin[i] = lb * c.rhoPrev[i];
+        V3 up = V3{c.rhoUPrev[3 * (size_t)i], c.rhoUPrev[3 * (size_t)i + 1], c.rhoUPrev[3 * (size_t)i + 2]} / c.rhoPrev[i];
+        eMin[i] = lb * (c.rhoEPrev[i] / c.rhoPrev[i] - 0.5 * magSqr(up));
+        V3 u = V3{c.rhoU[3 * (size_t)i], c.rhoU[3 * (size_t)i + 1], c.rhoU[3 * (size_t)i + 2]} / c.rho[i];
+        eTemp[i] = c.rhoE[i] / c.rho[i] - 0.5 * magSqr(u);
+        bad[i] = (c.rho[i] < rhoMin[i]) || (eTemp[i] < eMin[i]) || (eTemp[i] < SMALL);
+    }
+    for (int f = 0; f < m.F; f++) {
+        int own = m.owner[f], nei = m.neighbour[f];
+        if (bad[own]) { factor[own] = std::min(0.5, factor[own]); factor[nei] = std::min(0.75, factor[nei]); }
+        if (bad[nei]) { factor[nei] = std::min(0.5, factor[nei]); factor[own] = std::min(0.75, factor[own]); }
+    }
+    vecd badv((size_t)m.N + m.NB, 0.0);
+    for (int i = 0; i < m.N; i++) badv[i] = bad[i];
+    syncCoupled(c, badv, 1);
+    for (auto& p : m.patches)
+        if (m.coupled(p))
+            for (int f = p.start; f < p.start + p.size; f++) {
+                int o = m.owner[f];
+                if (bad[o]) factor[o] = std::min(0.5, factor[o]);
+                if (badv[m.N + f - m.F] != 0.0) factor[o] = std::min(0.75, factor[o]);
+            }
+    for (int i = 0; i < m.N; i++) c.pseudoCoField[i] *= factor[i];
+}
+
+// updateFields.H
+void updateFields(Ctx& c)
+{
+    const Mesh& m = c.m;
+    bool boundLow = false, boundHigh = false;
+    const double eBoundMin = c.Cv * c.sch.T_min, eBoundMax = c.Cv * c.sch.T_max;
+    for (int i = 0; i < m.N; i++) {
+        c.rho[i] += c.dRho[i];
+        for (int d = 0; d < 3; d++) c.rhoU[3 * (size_t)i + d] += c.dRhoU[3 * (size_t)i + d];
+        c.rhoE[i] += c.dRhoE[i];
+    }
+    // bound(rho, rhoMin): only acts when rho < rhoMin somewhere (rhoMin defaults to -GREAT)
+    if (c.sch.rho_min > -GREAT)
+        for (int i = 0; i < m.N; i++) c.rho[i] = std::max(c.rho[i], c.sch.rho_min);
+    for (int i = 0; i < m.N; i++) {
+        for (int d = 0; d < 3; d++) c.U[3 * (size_t)i + d] = c.rhoU[3 * (size_t)i + d] / c.rho[i];
+        const double* u = &c.U[3 * (size_t)i];
+        c.e[i] = c.rhoE[i] / c.rho[i] - 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        if (c.e[i] - eBoundMin < 0) boundLow = true;
+    }
+    boundLow = c.comm->max(boundLow ? 1.0 : 0.0) > 0.5;
+    if (boundLow) for (int i = 0; i < m.N; i++) c.e[i] = std::max(c.e[i], eBoundMin);
+    if (c.sch.T_max < GREAT) {
+        for (int i = 0; i < m.N; i++) if (c.e[i] - eBoundMax >= 0) boundHigh = true;
+        boundHigh = c.comm->max(boundHigh ? 1.0 : 0.0) > 0.5;
+        if (boundHigh) for (int i = 0; i < m.N; i++) c.e[i] = std::min(c.e[i], eBoundMax);
+    }
+    for (int i = 0; i < m.N; i++) {
+        c.T[i] = c.e[i] / c.Cv;           // thermo.correct(): THE(e, p, T0) for hConst, Tref = 0
+        c.psi[i] = 1.0 / (c.R * c.T[i]);  // perfectGas::psi
+        c.p[i] = c.rho[i] / c.psi[i];
+        const double* u = &c.U[3 * (size_t)i];
+        for (int d = 0; d < 3; d++) c.rhoU[3 * (size_t)i + d] = c.rho[i] * u[d];
+        c.rhoE[i] = c.rho[i] * (c.e[i] + 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]));
+    }
+    correctBoundary(c);
+}
+
+void newTimeStep(Ctx& c)
+{
+    const Mesh& m = c.m;
+    c.rho00 = c.rho0; c.rhoU00 = c.rhoU0; c.rhoE00 = c.rhoE0;
+    c.rho0.assign(c.rho.begin(), c.rho.begin() + m.N);
+    c.rhoU0.assign(c.rhoU.begin(), c.rhoU.begin() + 3 * (size_t)m.N);
+    c.rhoE0.assign(c.rhoE.begin(), c.rhoE.begin() + m.N);
+    c.timeIndex++;
+    // beginTimeStep.H:1-6: transient runs clear the SER residual memory every time step
+    c.haveInitRes = c.havePrevRes = false;
+    c.firstIter = true;
+}
+
+}  // namespace orc
