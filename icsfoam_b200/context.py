@@ -1,0 +1,77 @@
+"""The CUDA product behind the icsb200 C-ABI (libicsb200.so, sm_100a).  No CPU fallback: constructing a
+`Context` without the built library or without a B200-class GPU raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+LIB_PATH = os.path.join(_PKG, "libicsb200.so")
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the CUDA extension is the product; there is no fallback path)")
+        _LIB = C.CDLL(LIB_PATH)
+    return _LIB
+
+
+def exported_symbols():
+    """Names declared in include/icsb200.h (used by the CPU-side 'library loads and exports' test)."""
+    import re
+    hdr = open(os.path.join(os.path.dirname(_PKG), "include", "icsb200.h")).read()
+    return sorted(set(re.findall(r"\b(icsb200_[a-z0-9_]+)\s*\(", hdr)))
+
+
+class Context(capi.Api):
+    def __init__(self, device=0, nccl_id=None, rank=0, n_ranks=1):
+        sigs = dict(capi.SHARED_SIGNATURES)
+        sigs.update(capi.PRODUCT_SIGNATURES)
+        super().__init__(lib(), "icsb200_", sigs)
+        idbuf = None
+        if nccl_id is not None:
+            idbuf = C.create_string_buffer(bytes(nccl_id), 128)
+        rc = self._fn["create"](C.byref(self.h), device, idbuf, rank, n_ranks)
+        if rc != 0 or not self.h:
+            raise RuntimeError(f"icsb200_create failed ({rc}): needs an sm_100 (B200) GPU; there is no CPU fallback")
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = C.create_string_buffer(128)
+        f = lib().icsb200_nccl_unique_id
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p]
+        rc = f(buf)
+        if rc != 0:
+            raise RuntimeError("icsb200_nccl_unique_id failed")
+        return buf.raw
+
+    def iterate_host(self, ctl, p, U, T):
+        res = capi.Residuals()
+        self._call("iterate_host", C.byref(ctl), capi.dptr(p), capi.dptr(U), capi.dptr(T), C.byref(res))
+        return res
+
+    def launch_count(self):
+        return int(self._fn["launch_count"](self.h))
+
+    def timers_reset(self, enable=True):
+        self._call("timers_reset", 1 if enable else 0)
+
+    def timers_get(self):
+        names = C.create_string_buffer(1024)
+        ms = (C.c_double * 32)()
+        calls = (C.c_longlong * 32)()
+        n = self._fn["timers_get"](self.h, names, 1024, ms, calls, 32)
+        nm = names.raw.split(b"\0")[:n]
+        return {nm[i].decode(): (ms[i], int(calls[i])) for i in range(n)}
+
+    def schedule_info(self):
+        out = (C.c_int * 4)()
+        self._call("schedule_info", out)
+        return {"n_levels_fwd": out[0], "n_levels_rev": out[1], "max_width": out[2], "n_positions": out[3]}

@@ -1,0 +1,231 @@
+// common.cuh — context, device layout and launch helpers of libicsb200 (sm_100a).
+//
+// Device layout (private; see DESIGN.md "Data layout in HBM"):
+//  * cells are renumbered into POSITIONS: sorted by LU-SGS forward level (longest path in the owner<neighbour
+//    DAG, lusgs.C:130-159), ties by cell id, each level padded to a multiple of 32 so a warp never straddles
+//    a level.  All cell vectors are SoA of length NPH = NP (+ halo slots + boundary-face slots).
+//  * the coupled matrix (coupledMatrix.H: 9 LDU sub-blocks) is stored row-wise as sliced-ELL with one 5x5
+//    block per face of the row (SELL-32, entry-major SoA): value (e, k, lane) at ((sliceOff[s]+j)*25+k)*32+lane.
+//    Row entries are the faces of the cell in ascending reference face id = [faces where the cell is the
+//    neighbour][faces the cell owns][boundary faces], which is exactly the order in which the reference's
+//    face loops touch that cell (negSumDiag, Amul, fvc::div, gaussGrad) — so per-row accumulation in entry
+//    order reproduces the reference's rounding without atomics or colouring.
+//  * block variable order: (rho, rhoUx, rhoUy, rhoUz, rhoE).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "icsb200.h"
+
+#define ICS_SMALL 1e-15
+#define ICS_VSMALL 1e-300
+#define ICS_ROOTVSMALL 1e-150
+#define ICS_GREAT 1e15
+#define ICS_VGREAT 1e300
+
+constexpr int NQ = 8;   // reconstructed scalars: rho, p, Ux, Uy, Uz, cR, E, H
+constexpr int NG = 7;   // geometry doubles per face (SoA over GPU face ids)
+enum { G_SFX = 0, G_SFY, G_SFZ, G_MAGSF, G_W, G_NONORTH, G_DELTA };
+// entry types (low 2 bits of meta); face id = meta >> 2
+enum { ET_LOWER = 0, ET_UPPER = 1, ET_COUPLED = 2, ET_PHYS = 3 };
+// cell field ids (SoA arrays of length NPH)
+enum {
+    Q_RHO = 0, Q_P, Q_UX, Q_UY, Q_UZ, Q_CR, Q_E, Q_H,  // the NQ reconstructed scalars (order matters)
+    Q_C,                                                 // sqrt(gamma/psi) (lambda)
+    Q_T, Q_PSI,
+    Q_W0, Q_W1, Q_W2, Q_W3, Q_W4,                        // conserved rho, rhoU(3), rhoE
+    Q_COUNT
+};
+
+struct BCDev {
+    int kind[3];       // p, U, T
+    double prm[3][8];
+};
+
+// timer classes
+enum {
+    TM_BC = 0, TM_PRIM, TM_GRAD, TM_FLUX, TM_JAC, TM_SPMV, TM_LUSGS, TM_JACOBI, TM_VEC, TM_RED, TM_UPDATE, TM_PERM, TM_HALO, TM_COUNT
+};
+static const char* const kTimerNames[TM_COUNT] = {"bc", "primitives", "gradient", "flux_residual", "jacobian", "spmv", "lusgs",
+                                                  "jacobi", "vector_ops", "reductions", "update", "permute", "halo"};
+
+struct ProcPatchDev {
+    int nbrRank, size;
+    int haloStart;   // first halo slot (relative to NP)
+    int* d_sendPos;  // positions of faceCells
+};
+
+struct icsb200_ctx {
+    int device = 0, rank = 0, nRanks = 1;
+    cudaStream_t stream = nullptr, commStream = nullptr;
+    void* nccl = nullptr;  // ncclComm_t
+    std::string err;
+    long long launches = 0;
+    int numSMs = 148;
+
+    // ---- host mesh copy (reference numbering) ----
+    int N = 0, F = 0, FT = 0, NB = 0;
+    std::vector<int> owner, neighbour;
+    std::vector<icsb200_patch> patches;
+    std::vector<int> bfacePatch;  // [NB] patch of a boundary face (-1: empty)
+    int solutionD[3] = {1, 1, 1};
+    bool meshSet = false, stateSet = false, matrixSet = false, fluxValid = false, thermoSet = false;
+
+    // ---- positions ----
+    int NP = 0, NH = 0, NPH = 0, NX = 0;  // positions, halo slots, NP+NH, NP+NH+NB (extended slots)
+    int nSlices = 0;
+    long long nEntries = 0;  // total slice entries (each = 32 lanes)
+    std::vector<int> pos2cell, cell2pos;
+    std::vector<int> h_sliceOff;
+    std::vector<int> h_rowNLow, h_rowNInt, h_rowNAll;
+    std::vector<int> h_col, h_meta, h_gfid;  // [nEntries*32]: neighbour slot, type | refFaceId<<2, GPU face id
+    std::vector<int> h_gf2ref;               // [NFG] GPU face id -> reference face id
+    int NFG = 0;                             // number of GPU faces (all non-empty faces)
+    int *d_pos2cell = nullptr, *d_cell2pos = nullptr, *d_sliceOff = nullptr, *d_rowNLow = nullptr, *d_rowNInt = nullptr,
+        *d_rowNAll = nullptr, *d_col = nullptr, *d_meta = nullptr, *d_gfid = nullptr;
+    double* d_geo = nullptr;  // [NG*NFG] face geometry, SoA over GPU face ids (owner-side entry order)
+    double* d_dCoupled = nullptr;  // [3*NB] delta vector of coupled boundary faces (SoA)
+    double* d_V = nullptr;    // [NP] cell volumes (1 for padding)
+    double* d_C = nullptr;    // [3*NPH] cell centres (SoA)
+    // levels
+    int nLevF = 0, nLevR = 0, maxWidth = 0;
+    int *d_levStartF = nullptr, *d_levStartR = nullptr, *d_revList = nullptr;
+    // boundary faces
+    int* d_bfOwnerPos = nullptr;  // [NB] position of faceCell (-1 for empty)
+    int* d_bfPatch = nullptr;     // [NB]
+    int* d_bfKind = nullptr;      // [NB] fvPatch kind of the face's patch (-1: empty)
+    double* d_bfGeo = nullptr;    // [4*NB] Sf(3), magSf  (SoA)
+    BCDev* d_bc = nullptr;        // [nPatches]
+    std::vector<BCDev> h_bc;
+    double *d_phiB = nullptr;               // [NB] mass flux through boundary faces (lagged, for inletOutlet-type BCs)
+    double *d_vic = nullptr;                // [5*NB] pVIC, uVIC(3), tVIC frozen at BC evaluation
+    // processor patches
+    std::vector<ProcPatchDev> procs;
+    double *d_sendBuf = nullptr, *d_recvBuf = nullptr;
+
+    // ---- thermo / schemes ----
+    double R = 287, Cp = 1005, Cv = 718, gamma = 1.4, mu = 0, Pr = 1;
+    icsb200_schemes sch{};
+    double pseudoCoNum = 1;
+    bool haveInitRes = false, havePrevRes = false, firstIter = true;
+    icsb200_residuals initRes{}, prevRes{};
+    int timeIndex = 0;
+
+    // ---- fields: d_q[Q_COUNT] each [NX]; gradients d_grad [NQ*3] each [NPH] ----
+    double* d_fields = nullptr;  // Q_COUNT * NX
+    double* d_grad = nullptr;    // NQ*3 * NPH
+    double *d_rdt = nullptr, *d_co = nullptr, *d_ddtCoeff = nullptr;  // [NP]
+    double *d_Wold = nullptr, *d_Wold2 = nullptr, *d_Wprev = nullptr; // [5*NP] each
+    double *d_src = nullptr, *d_dW = nullptr;                         // [5*NPH]
+    double* d_faceFlux = nullptr;                                     // [5*NFG] GPU face order (only when requested)
+    int* d_bad = nullptr;                                              // [NPH] boundLocalTimeStep flags
+    // ---- matrix ----
+    double* d_offd = nullptr;  // [nEntries*25*32]
+    double* d_diag = nullptr;  // [25*NP]
+    double* d_rD = nullptr;    // [NP] lusgs rDiagCoeff
+    double* d_invD = nullptr;  // [25*NP] Jacobi inverse blocks (lazily)
+    bool rDValid = false, invDValid = false;
+    // ---- solver work ----
+    int mAlloc = 0;
+    double* d_kry = nullptr;  // [m][5*NPH]
+    double *d_w = nullptr, *d_x = nullptr;  // [5*NPH]
+    double* d_scal = nullptr;  // device scalars
+    double* h_scal = nullptr;  // pinned mirror
+    double* d_partial = nullptr;
+    unsigned int* d_counter = nullptr;
+    unsigned int* d_barrier = nullptr;
+    int lusgsGrid = 0;
+    // staging
+    double* d_stage = nullptr;
+    size_t stageBytes = 0;
+    double* h_pinned = nullptr;
+    size_t pinnedBytes = 0;
+
+    // timers
+    bool timing = false;
+    double tms[TM_COUNT] = {0};
+    long long tcalls[TM_COUNT] = {0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    double* q(int id) const { return d_fields + (size_t)id * NX; }
+    double* grad(int qi, int d) const { return d_grad + (size_t)(qi * 3 + d) * NPH; }
+};
+
+#define CUDA_TRY(ctx, call)                                                                            \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+            return ICSB200_ECUDA;                                                                      \
+        }                                                                                              \
+    } while (0)
+
+inline int ics_fail(icsb200_ctx* c, int code, const std::string& msg) { c->err = msg; return code; }
+
+// RAII-ish timer/launch accounting around one kernel launch
+struct LaunchScope {
+    icsb200_ctx* c;
+    int cls;
+    LaunchScope(icsb200_ctx* c_, int cls_) : c(c_), cls(cls_)
+    {
+        c->launches++;
+        if (c->timing) cudaEventRecord(c->ev0, c->stream);
+    }
+    ~LaunchScope()
+    {
+        if (c->timing) {
+            cudaEventRecord(c->ev1, c->stream);
+            cudaEventSynchronize(c->ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+            c->tms[cls] += ms;
+            c->tcalls[cls]++;
+        }
+    }
+};
+
+template <class T>
+inline int devAlloc(icsb200_ctx* c, T** p, size_t n)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (n == 0) return 0;
+    CUDA_TRY(c, cudaMalloc((void**)p, n * sizeof(T)));
+    return 0;
+}
+template <class T>
+inline int devUpload(icsb200_ctx* c, T** p, const std::vector<T>& v)
+{
+    int r = devAlloc(c, p, v.size());
+    if (r) return r;
+    if (!v.empty()) CUDA_TRY(c, cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+inline int gridFor(long long n, int block) { return (int)((n + block - 1) / block); }
+
+// ---- internal entry points across translation units ----
+int ics_ensure_stage(icsb200_ctx* c, size_t bytes);
+// cell-order AoS host array (nc comps) -> position-order SoA device arrays dst[k] = base + k*stride
+int ics_upload_cells(icsb200_ctx* c, const double* host, int nc, double* dst, size_t stride);
+int ics_download_cells(icsb200_ctx* c, double* host, int nc, const double* src, size_t stride);
+int ics_eval_bc(icsb200_ctx* c, bool init);
+int ics_primitives(icsb200_ctx* c);  // derived fields from p,T,U,rho (cells + boundary slots)
+int ics_halo_fields(icsb200_ctx* c, double* base, size_t stride, int nArrays);
+int ics_gradients(icsb200_ctx* c);
+int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux);
+int ics_pseudo_ser(icsb200_ctx* c);
+int ics_jacobian(icsb200_ctx* c, bool useStoredRdt);
+int ics_rdiag(icsb200_ctx* c);
+int ics_spmv(icsb200_ctx* c, const double* x, double* y, const double* b /*nullable: y = b - A x*/);
+int ics_lusgs(icsb200_ctx* c, double* x);
+int ics_jacobi_prepare(icsb200_ctx* c);
+int ics_jacobi(icsb200_ctx* c, double* x);
+int ics_gmres(icsb200_ctx* c, const icsb200_solver_controls* ctl, icsb200_residuals* res);
+int ics_bound_local_dt(icsb200_ctx* c);
+int ics_update(icsb200_ctx* c);
+int ics_copy_prev(icsb200_ctx* c);
+int ics_state_from_primitives(icsb200_ctx* c);

@@ -1,0 +1,561 @@
+// jacobian.cu — pseudo time step and approximate flux Jacobian, assembled straight into the sliced-ELL block rows.
+//
+// Replaces convectiveFluxScheme::createConvectiveJacobian (convectiveFluxScheme.C:537-546):
+//   addFluxTerms :374-484 (7 x blockFvMatrix::insertBlock, blockFvMatrix.C:211-268),
+//   addDissipationJacobian :487-534 (3 x insertDissipationBlock, blockFvMatrix.C:271-326),
+//   addBoundaryTerms + boundaryJacobian :47-120, 219-355, addTemporalTerms :358-369,
+// the Lax-Friedrichs branch of viscousFluxScheme::addFluxTerms (viscousFluxScheme.C:220-246 with
+// fvj::laplacian(sf, one), blockFvOperatorsTemplates.C:499-557), setCoAndDeltaT.H:39-173 (local pseudo time step)
+// and outerLoop.H:61-64 (ddtCoeff).
+//
+// One thread per cell row.  The reference builds 10 temporary LDU matrices with face loops and scatters
+// (negSumDiag); here the row owner gathers its faces in ascending face id, which visits the same addends in the
+// same order, so every diag / upper / lower coefficient carries the reference's rounding.  Each face's two 5x5
+// Jacobians (left state, right state) are evaluated by both adjacent rows: one lands in the row's off-diagonal
+// block, the other in its diagonal — no atomics, no colouring, all stores coalesced across the slice.
+#include "common.cuh"
+
+namespace {
+
+struct V3 { double x, y, z; };
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ V3 operator/(V3 a, double s) { return {a.x / s, a.y / s, a.z / s}; }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double magSqr(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+__device__ __forceinline__ V3 cm(V3 a, V3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+__device__ __forceinline__ double sgn(double s) { return s >= 0 ? 1.0 : -1.0; }
+
+__device__ __forceinline__ double nvdR(double gradcf, double gradf)
+{
+    if (fabs(gradcf) >= 1000 * fabs(gradf)) return 2 * 1000 * sgn(gradcf) * sgn(gradf) - 1;
+    return 2 * (gradcf / gradf) - 1;
+}
+__device__ __forceinline__ double limiterOf(int lim, double gradcf, double gradf)
+{
+    if (lim == ICSB200_LIM_VANLEER) { double r = nvdR(gradcf, gradf); return (r + fabs(r)) / (1 + fabs(r)); }
+    if (lim == ICSB200_LIM_MINMOD) { double r = nvdR(gradcf, gradf); return fmax(fmin(r, 1.0), 0.0); }
+    return lim == ICSB200_LIM_LINEAR ? 1.0 : 0.0;
+}
+
+struct JacArgs {
+    int NP, NB, F;
+    const int *pos2cell, *sliceOff, *rowNAll, *col, *meta, *gfid, *bfKind;
+    const double *geo, *dCoupled, *C, *V, *f, *grad, *vic, *co;
+    size_t NFG, NX, NPH;
+    int limU, limT, localDt, useStoredRdt;
+    double gamma, Cv, rdtUniform;
+    int ddtScheme;
+    double rDeltaT, coefft;
+    double mu, alphaEff;  // viscous LF Jacobian (mu > 0)
+    const double* src;    // unused here (sources live in d_src)
+    double *offd, *diag, *rD, *rdt, *ddtCoeff;
+};
+
+// analytic Euler flux Jacobian d(F.n)/dW at state (U, E) — convectiveFluxScheme.C:402-464
+// J[r*5+c], variable order (rho, rhoU, rhoE)
+__device__ __forceinline__ void eulerJacobian(V3 U, double E, V3 n, double gamma, double* J)
+{
+    const double theta = 0.5 * (gamma - 1) * magSqr(U);
+    const double a1 = gamma * E - theta;
+    const double a2 = gamma - 1;
+    const double projU = dot(U, n);
+    J[0] = 0.0; J[1] = n.x; J[2] = n.y; J[3] = n.z; J[4] = 0.0;
+    const V3 mr = n * theta - U * projU;
+    J[5] = mr.x; J[10] = mr.y; J[15] = mr.z;
+    const V3 a2n = a2 * n;
+    // U*n - a2*n*U + projU*I   (outer products)
+    J[6] = (U.x * n.x - a2n.x * U.x) + projU * 1.0; J[7] = (U.x * n.y - a2n.x * U.y) + projU * 0.0; J[8] = (U.x * n.z - a2n.x * U.z) + projU * 0.0;
+    J[11] = (U.y * n.x - a2n.y * U.x) + projU * 0.0; J[12] = (U.y * n.y - a2n.y * U.y) + projU * 1.0; J[13] = (U.y * n.z - a2n.y * U.z) + projU * 0.0;
+    J[16] = (U.z * n.x - a2n.z * U.x) + projU * 0.0; J[17] = (U.z * n.y - a2n.z * U.y) + projU * 0.0; J[18] = (U.z * n.z - a2n.z * U.z) + projU * 1.0;
+    const V3 me = n * a2;
+    J[9] = me.x; J[14] = me.y; J[19] = me.z;
+    J[20] = projU * (theta - a1);
+    const V3 er = n * a1 - a2 * U * projU;
+    J[21] = er.x; J[22] = er.y; J[23] = er.z;
+    J[24] = gamma * projU;
+}
+
+__device__ __forceinline__ bool isDiagEntry(int k) { return k == 0 || k == 6 || k == 12 || k == 18 || k == 24; }
+
+__global__ void __launch_bounds__(128)
+k_jac(JacArgs a)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.NP || a.pos2cell[p] < 0) return;
+    const int lane = p & 31;
+    const size_t base = (size_t)a.sliceOff[p >> 5];
+    const int nAll = a.rowNAll[p];
+    const bool lim4U = a.limU == ICSB200_LIM_VANLEER || a.limU == ICSB200_LIM_MINMOD;
+    const bool lim4T = a.limT == ICSB200_LIM_VANLEER || a.limT == ICSB200_LIM_MINMOD;
+    double conv[25], dissAcc = 0.0, viscAcc = 0.0, rdt = 0.0;
+#pragma unroll
+    for (int k = 0; k < 25; k++) conv[k] = 0.0;
+    bool hasPhys = false;
+    const double cOwn = a.f[(size_t)Q_C * a.NX + p];
+    const V3 UOwn = {a.f[(size_t)Q_UX * a.NX + p], a.f[(size_t)Q_UY * a.NX + p], a.f[(size_t)Q_UZ * a.NX + p]};
+    for (int j = 0; j < nAll; j++) {
+        const size_t e = (base + j) * 32 + lane;
+        const int c = a.col[e], m = a.meta[e], type = m & 3;
+        const size_t g = a.gfid[e];
+        const int b = (m >> 2) - a.F;
+        const V3 Sf = {a.geo[G_SFX * a.NFG + g], a.geo[G_SFY * a.NFG + g], a.geo[G_SFZ * a.NFG + g]};
+        const double magSf = a.geo[G_MAGSF * a.NFG + g];
+        const V3 n = Sf / magSf;
+        double* blk = a.offd + ((base + j) * 25) * 32 + lane;
+        if (type == ET_PHYS) {
+            hasPhys = true;
+            // lambdaConv boundary value: c_b + |U_b & n|  (interpolate() returns the patch value)
+            const V3 Ub = {a.f[(size_t)Q_UX * a.NX + c], a.f[(size_t)Q_UY * a.NX + c], a.f[(size_t)Q_UZ * a.NX + c]};
+            const double lam = a.f[(size_t)Q_C * a.NX + c] + fabs(dot(Ub, n) - 0.0);
+            const double dl = 0.5 * magSf * lam;
+            dissAcc -= dl;  // mx.diag[own] -= interfacesLower (physical boundaries included, blockFvMatrix.C:310-321)
+            if (a.bfKind[b] == ICSB200_WALL) {
+                // setCoAndDeltaT.H:87-138: wall patches use the cell state with a factor 1/2
+                const double pLambda = 0.5 * a.geo[G_NONORTH * a.NFG + g] * (cOwn + fabs(dot(UOwn, n) - 0.0));
+                rdt = fmax(rdt, pLambda);
+            }
+#pragma unroll
+            for (int k = 0; k < 25; k++) blk[(size_t)k * 32] = 0.0;
+            continue;
+        }
+        const bool rowIsP = type != ET_LOWER;
+        const bool coupled = type == ET_COUPLED;
+        const int P = rowIsP ? p : c, N = rowIsP ? c : p;
+        const double w = a.geo[G_W * a.NFG + g];
+        V3 d;
+        if (coupled) d = {a.dCoupled[b], a.dCoupled[a.NB + b], a.dCoupled[2 * (size_t)a.NB + b]};
+        else d = {a.C[N] - a.C[P], a.C[a.NPH + N] - a.C[a.NPH + P], a.C[2 * a.NPH + N] - a.C[2 * a.NPH + P]};
+        // limited reconstruction of U (3 comps) and E on both sides (convectiveFluxScheme.C:387-400)
+        double L[4], R[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = (q < 3) ? (Q_UX + q) : Q_E;
+            const int lim = (q < 3) ? a.limU : a.limT;
+            const bool useG = (q < 3) ? lim4U : lim4T;
+            const double phiP = a.f[(size_t)k * a.NX + P], phiN = a.f[(size_t)k * a.NX + N];
+            double gcP = 0.0, gcN = 0.0;
+            if (useG) {
+                gcP = d.x * a.grad[(size_t)(k * 3) * a.NPH + P] + d.y * a.grad[(size_t)(k * 3 + 1) * a.NPH + P] + d.z * a.grad[(size_t)(k * 3 + 2) * a.NPH + P];
+                gcN = d.x * a.grad[(size_t)(k * 3) * a.NPH + N] + d.y * a.grad[(size_t)(k * 3 + 1) * a.NPH + N] + d.z * a.grad[(size_t)(k * 3 + 2) * a.NPH + N];
+            }
+            const double gradf = phiN - phiP;
+            const double limL = limiterOf(lim, gcP, gradf), limR = limiterOf(lim, gcN, gradf);
+            const double wL = limL * w + (1.0 - limL) * 1.0, wR = limR * w + (1.0 - limR) * 0.0;
+            if (coupled) { L[q] = wL * phiP + (1.0 - wL) * phiN; R[q] = wR * phiP + (1.0 - wR) * phiN; }
+            else { L[q] = wL * (phiP - phiN) + phiN; R[q] = wR * (phiP - phiN) + phiN; }
+        }
+        // lambdaConv = interpolate(c) + |interpolate(U) & n - MRFFaceVelocity|   (convectiveFluxScheme.C:498-524)
+        double lam;
+        {
+            const double cP = a.f[(size_t)Q_C * a.NX + P], cN = a.f[(size_t)Q_C * a.NX + N];
+            const V3 UP = {a.f[(size_t)Q_UX * a.NX + P], a.f[(size_t)Q_UY * a.NX + P], a.f[(size_t)Q_UZ * a.NX + P]};
+            const V3 UN = {a.f[(size_t)Q_UX * a.NX + N], a.f[(size_t)Q_UY * a.NX + N], a.f[(size_t)Q_UZ * a.NX + N]};
+            double cf;
+            V3 uf;
+            if (coupled) {
+                cf = w * cP + (1.0 - w) * cN;
+                uf = {w * UP.x + (1.0 - w) * UN.x, w * UP.y + (1.0 - w) * UN.y, w * UP.z + (1.0 - w) * UN.z};
+            } else {
+                cf = w * (cP - cN) + cN;
+                uf = {w * (UP.x - UN.x) + UN.x, w * (UP.y - UN.y) + UN.y, w * (UP.z - UN.z) + UN.z};
+            }
+            lam = cf + fabs(dot(uf, n) - 0.0);
+        }
+        rdt = fmax(rdt, a.geo[G_NONORTH * a.NFG + g] * lam);
+        const double dl = 0.5 * magSf * lam;
+        dissAcc -= dl;
+        double sf2 = 0.0;
+        if (a.mu > 0) {
+            const double rP = a.f[(size_t)Q_RHO * a.NX + P], rN = a.f[(size_t)Q_RHO * a.NX + N];
+            const double rhof = coupled ? (w * rP + (1.0 - w) * rN) : (w * (rP - rN) + rN);
+            const double lambdaVisc = (a.mu + a.alphaEff) / rhof;
+            sf2 = (0.5 * lambdaVisc) * magSf * a.geo[G_DELTA * a.NFG + g];
+            viscAcc -= sf2;
+        }
+        double JL[25], JR[25];
+        eulerJacobian({L[0], L[1], L[2]}, L[3], n, a.gamma, JL);
+        eulerJacobian({R[0], R[1], R[2]}, R[3], n, a.gamma, JR);
+        const double hp = 0.5 * magSf, hm = -0.5 * magSf;
+#pragma unroll
+        for (int k = 0; k < 25; k++) {
+            const bool hasConv = !(k == 0 || k == 4);  // dSByS(0,0) and dSByS(0,1) receive no insertBlock
+            const double upp = hp * JR[k];             // upper / interfacesUpper
+            const double low = hm * JL[k];             // lower / interfacesLower
+            double off;
+            if (rowIsP) { off = hasConv ? (0.0 + upp) : 0.0; if (hasConv) conv[k] -= low; }
+            else { off = hasConv ? (0.0 + low) : 0.0; if (hasConv) conv[k] -= upp; }
+            if (isDiagEntry(k)) { off -= dl; if (a.mu > 0) off -= sf2 * 1.0; }
+            blk[(size_t)k * 32] = off;
+        }
+    }
+    // ---- pseudo time step (setCoAndDeltaT.H:57-147) and ddtCoeff (outerLoop.H:61-64)
+    const double vol = a.V[p];
+    if (a.useStoredRdt) rdt = a.rdt[p];
+    else if (a.localDt) rdt = rdt / a.co[p];
+    else rdt = a.rdtUniform;
+    double innerDiag = 0.0;
+    if (a.ddtScheme == ICSB200_DDT_EULER) innerDiag = a.rDeltaT * vol;
+    else if (a.ddtScheme == ICSB200_DDT_BACKWARD) innerDiag = (a.coefft * a.rDeltaT) * vol;
+    const double ddtCoeff = (a.ddtScheme == ICSB200_DDT_STEADY ? (0.0 + rdt * vol) : (innerDiag + rdt * vol)) / vol;
+    a.rdt[p] = rdt;
+    a.ddtCoeff[p] = ddtCoeff;
+    // ---- diagonal block: conv (0 + mx.diag), -= dissipation mx.diag, += boundary terms, += temporal, -= viscous
+    double dg[25];
+#pragma unroll
+    for (int k = 0; k < 25; k++) {
+        dg[k] = 0.0 + conv[k];
+        if (isDiagEntry(k)) dg[k] -= dissAcc;
+    }
+    if (hasPhys) {
+        const double rhoI = a.f[(size_t)Q_RHO * a.NX + p];
+        const double TI = a.f[(size_t)Q_T * a.NX + p];
+        const V3 UI = UOwn;
+        const double rhoEI = rhoI * (a.Cv * TI + 0.5 * magSqr(UI));
+        const double gammaI = a.gamma, cvI = a.Cv;
+        const double dPdRho = 0.5 * (gammaI - 1) * magSqr(UI);
+        const V3 dUdRho = -1.0 * UI / rhoI;
+        const double dTdRho = -1.0 / (cvI * rhoI) * (rhoEI / rhoI - magSqr(UI));
+        const V3 dPdRhoU = -(gammaI - 1) * UI;
+        const double dUdRhoU = 1.0 / rhoI * 1.0;
+        const V3 dTdRhoU = -1.0 * UI / (cvI * rhoI);
+        const double dPdRhoE = gammaI - 1;
+        const double dTdRhoE = 1.0 / (cvI * rhoI);
+        for (int j = 0; j < nAll; j++) {
+            const size_t e = (base + j) * 32 + lane;
+            const int m = a.meta[e];
+            if ((m & 3) != ET_PHYS) continue;
+            const int c = a.col[e];
+            const size_t g = a.gfid[e];
+            const int b = (m >> 2) - a.F;
+            const V3 SfB = {a.geo[G_SFX * a.NFG + g], a.geo[G_SFY * a.NFG + g], a.geo[G_SFZ * a.NFG + g]};
+            const double pVIC = a.vic[b], tVIC = a.vic[4 * (size_t)a.NB + b];
+            const V3 uVIC = {a.vic[a.NB + b], a.vic[2 * (size_t)a.NB + b], a.vic[3 * (size_t)a.NB + b]};
+            const double rhoB = a.f[(size_t)Q_RHO * a.NX + c], pB = a.f[(size_t)Q_P * a.NX + c], TB = a.f[(size_t)Q_T * a.NX + c];
+            const V3 UB = {a.f[(size_t)Q_UX * a.NX + c], a.f[(size_t)Q_UY * a.NX + c], a.f[(size_t)Q_UZ * a.NX + c]};
+            double UrelBdotSf = dot(UB, SfB);
+            UrelBdotSf -= 0.0 * a.geo[G_MAGSF * a.NFG + g];
+            const double rhoEB = rhoB * (a.Cv * TB + 0.5 * magSqr(UB));
+            const double cvB = a.Cv;
+            // boundaryJacobian (convectiveFluxScheme.C:96-117)
+            const double dContFluxdp = rhoB / pB * UrelBdotSf * pVIC;
+            const V3 dContFluxdU = rhoB * cm(SfB, uVIC);
+            const double dContFluxdT = -rhoB / TB * UrelBdotSf * tVIC;
+            const V3 dMomFluxdp = (rhoB / pB * UB * UrelBdotSf + SfB) * pVIC;
+            const V3 rUB = rhoB * UB, sv = cm(SfB, uVIC);
+            double dMomFluxdU[9] = {rUB.x * sv.x, rUB.x * sv.y, rUB.x * sv.z, rUB.y * sv.x, rUB.y * sv.y, rUB.y * sv.z, rUB.z * sv.x, rUB.z * sv.y, rUB.z * sv.z};
+            const V3 dMomFluxdUDiag = rhoB * UrelBdotSf * uVIC;
+            const V3 dMomFluxdT = -rhoB / TB * UB * UrelBdotSf * tVIC;
+            const double dEnergyFluxdp = (rhoEB / pB * UrelBdotSf + dot(UB, SfB)) * pVIC;
+            const V3 dEnergyFluxdU = cm(SfB, uVIC) * (rhoEB + pB) + rhoB * UrelBdotSf * cm(UB, uVIC);
+            const double dEnergyFluxdT = UrelBdotSf * (rhoB * cvB - rhoEB / TB) * tVIC;
+            dMomFluxdU[0] = dMomFluxdU[0] + dMomFluxdUDiag.x;
+            dMomFluxdU[4] = dMomFluxdU[4] + dMomFluxdUDiag.y;
+            dMomFluxdU[8] = dMomFluxdU[8] + dMomFluxdUDiag.z;
+            // addBoundaryTerms (convectiveFluxScheme.C:293-349): three separate += per sub-block
+            dg[0] += dContFluxdp * dPdRho;
+            dg[0] += dot(dContFluxdU, dUdRho);
+            dg[0] += dContFluxdT * dTdRho;
+            { const V3 t1 = dContFluxdp * dPdRhoU, t2 = dContFluxdU * dUdRhoU, t3 = dContFluxdT * dTdRhoU;
+              dg[1] += t1.x; dg[2] += t1.y; dg[3] += t1.z; dg[1] += t2.x; dg[2] += t2.y; dg[3] += t2.z; dg[1] += t3.x; dg[2] += t3.y; dg[3] += t3.z; }
+            dg[4] += dContFluxdp * dPdRhoE;
+            dg[4] += dContFluxdU.x * 0.0 + dContFluxdU.y * 0.0 + dContFluxdU.z * 0.0;
+            dg[4] += dContFluxdT * dTdRhoE;
+            { const V3 t1 = dMomFluxdp * dPdRho;
+              const V3 t2 = {dMomFluxdU[0] * dUdRho.x + dMomFluxdU[1] * dUdRho.y + dMomFluxdU[2] * dUdRho.z,
+                             dMomFluxdU[3] * dUdRho.x + dMomFluxdU[4] * dUdRho.y + dMomFluxdU[5] * dUdRho.z,
+                             dMomFluxdU[6] * dUdRho.x + dMomFluxdU[7] * dUdRho.y + dMomFluxdU[8] * dUdRho.z};
+              const V3 t3 = dMomFluxdT * dTdRho;
+              dg[5] += t1.x; dg[10] += t1.y; dg[15] += t1.z; dg[5] += t2.x; dg[10] += t2.y; dg[15] += t2.z; dg[5] += t3.x; dg[10] += t3.y; dg[15] += t3.z; }
+            {
+                const double mp[3] = {dMomFluxdp.x, dMomFluxdp.y, dMomFluxdp.z}, pu[3] = {dPdRhoU.x, dPdRhoU.y, dPdRhoU.z};
+                const double mt[3] = {dMomFluxdT.x, dMomFluxdT.y, dMomFluxdT.z}, tu[3] = {dTdRhoU.x, dTdRhoU.y, dTdRhoU.z};
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int cc = 0; cc < 3; cc++) {
+                        const int k = (r + 1) * 5 + (cc + 1);
+                        dg[k] += mp[r] * pu[cc];
+                        dg[k] += dMomFluxdU[r * 3 + cc] * dUdRhoU;
+                        dg[k] += mt[r] * tu[cc];
+                    }
+            }
+            { const V3 t1 = dMomFluxdp * dPdRhoE;
+              const V3 t2 = {dMomFluxdU[0] * 0.0 + dMomFluxdU[1] * 0.0 + dMomFluxdU[2] * 0.0, dMomFluxdU[3] * 0.0 + dMomFluxdU[4] * 0.0 + dMomFluxdU[5] * 0.0,
+                             dMomFluxdU[6] * 0.0 + dMomFluxdU[7] * 0.0 + dMomFluxdU[8] * 0.0};
+              const V3 t3 = dMomFluxdT * dTdRhoE;
+              dg[9] += t1.x; dg[14] += t1.y; dg[19] += t1.z; dg[9] += t2.x; dg[14] += t2.y; dg[19] += t2.z; dg[9] += t3.x; dg[14] += t3.y; dg[19] += t3.z; }
+            dg[20] += dEnergyFluxdp * dPdRho;
+            dg[20] += dot(dEnergyFluxdU, dUdRho);
+            dg[20] += dEnergyFluxdT * dTdRho;
+            { const V3 t1 = dEnergyFluxdp * dPdRhoU, t2 = dEnergyFluxdU * dUdRhoU, t3 = dEnergyFluxdT * dTdRhoU;
+              dg[21] += t1.x; dg[22] += t1.y; dg[23] += t1.z; dg[21] += t2.x; dg[22] += t2.y; dg[23] += t2.z; dg[21] += t3.x; dg[22] += t3.y; dg[23] += t3.z; }
+            dg[24] += dEnergyFluxdp * dPdRhoE;
+            dg[24] += dEnergyFluxdU.x * 0.0 + dEnergyFluxdU.y * 0.0 + dEnergyFluxdU.z * 0.0;
+            dg[24] += dEnergyFluxdT * dTdRhoE;
+        }
+    }
+    const double diagCoeff = ddtCoeff * vol;
+    dg[0] += diagCoeff; dg[6] += diagCoeff * 1.0; dg[12] += diagCoeff * 1.0; dg[18] += diagCoeff * 1.0; dg[24] += diagCoeff;
+    if (a.mu > 0) { dg[0] -= viscAcc * 1.0; dg[6] -= viscAcc * 1.0; dg[12] -= viscAcc * 1.0; dg[18] -= viscAcc * 1.0; dg[24] -= viscAcc * 1.0; }
+#pragma unroll
+    for (int k = 0; k < 25; k++) a.diag[(size_t)k * a.NP + p] = dg[k];
+    // lusgs ctor (lusgs.C:50-125): rDiagCoeff = 1/max(|diag entries of the S-S and V-V diagonal blocks|)
+    double rD = ICS_GREAT;
+    rD = 1.0 / fmax(1.0 / rD, fabs(dg[0]));
+    rD = 1.0 / fmax(1.0 / rD, fabs(dg[24]));
+    rD = 1.0 / fmax(1.0 / rD, fabs(dg[6]));
+    rD = 1.0 / fmax(1.0 / rD, fabs(dg[12]));
+    rD = 1.0 / fmax(1.0 / rD, fabs(dg[18]));
+    a.rD[p] = rD;
+}
+
+// non-local time stepping: max over faces of deltaCoeffs*lambda (setCoAndDeltaT.H:143-146)
+__global__ void k_lambda_max(int NP, const int* __restrict__ pos2cell, const int* __restrict__ sliceOff, const int* __restrict__ rowNAll,
+                             const int* __restrict__ rowNLow, const int* __restrict__ col, const int* __restrict__ meta, const int* __restrict__ gfid,
+                             const double* __restrict__ geo, size_t NFG, const double* __restrict__ f, size_t NX, unsigned long long* __restrict__ out)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    double mx = 0.0;
+    if (p < NP && pos2cell[p] >= 0) {
+        const int lane = p & 31;
+        const size_t base = (size_t)sliceOff[p >> 5];
+        for (int j = rowNLow[p]; j < rowNAll[p]; j++) {
+            const size_t e = (base + j) * 32 + lane;
+            const int c = col[e], type = meta[e] & 3;
+            const size_t g = gfid[e];
+            const double magSf = geo[G_MAGSF * NFG + g], w = geo[G_W * NFG + g];
+            const V3 n = V3{geo[G_SFX * NFG + g], geo[G_SFY * NFG + g], geo[G_SFZ * NFG + g]} / magSf;
+            double cf;
+            V3 uf;
+            const double cP = f[(size_t)Q_C * NX + p], cN = f[(size_t)Q_C * NX + c];
+            const V3 UP = {f[(size_t)Q_UX * NX + p], f[(size_t)Q_UY * NX + p], f[(size_t)Q_UZ * NX + p]};
+            const V3 UN = {f[(size_t)Q_UX * NX + c], f[(size_t)Q_UY * NX + c], f[(size_t)Q_UZ * NX + c]};
+            if (type == ET_PHYS) { cf = cN; uf = UN; }
+            else if (type == ET_COUPLED) { cf = w * cP + (1.0 - w) * cN; uf = {w * UP.x + (1.0 - w) * UN.x, w * UP.y + (1.0 - w) * UN.y, w * UP.z + (1.0 - w) * UN.z}; }
+            else { cf = w * (cP - cN) + cN; uf = {w * (UP.x - UN.x) + UN.x, w * (UP.y - UN.y) + UN.y, w * (UP.z - UN.z) + UN.z}; }
+            mx = fmax(mx, geo[G_DELTA * NFG + g] * (cf + fabs(dot(uf, n) - 0.0)));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
+}
+
+// ---- LDU views of the block rows (parity API) ----
+__device__ __forceinline__ int blockRows(int blk, int* r0) { int rows; switch (blk) { case 0: case 1: case 4: *r0 = 0; rows = 1; break; case 2: case 3: case 5: *r0 = 4; rows = 1; break; default: *r0 = 1; rows = 3; } return rows; }
+__device__ __forceinline__ int blockCols(int blk, int* c0) { int cols; switch (blk) { case 0: case 2: case 6: *c0 = 0; cols = 1; break; case 1: case 3: case 7: *c0 = 4; cols = 1; break; default: *c0 = 1; cols = 3; } return cols; }
+
+// thread per (entry slot): copy sub-block coefficients of internal faces to upper[F*nc] / lower[F*nc] (or back)
+__global__ void k_ldu_offdiag(long long nE32, const int* __restrict__ meta, const int* __restrict__ rowNAllBySlot, int blk, int F, bool toHost,
+                              double* __restrict__ offd, double* __restrict__ upper, double* __restrict__ lower)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nE32) return;
+    (void)rowNAllBySlot;
+    const int m = meta[i], type = m & 3, fc = m >> 2;
+    if (type > ET_UPPER || fc >= F || fc < 0) return;
+    const long long ent = i >> 5;
+    const int lane = (int)(i & 31);
+    int r0, c0;
+    const int rows = blockRows(blk, &r0), cols = blockCols(blk, &c0), nc = rows * cols;
+    double* dst = (type == ET_UPPER) ? upper : lower;
+    if (!dst) return;
+    for (int r = 0; r < rows; r++)
+        for (int cc = 0; cc < cols; cc++) {
+            double* v = offd + ((size_t)ent * 25 + (r0 + r) * 5 + (c0 + cc)) * 32 + lane;
+            if (toHost) dst[(size_t)fc * nc + r * cols + cc] = *v;
+            else *v = dst[(size_t)fc * nc + r * cols + cc];
+        }
+}
+
+__global__ void k_ldu_diag(int NP, const int* __restrict__ pos2cell, int blk, bool toHost, double* __restrict__ diag, double* __restrict__ out)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= NP) return;
+    int cell = pos2cell[p];
+    if (cell < 0) return;
+    int r0, c0;
+    const int rows = blockRows(blk, &r0), cols = blockCols(blk, &c0), nc = rows * cols;
+    for (int r = 0; r < rows; r++)
+        for (int cc = 0; cc < cols; cc++) {
+            double* v = diag + (size_t)((r0 + r) * 5 + (c0 + cc)) * NP + p;
+            if (toHost) out[(size_t)cell * nc + r * cols + cc] = *v;
+            else *v = out[(size_t)cell * nc + r * cols + cc];
+        }
+}
+
+__global__ void k_rdiag(int NP, const int* __restrict__ pos2cell, const double* __restrict__ diag, double* __restrict__ rD, int* __restrict__ err)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= NP) return;
+    if (pos2cell[p] < 0) { rD[p] = 0.0; return; }
+    double r = ICS_GREAT;
+    r = 1.0 / fmax(1.0 / r, fabs(diag[(size_t)0 * NP + p]));
+    r = 1.0 / fmax(1.0 / r, fabs(diag[(size_t)24 * NP + p]));
+    r = 1.0 / fmax(1.0 / r, fabs(diag[(size_t)6 * NP + p]));
+    r = 1.0 / fmax(1.0 / r, fabs(diag[(size_t)12 * NP + p]));
+    r = 1.0 / fmax(1.0 / r, fabs(diag[(size_t)18 * NP + p]));
+    rD[p] = r;
+    if (r < ICS_VSMALL) atomicOr(err, 1);
+}
+
+}  // namespace
+
+int ics_jacobian(icsb200_ctx* c, bool useStoredRdt)
+{
+    JacArgs a{};
+    a.NP = c->NP; a.NB = c->NB; a.F = c->F;
+    a.pos2cell = c->d_pos2cell; a.sliceOff = c->d_sliceOff; a.rowNAll = c->d_rowNAll; a.col = c->d_col; a.meta = c->d_meta; a.gfid = c->d_gfid;
+    a.bfKind = c->d_bfKind;
+    a.geo = c->d_geo; a.dCoupled = c->d_dCoupled; a.C = c->d_C; a.V = c->d_V; a.f = c->d_fields; a.grad = c->d_grad; a.vic = c->d_vic; a.co = c->d_co;
+    a.NFG = c->NFG; a.NX = c->NX; a.NPH = c->NPH;
+    a.limU = c->sch.limiter_U; a.limT = c->sch.limiter_T; a.localDt = c->sch.local_timestepping;
+    a.gamma = c->gamma; a.Cv = c->Cv;
+    a.ddtScheme = c->sch.ddt_scheme;
+    if (a.ddtScheme != ICSB200_DDT_STEADY) {
+        a.rDeltaT = 1.0 / c->sch.delta_t;
+        double deltaT0 = (c->timeIndex < 2) ? ICS_GREAT : c->sch.delta_t;
+        a.coefft = 1 + c->sch.delta_t / (c->sch.delta_t + deltaT0);
+    }
+    a.mu = c->mu; a.alphaEff = c->gamma * (c->mu / c->Pr);
+    a.offd = c->d_offd; a.diag = c->d_diag; a.rD = c->d_rD; a.rdt = c->d_rdt; a.ddtCoeff = c->d_ddtCoeff;
+    a.rdtUniform = 0.0;
+    a.useStoredRdt = useStoredRdt ? 1 : 0;
+    if (!a.localDt && !useStoredRdt) {
+        unsigned long long* d_max = (unsigned long long*)(c->d_scal + 4000);
+        CUDA_TRY(c, cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), c->stream));
+        {
+            LaunchScope ls(c, TM_JAC);
+            k_lambda_max<<<gridFor(c->NP, 128), 128, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_rowNLow, c->d_col, c->d_meta,
+                                                                    c->d_gfid, c->d_geo, c->NFG, c->d_fields, c->NX, d_max);
+        }
+        double mx = 0.0;
+        CUDA_TRY(c, cudaMemcpyAsync(&mx, d_max, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        if (c->nRanks > 1) return ics_fail(c, ICSB200_ESTATE, "global time stepping is single-rank only in this build");
+        a.rdtUniform = mx / c->pseudoCoNum;
+    }
+    {
+        LaunchScope ls(c, TM_JAC);
+        k_jac<<<gridFor(c->NP, 128), 128, 0, c->stream>>>(a);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    c->matrixSet = true;
+    c->rDValid = true;
+    c->invDValid = false;
+    return 0;
+}
+
+int ics_rdiag(icsb200_ctx* c)
+{
+    int* err = (int*)c->d_counter + 40;
+    CUDA_TRY(c, cudaMemsetAsync(err, 0, sizeof(int), c->stream));
+    {
+        LaunchScope ls(c, TM_JAC);
+        k_rdiag<<<gridFor(c->NP, 256), 256, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_diag, c->d_rD, err);
+    }
+    int h = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&h, err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (h) return ics_fail(c, ICSB200_ESINGULAR, "All diagonals of coupledMatrix are zero.");
+    c->rDValid = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+static const int kBlockNc[9] = {1, 1, 1, 1, 3, 3, 3, 3, 9};
+
+extern "C" int icsb200_matrix_get_ldu(icsb200_ctx* c, int block, double* diag, double* upper, double* lower)
+{
+    if (!c->matrixSet) return ics_fail(c, ICSB200_ESTATE, "matrix_get_ldu: matrix not assembled");
+    if (block < 0 || block > 8) return ics_fail(c, ICSB200_EINVAL, "matrix_get_ldu: block id");
+    const int nc = kBlockNc[block];
+    const size_t nd = (size_t)nc * c->N, nf = (size_t)nc * c->F;
+    int r = ics_ensure_stage(c, sizeof(double) * (nd + 2 * nf + 1));
+    if (r) return r;
+    double *sd = c->d_stage, *su = sd + nd, *sl = su + nf;
+    CUDA_TRY(c, cudaMemsetAsync(sd, 0, sizeof(double) * (nd + 2 * nf), c->stream));
+    const long long nE32 = c->nEntries * 32;
+    {
+        LaunchScope ls(c, TM_PERM);
+        k_ldu_diag<<<gridFor(c->NP, 256), 256, 0, c->stream>>>(c->NP, c->d_pos2cell, block, true, c->d_diag, sd);
+        if (nE32 > 0) k_ldu_offdiag<<<gridFor(nE32, 256), 256, 0, c->stream>>>(nE32, c->d_meta, nullptr, block, c->F, true, c->d_offd, su, sl);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    if (diag) CUDA_TRY(c, cudaMemcpyAsync(diag, sd, sizeof(double) * nd, cudaMemcpyDeviceToHost, c->stream));
+    if (upper && nf) CUDA_TRY(c, cudaMemcpyAsync(upper, su, sizeof(double) * nf, cudaMemcpyDeviceToHost, c->stream));
+    if (lower && nf) CUDA_TRY(c, cudaMemcpyAsync(lower, sl, sizeof(double) * nf, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int icsb200_matrix_set_ldu(icsb200_ctx* c, int block, const double* diag, const double* upper, const double* lower)
+{
+    if (!c->meshSet) return ics_fail(c, ICSB200_ESTATE, "matrix_set_ldu: mesh not set");
+    if (block < 0 || block > 8 || !diag) return ics_fail(c, ICSB200_EINVAL, "matrix_set_ldu: bad argument");
+    if ((upper == nullptr) != (lower == nullptr)) return ics_fail(c, ICSB200_EINVAL, "matrix_set_ldu: upper and lower must come together");
+    const int nc = kBlockNc[block];
+    const size_t nd = (size_t)nc * c->N, nf = (size_t)nc * c->F;
+    int r = ics_ensure_stage(c, sizeof(double) * (nd + 2 * nf + 1));
+    if (r) return r;
+    double *sd = c->d_stage, *su = sd + nd, *sl = su + nf;
+    CUDA_TRY(c, cudaMemcpyAsync(sd, diag, sizeof(double) * nd, cudaMemcpyHostToDevice, c->stream));
+    if (upper && nf) {
+        CUDA_TRY(c, cudaMemcpyAsync(su, upper, sizeof(double) * nf, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(sl, lower, sizeof(double) * nf, cudaMemcpyHostToDevice, c->stream));
+    } else if (nf) {
+        CUDA_TRY(c, cudaMemsetAsync(su, 0, sizeof(double) * 2 * nf, c->stream));
+    }
+    const long long nE32 = c->nEntries * 32;
+    {
+        LaunchScope ls(c, TM_PERM);
+        k_ldu_diag<<<gridFor(c->NP, 256), 256, 0, c->stream>>>(c->NP, c->d_pos2cell, block, false, c->d_diag, sd);
+        if (nE32 > 0 && nf) k_ldu_offdiag<<<gridFor(nE32, 256), 256, 0, c->stream>>>(nE32, c->d_meta, nullptr, block, c->F, false, c->d_offd, su, sl);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->matrixSet = true;
+    c->rDValid = false;
+    c->invDValid = false;
+    return 0;
+}
+
+extern "C" int icsb200_source_set(icsb200_ctx* c, const double* sRho, const double* sRhoU, const double* sRhoE)
+{
+    if (!c->meshSet) return ics_fail(c, ICSB200_ESTATE, "source_set: mesh not set");
+    int r;
+    if ((r = ics_upload_cells(c, sRho, 1, c->d_src, c->NPH))) return r;
+    if ((r = ics_upload_cells(c, sRhoU, 3, c->d_src + c->NPH, c->NPH))) return r;
+    if ((r = ics_upload_cells(c, sRhoE, 1, c->d_src + 4 * (size_t)c->NPH, c->NPH))) return r;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int icsb200_pseudo_dt(icsb200_ctx* c, double* rPseudoDeltaT, double* pseudoCo)
+{
+    // setCoAndDeltaT.H: SER update of the pseudo Courant number, then the local pseudo time step.  On the device the
+    // time-step part is fused into the Jacobian kernel (same lambda); this entry point runs both and reads the result.
+    if (!c->stateSet) return ics_fail(c, ICSB200_ESTATE, "pseudo_dt: state not set");
+    int r;
+    if ((r = ics_pseudo_ser(c))) return r;
+    if ((r = ics_gradients(c))) return r;
+    if ((r = ics_jacobian(c, false))) return r;
+    if (rPseudoDeltaT && (r = ics_download_cells(c, rPseudoDeltaT, 1, c->d_rdt, c->NP))) return r;
+    if (pseudoCo && (r = ics_download_cells(c, pseudoCo, 1, c->d_co, c->NP))) return r;
+    return 0;
+}
+
+extern "C" int icsb200_assemble(icsb200_ctx* c)
+{
+    if (!c->stateSet) return ics_fail(c, ICSB200_ESTATE, "assemble: state not set");
+    int r;
+    // piecewise use (parity API): the pseudo time step is the one left by the last pseudo_dt() call, as in the
+    // reference where createConvectiveJacobian only sees ddtCoeff (outerLoop.H:61-78)
+    if ((r = ics_gradients(c))) return r;
+    if ((r = ics_copy_prev(c))) return r;
+    if ((r = ics_jacobian(c, true))) return r;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}

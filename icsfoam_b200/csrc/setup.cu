@@ -1,0 +1,531 @@
+// setup.cu — context lifetime, mesh ingestion (level schedule, positions, sliced-ELL rows), selectors.
+//
+// Replaces, on the reference side: the lduAddressing / mesh.cells() traversal order the solver relies on
+// (lusgs.C:141-156, blockFvMatrix.C:340-380), construction of coupledMatrix storage (coupledMatrix.C:45-61,
+// re-done every outer iteration at outerLoop.H:53 — here allocated once), and run-time selection
+// (newConvectiveFluxScheme.C:39-69, coupledMatrixSolver.C:41-67, coupledMatrixPreconditioner.C:41-64).
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void k_gather_cells(const double* __restrict__ stage, int nc, const int* __restrict__ pos2cell, int NP, double* __restrict__ dst,
+                               size_t stride, double padValue)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= NP) return;
+    int c = pos2cell[p];
+    for (int k = 0; k < nc; k++) dst[k * stride + p] = (c >= 0) ? stage[(size_t)c * nc + k] : padValue;
+}
+
+__global__ void k_scatter_cells(double* __restrict__ stage, int nc, const int* __restrict__ pos2cell, int NP, const double* __restrict__ src,
+                                size_t stride)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= NP) return;
+    int c = pos2cell[p];
+    if (c < 0) return;
+    for (int k = 0; k < nc; k++) stage[(size_t)c * nc + k] = src[k * stride + p];
+}
+
+int ics_ensure_stage(icsb200_ctx* c, size_t bytes)
+{
+    if (c->stageBytes >= bytes) return 0;
+    if (c->d_stage) cudaFree(c->d_stage);
+    c->d_stage = nullptr;
+    c->stageBytes = 0;
+    CUDA_TRY(c, cudaMalloc((void**)&c->d_stage, bytes));
+    c->stageBytes = bytes;
+    return 0;
+}
+
+int ics_upload_cells(icsb200_ctx* c, const double* host, int nc, double* dst, size_t stride)
+{
+    size_t bytes = (size_t)c->N * nc * sizeof(double);
+    int r = ics_ensure_stage(c, bytes);
+    if (r) return r;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_stage, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    {
+        LaunchScope ls(c, TM_PERM);
+        k_gather_cells<<<gridFor(c->NP, 256), 256, 0, c->stream>>>(c->d_stage, nc, c->d_pos2cell, c->NP, dst, stride, 0.0);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+int ics_download_cells(icsb200_ctx* c, double* host, int nc, const double* src, size_t stride)
+{
+    size_t bytes = (size_t)c->N * nc * sizeof(double);
+    int r = ics_ensure_stage(c, bytes);
+    if (r) return r;
+    {
+        LaunchScope ls(c, TM_PERM);
+        k_scatter_cells<<<gridFor(c->NP, 256), 256, 0, c->stream>>>(c->d_stage, nc, c->d_pos2cell, c->NP, src, stride);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(host, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ lifetime
+extern "C" int icsb200_nccl_unique_id(void* out128)
+{
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return ICSB200_ECUDA;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    std::memcpy(out128, &id, 128);
+    return 0;
+}
+
+extern "C" int icsb200_create(icsb200_ctx** out, int device, const void* nccl_unique_id, int rank, int n_ranks)
+{
+    *out = nullptr;
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) return ICSB200_ECUDA;  // no CPU fallback
+    if (device < 0 || device >= nDev) return ICSB200_EINVAL;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ICSB200_ECUDA;
+    if (prop.major != 10) return ICSB200_ECUDA;  // kernels are built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return ICSB200_ECUDA;
+    icsb200_ctx* c = new icsb200_ctx;
+    c->device = device;
+    c->rank = rank;
+    c->nRanks = n_ranks;
+    c->numSMs = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ICSB200_ECUDA; }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    cudaMalloc((void**)&c->d_scal, 4096 * sizeof(double));
+    cudaMallocHost((void**)&c->h_scal, 4096 * sizeof(double));
+    cudaMalloc((void**)&c->d_partial, 64 * 4096 * sizeof(double));
+    cudaMalloc((void**)&c->d_counter, 64 * sizeof(unsigned int));
+    cudaMemset(c->d_counter, 0, 64 * sizeof(unsigned int));
+    cudaMalloc((void**)&c->d_barrier, 64 * sizeof(unsigned int));
+    cudaMemset(c->d_barrier, 0, 64 * sizeof(unsigned int));
+    if (n_ranks > 1) {
+        if (!nccl_unique_id) { delete c; return ICSB200_EINVAL; }
+        ncclUniqueId id;
+        std::memcpy(&id, nccl_unique_id, 128);
+        ncclComm_t comm;
+        if (ncclCommInitRank(&comm, n_ranks, id, rank) != ncclSuccess) { delete c; return ICSB200_ECUDA; }
+        c->nccl = comm;
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" int icsb200_destroy(icsb200_ctx* c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->nccl) ncclCommDestroy((ncclComm_t)c->nccl);
+    void* ptrs[] = {c->d_pos2cell, c->d_cell2pos, c->d_sliceOff, c->d_rowNLow, c->d_rowNInt, c->d_rowNAll, c->d_col, c->d_meta, c->d_gfid,
+                    c->d_geo, c->d_dCoupled, c->d_V, c->d_C, c->d_levStartF, c->d_levStartR, c->d_revList, c->d_bfOwnerPos, c->d_bfPatch, c->d_bfKind,
+                    c->d_bfGeo, c->d_bc, c->d_phiB, c->d_vic, c->d_sendBuf, c->d_recvBuf, c->d_fields, c->d_grad, c->d_rdt, c->d_co,
+                    c->d_ddtCoeff, c->d_Wold, c->d_Wold2, c->d_Wprev, c->d_src, c->d_dW, c->d_faceFlux, c->d_bad, c->d_offd, c->d_diag,
+                    c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
+    if (c->h_scal) cudaFreeHost(c->h_scal);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->commStream);
+    delete c;
+    return 0;
+}
+
+extern "C" const char* icsb200_last_error(icsb200_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+extern "C" long long icsb200_launch_count(icsb200_ctx* c) { return c->launches; }
+
+extern "C" int icsb200_timers_reset(icsb200_ctx* c, int enable)
+{
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < TM_COUNT; i++) { c->tms[i] = 0; c->tcalls[i] = 0; }
+    c->timing = enable != 0;
+    return 0;
+}
+
+extern "C" int icsb200_timers_get(icsb200_ctx* c, char* names_buf, int names_len, double* ms, long long* calls, int max_classes)
+{
+    int n = std::min<int>(TM_COUNT, max_classes);
+    int off = 0;
+    for (int i = 0; i < n; i++) {
+        int len = (int)std::strlen(kTimerNames[i]) + 1;
+        if (names_buf && off + len <= names_len) { std::memcpy(names_buf + off, kTimerNames[i], len); off += len; }
+        if (ms) ms[i] = c->tms[i];
+        if (calls) calls[i] = c->tcalls[i];
+    }
+    return n;
+}
+
+extern "C" int icsb200_schedule_info(icsb200_ctx* c, int out[4])
+{
+    out[0] = c->nLevF; out[1] = c->nLevR; out[2] = c->maxWidth; out[3] = c->NP;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ selectors
+extern "C" int icsb200_thermo_set(icsb200_ctx* c, double R, double Cp, double mu, double Pr)
+{
+    if (!(R > 0) || !(Cp > R)) return ics_fail(c, ICSB200_EINVAL, "thermo: need Cp > R > 0");
+    c->R = R; c->Cp = Cp; c->Cv = Cp - R; c->gamma = Cp / c->Cv; c->mu = mu; c->Pr = Pr;
+    c->thermoSet = true;
+    return 0;
+}
+
+extern "C" int icsb200_schemes_set(icsb200_ctx* c, const icsb200_schemes* s)
+{
+    // newConvectiveFluxScheme.C:56-66: unknown type is a fatal error listing the valid ones
+    if (s->flux_scheme < 0 || s->flux_scheme > ICSB200_FLUX_AUSMPLUSUP)
+        return ics_fail(c, ICSB200_EINVAL, "Unknown convectiveFluxScheme type; valid types are: AUSMPlusUp HLLC ROE");
+    for (int l : {s->limiter_rho, s->limiter_U, s->limiter_T})
+        if (l < 0 || l > ICSB200_LIM_LINEAR) return ics_fail(c, ICSB200_EINVAL, "unknown interpolation scheme for reconstruct(.)");
+    if (s->ddt_scheme < 0 || s->ddt_scheme > ICSB200_DDT_BACKWARD) return ics_fail(c, ICSB200_EINVAL, "unknown ddt scheme");
+    if (s->ddt_scheme != ICSB200_DDT_STEADY && !(s->delta_t > 0)) return ics_fail(c, ICSB200_EINVAL, "transient run needs delta_t > 0");
+    c->sch = *s;
+    c->pseudoCoNum = s->pseudo_co_num;
+    return 0;
+}
+
+extern "C" int icsb200_bc_set(icsb200_ctx* c, int patch, int field, int kind, const double* params, int n_params)
+{
+    if (!c->meshSet) return ics_fail(c, ICSB200_ESTATE, "bc_set: mesh not set");
+    if (patch < 0 || patch >= (int)c->patches.size() || field < 0 || field > 2 || n_params < 0 || n_params > 8 || kind < 0 ||
+        kind > ICSB200_BC_COUPLED)
+        return ics_fail(c, ICSB200_EINVAL, "bc_set: bad argument");
+    c->h_bc[patch].kind[field] = kind;
+    for (int i = 0; i < 8; i++) c->h_bc[patch].prm[field][i] = i < n_params ? params[i] : 0.0;
+    CUDA_TRY(c, cudaMemcpy(c->d_bc, c->h_bc.data(), sizeof(BCDev) * c->h_bc.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ mesh
+extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int* owner, const int* neighbour, const double* Sf,
+                                const double* magSf, const double* weights, const double* deltaCoeffs, const double* nonOrthDeltaCoeffs,
+                                const double* C, const double* V, const double* Cf, int n_patches, const icsb200_patch* patches,
+                                const int solutionD[3])
+{
+    if (N <= 0 || F < 0 || FT < F) return ics_fail(c, ICSB200_EINVAL, "mesh_set: bad sizes");
+    cudaSetDevice(c->device);
+    for (int f = 0; f < F; f++)
+        if (owner[f] >= neighbour[f] || owner[f] < 0 || neighbour[f] >= N)
+            return ics_fail(c, ICSB200_EINVAL, "mesh_set: faces must be in upper-triangular order (owner < neighbour)");
+    c->N = N; c->F = F; c->FT = FT; c->NB = FT - F;
+    c->owner.assign(owner, owner + FT);
+    c->neighbour.assign(neighbour, neighbour + F);
+    c->patches.assign(patches, patches + n_patches);
+    for (int d = 0; d < 3; d++) c->solutionD[d] = solutionD[d];
+    const int NB = c->NB;
+    c->bfacePatch.assign(NB, -1);
+    for (int pi = 0; pi < n_patches; pi++) {
+        const icsb200_patch& p = patches[pi];
+        if (p.start < F || p.start + p.size > FT) return ics_fail(c, ICSB200_EINVAL, "mesh_set: patch range outside boundary faces");
+        if ((p.kind == ICSB200_CYCLIC) && (p.nbr_patch < 0 || p.nbr_patch >= n_patches || patches[p.nbr_patch].size != p.size))
+            return ics_fail(c, ICSB200_EINVAL, "mesh_set: cyclic patch without a matching neighbour patch");
+        if (p.kind == ICSB200_PROCESSOR && (p.nbr_rank < 0 || p.nbr_rank >= c->nRanks || c->nRanks == 1))
+            return ics_fail(c, ICSB200_EINVAL, "mesh_set: processor patch needs a multi-rank context");
+        if ((p.kind == ICSB200_CYCLIC || p.kind == ICSB200_PROCESSOR) && !Cf) return ics_fail(c, ICSB200_EINVAL, "mesh_set: coupled patches need Cf");
+        if (p.kind != ICSB200_EMPTY) for (int f = p.start; f < p.start + p.size; f++) c->bfacePatch[f - F] = pi;
+    }
+
+    // ---- LU-SGS level schedule (forward: longest path from below; reverse: longest path from above)
+    std::vector<int> levF(N, 0), levR(N, 0);
+    for (int f = 0; f < F; f++) levF[neighbour[f]] = std::max(levF[neighbour[f]], levF[owner[f]] + 1);
+    for (int f = F - 1; f >= 0; f--) levR[owner[f]] = std::max(levR[owner[f]], levR[neighbour[f]] + 1);
+    int nLevF = 0, nLevR = 0;
+    for (int i = 0; i < N; i++) { nLevF = std::max(nLevF, levF[i] + 1); nLevR = std::max(nLevR, levR[i] + 1); }
+    c->nLevF = nLevF; c->nLevR = nLevR;
+    std::vector<int> cntF(nLevF + 1, 0);
+    for (int i = 0; i < N; i++) cntF[levF[i] + 1]++;
+    std::vector<int> levStartF(nLevF + 1, 0);
+    c->maxWidth = 0;
+    for (int l = 0; l < nLevF; l++) {
+        levStartF[l + 1] = levStartF[l] + ((cntF[l + 1] + 31) / 32) * 32;
+        c->maxWidth = std::max(c->maxWidth, cntF[l + 1]);
+    }
+    const int NP = levStartF[nLevF];
+    c->NP = NP;
+    c->pos2cell.assign(NP, -1);
+    c->cell2pos.assign(N, -1);
+    {
+        std::vector<int> fill(levStartF.begin(), levStartF.end() - 1);
+        for (int i = 0; i < N; i++) { int p = fill[levF[i]]++; c->pos2cell[p] = i; c->cell2pos[i] = p; }
+    }
+    // reverse level lists of positions (ascending position inside a level)
+    std::vector<int> levStartR(nLevR + 1, 0), revList(N);
+    {
+        std::vector<int> cnt(nLevR + 1, 0);
+        for (int i = 0; i < N; i++) cnt[levR[i] + 1]++;
+        for (int l = 0; l < nLevR; l++) levStartR[l + 1] = levStartR[l] + cnt[l + 1];
+        std::vector<int> fill(levStartR.begin(), levStartR.end() - 1);
+        for (int p = 0; p < NP; p++) { int i = c->pos2cell[p]; if (i >= 0) revList[fill[levR[i]]++] = p; }
+    }
+
+    // ---- halo slots for processor patches
+    c->procs.clear();
+    int NH = 0;
+    std::vector<int> patchHaloStart(n_patches, -1);
+    for (int pi = 0; pi < n_patches; pi++)
+        if (patches[pi].kind == ICSB200_PROCESSOR) { patchHaloStart[pi] = NH; NH += patches[pi].size; }
+    c->NH = NH; c->NPH = NP + NH; c->NX = NP + NH + NB;
+
+    // ---- rows: faces of each cell in ascending face id
+    std::vector<int> nLowC(N, 0), nUpC(N, 0), nBndC(N, 0);
+    for (int f = 0; f < F; f++) { nLowC[neighbour[f]]++; nUpC[owner[f]]++; }
+    for (int b = 0; b < NB; b++) if (c->bfacePatch[b] >= 0) nBndC[owner[F + b]]++;
+    const int nSlices = NP / 32;
+    c->nSlices = nSlices;
+    c->h_sliceOff.assign(nSlices + 1, 0);
+    c->h_rowNLow.assign(NP, 0); c->h_rowNInt.assign(NP, 0); c->h_rowNAll.assign(NP, 0);
+    for (int s = 0; s < nSlices; s++) {
+        int w = 0;
+        for (int l = 0; l < 32; l++) {
+            int p = s * 32 + l, i = c->pos2cell[p];
+            if (i < 0) continue;
+            c->h_rowNLow[p] = nLowC[i];
+            c->h_rowNInt[p] = nLowC[i] + nUpC[i];
+            c->h_rowNAll[p] = nLowC[i] + nUpC[i] + nBndC[i];
+            w = std::max(w, c->h_rowNAll[p]);
+        }
+        c->h_sliceOff[s + 1] = c->h_sliceOff[s] + w;
+    }
+    c->nEntries = c->h_sliceOff[nSlices];
+    const size_t nE32 = (size_t)c->nEntries * 32;
+    if (nE32 * 25 > (size_t)1 << 40) return ics_fail(c, ICSB200_EINVAL, "mesh too large");
+    c->h_col.assign(nE32, -1); c->h_meta.assign(nE32, ET_PHYS); c->h_gfid.assign(nE32, -1);
+    {
+        std::vector<int> fillLow(N, 0), fillUp(N, 0), fillB(N, 0);
+        auto slot = [&](int p, int j) { return ((size_t)c->h_sliceOff[p / 32] + j) * 32 + (p % 32); };
+        for (int f = 0; f < F; f++) {
+            int o = owner[f], n = neighbour[f];
+            int pn = c->cell2pos[n], po = c->cell2pos[o];
+            size_t sl = slot(pn, fillLow[n]++);
+            c->h_col[sl] = po; c->h_meta[sl] = ET_LOWER | (f << 2);
+            size_t su = slot(po, nLowC[o] + fillUp[o]++);
+            c->h_col[su] = pn; c->h_meta[su] = ET_UPPER | (f << 2);
+        }
+        for (int b = 0; b < NB; b++) {
+            int pi = c->bfacePatch[b];
+            if (pi < 0) continue;
+            int f = F + b, o = owner[f], po = c->cell2pos[o];
+            size_t sb = slot(po, nLowC[o] + nUpC[o] + fillB[o]++);
+            const icsb200_patch& pa = patches[pi];
+            if (pa.kind == ICSB200_CYCLIC) {
+                int nbrFace = patches[pa.nbr_patch].start + (f - pa.start);
+                c->h_col[sb] = c->cell2pos[owner[nbrFace]];
+                c->h_meta[sb] = ET_COUPLED | (f << 2);
+            } else if (pa.kind == ICSB200_PROCESSOR) {
+                c->h_col[sb] = NP + patchHaloStart[pi] + (f - pa.start);
+                c->h_meta[sb] = ET_COUPLED | (f << 2);
+            } else {
+                c->h_col[sb] = NP + NH + b;  // boundary-value slot
+                c->h_meta[sb] = ET_PHYS | (f << 2);
+            }
+        }
+    }
+    // GPU face ids: owner-side entries in (slice, j, lane) order
+    std::vector<int> ref2gf(FT, -1);
+    c->h_gf2ref.clear();
+    c->h_gf2ref.reserve((size_t)F + NB);
+    for (int s = 0; s < nSlices; s++) {
+        int w = c->h_sliceOff[s + 1] - c->h_sliceOff[s];
+        for (int j = 0; j < w; j++)
+            for (int l = 0; l < 32; l++) {
+                int p = s * 32 + l;
+                if (j >= c->h_rowNAll[p] || j < c->h_rowNLow[p]) continue;
+                size_t sl = ((size_t)c->h_sliceOff[s] + j) * 32 + l;
+                int f = c->h_meta[sl] >> 2;
+                ref2gf[f] = (int)c->h_gf2ref.size();
+                c->h_gf2ref.push_back(f);
+            }
+    }
+    c->NFG = (int)c->h_gf2ref.size();
+    for (int s = 0; s < nSlices; s++) {
+        int w = c->h_sliceOff[s + 1] - c->h_sliceOff[s];
+        for (int j = 0; j < w; j++)
+            for (int l = 0; l < 32; l++) {
+                int p = s * 32 + l;
+                if (j >= c->h_rowNAll[p]) continue;
+                size_t sl = ((size_t)c->h_sliceOff[s] + j) * 32 + l;
+                c->h_gfid[sl] = ref2gf[c->h_meta[sl] >> 2];
+            }
+    }
+    // face geometry in GPU face order
+    const int NFG = c->NFG;
+    std::vector<double> geo((size_t)NG * NFG);
+    for (int g = 0; g < NFG; g++) {
+        int f = c->h_gf2ref[g];
+        geo[(size_t)G_SFX * NFG + g] = Sf[3 * (size_t)f];
+        geo[(size_t)G_SFY * NFG + g] = Sf[3 * (size_t)f + 1];
+        geo[(size_t)G_SFZ * NFG + g] = Sf[3 * (size_t)f + 2];
+        geo[(size_t)G_MAGSF * NFG + g] = magSf[f];
+        geo[(size_t)G_W * NFG + g] = weights[f];
+        geo[(size_t)G_NONORTH * NFG + g] = nonOrthDeltaCoeffs[f];
+        geo[(size_t)G_DELTA * NFG + g] = deltaCoeffs[f];
+    }
+    // cell centres / volumes in position order
+    const int NPH = c->NPH;
+    std::vector<double> Cp3((size_t)3 * NPH, 0.0), Vp(NP, 1.0);
+    for (int p = 0; p < NP; p++) {
+        int i = c->pos2cell[p];
+        if (i < 0) continue;
+        for (int d = 0; d < 3; d++) Cp3[(size_t)d * NPH + p] = C[3 * (size_t)i + d];
+        Vp[p] = V[i];
+    }
+    // boundary faces
+    std::vector<int> bfOwnerPos(NB, -1);
+    std::vector<double> bfGeo((size_t)4 * std::max(NB, 1), 0.0), dCoupled((size_t)3 * std::max(NB, 1), 0.0);
+    for (int b = 0; b < NB; b++) {
+        if (c->bfacePatch[b] < 0) continue;
+        int f = F + b;
+        bfOwnerPos[b] = c->cell2pos[owner[f]];
+        for (int d = 0; d < 3; d++) bfGeo[(size_t)d * NB + b] = Sf[3 * (size_t)f + d];
+        bfGeo[(size_t)3 * NB + b] = magSf[f];
+    }
+    // coupled deltas (cyclic: own delta - neighbour-patch delta; processor: exchanged below)
+    std::vector<double> ownDelta((size_t)3 * std::max(NB, 1), 0.0);
+    for (int pi = 0; pi < n_patches; pi++) {
+        const icsb200_patch& pa = patches[pi];
+        if (pa.kind != ICSB200_CYCLIC && pa.kind != ICSB200_PROCESSOR) continue;
+        for (int f = pa.start; f < pa.start + pa.size; f++)
+            for (int d = 0; d < 3; d++) ownDelta[3 * (size_t)(f - F) + d] = Cf[3 * (size_t)f + d] - C[3 * (size_t)owner[f] + d];
+    }
+    std::vector<double> nbrDelta(ownDelta.size(), 0.0);
+    for (int pi = 0; pi < n_patches; pi++) {
+        const icsb200_patch& pa = patches[pi];
+        if (pa.kind == ICSB200_CYCLIC) {
+            const icsb200_patch& qa = patches[pa.nbr_patch];
+            for (int i = 0; i < pa.size; i++)
+                for (int d = 0; d < 3; d++) nbrDelta[3 * (size_t)(pa.start + i - F) + d] = ownDelta[3 * (size_t)(qa.start + i - F) + d];
+        }
+    }
+    if (NH > 0) {
+        // exchange processor-patch deltas through NCCL (device staging)
+        double *dS = nullptr, *dR = nullptr;
+        CUDA_TRY(c, cudaMalloc((void**)&dS, sizeof(double) * 3 * NH));
+        CUDA_TRY(c, cudaMalloc((void**)&dR, sizeof(double) * 3 * NH));
+        std::vector<double> sendv((size_t)3 * NH), recvv((size_t)3 * NH);
+        for (int pi = 0; pi < n_patches; pi++) {
+            if (patches[pi].kind != ICSB200_PROCESSOR) continue;
+            for (int i = 0; i < patches[pi].size; i++)
+                for (int d = 0; d < 3; d++) sendv[3 * (size_t)(patchHaloStart[pi] + i) + d] = ownDelta[3 * (size_t)(patches[pi].start + i - F) + d];
+        }
+        CUDA_TRY(c, cudaMemcpy(dS, sendv.data(), sizeof(double) * 3 * NH, cudaMemcpyHostToDevice));
+        ncclGroupStart();
+        for (int pi = 0; pi < n_patches; pi++) {
+            if (patches[pi].kind != ICSB200_PROCESSOR) continue;
+            ncclSend(dS + 3 * (size_t)patchHaloStart[pi], 3 * (size_t)patches[pi].size, ncclDouble, patches[pi].nbr_rank, (ncclComm_t)c->nccl, c->stream);
+            ncclRecv(dR + 3 * (size_t)patchHaloStart[pi], 3 * (size_t)patches[pi].size, ncclDouble, patches[pi].nbr_rank, (ncclComm_t)c->nccl, c->stream);
+        }
+        ncclGroupEnd();
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        CUDA_TRY(c, cudaMemcpy(recvv.data(), dR, sizeof(double) * 3 * NH, cudaMemcpyDeviceToHost));
+        cudaFree(dS); cudaFree(dR);
+        for (int pi = 0; pi < n_patches; pi++) {
+            if (patches[pi].kind != ICSB200_PROCESSOR) continue;
+            for (int i = 0; i < patches[pi].size; i++)
+                for (int d = 0; d < 3; d++) nbrDelta[3 * (size_t)(patches[pi].start + i - F) + d] = recvv[3 * (size_t)(patchHaloStart[pi] + i) + d];
+        }
+    }
+    for (int b = 0; b < NB; b++)
+        for (int d = 0; d < 3; d++) dCoupled[(size_t)d * NB + b] = ownDelta[3 * (size_t)b + d] - nbrDelta[3 * (size_t)b + d];
+
+    // ---- uploads
+    int r = 0;
+    r |= devUpload(c, &c->d_pos2cell, c->pos2cell);
+    r |= devUpload(c, &c->d_cell2pos, c->cell2pos);
+    r |= devUpload(c, &c->d_sliceOff, c->h_sliceOff);
+    r |= devUpload(c, &c->d_rowNLow, c->h_rowNLow);
+    r |= devUpload(c, &c->d_rowNInt, c->h_rowNInt);
+    r |= devUpload(c, &c->d_rowNAll, c->h_rowNAll);
+    r |= devUpload(c, &c->d_col, c->h_col);
+    r |= devUpload(c, &c->d_meta, c->h_meta);
+    r |= devUpload(c, &c->d_gfid, c->h_gfid);
+    r |= devUpload(c, &c->d_geo, geo);
+    r |= devUpload(c, &c->d_dCoupled, dCoupled);
+    r |= devUpload(c, &c->d_V, Vp);
+    r |= devUpload(c, &c->d_C, Cp3);
+    r |= devUpload(c, &c->d_levStartF, levStartF);
+    r |= devUpload(c, &c->d_levStartR, levStartR);
+    r |= devUpload(c, &c->d_revList, revList);
+    r |= devUpload(c, &c->d_bfOwnerPos, bfOwnerPos);
+    r |= devUpload(c, &c->d_bfPatch, c->bfacePatch);
+    {
+        std::vector<int> bfKind(NB, -1);
+        for (int b = 0; b < NB; b++) if (c->bfacePatch[b] >= 0) bfKind[b] = patches[c->bfacePatch[b]].kind;
+        r |= devUpload(c, &c->d_bfKind, bfKind);
+    }
+    r |= devUpload(c, &c->d_bfGeo, bfGeo);
+    if (r) return r;
+    // the big host index arrays are no longer needed except the row bookkeeping used by matrix get/set
+    // processor patches: send lists
+    for (int pi = 0; pi < n_patches; pi++) {
+        if (patches[pi].kind != ICSB200_PROCESSOR) continue;
+        ProcPatchDev pp;
+        pp.nbrRank = patches[pi].nbr_rank; pp.size = patches[pi].size; pp.haloStart = patchHaloStart[pi]; pp.d_sendPos = nullptr;
+        std::vector<int> sp(pp.size);
+        for (int i = 0; i < pp.size; i++) sp[i] = c->cell2pos[owner[patches[pi].start + i]];
+        r |= devUpload(c, &pp.d_sendPos, sp);
+        c->procs.push_back(pp);
+    }
+    if (NH > 0) {
+        r |= devAlloc(c, &c->d_sendBuf, (size_t)NH * 40);
+        r |= devAlloc(c, &c->d_recvBuf, (size_t)NH * 40);
+    }
+    // halo centres are never read (coupled faces use dCoupled)
+    // ---- BCs default: zeroGradient on physical patches
+    c->h_bc.assign(n_patches, BCDev{});
+    for (int pi = 0; pi < n_patches; pi++) {
+        int k = (patches[pi].kind == ICSB200_CYCLIC || patches[pi].kind == ICSB200_PROCESSOR) ? ICSB200_BC_COUPLED
+                : patches[pi].kind == ICSB200_EMPTY ? ICSB200_BC_EMPTY : ICSB200_BC_ZEROGRADIENT;
+        for (int fl = 0; fl < 3; fl++) c->h_bc[pi].kind[fl] = k;
+    }
+    r |= devUpload(c, &c->d_bc, c->h_bc);
+    // ---- field storage
+    const size_t NX = c->NX;
+    r |= devAlloc(c, &c->d_fields, (size_t)Q_COUNT * NX);
+    r |= devAlloc(c, &c->d_grad, (size_t)NQ * 3 * NPH);
+    r |= devAlloc(c, &c->d_rdt, (size_t)NP);
+    r |= devAlloc(c, &c->d_co, (size_t)NP);
+    r |= devAlloc(c, &c->d_ddtCoeff, (size_t)NP);
+    r |= devAlloc(c, &c->d_Wold, (size_t)5 * NP);
+    r |= devAlloc(c, &c->d_Wold2, (size_t)5 * NP);
+    r |= devAlloc(c, &c->d_Wprev, (size_t)5 * NPH);
+    r |= devAlloc(c, &c->d_src, (size_t)5 * NPH);
+    r |= devAlloc(c, &c->d_dW, (size_t)5 * NPH);
+    r |= devAlloc(c, &c->d_bad, (size_t)NPH);
+    r |= devAlloc(c, &c->d_phiB, (size_t)std::max(NB, 1));
+    r |= devAlloc(c, &c->d_vic, (size_t)5 * std::max(NB, 1));
+    r |= devAlloc(c, &c->d_offd, nE32 * 25);
+    r |= devAlloc(c, &c->d_diag, (size_t)25 * NP);
+    r |= devAlloc(c, &c->d_rD, (size_t)NP);
+    r |= devAlloc(c, &c->d_w, (size_t)5 * NPH);
+    r |= devAlloc(c, &c->d_x, (size_t)5 * NPH);
+    if (r) return r;
+    CUDA_TRY(c, cudaMemset(c->d_fields, 0, sizeof(double) * Q_COUNT * NX));
+    CUDA_TRY(c, cudaMemset(c->d_grad, 0, sizeof(double) * NQ * 3 * NPH));
+    CUDA_TRY(c, cudaMemset(c->d_offd, 0, sizeof(double) * nE32 * 25));
+    CUDA_TRY(c, cudaMemset(c->d_diag, 0, sizeof(double) * 25 * NP));
+    CUDA_TRY(c, cudaMemset(c->d_src, 0, sizeof(double) * 5 * NPH));
+    CUDA_TRY(c, cudaMemset(c->d_dW, 0, sizeof(double) * 5 * NPH));
+    CUDA_TRY(c, cudaMemset(c->d_Wprev, 0, sizeof(double) * 5 * NPH));
+    CUDA_TRY(c, cudaMemset(c->d_w, 0, sizeof(double) * 5 * NPH));
+    CUDA_TRY(c, cudaMemset(c->d_x, 0, sizeof(double) * 5 * NPH));
+    CUDA_TRY(c, cudaMemset(c->d_rdt, 0, sizeof(double) * NP));
+    CUDA_TRY(c, cudaMemset(c->d_phiB, 0, sizeof(double) * std::max(NB, 1)));
+    CUDA_TRY(c, cudaMemset(c->d_vic, 0, sizeof(double) * 5 * std::max(NB, 1)));
+    CUDA_TRY(c, cudaMemset(c->d_bad, 0, sizeof(int) * NPH));
+    c->meshSet = true;
+    c->stateSet = c->matrixSet = c->fluxValid = false;
+    return 0;
+}
