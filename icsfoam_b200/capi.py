@@ -140,6 +140,8 @@ PRODUCT_SIGNATURES = {
     "timers_get": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, _dp, C.POINTER(C.c_longlong), C.c_int]),
     "timers_reset": (C.c_int, [C.c_void_p, C.c_int]),
     "schedule_info": (C.c_int, [C.c_void_p, _ip]),
+    "timer_begin": (C.c_int, [C.c_void_p]),
+    "timer_end": (C.c_int, [C.c_void_p, _dp]),
 }
 
 BLOCK_NC = [1, 1, 1, 1, 3, 3, 3, 3, 9]

@@ -71,6 +71,14 @@ class Context(capi.Api):
         nm = names.raw.split(b"\0")[:n]
         return {nm[i].decode(): (ms[i], int(calls[i])) for i in range(n)}
 
+    def timer_begin(self):
+        self._call("timer_begin")
+
+    def timer_end(self):
+        ms = C.c_double()
+        self._call("timer_end", C.byref(ms))
+        return ms.value
+
     def schedule_info(self):
         out = (C.c_int * 4)()
         self._call("schedule_info", out)

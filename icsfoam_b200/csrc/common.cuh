@@ -139,6 +139,9 @@ struct icsb200_ctx {
     unsigned int* d_counter = nullptr;
     unsigned int* d_barrier = nullptr;
     int lusgsGrid = 0;
+    double* d_lusgsYZ = nullptr;  // [2][5*NPH] forward / reverse sweep values (sentinel protocol)
+    int* d_lusgsHint = nullptr;   // [2*nSlices] publication hints
+    int lusgsEpoch = 0;
     // staging
     double* d_stage = nullptr;
     size_t stageBytes = 0;
@@ -149,7 +152,7 @@ struct icsb200_ctx {
     bool timing = false;
     double tms[TM_COUNT] = {0};
     long long tcalls[TM_COUNT] = {0};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
 
     double* q(int id) const { return d_fields + (size_t)id * NX; }
     double* grad(int qi, int d) const { return d_grad + (size_t)(qi * 3 + d) * NPH; }

@@ -101,6 +101,8 @@ extern "C" int icsb200_create(icsb200_ctx** out, int device, const void* nccl_un
         cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ICSB200_ECUDA; }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    cudaEventCreate(&c->evA);
+    cudaEventCreate(&c->evB);
     cudaMalloc((void**)&c->d_scal, 4096 * sizeof(double));
     cudaMallocHost((void**)&c->h_scal, 4096 * sizeof(double));
     cudaMalloc((void**)&c->d_partial, 64 * 4096 * sizeof(double));
@@ -130,13 +132,15 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
                     c->d_geo, c->d_dCoupled, c->d_V, c->d_C, c->d_levStartF, c->d_levStartR, c->d_revList, c->d_bfOwnerPos, c->d_bfPatch, c->d_bfKind,
                     c->d_bfGeo, c->d_bc, c->d_phiB, c->d_vic, c->d_sendBuf, c->d_recvBuf, c->d_fields, c->d_grad, c->d_rdt, c->d_co,
                     c->d_ddtCoeff, c->d_Wold, c->d_Wold2, c->d_Wprev, c->d_src, c->d_dW, c->d_faceFlux, c->d_bad, c->d_offd, c->d_diag,
-                    c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage};
+                    c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage, c->d_lusgsYZ, c->d_lusgsHint};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->evA);
+    cudaEventDestroy(c->evB);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->commStream);
     delete c;
@@ -166,6 +170,23 @@ extern "C" int icsb200_timers_get(icsb200_ctx* c, char* names_buf, int names_len
         if (calls) calls[i] = c->tcalls[i];
     }
     return n;
+}
+
+extern "C" int icsb200_timer_begin(icsb200_ctx* c)
+{
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaEventRecord(c->evA, c->stream));
+    return 0;
+}
+
+extern "C" int icsb200_timer_end(icsb200_ctx* c, double* elapsed_ms)
+{
+    CUDA_TRY(c, cudaEventRecord(c->evB, c->stream));
+    CUDA_TRY(c, cudaEventSynchronize(c->evB));
+    float ms = 0;
+    CUDA_TRY(c, cudaEventElapsedTime(&ms, c->evA, c->evB));
+    *elapsed_ms = ms;
+    return 0;
 }
 
 extern "C" int icsb200_schedule_info(icsb200_ctx* c, int out[4])
@@ -522,9 +543,13 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     CUDA_TRY(c, cudaMemset(c->d_w, 0, sizeof(double) * 5 * NPH));
     CUDA_TRY(c, cudaMemset(c->d_x, 0, sizeof(double) * 5 * NPH));
     CUDA_TRY(c, cudaMemset(c->d_rdt, 0, sizeof(double) * NP));
+    CUDA_TRY(c, cudaMemset(c->d_rD, 0, sizeof(double) * NP));
+    CUDA_TRY(c, cudaMemset(c->d_co, 0, sizeof(double) * NP));
+    CUDA_TRY(c, cudaMemset(c->d_ddtCoeff, 0, sizeof(double) * NP));
     CUDA_TRY(c, cudaMemset(c->d_phiB, 0, sizeof(double) * std::max(NB, 1)));
     CUDA_TRY(c, cudaMemset(c->d_vic, 0, sizeof(double) * 5 * std::max(NB, 1)));
     CUDA_TRY(c, cudaMemset(c->d_bad, 0, sizeof(int) * NPH));
+    c->lusgsGrid = 0;
     c->meshSet = true;
     c->stateSet = c->matrixSet = c->fluxValid = false;
     return 0;

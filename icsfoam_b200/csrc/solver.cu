@@ -122,93 +122,185 @@ k_spmv(int NP, const int* __restrict__ pos2cell, const int* __restrict__ sliceOf
 }
 
 // ------------------------------------------------------------------------------------------------ LU-SGS
-__device__ __forceinline__ void gridBarrier(unsigned int* counter, unsigned int& target, unsigned int nBlocks)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += nBlocks;
-        __threadfence();
-        atomicAdd(counter, 1u);
-        while (*((volatile unsigned int*)counter) < target) { }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
+// Exact Gauss-Seidel order of lusgs.C:220-382 without barriers and without flags.
+// Positions are sorted by forward level, so every lower neighbour of a row lives in a LOWER slice (32 rows = one warp)
+// and every upper neighbour in a HIGHER slice.  Warps take slices round-robin in sweep order (ascending for the
+// forward sweep, descending for the reverse sweep).  The sweep outputs go to two buffers pre-filled with a sentinel
+// bit pattern (a quiet NaN payload no arithmetic can produce): a producer simply stores its 5 values, a consumer
+// polls the neighbour's values until none is the sentinel — the data is its own flag (8-byte stores are atomic), so a
+// dependency hop costs one store + one L2 round trip, with no fence.  All warps are co-resident (cooperative launch)
+// and each walks its slices in dependency order, hence no deadlock; independent levels overlap freely, so a sweep
+// costs max(bandwidth, longest dependency chain x hop latency) instead of levels x grid-barrier.
 struct LusgsArgs {
-    int NP, nLevF, nLevR;
-    const int *pos2cell, *sliceOff, *rowNLow, *rowNInt, *col, *levStartF, *levStartR, *revList;
+    int nSlices;
+    const int *sliceOff, *rowNLow, *rowNInt, *col;
     const double *offd, *rD;
-    double* x;
+    double* x;         // in: right-hand side, out: preconditioned vector
+    double *y, *z;     // forward / reverse sweep values, sentinel-filled before launch
     size_t NPH;
-    unsigned int* barrier;
+    int* err;
+    int *hintF, *hintR;  // per-slice "probably published" epochs: cheap to poll; correctness comes from the sentinel check
+    int epoch;
 };
 
-__device__ __forceinline__ void lusgsSub(double* xr, const double* __restrict__ blk, const double* dl)
+constexpr unsigned long long LUSGS_SENTINEL = 0xFFF8DEADBEEF0B1DULL;
+
+__device__ __forceinline__ double ldPoll(const double* p)
+{
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool isSentinel(double v) { return (unsigned long long)__double_as_longlong(v) == LUSGS_SENTINEL; }
+
+__device__ __forceinline__ int ldHint(const int* p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// wait until the 5 components of position q in buffer buf have been published: spin on the slice hint (1 sector per
+// warp poll), then read the values and make sure none is still the sentinel
+__device__ __forceinline__ void pollVec(const double* buf, const int* hint, int epoch, size_t NPH, int q, double* out, int* err)
+{
+    unsigned int spins = 0;
+    const int* h = hint + (q >> 5);
+    while (true) {
+        if (ldHint(h) == epoch) {
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 5; k++) { out[k] = ldPoll(buf + k * NPH + q); ok &= !isSentinel(out[k]); }
+            if (ok) return;
+        }
+        if (++spins > (1u << 24)) { *err = 1; return; }  // never hang the device on a broken schedule
+        if (spins > 64) __nanosleep(100);
+    }
+}
+
+// one neighbour contribution with the block already in registers
+__device__ __forceinline__ void lusgsSubReg(double* xr, const double* B, const double* dl)
 {
 #pragma unroll
     for (int r = 0; r < 5; r++) {
-        const double b0 = __ldcs(blk + (size_t)(r * 5 + 0) * 32), b1 = __ldcs(blk + (size_t)(r * 5 + 1) * 32), b2 = __ldcs(blk + (size_t)(r * 5 + 2) * 32),
-                     b3 = __ldcs(blk + (size_t)(r * 5 + 3) * 32), b4 = __ldcs(blk + (size_t)(r * 5 + 4) * 32);
         // sub-block order of lusgs.C:240-303: S.S (rho col, rhoE col) then S.V / V.S then V.V, one subtraction each
-        xr[r] -= b0 * dl[0];
-        xr[r] -= b4 * dl[4];
-        xr[r] -= b1 * dl[1] + b2 * dl[2] + b3 * dl[3];
+        xr[r] -= B[r * 5 + 0] * dl[0];
+        xr[r] -= B[r * 5 + 4] * dl[4];
+        xr[r] -= B[r * 5 + 1] * dl[1] + B[r * 5 + 2] * dl[2] + B[r * 5 + 3] * dl[3];
     }
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int LCH = 3;  // neighbours handled per chunk (hex cells have at most 3 lower and 3 upper neighbours)
+
+// entries [jBeg, jEnd) of row p (ascending if FWD, descending otherwise): everything that does not depend on the sweep
+// values (column, rD, 5x5 block) is fetched BEFORE polling, so the dependent part of a hop is poll -> 75 flops -> store
+template <bool FWD>
+__device__ __forceinline__ void lusgsRow(const LusgsArgs& a, int lane, size_t base, int jBeg, int jEnd, double* xr)
+{
+    const int n = jEnd - jBeg;
+    const double* buf = FWD ? a.y : a.z;
+    const int* hint = FWD ? a.hintF : a.hintR;
+    for (int c0 = 0; c0 < n; c0 += LCH) {
+        double B[LCH][25], scale[LCH], dl[LCH][5];
+        int q[LCH];
+        unsigned int pend = 0;
+#pragma unroll
+        for (int t = 0; t < LCH; t++) {
+            q[t] = 0;
+            if (c0 + t < n) {
+                const int j = FWD ? (jBeg + c0 + t) : (jEnd - 1 - c0 - t);
+                q[t] = a.col[(base + j) * 32 + lane];
+                scale[t] = FWD ? a.rD[q[t]] : 1.0;
+                const double* blk = a.offd + ((base + j) * 25) * 32 + lane;
+#pragma unroll
+                for (int k = 0; k < 25; k++) B[t][k] = __ldcs(blk + (size_t)k * 32);
+                pend |= 1u << t;
+            }
+        }
+        const unsigned int want = pend;
+        // wait for all neighbours of the chunk at once: hint loads in flight together, then the value loads together
+        unsigned int spins = 0;
+        while (pend) {
+            int hv[LCH];
+#pragma unroll
+            for (int t = 0; t < LCH; t++) hv[t] = (pend >> t & 1u) ? ldHint(hint + (q[t] >> 5)) : 0;
+            unsigned int ready = 0;
+#pragma unroll
+            for (int t = 0; t < LCH; t++)
+                if ((pend >> t & 1u) && hv[t] == a.epoch) {
+                    ready |= 1u << t;
+#pragma unroll
+                    for (int k = 0; k < 5; k++) dl[t][k] = ldPoll(buf + k * a.NPH + q[t]);
+                }
+#pragma unroll
+            for (int t = 0; t < LCH; t++)
+                if (ready >> t & 1u) {
+                    bool ok = true;
+#pragma unroll
+                    for (int k = 0; k < 5; k++) ok &= !isSentinel(dl[t][k]);
+                    if (ok) pend &= ~(1u << t);
+                }
+            if (pend) {
+                if (++spins > (1u << 24)) { *a.err = 1; break; }  // never hang the device on a broken schedule
+                if (spins > 64) __nanosleep(100);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < LCH; t++)
+            if (want >> t & 1u) {
+                if (FWD) {
+#pragma unroll
+                    for (int k = 0; k < 5; k++) dl[t][k] = scale[t] * dl[t][k];  // dW*_q = rD_q x_q (lusgs.C:194-216)
+                }
+                lusgsSubReg(xr, B[t], dl[t]);
+            }
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
 k_lusgs(LusgsArgs a)
 {
-    const unsigned int nBlocks = gridDim.x;
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
-    unsigned int target = 0;
-    // forward sweep: D dW* = R - L dW*   (rows of level 0 have no lower neighbours)
-    for (int L = 1; L < a.nLevF; L++) {
-        for (int p = a.levStartF[L] + gtid; p < a.levStartF[L + 1]; p += gsize) {
-            if (a.pos2cell[p] < 0) continue;
-            const int lane = p & 31;
-            const size_t base = (size_t)a.sliceOff[p >> 5];
-            double xr[5];
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, W = (gridDim.x * blockDim.x) >> 5;
+    // forward sweep: D dW* = R - L dW*  (y keeps the un-scaled running value, lusgs.C:233-237)
+    for (int s = gw; s < a.nSlices; s += W) {
+        const int p = s * 32 + lane;
+        const size_t base = (size_t)a.sliceOff[s];
+        const int nLow = a.rowNLow[p];
+        double xr[5];
 #pragma unroll
-            for (int k = 0; k < 5; k++) xr[k] = __ldcg(a.x + k * a.NPH + p);
-            const int nLow = a.rowNLow[p];
-            for (int j = 0; j < nLow; j++) {
-                const int q = a.col[(base + j) * 32 + lane];
-                const double rdq = a.rD[q];
-                double dl[5];
+        for (int k = 0; k < 5; k++) xr[k] = a.x[k * a.NPH + p];
+        lusgsRow<true>(a, lane, base, 0, nLow, xr);
 #pragma unroll
-                for (int k = 0; k < 5; k++) dl[k] = rdq * __ldcg(a.x + k * a.NPH + q);
-                lusgsSub(xr, a.offd + ((base + j) * 25) * 32 + lane, dl);
-            }
-#pragma unroll
-            for (int k = 0; k < 5; k++) __stcg(a.x + k * a.NPH + p, xr[k]);
-        }
-        gridBarrier(a.barrier, target, nBlocks);
+        for (int k = 0; k < 5; k++) __stcg(a.y + k * a.NPH + p, xr[k]);
+        __syncwarp();
+        if (lane == 0) __stcg(a.hintF + s, a.epoch);
     }
-    // reverse sweep: dW = rD (D dW* - U dW), neighbours in descending order
-    for (int L = 0; L < a.nLevR; L++) {
-        for (int i = a.levStartR[L] + gtid; i < a.levStartR[L + 1]; i += gsize) {
-            const int p = a.revList[i];
-            const int lane = p & 31;
-            const size_t base = (size_t)a.sliceOff[p >> 5];
-            double xr[5];
+    // reverse sweep: dW = rD (D dW* - U dW), upper neighbours in descending order (lusgs.C:307-381)
+    for (int t = gw; t < a.nSlices; t += W) {
+        const int s = a.nSlices - 1 - t;
+        const int p = s * 32 + lane;
+        const size_t base = (size_t)a.sliceOff[s];
+        const int nLow = a.rowNLow[p], nInt = a.rowNInt[p];
+        const double rd = a.rD[p];
+        double xr[5];
+        pollVec(a.y, a.hintF, a.epoch, a.NPH, p, xr, a.err);  // own forward value (possibly produced by another warp)
+        lusgsRow<false>(a, lane, base, nLow, nInt, xr);
 #pragma unroll
-            for (int k = 0; k < 5; k++) xr[k] = __ldcg(a.x + k * a.NPH + p);
-            const int nLow = a.rowNLow[p], nInt = a.rowNInt[p];
-            for (int j = nInt - 1; j >= nLow; j--) {
-                const int q = a.col[(base + j) * 32 + lane];
-                double dl[5];
-#pragma unroll
-                for (int k = 0; k < 5; k++) dl[k] = __ldcg(a.x + k * a.NPH + q);
-                lusgsSub(xr, a.offd + ((base + j) * 25) * 32 + lane, dl);
-            }
-            const double rd = a.rD[p];
-#pragma unroll
-            for (int k = 0; k < 5; k++) __stcg(a.x + k * a.NPH + p, rd * xr[k]);
+        for (int k = 0; k < 5; k++) {
+            const double v = rd * xr[k];
+            __stcg(a.z + k * a.NPH + p, v);
+            a.x[k * a.NPH + p] = v;
         }
-        if (L + 1 < a.nLevR) gridBarrier(a.barrier, target, nBlocks);
+        __syncwarp();
+        if (lane == 0) __stcg(a.hintR + s, a.epoch);
     }
+}
+
+__global__ void k_fill_sentinel(size_t n, unsigned long long* __restrict__ a, unsigned long long* __restrict__ b)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { a[i] = LUSGS_SENTINEL; b[i] = LUSGS_SENTINEL; }
 }
 
 // ------------------------------------------------------------------------------------------------ Jacobi
@@ -522,23 +614,44 @@ int ics_spmv(icsb200_ctx* c, const double* x, double* y, const double* b)
 int ics_lusgs(icsb200_ctx* c, double* x)
 {
     if (!c->rDValid) { int r = ics_rdiag(c); if (r) return r; }
+    const size_t V5 = (size_t)5 * c->NPH;
     if (c->lusgsGrid == 0) {
         int perSM = 0;
         CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_lusgs, 256, 0));
         if (perSM < 1) return ics_fail(c, ICSB200_ECUDA, "lusgs kernel does not fit on an SM");
-        c->lusgsGrid = c->numSMs * std::min(perSM, 4);
+        c->lusgsGrid = c->numSMs * perSM;
+        int r = devAlloc(c, &c->d_lusgsYZ, 2 * V5);
+        if (r) return r;
+        if ((r = devAlloc(c, &c->d_lusgsHint, (size_t)2 * c->nSlices))) return r;
+        CUDA_TRY(c, cudaMemsetAsync(c->d_lusgsHint, 0, sizeof(int) * 2 * c->nSlices, c->stream));
+        c->lusgsEpoch = 0;
     }
     LusgsArgs a{};
-    a.NP = c->NP; a.nLevF = c->nLevF; a.nLevR = c->nLevR;
-    a.pos2cell = c->d_pos2cell; a.sliceOff = c->d_sliceOff; a.rowNLow = c->d_rowNLow; a.rowNInt = c->d_rowNInt; a.col = c->d_col;
-    a.levStartF = c->d_levStartF; a.levStartR = c->d_levStartR; a.revList = c->d_revList;
-    a.offd = c->d_offd; a.rD = c->d_rD; a.x = x; a.NPH = c->NPH; a.barrier = c->d_barrier;
-    // do not launch more blocks than the widest level can use (fewer blocks = cheaper barrier)
-    int grid = std::min(c->lusgsGrid, std::max(c->numSMs, gridFor(c->maxWidth, 256)));
-    CUDA_TRY(c, cudaMemsetAsync(c->d_barrier, 0, sizeof(unsigned int), c->stream));
+    a.nSlices = c->nSlices;
+    a.sliceOff = c->d_sliceOff; a.rowNLow = c->d_rowNLow; a.rowNInt = c->d_rowNInt; a.col = c->d_col;
+    a.offd = c->d_offd; a.rD = c->d_rD; a.x = x; a.NPH = c->NPH;
+    a.y = c->d_lusgsYZ; a.z = c->d_lusgsYZ + V5;
+    a.err = (int*)c->d_counter + 48;
+    a.hintF = c->d_lusgsHint; a.hintR = c->d_lusgsHint + c->nSlices; a.epoch = ++c->lusgsEpoch;
+    const int grid = std::min(c->lusgsGrid, std::max(1, (c->nSlices + 7) / 8));
     LaunchScope ls(c, TM_LUSGS);
+    k_fill_sentinel<<<gridFor(V5, 256), 256, 0, c->stream>>>(V5, (unsigned long long*)a.y, (unsigned long long*)a.z);
+    c->launches++;
     void* args[] = {&a};
     CUDA_TRY(c, cudaLaunchCooperativeKernel((void*)k_lusgs, dim3(grid), dim3(256), args, 0, c->stream));
+    return 0;
+}
+
+// the sweeps flag a broken dependency schedule instead of hanging; checked once per solve
+static int lusgsCheck(icsb200_ctx* c)
+{
+    int h = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&h, (int*)c->d_counter + 48, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (h) {
+        cudaMemsetAsync((int*)c->d_counter + 48, 0, sizeof(int), c->stream);
+        return ics_fail(c, ICSB200_ECUDA, "lusgs: dependency wait timed out (non-finite values in the sweep?)");
+    }
     return 0;
 }
 
@@ -746,7 +859,7 @@ int ics_gmres(icsb200_ctx* c, const icsb200_solver_controls* ctl, icsb200_residu
         k_copy<<<gridFor(V5, 256), 256, 0, c->stream>>>(V5, c->d_x, c->d_dW);
     }
     CUDA_TRY(c, cudaGetLastError());
-    return 0;
+    return lusgsCheck(c);
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI
@@ -782,6 +895,7 @@ extern "C" int icsb200_precondition(icsb200_ctx* c, int preconditioner, double* 
     int r;
     if ((r = uploadVec5(c, xRho, xRhoU, xRhoE, c->d_x))) return r;
     if ((r = precond(c, preconditioner, c->d_x))) return r;
+    if ((r = lusgsCheck(c))) return r;
     return downloadVec5(c, xRho, xRhoU, xRhoE, c->d_x);
 }
 

@@ -168,8 +168,18 @@ inline double gradedLambda(int j, int n, double r)
 struct StructGen {
     int nb, nxb, ny, nz;
     Mapping map;
+    std::vector<V3> pts;  // cached points, (nxT+1)*(ny+1)*(nz+1)
     int nxT() const { return nb * nxb; }
-    V3 point(int I, int J, int K) const
+    void cachePoints()
+    {
+        const int nx = nxT();
+        pts.resize((size_t)(nx + 1) * (ny + 1) * (nz + 1));
+        for (int K = 0; K <= nz; K++)
+            for (int J = 0; J <= ny; J++)
+                for (int I = 0; I <= nx; I++) pts[((size_t)K * (ny + 1) + J) * (nx + 1) + I] = computePoint(I, J, K);
+    }
+    V3 point(int I, int J, int K) const { return pts[((size_t)K * (ny + 1) + J) * (nxT() + 1) + I]; }
+    V3 computePoint(int I, int J, int K) const
     {
         double xi = double(I) / nxT();
         double eta = gradedLambda(J, ny, map.gradY);
@@ -466,7 +476,8 @@ extern "C" {
 void* icsmesh_structured(int nb, int nxb, int ny, int nz, int kind, const double lo[3], const double hi[3], double gradY,
                          double amp, const int patchKinds[6], const char* const patchNames[6])
 {
-    StructGen g{nb, nxb, ny, nz, Mapping{kind, {lo[0], lo[1], lo[2]}, {hi[0], hi[1], hi[2]}, gradY, amp}};
+    StructGen g{nb, nxb, ny, nz, Mapping{kind, {lo[0], lo[1], lo[2]}, {hi[0], hi[1], hi[2]}, gradY, amp}, {}};
+    g.cachePoints();
     return buildStructured(g, patchKinds, patchNames);
 }
 

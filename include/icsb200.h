@@ -178,6 +178,9 @@ long long icsb200_launch_count(icsb200_ctx* ctx);
  * names: NUL-separated list written to names_buf; returns the number of classes */
 int icsb200_timers_get(icsb200_ctx* ctx, char* names_buf, int names_len, double* ms, long long* calls, int max_classes);
 int icsb200_timers_reset(icsb200_ctx* ctx, int enable);
+/* device-side stopwatch: CUDA events recorded on the library's compute stream (bench.py times its steps with these) */
+int icsb200_timer_begin(icsb200_ctx* ctx);
+int icsb200_timer_end(icsb200_ctx* ctx, double* elapsed_ms);
 /* LU-SGS level schedule statistics: n_levels_fwd, n_levels_rev, max_width, n_positions */
 int icsb200_schedule_info(icsb200_ctx* ctx, int out[4]);
 
