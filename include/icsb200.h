@@ -164,7 +164,7 @@ int icsb200_solve_delta(icsb200_ctx* ctx, const icsb200_solver_controls* c, doub
 int icsb200_update_fields(icsb200_ctx* ctx);
 
 /* ---- the hot path, fused: one outer pseudo-time iteration of dbnsFoam (outerLoop.H:51-99 + updateFields.H) -- */
-/* device-resident: flux -> residual -> pseudo dt -> Jacobian -> GMRES/LU-SGS -> update */
+/* device-resident: flux -> residual -> pseudo dt -> Jacobian -> GMRES/LU-SGS -> update (outerLoop.H:51-99, updateFields.H:1-104) */
 int icsb200_iterate_dev(icsb200_ctx* ctx, const icsb200_solver_controls* c, icsb200_residuals* res);
 /* same through host buffers: uploads p,U,T (6N doubles), iterates once, downloads p,U,T — the call an
  * OpenFOAM adapter makes when fields live on the host */

@@ -343,3 +343,37 @@ int orc_world_state_set(Ctx** ctxs, int n, const double* const* p, const double*
 }
 
 }  // extern "C"
+
+// ---- test hooks (oracle only): expose the restated OpenFOAM operators for known-answer tests ----
+extern "C" {
+
+// fvc::interpolate(vf, pos_/neg_, limited scheme): cell values [N] (boundary = zeroGradient / coupled) -> L[FT], R[FT]
+int orc_debug_reconstruct(Ctx* c, int lim, const double* cells, double* L, double* R)
+{
+    const Mesh& m = c->m;
+    vecd vf((size_t)m.N + m.NB, 0.0), sl, sr;
+    for (int i = 0; i < m.N; i++) vf[i] = cells[i];
+    for (auto& p : m.patches)
+        if (!m.empty(p)) for (int f = p.start; f < p.start + p.size; f++) vf[m.N + f - m.F] = cells[m.owner[f]];
+    syncCoupled(*c, vf, 1);
+    interpolateLimitedLR(*c, vf, lim, sl, sr);
+    std::memcpy(L, sl.data(), sizeof(double) * m.FT);
+    std::memcpy(R, sr.data(), sizeof(double) * m.FT);
+    return 0;
+}
+
+// Gauss linear gradient of a cell field with zeroGradient boundaries -> grad[3N]
+int orc_debug_grad(Ctx* c, const double* cells, double* grad)
+{
+    const Mesh& m = c->m;
+    vecd vf((size_t)m.N + m.NB, 0.0), g;
+    for (int i = 0; i < m.N; i++) vf[i] = cells[i];
+    for (auto& p : m.patches)
+        if (!m.empty(p)) for (int f = p.start; f < p.start + p.size; f++) vf[m.N + f - m.F] = cells[m.owner[f]];
+    syncCoupled(*c, vf, 1);
+    gradGauss(*c, vf, g);
+    std::memcpy(grad, g.data(), sizeof(double) * 3 * m.N);
+    return 0;
+}
+
+}  // extern "C"

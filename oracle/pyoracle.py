@@ -90,3 +90,18 @@ class World:
         rc = lib().orc_world_iterate(ctxs, n, C.byref(ctl), n_iter, C.byref(res))
         assert rc == 0, rc
         return res
+
+
+def debug_reconstruct(o, lim, cells):
+    FT = o.mesh.n_faces
+    L, R = np.zeros(FT), np.zeros(FT)
+    cells = np.ascontiguousarray(cells, np.float64)
+    lib().orc_debug_reconstruct(o.h, int(lim), capi.dptr(cells), capi.dptr(L), capi.dptr(R))
+    return L, R
+
+
+def debug_grad(o, cells):
+    g = np.zeros((o.mesh.n_cells, 3))
+    cells = np.ascontiguousarray(cells, np.float64)
+    lib().orc_debug_grad(o.h, capi.dptr(cells), capi.dptr(g))
+    return g
