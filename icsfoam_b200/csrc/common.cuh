@@ -141,6 +141,7 @@ struct icsb200_ctx {
     int lusgsGrid = 0;
     double* d_lusgsYZ = nullptr;  // [2][5*NPH] forward / reverse sweep values (sentinel protocol)
     int* d_lusgsHint = nullptr;   // [2*nSlices] publication hints
+    long long* d_lusgsTrace = nullptr;
     int lusgsEpoch = 0;
     // staging
     double* d_stage = nullptr;

@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -139,6 +140,8 @@ struct LusgsArgs {
     double *y, *z;     // forward / reverse sweep values, sentinel-filled before launch
     size_t NPH;
     int* err;
+    unsigned int busySpins, sleepNs;
+    long long* trace;  // optional [nSlices][4] forward-sweep time stamps (ns): start, prefetch issued, deps ready, stored
     int *hintF, *hintR;  // per-slice "probably published" epochs: cheap to poll; correctness comes from the sentinel check
     int epoch;
 };
@@ -162,7 +165,8 @@ __device__ __forceinline__ int ldHint(const int* p)
 
 // wait until the 5 components of position q in buffer buf have been published: spin on the slice hint (1 sector per
 // warp poll), then read the values and make sure none is still the sentinel
-__device__ __forceinline__ void pollVec(const double* buf, const int* hint, int epoch, size_t NPH, int q, double* out, int* err)
+__device__ __forceinline__ void pollVec(const double* buf, const int* hint, int epoch, size_t NPH, int q, double* out, int* err, unsigned int busySpins,
+                                        unsigned int sleepNs)
 {
     unsigned int spins = 0;
     const int* h = hint + (q >> 5);
@@ -174,7 +178,7 @@ __device__ __forceinline__ void pollVec(const double* buf, const int* hint, int 
             if (ok) return;
         }
         if (++spins > (1u << 24)) { *err = 1; return; }  // never hang the device on a broken schedule
-        if (spins > 64) __nanosleep(100);
+        if (spins > busySpins) __nanosleep(sleepNs);
     }
 }
 
@@ -194,8 +198,10 @@ constexpr int LCH = 3;  // neighbours handled per chunk (hex cells have at most 
 
 // entries [jBeg, jEnd) of row p (ascending if FWD, descending otherwise): everything that does not depend on the sweep
 // values (column, rD, 5x5 block) is fetched BEFORE polling, so the dependent part of a hop is poll -> 75 flops -> store
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
 template <bool FWD>
-__device__ __forceinline__ void lusgsRow(const LusgsArgs& a, int lane, size_t base, int jBeg, int jEnd, double* xr)
+__device__ __forceinline__ void lusgsRow(const LusgsArgs& a, int lane, size_t base, int jBeg, int jEnd, double* xr, long long* tr)
 {
     const int n = jEnd - jBeg;
     const double* buf = FWD ? a.y : a.z;
@@ -218,6 +224,7 @@ __device__ __forceinline__ void lusgsRow(const LusgsArgs& a, int lane, size_t ba
             }
         }
         const unsigned int want = pend;
+        if (tr && lane == 0 && c0 == 0) tr[1] = gtime();
         // wait for all neighbours of the chunk at once: hint loads in flight together, then the value loads together
         unsigned int spins = 0;
         while (pend) {
@@ -242,9 +249,10 @@ __device__ __forceinline__ void lusgsRow(const LusgsArgs& a, int lane, size_t ba
                 }
             if (pend) {
                 if (++spins > (1u << 24)) { *a.err = 1; break; }  // never hang the device on a broken schedule
-                if (spins > 64) __nanosleep(100);
+                if (spins > a.busySpins) __nanosleep(a.sleepNs);
             }
         }
+        if (tr && c0 == 0) atomicMax((unsigned long long*)(tr + 2), (unsigned long long)gtime());
 #pragma unroll
         for (int t = 0; t < LCH; t++)
             if (want >> t & 1u) {
@@ -270,11 +278,14 @@ k_lusgs(LusgsArgs a)
         double xr[5];
 #pragma unroll
         for (int k = 0; k < 5; k++) xr[k] = a.x[k * a.NPH + p];
-        lusgsRow<true>(a, lane, base, 0, nLow, xr);
+        long long* tr = a.trace ? a.trace + 4 * (size_t)s : nullptr;
+        if (tr && lane == 0) tr[0] = gtime();
+        lusgsRow<true>(a, lane, base, 0, nLow, xr, tr);
 #pragma unroll
         for (int k = 0; k < 5; k++) __stcg(a.y + k * a.NPH + p, xr[k]);
         __syncwarp();
         if (lane == 0) __stcg(a.hintF + s, a.epoch);
+        if (tr && lane == 0) tr[3] = gtime();
     }
     // reverse sweep: dW = rD (D dW* - U dW), upper neighbours in descending order (lusgs.C:307-381)
     for (int t = gw; t < a.nSlices; t += W) {
@@ -284,8 +295,8 @@ k_lusgs(LusgsArgs a)
         const int nLow = a.rowNLow[p], nInt = a.rowNInt[p];
         const double rd = a.rD[p];
         double xr[5];
-        pollVec(a.y, a.hintF, a.epoch, a.NPH, p, xr, a.err);  // own forward value (possibly produced by another warp)
-        lusgsRow<false>(a, lane, base, nLow, nInt, xr);
+        pollVec(a.y, a.hintF, a.epoch, a.NPH, p, xr, a.err, a.busySpins, a.sleepNs);  // own forward value (possibly produced by another warp)
+        lusgsRow<false>(a, lane, base, nLow, nInt, xr, nullptr);
 #pragma unroll
         for (int k = 0; k < 5; k++) {
             const double v = rd * xr[k];
@@ -633,7 +644,26 @@ int ics_lusgs(icsb200_ctx* c, double* x)
     a.y = c->d_lusgsYZ; a.z = c->d_lusgsYZ + V5;
     a.err = (int*)c->d_counter + 48;
     a.hintF = c->d_lusgsHint; a.hintR = c->d_lusgsHint + c->nSlices; a.epoch = ++c->lusgsEpoch;
-    const int grid = std::min(c->lusgsGrid, std::max(1, (c->nSlices + 7) / 8));
+    {
+        static const char* e1 = getenv("ICSB200_LUSGS_SPIN");
+        static const char* e2 = getenv("ICSB200_LUSGS_SLEEP");
+        a.busySpins = e1 ? (unsigned)atoi(e1) : 64u;
+        a.sleepNs = e2 ? (unsigned)atoi(e2) : 100u;
+    }
+    int grid = std::min(c->lusgsGrid, std::max(1, (c->nSlices + 7) / 8));
+    {
+        static const char* e3 = getenv("ICSB200_LUSGS_GRID");
+        if (e3) grid = std::min(grid, std::max(1, atoi(e3)));
+    }
+    a.trace = nullptr;
+    {
+        static const char* e4 = getenv("ICSB200_LUSGS_TRACE");
+        if (e4) {
+            if (!c->d_lusgsTrace) { int r = devAlloc(c, &c->d_lusgsTrace, (size_t)4 * c->nSlices); if (r) return r; }
+            cudaMemsetAsync(c->d_lusgsTrace, 0, sizeof(long long) * 4 * c->nSlices, c->stream);
+            a.trace = c->d_lusgsTrace;
+        }
+    }
     LaunchScope ls(c, TM_LUSGS);
     k_fill_sentinel<<<gridFor(V5, 256), 256, 0, c->stream>>>(V5, (unsigned long long*)a.y, (unsigned long long*)a.z);
     c->launches++;
@@ -955,5 +985,18 @@ extern "C" int icsb200_iterate_host(icsb200_ctx* c, const icsb200_solver_control
     if ((r = ics_download_cells(c, p, 1, c->q(Q_P), c->NX))) return r;
     if ((r = ics_download_cells(c, U, 3, c->q(Q_UX), c->NX))) return r;
     if ((r = ics_download_cells(c, T, 1, c->q(Q_T), c->NX))) return r;
+    return 0;
+}
+
+// development aid: copy the forward-sweep trace of the last LU-SGS application (ICSB200_LUSGS_TRACE=1) and the slice->level data
+extern "C" int icsb200_debug_lusgs_trace(icsb200_ctx* c, long long* out, int* rowNLow, int* cols3)
+{
+    if (!c->d_lusgsTrace) return ICSB200_ESTATE;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaMemcpy(out, c->d_lusgsTrace, sizeof(long long) * 4 * c->nSlices, cudaMemcpyDeviceToHost));
+    for (int s = 0; s < c->nSlices; s++) {
+        rowNLow[s] = c->h_rowNLow[(size_t)s * 32];
+        for (int j = 0; j < 3; j++) cols3[3 * s + j] = (j < rowNLow[s]) ? c->h_col[((size_t)c->h_sliceOff[s] + j) * 32] : -1;
+    }
     return 0;
 }
