@@ -168,20 +168,22 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
 
-    case = make_case(args.n)
-    N_total = case.mesh.n_cells
     nccl_id = None
     if multi:
+        from icsfoam_b200 import cases
         ids = [Context.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         nccl_id = ids[0]
-        nb = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world, "x")
-        part, meshes = case.partition(world, nb)
-        mesh = meshes[rank]
+        # strong scaling: the SAME mesh split into `world` blocks (decomposePar-style processor patches); every rank
+        # generates only its own block (+ one ghost layer), never the global mesh
+        parts = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world, (world, 1, 1))
+        case = cases.onera_box(args.n, parts=parts, rank=rank)
+        N_total = args.n ** 3
         ctx = Context(device=local_rank, nccl_id=nccl_id, rank=rank, n_ranks=world)
-        case.apply(ctx, mesh=mesh, cells=mesh.cell_global)
-        del meshes
+        case.apply(ctx)
     else:
+        case = make_case(args.n)
+        N_total = case.mesh.n_cells
         ctx = Context(device=local_rank)
         case.apply(ctx)
     ctl = case.controls

@@ -50,9 +50,11 @@ class Case:
         else:  # 2x2x2-style blocks by coordinate medians
             nx, ny, nz = mode
             part = np.zeros(self.mesh.n_cells, np.int32)
-            for d, n in enumerate((nx, ny, nz)):
+            stride = 1
+            for d, n in enumerate((nx, ny, nz)):       # rank = ix + nx*(iy + ny*iz), as meshtools.structured_part
                 q = np.quantile(C[:, d], np.linspace(0, 1, n + 1)[1:-1]) if n > 1 else []
-                part = part * n + np.searchsorted(q, C[:, d]).astype(np.int32)
+                part += stride * np.searchsorted(q, C[:, d]).astype(np.int32)
+                stride *= n
         meshes = [self.mesh.extract_part(part, r) for r in range(n_parts)]
         return part, meshes
 
@@ -98,9 +100,15 @@ def bump(nxb=66, ny=54, co=200.0):
     return Case("bump", mesh, R, Cp, sch, ctl, bcs, p, U, T, n_iter_default=20)
 
 
-def onera_box(n=48, co=100.0, flux="HLLC"):
-    """C4 synthetic stand-in for tutorials/OneraM6Wing (inviscid, HLLC, vanLeer, steady, Co=100)."""
-    mesh = mt.onera_box(n)
+def onera_box(n=48, co=100.0, flux="HLLC", parts=None, rank=0):
+    """C4 synthetic stand-in for tutorials/OneraM6Wing (inviscid, HLLC, vanLeer, steady, Co=100).
+    With parts=(px,py,pz) only partition `rank` is generated (fields are uniform, so no global arrays are needed)."""
+    if parts is None:
+        mesh = mt.onera_box(n)
+    else:
+        mesh = mt.structured_part((n, n, n), parts, rank, 2, (-1.0, 0.0, 0.0), (2.0, 3.0, 3.0), amp=0.12,
+                                  patch_kinds=(mt.PATCH, mt.PATCH, mt.SYMMETRYPLANE, mt.PATCH, mt.WALL, mt.PATCH),
+                                  patch_names=("inlet", "outlet", "symmetry", "lateral", "wing", "top"))
     R, Cp = RR / 28.966, 1005.0
     Uinf = (285.6, 15.268, 0.0)
     p, U, T = _uniform(mesh, 101325.0, Uinf, 288.15)

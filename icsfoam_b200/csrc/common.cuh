@@ -233,3 +233,4 @@ int ics_bound_local_dt(icsb200_ctx* c);
 int ics_update(icsb200_ctx* c);
 int ics_copy_prev(icsb200_ctx* c);
 int ics_state_from_primitives(icsb200_ctx* c);
+int ics_allreduce_max_int(icsb200_ctx* c, int* d, int n);

@@ -250,23 +250,23 @@ __global__ void k_update2(int NP, const int* __restrict__ pos2cell, Thermo th, d
 
 // boundLocalTimeStep.H:10-45 — cells whose rho / e dropped below lowerBound x previous value
 __global__ void k_bad(int NP, const int* __restrict__ pos2cell, double lb, const double* __restrict__ Wprev, size_t NPH, const double* __restrict__ f,
-                      size_t NX, int* __restrict__ bad)
+                      size_t NX, double* __restrict__ bad)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= NP) return;
-    if (pos2cell[p] < 0) { bad[p] = 0; return; }
+    if (pos2cell[p] < 0) { bad[p] = 0.0; return; }
     double rp = Wprev[p], rup[3] = {Wprev[NPH + p] / rp, Wprev[2 * NPH + p] / rp, Wprev[3 * NPH + p] / rp};
     double rhoMin = lb * rp;
     double eMin = lb * (Wprev[4 * NPH + p] / rp - 0.5 * (rup[0] * rup[0] + rup[1] * rup[1] + rup[2] * rup[2]));
     double r = f[Q_W0 * NX + p];
     double u[3] = {f[Q_W1 * NX + p] / r, f[Q_W2 * NX + p] / r, f[Q_W3 * NX + p] / r};
     double eTemp = f[Q_W4 * NX + p] / r - 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
-    bad[p] = (r < rhoMin) || (eTemp < eMin) || (eTemp < ICS_SMALL);
+    bad[p] = ((r < rhoMin) || (eTemp < eMin) || (eTemp < ICS_SMALL)) ? 1.0 : 0.0;
 }
 
 // boundLocalTimeStep.H:47-97 — factor 0.5 for a bad cell, 0.75 next to one; pseudoCoField *= factor
 __global__ void k_factor(int NP, const int* __restrict__ pos2cell, const int* __restrict__ sliceOff, const int* __restrict__ rowNAll,
-                         const int* __restrict__ col, const int* __restrict__ meta, const int* __restrict__ bad, double* __restrict__ co)
+                         const int* __restrict__ col, const int* __restrict__ meta, const double* __restrict__ bad, double* __restrict__ co)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= NP || pos2cell[p] < 0) return;
@@ -278,9 +278,9 @@ __global__ void k_factor(int NP, const int* __restrict__ pos2cell, const int* __
         size_t e = (base + j) * 32 + lane;
         if ((meta[e] & 3) == ET_PHYS) continue;
         hasFace = true;
-        nbrBad |= bad[col[e]] != 0;
+        nbrBad |= bad[col[e]] != 0.0;
     }
-    if (bad[p] && hasFace) factor = fmin(0.5, factor);
+    if (bad[p] != 0.0 && hasFace) factor = fmin(0.5, factor);
     if (nbrBad) factor = fmin(0.75, factor);
     co[p] *= factor;
 }
@@ -360,21 +360,19 @@ int ics_copy_prev(icsb200_ctx* c)
 int ics_bound_local_dt(icsb200_ctx* c)
 {
     if (!(c->sch.local_timestepping && c->sch.local_timestepping_bounding)) return 0;
+    double* bad = c->d_w;  // scratch: one double per slot so the flags can ride the generic halo exchange
     {
         LaunchScope ls(c, TM_UPDATE);
         k_bad<<<gridFor(c->NP, 256), 256, 0, c->stream>>>(c->NP, c->d_pos2cell, c->sch.local_timestepping_lower_bound, c->d_Wprev, c->NPH,
-                                                          c->d_fields, c->NX, c->d_bad);
+                                                          c->d_fields, c->NX, bad);
     }
     CUDA_TRY(c, cudaGetLastError());
-    if (c->NH > 0) {
-        // flags of neighbour-rank cells (patchNeighbourField of rho/e tests, boundLocalTimeStep.H:60-95): exchange as doubles
-        // via the generic halo path on a scratch view is overkill; the flags ride in d_x[0..NPH) as doubles
-        return ics_fail(c, ICSB200_ESTATE, "internal: multi-rank boundLocalTimeStep flags not exchanged");
-    }
+    // patchNeighbourField of the rho / e tests on processor patches (boundLocalTimeStep.H:60-95)
+    int r = ics_halo_fields(c, bad, c->NPH, 1);
+    if (r) return r;
     {
         LaunchScope ls(c, TM_UPDATE);
-        k_factor<<<gridFor(c->NP, 256), 256, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_col, c->d_meta, c->d_bad,
-                                                             c->d_co);
+        k_factor<<<gridFor(c->NP, 256), 256, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_col, c->d_meta, bad, c->d_co);
     }
     CUDA_TRY(c, cudaGetLastError());
     return 0;
@@ -391,6 +389,8 @@ int ics_update(icsb200_ctx* c)
         k_update1<<<gridFor(c->NP, 256), 256, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_dW, c->NPH, c->sch.rho_min, eMin,
                                                               haveTMax ? eMax : ICS_VGREAT, c->d_fields, c->NX, c->d_w, flags);
     }
+    // max(neg(e - eBound)) is a global reduction in the reference (updateFields.H:46,58)
+    if (c->nRanks > 1 && ics_allreduce_max_int(c, flags, 2)) return ICSB200_ECUDA;
     {
         LaunchScope ls(c, TM_UPDATE);
         k_update2<<<gridFor(c->NP, 256), 256, 0, c->stream>>>(c->NP, c->d_pos2cell, thermoOf(c), eMin, eMax, haveTMax, c->d_w, flags,

@@ -24,6 +24,7 @@ def _lib():
         _LIB = C.CDLL(path)
         _LIB.icsmesh_structured.restype = C.c_void_p
         _LIB.icsmesh_read_polymesh.restype = C.c_void_p
+        _LIB.icsmesh_structured_subbox.restype = C.c_void_p
         _LIB.icsmesh_extract_part.restype = C.c_void_p
         _LIB.icsmesh_error.restype = C.c_char_p
     return _LIB
@@ -137,6 +138,42 @@ def structured(nb, nxb, ny, nz, kind=0, lo=(0, 0, 0), hi=(1, 1, 1), grad_y=1.0, 
     names = (C.c_char_p * 6)(*[n.encode() for n in patch_names])
     h = _lib().icsmesh_structured(nb, nxb, ny, nz, kind, lo_a, hi_a, C.c_double(grad_y), C.c_double(amp), kinds, names)
     return Mesh(h)
+
+
+def structured_part(n, parts, rank, kind=0, lo=(0, 0, 0), hi=(1, 1, 1), grad_y=1.0, amp=0.0, patch_kinds=(PATCH,) * 6,
+                    patch_names=("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")):
+    """Partition `rank` of a parts=(px,py,pz) block decomposition of the single-block structured mesh n=(nx,ny,nz),
+    built WITHOUT the global mesh: the rank's box plus one ghost layer is generated with the global point mapping and
+    then cut with extract_part, which yields processor patches ordered consistently on both sides."""
+    n, parts = np.asarray(n), np.asarray(parts)
+    r = np.array([rank % parts[0], (rank // parts[0]) % parts[1], rank // (parts[0] * parts[1])])
+    edges = [np.linspace(0, n[d], parts[d] + 1).round().astype(int) for d in range(3)]
+    lo_i = np.array([edges[d][r[d]] for d in range(3)])
+    hi_i = np.array([edges[d][r[d] + 1] for d in range(3)])
+    elo, ehi = np.maximum(lo_i - 1, 0), np.minimum(hi_i + 1, n)
+    en = ehi - elo
+    kinds, names = list(patch_kinds), list(patch_names)
+    for d in range(3):                                   # artificial cuts are not real patches
+        if elo[d] > 0:
+            kinds[2 * d], names[2 * d] = PATCH, f"cut{2 * d}"
+        if ehi[d] < n[d]:
+            kinds[2 * d + 1], names[2 * d + 1] = PATCH, f"cut{2 * d + 1}"
+    ia = lambda v: (C.c_int * 3)(*[int(x) for x in v])
+    h = _lib().icsmesh_structured_subbox(ia(en), ia(elo), ia(n), kind, (C.c_double * 3)(*lo), (C.c_double * 3)(*hi),
+                                         C.c_double(grad_y), C.c_double(amp), (C.c_int * 6)(*kinds),
+                                         (C.c_char_p * 6)(*[s.encode() for s in names]))
+    ext = Mesh(h)
+    # owner rank of every cell of the extended box
+    gi = np.arange(elo[0], ehi[0]); gj = np.arange(elo[1], ehi[1]); gk = np.arange(elo[2], ehi[2])
+    ri = np.searchsorted(edges[0], gi, side="right") - 1
+    rj = np.searchsorted(edges[1], gj, side="right") - 1
+    rk = np.searchsorted(edges[2], gk, side="right") - 1
+    part = (ri[None, None, :] + parts[0] * (rj[None, :, None] + parts[1] * rk[:, None, None])).astype(np.int32).reshape(-1)
+    sub = ext.extract_part(part, rank)
+    # global cell ids of the local cells (lexicographic in the global grid)
+    gid = (gi[None, None, :] + n[0] * (gj[None, :, None] + n[1] * gk[:, None, None])).reshape(-1)
+    sub.cell_global = gid[sub.cell_global].astype(np.int64)
+    return sub
 
 
 def read_polymesh(directory):

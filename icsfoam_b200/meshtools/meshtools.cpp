@@ -169,7 +169,13 @@ struct StructGen {
     int nb, nxb, ny, nz;
     Mapping map;
     std::vector<V3> pts;  // cached points, (nxT+1)*(ny+1)*(nz+1)
+    // sub-box of a larger global grid: this generator covers global cells [off, off + n) in each direction
+    int off[3] = {0, 0, 0};
+    int glob[3] = {0, 0, 0};  // global cell counts (0 = same as local)
     int nxT() const { return nb * nxb; }
+    int gx() const { return glob[0] ? glob[0] : nxT(); }
+    int gy() const { return glob[1] ? glob[1] : ny; }
+    int gz() const { return glob[2] ? glob[2] : nz; }
     void cachePoints()
     {
         const int nx = nxT();
@@ -179,11 +185,12 @@ struct StructGen {
                 for (int I = 0; I <= nx; I++) pts[((size_t)K * (ny + 1) + J) * (nx + 1) + I] = computePoint(I, J, K);
     }
     V3 point(int I, int J, int K) const { return pts[((size_t)K * (ny + 1) + J) * (nxT() + 1) + I]; }
-    V3 computePoint(int I, int J, int K) const
+    V3 computePoint(int Il, int Jl, int Kl) const
     {
-        double xi = double(I) / nxT();
-        double eta = gradedLambda(J, ny, map.gradY);
-        double zeta = double(K) / nz;
+        const int I = Il + off[0], J = Jl + off[1], K = Kl + off[2];
+        double xi = double(I) / gx();
+        double eta = gradedLambda(J, gy(), map.gradY);
+        double zeta = double(K) / gz();
         V3 p;
         p.x = map.lo[0] + xi * (map.hi[0] - map.lo[0]);
         p.y = map.lo[1] + eta * (map.hi[1] - map.lo[1]);
@@ -477,6 +484,16 @@ void* icsmesh_structured(int nb, int nxb, int ny, int nz, int kind, const double
                          double amp, const int patchKinds[6], const char* const patchNames[6])
 {
     StructGen g{nb, nxb, ny, nz, Mapping{kind, {lo[0], lo[1], lo[2]}, {hi[0], hi[1], hi[2]}, gradY, amp}, {}};
+    g.cachePoints();
+    return buildStructured(g, patchKinds, patchNames);
+}
+
+// sub-box [off, off+n) of a single-block global grid of gl[3] cells (same mapping => identical points as the global mesh)
+void* icsmesh_structured_subbox(const int n[3], const int off[3], const int gl[3], int kind, const double lo[3], const double hi[3],
+                                double gradY, double amp, const int patchKinds[6], const char* const patchNames[6])
+{
+    StructGen g{1, n[0], n[1], n[2], Mapping{kind, {lo[0], lo[1], lo[2]}, {hi[0], hi[1], hi[2]}, gradY, amp}, {}};
+    for (int d = 0; d < 3; d++) { g.off[d] = off[d]; g.glob[d] = gl[d]; }
     g.cachePoints();
     return buildStructured(g, patchKinds, patchNames);
 }

@@ -1,0 +1,75 @@
+"""Multi-GPU parity driver (launched by torchrun, one rank per GPU): the P-GPU run must match the P-partition CPU
+oracle with the same decomposition (LU-SGS is rank-local, so parity is defined per decomposition)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from icsfoam_b200 import capi, cases  # noqa: E402
+from icsfoam_b200.context import Context  # noqa: E402
+
+
+def main():
+    n = int(os.environ.get("ICS_MULTI_N", "10"))
+    n_iter = int(os.environ.get("ICS_MULTI_ITERS", "4"))
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    parts = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+    ids = [Context.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    case = cases.onera_box(n, parts=parts, rank=rank)
+    ctx = case.apply(Context(device=local, nccl_id=ids[0], rank=rank, n_ranks=world))
+    hist = []
+    flux0 = ctx.calc_flux()
+    for _ in range(n_iter):
+        r = ctx.iterate(case.controls)
+        hist.append(list(r.s_init) + list(r.v_init) + [r.n_iterations])
+    st = ctx.state_get()
+    payload = {"rho": st["rho"], "rhoU": st["rhoU"], "rhoE": st["rhoE"], "phi": flux0[0], "hist": hist}
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(payload, gathered, dst=0)
+    ok = True
+    if rank == 0:
+        from oracle.pyoracle import World
+        meshes = [cases.onera_box(n, parts=parts, rank=r) for r in range(world)]
+        w = World(world)
+        w.mesh_set([c.mesh for c in meshes])
+        for o, c in zip(w.ranks, meshes):
+            o.thermo_set(c.R, c.Cp, c.mu, c.Pr)
+            o.schemes_set(c.schemes)
+            names = [p["name"] for p in c.mesh.patches]
+            for patch, fields in c.bcs.items():
+                if patch in names:
+                    for field, (kind, params) in fields.items():
+                        o.bc_set(patch, {"p": 0, "U": 1, "T": 2}[field], kind, params)
+        w.state_set([c.p for c in meshes], [c.U for c in meshes], [c.T for c in meshes])
+        ohist = []
+        for _ in range(n_iter):
+            r = w.iterate(case.controls, 1)
+            ohist.append(list(r.s_init) + list(r.v_init) + [r.n_iterations])
+        ohist, ghist = np.array(ohist), np.array(gathered[0]["hist"])
+        print("oracle history", ohist[:, [0, 1, -1]].tolist())
+        print("gpu    history", ghist[:, [0, 1, -1]].tolist())
+        ok &= np.array_equal(ohist[:, -1], ghist[:, -1])
+        ok &= np.allclose(ohist[:, :5], ghist[:, :5], rtol=1e-8, atol=1e-14)
+        for r_, (o, g) in enumerate(zip(w.ranks, gathered)):
+            so = o.state_get()
+            for k in ("rho", "rhoU", "rhoE"):
+                err = np.abs(g[k] - so[k]).max() / np.abs(so[k]).max()
+                print(f"rank {r_} {k} rel err {err:.3e}")
+                ok &= err <= 1e-8
+        print("MULTI_GPU_PARITY", "OK" if ok else "FAILED")
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

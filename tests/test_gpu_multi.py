@@ -1,0 +1,28 @@
+"""2-GPU parity (needs a box with >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from tests.conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("world", [2])
+def test_multi_gpu_matches_partitioned_oracle(world):
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29544")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+                        "127.0.0.1", "--master-port", "29544", os.path.join(ROOT, "tests", "multi_gpu_check.py")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTI_GPU_PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
