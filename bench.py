@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — Mcell-iterations/s of the ICSFoam implicit pseudo-time iteration on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--n CELLS_PER_DIRECTION]
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--cells-per-dim N]
 
 A "step" is one outer pseudo-time iteration of dbnsFoam (outerLoop.H:51-99 + updateFields.H): gradients, flux,
 residual, local pseudo time step, Jacobian assembly, GMRES(m)/LU-SGS solve, field update.
@@ -147,10 +147,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--n", type=int, default=int(os.environ.get("ICSB200_BENCH_N", "256")), help="cells per direction of the 3-D mesh")
-    ap.add_argument("--n-cpu", type=int, default=64, help="cells per direction of the bounded CPU-baseline sample")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cells-per-dim", "--n", dest="n", type=int, default=int(os.environ.get("ICSB200_BENCH_N", "256")),
+                    help="cells per direction of the 3-D mesh (use the long form under torchrun)")
+    ap.add_argument("--cpu-cells-per-dim", "--n-cpu", dest="n_cpu", type=int, default=96, help="cells per direction of the bounded CPU-baseline sample")
+    ap.add_argument("--skip-cpu", "--no-cpu", dest="no_cpu", action="store_true")
+    ap.add_argument("--skip-e2e", "--no-e2e", dest="no_e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -263,6 +264,8 @@ def main():
     if rank != 0:
         if multi:
             dist.barrier()
+            ctx.close()
+            dist.destroy_process_group()
         return
     cpu = None
     if not args.no_cpu and not multi:
@@ -280,9 +283,11 @@ def main():
                        "restarts_per_step": float(np.mean(restarts)), "lusgs_levels": sched["n_levels_fwd"],
                        "l2": "working set per step >> 126 MB L2 (inputs larger than L2)", "partition": "1" if not multi else f"{world} blocks"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if multi:
         dist.barrier()
+        ctx.close()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
