@@ -80,6 +80,7 @@ class Context(capi.Api):
         return ms.value
 
     def schedule_info(self):
-        out = (C.c_int * 4)()
+        out = (C.c_int * 8)()
         self._call("schedule_info", out)
-        return {"n_levels_fwd": out[0], "n_levels_rev": out[1], "max_width": out[2], "n_positions": out[3]}
+        return {"n_levels_fwd": out[0], "n_levels_rev": out[1], "max_width": out[2], "n_positions": out[3],
+                "tile_mode": bool(out[4]), "n_tiles": out[5], "n_tile_levels": out[6]}

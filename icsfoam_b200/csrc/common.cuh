@@ -26,6 +26,7 @@
 #define ICS_ROOTVSMALL 1e-150
 #define ICS_GREAT 1e15
 #define ICS_VGREAT 1e300
+#define ICS_TILE_MAXROWS 1024  // rows a LU-SGS tile may hold (shared-memory staging of 5 doubles per row)
 
 constexpr int NQ = 8;   // reconstructed scalars: rho, p, Ux, Uy, Uz, cR, E, H
 constexpr int NG = 7;   // geometry doubles per face (SoA over GPU face ids)
@@ -93,7 +94,12 @@ struct icsb200_ctx {
     double* d_C = nullptr;    // [3*NPH] cell centres (SoA)
     // levels
     int nLevF = 0, nLevR = 0, maxWidth = 0;
-    int *d_levStartF = nullptr, *d_levStartR = nullptr, *d_revList = nullptr;
+    // blocked-wavefront schedule (tile mode)
+    bool tileMode = false;
+    int nTiles = 0, nTileLevels = 0;
+    int tileMaxRows = 0, lusgsTileGrid = 0;
+    int* d_sliceTile = nullptr;  // [nSlices] tile of a slice
+    int *d_tileStart = nullptr, *d_tileFPtr = nullptr, *d_tileFLev = nullptr, *d_tileRPtr = nullptr, *d_tileRLev = nullptr, *d_tileRRows = nullptr;
     // boundary faces
     int* d_bfOwnerPos = nullptr;  // [NB] position of faceCell (-1 for empty)
     int* d_bfPatch = nullptr;     // [NB]

@@ -7,6 +7,8 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -129,7 +131,7 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
     cudaDeviceSynchronize();
     if (c->nccl) ncclCommDestroy((ncclComm_t)c->nccl);
     void* ptrs[] = {c->d_pos2cell, c->d_cell2pos, c->d_sliceOff, c->d_rowNLow, c->d_rowNInt, c->d_rowNAll, c->d_col, c->d_meta, c->d_gfid,
-                    c->d_geo, c->d_dCoupled, c->d_V, c->d_C, c->d_levStartF, c->d_levStartR, c->d_revList, c->d_bfOwnerPos, c->d_bfPatch, c->d_bfKind,
+                    c->d_geo, c->d_dCoupled, c->d_V, c->d_C, c->d_tileStart, c->d_tileFPtr, c->d_tileFLev, c->d_tileRPtr, c->d_tileRLev, c->d_tileRRows, c->d_sliceTile, c->d_bfOwnerPos, c->d_bfPatch, c->d_bfKind,
                     c->d_bfGeo, c->d_bc, c->d_phiB, c->d_vic, c->d_sendBuf, c->d_recvBuf, c->d_fields, c->d_grad, c->d_rdt, c->d_co,
                     c->d_ddtCoeff, c->d_Wold, c->d_Wold2, c->d_Wprev, c->d_src, c->d_dW, c->d_faceFlux, c->d_bad, c->d_offd, c->d_diag,
                     c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage, c->d_lusgsYZ, c->d_lusgsHint};
@@ -189,9 +191,10 @@ extern "C" int icsb200_timer_end(icsb200_ctx* c, double* elapsed_ms)
     return 0;
 }
 
-extern "C" int icsb200_schedule_info(icsb200_ctx* c, int out[4])
+extern "C" int icsb200_schedule_info(icsb200_ctx* c, int out[8])
 {
     out[0] = c->nLevF; out[1] = c->nLevR; out[2] = c->maxWidth; out[3] = c->NP;
+    out[4] = c->tileMode ? 1 : 0; out[5] = c->nTiles; out[6] = c->nTileLevels;
     return 0;
 }
 
@@ -259,38 +262,135 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
         if (p.kind != ICSB200_EMPTY) for (int f = p.start; f < p.start + p.size; f++) c->bfacePatch[f - F] = pi;
     }
 
-    // ---- LU-SGS level schedule (forward: longest path from below; reverse: longest path from above)
+    // ---- LU-SGS schedule.  Levels: forward = longest path from below, reverse = longest path from above.
     std::vector<int> levF(N, 0), levR(N, 0);
     for (int f = 0; f < F; f++) levF[neighbour[f]] = std::max(levF[neighbour[f]], levF[owner[f]] + 1);
     for (int f = F - 1; f >= 0; f--) levR[owner[f]] = std::max(levR[owner[f]], levR[neighbour[f]] + 1);
     int nLevF = 0, nLevR = 0;
     for (int i = 0; i < N; i++) { nLevF = std::max(nLevF, levF[i] + 1); nLevR = std::max(nLevR, levR[i] + 1); }
     c->nLevF = nLevF; c->nLevR = nLevR;
-    std::vector<int> cntF(nLevF + 1, 0);
-    for (int i = 0; i < N; i++) cntF[levF[i] + 1]++;
-    std::vector<int> levStartF(nLevF + 1, 0);
     c->maxWidth = 0;
-    for (int l = 0; l < nLevF; l++) {
-        levStartF[l + 1] = levStartF[l] + ((cntF[l + 1] + 31) / 32) * 32;
-        c->maxWidth = std::max(c->maxWidth, cntF[l + 1]);
-    }
-    const int NP = levStartF[nLevF];
-    c->NP = NP;
-    c->pos2cell.assign(NP, -1);
-    c->cell2pos.assign(N, -1);
     {
+        std::vector<int> cnt(nLevF, 0);
+        for (int i = 0; i < N; i++) c->maxWidth = std::max(c->maxWidth, ++cnt[levF[i]]);
+    }
+    // Tile mode (blocked wavefront): cells are binned into boxes of ~512 cells by coordinate thresholds.  If every
+    // internal face goes from a tile to a component-wise >= tile, the tile graph is acyclic with tile level a+b+c and
+    // ordering positions by (tile level, tile, forward level, cell) is a valid topological order in which a CTA can sweep
+    // a whole tile with shared memory, synchronising with other CTAs only once per tile.  Otherwise fall back to the
+    // level order (one 32-row slice per "tile").
+    std::vector<int> tileOf;  // per cell
+    int nTiles = 0;
+    c->tileMode = false;
+    {
+        const char* env = getenv("ICSB200_LUSGS_MODE");
+        // tile mode is correct (bit-identical) but not yet faster than the level pipeline: opt-in
+        const bool wantTiles = env && std::string(env) == "tile" && N >= 64;
+        if (wantTiles) {
+            // logical coordinates from the graph alone: u_d = longest path using only faces whose normal is mostly along
+            // axis d (exactly (i,j,k) on a block-structured mesh, however curved); tiles = boxes of u
+            std::vector<int> u[3];
+            int umax[3] = {0, 0, 0};
+            for (int d = 0; d < 3; d++) u[d].assign(N, 0);
+            for (int f = 0; f < F; f++) {
+                double ax = std::fabs(Sf[3 * (size_t)f]), ay = std::fabs(Sf[3 * (size_t)f + 1]), az = std::fabs(Sf[3 * (size_t)f + 2]);
+                int d = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+                int v = u[d][owner[f]] + 1;
+                if (v > u[d][neighbour[f]]) { u[d][neighbour[f]] = v; umax[d] = std::max(umax[d], v); }
+            }
+            int active = 0;
+            for (int d = 0; d < 3; d++) if (umax[d] + 1 >= 4) active++;
+            const int side = active > 0 ? std::max(2, (int)std::lround(std::pow(512.0, 1.0 / active))) : 512;
+            int nb[3];
+            std::vector<int> bin[3];
+            for (int d = 0; d < 3; d++) {
+                const bool act = umax[d] + 1 >= 4;
+                nb[d] = act ? (umax[d] + side) / side : 1;
+                bin[d].assign(N, 0);
+                if (act) for (int i = 0; i < N; i++) bin[d][i] = u[d][i] / side;
+            }
+            bool ok = true;
+            for (int f = 0; f < F && ok; f++)
+                for (int d = 0; d < 3; d++)
+                    if (bin[d][neighbour[f]] < bin[d][owner[f]]) { ok = false; break; }
+            if (ok) {
+                // dense tile numbering sorted by (tile level, a, b, c)
+                const long long nbAll = (long long)nb[0] * nb[1] * nb[2];
+                std::vector<int> key(N);
+                std::vector<int> cntT(nbAll, 0);
+                for (int i = 0; i < N; i++) { key[i] = bin[0][i] + nb[0] * (bin[1][i] + nb[1] * bin[2][i]); cntT[key[i]]++; }
+                std::vector<int> order;
+                for (long long t = 0; t < nbAll; t++) if (cntT[t] > 0) order.push_back((int)t);
+                auto tl = [&](int t) { return t % nb[0] + (t / nb[0]) % nb[1] + t / (nb[0] * nb[1]); };
+                std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tl(x) < tl(y); });
+                int maxRows = 0, maxTL = 0;
+                for (int t : order) { maxRows = std::max(maxRows, cntT[t]); maxTL = std::max(maxTL, tl(t)); }
+                if (maxRows <= ICS_TILE_MAXROWS - 32) {
+                    std::vector<int> dense(nbAll, -1);
+                    for (size_t k = 0; k < order.size(); k++) dense[order[k]] = (int)k;
+                    tileOf.resize(N);
+                    for (int i = 0; i < N; i++) tileOf[i] = dense[key[i]];
+                    nTiles = (int)order.size();
+                    c->tileMode = true;
+                    c->nTileLevels = maxTL + 1;
+                }
+            }
+        }
+    }
+    std::vector<int> tileStart;                 // [nTiles+1] first position of a tile (multiple of 32)
+    std::vector<int> tileFPtr, tileFLev;        // forward: CSR over tiles of local row offsets where a new level starts
+    std::vector<int> tileRPtr, tileRLev, tileRRows;  // reverse: rows of a tile sorted by reverse level + level offsets
+    int NP = 0;
+    if (c->tileMode) {
+        std::vector<int> cntT(nTiles, 0);
+        for (int i = 0; i < N; i++) cntT[tileOf[i]]++;
+        tileStart.assign(nTiles + 1, 0);
+        for (int t = 0; t < nTiles; t++) tileStart[t + 1] = tileStart[t] + ((cntT[t] + 31) / 32) * 32;
+        NP = tileStart[nTiles];
+        c->pos2cell.assign(NP, -1);
+        c->cell2pos.assign(N, -1);
+        // cells of a tile sorted by (forward level, cell id): bucket by tile, then sort each bucket
+        std::vector<int> fill(tileStart.begin(), tileStart.end() - 1);
+        for (int i = 0; i < N; i++) c->pos2cell[fill[tileOf[i]]++] = i;
+        tileFPtr.assign(nTiles + 1, 0); tileRPtr.assign(nTiles + 1, 0);
+        tileRRows.assign(NP, 0);
+        for (int t = 0; t < nTiles; t++) {
+            int* beg = c->pos2cell.data() + tileStart[t];
+            int n = cntT[t];
+            std::sort(beg, beg + n, [&](int x, int y) { return levF[x] != levF[y] ? levF[x] < levF[y] : x < y; });
+            for (int r = 0; r < n; r++) {
+                c->cell2pos[beg[r]] = tileStart[t] + r;
+                if (r == 0 || levF[beg[r]] != levF[beg[r - 1]]) tileFLev.push_back(r);
+            }
+            tileFLev.push_back(n);
+            tileFPtr[t + 1] = (int)tileFLev.size();
+            // reverse order: local rows sorted by (reverse level, local row)
+            std::vector<int> rr(n);
+            for (int r = 0; r < n; r++) rr[r] = r;
+            std::sort(rr.begin(), rr.end(), [&](int x, int y) { return levR[beg[x]] != levR[beg[y]] ? levR[beg[x]] < levR[beg[y]] : x < y; });
+            for (int r = 0; r < n; r++) {
+                tileRRows[tileStart[t] + r] = rr[r];
+                if (r == 0 || levR[beg[rr[r]]] != levR[beg[rr[r - 1]]]) tileRLev.push_back(r);
+            }
+            tileRLev.push_back(n);
+            tileRPtr[t + 1] = (int)tileRLev.size();
+        }
+        c->nTiles = nTiles;
+    } else {
+        // level order: positions sorted by (forward level, cell id), levels padded to a multiple of 32
+        std::vector<int> cntF(nLevF + 1, 0);
+        for (int i = 0; i < N; i++) cntF[levF[i] + 1]++;
+        std::vector<int> levStartF(nLevF + 1, 0);
+        for (int l = 0; l < nLevF; l++) levStartF[l + 1] = levStartF[l] + ((cntF[l + 1] + 31) / 32) * 32;
+        NP = levStartF[nLevF];
+        c->pos2cell.assign(NP, -1);
+        c->cell2pos.assign(N, -1);
         std::vector<int> fill(levStartF.begin(), levStartF.end() - 1);
         for (int i = 0; i < N; i++) { int p = fill[levF[i]]++; c->pos2cell[p] = i; c->cell2pos[i] = p; }
+        c->nTiles = 0;
+        c->nTileLevels = 0;
     }
-    // reverse level lists of positions (ascending position inside a level)
-    std::vector<int> levStartR(nLevR + 1, 0), revList(N);
-    {
-        std::vector<int> cnt(nLevR + 1, 0);
-        for (int i = 0; i < N; i++) cnt[levR[i] + 1]++;
-        for (int l = 0; l < nLevR; l++) levStartR[l + 1] = levStartR[l] + cnt[l + 1];
-        std::vector<int> fill(levStartR.begin(), levStartR.end() - 1);
-        for (int p = 0; p < NP; p++) { int i = c->pos2cell[p]; if (i >= 0) revList[fill[levR[i]]++] = p; }
-    }
+    c->NP = NP;
 
     // ---- halo slots for processor patches
     c->procs.clear();
@@ -476,9 +576,21 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     r |= devUpload(c, &c->d_dCoupled, dCoupled);
     r |= devUpload(c, &c->d_V, Vp);
     r |= devUpload(c, &c->d_C, Cp3);
-    r |= devUpload(c, &c->d_levStartF, levStartF);
-    r |= devUpload(c, &c->d_levStartR, levStartR);
-    r |= devUpload(c, &c->d_revList, revList);
+    if (c->tileMode) {
+        r |= devUpload(c, &c->d_tileStart, tileStart);
+        r |= devUpload(c, &c->d_tileFPtr, tileFPtr);
+        r |= devUpload(c, &c->d_tileFLev, tileFLev);
+        r |= devUpload(c, &c->d_tileRPtr, tileRPtr);
+        r |= devUpload(c, &c->d_tileRLev, tileRLev);
+        r |= devUpload(c, &c->d_tileRRows, tileRRows);
+        std::vector<int> sliceTile(NP / 32, 0);
+        c->tileMaxRows = 32;
+        for (int t = 0; t < c->nTiles; t++) {
+            for (int s = tileStart[t] / 32; s < tileStart[t + 1] / 32; s++) sliceTile[s] = t;
+            c->tileMaxRows = std::max(c->tileMaxRows, tileStart[t + 1] - tileStart[t]);
+        }
+        r |= devUpload(c, &c->d_sliceTile, sliceTile);
+    }
     r |= devUpload(c, &c->d_bfOwnerPos, bfOwnerPos);
     r |= devUpload(c, &c->d_bfPatch, c->bfacePatch);
     {
@@ -550,6 +662,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     CUDA_TRY(c, cudaMemset(c->d_vic, 0, sizeof(double) * 5 * std::max(NB, 1)));
     CUDA_TRY(c, cudaMemset(c->d_bad, 0, sizeof(int) * NPH));
     c->lusgsGrid = 0;
+    c->lusgsTileGrid = 0;
     c->meshSet = true;
     c->stateSet = c->matrixSet = c->fluxValid = false;
     return 0;

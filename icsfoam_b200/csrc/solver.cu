@@ -315,6 +315,294 @@ k_lusgs(LusgsArgs a)
     }
 }
 
+// ---------------- tile mode: blocked wavefront ----------------
+// Positions are ordered tile by tile (setup.cu).  One CTA sweeps a whole tile: the rows of a tile are processed
+// intra-tile level by level with __syncthreads in between, in-tile neighbours come from shared memory, out-of-tile
+// neighbours (always in tiles of lower tile level) from the sentinel-validated global buffers; the tile publishes one
+// hint when it is complete.  The dependency chain across SMs shrinks from the number of levels to the number of tile
+// levels (e.g. 598 -> 75 for 200^3), so the sweep becomes bandwidth bound.
+struct TileArgs {
+    int nTiles;
+    const int *tileStart, *tileFPtr, *tileFLev, *tileRPtr, *tileRLev, *tileRRows, *sliceTile;
+    const int *sliceOff, *rowNLow, *rowNInt, *col;
+    const double *offd, *rD;
+    double *x, *y, *z;
+    size_t NPH;
+    int *hintF, *hintR;
+    int epoch;
+    int* err;
+    int maxRows;
+};
+
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void pollTile(const double* buf, const int* hint, const int* sliceTile, int epoch, size_t NPH, int q, double* out, int* err)
+{
+    unsigned int spins = 0;
+    const int* h = hint + sliceTile[q >> 5];
+    while (true) {
+        if (ldHint(h) == epoch) {
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 5; k++) { out[k] = ldPoll(buf + k * NPH + q); ok &= !isSentinel(out[k]); }
+            if (ok) return;
+        }
+        if (++spins > (1u << 24)) { *err = 1; return; }
+        if (spins > 64) __nanosleep(100);
+    }
+}
+
+__device__ __forceinline__ void subBlockGlobal(double* xr, const double* __restrict__ blk, const double* dl)
+{
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const double b0 = __ldcs(blk + (size_t)(r * 5 + 0) * 32), b1 = __ldcs(blk + (size_t)(r * 5 + 1) * 32), b2 = __ldcs(blk + (size_t)(r * 5 + 2) * 32),
+                     b3 = __ldcs(blk + (size_t)(r * 5 + 3) * 32), b4 = __ldcs(blk + (size_t)(r * 5 + 4) * 32);
+        xr[r] -= b0 * dl[0];
+        xr[r] -= b4 * dl[4];
+        xr[r] -= b1 * dl[1] + b2 * dl[2] + b3 * dl[3];
+    }
+}
+
+constexpr int TILE_TPB = 128;
+
+// one row's sweep inputs, fetched one intra-tile level ahead (everything here is independent of the sweep values, except
+// `own` in the reverse sweep which is validated against the sentinel before use)
+struct RowPf {
+    int r, n;             // local row (-1: none), number of neighbour entries of this sweep
+    int jFirst;           // first entry index (forward: 0; reverse: nInt-1, descending)
+    int q[LCH];
+    double sc[LCH];
+    double B[LCH][25];
+    double own[5], rd;
+    size_t base;
+    int ln;
+};
+
+constexpr int TILE_CW = 8;        // column entries per row staged in shared memory (hex rows have 6)
+constexpr int TILE_MAXHALO = 768; // out-of-tile neighbour values staged per tile and sweep
+
+// shared-memory view of one tile: sweep values + the small per-row metadata, staged once per tile with coalesced loads
+// so that the per-level critical path contains no dependent global index loads
+struct TileSmem {
+    double* xs;   // [5][MR] sweep values of the tile's rows
+    double* rDs;  // [MR]
+    int* nLow;    // [MR]
+    int* nInt;    // [MR]
+    int* cols;    // [MR/32][TILE_CW][32]  in-tile: position; out-of-tile: -(halo slot + 1)
+    double* halo; // [5][TILE_MAXHALO] out-of-tile neighbour values of this sweep (forward: already scaled by rD)
+    int* haloQ;   // [TILE_MAXHALO]
+    int* cnt;     // [1]
+};
+
+__device__ __forceinline__ TileSmem carve(double* base, int MR)
+{
+    TileSmem t;
+    t.xs = base;
+    t.rDs = base + 5 * (size_t)MR;
+    t.nLow = (int*)(t.rDs + MR);
+    t.nInt = t.nLow + MR;
+    t.cols = t.nInt + MR;
+    t.halo = (double*)(t.cols + (size_t)(MR / 32) * TILE_CW * 32 + 2);
+    t.halo = (double*)(((size_t)t.halo + 7) & ~(size_t)7);
+    t.haloQ = (int*)(t.halo + 5 * TILE_MAXHALO);
+    t.cnt = t.haloQ + TILE_MAXHALO;
+    return t;
+}
+
+template <bool FWD>
+__device__ __forceinline__ void pfLoad(const TileArgs& a, const TileSmem& sm, int t0, int t1, int r, RowPf& d)
+{
+    d.r = r;
+    if (r < 0) { d.n = 0; return; }
+    const int p = t0 + r;
+    d.ln = p & 31;
+    d.base = (size_t)a.sliceOff[p >> 5];
+    const int nLow = sm.nLow[r];
+    if (FWD) { d.n = nLow; d.jFirst = 0; d.rd = 1.0; }
+    else { const int nInt = sm.nInt[r]; d.n = nInt - nLow; d.jFirst = nInt - 1; d.rd = sm.rDs[r]; }
+    const double* src = FWD ? a.x : a.y;
+#pragma unroll
+    for (int k = 0; k < 5; k++) d.own[k] = FWD ? src[k * a.NPH + p] : ldPoll(src + k * a.NPH + p);
+#pragma unroll
+    for (int t = 0; t < LCH; t++) {
+        d.q[t] = -1;
+        if (t < d.n) {
+            const int j = FWD ? (d.jFirst + t) : (d.jFirst - t);
+            const int q = (j < TILE_CW) ? sm.cols[((r >> 5) * TILE_CW + j) * 32 + d.ln] : a.col[(d.base + j) * 32 + d.ln];
+            d.q[t] = q;
+            d.sc[t] = FWD ? ((q >= t0) ? sm.rDs[q - t0] : (q >= 0 ? a.rD[q] : 1.0)) : 1.0;
+            const double* blk = a.offd + ((d.base + j) * 25) * 32 + d.ln;
+#pragma unroll
+            for (int k = 0; k < 25; k++) d.B[t][k] = __ldcs(blk + (size_t)k * 32);
+        }
+    }
+}
+
+template <bool FWD>
+__device__ __forceinline__ void pfProcess(const TileArgs& a, const TileSmem& sm, int t0, int t1, const RowPf& d, int MR)
+{
+    double* xs = sm.xs;
+    if (d.r < 0) return;
+    const int p = t0 + d.r;
+    double xr[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) xr[k] = d.own[k];
+    if (!FWD) {
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 5; k++) ok &= !isSentinel(xr[k]);
+        if (!ok) pollTile(a.y, a.hintF, a.sliceTile, a.epoch, a.NPH, p, xr, a.err);  // own forward value not published yet
+    }
+#pragma unroll
+    for (int t = 0; t < LCH; t++) {
+        if (t < d.n) {
+            double dl[5];
+            const int q = d.q[t];
+            if (q < 0) {  // staged out-of-tile value (forward: rD_q x_q already applied)
+#pragma unroll
+                for (int k = 0; k < 5; k++) dl[k] = sm.halo[k * TILE_MAXHALO + (-q - 1)];
+            } else {
+                const bool inTile = FWD ? (q >= t0) : (q < t1);
+                if (inTile) {
+#pragma unroll
+                    for (int k = 0; k < 5; k++) dl[k] = xs[k * MR + (q - t0)];
+                } else {
+                    pollTile(FWD ? a.y : a.z, FWD ? a.hintF : a.hintR, a.sliceTile, a.epoch, a.NPH, q, dl, a.err);
+                }
+                if (FWD) {
+#pragma unroll
+                    for (int k = 0; k < 5; k++) dl[k] = d.sc[t] * dl[k];  // dW*_q = rD_q x_q (lusgs.C:194-216)
+                }
+            }
+            lusgsSubReg(xr, d.B[t], dl);
+        }
+    }
+    for (int t = LCH; t < d.n; t++) {  // rows with more than LCH neighbours in this sweep (polyhedral cells)
+        const int j = FWD ? (d.jFirst + t) : (d.jFirst - t);
+        const int q = (j < TILE_CW) ? sm.cols[((d.r >> 5) * TILE_CW + j) * 32 + d.ln] : a.col[(d.base + j) * 32 + d.ln];
+        double dl[5];
+        if (q < 0) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) dl[k] = sm.halo[k * TILE_MAXHALO + (-q - 1)];
+        } else {
+            const bool inTile = FWD ? (q >= t0) : (q < t1);
+            if (inTile) {
+#pragma unroll
+                for (int k = 0; k < 5; k++) dl[k] = xs[k * MR + (q - t0)];
+            } else {
+                pollTile(FWD ? a.y : a.z, FWD ? a.hintF : a.hintR, a.sliceTile, a.epoch, a.NPH, q, dl, a.err);
+            }
+            if (FWD) {
+                const double sc = a.rD[q];
+#pragma unroll
+                for (int k = 0; k < 5; k++) dl[k] = sc * dl[k];
+            }
+        }
+        subBlockGlobal(xr, a.offd + ((d.base + j) * 25) * 32 + d.ln, dl);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const double v = FWD ? xr[k] : d.rd * xr[k];
+        xs[k * MR + d.r] = v;
+        __stcg((FWD ? a.y : a.z) + k * a.NPH + p, v);
+        if (!FWD) a.x[k * a.NPH + p] = v;
+    }
+}
+
+// Two thread groups alternate over the intra-tile levels: while group g computes level L from registers, the other
+// group's loads for level L+1 are in flight; after the barrier g issues its loads for level L+2.
+template <bool FWD>
+__device__ __forceinline__ void sweepTile(const TileArgs& a, int tile, double* smemBase, int MR)
+{
+    const TileSmem sm = carve(smemBase, MR);
+    if (threadIdx.x == 0) *sm.cnt = 0;
+    __syncthreads();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int GT = TILE_TPB / 2;  // threads per group
+    const int grp = tid / GT, gtid = tid % GT;
+    const int t0 = a.tileStart[tile], t1 = a.tileStart[tile + 1];
+    // pull this sweep's blocks and columns of the tile's slices into L2 while the predecessors finish
+    for (int s = (t0 >> 5) + warp; s < (t1 >> 5); s += TILE_TPB / 32) {
+        int nl = a.rowNLow[s * 32 + lane], ni = a.rowNInt[s * 32 + lane];
+        int lo, hi;
+        if (FWD) { lo = 0; hi = nl; }
+        else { lo = (ni > nl) ? nl : (1 << 20); hi = ni; }
+        for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+        if (hi > lo) {
+            const size_t e0 = (size_t)a.sliceOff[s] + lo;
+            const char* b = (const char*)(a.offd + e0 * 25 * 32);
+            const size_t bytes = (size_t)(hi - lo) * 25 * 32 * 8;
+            for (size_t off = (size_t)lane * 128; off < bytes; off += 32 * 128) prefetchL2(b + off);
+        }
+        // stage this slice's columns (first TILE_CW entries) in shared memory
+        const int wdt = a.sliceOff[s + 1] - a.sliceOff[s];
+        const int sl = s - (t0 >> 5);
+        const int myLow = a.rowNLow[s * 32 + lane], myInt = a.rowNInt[s * 32 + lane];
+        for (int j = 0; j < min(wdt, TILE_CW); j++) {
+            int q = a.col[((size_t)a.sliceOff[s] + j) * 32 + lane];
+            // entries of THIS sweep that point outside the tile get a halo slot
+            const bool mineSweep = FWD ? (j < myLow) : (j >= myLow && j < myInt);
+            if (mineSweep && (FWD ? (q < t0) : (q >= t1))) {
+                const int slot = atomicAdd(sm.cnt, 1);
+                if (slot < TILE_MAXHALO) { sm.haloQ[slot] = q; q = -(slot + 1); }
+            }
+            sm.cols[(sl * TILE_CW + j) * 32 + lane] = q;
+        }
+    }
+    for (int r = tid; r < t1 - t0; r += TILE_TPB) { sm.nLow[r] = a.rowNLow[t0 + r]; sm.nInt[r] = a.rowNInt[t0 + r]; sm.rDs[r] = a.rD[t0 + r]; }
+    __syncthreads();
+    {
+        // wait for the predecessor tiles once and stage every out-of-tile neighbour value of this sweep
+        const int nH = min(*sm.cnt, TILE_MAXHALO);
+        for (int h = tid; h < nH; h += TILE_TPB) {
+            const int q = sm.haloQ[h];
+            double v[5];
+            pollTile(FWD ? a.y : a.z, FWD ? a.hintF : a.hintR, a.sliceTile, a.epoch, a.NPH, q, v, a.err);
+            const double sc = FWD ? a.rD[q] : 1.0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) sm.halo[k * TILE_MAXHALO + h] = FWD ? sc * v[k] : v[k];
+        }
+    }
+    __syncthreads();
+    const int* lev = FWD ? a.tileFLev : a.tileRLev;
+    const int lp0 = FWD ? a.tileFPtr[tile] : a.tileRPtr[tile];
+    const int nLev = (FWD ? a.tileFPtr[tile + 1] : a.tileRPtr[tile + 1]) - lp0 - 1;
+    auto rowOf = [&](int L, int i) -> int {  // i-th row of level L handled by this thread, or -1
+        if (L >= nLev) return -1;
+        const int r0 = lev[lp0 + L], r1 = lev[lp0 + L + 1];
+        const int idx = r0 + i * GT + gtid;
+        if (idx >= r1) return -1;
+        return FWD ? idx : a.tileRRows[t0 + idx];
+    };
+    RowPf cur;
+    pfLoad<FWD>(a, sm, t0, t1, rowOf(grp, 0), cur);  // group 0 starts with level 0, group 1 with level 1
+    for (int L = 0; L < nLev; L++) {
+        const bool mine = (L & 1) == grp;
+        if (mine) {
+            pfProcess<FWD>(a, sm, t0, t1, cur, MR);
+            const int width = lev[lp0 + L + 1] - lev[lp0 + L];
+            for (int i = 1; i * GT < width; i++) {  // levels wider than a group: remaining rows, unpipelined
+                pfLoad<FWD>(a, sm, t0, t1, rowOf(L, i), cur);
+                pfProcess<FWD>(a, sm, t0, t1, cur, MR);
+            }
+        }
+        __syncthreads();
+        if (mine) pfLoad<FWD>(a, sm, t0, t1, rowOf(L + 2, 0), cur);
+    }
+    if (tid == 0) __stcg((FWD ? a.hintF : a.hintR) + tile, a.epoch);
+    __syncthreads();  // the staged metadata is reused by the next tile
+}
+
+__global__ void __launch_bounds__(TILE_TPB)
+k_lusgs_tile(TileArgs a)
+{
+    extern __shared__ double xs[];  // [5][maxRows]
+    const int MR = a.maxRows;
+    for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) sweepTile<true>(a, tile, xs, MR);        // forward, ascending
+    for (int tt = blockIdx.x; tt < a.nTiles; tt += gridDim.x) sweepTile<false>(a, a.nTiles - 1 - tt, xs, MR);  // reverse, descending
+}
+
 __global__ void k_fill_sentinel(size_t n, unsigned long long* __restrict__ a, unsigned long long* __restrict__ b)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -643,6 +931,37 @@ int ics_lusgs(icsb200_ctx* c, double* x)
         if ((r = devAlloc(c, &c->d_lusgsHint, (size_t)2 * c->nSlices))) return r;
         CUDA_TRY(c, cudaMemsetAsync(c->d_lusgsHint, 0, sizeof(int) * 2 * c->nSlices, c->stream));
         c->lusgsEpoch = 0;
+    }
+    if (c->tileMode) {
+        TileArgs t{};
+        t.nTiles = c->nTiles;
+        t.tileStart = c->d_tileStart; t.tileFPtr = c->d_tileFPtr; t.tileFLev = c->d_tileFLev; t.tileRPtr = c->d_tileRPtr;
+        t.tileRLev = c->d_tileRLev; t.tileRRows = c->d_tileRRows; t.sliceTile = c->d_sliceTile;
+        t.sliceOff = c->d_sliceOff; t.rowNLow = c->d_rowNLow; t.rowNInt = c->d_rowNInt; t.col = c->d_col;
+        t.offd = c->d_offd; t.rD = c->d_rD; t.x = x; t.NPH = c->NPH;
+        t.y = c->d_lusgsYZ; t.z = c->d_lusgsYZ + V5;
+        t.hintF = c->d_lusgsHint; t.hintR = c->d_lusgsHint + c->nSlices; t.epoch = ++c->lusgsEpoch;
+        t.err = (int*)c->d_counter + 48;
+        t.maxRows = c->tileMaxRows;
+        const size_t smem = (size_t)c->tileMaxRows * (6 * sizeof(double) + (2 + TILE_CW) * sizeof(int)) + 5 * TILE_MAXHALO * sizeof(double) + (TILE_MAXHALO + 8) * sizeof(int) + 64;
+        if (c->lusgsTileGrid == 0) {
+            int perSM = 0;
+            CUDA_TRY(c, cudaFuncSetAttribute(k_lusgs_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_lusgs_tile, TILE_TPB, smem));
+            if (perSM < 1) return ics_fail(c, ICSB200_ECUDA, "lusgs tile kernel does not fit on an SM");
+            c->lusgsTileGrid = c->numSMs * perSM;
+        }
+        int grid = std::min(c->lusgsTileGrid, c->nTiles);
+        {
+            static const char* e3 = getenv("ICSB200_LUSGS_GRID");
+            if (e3) grid = std::min(grid, std::max(1, atoi(e3)));
+        }
+        LaunchScope ls(c, TM_LUSGS);
+        k_fill_sentinel<<<gridFor(V5, 256), 256, 0, c->stream>>>(V5, (unsigned long long*)t.y, (unsigned long long*)t.z);
+        c->launches++;
+        void* targs[] = {&t};
+        CUDA_TRY(c, cudaLaunchCooperativeKernel((void*)k_lusgs_tile, dim3(grid), dim3(TILE_TPB), targs, smem, c->stream));
+        return 0;
     }
     LusgsArgs a{};
     a.nSlices = c->nSlices;

@@ -181,8 +181,9 @@ int icsb200_timers_reset(icsb200_ctx* ctx, int enable);
 /* device-side stopwatch: CUDA events recorded on the library's compute stream (bench.py times its steps with these) */
 int icsb200_timer_begin(icsb200_ctx* ctx);
 int icsb200_timer_end(icsb200_ctx* ctx, double* elapsed_ms);
-/* LU-SGS level schedule statistics: n_levels_fwd, n_levels_rev, max_width, n_positions */
-int icsb200_schedule_info(icsb200_ctx* ctx, int out[4]);
+/* LU-SGS schedule statistics: n_levels_fwd, n_levels_rev, max_level_width, n_positions, tile_mode (0/1), n_tiles,
+ * n_tile_levels, reserved */
+int icsb200_schedule_info(icsb200_ctx* ctx, int out[8]);
 
 #ifdef __cplusplus
 }

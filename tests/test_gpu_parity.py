@@ -197,3 +197,26 @@ def test_iterate_host_round_trip(gpu_context):
         b.iterate_host(case.controls, p, U, T)
     sa = a.state_get()
     assert rel_err(p, sa["p"]) < 1e-9 and rel_err(U, sa["U"]) < 1e-9 and rel_err(T, sa["T"]) < 1e-9
+
+
+def test_lusgs_tile_mode_is_bit_identical(gpu_context, monkeypatch):
+    """ICSB200_LUSGS_MODE=tile (blocked wavefront schedule) must reproduce the level pipeline and the oracle bit for bit."""
+    monkeypatch.setenv("ICSB200_LUSGS_MODE", "tile")
+    case = cases.onera_box(20)
+    g = case.apply(gpu_context())
+    assert g.schedule_info()["tile_mode"] and g.schedule_info()["n_tiles"] >= 8
+    monkeypatch.delenv("ICSB200_LUSGS_MODE")
+    o = case.apply(Oracle())
+    for api in (g, o):
+        api.calc_flux(); api.residual(); api.pseudo_dt(); api.assemble()
+    rng = np.random.default_rng(3)
+    N = case.mesh.n_cells
+    x = (rng.standard_normal(N), rng.standard_normal((N, 3)), rng.standard_normal(N))
+    for a, b in zip(g.precondition("LUSGS", *x), o.precondition("LUSGS", *x)):
+        assert np.array_equal(a, b)
+    for a, b in zip(g.matrix_mul(*x), o.matrix_mul(*x)):
+        assert np.array_equal(a, b)
+    for _ in range(2):
+        rg, ro = g.iterate(case.controls), o.iterate(case.controls)
+        assert rg.n_iterations == ro.n_iterations
+    assert rel_err(g.state_get()["rho"], o.state_get()["rho"]) < 1e-10
