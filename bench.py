@@ -7,7 +7,7 @@ A "step" is one outer pseudo-time iteration of dbnsFoam (outerLoop.H:51-99 + upd
 residual, local pseudo time step, Jacobian assembly, GMRES(m)/LU-SGS solve, field update.
 Workload at N=1: the synthetic OneraM6-scale 3-D transonic mesh of SURVEY.md §8d (config C4; the shipped OneraM6
 mesh is incomplete in the reference checkout), HLLC + vanLeer, steady, Co=100, GMRES m=5 maxIter 10 relTol 0.1 with
-LU-SGS, at the largest size that fits one GPU within the default run time (--n cells per direction).
+LU-SGS, at 344^3 = 40.7 M cells (the OneraM6-scale size of BASELINE.json; ~100 GB of HBM; --cells-per-dim to change).
 Prints ONE JSON line.  `value` = device-resident throughput (inputs in HBM), `e2e` = the same iteration through
 icsb200_iterate_host with pinned host buffers (p,U,T in and out every step).
 """
@@ -83,62 +83,81 @@ def make_case(n):
     return cases.onera_box(n)
 
 
-def cpu_baseline(n_cpu, threads, iters):
-    """The CPU restatement (oracle 'port') on the host cores: P partitions on P threads, mirroring P MPI ranks."""
-    from oracle.pyoracle import Oracle, World
-    case = make_case(n_cpu)
-    if threads > 1:
-        part, meshes = case.partition(threads, "x")
-        world = World(threads)
-        world.mesh_set(meshes)
-        for r, o in enumerate(world.ranks):
-            o.thermo_set(case.R, case.Cp, case.mu, case.Pr)
-            o.schemes_set(case.schemes)
-            names = [p["name"] for p in meshes[r].patches]
-            for patch, fields in case.bcs.items():
-                if patch in names:
-                    for field, (kind, params) in fields.items():
-                        o.bc_set(patch, {"p": 0, "U": 1, "T": 2}[field], kind, params)
-        world.state_set([case.p[m.cell_global] for m in meshes], [case.U[m.cell_global] for m in meshes],
-                        [case.T[m.cell_global] for m in meshes])
-        world.iterate(case.controls, 1)  # warm-up
+class CpuRun:
+    """The CPU restatement (oracle 'port') on the host cores: P partitions on P threads, mirroring P MPI ranks
+    (halo exchange between threads, rank-ordered reductions, LU-SGS local to each partition as lusgs.C:149,181)."""
+
+    def __init__(self, n_cpu, threads):
+        from icsfoam_b200 import cases
+        from oracle.pyoracle import Oracle, World
+        self.threads = threads
+        if threads > 1:
+            px = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2), 16: (4, 2, 2), 32: (4, 4, 2)}.get(threads, (threads, 1, 1))
+            parts = [cases.onera_box(n_cpu, parts=px, rank=r) for r in range(threads)]
+            self.case = parts[0]
+            self.world = World(threads)
+            self.world.mesh_set([c.mesh for c in parts])
+            for o, c in zip(self.world.ranks, parts):
+                o.thermo_set(c.R, c.Cp, c.mu, c.Pr)
+                o.schemes_set(c.schemes)
+                names = [p["name"] for p in c.mesh.patches]
+                for patch, fields in c.bcs.items():
+                    if patch in names:
+                        for field, (kind, params) in fields.items():
+                            o.bc_set(patch, {"p": 0, "U": 1, "T": 2}[field], kind, params)
+            self.world.state_set([c.p for c in parts], [c.U for c in parts], [c.T for c in parts])
+            self.n_cells = n_cpu ** 3
+        else:
+            self.case = cases.onera_box(n_cpu)
+            self.single = self.case.apply(Oracle())
+            self.n_cells = self.case.mesh.n_cells
+
+    def iterate(self, iters):
         t0 = time.perf_counter()
-        res = world.iterate(case.controls, iters)
+        if self.threads > 1:
+            res = self.world.iterate(self.case.controls, iters)
+        else:
+            for _ in range(iters):
+                res = self.single.iterate(self.case.controls)
         dt = time.perf_counter() - t0
-    else:
-        o = case.apply(Oracle())
-        o.iterate(case.controls)
-        t0 = time.perf_counter()
-        for _ in range(iters):
-            res = o.iterate(case.controls)
-        dt = time.perf_counter() - t0
-    return case.mesh.n_cells * iters / dt / 1e6, dt, res.n_iterations
+        return self.n_cells * iters / dt / 1e6, dt, res.n_iterations
+
+
+def host_threads():
+    cores = os.cpu_count() or 1
+    t = 1
+    while t * 2 <= min(cores, 32):
+        t *= 2
+    return t
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU path cannot be built here (OpenFOAM v2112 absent), so this arm times the
+    CPU restatement with all host threads it can use; each step is one outer iteration of a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    threads = max(1, min(cores, 32))
-    n_cpu = args.n_cpu
-    vals = []
+    threads = host_threads()
+    run = CpuRun(args.n_cpu, threads)
     for _ in range(args.warmup):
-        cpu_baseline(n_cpu, threads, 1)
-    t_all = 0.0
+        run.iterate(1)
+    vals, t_all, restarts = [], 0.0, []
     for _ in range(args.steps):
-        v, dt, r = cpu_baseline(n_cpu, threads, 1)
-        vals.append(v); t_all += dt
-    value = float(np.mean(vals))
+        v, dt, r = run.iterate(1)
+        vals.append(v); t_all += dt; restarts.append(r)
+    value = run.n_cells * args.steps / t_all / 1e6
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"onera-box {args.n}^3 (C4 synthetic OneraM6-scale), HLLC vanLeer steady Co=100, GMRES m=5 LU-SGS",
-                       "note": "CPU restatement of the ICSFoam path (OpenFOAM v2112 cannot be built here); bounded sample"},
+            "config": {"workload": f"onera-box {args.n}^3 (C4 synthetic OneraM6-scale 3-D transonic), HLLC vanLeer steady Co=100, GMRES m=5 "
+                                   f"maxIter 10 relTol 0.1, LU-SGS",
+                       "restarts_per_step": float(np.mean(restarts)),
+                       "note": "CPU restatement of the ICSFoam path (OpenFOAM v2112 cannot be built here); bounded sample of the workload"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"onera-box {n_cpu}^3 ({n_cpu**3} cells), 1 iteration per step, {threads} partitions on {threads} threads"},
+                             "sample": f"onera-box {args.n_cpu}^3 ({args.n_cpu**3} cells), 1 outer iteration per step, {threads} partitions "
+                                       f"on {threads} threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -147,9 +166,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--cells-per-dim", "--n", dest="n", type=int, default=int(os.environ.get("ICSB200_BENCH_N", "256")),
+    ap.add_argument("--cells-per-dim", "--n", dest="n", type=int, default=int(os.environ.get("ICSB200_BENCH_N", "344")),
                     help="cells per direction of the 3-D mesh (use the long form under torchrun)")
-    ap.add_argument("--cpu-cells-per-dim", "--n-cpu", dest="n_cpu", type=int, default=96, help="cells per direction of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-cells-per-dim", "--n-cpu", dest="n_cpu", type=int, default=128, help="cells per direction of the bounded CPU-baseline sample")
     ap.add_argument("--skip-cpu", "--no-cpu", dest="no_cpu", action="store_true")
     ap.add_argument("--skip-e2e", "--no-e2e", dest="no_e2e", action="store_true")
     args = ap.parse_args()
@@ -269,12 +288,13 @@ def main():
         return
     cpu = None
     if not args.no_cpu and not multi:
-        cores = os.cpu_count() or 1
-        threads = max(1, min(cores, 32))
-        v, dt, r = cpu_baseline(args.n_cpu, threads, 2)
+        threads = host_threads()
+        run = CpuRun(args.n_cpu, threads)
+        run.iterate(1)
+        v, dt, r = run.iterate(3)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"onera-box {args.n_cpu}^3 ({args.n_cpu**3} cells), 2 iterations, {threads} partitions on {threads} threads, {dt:.1f} s; "
-                         f"CPU restatement of the ICSFoam path, not the OpenFOAM binary"}
+               "sample": f"onera-box {args.n_cpu}^3 ({args.n_cpu**3} cells), 3 outer iterations ({r} restarts in the last), {threads} partitions on "
+                         f"{threads} threads, {dt:.1f} s; CPU restatement of the ICSFoam path, not the OpenFOAM binary"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",

@@ -250,7 +250,7 @@ __device__ __forceinline__ Flux5 faceFlux(const FaceState& s, V3 Sf, double magS
 
 // ------------------------------------------------------------------------------------------------ k_grad
 // gaussGrad::gradf for the NQ reconstructed scalars.  f: fields [Q_COUNT][NX]; grad: [NQ*3][NPH]
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_grad(int NP, const int* __restrict__ pos2cell, const int* __restrict__ sliceOff, const int* __restrict__ rowNAll, const int* __restrict__ col,
        const int* __restrict__ meta, const int* __restrict__ gfid, const double* __restrict__ geo, size_t NFG, const double* __restrict__ V,
        const double* __restrict__ f, size_t NX, double* __restrict__ grad, size_t NPH)
@@ -343,7 +343,7 @@ __device__ __forceinline__ void reconstructFace(const FluxArgs& a, int p, int c,
 }
 
 template <int SCHEME>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_flux(FluxArgs a)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -80,7 +80,7 @@ __device__ __forceinline__ void eulerJacobian(V3 U, double E, V3 n, double gamma
 
 __device__ __forceinline__ bool isDiagEntry(int k) { return k == 0 || k == 6 || k == 12 || k == 18 || k == 24; }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 k_jac(JacArgs a)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
