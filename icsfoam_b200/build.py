@@ -79,6 +79,18 @@ def build_product(force=False, verbose=False):
     return out
 
 
+def build_host(force=False):
+    """C++ host mirror of the reference plugin interface + the standalone driver dbnsB200 (links libicsb200.so)."""
+    host = os.path.join(_PKG, "host")
+    src = os.path.join(host, "dbnsB200.cpp")
+    hdr = os.path.join(host, "icsfoamB200.H")
+    out = os.path.join(host, "dbnsB200")
+    if force or _newer(out, [src, hdr, os.path.join(_ROOT, "include", "icsb200.h")]):
+        _run(["g++", "-O2", "-std=c++17", "-I", os.path.join(_ROOT, "include"), "-I", host, src, "-o", out, "-L", _PKG, "-licsb200",
+              "-Wl,-rpath," + _PKG, "-Wl,-rpath,/usr/local/cuda/lib64", "-ldl"])
+    return out
+
+
 def build_oracle(force=False):
     d = os.path.join(_ROOT, "oracle")
     if force:
@@ -91,3 +103,4 @@ def build_all(force=False):
     build_meshtools(force)
     build_oracle(force)
     build_product(force)
+    build_host(force)

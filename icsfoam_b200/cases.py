@@ -145,3 +145,42 @@ def periodic_box(n=8, flux="HLLC", limiter="vanLeer", seed=0, nz=None):
                  "T": ("fixedValue", (305.0,))},
     }
     return Case("periodic-box", mesh, 287.0, 1005.0, sch, ctl, bcs, p, U, T)
+
+
+def scrambled_box(n=6, flux="HLLC", limiter="vanLeer", seed=0):
+    """A box whose cells are renumbered at random: irregular LU-SGS levels, rows with up to 6 lower (or upper)
+    neighbours, no structure for the tile heuristics to find — the 'unstructured numbering' stress case."""
+    base = periodic_box(n, flux, limiter, seed)
+    rng = np.random.default_rng(seed + 1000)
+    perm = rng.permutation(base.mesh.n_cells).astype(np.int32)
+    mesh = base.mesh.renumber(perm)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size, dtype=np.int32)
+    # the cyclic pair survives renumbering only if both patches keep matching face order: re-pair by face centre
+    for p in mesh.patches:
+        if p["kind"] == capi.CYCLIC:
+            p["kind"], p["nbr_patch"] = capi.PATCH, -1
+    c = Case("scrambled-box", mesh, base.R, base.Cp, base.schemes, base.controls,
+             {k: v for k, v in base.bcs.items()}, base.p[inv], base.U[inv], base.T[inv])
+    return c
+
+
+def forward_step(polymesh_dir):
+    """C2 tutorials/forwardStep: Mach-3 step on the shipped polyhedral 2-D mesh (36 576 cells), HLLC, Minmod, transient
+    dual time (backward, deltaT 1e-3), GMRES m=8 maxIter 20 relTol 1e-4, LU-SGS.  The mesh is read from `polymesh_dir`
+    (the reference's constant/polyMesh — input data, never copied into this repository)."""
+    mesh = mt.read_polymesh(polymesh_dir)
+    R, Cp = RR / 11640.3, 2.5          # "normalised" gas: c = 1 m/s at T = 1 K, gamma = 7/5
+    p, U, T = _uniform(mesh, 1.0, (3.0, 0, 0), 1.0)
+    sch = capi.default_schemes(flux_scheme="HLLC", limiter_rho="Minmod", limiter_U="Minmod", limiter_T="Minmod",
+                               ddt_scheme="backward", delta_t=1e-3, pseudo_co_num=1.0, pseudo_co_num_max=10.0)
+    ctl = capi.solver_controls("LUSGS", n_directions=8, max_iter=20, tolerance=1e-12, rel_tol=1e-4)
+    zg, slip = ("zeroGradient", ()), ("slip", ())
+    bcs = {
+        "inlet": {"p": ("fixedValue", (1.0,)), "U": ("fixedValue", (3.0, 0, 0)), "T": ("fixedValue", (1.0,))},
+        "outlet": {"p": zg, "U": ("inletOutlet", (3.0, 0, 0)), "T": ("inletOutlet", (1.0,))},
+        "bottom": {"p": slip, "U": slip, "T": slip},
+        "top": {"p": slip, "U": slip, "T": slip},
+        "obstacle": {"p": zg, "U": slip, "T": zg},
+    }
+    return Case("forwardStep", mesh, R, Cp, sch, ctl, bcs, p, U, T, n_iter_default=50)

@@ -1,0 +1,251 @@
+// dbnsB200 — standalone driver: dbnsFoam's time / pseudo-time loop (dbnsFoam.C:88-151, outerLoop.H, updateFields.H,
+// pseudotimeControl.C:72-101,159-241) over the icsb200 C ABI, reading an OpenFOAM case directory verbatim:
+//   constant/polyMesh/{points,faces,owner,neighbour,boundary}, constant/thermophysicalProperties,
+//   system/{controlDict,fvSchemes,fvSolution}, 0/{p,U,T} (uniform internalField + boundaryField types).
+// It exists because OpenFOAM v2112 is not available in this image (the OpenFOAM adapter is shown in INTEGRATION.md);
+// the dictionary keys are the reference's (SURVEY.md §5 "Config / flags").
+//
+//   dbnsB200 <caseDir> [-maxSteps N] [-device D]
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+
+#include "icsfoamB200.H"
+
+using namespace icsfoamB200;
+
+namespace {
+
+// ---- meshtools C API (libicsmesh.so), loaded at run time ----
+struct MeshLib {
+    void* h = nullptr;
+    void* (*read_polymesh)(const char*) = nullptr;
+    const char* (*error)(void*) = nullptr;
+    void (*sizes)(void*, int*) = nullptr;
+    void (*patch)(void*, int, int*, char*) = nullptr;
+    void (*arrays)(void*, int*, int*, double*, double*, double*, double*, double*, double*, double*, double*) = nullptr;
+    void (*free_)(void*) = nullptr;
+    explicit MeshLib(const std::string& path)
+    {
+        h = dlopen(path.c_str(), RTLD_NOW);
+        if (!h) throw FatalError(std::string("cannot load ") + path + ": " + dlerror());
+        read_polymesh = (decltype(read_polymesh))dlsym(h, "icsmesh_read_polymesh");
+        error = (decltype(error))dlsym(h, "icsmesh_error");
+        sizes = (decltype(sizes))dlsym(h, "icsmesh_sizes");
+        patch = (decltype(patch))dlsym(h, "icsmesh_patch");
+        arrays = (decltype(arrays))dlsym(h, "icsmesh_arrays");
+        free_ = (decltype(free_))dlsym(h, "icsmesh_free");
+    }
+};
+
+struct BcSpec { int kind; std::vector<double> prm; };
+
+std::vector<double> numbers(const std::vector<std::string>& toks)
+{
+    std::vector<double> v;
+    for (auto& t : toks) {
+        char* end = nullptr;
+        double x = std::strtod(t.c_str(), &end);
+        if (end && *end == 0 && !t.empty()) v.push_back(x);
+    }
+    return v;
+}
+
+// fvPatchField type name -> ICSB200_BC_* + parameters (the BC set of the five tutorials)
+BcSpec bcFromDict(const dictionary& d, int field, const std::vector<double>& Uinf)
+{
+    const std::string type = d.word("type");
+    BcSpec b{ICSB200_BC_ZEROGRADIENT, {}};
+    auto val = [&](const char* k) { return numbers(d.lookup(k)); };
+    if (type == "zeroGradient") b.kind = ICSB200_BC_ZEROGRADIENT;
+    else if (type == "fixedValue") { b.kind = ICSB200_BC_FIXEDVALUE; b.prm = val("value"); }
+    else if (type == "slip" || type == "symmetryPlane" || type == "symmetry") b.kind = ICSB200_BC_SLIP;
+    else if (type == "empty") b.kind = ICSB200_BC_EMPTY;
+    else if (type == "inletOutlet") { b.kind = ICSB200_BC_INLETOUTLET; b.prm = val("inletValue"); }
+    else if (type == "freestream") { b.kind = ICSB200_BC_INLETOUTLET; b.prm = val("freestreamValue"); }
+    else if (type == "totalPressure") { b.kind = ICSB200_BC_TOTALPRESSURE; b.prm = {val("p0").at(0), d.get<double>("gamma")}; }
+    else if (type == "totalTemperature") { b.kind = ICSB200_BC_TOTALTEMPERATURE; b.prm = {val("T0").at(0), d.get<double>("gamma")}; }
+    else if (type == "pressureInletOutletVelocity") {
+        b.kind = ICSB200_BC_PRESSUREINLETOUTLETVELOCITY;
+        b.prm = d.found("tangentialVelocity") ? val("tangentialVelocity") : std::vector<double>{0, 0, 0};
+    } else if (type == "freestreamPressure") {
+        b.kind = ICSB200_BC_FREESTREAMPRESSURE;
+        b.prm = {val("freestreamValue").at(0), Uinf.at(0), Uinf.at(1), Uinf.at(2)};
+    } else if (type == "noSlip") { b.kind = ICSB200_BC_FIXEDVALUE; b.prm = {0, 0, 0}; }
+    else if (type == "cyclic" || type == "processor") b.kind = ICSB200_BC_COUPLED;
+    else throw FatalError("unsupported patch field type " + type + " (supported: zeroGradient fixedValue slip symmetryPlane empty inletOutlet "
+                          "freestream totalPressure totalTemperature pressureInletOutletVelocity freestreamPressure noSlip)");
+    (void)field;
+    return b;
+}
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    try {
+        if (argc < 2) { std::fprintf(stderr, "usage: dbnsB200 <caseDir> [-maxSteps N] [-device D]\n"); return 2; }
+        const std::string caseDir = argv[1];
+        int maxSteps = 1 << 30, device = 0;
+        for (int i = 2; i + 1 < argc; i += 2) {
+            if (!std::strcmp(argv[i], "-maxSteps")) maxSteps = std::atoi(argv[i + 1]);
+            else if (!std::strcmp(argv[i], "-device")) device = std::atoi(argv[i + 1]);
+        }
+        const char* libEnv = std::getenv("ICSMESH_LIB");
+        MeshLib ml(libEnv ? libEnv : "libicsmesh.so");
+
+        // ---- dictionaries
+        const dictionary controlDict = dictionary::fromFile(caseDir + "/system/controlDict");
+        const dictionary fvSchemes = dictionary::fromFile(caseDir + "/system/fvSchemes");
+        const dictionary fvSolution = dictionary::fromFile(caseDir + "/system/fvSolution");
+        const dictionary thermoDict = dictionary::fromFile(caseDir + "/constant/thermophysicalProperties");
+        const dictionary pDict = dictionary::fromFile(caseDir + "/0/p"), UDict = dictionary::fromFile(caseDir + "/0/U"),
+                         TDict = dictionary::fromFile(caseDir + "/0/T");
+
+        // ---- mesh
+        void* mh = ml.read_polymesh((caseDir + "/constant/polyMesh").c_str());
+        if (ml.error(mh)[0]) throw FatalError(ml.error(mh));
+        int sz[7];
+        ml.sizes(mh, sz);
+        const int N = sz[0], F = sz[1], FT = sz[2], nP = sz[3];
+        std::vector<int> owner(FT), neighbour(F);
+        std::vector<double> Sf(3 * (size_t)FT), Cf(3 * (size_t)FT), magSf(FT), w(FT), dc(FT), nodc(FT), C(3 * (size_t)N), V(N);
+        ml.arrays(mh, owner.data(), neighbour.data(), Sf.data(), Cf.data(), magSf.data(), w.data(), dc.data(), nodc.data(), C.data(), V.data());
+        std::vector<icsb200_patch> patches(nP);
+        std::vector<std::string> patchNames(nP);
+        for (int i = 0; i < nP; i++) {
+            int o[5];
+            char name[64];
+            ml.patch(mh, i, o, name);
+            patchNames[i] = name;
+            patches[i] = icsb200_patch{o[0], o[1], o[2], o[3], o[4], {1, 0, 0, 0, 1, 0, 0, 0, 1}};
+            if (o[0] == ICSB200_CYCLIC) throw FatalError("cyclic patches need the neighbourPatch entry: not wired in the standalone reader yet");
+        }
+        std::cout << "Mesh: " << N << " cells, " << F << " internal faces, " << nP << " patches\n";
+
+        icsb200_ctx* ctx = nullptr;
+        check(nullptr, icsb200_create(&ctx, device, nullptr, 0, 1), "icsb200_create (needs a B200; there is no CPU fallback)");
+        check(ctx, icsb200_mesh_set(ctx, N, F, FT, owner.data(), neighbour.data(), Sf.data(), magSf.data(), w.data(), dc.data(), nodc.data(),
+                                    C.data(), V.data(), Cf.data(), nP, patches.data(), sz + 4), "mesh_set");
+
+        // ---- thermo: hePsiThermo<pureMixture<constTransport<hConst<perfectGas>>>>, sensibleInternalEnergy (createFields.H:17-35)
+        const dictionary& mix = thermoDict.subDict("mixture");
+        const double W = mix.subDict("specie").get<double>("molWeight"), Cp = mix.subDict("thermodynamics").get<double>("Cp");
+        const double mu = mix.subDict("transport").get<double>("mu"), Pr = mix.subDict("transport").get<double>("Pr");
+        if (mix.subDict("thermodynamics").getOrDefault<double>("Tref", 0.0) != 0.0) throw FatalError("Tref != 0 is not supported");
+        check(ctx, icsb200_thermo_set(ctx, 8314.46261815324 / W, Cp, mu, Pr), "thermo_set");
+        if (mu > 0) std::cout << "Viscous analysis detected: only the Lax-Friedrichs viscous Jacobian is on the device (viscous residual: next round)\n";
+
+        // ---- schemes (fvSchemes / fvSolution pseudoTime; initialise.H:39-71, beginTimeStep.H:8-45, updateFields.H:11-35)
+        auto flux = convectiveFluxScheme::New(ctx, fvSchemes);
+        const dictionary& interp = fvSchemes.subDict("interpolationSchemes");
+        const dictionary& pseudo = fvSolution.subDict("pseudoTime");
+        icsb200_schemes sch{};
+        sch.flux_scheme = flux->id();
+        sch.limiter_rho = limiterId(interp.word("reconstruct(rho)"));
+        sch.limiter_U = limiterId(interp.word("reconstruct(U)"));
+        sch.limiter_T = limiterId(interp.word("reconstruct(T)"));
+        const dictionary& cfs = fvSchemes.subDict("convectiveFluxScheme");
+        sch.low_mach_ausm = cfs.getSwitch("lowMachAusm", true);
+        sch.entropy_fix_coeff = cfs.getOrDefault<double>("entropyFixCoeff", 0.05);
+        const std::vector<std::string>& ddt = fvSchemes.subDict("ddtSchemes").lookup("default");
+        if (ddt.at(0) != "dualTime") throw FatalError("ddtSchemes default must be 'dualTime rPseudoDeltaT <inner>' (dualTimeDdtScheme.H:103)");
+        const std::string inner = ddt.back();
+        const bool steadyState = inner == "steadyState";
+        sch.ddt_scheme = steadyState ? ICSB200_DDT_STEADY : inner == "Euler" ? ICSB200_DDT_EULER : ICSB200_DDT_BACKWARD;
+        sch.delta_t = controlDict.get<double>("deltaT");
+        sch.local_timestepping = pseudo.getSwitch("localTimestepping", true);
+        sch.local_timestepping_bounding = pseudo.getSwitch("localTimesteppingBounding", true);
+        sch.local_timestepping_lower_bound = std::min(std::max(pseudo.getOrDefault<double>("localTimesteppingLowerBound", 0.95), 0.0), 0.99);
+        sch.pseudo_co_num = pseudo.getOrDefault<double>("pseudoCoNum", 1.0);
+        sch.pseudo_co_num_min = pseudo.getOrDefault<double>("pseudoCoNumMin", 0.1);  // 'pseudoCoMin' is never read (Q11)
+        sch.pseudo_co_num_max = pseudo.getOrDefault<double>("pseudoCoNumMax", 25.0);
+        sch.pseudo_co_num_max_incr = pseudo.getOrDefault<double>("pseudoCoNumMaxIncreaseFactor", 1.25);
+        sch.pseudo_co_num_min_decr = pseudo.getOrDefault<double>("pseudoCoNumMinDecreaseFactor", 0.1);
+        sch.rho_min = pseudo.getOrDefault<double>("rhoMin", -1e15);
+        sch.T_min = pseudo.getOrDefault<double>("TMin", 1e-15);
+        sch.T_max = pseudo.getOrDefault<double>("TMax", 1e15);
+        check(ctx, icsb200_schemes_set(ctx, &sch), "schemes_set");
+        std::cout << (steadyState ? "Steady-state analysis detected\n" : "Transient analysis detected\n");
+
+        // ---- boundary conditions and initial fields
+        const std::vector<double> U0 = numbers(UDict.lookup("internalField"));
+        const double p0 = numbers(pDict.lookup("internalField")).at(0), T0 = numbers(TDict.lookup("internalField")).at(0);
+        if (UDict.lookup("internalField").at(0) != "uniform") throw FatalError("only uniform internalField is supported by the standalone reader");
+        const dictionary *bf[3] = {&pDict.subDict("boundaryField"), &UDict.subDict("boundaryField"), &TDict.subDict("boundaryField")};
+        for (int pi = 0; pi < nP; pi++)
+            for (int fld = 0; fld < 3; fld++) {
+                if (!bf[fld]->isDict(patchNames[pi])) throw FatalError("patch " + patchNames[pi] + " missing in boundaryField");
+                BcSpec b = bcFromDict(bf[fld]->subDict(patchNames[pi]), fld, U0);
+                if (b.kind == ICSB200_BC_EMPTY || b.kind == ICSB200_BC_COUPLED) continue;
+                check(ctx, icsb200_bc_set(ctx, pi, fld, b.kind, b.prm.data(), (int)b.prm.size()), "bc_set");
+            }
+        std::vector<double> p(N, p0), T(N, T0), U(3 * (size_t)N);
+        for (int i = 0; i < N; i++) for (int d = 0; d < 3; d++) U[3 * (size_t)i + d] = U0.at(d);
+        check(ctx, icsb200_state_set(ctx, p.data(), U.data(), T.data()), "state_set");
+
+        // ---- solver controls (fvSolution/flowSolver) and pseudo-time control (pseudotimeControl.C:42-69)
+        const icsb200_solver_controls ctl = coupledMatrix::controlsFromDict(fvSolution.subDict("flowSolver"));
+        coupledMatrix eqSystem(ctx);
+        (void)eqSystem;
+        const int nCorrOuter = pseudo.getOrDefault<int>("nPseudoCorr", 20), nCorrOuterMin = pseudo.getOrDefault<int>("nPseudoCorrMin", 1);
+        const double pseudoTol = pseudo.get<double>("pseudoTol"), pseudoTolRel = pseudo.get<double>("pseudoTolRel");
+        const double endTime = controlDict.get<double>("endTime"), deltaT = controlDict.get<double>("deltaT");
+        double time = controlDict.getOrDefault<double>("startTime", 0.0);
+
+        // ---- time loop (dbnsFoam.C:88-151)
+        residualsIO residuals, initResiduals;
+        bool haveInit = false;
+        int corr = 0, step = 0;  // steady: corr runs over the whole run (pseudotimeControl::loop, Q7)
+        while (time < endTime - 1e-12 * std::fabs(endTime) && step < maxSteps) {
+            time += steadyState ? 1.0 : deltaT;
+            step++;
+            std::cout << "Time = " << time << "\n\n";
+            if (!steadyState) { check(ctx, icsb200_new_time_step(ctx), "new_time_step"); corr = 0; haveInit = false; }
+            bool converged = false;
+            while (true) {
+                corr++;
+                if (!steadyState && corr == nCorrOuter + 1) {
+                    std::cout << "pseudoTime: not converged within " << nCorrOuter << " iterations\n";
+                    break;
+                }
+                // criteriaSatisfied (pseudotimeControl.C:72-101): no check on the first iteration
+                if (corr > 1) {
+                    const bool storeIni = (corr == 2);
+                    if (storeIni) { initResiduals = residuals; haveInit = true; }
+                    const bool absCheck = residuals.maxInit() < pseudoTol;
+                    bool relCheck = false;
+                    if (!storeIni && haveInit) {
+                        double m = -1e300;
+                        for (int i = 0; i < 2; i++) m = std::max(m, residuals.sInitRes[i] / (initResiduals.sInitRes[i] + 1e-150));
+                        for (int d = 0; d < 3; d++) m = std::max(m, residuals.vInitRes[d] / (initResiduals.vInitRes[d] + 1e-150));
+                        relCheck = m < pseudoTolRel;
+                    }
+                    if (corr >= nCorrOuterMin && (absCheck || relCheck)) { converged = true; }
+                }
+                if (converged) { std::cout << "pseudoTime: converged in " << corr - 1 << " iterations\n"; break; }
+                std::cout << "pseudoTime: iteration " << corr << "\n";
+                icsb200_residuals r;
+                check(ctx, icsb200_iterate_dev(ctx, &ctl, &r), "outerLoop");   // outerLoop.H + updateFields.H on the device
+                residuals = residualsIO(r);
+                std::cout << "GMRES : Solving for (  rhoIncr rhoEIncr rhoUIncr ) \n";
+                residuals.print(std::cout);
+                if (steadyState) break;
+            }
+            if (steadyState && converged) break;
+        }
+        std::vector<double> rho(N);
+        check(ctx, icsb200_state_get(ctx, rho.data(), nullptr, nullptr, nullptr, nullptr, nullptr), "state_get");
+        double rmin = 1e300, rmax = -1e300;
+        for (double v : rho) { rmin = std::min(rmin, v); rmax = std::max(rmax, v); }
+        std::cout << "rho min/max: " << rmin << " " << rmax << "\nkernel launches: " << icsb200_launch_count(ctx) << "\nEnd\n";
+        icsb200_destroy(ctx);
+        ml.free_(mh);
+        return 0;
+    } catch (const FatalError& e) {
+        std::cerr << "--> FOAM FATAL ERROR:\n" << e.what() << "\n";
+        return 1;
+    }
+}

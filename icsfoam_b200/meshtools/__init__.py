@@ -25,6 +25,7 @@ def _lib():
         _LIB.icsmesh_structured.restype = C.c_void_p
         _LIB.icsmesh_read_polymesh.restype = C.c_void_p
         _LIB.icsmesh_structured_subbox.restype = C.c_void_p
+        _LIB.icsmesh_renumber.restype = C.c_void_p
         _LIB.icsmesh_extract_part.restype = C.c_void_p
         _LIB.icsmesh_error.restype = C.c_char_p
     return _LIB
@@ -95,6 +96,12 @@ class Mesh:
             md = np.linalg.norm(d, axis=1)
             self.deltaCoeffs[fa] = 1.0 / md
             self.nonOrthDeltaCoeffs[fa] = 1.0 / np.maximum(np.einsum("ij,ij->i", nfa, d), 0.05 * md)
+
+    def renumber(self, perm):
+        """renumberMesh stand-in: new cell id = perm[old id]; faces re-sorted into upper-triangular order."""
+        perm = np.ascontiguousarray(perm, np.int32)
+        assert sorted(perm.tolist()) == list(range(self.n_cells))
+        return Mesh(_lib().icsmesh_renumber(self._h, perm.ctypes.data_as(C.c_void_p)))
 
     def extract_part(self, part, rank):
         """decomposePar stand-in: sub-mesh of the cells with part[c] == rank (processor patches appended)."""

@@ -475,6 +475,36 @@ Mesh* extractPart(const Mesh& g, const int* part, int rank)
     return mp;
 }
 
+// ---------------------------------------------------------------- renumbering (renumberMesh stand-in)
+// new cell id = perm[old id].  Faces whose new owner would exceed the new neighbour are flipped, internal faces are
+// re-sorted into upper-triangular order, boundary patches keep their order.
+Mesh* renumber(const Mesh& g, const int* perm)
+{
+    Mesh* mp = new Mesh;
+    Mesh& m = *mp;
+    m.nCells = g.nCells; m.nInternalFaces = g.nInternalFaces; m.nFaces = g.nFaces;
+    struct IF { int o, n, f; bool flip; };
+    std::vector<IF> ifs(g.nInternalFaces);
+    for (int f = 0; f < g.nInternalFaces; f++) {
+        int o = perm[g.owner[f]], n = perm[g.neighbour[f]];
+        bool flip = o > n;
+        if (flip) std::swap(o, n);
+        ifs[f] = {o, n, f, flip};
+    }
+    std::sort(ifs.begin(), ifs.end(), [](const IF& a, const IF& b) { return a.o != b.o ? a.o < b.o : (a.n != b.n ? a.n < b.n : a.f < b.f); });
+    m.owner.resize(g.nFaces); m.neighbour.resize(g.nInternalFaces); m.Sf.resize(g.nFaces); m.Cf.resize(g.nFaces);
+    for (int k = 0; k < g.nInternalFaces; k++) {
+        m.owner[k] = ifs[k].o; m.neighbour[k] = ifs[k].n;
+        m.Sf[k] = ifs[k].flip ? -1.0 * g.Sf[ifs[k].f] : g.Sf[ifs[k].f];
+        m.Cf[k] = g.Cf[ifs[k].f];
+    }
+    for (int f = g.nInternalFaces; f < g.nFaces; f++) { m.owner[f] = perm[g.owner[f]]; m.Sf[f] = g.Sf[f]; m.Cf[f] = g.Cf[f]; }
+    m.patches = g.patches;
+    for (int d = 0; d < 3; d++) m.solutionD[d] = g.solutionD[d];
+    finishGeometry(m);
+    return mp;
+}
+
 }  // namespace
 
 // ================================================================ C API
@@ -501,6 +531,8 @@ void* icsmesh_structured_subbox(const int n[3], const int off[3], const int gl[3
 void* icsmesh_read_polymesh(const char* dir) { return readPolyMesh(dir); }
 
 void* icsmesh_extract_part(void* h, const int* part, int rank) { return extractPart(*(Mesh*)h, part, rank); }
+
+void* icsmesh_renumber(void* h, const int* perm) { return renumber(*(Mesh*)h, perm); }
 
 void icsmesh_free(void* h) { delete (Mesh*)h; }
 

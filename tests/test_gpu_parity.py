@@ -47,6 +47,8 @@ LIVE = {
     "box-ragged": lambda: cases.periodic_box(5, "HLLC", "vanLeer", seed=25, nz=3),
     "bump": lambda: cases.bump(15, 10),
     "onera": lambda: cases.onera_box(9),
+    "scrambled-hllc": lambda: cases.scrambled_box(6, "HLLC", "vanLeer", seed=41),
+    "scrambled-roe": lambda: cases.scrambled_box(5, "ROE", "Minmod", seed=42),
     "shocktube-ausm": lambda: cases.shock_tube(64, "AUSMPlusUp"),
     "shocktube-roe": lambda: cases.shock_tube(50, "ROE"),
 }
@@ -220,3 +222,37 @@ def test_lusgs_tile_mode_is_bit_identical(gpu_context, monkeypatch):
         rg, ro = g.iterate(case.controls), o.iterate(case.controls)
         assert rg.n_iterations == ro.n_iterations
     assert rel_err(g.state_get()["rho"], o.state_get()["rho"]) < 1e-10
+
+
+LOCAL_STEP = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cases_local", "forwardStep", "constant", "polyMesh")
+
+
+@pytest.mark.skipif(not os.path.isdir(LOCAL_STEP), reason="forwardStep tutorial mesh not staged (cases_local/ is not part of the repository)")
+def test_forward_step_c2_polyhedral_mesh(gpu_context):
+    """C2 on the reference's own polyhedral mesh: cells with more than 6 faces, rows with > 3 lower neighbours."""
+    case = cases.forward_step(LOCAL_STEP)
+    o, g = case.apply(Oracle()), case.apply(gpu_context())
+    o.new_time_step(); g.new_time_step()
+    for a, b in zip(g.calc_flux(), o.calc_flux()):
+        assert np.array_equal(a, b)
+    for a, b in zip(g.residual(), o.residual()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(g.pseudo_dt()[0], o.pseudo_dt()[0])
+    g.assemble(); o.assemble()
+    for blk in range(9):
+        for a, b in zip(g.matrix_get_ldu(blk), o.matrix_get_ldu(blk)):
+            assert np.array_equal(a, b), blk
+    rng = np.random.default_rng(5)
+    N = case.mesh.n_cells
+    x = (rng.standard_normal(N), rng.standard_normal((N, 3)), rng.standard_normal(N))
+    x[1][:, 2] = 0
+    for a, b in zip(g.matrix_mul(*x), o.matrix_mul(*x)):
+        assert np.array_equal(a, b)
+    for a, b in zip(g.precondition("LUSGS", *x), o.precondition("LUSGS", *x)):
+        assert np.array_equal(a, b)
+    for it in range(3):
+        ro, rg = o.iterate(case.controls), g.iterate(case.controls)
+        assert ro.n_iterations == rg.n_iterations
+    so, sg = o.state_get(), g.state_get()
+    for k in STATE_KEYS:
+        assert rel_err(sg[k], so[k]) <= TOL_STATE, k
