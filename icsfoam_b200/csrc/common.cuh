@@ -147,6 +147,8 @@ struct icsb200_ctx {
     int lusgsGrid = 0;
     double* d_lusgsYZ = nullptr;  // [2][5*NPH] forward / reverse sweep values (sentinel protocol)
     int* d_lusgsHint = nullptr;   // [2*nSlices] publication hints
+    int* d_sliceRange = nullptr;  // [3*nSlices] per slice: forward hi, reverse lo, reverse hi entry index (TMA staging ranges)
+    bool lusgsTmaReady = false;
     long long* d_lusgsTrace = nullptr;
     int lusgsEpoch = 0;
     // staging

@@ -134,7 +134,7 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
                     c->d_geo, c->d_dCoupled, c->d_V, c->d_C, c->d_tileStart, c->d_tileFPtr, c->d_tileFLev, c->d_tileRPtr, c->d_tileRLev, c->d_tileRRows, c->d_sliceTile, c->d_bfOwnerPos, c->d_bfPatch, c->d_bfKind,
                     c->d_bfGeo, c->d_bc, c->d_phiB, c->d_vic, c->d_sendBuf, c->d_recvBuf, c->d_fields, c->d_grad, c->d_rdt, c->d_co,
                     c->d_ddtCoeff, c->d_Wold, c->d_Wold2, c->d_Wprev, c->d_src, c->d_dW, c->d_faceFlux, c->d_bad, c->d_offd, c->d_diag,
-                    c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage, c->d_lusgsYZ, c->d_lusgsHint};
+                    c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage, c->d_lusgsYZ, c->d_lusgsHint, c->d_sliceRange};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
     if (c->h_scal) cudaFreeHost(c->h_scal);
@@ -453,6 +453,22 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                 c->h_meta[sb] = ET_PHYS | (f << 2);
             }
         }
+    }
+    // per-slice entry ranges the LU-SGS sweeps touch: forward [0, max nLow), reverse [min nLow over rows with uppers, max nInt)
+    {
+        std::vector<int> range((size_t)3 * nSlices, 0);
+        for (int s = 0; s < nSlices; s++) {
+            int fHi = 0, rLo = 1 << 20, rHi = 0;
+            for (int l = 0; l < 32; l++) {
+                const int p = s * 32 + l;
+                fHi = std::max(fHi, c->h_rowNLow[p]);
+                if (c->h_rowNInt[p] > c->h_rowNLow[p]) { rLo = std::min(rLo, c->h_rowNLow[p]); rHi = std::max(rHi, c->h_rowNInt[p]); }
+            }
+            if (rHi == 0) rLo = 0;
+            range[s] = fHi; range[(size_t)nSlices + s] = rLo; range[2 * (size_t)nSlices + s] = rHi;
+        }
+        int rr = devUpload(c, &c->d_sliceRange, range);
+        if (rr) return rr;
     }
     // GPU face ids: owner-side entries in (slice, j, lane) order
     std::vector<int> ref2gf(FT, -1);

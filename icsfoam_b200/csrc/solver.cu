@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "common.cuh"
 
@@ -312,6 +313,231 @@ k_lusgs(LusgsArgs a)
         }
         __syncwarp();
         if (lane == 0) __stcg(a.hintR + s, a.epoch);
+    }
+}
+
+__device__ __forceinline__ void subBlockGlobal(double* xr, const double* __restrict__ blk, const double* dl);
+
+// ---------------- level pipeline with a TMA producer warp ----------------
+// Same schedule and protocol as k_lusgs, but the 5x5 blocks of a slice are no longer prefetched into the consumer's
+// registers: one producer warp per CTA streams them with cp.async.bulk (TMA, 1-D bulk copies completing on mbarriers)
+// into a shared-memory ring many slices ahead of the consumers.  The consumer warps' dependent path is then only
+// hint/value polls (L2) + shared-memory reads + 75 flops + stores: no HBM latency can land on the dependency chain,
+// and the bulk traffic does not share the LSU queue with the polls.
+constexpr int TMA_NC = 8;        // consumer warps per CTA
+constexpr int TMA_SE = 3;        // entries (5x5 block columns) staged per slice and sweep
+constexpr int TMA_STAGES = 10;   // ring depth
+constexpr int TMA_STAGE_DOUBLES = TMA_SE * 25 * 32;
+
+struct TmaArgs {
+    int nSlices;
+    const int *sliceOff, *rowNLow, *rowNInt, *col;
+    const int *sliceFwdHi, *sliceRevLo, *sliceRevHi;  // per slice: staged entry range of each sweep
+    const double *offd, *rD;
+    double *x, *y, *z;
+    size_t NPH;
+    int *hintF, *hintR;
+    int epoch;
+    int* err;
+};
+
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarArrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbarTryWait(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smemAddr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbarWait(unsigned long long* bar, unsigned parity, int* err)
+{
+    unsigned int spins = 0;
+    while (!mbarTryWait(bar, parity)) {
+        if (++spins > (1u << 26)) { *err = 2; return false; }
+    }
+    return true;
+}
+__device__ __forceinline__ void tmaLoad1D(void* dstSmem, const void* srcGlobal, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)), "l"(srcGlobal),
+                 "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+
+// one neighbour contribution with the block in shared memory: element (k, lane) at blk[k*32 + lane]
+__device__ __forceinline__ void lusgsSubSmem(double* xr, const double* blk, const double* dl)
+{
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        xr[r] -= blk[(r * 5 + 0) * 32] * dl[0];
+        xr[r] -= blk[(r * 5 + 4) * 32] * dl[4];
+        xr[r] -= blk[(r * 5 + 1) * 32] * dl[1] + blk[(r * 5 + 2) * 32] * dl[2] + blk[(r * 5 + 3) * 32] * dl[3];
+    }
+}
+
+__global__ void __launch_bounds__((TMA_NC + 1) * 32, 1)
+k_lusgs_tma(TmaArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    double* ring = (double*)smemRaw;                                                   // [TMA_STAGES][TMA_STAGE_DOUBLES]
+    unsigned long long* full = (unsigned long long*)(ring + (size_t)TMA_STAGES * TMA_STAGE_DOUBLES);  // [TMA_STAGES]
+    unsigned long long* empty = full + TMA_STAGES;
+    volatile int* consumed = (volatile int*)(empty + TMA_STAGES);  // [TMA_STAGES] rounds consumed per stage (guards against parity aliasing)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x, b = blockIdx.x;
+    // my items: forward slices b, b+G, ... then reverse slices nSlices-1-b, nSlices-1-b-G, ...
+    const int nMine = (a.nSlices > b) ? (a.nSlices - b + G - 1) / G : 0;
+    const int nItems = 2 * nMine;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TMA_STAGES; s++) { mbarInit(full + s, 1); mbarInit(empty + s, 1); consumed[s] = 0; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto itemSlice = [&](int i, bool& fwd) { fwd = i < nMine; return fwd ? (b + i * G) : (a.nSlices - 1 - (b + (i - nMine) * G)); };
+
+    if (warp == TMA_NC) {
+        // ---------------- producer warp (one elected lane issues the bulk copies) ----------------
+        if (lane == 0) {
+            for (int i = 0; i < nItems; i++) {
+                const int st = i % TMA_STAGES;
+                if (i >= TMA_STAGES && !mbarWait(empty + st, ((i / TMA_STAGES) + 1) & 1, a.err)) break;
+                bool fwd;
+                const int s = itemSlice(i, fwd);
+                const int lo = fwd ? 0 : a.sliceRevLo[s];
+                const int hi = min(fwd ? a.sliceFwdHi[s] : a.sliceRevHi[s], lo + TMA_SE);
+                const unsigned bytes = (hi > lo) ? (unsigned)(hi - lo) * 25 * 32 * 8 : 0;
+                if (bytes) {
+                    mbarExpectTx(full + st, bytes);
+                    tmaLoad1D(ring + (size_t)st * TMA_STAGE_DOUBLES, a.offd + ((size_t)a.sliceOff[s] + lo) * 25 * 32, bytes, full + st);
+                } else {
+                    mbarArrive(full + st);
+                }
+            }
+        }
+        return;
+    }
+    // ---------------- consumer warps ----------------
+    for (int i = warp; i < nItems; i += TMA_NC) {
+        const int st = i % TMA_STAGES;
+        bool fwd;
+        const int s = itemSlice(i, fwd);
+        const int p = s * 32 + lane;
+        const size_t base = (size_t)a.sliceOff[s];
+        const int nLow = a.rowNLow[p], nInt = a.rowNInt[p];
+        const int stageLo = fwd ? 0 : a.sliceRevLo[s];
+        const int jBeg = fwd ? 0 : nLow, jEnd = fwd ? nLow : nInt;
+        const int n = jEnd - jBeg;
+        const double* buf = fwd ? a.y : a.z;
+        const int* hint = fwd ? a.hintF : a.hintR;
+        double xr[5];
+        // columns / scales of the first LCH neighbours (tiny, L2)
+        int q[LCH];
+        double sc[LCH];
+#pragma unroll
+        for (int t = 0; t < LCH; t++) {
+            q[t] = -1;
+            if (t < n) {
+                const int j = fwd ? (jBeg + t) : (jEnd - 1 - t);
+                q[t] = a.col[(base + j) * 32 + lane];
+                sc[t] = fwd ? a.rD[q[t]] : 1.0;
+            }
+        }
+        const double rd = fwd ? 1.0 : a.rD[p];
+        if (fwd) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) xr[k] = a.x[k * a.NPH + p];
+        } else {
+            pollVec(a.y, a.hintF, a.epoch, a.NPH, p, xr, a.err, 64u, 100u);  // own forward value (possibly from another warp)
+        }
+        // the staged blocks of this item (issued long ago by the producer).  First make sure the previous round of this
+        // stage has been consumed: an mbarrier parity wait is only meaningful for the current or the preceding phase
+        {
+            const int round = i / TMA_STAGES;
+            unsigned int spins = 0;
+            while (consumed[st] != round) { if (++spins > (1u << 28)) { *a.err = 3; break; } }
+        }
+        mbarWait(full + st, (i / TMA_STAGES) & 1, a.err);
+        const double* stage = ring + (size_t)st * TMA_STAGE_DOUBLES;
+        for (int c0 = 0; c0 < n; c0 += LCH) {
+            if (c0 > 0) {
+#pragma unroll
+                for (int t = 0; t < LCH; t++) {
+                    q[t] = -1;
+                    if (c0 + t < n) {
+                        const int j = fwd ? (jBeg + c0 + t) : (jEnd - 1 - c0 - t);
+                        q[t] = a.col[(base + j) * 32 + lane];
+                        sc[t] = fwd ? a.rD[q[t]] : 1.0;
+                    }
+                }
+            }
+            unsigned int pend = 0;
+#pragma unroll
+            for (int t = 0; t < LCH; t++) if (q[t] >= 0) pend |= 1u << t;
+            const unsigned int want = pend;
+            double dl[LCH][5];
+            unsigned int spins = 0;
+            while (pend) {
+                int hv[LCH];
+#pragma unroll
+                for (int t = 0; t < LCH; t++) hv[t] = (pend >> t & 1u) ? ldHint(hint + (q[t] >> 5)) : 0;
+                unsigned int ready = 0;
+#pragma unroll
+                for (int t = 0; t < LCH; t++)
+                    if ((pend >> t & 1u) && hv[t] == a.epoch) {
+                        ready |= 1u << t;
+#pragma unroll
+                        for (int k = 0; k < 5; k++) dl[t][k] = ldPoll(buf + k * a.NPH + q[t]);
+                    }
+#pragma unroll
+                for (int t = 0; t < LCH; t++)
+                    if (ready >> t & 1u) {
+                        bool ok = true;
+#pragma unroll
+                        for (int k = 0; k < 5; k++) ok &= !isSentinel(dl[t][k]);
+                        if (ok) pend &= ~(1u << t);
+                    }
+                if (pend) {
+                    if (++spins > (1u << 24)) { *a.err = 1; break; }
+                    if (spins > 64) __nanosleep(100);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < LCH; t++)
+                if (want >> t & 1u) {
+                    const int j = fwd ? (jBeg + c0 + t) : (jEnd - 1 - c0 - t);
+                    if (fwd) {
+#pragma unroll
+                        for (int k = 0; k < 5; k++) dl[t][k] = sc[t] * dl[t][k];
+                    }
+                    const int js = j - stageLo;
+                    if (js >= 0 && js < TMA_SE) lusgsSubSmem(xr, stage + (size_t)js * 25 * 32 + lane, dl[t]);
+                    else subBlockGlobal(xr, a.offd + ((base + j) * 25) * 32 + lane, dl[t]);
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const double v = fwd ? xr[k] : rd * xr[k];
+            __stcg((fwd ? a.y : a.z) + k * a.NPH + p, v);
+            if (!fwd) a.x[k * a.NPH + p] = v;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __stcg((fwd ? a.hintF : a.hintR) + s, a.epoch);
+            consumed[st] = i / TMA_STAGES + 1;
+            __threadfence_block();
+            mbarArrive(empty + st);  // stage may be refilled
+        }
     }
 }
 
@@ -962,6 +1188,31 @@ int ics_lusgs(icsb200_ctx* c, double* x)
         void* targs[] = {&t};
         CUDA_TRY(c, cudaLaunchCooperativeKernel((void*)k_lusgs_tile, dim3(grid), dim3(TILE_TPB), targs, smem, c->stream));
         return 0;
+    }
+    {
+        static const char* impl = getenv("ICSB200_LUSGS_IMPL");
+        if (!(impl && std::string(impl) == "reg")) {
+            TmaArgs t{};
+            t.nSlices = c->nSlices;
+            t.sliceOff = c->d_sliceOff; t.rowNLow = c->d_rowNLow; t.rowNInt = c->d_rowNInt; t.col = c->d_col;
+            t.sliceFwdHi = c->d_sliceRange; t.sliceRevLo = c->d_sliceRange + c->nSlices; t.sliceRevHi = c->d_sliceRange + 2 * (size_t)c->nSlices;
+            t.offd = c->d_offd; t.rD = c->d_rD; t.x = x; t.NPH = c->NPH;
+            t.y = c->d_lusgsYZ; t.z = c->d_lusgsYZ + V5;
+            t.hintF = c->d_lusgsHint; t.hintR = c->d_lusgsHint + c->nSlices; t.epoch = ++c->lusgsEpoch;
+            t.err = (int*)c->d_counter + 48;
+            const size_t smem = (size_t)TMA_STAGES * TMA_STAGE_DOUBLES * sizeof(double) + 2 * TMA_STAGES * sizeof(unsigned long long) + TMA_STAGES * sizeof(int) + 128;
+            if (!c->lusgsTmaReady) {
+                CUDA_TRY(c, cudaFuncSetAttribute(k_lusgs_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                c->lusgsTmaReady = true;
+            }
+            int grid = std::min(c->numSMs, std::max(1, c->nSlices));
+            LaunchScope ls(c, TM_LUSGS);
+            k_fill_sentinel<<<gridFor(V5, 256), 256, 0, c->stream>>>(V5, (unsigned long long*)t.y, (unsigned long long*)t.z);
+            c->launches++;
+            void* targs[] = {&t};
+            CUDA_TRY(c, cudaLaunchCooperativeKernel((void*)k_lusgs_tma, dim3(grid), dim3((TMA_NC + 1) * 32), targs, smem, c->stream));
+            return 0;
+        }
     }
     LusgsArgs a{};
     a.nSlices = c->nSlices;
