@@ -142,6 +142,8 @@ PRODUCT_SIGNATURES = {
     "schedule_info": (C.c_int, [C.c_void_p, _ip]),
     "timer_begin": (C.c_int, [C.c_void_p]),
     "timer_end": (C.c_int, [C.c_void_p, _dp]),
+    "hb_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _ip, _ip, _dp, _dp]),
+    "hb_residuals_get": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp]),
 }
 
 BLOCK_NC = [1, 1, 1, 1, 3, 3, 3, 3, 9]

@@ -123,11 +123,12 @@ def onera_box(n=48, co=100.0, flux="HLLC", parts=None, rank=0):
     return Case("onera-box", mesh, R, Cp, sch, ctl, bcs, p, U, T, n_iter_default=20)
 
 
-def periodic_box(n=8, flux="HLLC", limiter="vanLeer", seed=0, nz=None):
+def periodic_box(n=8, flux="HLLC", limiter="vanLeer", seed=0, nz=None, cyclic=True):
     """Small randomised box with a translational cyclic pair in x — a parity-test workhorse, not a tutorial."""
     mesh = mt.structured(1, n, n, nz or n, 0, (0, 0, 0), (1.0, 1.2, 0.9),
                          patch_kinds=(capi.PATCH, capi.PATCH, capi.WALL, capi.PATCH, capi.SYMMETRYPLANE, capi.PATCH))
-    mesh.set_cyclic("xmin", "xmax")
+    if cyclic:
+        mesh.set_cyclic("xmin", "xmax")
     rng = np.random.default_rng(seed)
     N = mesh.n_cells
     p = 1e5 * (1 + 0.2 * rng.random(N))
@@ -184,3 +185,70 @@ def forward_step(polymesh_dir):
         "obstacle": {"p": zg, "U": slip, "T": zg},
     }
     return Case("forwardStep", mesh, R, Cp, sch, ctl, bcs, p, U, T, n_iter_default=50)
+
+
+class HBCase:
+    """Harmonic Balance configuration (C5 'vki-HB' stand-in; dbnsFullyImplicitHBFoam): one base `Case` per time instance
+    (same mesh, instance-specific boundary values and initial fields) plus the HBZone set-up.
+
+    `apply(api)` configures the product through the icsb200 C-ABI on the instance-replicated mesh
+    (`hb.ReplicatedMesh` + `icsb200_hb_set`); `instances` are what a per-instance implementation (the oracle) consumes."""
+
+    def __init__(self, name, instances, snapshots, D, zone_of_cell=None, cyl_coords=None, rotation_axis=None, rotation_centre=None):
+        from . import hb
+        self.name, self.instances, self.snapshots = name, instances, np.asarray(snapshots, float)
+        self.n_instants = len(instances)
+        self.D = np.ascontiguousarray(np.asarray(D, float).reshape(-1, self.n_instants, self.n_instants))
+        self.zone_of_cell = None if zone_of_cell is None else np.ascontiguousarray(zone_of_cell, np.int32)
+        self.cyl_coords, self.rotation_axis, self.rotation_centre = cyl_coords, rotation_axis, rotation_centre
+        self.base = instances[0]
+        self.mesh = hb.replicate(self.base.mesh, self.n_instants)
+        self.schemes, self.controls = self.base.schemes, self.base.controls
+        self.p = np.concatenate([c.p for c in instances])
+        self.U = np.concatenate([c.U for c in instances])
+        self.T = np.concatenate([c.T for c in instances])
+
+    def apply(self, api):
+        b = self.base
+        api.mesh_set(self.mesh)
+        api.thermo_set(b.R, b.Cp, b.mu, b.Pr)
+        api.schemes_set(self.schemes)
+        fid = {"p": capi.FIELD_P, "U": capi.FIELD_U, "T": capi.FIELD_T}
+        for K, inst in enumerate(self.instances):
+            for patch, fields in inst.bcs.items():
+                for field, (kind, params) in fields.items():
+                    api.bc_set(f"{patch}@{K}", fid[field], kind, params)
+        api.hb_set(self.n_instants, self.D, self.zone_of_cell, self.cyl_coords, self.rotation_axis, self.rotation_centre)
+        api.state_set(self.p, self.U, self.T)
+        return api
+
+
+def hb_box(n=6, n_instants=3, omega=2 * np.pi * 40.0, flux="ROE", limiter="vanLeer", cyl=False, zoned=False, seed=0, co=5.0,
+           cyclic=True):
+    """Small 3-D box with a cyclic pair, a wall, a symmetry plane and an inlet whose total state oscillates at `omega`:
+    n_instants = 2*harmonics+1 time instances coupled by the HB operator D (one frequency, uniform snapshots over one
+    period, `selectedPeriod` = 2 pi / omega).  `zoned`: only the cells with x > 0.4 belong to the HB zone (cellZone
+    instead of `allMesh`); `cyl`: cylindrical momentum source about the z axis through (0.5, -2, 0)."""
+    from . import hb
+    harmonics = (n_instants - 1) // 2
+    omegas = hb.omega_list([omega], [harmonics])
+    snaps, Ds = hb.set_instants([omegas], n_instants, selected_period=2 * np.pi / omega)
+    insts = []
+    for K, t in enumerate(snaps):
+        c = periodic_box(n, flux, limiter, seed + 17 * K, cyclic=cyclic)
+        s = np.sin(omega * t)
+        c.bcs["ymax"] = {"p": ("fixedValue", (1.05e5 * (1 + 0.03 * s),)), "U": ("inletOutlet", (50.0 + 15.0 * s, 10.0, 0.0)),
+                         "T": ("inletOutlet", (310.0 + 4.0 * s,))}
+        c.schemes = capi.default_schemes(flux_scheme=flux, limiter_rho=limiter, limiter_U=limiter, limiter_T=limiter,
+                                         ddt_scheme="steadyState", pseudo_co_num=co, pseudo_co_num_max=50.0)
+        insts.append(c)
+    base_mesh = insts[0].mesh
+    for c in insts[1:]:
+        c.mesh = base_mesh
+    zone = None
+    if zoned:
+        zone = np.where(base_mesh.C[:, 0] > 0.4, 0, -1).astype(np.int32)
+    kw = {}
+    if cyl:
+        kw = dict(cyl_coords=[1], rotation_axis=[0.0, 0.0, 2.0], rotation_centre=[0.5, -2.0, 0.0])
+    return HBCase("hb-box", insts, snaps, Ds[0], zone, **kw)

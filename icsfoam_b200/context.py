@@ -84,3 +84,20 @@ class Context(capi.Api):
         self._call("schedule_info", out)
         return {"n_levels_fwd": out[0], "n_levels_rev": out[1], "max_width": out[2], "n_positions": out[3],
                 "tile_mode": bool(out[4]), "n_tiles": out[5], "n_tile_levels": out[6]}
+
+    # ---- Harmonic Balance (icsb200_hb_set): the mesh must be an `hb.ReplicatedMesh`
+    def hb_set(self, n_instants, D, zone_of_cell=None, cyl_coords=None, rotation_axis=None, rotation_centre=None):
+        D = np.ascontiguousarray(np.asarray(D, np.float64).reshape(-1, n_instants, n_instants))
+        nz = D.shape[0]
+        zoc = None if zone_of_cell is None else np.ascontiguousarray(zone_of_cell, np.int32)
+        cyl = None if cyl_coords is None else np.ascontiguousarray(cyl_coords, np.int32)
+        ax = None if rotation_axis is None else np.ascontiguousarray(rotation_axis, np.float64)
+        ce = None if rotation_centre is None else np.ascontiguousarray(rotation_centre, np.float64)
+        self._call("hb_set", int(n_instants), int(nz), capi.dptr(D), capi.iptr(zoc), capi.iptr(cyl), capi.dptr(ax), capi.dptr(ce))
+        self.n_instants = int(n_instants)
+
+    def hb_residuals(self):
+        n = self.n_instants
+        out = {"s_init": np.zeros(2 * n), "v_init": np.zeros(3 * n), "s_final": np.zeros(2 * n), "v_final": np.zeros(3 * n)}
+        self._call("hb_residuals_get", *[capi.dptr(out[k]) for k in ("s_init", "v_init", "s_final", "v_final")])
+        return out

@@ -151,6 +151,16 @@ struct icsb200_ctx {
     bool lusgsTmaReady = false;
     long long* d_lusgsTrace = nullptr;
     int lusgsEpoch = 0;
+    // ---- harmonic balance (hb.cu): nO time instances as one mesh of nO disconnected copies ----
+    int hbNO = 1, hbNZones = 0;
+    double* d_hbD = nullptr;      // [nZones][nO][nO]
+    int* d_hbPeer = nullptr;      // [nO][NP] position of the same cell in instance K (-1 for padding rows)
+    int* d_hbInst = nullptr;      // [NP] instance of a position (-1 padding)
+    int* d_hbZone = nullptr;      // [NP] HB zone of the position's cell (-1 none)
+    void* d_hbZonePrm = nullptr;  // [nZones] HBZonePrm
+    double* d_hbInv = nullptr;    // [(5 nO)^2][NP/nO...] dense Jacobi inverses (lazily)
+    double* d_hbWork = nullptr;
+    std::vector<double> hbSInit, hbVInit, hbSFinal, hbVFinal, hbSInitPrev, hbVInitPrev;
     // staging
     double* d_stage = nullptr;
     size_t stageBytes = 0;
@@ -242,3 +252,10 @@ int ics_update(icsb200_ctx* c);
 int ics_copy_prev(icsb200_ctx* c);
 int ics_state_from_primitives(icsb200_ctx* c);
 int ics_allreduce_max_int(icsb200_ctx* c, int* d, int n);
+// hb.cu
+int ics_hb_source(icsb200_ctx* c);        // src += HB source (after the flux residual)
+int ics_hb_diag(icsb200_ctx* c);          // diag += V D[J][J] (after the Jacobian)
+int ics_hb_rdiag(icsb200_ctx* c);         // shared lusgs rDiagCoeff over all instances
+int ics_hb_jacobi(icsb200_ctx* c, double* x);
+struct HBSpmv { int nO; const int* peer; const int* inst; const int* zone; const double* D; const double* V; };
+inline HBSpmv ics_hb_spmv_args(const icsb200_ctx* c) { return HBSpmv{c->hbNO, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbD, c->d_V}; }

@@ -460,7 +460,7 @@ int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
     }
     CUDA_TRY(c, cudaGetLastError());
     c->fluxValid = true;
-    return 0;
+    return ics_hb_source(c);  // Harmonic Balance: sources += -V sum_K D[J][K] W_K
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI

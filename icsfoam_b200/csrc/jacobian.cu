@@ -445,11 +445,13 @@ int ics_jacobian(icsb200_ctx* c, bool useStoredRdt)
     c->matrixSet = true;
     c->rDValid = true;
     c->invDValid = false;
+    if (c->hbNO > 1) return ics_hb_diag(c);  // HB.addBlock(J,J) + the shared lusgs diagonal
     return 0;
 }
 
 int ics_rdiag(icsb200_ctx* c)
 {
+    if (c->hbNO > 1) return ics_hb_rdiag(c);
     int* err = (int*)c->d_counter + 40;
     CUDA_TRY(c, cudaMemsetAsync(err, 0, sizeof(int), c->stream));
     {

@@ -134,7 +134,8 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
                     c->d_geo, c->d_dCoupled, c->d_V, c->d_C, c->d_tileStart, c->d_tileFPtr, c->d_tileFLev, c->d_tileRPtr, c->d_tileRLev, c->d_tileRRows, c->d_sliceTile, c->d_bfOwnerPos, c->d_bfPatch, c->d_bfKind,
                     c->d_bfGeo, c->d_bc, c->d_phiB, c->d_vic, c->d_sendBuf, c->d_recvBuf, c->d_fields, c->d_grad, c->d_rdt, c->d_co,
                     c->d_ddtCoeff, c->d_Wold, c->d_Wold2, c->d_Wprev, c->d_src, c->d_dW, c->d_faceFlux, c->d_bad, c->d_offd, c->d_diag,
-                    c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage, c->d_lusgsYZ, c->d_lusgsHint, c->d_sliceRange};
+                    c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage, c->d_lusgsYZ, c->d_lusgsHint, c->d_sliceRange,
+                    c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
     if (c->h_scal) cudaFreeHost(c->h_scal);
@@ -681,5 +682,6 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     c->lusgsTileGrid = 0;
     c->meshSet = true;
     c->stateSet = c->matrixSet = c->fluxValid = false;
+    c->hbNO = 1;  // a new mesh drops the Harmonic Balance setup (icsb200_hb_set must follow mesh_set)
     return 0;
 }

@@ -83,11 +83,14 @@ int ics_allreduce_max_int(icsb200_ctx* c, int* d, int n)
 namespace {
 
 // ------------------------------------------------------------------------------------------------ SpMV
-template <bool RESID>
+// HB (template flag): the rows of instance J also receive the diagonal-only blocks dSByS(2J,2K), dSByS(2J+1,2K+1), dVByV(J,K)
+// = V D[J][K] of the other instances, accumulated at the place coupledMatrix::matrixMul's (i, j) loops visit them
+// (coupledMatrix.C:66-123; dbnsFullyImplicitHBFoam/outerLoop.H:157-204).
+template <bool RESID, bool HB>
 __global__ void __launch_bounds__(128)
 k_spmv(int NP, const int* __restrict__ pos2cell, const int* __restrict__ sliceOff, const int* __restrict__ rowNAll, const int* __restrict__ col,
        const double* __restrict__ offd, const double* __restrict__ diag, const double* __restrict__ x, size_t NPH, const double* __restrict__ b,
-       double* __restrict__ y)
+       double* __restrict__ y, HBSpmv hb)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= NP || pos2cell[p] < 0) return;
@@ -122,6 +125,39 @@ k_spmv(int NP, const int* __restrict__ pos2cell, const int* __restrict__ sliceOf
             aE[r] += b4 * xc[4];
             aU[r] += b1 * xc[1] + b2 * xc[2] + b3 * xc[3];
         }
+    }
+    if (HB) {
+        const int J = hb.inst[p], z = hb.zone[p];
+        const double vol = hb.V[p];
+        const double* Dz = hb.D + ((size_t)(z < 0 ? 0 : z) * hb.nO + J) * hb.nO;
+        double v[5];
+        // scalar rows: SS blocks of instance 0..nO-1 in order, then the own SV block
+        double a0 = 0.0, a4 = 0.0;
+        for (int K = 0; K < hb.nO; K++) {
+            if (K == J) { a0 += aR[0]; a0 += aE[0]; a4 += aR[4]; a4 += aE[4]; }
+            else if (z >= 0) {
+                const int q = hb.peer[(size_t)K * NP + p];
+                const double sK = vol * Dz[K];
+                a0 += sK * x[q];
+                a4 += sK * x[4 * NPH + q];
+            }
+        }
+        v[0] = a0 + aU[0];
+        v[4] = a4 + aU[4];
+        // vector rows: own VS blocks, then VV blocks of instance 0..nO-1 in order
+        for (int r = 1; r < 4; r++) {
+            double au = 0.0;
+            au += aR[r];
+            au += aE[r];
+            for (int K = 0; K < hb.nO; K++) {
+                if (K == J) au += aU[r];
+                else if (z >= 0) au += (vol * Dz[K]) * x[(size_t)r * NPH + hb.peer[(size_t)K * NP + p]];
+            }
+            v[r] = au;
+        }
+#pragma unroll
+        for (int r = 0; r < 5; r++) y[r * NPH + p] = RESID ? (b[r * NPH + p] - v[r]) : v[r];
+        return;
     }
 #pragma unroll
     for (int r = 0; r < 5; r++) {
@@ -917,6 +953,10 @@ __device__ __forceinline__ void finishReduction(double* v, double* __restrict__ 
     __shared__ double sh[NV][RED_BLOCK / 32];
     __shared__ bool last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // blockIdx.y = time instance (Harmonic Balance): separate partials, counter and outputs per instance
+    partial += (size_t)blockIdx.y * NV * gridDim.x;
+    counter += blockIdx.y;
+    out += (size_t)blockIdx.y * NV;
 #pragma unroll
     for (int k = 0; k < NV; k++) { double s = warpSum(v[k]); if (lane == 0) sh[k][warp] = s; }
     __syncthreads();
@@ -971,34 +1011,42 @@ k_axpy_dot(int NP, size_t NPH, double* __restrict__ w, const double* __restrict_
 }
 
 // 5 component sums of |r| (gSumMag / gSumCmptMag, gmres.C:1081-1098)
+// inst != null (Harmonic Balance): grid.y = nO, the y-slice only sums the rows of its own time instance
 __global__ void __launch_bounds__(RED_BLOCK)
-k_sum_mag5(int NP, size_t NPH, const double* __restrict__ r, double* __restrict__ partial, unsigned int* __restrict__ counter, double* __restrict__ out)
+k_sum_mag5(int NP, size_t NPH, const double* __restrict__ r, const int* __restrict__ inst, double* __restrict__ partial, unsigned int* __restrict__ counter,
+           double* __restrict__ out)
 {
     double acc[5] = {0, 0, 0, 0, 0};
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < NP; p += gridDim.x * blockDim.x)
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < NP; p += gridDim.x * blockDim.x) {
+        if (inst && inst[p] != (int)blockIdx.y) continue;
 #pragma unroll
         for (int k = 0; k < 5; k++) acc[k] += fabs(r[k * NPH + p]);
+    }
     finishReduction<5>(acc, partial, counter, out);
 }
 
 // plain sums of the 5 components of W (gAverage, gmres.C:812-823)
 __global__ void __launch_bounds__(RED_BLOCK)
-k_sum5(int NP, size_t stride, const double* __restrict__ r, double* __restrict__ partial, unsigned int* __restrict__ counter, double* __restrict__ out)
+k_sum5(int NP, size_t stride, const double* __restrict__ r, const int* __restrict__ inst, double* __restrict__ partial, unsigned int* __restrict__ counter,
+       double* __restrict__ out)
 {
     double acc[5] = {0, 0, 0, 0, 0};
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < NP; p += gridDim.x * blockDim.x)
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < NP; p += gridDim.x * blockDim.x) {
+        if (inst && inst[p] != (int)blockIdx.y) continue;
 #pragma unroll
         for (int k = 0; k < 5; k++) acc[k] += r[k * stride + p];
+    }
     finishReduction<5>(acc, partial, counter, out);
 }
 
 // normalisation factors (gmres.C:839-851): sum(|Ax| + |b|) for rho, rhoE; sum(mag(Ax) + mag(b)) for rhoU
 __global__ void __launch_bounds__(RED_BLOCK)
-k_norm_factors(int NP, size_t NPH, const double* __restrict__ ax, const double* __restrict__ b, double* __restrict__ partial,
+k_norm_factors(int NP, size_t NPH, const double* __restrict__ ax, const double* __restrict__ b, const int* __restrict__ inst, double* __restrict__ partial,
                unsigned int* __restrict__ counter, double* __restrict__ out)
 {
     double acc[3] = {0, 0, 0};
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < NP; p += gridDim.x * blockDim.x) {
+        if (inst && inst[p] != (int)blockIdx.y) continue;
         acc[0] += fabs(ax[p]) + fabs(b[p]);
         acc[1] += fabs(ax[4 * NPH + p]) + fabs(b[4 * NPH + p]);
         const double m1 = sqrt(ax[NPH + p] * ax[NPH + p] + ax[2 * NPH + p] * ax[2 * NPH + p] + ax[3 * NPH + p] * ax[3 * NPH + p]);
@@ -1010,13 +1058,14 @@ k_norm_factors(int NP, size_t NPH, const double* __restrict__ ax, const double* 
 
 // ------------------------------------------------------------------------------------------------ vector ops
 __global__ void k_sub_avg(int NP, const int* __restrict__ pos2cell, size_t NPH, const double* __restrict__ W, size_t wstride, const double* __restrict__ sums,
-                          double nTot, double* __restrict__ x)
+                          const int* __restrict__ inst, double nTot, double* __restrict__ x)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= NP) return;
     const bool valid = pos2cell[p] >= 0;
+    const double* sm = sums + ((inst && valid) ? 5 * inst[p] : 0);
 #pragma unroll
-    for (int k = 0; k < 5; k++) x[k * NPH + p] = valid ? (W[k * wstride + p] - sums[k] / nTot) : 0.0;
+    for (int k = 0; k < 5; k++) x[k * NPH + p] = valid ? (W[k * wstride + p] - sm[k] / nTot) : 0.0;
 }
 
 __global__ void k_scale_div(int NP, size_t NPH, const double* __restrict__ w, const double* __restrict__ beta2, double* __restrict__ v)
@@ -1137,8 +1186,14 @@ int ics_spmv(icsb200_ctx* c, const double* x, double* y, const double* b)
     if (r) return r;
     LaunchScope ls(c, TM_SPMV);
     const int grid = gridFor(c->NP, 128);
-    if (b) k_spmv<true><<<grid, 128, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_col, c->d_offd, c->d_diag, x, c->NPH, b, y);
-    else k_spmv<false><<<grid, 128, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_col, c->d_offd, c->d_diag, x, c->NPH, nullptr, y);
+    const HBSpmv hb = ics_hb_spmv_args(c);
+    if (c->hbNO > 1) {
+        if (b) k_spmv<true, true><<<grid, 128, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_col, c->d_offd, c->d_diag, x, c->NPH, b, y, hb);
+        else k_spmv<false, true><<<grid, 128, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_col, c->d_offd, c->d_diag, x, c->NPH, nullptr, y, hb);
+    } else {
+        if (b) k_spmv<true, false><<<grid, 128, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_col, c->d_offd, c->d_diag, x, c->NPH, b, y, hb);
+        else k_spmv<false, false><<<grid, 128, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_col, c->d_offd, c->d_diag, x, c->NPH, nullptr, y, hb);
+    }
     CUDA_TRY(c, cudaGetLastError());
     return 0;
 }
@@ -1288,6 +1343,34 @@ static int redGrid(const icsb200_ctx* c) { return std::min(4 * c->numSMs, std::m
 // setCoAndDeltaT.H:3-37 — switched evolution relaxation of the pseudo Courant number
 int ics_pseudo_ser(icsb200_ctx* c)
 {
+    if (c->hbNO > 1) {
+        // dbnsFullyImplicitHBFoam/outerLoop.H:32-64 + setCoAndDeltaT.H:3-11.  As coded there, coNumRatio stays 0 on the
+        // first iteration that has an initRes but no prevRes yet and the Courant field is still multiplied by it.
+        if (!c->haveInitRes) return 0;
+        const int nO = c->hbNO;
+        double ratio = 0.0;
+        if (!c->firstIter && c->havePrevRes) {
+            auto sq = [](double x) { return x * x; };
+            double ni = 0, np = 0;
+            for (int J = 0; J < nO; J++) {
+                const double* vi = &c->hbVInit[3 * J];
+                const double* vp = &c->hbVInitPrev[3 * J];
+                ni += sq(c->hbSInit[2 * J]) + sq(c->hbSInit[2 * J + 1]) + (vi[0] * vi[0] + vi[1] * vi[1] + vi[2] * vi[2]);
+                np += sq(c->hbSInitPrev[2 * J]) + sq(c->hbSInitPrev[2 * J + 1]) + (vp[0] * vp[0] + vp[1] * vp[1] + vp[2] * vp[2]);
+            }
+            ratio = std::sqrt(np) / std::sqrt(ni);
+            ratio = std::max(std::min(ratio, c->sch.pseudo_co_num_max_incr), c->sch.pseudo_co_num_min_decr);
+        }
+        c->hbSInitPrev = c->hbSInit;
+        c->hbVInitPrev = c->hbVInit;
+        c->havePrevRes = true;
+        if (!c->firstIter) {
+            LaunchScope ls(c, TM_UPDATE);
+            k_co_update<<<gridFor(c->NP, 256), 256, 0, c->stream>>>(c->NP, ratio, c->sch.pseudo_co_num_min, c->sch.pseudo_co_num_max, c->d_co);
+            CUDA_TRY(c, cudaGetLastError());
+        }
+        return 0;
+    }
     if (c->haveInitRes) {
         if (!c->firstIter && c->havePrevRes) {
             const icsb200_residuals &ir = c->initRes, &pr = c->prevRes;
@@ -1314,7 +1397,7 @@ int ics_pseudo_ser(icsb200_ctx* c)
 static int precond(icsb200_ctx* c, int kind, double* x)
 {
     if (kind == ICSB200_PRECOND_LUSGS) return ics_lusgs(c, x);
-    if (kind == ICSB200_PRECOND_JACOBI) return ics_jacobi(c, x);
+    if (kind == ICSB200_PRECOND_JACOBI) return c->hbNO > 1 ? ics_hb_jacobi(c, x) : ics_jacobi(c, x);
     return ics_fail(c, ICSB200_EINVAL, "Unknown preconditioner; valid types are: LUSGS Jacobi");
 }
 
@@ -1339,34 +1422,41 @@ int ics_gmres(icsb200_ctx* c, const icsb200_solver_controls* ctl, icsb200_residu
     const int rg = redGrid(c);
     const int g256 = gridFor(NP, 256);
     int r;
-    // global cell count
-    double nTot = c->N;
+    // Harmonic Balance: nI time instances, every per-variable quantity of the residualsIO exists once per instance
+    const int nI = c->hbNO;
+    const int* inst = nI > 1 ? c->d_hbInst : nullptr;
+    const dim3 rgI(rg, nI);
+    // layout of the host-read reduction area: [0,80) sums of W, [100] cell count, [128,176) norm factors,
+    // [192,272) |b| sums, [288,368) |r| sums
+    enum { R_SUM = 0, R_NTOT = 100, R_NORM = 128, R_B = 192, R_R = 288, R_END = 368 };
+    // global cell count of one instance mesh
+    double nTot = c->N / nI;
     if (c->nRanks > 1) {
-        CUDA_TRY(c, cudaMemcpyAsync(red + 100, &nTot, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        if ((r = allreduceSum(c, red + 100, 1))) return r;
-        CUDA_TRY(c, cudaMemcpyAsync(&nTot, red + 100, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(red + R_NTOT, &nTot, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        if ((r = allreduceSum(c, red + R_NTOT, 1))) return r;
+        CUDA_TRY(c, cudaMemcpyAsync(&nTot, red + R_NTOT, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     }
     // ---- normalisation: A (W - avg(W))   (gmres.C:812-851)
     {
         LaunchScope ls(c, TM_RED);
-        k_sum5<<<rg, RED_BLOCK, 0, c->stream>>>(NP, NPH, c->d_Wprev, c->d_partial, c->d_counter, red);
+        k_sum5<<<rgI, RED_BLOCK, 0, c->stream>>>(NP, NPH, c->d_Wprev, inst, c->d_partial, c->d_counter, red + R_SUM);
     }
-    if ((r = allreduceSum(c, red, 5))) return r;
+    if ((r = allreduceSum(c, red + R_SUM, 5 * nI))) return r;
     {
         LaunchScope ls(c, TM_VEC);
-        k_sub_avg<<<g256, 256, 0, c->stream>>>(NP, c->d_pos2cell, NPH, c->d_Wprev, NPH, red, nTot, c->d_x);
+        k_sub_avg<<<g256, 256, 0, c->stream>>>(NP, c->d_pos2cell, NPH, c->d_Wprev, NPH, red + R_SUM, inst, nTot, c->d_x);
     }
     if ((r = ics_spmv(c, c->d_x, c->d_w, nullptr))) return r;
     {
         LaunchScope ls(c, TM_RED);
-        k_norm_factors<<<rg, RED_BLOCK, 0, c->stream>>>(NP, NPH, c->d_w, c->d_src, c->d_partial, c->d_counter, red + 8);
-        k_sum_mag5<<<rg, RED_BLOCK, 0, c->stream>>>(NP, NPH, c->d_src, c->d_partial, c->d_counter, red + 16);
+        k_norm_factors<<<rgI, RED_BLOCK, 0, c->stream>>>(NP, NPH, c->d_w, c->d_src, inst, c->d_partial, c->d_counter, red + R_NORM);
+        k_sum_mag5<<<rgI, RED_BLOCK, 0, c->stream>>>(NP, NPH, c->d_src, inst, c->d_partial, c->d_counter, red + R_B);
         c->launches++;
     }
-    if ((r = allreduceSum(c, red + 8, 3))) return r;
-    if ((r = allreduceSum(c, red + 16, 5))) return r;
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, red, sizeof(double) * 32, cudaMemcpyDeviceToHost, c->stream));
+    if ((r = allreduceSum(c, red + R_NORM, 3 * nI))) return r;
+    if ((r = allreduceSum(c, red + R_B, 5 * nI))) return r;
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, red, sizeof(double) * R_END, cudaMemcpyDeviceToHost, c->stream));
     // x0 = 0, r0 = b
     {
         LaunchScope ls(c, TM_VEC);
@@ -1375,12 +1465,25 @@ int ics_gmres(icsb200_ctx* c, const icsb200_solver_controls* ctl, icsb200_residu
         c->launches++;
     }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    const double sNorm0 = c->h_scal[8] + ICS_VSMALL, sNorm1 = c->h_scal[9] + ICS_VSMALL, vNorm = c->h_scal[10] + ICS_VSMALL;
-    res->s_init[0] = c->h_scal[16] / sNorm0;
-    res->s_init[1] = c->h_scal[20] / sNorm1;
-    for (int d = 0; d < 3; d++) res->v_init[d] = c->h_scal[17 + d] / vNorm;
-    for (int i = 0; i < 2; i++) res->s_final[i] = res->s_init[i];
-    for (int d = 0; d < 3; d++) res->v_final[d] = res->v_init[d];
+    // residualsIO per instance: scalars (rho_I, rhoE_I) and the vector rhoU_I
+    std::vector<double> sNorm(2 * nI), vNorm(nI), sInit(2 * nI), vInit(3 * nI), sFinal(2 * nI), vFinal(3 * nI);
+    for (int I = 0; I < nI; I++) {
+        sNorm[2 * I] = c->h_scal[R_NORM + 3 * I] + ICS_VSMALL;
+        sNorm[2 * I + 1] = c->h_scal[R_NORM + 3 * I + 1] + ICS_VSMALL;
+        vNorm[I] = c->h_scal[R_NORM + 3 * I + 2] + ICS_VSMALL;
+        sInit[2 * I] = c->h_scal[R_B + 5 * I] / sNorm[2 * I];
+        sInit[2 * I + 1] = c->h_scal[R_B + 5 * I + 4] / sNorm[2 * I + 1];
+        for (int d = 0; d < 3; d++) vInit[3 * I + d] = c->h_scal[R_B + 5 * I + 1 + d] / vNorm[I];
+    }
+    sFinal = sInit;
+    vFinal = vInit;
+    auto publish = [&]() {
+        res->s_init[0] = sInit[0]; res->s_init[1] = sInit[1];
+        res->s_final[0] = sFinal[0]; res->s_final[1] = sFinal[1];
+        for (int d = 0; d < 3; d++) { res->v_init[d] = vInit[d]; res->v_final[d] = vFinal[d]; }
+        if (nI > 1) { c->hbSInit = sInit; c->hbVInit = vInit; c->hbSFinal = sFinal; c->hbVFinal = vFinal; }
+    };
+    publish();
     if (ctl->preconditioner == ICSB200_PRECOND_JACOBI) c->invDValid = c->invDValid && true;
     bool stop = false;
     do {
@@ -1433,25 +1536,30 @@ int ics_gmres(icsb200_ctx* c, const icsb200_solver_controls* ctl, icsb200_residu
         if ((r = ics_spmv(c, c->d_x, c->d_w, c->d_src))) return r;
         {
             LaunchScope ls(c, TM_RED);
-            k_sum_mag5<<<rg, RED_BLOCK, 0, c->stream>>>(NP, NPH, c->d_w, c->d_partial, c->d_counter, red + 24);
+            k_sum_mag5<<<rgI, RED_BLOCK, 0, c->stream>>>(NP, NPH, c->d_w, inst, c->d_partial, c->d_counter, red + R_R);
         }
-        if ((r = allreduceSum(c, red + 24, 5))) return r;
-        CUDA_TRY(c, cudaMemcpyAsync(c->h_scal + 24, red + 24, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->stream));
+        if ((r = allreduceSum(c, red + R_R, 5 * nI))) return r;
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_scal + R_R, red + R_R, sizeof(double) * 5 * nI, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        res->s_final[0] = c->h_scal[24] / sNorm0;
-        res->s_final[1] = c->h_scal[28] / sNorm1;
-        for (int d = 0; d < 3; d++) {
-            res->v_final[d] = c->h_scal[25 + d] / vNorm;
-            if (c->solutionD[d] == -1) res->v_final[d] = 0.0;
+        for (int I = 0; I < nI; I++) {
+            sFinal[2 * I] = c->h_scal[R_R + 5 * I] / sNorm[2 * I];
+            sFinal[2 * I + 1] = c->h_scal[R_R + 5 * I + 4] / sNorm[2 * I + 1];
+            for (int d = 0; d < 3; d++) {
+                vFinal[3 * I + d] = c->h_scal[R_R + 5 * I + 1 + d] / vNorm[I];
+                if (c->solutionD[d] == -1) vFinal[3 * I + d] = 0.0;
+            }
         }
         res->n_iterations++;
-        // solver::stop (coupledMatrixSolver.C:198-221)
+        publish();
+        // solver::stop (coupledMatrixSolver.C:198-221) with residualsIO::max / maxRel over every variable
         if (res->n_iterations < ctl->min_iter) stop = false;
         else {
             double mx = -ICS_VGREAT, mr = -ICS_VGREAT;
-            for (int i = 0; i < 2; i++) { mx = std::max(mx, res->s_final[i]); mr = std::max(mr, res->s_final[i] / (res->s_init[i] + ICS_ROOTVSMALL)); }
-            mx = std::max(mx, std::max(res->v_final[0], std::max(res->v_final[1], res->v_final[2])));
-            for (int d = 0; d < 3; d++) if (c->solutionD[d] == 1) mr = std::max(mr, res->v_final[d] / (res->v_init[d] + ICS_ROOTVSMALL));
+            for (int i = 0; i < 2 * nI; i++) { mx = std::max(mx, sFinal[i]); mr = std::max(mr, sFinal[i] / (sInit[i] + ICS_ROOTVSMALL)); }
+            for (int I = 0; I < nI; I++) {
+                mx = std::max(mx, std::max(vFinal[3 * I], std::max(vFinal[3 * I + 1], vFinal[3 * I + 2])));
+                for (int d = 0; d < 3; d++) if (c->solutionD[d] == 1) mr = std::max(mr, vFinal[3 * I + d] / (vInit[3 * I + d] + ICS_ROOTVSMALL));
+            }
             stop = (res->n_iterations >= ctl->max_iter) || (mx < ctl->tolerance) || (mr < ctl->rel_tol);
         }
     } while (!stop);

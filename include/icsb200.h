@@ -171,6 +171,26 @@ int icsb200_iterate_dev(icsb200_ctx* ctx, const icsb200_solver_controls* c, icsb
 int icsb200_iterate_host(icsb200_ctx* ctx, const icsb200_solver_controls* c, double* p, double* U, double* T,
                          icsb200_residuals* res);
 
+/* ---- Harmonic Balance (dbnsFullyImplicitHBFoam) ------------------------------------ */
+/* HBZone / HBZoneList (src/cfdTools/HB/HBZone.C:270-356 operators, :435-518 addBlock, :521-651 cylindrical source;
+ * HBZoneTemplates.C:38-92 addSource) and the (2 nO, nO) coupled system of
+ * applications/solvers/dbnsFullyImplicitHBFoam/outerLoop.H:28-30,91-206.
+ * The n_instants time instances ("subTimeLevelK" meshes) are passed to icsb200_mesh_set as ONE mesh made of n_instants
+ * disconnected copies, instance-major in cells, faces and patches (cell c of instance K is cell K*N/n_instants + c; host
+ * tooling: meshtools replicate).  All field arrays of the other entry points are then instance-major as well.
+ * D[z] (n_instants x n_instants, row-major) is HBZone::D() of zone z; zone_of_cell[N/n_instants] gives the zone of every
+ * instance cell (-1: none; NULL: every cell is in zone 0 = `allMesh`).  cyl_coords[z] != 0 selects the cylindrical
+ * momentum source with rotation_axis[3z..] / rotation_centre[3z..].  Call after icsb200_mesh_set.
+ * Effect: residual adds S_J = -V sum_K D[J][K] W_K; assemble adds V D[J][J] to the (rho,rho), (rhoU,rhoU), (rhoE,rhoE)
+ * diagonals; matrix_mul / solve_delta include the inter-instance diagonal coupling V D[J][K]; LU-SGS uses the shared
+ * rDiagCoeff over all instances (lusgs.C:50-123); the SER ratio uses the residual norm over all instances
+ * (outerLoop.H:32-64); residuals are per instance (icsb200_hb_residuals_get). n_instants = 1 switches HB off. */
+int icsb200_hb_set(icsb200_ctx* ctx, int n_instants, int n_zones, const double* D, const int* zone_of_cell,
+                   const int* cyl_coords, const double* rotation_axis, const double* rotation_centre);
+/* residualsIO of the last solve for all instances: s_* [2 n_instants] = (rho_0, rhoE_0, rho_1, ...), v_* [3 n_instants]
+ * (residualsIO.H:204-240; dbnsFullyImplicitHBFoam/setUpResiduals.H:1-11) */
+int icsb200_hb_residuals_get(icsb200_ctx* ctx, double* s_init, double* v_init, double* s_final, double* v_final);
+
 /* ---- introspection ------------------------------------------------------------------------- */
 /* number of kernels this library launched since create (bench.py "gpu_launches") */
 long long icsb200_launch_count(icsb200_ctx* ctx);

@@ -392,10 +392,9 @@ static void spectralRadius(Ctx& c, vecd& lambda)
     }
 }
 
-// setCoAndDeltaT.H
-void setCoAndDeltaT(Ctx& c)
+// setCoAndDeltaT.H:3-37 — switched evolution relaxation
+void serUpdate(Ctx& c)
 {
-    const Mesh& m = c.m;
     if (c.haveInitRes) {
         if (!c.firstIter && c.havePrevRes) {
             const icsb200_residuals &ir = c.initRes, &pr = c.prevRes;
@@ -413,6 +412,12 @@ void setCoAndDeltaT(Ctx& c)
         c.prevRes = c.initRes;
         c.havePrevRes = true;
     }
+}
+
+// setCoAndDeltaT.H:39-173 — pseudo time step from the current pseudo Courant number
+void pseudoDeltaT(Ctx& c)
+{
+    const Mesh& m = c.m;
     vecd lambda;
     spectralRadius(c, lambda);
     if (c.sch.local_timestepping) {
@@ -447,6 +452,12 @@ void setCoAndDeltaT(Ctx& c)
         mx = c.comm->max(mx);
         for (int i = 0; i < m.N; i++) c.rPseudoDeltaT[i] = mx / c.pseudoCoNum;
     }
+}
+
+void setCoAndDeltaT(Ctx& c)
+{
+    serUpdate(c);
+    pseudoDeltaT(c);
 }
 
 // outerLoop.H:61-64

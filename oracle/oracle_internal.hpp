@@ -23,6 +23,8 @@ void stateInit(Ctx& c, const double* p, const double* U, const double* T);
 void calcFlux(Ctx& c);
 void residualsUpdate(Ctx& c);
 void setCoAndDeltaT(Ctx& c);
+void serUpdate(Ctx& c);
+void pseudoDeltaT(Ctx& c);
 void computeDdtCoeff(Ctx& c);
 void createJacobian(Ctx& c);
 void updateFields(Ctx& c);
@@ -30,6 +32,9 @@ void boundLocalTimeStep(Ctx& c);
 void newTimeStep(Ctx& c);
 
 // oracle_solver.cpp
+void Amul(const Ctx& c, const Blk& b, int rowDim, int colDim, const vecd& psi, vecd& Apsi);
+int lusgsPrecondition(Ctx& c, const vecd& rD, vecd& sRho, vecd& vRhoU, vecd& sRhoE);
+void luInverse(int n, const double* A, double* inv);
 void matrixMul(Ctx& c, vecd& xRho, vecd& xRhoU, vecd& xRhoE, vecd& yRho, vecd& yRhoU, vecd& yRhoE);
 int precondition(Ctx& c, int kind, vecd& xRho, vecd& xRhoU, vecd& xRhoE);
 int solveDelta(Ctx& c, const icsb200_solver_controls& ctl, icsb200_residuals& res);

@@ -36,6 +36,8 @@ inline void dotSub(const double* coef, int rowDim, int colDim, const double* x, 
     }
 }
 
+}  // namespace
+
 // blockFvMatrix::Amul — psi has boundary slots holding patchNeighbourField for coupled patches
 void Amul(const Ctx& c, const Blk& b, int rowDim, int colDim, const vecd& psi, vecd& Apsi)
 {
@@ -55,6 +57,8 @@ void Amul(const Ctx& c, const Blk& b, int rowDim, int colDim, const vecd& psi, v
                 for (int f = p.start; f < p.start + p.size; f++)
                     dotAdd(&b.intUpper[(size_t)nc * (f - m.F)], rowDim, colDim, &psi[(size_t)colDim * (m.N + f - m.F)], &Apsi[(size_t)rowDim * m.owner[f]]);
 }
+
+namespace {
 
 struct BlkRef { int id, rowVar, colVar; };  // var: 0 rho, 1 rhoE (scalars), 2 rhoU (vector)
 // coupledMatrix::matrixMul loop order: SS(i,j), SV(i,j), VS(i,j), VV
@@ -102,7 +106,7 @@ static int lusgsDiag(const Ctx& c, vecd& rD)
     return 0;
 }
 
-static int lusgsPrecondition(Ctx& c, const vecd& rD, vecd& sRho, vecd& vRhoU, vecd& sRhoE)
+int lusgsPrecondition(Ctx& c, const vecd& rD, vecd& sRho, vecd& vRhoU, vecd& sRhoE)
 {
     const Mesh& m = c.m;
     double* vecs[3] = {sRho.data(), sRhoE.data(), vRhoU.data()};
@@ -152,13 +156,12 @@ static int lusgsPrecondition(Ctx& c, const vecd& rD, vecd& sRho, vecd& vRhoU, ve
 
 // ---------------------------------------------------------------------------------------------- Jacobi
 // LUscalarMatrix::inv = LU decomposition with partial pivoting (Foam::LUDecompose) + column-by-column back substitution
-static void luInverse5(const double A[5][5], double inv[5][5])
+void luInverse(int n, const double* A, double* inv)
 {
-    const int n = 5;
-    double a[5][5];
-    int piv[5];
-    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) a[i][j] = A[i][j];
-    double vv[5];
+    std::vector<vecd> a(n, vecd(n));
+    std::vector<int> piv(n);
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) a[i][j] = A[i * n + j];
+    vecd vv(n);
     for (int i = 0; i < n; i++) {
         double largest = 0.0;
         for (int j = 0; j < n; j++) largest = std::max(largest, std::fabs(a[i][j]));
@@ -181,7 +184,7 @@ static void luInverse5(const double A[5][5], double inv[5][5])
         if (j != n - 1) { double rDiag = 1.0 / a[j][j]; for (int i = j + 1; i < n; i++) a[i][j] *= rDiag; }
     }
     for (int col = 0; col < n; col++) {
-        double x[5] = {0, 0, 0, 0, 0};
+        vecd x(n, 0.0);
         x[col] = 1.0;
         int ii = 0;
         for (int i = 0; i < n; i++) {
@@ -197,7 +200,7 @@ static void luInverse5(const double A[5][5], double inv[5][5])
             for (int j = i + 1; j < n; j++) sum -= a[i][j] * x[j];
             x[i] = sum / a[i][i];
         }
-        for (int i = 0; i < n; i++) inv[i][col] = x[i];
+        for (int i = 0; i < n; i++) inv[i * n + col] = x[i];
     }
 }
 
@@ -217,7 +220,7 @@ static int jacobiPrecondition(Ctx& c, vecd& sRho, vecd& vRhoU, vecd& sRhoE)
             J[2 + d][1] = c.blk[7].diag[3 * (size_t)celli + d];
             for (int e = 0; e < 3; e++) J[2 + d][2 + e] = c.blk[8].diag[9 * (size_t)celli + 3 * d + e];
         }
-        luInverse5(J, inv);
+        luInverse(5, &J[0][0], &inv[0][0]);
         // matrixMulNoDiag of a zero field is zero: sTmp = -(0 - source)
         double var[5] = {-(0.0 - sRho[celli]), -(0.0 - sRhoE[celli]), -(0.0 - vRhoU[3 * (size_t)celli]), -(0.0 - vRhoU[3 * (size_t)celli + 1]),
                          -(0.0 - vRhoU[3 * (size_t)celli + 2])};

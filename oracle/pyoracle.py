@@ -105,3 +105,99 @@ def debug_grad(o, cells):
     cells = np.ascontiguousarray(cells, np.float64)
     lib().orc_debug_grad(o.h, capi.dptr(cells), capi.dptr(g))
     return g
+
+
+class HB:
+    """The reference-structured Harmonic Balance system: nO oracle contexts (one per time-instance mesh) and the global
+    (2 nO, nO) coupled solve of dbnsFullyImplicitHBFoam (oracle/oracle_hb.cpp).  Arrays are instance-major."""
+
+    def __init__(self, hbcase):
+        L = lib()
+        L.orc_hb_create.restype = C.c_void_p
+        self.case = hbcase
+        self.n = hbcase.n_instants
+        self.inst = [c.apply(Oracle()) for c in hbcase.instances]
+        ctxs = (C.c_void_p * self.n)(*[o.h for o in self.inst])
+        self._h = C.c_void_p(L.orc_hb_create(ctxs, self.n))
+        N = hbcase.base.mesh.n_cells
+        self.N = N
+        for z in range(hbcase.D.shape[0]):
+            D = np.ascontiguousarray(hbcase.D[z])
+            if hbcase.zone_of_cell is None:
+                n_cells, cells = -2, None
+            else:
+                cells = np.ascontiguousarray(np.nonzero(hbcase.zone_of_cell == z)[0], np.int32)
+                n_cells = int(cells.size)
+            cyl = int(hbcase.cyl_coords[z]) if hbcase.cyl_coords is not None else 0
+            ax = np.ascontiguousarray(hbcase.rotation_axis[3 * z:3 * z + 3], np.float64) if cyl else None
+            ce = np.ascontiguousarray(hbcase.rotation_centre[3 * z:3 * z + 3], np.float64) if cyl else None
+            rc = L.orc_hb_zone_add(self._h, capi.dptr(D), n_cells, capi.iptr(cells), cyl, capi.dptr(ax), capi.dptr(ce))
+            assert rc == 0
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise capi.ApiError(f"orc_hb_{what} failed ({rc})")
+
+    def sources(self):
+        n, N = self.n, self.N
+        a, b, c = np.zeros(n * N), np.zeros((n * N, 3)), np.zeros(n * N)
+        self._chk(lib().orc_hb_sources(self._h, capi.dptr(a), capi.dptr(b), capi.dptr(c)), "sources")
+        return a, b, c
+
+    def assemble(self):
+        self._chk(lib().orc_hb_assemble(self._h), "assemble")
+
+    def residual(self):
+        """sources R*V + HB source of every instance after assemble()"""
+        n, N = self.n, self.N
+        a, b, c = np.zeros(n * N), np.zeros((n * N, 3)), np.zeros(n * N)
+        self._chk(lib().orc_hb_system_sources(self._h, capi.dptr(a), capi.dptr(b), capi.dptr(c)), "system_sources")
+        return a, b, c
+
+    def matrix_get_ldu(self, block):
+        parts = [o.matrix_get_ldu(block) for o in self.inst]
+        return tuple(np.concatenate([p[k] for p in parts]) for k in range(3))
+
+    def matrix_mul(self, xRho, xRhoU, xRhoE):
+        n, N = self.n, self.N
+        a, b, c = np.zeros(n * N), np.zeros((n * N, 3)), np.zeros(n * N)
+        self._chk(lib().orc_hb_matrix_mul(self._h, capi.dptr(np.ascontiguousarray(xRho)), capi.dptr(np.ascontiguousarray(xRhoU)),
+                                          capi.dptr(np.ascontiguousarray(xRhoE)), capi.dptr(a), capi.dptr(b), capi.dptr(c)), "matrix_mul")
+        return a, b, c
+
+    def precondition(self, kind, xRho, xRhoU, xRhoE):
+        if isinstance(kind, str):
+            kind = capi.PRECOND_NAMES[kind]
+        a, b, c = (np.array(xRho, dtype=np.float64, order="C"), np.array(xRhoU, dtype=np.float64, order="C"),
+                   np.array(xRhoE, dtype=np.float64, order="C"))
+        self._chk(lib().orc_hb_precondition(self._h, kind, capi.dptr(a), capi.dptr(b), capi.dptr(c)), "precondition")
+        return a, b, c
+
+    def solve_delta(self, ctl):
+        n, N = self.n, self.N
+        a, b, c = np.zeros(n * N), np.zeros((n * N, 3)), np.zeros(n * N)
+        self._chk(lib().orc_hb_solve_delta(self._h, C.byref(ctl), capi.dptr(a), capi.dptr(b), capi.dptr(c)), "solve_delta")
+        return (a, b, c), self.residuals()
+
+    def iterate(self, ctl, n_iter=1):
+        self._chk(lib().orc_hb_iterate(self._h, C.byref(ctl), int(n_iter)), "iterate")
+        return self.residuals()
+
+    def residuals(self):
+        n = self.n
+        out = {"s_init": np.zeros(2 * n), "v_init": np.zeros(3 * n), "s_final": np.zeros(2 * n), "v_final": np.zeros(3 * n)}
+        it = C.c_int()
+        self._chk(lib().orc_hb_residuals_get(self._h, *[capi.dptr(out[k]) for k in ("s_init", "v_init", "s_final", "v_final")],
+                                             C.byref(it)), "residuals_get")
+        out["n_iterations"] = it.value
+        return out
+
+    def state_get(self):
+        parts = [o.state_get() for o in self.inst]
+        return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+
+    def pseudo(self):
+        n, N = self.n, self.N
+        a, b = np.zeros(n * N), np.zeros(n * N)
+        self._chk(lib().orc_hb_pseudo(self._h, capi.dptr(a), capi.dptr(b)), "pseudo")
+        return a, b

@@ -1,0 +1,116 @@
+"""Harmonic Balance: the CUDA path — nO time instances run as ONE replicated mesh behind icsb200_hb_set —
+against the reference-structured oracle (nO separate instance contexts + the global (2 nO, nO) system of
+dbnsFullyImplicitHBFoam, oracle/oracle_hb.cpp).  GPU only (-m gpu).
+
+Bars as in test_gpu_parity.py: kernels without global reductions must be bit-identical (HB sources, all LDU blocks with
+the HB diagonal, the coupled matrix product, LU-SGS with the shared diagonal, the dense 15x15 block-Jacobi); GMRES
+increments, residual history and fields after several outer iterations within 1e-8 relative."""
+import numpy as np
+import pytest
+
+from icsfoam_b200 import capi, cases
+from oracle.pyoracle import HB
+from tests.common import rel_err
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "roe-allmesh": lambda: cases.hb_box(6, 3, flux="ROE"),
+    "hllc-zoned": lambda: cases.hb_box(5, 3, flux="HLLC", limiter="Minmod", zoned=True, seed=5),
+    "roe-cyl": lambda: cases.hb_box(5, 3, flux="ROE", cyl=True, seed=7),
+    "ausm-5-instants": lambda: cases.hb_box(4, 5, flux="AUSMPlusUp", seed=9),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_hb_piecewise_bitwise(name, gpu_context):
+    case = CASES[name]()
+    H = HB(case)
+    g = case.apply(gpu_context())
+    NT = case.mesh.n_cells
+    # sources: flux residual + HB source (outerLoop.H:28-30, residualsUpdate.H:72-74)
+    g.calc_flux()
+    src_g = g.residual()
+    rdt_g, co_g = g.pseudo_dt()
+    g.assemble()
+    H.assemble()
+    for a, b in zip(src_g, H.residual()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(rdt_g, H.pseudo()[0])
+    # all 27 LDU arrays of every instance, with V D[J][J] on the diagonals (HBZone.C:435-518)
+    for blk in range(9):
+        for a, b in zip(g.matrix_get_ldu(blk), H.matrix_get_ldu(blk)):
+            assert np.array_equal(a, b), blk
+    rng = np.random.default_rng(11)
+    x = (rng.standard_normal(NT), rng.standard_normal((NT, 3)), rng.standard_normal(NT))
+    # coupled product including the inter-instance diagonal blocks
+    for a, b in zip(g.matrix_mul(*x), H.matrix_mul(*x)):
+        assert np.array_equal(a, b)
+    # LU-SGS with the rDiagCoeff shared by all instances (lusgs.C:50-123)
+    for a, b in zip(g.precondition("LUSGS", *x), H.precondition("LUSGS", *x)):
+        assert np.array_equal(a, b)
+    # dense (5 nO)^2 block-Jacobi
+    for a, b in zip(g.precondition("Jacobi", *x), H.precondition("Jacobi", *x)):
+        assert rel_err(a, b) <= 1e-12
+    # GMRES on the global system
+    (dr, dru, dre), res = g.solve_delta(case.controls)
+    (orr, oru, ore), ores = H.solve_delta(case.controls)
+    assert res.n_iterations == ores["n_iterations"]
+    for a, b in ((dr, orr), (dru, oru), (dre, ore)):
+        assert rel_err(a, b) <= 1e-8
+    gr = g.hb_residuals()
+    for k in ("s_init", "v_init", "s_final", "v_final"):
+        assert rel_err(gr[k], ores[k]) <= 1e-8, k
+
+
+@pytest.mark.parametrize("name,precond", [("roe-allmesh", "LUSGS"), ("hllc-zoned", "LUSGS"), ("roe-cyl", "Jacobi")])
+def test_hb_outer_iterations(name, precond, gpu_context):
+    case = CASES[name]()
+    ctl = capi.solver_controls(precond, n_directions=5, max_iter=10, tolerance=1e-10, rel_tol=1e-3)
+    H = HB(case)
+    g = case.apply(gpu_context())
+    for it in range(6):
+        rg = g.iterate(ctl)
+        ro = H.iterate(ctl)
+        gr = g.hb_residuals()
+        assert rg.n_iterations == ro["n_iterations"], it
+        assert rel_err(gr["s_init"], ro["s_init"]) <= 1e-8, it
+        assert rel_err(gr["v_init"], ro["v_init"]) <= 1e-8, it
+    sg, so = g.state_get(), H.state_get()
+    for k in ("rho", "rhoU", "rhoE", "p", "T"):
+        assert rel_err(sg[k], so[k]) <= 1e-8, k
+    # the SER quirk of the reference's HB loop (Courant number multiplied by 0 on the second iteration) is reproduced
+    assert np.array_equal(g.pseudo_dt()[1] > 0, np.ones(case.mesh.n_cells, bool))
+
+
+def test_hb_set_rejects_non_replicated_mesh(gpu_context):
+    case = cases.periodic_box(4)
+    g = case.apply(gpu_context())
+    D = np.zeros((3, 3))
+    with pytest.raises(capi.ApiError):
+        g.hb_set(3, D)
+
+
+def test_hb_off_is_bit_identical_to_plain_path(gpu_context):
+    """n_instants = 1 switches HB off; and a replicated mesh WITHOUT hb_set is just nO independent copies."""
+    case = cases.hb_box(5, 3)
+    g = gpu_context()
+    g.mesh_set(case.mesh)
+    b = case.base
+    g.thermo_set(b.R, b.Cp, b.mu, b.Pr)
+    g.schemes_set(case.schemes)
+    fid = {"p": capi.FIELD_P, "U": capi.FIELD_U, "T": capi.FIELD_T}
+    for K, inst in enumerate(case.instances):
+        for patch, fields in inst.bcs.items():
+            for field, (kind, params) in fields.items():
+                g.bc_set(f"{patch}@{K}", fid[field], kind, params)
+    g.state_set(case.p, case.U, case.T)
+    g.calc_flux()
+    src = g.residual()
+    from oracle.pyoracle import Oracle
+    N = b.mesh.n_cells
+    for K, inst in enumerate(case.instances):
+        o = inst.apply(Oracle())
+        o.calc_flux()
+        for a, r in zip(src, o.residual()):
+            assert np.array_equal(a[K * N:(K + 1) * N], r)
