@@ -192,3 +192,46 @@ def test_oracle_hb_converges_and_responds_to_unsteady_inlet():
     st = [o.state_get()["p"] for o in H.inst]
     # the instances differ (the inlet state oscillates) ...
     assert np.abs(st[0] - st[1]).max() > 1e-4 * np.abs(st[0]).max()
+
+
+def test_cpp_host_mirror_HBZone_matches_python(tmp_path):
+    """The C++ host mirror (icsfoam_b200/host/icsfoamB200.H: HBZone / HBZoneList) computes the same snapshots and D."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hbz.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include "icsfoamB200.H"
+using namespace icsfoamB200;
+int main()
+{
+    HBZoneList l;
+    l.zones.resize(2);
+    l.zones[0].setOmegaList({10.0, 13.0}, {1, 1});
+    l.zones[1].setOmegaList({10.0}, {2});
+    l.setInstants(5);
+    for (double t : l.selectedSnapshots) std::printf("%.17g ", t);
+    std::printf("\n");
+    for (auto& z : l.zones) { for (double d : z.D) std::printf("%.17g ", d); std::printf("\n"); }
+    HBZoneList u;
+    u.zones.resize(1);
+    u.zones[0].setOmegaList({251.0}, {1});
+    u.setInstants(3, false, 2 * M_PI / 251.0);
+    for (double d : u.zones[0].D) std::printf("%.17g ", d);
+    std::printf("\n");
+    return 0;
+}
+''')
+    exe = tmp_path / "hbz"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), "-I", os.path.join(root, "icsfoam_b200", "host"),
+                    str(src), "-o", str(exe), "-Wl,--unresolved-symbols=ignore-all"], check=True)  # no icsb200_* call is made
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    rows = [np.array([float(x) for x in line.split()]) for line in out]
+    ols = [hb.omega_list([10.0, 13.0], [1, 1]), hb.omega_list([10.0], [2])]
+    snaps, Ds = hb.set_instants(ols, 5)
+    assert np.allclose(rows[0], snaps, rtol=1e-12)
+    assert np.allclose(rows[1].reshape(5, 5), Ds[0], rtol=1e-9, atol=1e-9)
+    assert np.allclose(rows[2].reshape(5, 5), Ds[1], rtol=1e-9, atol=1e-9)
+    _, (D3,) = hb.set_instants([hb.omega_list([251.0], [1])], 3, selected_period=2 * np.pi / 251.0)
+    assert np.allclose(rows[3].reshape(3, 3), D3, rtol=1e-10, atol=1e-10 * 251)

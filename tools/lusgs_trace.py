@@ -31,3 +31,27 @@ print("compute+store (t3-t2)       median %.2f p90 %.2f p99 %.2f" % tuple(np.per
 print("start after last dep store  median %.2f (negative = warp was already waiting)" % np.median(tr[s, 0] - depstore[s]))
 late = (tr[s, 0] > depstore[s]).mean()
 print("fraction of slices whose warp started AFTER deps were stored: %.3f" % late)
+
+# ---- composition of the critical path: walk back from the slice that finished last through its latest dependency
+cur = int(np.argmax(tr[:, 3]))
+hops, det, comp, latecnt, latewait = 0, [], [], 0, []
+while True:
+    d = dep[cur][dep[cur] >= 0] if nl[cur] > 0 else []
+    if len(d) == 0:
+        break
+    prev = int(d[np.argmax(tr[d, 3])])
+    ds = tr[prev, 3]
+    det.append(tr[cur, 2] - ds)
+    comp.append(tr[cur, 3] - tr[cur, 2])
+    if tr[cur, 0] > ds:
+        latecnt += 1
+        latewait.append(tr[cur, 2] - tr[cur, 0])
+    hops += 1
+    cur = prev
+det, comp = np.array(det), np.array(comp)
+print("critical path: hops %d, span %.1f us; detection mean %.2f (median %.2f p90 %.2f), compute+store mean %.2f (median %.2f p90 %.2f)" % (
+    hops, det.sum() + comp.sum(), det.mean(), np.median(det), np.percentile(det, 90), comp.mean(), np.median(comp), np.percentile(comp, 90)))
+print("critical path: slices whose warp started after the dependency was stored: %d (their start->ready mean %.2f us)" % (
+    latecnt, np.mean(latewait) if latewait else 0.0))
+big = np.argsort(det)[-5:]
+print("largest detection delays on the critical path (us):", np.round(det[big], 2))
