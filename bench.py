@@ -255,8 +255,20 @@ def main():
                      "share": round(v[0] / total_ms, 4),
                      **({"GBps": round(alg[k] / (v[0] / max(v[1], 1) * 1e-3) / 1e9, 1)} if k in alg and v[1] else {})}
                  for k, v in timers.items() if v[1]}
+    # DRAM traffic of the dominant kernel: recorded from one `ncu --set full` capture of this very workload
+    # (profiles/traffic.json; ncu cannot run inside the timed bench), null for any other size / partition
+    traffic = None
+    try:
+        rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))
+        traffic = rec.get(f"onera-box-{args.n}-{world}gpu", {}).get(dom)
+    except Exception:
+        traffic = None
+    step_alg = (alg["gradient"] + alg["flux_residual"] + alg["jacobian"] + alg["spmv"] + 160 * Nl
+                + float(np.mean(prof_restarts)) * ((ctl.n_directions + 1) * (alg["spmv"] + alg["lusgs"])
+                                                   + Nl * (100 * ctl.n_directions ** 2 + 260 * ctl.n_directions + 200)))
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_kind,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_kind,
+                "whole_step_frac": round(step_alg / (ms / args.steps * 1e-3) / 1e9 / peak, 4),
                 "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": round(avg_ms, 4), "kernel_classes": breakdown}
 
     # ---- end to end through host buffers (pinned), p,U,T in and out every step
