@@ -81,7 +81,7 @@ def shock_tube(n=500, flux="ROE", transient=True):
     return Case("shockTube", mesh, R, Cp, sch, ctl, bcs, p, U, T, n_iter_default=10)
 
 
-def bump(nxb=66, ny=54, co=200.0):
+def bump(nxb=66, ny=54, co=200.0, mu=0.0, Pr=0.71):
     """C3 tutorials/circularArcBump/transonic, optionally refined (bump-4M: nxb=1280, ny=1040)."""
     mesh = mt.bump(nxb, ny)
     R, Cp = RR / 28.966, 1005.0
@@ -97,10 +97,10 @@ def bump(nxb=66, ny=54, co=200.0):
         "WALL3": {"p": zg, "U": ("slip", ()), "T": zg},
         "WALL4": {"p": zg, "U": ("slip", ()), "T": zg},
     }
-    return Case("bump", mesh, R, Cp, sch, ctl, bcs, p, U, T, n_iter_default=20)
+    return Case("bump", mesh, R, Cp, sch, ctl, bcs, p, U, T, mu=mu, Pr=Pr, n_iter_default=20)
 
 
-def onera_box(n=48, co=100.0, flux="HLLC", parts=None, rank=0):
+def onera_box(n=48, co=100.0, flux="HLLC", parts=None, rank=0, mu=0.0, Pr=0.71):
     """C4 synthetic stand-in for tutorials/OneraM6Wing (inviscid, HLLC, vanLeer, steady, Co=100).
     With parts=(px,py,pz) only partition `rank` is generated (fields are uniform, so no global arrays are needed)."""
     if parts is None:
@@ -120,10 +120,10 @@ def onera_box(n=48, co=100.0, flux="HLLC", parts=None, rank=0):
     bcs = {"wing": {"p": slip, "U": slip, "T": slip}, "symmetry": {"p": slip, "U": slip, "T": slip}}
     for n_ in ("inlet", "outlet", "lateral", "top"):
         bcs[n_] = dict(fs)
-    return Case("onera-box", mesh, R, Cp, sch, ctl, bcs, p, U, T, n_iter_default=20)
+    return Case("onera-box", mesh, R, Cp, sch, ctl, bcs, p, U, T, mu=mu, Pr=Pr, n_iter_default=20)
 
 
-def periodic_box(n=8, flux="HLLC", limiter="vanLeer", seed=0, nz=None, cyclic=True):
+def periodic_box(n=8, flux="HLLC", limiter="vanLeer", seed=0, nz=None, cyclic=True, mu=0.0, Pr=0.71):
     """Small randomised box with a translational cyclic pair in x — a parity-test workhorse, not a tutorial."""
     mesh = mt.structured(1, n, n, nz or n, 0, (0, 0, 0), (1.0, 1.2, 0.9),
                          patch_kinds=(capi.PATCH, capi.PATCH, capi.WALL, capi.PATCH, capi.SYMMETRYPLANE, capi.PATCH))
@@ -145,13 +145,13 @@ def periodic_box(n=8, flux="HLLC", limiter="vanLeer", seed=0, nz=None, cyclic=Tr
         "zmax": {"p": ("freestreamPressure", (1.0e5, 50.0, 10.0, 20.0)), "U": ("freestream", (50.0, 10.0, 20.0)),
                  "T": ("fixedValue", (305.0,))},
     }
-    return Case("periodic-box", mesh, 287.0, 1005.0, sch, ctl, bcs, p, U, T)
+    return Case("periodic-box", mesh, 287.0, 1005.0, sch, ctl, bcs, p, U, T, mu=mu, Pr=Pr)
 
 
-def scrambled_box(n=6, flux="HLLC", limiter="vanLeer", seed=0):
+def scrambled_box(n=6, flux="HLLC", limiter="vanLeer", seed=0, mu=0.0):
     """A box whose cells are renumbered at random: irregular LU-SGS levels, rows with up to 6 lower (or upper)
     neighbours, no structure for the tile heuristics to find — the 'unstructured numbering' stress case."""
-    base = periodic_box(n, flux, limiter, seed)
+    base = periodic_box(n, flux, limiter, seed, mu=mu)
     rng = np.random.default_rng(seed + 1000)
     perm = rng.permutation(base.mesh.n_cells).astype(np.int32)
     mesh = base.mesh.renumber(perm)
@@ -162,7 +162,7 @@ def scrambled_box(n=6, flux="HLLC", limiter="vanLeer", seed=0):
         if p["kind"] == capi.CYCLIC:
             p["kind"], p["nbr_patch"] = capi.PATCH, -1
     c = Case("scrambled-box", mesh, base.R, base.Cp, base.schemes, base.controls,
-             {k: v for k, v in base.bcs.items()}, base.p[inv], base.U[inv], base.T[inv])
+             {k: v for k, v in base.bcs.items()}, base.p[inv], base.U[inv], base.T[inv], mu=base.mu, Pr=base.Pr)
     return c
 
 

@@ -37,6 +37,7 @@ enum { ET_LOWER = 0, ET_UPPER = 1, ET_COUPLED = 2, ET_PHYS = 3 };
 enum {
     Q_RHO = 0, Q_P, Q_UX, Q_UY, Q_UZ, Q_CR, Q_E, Q_H,  // the NQ reconstructed scalars (order matters)
     Q_C,                                                 // sqrt(gamma/psi) (lambda)
+    Q_EC,                                                // eCalc = rhoE/rho - 0.5 |U|^2 (viscous residual, residualsUpdate.H:40)
     Q_T, Q_PSI,
     Q_W0, Q_W1, Q_W2, Q_W3, Q_W4,                        // conserved rho, rhoU(3), rhoE
     Q_COUNT
@@ -128,6 +129,8 @@ struct icsb200_ctx {
     double *d_Wold = nullptr, *d_Wold2 = nullptr, *d_Wprev = nullptr; // [5*NP] each
     double *d_src = nullptr, *d_dW = nullptr;                         // [5*NPH]
     double* d_faceFlux = nullptr;                                     // [5*NFG] GPU face order (only when requested)
+    double* d_gradE = nullptr;                                        // [3*NPH] gradient of eCalc (viscous runs only)
+    double* d_visc = nullptr;                                         // [8*NP] per-row viscous divergences: lapU(3) divTau(3) divSigmaU lapE
     int* d_bad = nullptr;                                              // [NPH] boundLocalTimeStep flags
     // ---- matrix ----
     double* d_offd = nullptr;  // [nEntries*25*32]

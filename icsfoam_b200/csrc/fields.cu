@@ -206,6 +206,11 @@ __global__ void k_primitives(int NP, int NH, int NB, const int* __restrict__ pos
     if (scheme == ICSB200_FLUX_AUSMPLUSUP) cR = sqrt(2.0 * (th.gamma - 1.0) / (th.gamma + 1.0) * H);
     else cR = fmax(cc, ICS_VSMALL);
     f[Q_E * NX + s] = E; f[Q_H * NX + s] = H; f[Q_C * NX + s] = cc; f[Q_CR * NX + s] = cR;
+    // eCalc = rhoE/rho - 0.5 magSqr(U) (residualsUpdate.H:40); boundary rhoE as updateFields.H:99-104 builds it
+    const double k2 = ux * ux + uy * uy + uz * uz;
+    const double rhoE = (i < NP) ? f[Q_W4 * NX + s] : rho * (he + 0.5 * k2);
+    const double rho0 = (i < NP) ? f[Q_W0 * NX + s] : rho;
+    f[Q_EC * NX + s] = rhoE / rho0 - 0.5 * k2;
 }
 
 // updateFields.H:7-22 — W += dW, U, e; flag cells that need energy bounding (max(neg(e-eBound)) > 0.5, :46,:58)
@@ -332,8 +337,8 @@ int ics_primitives(icsb200_ctx* c)
                                                              c->sch.flux_scheme, c->d_fields, c->NX);
     }
     CUDA_TRY(c, cudaGetLastError());
-    // neighbour-rank copies of the 9 arrays the face kernels gather: rho p Ux Uy Uz cR E H c (contiguous ids 0..8)
-    return ics_halo_fields(c, c->d_fields, c->NX, 9);
+    // neighbour-rank copies of the arrays the face kernels gather: rho p Ux Uy Uz cR E H c (+ eCalc) (contiguous ids 0..9)
+    return ics_halo_fields(c, c->d_fields, c->NX, c->mu > 0 ? 10 : 9);
 }
 
 // conserved variables + boundary + derived fields from freshly uploaded p, U, T (host-facing iterate)

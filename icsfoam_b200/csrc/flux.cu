@@ -250,6 +250,7 @@ __device__ __forceinline__ Flux5 faceFlux(const FaceState& s, V3 Sf, double magS
 
 // ------------------------------------------------------------------------------------------------ k_grad
 // gaussGrad::gradf for the NQ reconstructed scalars.  f: fields [Q_COUNT][NX]; grad: [NQ*3][NPH]
+template <int NQ>
 __global__ void __launch_bounds__(128, 4)
 k_grad(int NP, const int* __restrict__ pos2cell, const int* __restrict__ sliceOff, const int* __restrict__ rowNAll, const int* __restrict__ col,
        const int* __restrict__ meta, const int* __restrict__ gfid, const double* __restrict__ geo, size_t NFG, const double* __restrict__ V,
@@ -308,6 +309,7 @@ struct FluxArgs {
     double* src;                       // [5*NPH]
     double* faceFlux;                  // [5*NFG] or null
     double* phiB;                      // [NB]
+    const double* visc;                // [8*NP] viscous divergences (already divided by V) or null
 };
 
 // reconstruct all NQ scalars of one face.  rowIsOwner: the row cell is the face's owner (P)
@@ -380,6 +382,10 @@ k_flux(FluxArgs a)
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         double Rk = -(acc[k] / vol);
+        if (a.visc) {  // residualsUpdate.H:25-42: rhoUR += laplacian(muEff,U); += div(tauMC); rhoER += div(sigmaDotU & Sf); += laplacian(alphaEff,e)
+            if (k >= 1 && k <= 3) { Rk += a.visc[(size_t)(k - 1) * a.NP + p]; Rk += a.visc[(size_t)(3 + k - 1) * a.NP + p]; }
+            else if (k == 4) { Rk += a.visc[(size_t)6 * a.NP + p]; Rk += a.visc[(size_t)7 * a.NP + p]; }
+        }
         if (a.ddt.scheme != ICSB200_DDT_STEADY) {
             const double Wk = a.f[(size_t)(Q_W0 + k) * a.NX + p];
             double diag, source;
@@ -404,6 +410,168 @@ __global__ void k_zero(size_t n, double* __restrict__ x)
     if (i < n) x[i] = 0.0;
 }
 
+
+// ------------------------------------------------------------------------------------------------ k_visc
+// Viscous part of residualsUpdate.H:16-43 (laminar): per row, in ascending face id, the four surface integrals
+//   laplacian(muEff,U), div(tauMC), div(sigmaDotU & Sf), laplacian(alphaEff,eCalc)
+// with `Gauss linear corrected` laplacians (snGrad = nonOrthDeltaCoeffs (N - P) + (n - delta nonOrthDeltaCoeffs) &
+// interpolate(grad)), tauMC = mu dev2(T(grad U)), patch snGrad of U by patch-field type and the boundary values of
+// grad(U) from gaussGrad::correctBoundaryConditions.  Output: the divergences (sum / V) for k_flux to add in order.
+struct ViscArgs {
+    int NP, NB, F;
+    const int *pos2cell, *sliceOff, *rowNAll, *col, *meta, *gfid, *bfPatch;
+    const BCDev* bcs;
+    const double *geo, *dCoupled, *C, *V, *f, *grad, *gradE, *vic;
+    size_t NFG, NX, NPH;
+    double mu, alphaEff;
+    double* out;  // [8*NP]
+};
+
+__device__ __forceinline__ void gradUAt(const ViscArgs& a, int q, double g[9])  // g[3*i+j] = d_i U_j
+{
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) g[3 * i + j] = a.grad[(size_t)((Q_UX + j) * 3 + i) * a.NPH + q];
+}
+__device__ __forceinline__ void dev2T(const double g[9], double mu, double tau[9])
+{
+    double A[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) A[3 * i + j] = g[3 * j + i];
+    const double tr = A[0] + A[4] + A[8];
+    const double sph = (2.0 / 3.0) * tr;
+#pragma unroll
+    for (int k = 0; k < 9; k++) tau[k] = A[k];
+    tau[0] = A[0] - sph; tau[4] = A[4] - sph; tau[8] = A[8] - sph;
+#pragma unroll
+    for (int k = 0; k < 9; k++) tau[k] = mu * tau[k];
+}
+
+__global__ void __launch_bounds__(128, 2)
+k_visc(ViscArgs a)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.NP || a.pos2cell[p] < 0) return;
+    const int lane = p & 31;
+    const size_t base = (size_t)a.sliceOff[p >> 5];
+    double lap[3] = {0, 0, 0}, dtau[3] = {0, 0, 0}, sg = 0.0, le = 0.0;
+    const int nAll = a.rowNAll[p];
+    for (int j = 0; j < nAll; j++) {
+        const size_t e = (base + j) * 32 + lane;
+        const int c = a.col[e], m = a.meta[e], type = m & 3;
+        const size_t g = a.gfid[e];
+        const int b = (m >> 2) - a.F;
+        const double Sf[3] = {a.geo[G_SFX * a.NFG + g], a.geo[G_SFY * a.NFG + g], a.geo[G_SFZ * a.NFG + g]};
+        const double magSf = a.geo[G_MAGSF * a.NFG + g];
+        double nf[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) nf[d] = Sf[d] / magSf;
+        double fl[3], ft[3], fs, fe;
+        if (type != ET_PHYS) {
+            const bool coupled = type == ET_COUPLED;
+            const bool rowIsP = type != ET_LOWER;
+            const int P = rowIsP ? p : c, N = rowIsP ? c : p;
+            const double w = a.geo[G_W * a.NFG + g], dcn = a.geo[G_NONORTH * a.NFG + g];
+            double dv[3];
+            if (coupled) { dv[0] = a.dCoupled[b]; dv[1] = a.dCoupled[a.NB + b]; dv[2] = a.dCoupled[2 * (size_t)a.NB + b]; }
+            else { dv[0] = a.C[N] - a.C[P]; dv[1] = a.C[a.NPH + N] - a.C[a.NPH + P]; dv[2] = a.C[2 * a.NPH + N] - a.C[2 * a.NPH + P]; }
+            double corr[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) corr[d] = nf[d] - dv[d] * dcn;
+            auto lin = [&](double x, double y) { return coupled ? w * x + (1.0 - w) * y : w * (x - y) + y; };
+            double gP[9], gN[9], gf[9], tP[9], tN[9], tf[9];
+            gradUAt(a, P, gP); gradUAt(a, N, gN);
+            dev2T(gP, a.mu, tP); dev2T(gN, a.mu, tN);
+#pragma unroll
+            for (int k = 0; k < 9; k++) { gf[k] = lin(gP[k], gN[k]); tf[k] = lin(tP[k], tN[k]); }
+            const double muf = lin(a.mu, a.mu), alf = lin(a.alphaEff, a.alphaEff);
+            double UP[3], UN[3], Uf[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) { UP[d] = a.f[(size_t)(Q_UX + d) * a.NX + P]; UN[d] = a.f[(size_t)(Q_UX + d) * a.NX + N]; Uf[d] = lin(UP[d], UN[d]); }
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const double snG = dcn * (UN[d] - UP[d]) + (corr[0] * gf[d] + corr[1] * gf[3 + d] + corr[2] * gf[6 + d]);
+                fl[d] = muf * snG * magSf;
+                ft[d] = Sf[0] * tf[d] + Sf[1] * tf[3 + d] + Sf[2] * tf[6 + d];
+            }
+            double sd[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const double a0 = muf * gf[3 * i] + tf[3 * i], a1 = muf * gf[3 * i + 1] + tf[3 * i + 1], a2 = muf * gf[3 * i + 2] + tf[3 * i + 2];
+                sd[i] = a0 * Uf[0] + a1 * Uf[1] + a2 * Uf[2];
+            }
+            fs = sd[0] * Sf[0] + sd[1] * Sf[1] + sd[2] * Sf[2];
+            double gEf[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) gEf[d] = lin(a.gradE[(size_t)d * a.NPH + P], a.gradE[(size_t)d * a.NPH + N]);
+            const double eP = a.f[(size_t)Q_EC * a.NX + P], eN = a.f[(size_t)Q_EC * a.NX + N];
+            const double snE = dcn * (eN - eP) + (corr[0] * gEf[0] + corr[1] * gEf[1] + corr[2] * gEf[2]);
+            fe = alf * snE * magSf;
+        } else {
+            // physical patch face: P = row, patch values at slot c
+            const double dc = a.geo[G_DELTA * a.NFG + g];
+            const int pi = a.bfPatch[b];
+            const BCDev& bc = a.bcs[pi];
+            double Ui[3], Ub[3], sn[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) { Ui[d] = a.f[(size_t)(Q_UX + d) * a.NX + p]; Ub[d] = a.f[(size_t)(Q_UX + d) * a.NX + c]; }
+            const int kind = bc.kind[ICSB200_FIELD_U];
+            if (kind == ICSB200_BC_FIXEDVALUE || kind == ICSB200_BC_PRESSUREINLETOUTLETVELOCITY) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) sn[d] = dc * (Ub[d] - Ui[d]);
+            } else if (kind == ICSB200_BC_SLIP) {
+                const double xx = 1.0 - 2.0 * (nf[0] * nf[0]), xy = 0.0 - 2.0 * (nf[0] * nf[1]), xz = 0.0 - 2.0 * (nf[0] * nf[2]);
+                const double yy = 1.0 - 2.0 * (nf[1] * nf[1]), yz = 0.0 - 2.0 * (nf[1] * nf[2]), zz = 1.0 - 2.0 * (nf[2] * nf[2]);
+                const double t[3] = {xx * Ui[0] + xy * Ui[1] + xz * Ui[2], xy * Ui[0] + yy * Ui[1] + yz * Ui[2], xz * Ui[0] + yz * Ui[1] + zz * Ui[2]};
+#pragma unroll
+                for (int d = 0; d < 3; d++) sn[d] = (t[d] - Ui[d]) * (dc / 2.0);
+            } else if (kind == ICSB200_BC_INLETOUTLET) {
+                const double vfrac = 1.0 - a.vic[a.NB + b];
+#pragma unroll
+                for (int d = 0; d < 3; d++) sn[d] = vfrac * (bc.prm[ICSB200_FIELD_U][d] - Ui[d]) * dc + (1.0 - vfrac) * 0.0;
+            } else {
+                sn[0] = sn[1] = sn[2] = 0.0;
+            }
+            double gP[9], gb[9], tb[9];
+            gradUAt(a, p, gP);
+#pragma unroll
+            for (int jj = 0; jj < 3; jj++) {
+                const double ng = nf[0] * gP[jj] + nf[1] * gP[3 + jj] + nf[2] * gP[6 + jj];
+#pragma unroll
+                for (int i = 0; i < 3; i++) gb[3 * i + jj] = gP[3 * i + jj] + nf[i] * (sn[jj] - ng);
+            }
+            dev2T(gb, a.mu, tb);
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                fl[d] = a.mu * sn[d] * magSf;
+                ft[d] = Sf[0] * tb[d] + Sf[1] * tb[3 + d] + Sf[2] * tb[6 + d];
+            }
+            double sd[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const double a0 = a.mu * gb[3 * i] + tb[3 * i], a1 = a.mu * gb[3 * i + 1] + tb[3 * i + 1], a2 = a.mu * gb[3 * i + 2] + tb[3 * i + 2];
+                sd[i] = a0 * Ub[0] + a1 * Ub[1] + a2 * Ub[2];
+            }
+            fs = sd[0] * Sf[0] + sd[1] * Sf[1] + sd[2] * Sf[2];
+            const double eP = a.f[(size_t)Q_EC * a.NX + p], eB = a.f[(size_t)Q_EC * a.NX + c];
+            fe = a.alphaEff * (dc * (eB - eP)) * magSf;
+        }
+        if (type == ET_LOWER) {
+            lap[0] -= fl[0]; lap[1] -= fl[1]; lap[2] -= fl[2]; dtau[0] -= ft[0]; dtau[1] -= ft[1]; dtau[2] -= ft[2]; sg -= fs; le -= fe;
+        } else {
+            lap[0] += fl[0]; lap[1] += fl[1]; lap[2] += fl[2]; dtau[0] += ft[0]; dtau[1] += ft[1]; dtau[2] += ft[2]; sg += fs; le += fe;
+        }
+    }
+    const double vol = a.V[p];
+#pragma unroll
+    for (int d = 0; d < 3; d++) { a.out[(size_t)d * a.NP + p] = lap[d] / vol; a.out[(size_t)(3 + d) * a.NP + p] = dtau[d] / vol; }
+    a.out[(size_t)6 * a.NP + p] = sg / vol;
+    a.out[(size_t)7 * a.NP + p] = le / vol;
+}
+
 }  // namespace
 
 DdtPrm makeDdt(const icsb200_ctx* c)
@@ -426,11 +594,24 @@ int ics_gradients(icsb200_ctx* c)
 {
     {
         LaunchScope ls(c, TM_GRAD);
-        k_grad<<<gridFor(c->NP, 128), 128, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_col, c->d_meta, c->d_gfid,
-                                                          c->d_geo, c->NFG, c->d_V, c->d_fields, c->NX, c->d_grad, c->NPH);
+        k_grad<NQ><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_col, c->d_meta, c->d_gfid,
+                                                              c->d_geo, c->NFG, c->d_V, c->d_fields, c->NX, c->d_grad, c->NPH);
     }
     CUDA_TRY(c, cudaGetLastError());
-    return ics_halo_fields(c, c->d_grad, c->NPH, NQ * 3);
+    int r = ics_halo_fields(c, c->d_grad, c->NPH, NQ * 3);
+    if (r || !(c->mu > 0)) return r;
+    // viscous runs: gradient of eCalc for the non-orthogonal correction of laplacian(alphaEff, e)
+    if (!c->d_gradE) {
+        if ((r = devAlloc(c, &c->d_gradE, (size_t)3 * c->NPH))) return r;
+        CUDA_TRY(c, cudaMemsetAsync(c->d_gradE, 0, sizeof(double) * 3 * c->NPH, c->stream));
+    }
+    {
+        LaunchScope ls(c, TM_GRAD);
+        k_grad<1><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_col, c->d_meta, c->d_gfid,
+                                                             c->d_geo, c->NFG, c->d_V, c->q(Q_EC), c->NX, c->d_gradE, c->NPH);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    return ics_halo_fields(c, c->d_gradE, c->NPH, 3);
 }
 
 int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
@@ -451,6 +632,22 @@ int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
     a.src = c->d_src;
     a.faceFlux = storeFaceFlux ? c->d_faceFlux : nullptr;
     a.phiB = c->d_phiB;
+    a.visc = nullptr;
+    if (c->mu > 0) {  // if (!inviscid)  (createFields.H:37-45)
+        if (!c->d_visc) { int r = devAlloc(c, &c->d_visc, (size_t)8 * c->NP); if (r) return r; }
+        ViscArgs v{};
+        v.NP = c->NP; v.NB = c->NB; v.F = c->F;
+        v.pos2cell = c->d_pos2cell; v.sliceOff = c->d_sliceOff; v.rowNAll = c->d_rowNAll; v.col = c->d_col; v.meta = c->d_meta; v.gfid = c->d_gfid;
+        v.bfPatch = c->d_bfPatch; v.bcs = c->d_bc;
+        v.geo = c->d_geo; v.dCoupled = c->d_dCoupled; v.C = c->d_C; v.V = c->d_V; v.f = c->d_fields; v.grad = c->d_grad; v.gradE = c->d_gradE; v.vic = c->d_vic;
+        v.NFG = c->NFG; v.NX = c->NX; v.NPH = c->NPH;
+        v.mu = c->mu; v.alphaEff = c->gamma * (c->mu / c->Pr);
+        v.out = c->d_visc;
+        LaunchScope ls(c, TM_FLUX);
+        k_visc<<<gridFor(c->NP, 128), 128, 0, c->stream>>>(v);
+        CUDA_TRY(c, cudaGetLastError());
+        a.visc = c->d_visc;
+    }
     {
         LaunchScope ls(c, TM_FLUX);
         const int grid = gridFor(c->NP, 128);

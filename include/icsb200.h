@@ -114,7 +114,10 @@ int icsb200_mesh_set(icsb200_ctx* ctx, int n_cells, int n_internal_faces, int n_
                      const int* neighbour, const double* Sf, const double* magSf, const double* weights,
                      const double* deltaCoeffs, const double* nonOrthDeltaCoeffs, const double* C, const double* V,
                      const double* Cf, int n_patches, const icsb200_patch* patches, const int solutionD[3]);
-/* hePsiThermo<pureMixture<constTransport<hConst<perfectGas>>>>, sensibleInternalEnergy (createFields.H:17-35) */
+/* hePsiThermo<pureMixture<constTransport<hConst<perfectGas>>>>, sensibleInternalEnergy (createFields.H:17-35).
+ * mu > 0 makes the run viscous (createFields.H:37-45 `inviscid`): icsb200_residual / iterate then add the laminar
+ * viscous terms of residualsUpdate.H:16-43 (laplacian(muEff,U), div(tauMC), div(sigmaDotU & Sf), laplacian(alphaEff,e),
+ * `Gauss linear corrected`) and icsb200_assemble the Lax-Friedrichs viscous Jacobian (viscousFluxScheme.C:220-246). */
 int icsb200_thermo_set(icsb200_ctx* ctx, double R, double Cp, double mu, double Pr);
 int icsb200_schemes_set(icsb200_ctx* ctx, const icsb200_schemes* s);
 /* fvPatchField of p, U or T on one patch (0/p, 0/U, 0/T boundaryField entries) */

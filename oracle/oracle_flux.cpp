@@ -340,7 +340,170 @@ static void fvmDdt(const Ctx& c, const vecd& vf, const vecd& vf0, const vecd& vf
     }
 }
 
-// residualsUpdate.H (inviscid part; the viscous fvc:: terms are SURVEY §8f rank 1)
+
+// ---------------------------------------------------------------------------------------------- viscous residual
+// residualsUpdate.H:16-43 (laminar: muEff = mu, alphaEff = gamma mu / Pr constant fields):
+//   tauMC = muEff*dev2(T(fvc::grad(U)));  rhoUR += fvc::laplacian(muEff,U) + fvc::div(tauMC);
+//   sigmaDotU = (interpolate(muEff)*interpolate(grad(U)) + interpolate(tauMC)) & interpolate(U);
+//   rhoER += fvc::div(sigmaDotU & Sf) + fvc::laplacian(alphaEff, eCalc),  eCalc = rhoE/rho - 0.5 magSqr(U)
+// OpenFOAM semantics restated (fvSchemes: laplacianSchemes `Gauss linear corrected`, gradSchemes / divSchemes
+// `Gauss linear`, snGradSchemes `corrected`):
+//   fvc::laplacian(g, vf) = fvc::div(interpolate(g) * snGrad(vf) * magSf)
+//   snGrad(vf)_f = nonOrthDeltaCoeffs (vf_N - vf_P) + nonOrthCorrectionVectors & interpolate(grad(vf.component))
+//   nonOrthCorrectionVectors = n - delta * nonOrthDeltaCoeffs (zero on non-coupled patches)
+//   patch snGrad: fvPatchField::snGrad() of the patch field type (below); eCalc has calculated patches
+//   grad(U) patch values: gaussGrad::correctBoundaryConditions: gb = gP + n (snGrad(U)_b - n & gP)
+namespace {
+
+// fvPatchField<vector>::snGrad() of the U patch field on face f (deltaCoeffs = patch.deltaCoeffs() = 1/|delta|)
+void snGradUPatch(const Ctx& c, int pi, int f, double out[3])
+{
+    const Mesh& m = c.m;
+    const int b = f - m.F, o = m.owner[f], s = m.N + b;
+    const double dc = m.deltaCoeffs[f];
+    const double* Ui = &c.U[3 * (size_t)o];
+    const double* Ub = &c.U[3 * (size_t)s];
+    switch (c.bc[pi][ICSB200_FIELD_U].kind) {
+        case ICSB200_BC_FIXEDVALUE:
+        case ICSB200_BC_PRESSUREINLETOUTLETVELOCITY:  // directionMixed::snGrad = (normalValue + transformGradValue - pif)*deltaCoeffs
+            for (int d = 0; d < 3; d++) out[d] = dc * (Ub[d] - Ui[d]);
+            break;
+        case ICSB200_BC_SLIP: {  // basicSymmetryFvPatchField::snGrad = (transform(I - 2.0*sqr(nHat), pif) - pif)*(deltaCoeffs/2.0)
+            double n[3];
+            for (int d = 0; d < 3; d++) n[d] = m.Sf[3 * f + d] / m.magSf[f];
+            double xx = 1.0 - 2.0 * (n[0] * n[0]), xy = 0.0 - 2.0 * (n[0] * n[1]), xz = 0.0 - 2.0 * (n[0] * n[2]);
+            double yy = 1.0 - 2.0 * (n[1] * n[1]), yz = 0.0 - 2.0 * (n[1] * n[2]), zz = 1.0 - 2.0 * (n[2] * n[2]);
+            double t[3] = {xx * Ui[0] + xy * Ui[1] + xz * Ui[2], xy * Ui[0] + yy * Ui[1] + yz * Ui[2], xz * Ui[0] + yz * Ui[1] + zz * Ui[2]};
+            for (int d = 0; d < 3; d++) out[d] = (t[d] - Ui[d]) * (dc / 2.0);
+            break;
+        }
+        case ICSB200_BC_INLETOUTLET: {  // mixedFvPatchField::snGrad, refGrad = 0; valueFraction as frozen at the last evaluation
+            const double vfrac = 1.0 - c.vicU[3 * (size_t)b];
+            const BC& bc = c.bc[pi][ICSB200_FIELD_U];
+            for (int d = 0; d < 3; d++) out[d] = vfrac * (bc.prm[d] - Ui[d]) * dc + (1.0 - vfrac) * 0.0;
+            break;
+        }
+        default:  // zeroGradient
+            out[0] = out[1] = out[2] = 0.0;
+    }
+}
+
+inline void dev2T(const double g[9] /* grad(U): g[3*i+j] = d_i U_j */, double mu, double tau[9])
+{
+    // mu * dev2(T(g)),  dev2(A) = A - (2/3) tr(A) I
+    double A[9];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) A[3 * i + j] = g[3 * j + i];
+    const double tr = A[0] + A[4] + A[8];
+    const double sph = (2.0 / 3.0) * tr;
+    for (int k = 0; k < 9; k++) tau[k] = A[k];
+    tau[0] = A[0] - sph; tau[4] = A[4] - sph; tau[8] = A[8] - sph;
+    for (int k = 0; k < 9; k++) tau[k] = mu * tau[k];
+}
+
+}  // namespace
+
+void viscousResidual(Ctx& c, vecd& rhoUR, vecd& rhoER)
+{
+    const Mesh& m = c.m;
+    const size_t n = (size_t)m.N + m.NB;
+    const double mu = c.mu, alphaEff = c.gamma * (c.mu / c.Pr);
+    // gradients of the components of U and of eCalc (cells + coupled boundary slots)
+    vecd comp(n), gU[3], eCalc(n), gE;
+    for (int d = 0; d < 3; d++) {
+        for (size_t i = 0; i < n; i++) comp[i] = c.U[3 * i + d];
+        gradGauss(c, comp, gU[d]);
+    }
+    for (size_t i = 0; i < n; i++) {
+        const double* u = &c.U[3 * i];
+        eCalc[i] = c.rho[i] != 0.0 ? c.rhoE[i] / c.rho[i] - 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) : 0.0;
+    }
+    gradGauss(c, eCalc, gE);
+    auto gradUOf = [&](size_t i, double g[9]) {  // g[3*i+j] = d_i U_j
+        for (int d = 0; d < 3; d++) for (int j = 0; j < 3; j++) g[3 * d + j] = gU[j][3 * i + d];
+    };
+    const size_t FT = m.FT;
+    vecd lapU(3 * FT, 0.0), divTau(3 * FT, 0.0), sig(FT, 0.0), lapE(FT, 0.0);
+    auto em = emptyMask(m);
+    auto faceCoupledOrInternal = [&](int f, int P, size_t Ns, const double* dvec, bool coupled) {
+        const double w = m.w[f], magSf = m.magSf[f], dcn = m.nonOrthDeltaCoeffs[f];
+        double nf[3], corr[3];
+        for (int d = 0; d < 3; d++) nf[d] = m.Sf[3 * f + d] / magSf;
+        for (int d = 0; d < 3; d++) corr[d] = nf[d] - dvec[d] * dcn;
+        auto lin = [&](double a, double b) { return coupled ? w * a + (1.0 - w) * b : w * (a - b) + b; };
+        double gP[9], gN[9], gf[9], tP[9], tN[9], tf[9];
+        gradUOf(P, gP); gradUOf(Ns, gN);
+        dev2T(gP, mu, tP); dev2T(gN, mu, tN);
+        for (int k = 0; k < 9; k++) { gf[k] = lin(gP[k], gN[k]); tf[k] = lin(tP[k], tN[k]); }
+        const double muf = lin(mu, mu), alf = lin(alphaEff, alphaEff);
+        double Uf[3];
+        for (int j = 0; j < 3; j++) Uf[j] = lin(c.U[3 * (size_t)P + j], c.U[3 * Ns + j]);
+        for (int j = 0; j < 3; j++) {
+            // component j: gradient of U_j at the face = column j of gf
+            const double snG = dcn * (c.U[3 * Ns + j] - c.U[3 * (size_t)P + j]) + (corr[0] * gf[j] + corr[1] * gf[3 + j] + corr[2] * gf[6 + j]);
+            lapU[3 * (size_t)f + j] = muf * snG * magSf;
+            divTau[3 * (size_t)f + j] = m.Sf[3 * f] * tf[j] + m.Sf[3 * f + 1] * tf[3 + j] + m.Sf[3 * f + 2] * tf[6 + j];
+        }
+        double sd[3];
+        for (int i = 0; i < 3; i++) {
+            const double a0 = muf * gf[3 * i] + tf[3 * i], a1 = muf * gf[3 * i + 1] + tf[3 * i + 1], a2 = muf * gf[3 * i + 2] + tf[3 * i + 2];
+            sd[i] = a0 * Uf[0] + a1 * Uf[1] + a2 * Uf[2];
+        }
+        sig[f] = sd[0] * m.Sf[3 * f] + sd[1] * m.Sf[3 * f + 1] + sd[2] * m.Sf[3 * f + 2];
+        double gEf[3];
+        for (int d = 0; d < 3; d++) gEf[d] = lin(gE[3 * (size_t)P + d], gE[3 * Ns + d]);
+        const double snE = dcn * (eCalc[Ns] - eCalc[P]) + (corr[0] * gEf[0] + corr[1] * gEf[1] + corr[2] * gEf[2]);
+        lapE[f] = alf * snE * magSf;
+    };
+    for (int f = 0; f < m.F; f++) {
+        const int P = m.owner[f], N = m.neighbour[f];
+        const double dvec[3] = {m.C[3 * (size_t)N] - m.C[3 * (size_t)P], m.C[3 * (size_t)N + 1] - m.C[3 * (size_t)P + 1], m.C[3 * (size_t)N + 2] - m.C[3 * (size_t)P + 2]};
+        faceCoupledOrInternal(f, P, (size_t)N, dvec, false);
+    }
+    for (size_t pi = 0; pi < m.patches.size(); pi++) {
+        const Patch& p = m.patches[pi];
+        if (m.empty(p)) continue;
+        for (int f = p.start; f < p.start + p.size; f++) {
+            if (!faceActive(m, f, em)) continue;
+            const int b = f - m.F, P = m.owner[f];
+            const size_t s = (size_t)m.N + b;
+            if (m.coupled(p)) { faceCoupledOrInternal(f, P, s, &m.dCoupled[3 * (size_t)b], true); continue; }
+            const double magSf = m.magSf[f];
+            double nf[3], sn[3], gP[9], gb[9], tb[9];
+            for (int d = 0; d < 3; d++) nf[d] = m.Sf[3 * f + d] / magSf;
+            snGradUPatch(c, (int)pi, f, sn);
+            gradUOf(P, gP);
+            // gaussGrad::correctBoundaryConditions: gb = gP + n * (snGrad - (n & gP))
+            for (int j = 0; j < 3; j++) {
+                const double ng = nf[0] * gP[j] + nf[1] * gP[3 + j] + nf[2] * gP[6 + j];
+                for (int i = 0; i < 3; i++) gb[3 * i + j] = gP[3 * i + j] + nf[i] * (sn[j] - ng);
+            }
+            dev2T(gb, mu, tb);
+            const double* Ub = &c.U[3 * s];
+            for (int j = 0; j < 3; j++) {
+                lapU[3 * (size_t)f + j] = mu * sn[j] * magSf;
+                divTau[3 * (size_t)f + j] = m.Sf[3 * f] * tb[j] + m.Sf[3 * f + 1] * tb[3 + j] + m.Sf[3 * f + 2] * tb[6 + j];
+            }
+            double sd[3];
+            for (int i = 0; i < 3; i++) {
+                const double a0 = mu * gb[3 * i] + tb[3 * i], a1 = mu * gb[3 * i + 1] + tb[3 * i + 1], a2 = mu * gb[3 * i + 2] + tb[3 * i + 2];
+                sd[i] = a0 * Ub[0] + a1 * Ub[1] + a2 * Ub[2];
+            }
+            sig[f] = sd[0] * m.Sf[3 * f] + sd[1] * m.Sf[3 * f + 1] + sd[2] * m.Sf[3 * f + 2];
+            lapE[f] = alphaEff * (m.deltaCoeffs[f] * (eCalc[s] - eCalc[P])) * magSf;
+        }
+    }
+    vecd dv;
+    surfaceIntegrate(c, lapU, 3, dv);
+    for (size_t i = 0; i < dv.size(); i++) rhoUR[i] += dv[i];
+    surfaceIntegrate(c, divTau, 3, dv);
+    for (size_t i = 0; i < dv.size(); i++) rhoUR[i] += dv[i];
+    surfaceIntegrate(c, sig, 1, dv);
+    for (size_t i = 0; i < dv.size(); i++) rhoER[i] += dv[i];
+    surfaceIntegrate(c, lapE, 1, dv);
+    for (size_t i = 0; i < dv.size(); i++) rhoER[i] += dv[i];
+}
+
+// residualsUpdate.H:1-83
 void residualsUpdate(Ctx& c)
 {
     const Mesh& m = c.m;
@@ -351,6 +514,7 @@ void residualsUpdate(Ctx& c)
     for (auto& v : rhoR) v = -v;
     for (auto& v : rhoUR) v = -v;
     for (auto& v : rhoER) v = -v;
+    if (c.mu > 0) viscousResidual(c, rhoUR, rhoER);  // if (!inviscid)  (createFields.H:37-45)
     if (c.sch.ddt_scheme != ICSB200_DDT_STEADY) {
         vecd dg, sr;
         fvmDdt(c, c.rho, c.rho0, c.rho00, 1, dg, sr);

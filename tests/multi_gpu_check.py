@@ -19,9 +19,10 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     parts = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+    mu = float(os.environ.get("ICS_MULTI_MU", "0"))   # > 0: laminar viscous residual (halo of eCalc and its gradient)
     ids = [Context.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
-    case = cases.onera_box(n, parts=parts, rank=rank)
+    case = cases.onera_box(n, parts=parts, rank=rank, mu=mu)
     ctx = case.apply(Context(device=local, nccl_id=ids[0], rank=rank, n_ranks=world))
     hist = []
     flux0 = ctx.calc_flux()
@@ -35,7 +36,7 @@ def main():
     ok = True
     if rank == 0:
         from oracle.pyoracle import World
-        meshes = [cases.onera_box(n, parts=parts, rank=r) for r in range(world)]
+        meshes = [cases.onera_box(n, parts=parts, rank=r, mu=mu) for r in range(world)]
         w = World(world)
         w.mesh_set([c.mesh for c in meshes])
         for o, c in zip(w.ranks, meshes):

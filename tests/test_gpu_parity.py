@@ -49,6 +49,12 @@ LIVE = {
     "onera": lambda: cases.onera_box(9),
     "scrambled-hllc": lambda: cases.scrambled_box(6, "HLLC", "vanLeer", seed=41),
     "scrambled-roe": lambda: cases.scrambled_box(5, "ROE", "Minmod", seed=42),
+    # laminar viscous residual (residualsUpdate.H:16-43) + LF viscous Jacobian: cyclic + wall + symmetry + mixed patches,
+    # a non-orthogonal mesh (bump: totalPressure / directionMixed inlet) and an unstructured numbering
+    "box-viscous-roe": lambda: cases.periodic_box(6, "ROE", "vanLeer", seed=51, mu=0.05),
+    "box-viscous-hllc": lambda: cases.periodic_box(5, "HLLC", "Minmod", seed=52, mu=0.2, Pr=1.3),
+    "bump-viscous": lambda: cases.bump(15, 10, mu=0.02),
+    "scrambled-viscous": lambda: cases.scrambled_box(5, "HLLC", "vanLeer", seed=53, mu=0.1),
     "shocktube-ausm": lambda: cases.shock_tube(64, "AUSMPlusUp"),
     "shocktube-roe": lambda: cases.shock_tube(50, "ROE"),
 }

@@ -393,3 +393,33 @@ def test_forward_step_polyhedral_mesh_c2():
     assert np.isfinite(st["rho"]).all() and st["rho"].min() > 0.2 * rho0.min()
     assert st["rho"].max() > 1.05 * rho0.max()                      # compression in front of the step
     assert np.abs(st["U"][:, 2]).max() == 0.0                       # empty direction stays untouched
+
+
+def test_viscous_residual_known_answers():
+    """Laminar viscous residual (residualsUpdate.H:16-43) on an orthogonal box, interior cells:
+    linear shear U = (a y, 0, 0): no momentum residual, energy residual = viscous heating mu a^2 per unit volume;
+    U = (b y^2, 0, 0): x-momentum residual = mu * 2 b (the discrete Laplacian is exact for quadratics)."""
+    from icsfoam_b200 import meshtools as mt
+    n, mu, a, b = 8, 0.7, 3.0, 2.0
+    mesh = mt.structured(1, n, n, n, 0, (0, 0, 0), (1.0, 1.0, 1.0), patch_kinds=(capi.PATCH,) * 6)
+    N = mesh.n_cells
+    interior = np.all((mesh.C > 0.2) & (mesh.C < 0.8), axis=1)
+    sch = capi.default_schemes(flux_scheme="HLLC", limiter_rho="linear", limiter_U="linear", limiter_T="linear")
+
+    def residual(U):
+        case = cases.Case("k", mesh, 287.0, 1005.0, sch, capi.solver_controls(), {}, np.full(N, 1e5), U, np.full(N, 300.0), mu=mu, Pr=0.71)
+        o = case.apply(Oracle())
+        o.calc_flux()
+        return o.residual()
+
+    U = np.zeros((N, 3)); U[:, 0] = a * mesh.C[:, 1]
+    r = residual(U)
+    assert np.allclose((r[2] / mesh.V)[interior], mu * a * a, rtol=1e-9)
+    assert np.abs(r[1] / mesh.V[:, None])[interior].max() < 1e-9
+    U = np.zeros((N, 3)); U[:, 0] = b * mesh.C[:, 1] ** 2
+    r = residual(U)
+    assert np.allclose((r[1][:, 0] / mesh.V)[interior], 2 * mu * b, rtol=1e-9)
+    # inviscid run of the same state has none of it
+    case = cases.Case("k", mesh, 287.0, 1005.0, sch, capi.solver_controls(), {}, np.full(N, 1e5), U, np.full(N, 300.0))
+    o = case.apply(Oracle()); o.calc_flux()
+    assert np.abs(o.residual()[1][:, 0] / mesh.V)[interior].max() < 1e-9

@@ -48,11 +48,12 @@ def test_partition_processor_patches_match():
             assert np.allclose(m.weights[fa] + other.weights[fb], 1.0, atol=1e-14)
 
 
-@pytest.mark.parametrize("n_parts,mode", [(2, "x"), (4, (2, 2, 1))])
-def test_partitioned_oracle_matches_single_domain(n_parts, mode):
+@pytest.mark.parametrize("n_parts,mode,mu", [(2, "x", 0.0), (4, (2, 2, 1), 0.0), (4, (2, 2, 1), 0.5)])
+def test_partitioned_oracle_matches_single_domain(n_parts, mode, mu):
     """Fluxes / residuals / SpMV do not depend on the decomposition (only LU-SGS and hence the GMRES history do —
-    lusgs.C:149,181 keeps the sweeps rank-local)."""
-    case = cases.onera_box(6)
+    lusgs.C:149,181 keeps the sweeps rank-local).  mu > 0 adds the viscous residual, whose processor-patch faces need the
+    neighbour's gradients of U and eCalc."""
+    case = cases.onera_box(6, mu=mu)
     single = case.apply(Oracle())
     phi, phiUp, phiEp = single.calc_flux()
     src = single.residual()
