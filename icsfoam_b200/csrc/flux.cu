@@ -6,10 +6,12 @@
 // and of residualsUpdate.H:1-83, by two kernels:
 //   k_grad : one thread per cell row, gathers the cell's faces in ascending face id (= the order gaussGrad::gradf's
 //            face loop touches that cell), 8 scalars at once;
-//   k_flux : one thread per cell row, reconstructs L/R states of each face of the row (NVD/TVD r, vanLeer / Minmod),
-//            evaluates the face flux in the face's own orientation (so both sides compute the identical value),
-//            accumulates -div in face order (fvc::surfaceIntegrate order), applies the dual-time terms
-//            (dualTimeDdtScheme.C:111-126, residualsUpdate.H:74-79) and writes the sources R*V.
+//   k_flux_faces : one thread per cell row; reconstructs L/R states (NVD/TVD r, vanLeer / Minmod) and evaluates the flux
+//            of every face the row OWNS (upper, coupled, physical) once, in the face's own orientation, 5 doubles per
+//            face in GPU-face order (the fp64 pipe, not HBM, bounds this kernel: ~42 IEEE divisions/sqrts per face);
+//   k_flux_gather : one thread per row; sums its faces' fluxes in ascending face id (fvc::surfaceIntegrate order; the
+//            faces where it is the neighbour with a minus sign), adds the viscous divergences, applies the dual-time
+//            terms (dualTimeDdtScheme.C:111-126, residualsUpdate.H:74-79) and writes the sources R*V.
 // No atomics, no colouring: every output is owned by exactly one thread.  HBM-bound reads are coalesced across
 // the 32 rows of a slice; neighbour gathers hit L2/L1 (hyperplane ordering keeps the three live levels resident).
 // Arithmetic: fp64, -fmad=false, same operand order as the reference expressions.
@@ -299,7 +301,7 @@ struct DdtPrm {
 
 struct FluxArgs {
     int NP, NB, F;
-    const int *pos2cell, *sliceOff, *rowNAll, *col, *meta, *gfid;
+    const int *pos2cell, *sliceOff, *rowNAll, *rowNLow, *col, *meta, *gfid;
     const double *geo, *dCoupled, *C, *V, *f, *grad;
     size_t NFG, NX, NPH;
     int limRho, limU, limT;
@@ -344,18 +346,20 @@ __device__ __forceinline__ void reconstructFace(const FluxArgs& a, int p, int c,
     s.c_l = L[Q_CR]; s.c_r = R[Q_CR]; s.E_l = L[Q_E]; s.E_r = R[Q_E]; s.H_l = L[Q_H]; s.H_r = R[Q_H];
 }
 
+// Pass 1: every row evaluates the faces it owns (entries at and after rowNLow: upper, coupled and physical faces) ONCE,
+// in the face's own orientation, and stores the 5 fluxes in GPU-face order — the row's own entries are consecutive
+// GPU face ids per lane, so the stores coalesce like the geometry reads.
 template <int SCHEME>
 __global__ void __launch_bounds__(128, 4)
-k_flux(FluxArgs a)
+k_flux_faces(FluxArgs a)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.NP || a.pos2cell[p] < 0) return;
     const int lane = p & 31;
     const size_t base = (size_t)a.sliceOff[p >> 5];
-    double acc[5] = {0, 0, 0, 0, 0};
     const int nAll = a.rowNAll[p];
     constexpr bool needC = SCHEME != ICSB200_FLUX_ROE;
-    for (int j = 0; j < nAll; j++) {
+    for (int j = a.rowNLow[p]; j < nAll; j++) {
         const size_t e = (base + j) * 32 + lane;
         const int c = a.col[e], m = a.meta[e], type = m & 3;
         const size_t g = a.gfid[e];
@@ -365,16 +369,29 @@ k_flux(FluxArgs a)
         const V3 Sf = {a.geo[G_SFX * a.NFG + g], a.geo[G_SFY * a.NFG + g], a.geo[G_SFZ * a.NFG + g]};
         const double magSf = a.geo[G_MAGSF * a.NFG + g];
         const Flux5 F = faceFlux<SCHEME>(s, Sf, magSf, a.sp);
-        if (type == ET_LOWER) {
-            acc[0] -= F.phi; acc[1] -= F.phiUp.x; acc[2] -= F.phiUp.y; acc[3] -= F.phiUp.z; acc[4] -= F.phiEp;
-        } else {
-            acc[0] += F.phi; acc[1] += F.phiUp.x; acc[2] += F.phiUp.y; acc[3] += F.phiUp.z; acc[4] += F.phiEp;
-            if (a.faceFlux) {
-                a.faceFlux[g] = F.phi; a.faceFlux[a.NFG + g] = F.phiUp.x; a.faceFlux[2 * a.NFG + g] = F.phiUp.y;
-                a.faceFlux[3 * a.NFG + g] = F.phiUp.z; a.faceFlux[4 * a.NFG + g] = F.phiEp;
-            }
-            if (type == ET_PHYS) a.phiB[b] = F.phi;
-        }
+        a.faceFlux[g] = F.phi; a.faceFlux[a.NFG + g] = F.phiUp.x; a.faceFlux[2 * a.NFG + g] = F.phiUp.y;
+        a.faceFlux[3 * a.NFG + g] = F.phiUp.z; a.faceFlux[4 * a.NFG + g] = F.phiEp;
+        if (type == ET_PHYS) a.phiB[b] = F.phi;
+    }
+}
+
+// Pass 2: fvc::surfaceIntegrate per row in ascending face id (+ for owned / boundary faces, - where the row is the
+// neighbour), then the viscous, dual-time and source terms of residualsUpdate.H.
+__global__ void __launch_bounds__(256)
+k_flux_gather(FluxArgs a)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.NP || a.pos2cell[p] < 0) return;
+    const int lane = p & 31;
+    const size_t base = (size_t)a.sliceOff[p >> 5];
+    double acc[5] = {0, 0, 0, 0, 0};
+    const int nAll = a.rowNAll[p], nLow = a.rowNLow[p];
+    for (int j = 0; j < nAll; j++) {
+        const size_t g = a.gfid[(base + j) * 32 + lane];
+        const double f0 = a.faceFlux[g], f1 = a.faceFlux[a.NFG + g], f2 = a.faceFlux[2 * a.NFG + g], f3 = a.faceFlux[3 * a.NFG + g],
+                     f4 = a.faceFlux[4 * a.NFG + g];
+        if (j < nLow) { acc[0] -= f0; acc[1] -= f1; acc[2] -= f2; acc[3] -= f3; acc[4] -= f4; }
+        else { acc[0] += f0; acc[1] += f1; acc[2] += f2; acc[3] += f3; acc[4] += f4; }
     }
     // residualsUpdate.H: R = -div(phi*) [- (ddt.diag*W - ddt.source)/V]; source = R*V
     const double vol = a.V[p];
@@ -616,13 +633,14 @@ int ics_gradients(icsb200_ctx* c)
 
 int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
 {
-    if (storeFaceFlux && !c->d_faceFlux) {
+    (void)storeFaceFlux;  // the face fluxes are always stored now: each face is evaluated once
+    if (!c->d_faceFlux) {
         int r = devAlloc(c, &c->d_faceFlux, (size_t)5 * c->NFG);
         if (r) return r;
     }
     FluxArgs a{};
     a.NP = c->NP; a.NB = c->NB; a.F = c->F;
-    a.pos2cell = c->d_pos2cell; a.sliceOff = c->d_sliceOff; a.rowNAll = c->d_rowNAll; a.col = c->d_col; a.meta = c->d_meta; a.gfid = c->d_gfid;
+    a.pos2cell = c->d_pos2cell; a.sliceOff = c->d_sliceOff; a.rowNAll = c->d_rowNAll; a.rowNLow = c->d_rowNLow; a.col = c->d_col; a.meta = c->d_meta; a.gfid = c->d_gfid;
     a.geo = c->d_geo; a.dCoupled = c->d_dCoupled; a.C = c->d_C; a.V = c->d_V; a.f = c->d_fields; a.grad = c->d_grad;
     a.NFG = c->NFG; a.NX = c->NX; a.NPH = c->NPH;
     a.limRho = c->sch.limiter_rho; a.limU = c->sch.limiter_U; a.limT = c->sch.limiter_T;
@@ -630,7 +648,7 @@ int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
     a.ddt = makeDdt(c);
     a.rdt = c->d_rdt; a.Wold = c->d_Wold; a.Wold2 = c->d_Wold2;
     a.src = c->d_src;
-    a.faceFlux = storeFaceFlux ? c->d_faceFlux : nullptr;
+    a.faceFlux = c->d_faceFlux;
     a.phiB = c->d_phiB;
     a.visc = nullptr;
     if (c->mu > 0) {  // if (!inviscid)  (createFields.H:37-45)
@@ -651,9 +669,11 @@ int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
     {
         LaunchScope ls(c, TM_FLUX);
         const int grid = gridFor(c->NP, 128);
-        if (c->sch.flux_scheme == ICSB200_FLUX_HLLC) k_flux<ICSB200_FLUX_HLLC><<<grid, 128, 0, c->stream>>>(a);
-        else if (c->sch.flux_scheme == ICSB200_FLUX_ROE) k_flux<ICSB200_FLUX_ROE><<<grid, 128, 0, c->stream>>>(a);
-        else k_flux<ICSB200_FLUX_AUSMPLUSUP><<<grid, 128, 0, c->stream>>>(a);
+        if (c->sch.flux_scheme == ICSB200_FLUX_HLLC) k_flux_faces<ICSB200_FLUX_HLLC><<<grid, 128, 0, c->stream>>>(a);
+        else if (c->sch.flux_scheme == ICSB200_FLUX_ROE) k_flux_faces<ICSB200_FLUX_ROE><<<grid, 128, 0, c->stream>>>(a);
+        else k_flux_faces<ICSB200_FLUX_AUSMPLUSUP><<<grid, 128, 0, c->stream>>>(a);
+        k_flux_gather<<<gridFor(c->NP, 256), 256, 0, c->stream>>>(a);
+        c->launches++;
     }
     CUDA_TRY(c, cudaGetLastError());
     c->fluxValid = true;
