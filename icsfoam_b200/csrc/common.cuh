@@ -97,9 +97,13 @@ struct icsb200_ctx {
     int nLevF = 0, nLevR = 0, maxWidth = 0;
     // blocked-wavefront schedule (tile mode)
     bool tileMode = false;
+    bool tileTma = false;  // tiles of <= 64 rows swept by k_lusgs_tile_tma (thread = row, TMA-staged blocks, double-buffered)
     int nTiles = 0, nTileLevels = 0;
     int tileMaxRows = 0, lusgsTileGrid = 0;
     int* d_sliceTile = nullptr;  // [nSlices] tile of a slice
+    int *d_rowLevF = nullptr, *d_rowLevR = nullptr;      // [NP] intra-tile level of a row in the forward / reverse sweep (-1 padding)
+    int *d_tileNLevF = nullptr, *d_tileNLevR = nullptr;  // [nTiles] number of intra-tile levels
+    int *d_tileDescF = nullptr, *d_tileDescR = nullptr;  // [nTiles][16] bulk-copy descriptors of a tile's sweep (solver.cu TT_DESC_*)
     int *d_tileStart = nullptr, *d_tileFPtr = nullptr, *d_tileFLev = nullptr, *d_tileRPtr = nullptr, *d_tileRLev = nullptr, *d_tileRRows = nullptr;
     // boundary faces
     int* d_bfOwnerPos = nullptr;  // [NB] position of faceCell (-1 for empty)

@@ -135,7 +135,7 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
                     c->d_bfGeo, c->d_bc, c->d_phiB, c->d_vic, c->d_sendBuf, c->d_recvBuf, c->d_fields, c->d_grad, c->d_rdt, c->d_co,
                     c->d_ddtCoeff, c->d_Wold, c->d_Wold2, c->d_Wprev, c->d_src, c->d_dW, c->d_faceFlux, c->d_bad, c->d_offd, c->d_diag,
                     c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage, c->d_lusgsYZ, c->d_lusgsHint, c->d_sliceRange,
-                    c->d_gradE, c->d_visc, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
+                    c->d_gradE, c->d_visc, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
     if (c->h_scal) cudaFreeHost(c->h_scal);
@@ -195,7 +195,7 @@ extern "C" int icsb200_timer_end(icsb200_ctx* c, double* elapsed_ms)
 extern "C" int icsb200_schedule_info(icsb200_ctx* c, int out[8])
 {
     out[0] = c->nLevF; out[1] = c->nLevR; out[2] = c->maxWidth; out[3] = c->NP;
-    out[4] = c->tileMode ? 1 : 0; out[5] = c->nTiles; out[6] = c->nTileLevels;
+    out[4] = c->tileMode ? 1 : 0; out[5] = c->nTiles; out[6] = c->nTileLevels; out[7] = c->tileTma ? 1 : 0;
     return 0;
 }
 
@@ -286,7 +286,12 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     {
         const char* env = getenv("ICSB200_LUSGS_MODE");
         // tile mode is correct (bit-identical) but not yet faster than the level pipeline: opt-in
-        const bool wantTiles = env && std::string(env) == "tile" && N >= 64;
+        // "tile64": 64-row tiles for the TMA tile kernel (chain-bound sizes); "tile": the older ~512-row tiles
+        const bool want64 = env && std::string(env) == "tile64";
+        const bool wantTiles = env && (std::string(env) == "tile" || want64) && N >= 64;
+        const double tileTarget = want64 ? 64.0 : 512.0;
+        const int tileRowCap = want64 ? 64 : ICS_TILE_MAXROWS - 32;
+        c->tileTma = false;
         if (wantTiles) {
             // logical coordinates from the graph alone: u_d = longest path using only faces whose normal is mostly along
             // axis d (exactly (i,j,k) on a block-structured mesh, however curved); tiles = boxes of u
@@ -301,7 +306,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             }
             int active = 0;
             for (int d = 0; d < 3; d++) if (umax[d] + 1 >= 4) active++;
-            const int side = active > 0 ? std::max(2, (int)std::lround(std::pow(512.0, 1.0 / active))) : 512;
+            const int side = active > 0 ? std::max(2, (int)std::lround(std::pow(tileTarget, 1.0 / active))) : (int)tileTarget;
             int nb[3];
             std::vector<int> bin[3];
             for (int d = 0; d < 3; d++) {
@@ -326,13 +331,14 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                 std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tl(x) < tl(y); });
                 int maxRows = 0, maxTL = 0;
                 for (int t : order) { maxRows = std::max(maxRows, cntT[t]); maxTL = std::max(maxTL, tl(t)); }
-                if (maxRows <= ICS_TILE_MAXROWS - 32) {
+                if (maxRows <= tileRowCap) {
                     std::vector<int> dense(nbAll, -1);
                     for (size_t k = 0; k < order.size(); k++) dense[order[k]] = (int)k;
                     tileOf.resize(N);
                     for (int i = 0; i < N; i++) tileOf[i] = dense[key[i]];
                     nTiles = (int)order.size();
                     c->tileMode = true;
+                    c->tileTma = want64;
                     c->nTileLevels = maxTL + 1;
                 }
             }
@@ -399,6 +405,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     std::vector<int> patchHaloStart(n_patches, -1);
     for (int pi = 0; pi < n_patches; pi++)
         if (patches[pi].kind == ICSB200_PROCESSOR) { patchHaloStart[pi] = NH; NH += patches[pi].size; }
+    NH += NH & 1;  // keep NPH even: every component array of a cell vector then starts 16-byte aligned (TMA bulk copies)
     c->NH = NH; c->NPH = NP + NH; c->NX = NP + NH + NB;
 
     // ---- rows: faces of each cell in ascending face id
@@ -593,6 +600,12 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     r |= devUpload(c, &c->d_dCoupled, dCoupled);
     r |= devUpload(c, &c->d_V, Vp);
     r |= devUpload(c, &c->d_C, Cp3);
+    if (c->tileMode && c->tileTma) {
+        for (int p2 = 0; p2 < NP && c->tileTma; p2++) {
+            if (c->pos2cell[p2] < 0) continue;
+            if (c->h_rowNLow[p2] > 3 || c->h_rowNInt[p2] - c->h_rowNLow[p2] > 3 || c->h_rowNInt[p2] > 8) c->tileTma = false;
+        }
+    }
     if (c->tileMode) {
         r |= devUpload(c, &c->d_tileStart, tileStart);
         r |= devUpload(c, &c->d_tileFPtr, tileFPtr);
@@ -607,6 +620,49 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             c->tileMaxRows = std::max(c->tileMaxRows, tileStart[t + 1] - tileStart[t]);
         }
         r |= devUpload(c, &c->d_sliceTile, sliceTile);
+        if (c->tileTma) {
+            // per-row intra-tile levels of both sweeps, so the tile kernel can stage them with one bulk copy
+            std::vector<int> rowLevF(NP, -1), rowLevR(NP, -1), nLevF2(c->nTiles, 0), nLevR2(c->nTiles, 0);
+            for (int t = 0; t < c->nTiles; t++) {
+                const int t0 = tileStart[t];
+                const int nf = tileFPtr[t + 1] - tileFPtr[t] - 1, nr = tileRPtr[t + 1] - tileRPtr[t] - 1;
+                nLevF2[t] = nf; nLevR2[t] = nr;
+                for (int L = 0; L < nf; L++)
+                    for (int rr2 = tileFLev[tileFPtr[t] + L]; rr2 < tileFLev[tileFPtr[t] + L + 1]; rr2++) rowLevF[t0 + rr2] = L;
+                for (int L = 0; L < nr; L++)
+                    for (int i2 = tileRLev[tileRPtr[t] + L]; i2 < tileRLev[tileRPtr[t] + L + 1]; i2++) rowLevR[t0 + tileRRows[t0 + i2]] = L;
+            }
+            r |= devUpload(c, &c->d_rowLevF, rowLevF);
+            r |= devUpload(c, &c->d_rowLevR, rowLevR);
+            r |= devUpload(c, &c->d_tileNLevF, nLevF2);
+            r |= devUpload(c, &c->d_tileNLevR, nLevR2);
+            // per (tile, sweep): t0, nRows, nLev, -, then per slice (2): first entry offset, first staged entry, staged entries,
+            // staged column entries — everything the producer needs to issue a tile's bulk copies with one 64-byte read
+            std::vector<int> descF((size_t)16 * c->nTiles, 0), descR((size_t)16 * c->nTiles, 0);
+            for (int t = 0; t < c->nTiles; t++)
+                for (int sw = 0; sw < 2; sw++) {
+                    int* d = (sw == 0 ? descF.data() : descR.data()) + (size_t)16 * t;
+                    const int t0 = tileStart[t], nRows = tileStart[t + 1] - t0;
+                    d[0] = t0; d[1] = nRows; d[2] = sw == 0 ? nLevF2[t] : nLevR2[t];
+                    for (int sl = 0; sl < nRows / 32 && sl < 2; sl++) {
+                        const int s2 = t0 / 32 + sl;
+                        int fHi = 0, rLo = 1 << 20, rHi = 0;
+                        for (int l = 0; l < 32; l++) {
+                            const int p2 = s2 * 32 + l;
+                            fHi = std::max(fHi, c->h_rowNLow[p2]);
+                            if (c->h_rowNInt[p2] > c->h_rowNLow[p2]) { rLo = std::min(rLo, c->h_rowNLow[p2]); rHi = std::max(rHi, c->h_rowNInt[p2]); }
+                        }
+                        if (rHi == 0) rLo = 0;
+                        const int lo = sw == 0 ? 0 : rLo, hi = sw == 0 ? fHi : rHi;
+                        d[4 + sl] = c->h_sliceOff[s2];
+                        d[6 + sl] = lo;
+                        d[8 + sl] = std::max(0, std::min(hi - lo, 3));
+                        d[10 + sl] = std::min(c->h_sliceOff[s2 + 1] - c->h_sliceOff[s2], 8);
+                    }
+                }
+            r |= devUpload(c, &c->d_tileDescF, descF);
+            r |= devUpload(c, &c->d_tileDescR, descR);
+        }
     }
     r |= devUpload(c, &c->d_bfOwnerPos, bfOwnerPos);
     r |= devUpload(c, &c->d_bfPatch, c->bfacePatch);

@@ -396,6 +396,12 @@ __device__ __forceinline__ bool mbarTryWait(unsigned long long* bar, unsigned pa
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smemAddr(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbarTestWait(unsigned long long* bar, unsigned parity)  // non-blocking
+{
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smemAddr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ bool mbarWait(unsigned long long* bar, unsigned parity, int* err)
 {
     unsigned int spins = 0;
@@ -865,6 +871,245 @@ k_lusgs_tile(TileArgs a)
     for (int tt = blockIdx.x; tt < a.nTiles; tt += gridDim.x) sweepTile<false>(a, a.nTiles - 1 - tt, xs, MR);  // reverse, descending
 }
 
+
+// ---------------- tile mode with TMA staging (k_lusgs_tile_tma): the chain-bound regime ----------------
+// 64-row tiles (4x4x4 cells of a structured-like mesh), thread = row.  Each CTA runs TT_LANES independent "lanes" of 64
+// consumer threads; a lane sweeps one tile at a time out of its own shared-memory stage.  One producer warp streams
+// EVERYTHING a tile's sweep needs that does not depend on other tiles — the 5x5 blocks, column indices, row lengths, rD,
+// the rows' intra-tile levels and their right-hand side / forward values — with cp.async.bulk into the stage of whichever
+// lane has just released it, so the load of one lane overlaps the sweeps of the others.  A lane walks its tile's ~10
+// intra-tile levels with a named barrier per level, reading only shared memory; out-of-tile neighbour values (always from
+// tiles of a lower tile level) are polled once per tile with the hint + sentinel protocol of the level kernels.  The
+// cross-SM dependency chain shrinks from the number of levels (3n) to the number of tile levels (3n/4), and an intra-tile
+// level costs a barrier + ~100 shared-memory reads instead of an L2 round trip.  Meant for small meshes / partitions,
+// where the level pipeline is bound by hop latency; bit-identical to it.
+constexpr int TT_ROWS = 64;          // rows per tile = consumer threads per lane
+constexpr int TT_SL = TT_ROWS / 32;  // slices per tile
+constexpr int TT_SE = 3;             // staged block entries per slice (interior rows: exactly 3 per sweep; else global fallback)
+constexpr int TT_CW = 8;             // staged column entries per slice
+constexpr int TT_LANES = 4;          // concurrent tiles per CTA
+
+struct TTStage {
+    double blocks[TT_SL][TT_SE][25][32];  // 38400 B
+    int cols[TT_SL][TT_CW][32];           //  2048 B
+    int nLow[TT_ROWS], nInt[TT_ROWS], lev[TT_ROWS];
+    double rD[TT_ROWS];
+    double own[5][TT_ROWS];               // forward: right-hand side; reverse: the rows' forward values (validated)
+    int desc[16];                         // the tile's descriptor (TT_DESC_*): consumers need no global metadata
+    double xs[5][TT_ROWS];                // sweep values of the tile (not staged)
+};
+// descriptor layout (setup.cu): [0] t0 [1] nRows [2] nLev; per slice sl: [4+sl] first entry offset (sliceOff), [6+sl] first
+// staged entry, [8+sl] staged entries, [10+sl] staged column entries
+struct TTShared {
+    TTStage st[TT_LANES];
+    unsigned long long full[TT_LANES], empty[TT_LANES];
+};
+
+struct TileTmaArgs {
+    int nTiles;
+    const int *sliceTile, *rowLevF, *rowLevR, *tileDescF, *tileDescR;
+    const int *rowNLow, *rowNInt, *col;
+    const double *offd, *rD;
+    double *x, *y, *z;
+    size_t NPH;
+    int *hintF, *hintR;
+    int epoch;
+    int* err;
+};
+
+__device__ __forceinline__ void laneBarrier(int ln) { asm volatile("bar.sync %0, %1;" ::"r"(ln + 1), "n"(TT_ROWS) : "memory"); }
+
+__global__ void __launch_bounds__(TT_LANES * (TT_ROWS + 32), 1)
+k_lusgs_tile_tma(TileTmaArgs a)
+{
+    extern __shared__ __align__(128) unsigned char ttRaw[];
+    TTShared& sm = *reinterpret_cast<TTShared*>(ttRaw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int G = gridDim.x, b = blockIdx.x, GL = G * TT_LANES;
+    if (tid == 0) {
+        for (int s2 = 0; s2 < TT_LANES; s2++) { mbarInit(sm.full + s2, 1); mbarInit(sm.empty + s2, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // lane ln of CTA b sweeps the tiles T = b + ln*G + i*GL (forward, ascending) and then nTiles-1-T (reverse): consecutive
+    // tiles — same tile level — go to different SMs first
+    auto nMineOf = [&](int ln) { const int first = b + ln * G; return (a.nTiles > first) ? (a.nTiles - first + GL - 1) / GL : 0; };
+    auto itemTile = [&](int ln, int nMine, int i, bool& fwd) {
+        fwd = i < nMine;
+        const int T = b + ln * G + (fwd ? i : i - nMine) * GL;
+        return fwd ? T : a.nTiles - 1 - T;
+    };
+
+    if (tid >= TT_LANES * TT_ROWS) {
+        // ---------------- producer warps: warp w serves lane w; the next tile's descriptor is fetched while the current
+        // one is being swept, so a released stage is refilled without a global round trip ----------------
+        const int ln = (tid - TT_LANES * TT_ROWS) >> 5;
+        if (lane == 0) {
+            const int nMine = nMineOf(ln), nItems = 2 * nMine;
+            TTStage& S = sm.st[ln];
+            int4 d0, d1, d2;
+            auto loadDesc = [&](int i) {
+                bool fwd;
+                const int tile = itemTile(ln, nMine, i, fwd);
+                const int4* dp = reinterpret_cast<const int4*>((fwd ? a.tileDescF : a.tileDescR) + (size_t)16 * tile);
+                d0 = dp[0]; d1 = dp[1]; d2 = dp[2];
+            };
+            if (nItems > 0) loadDesc(0);
+            for (int i = 0; i < nItems; i++) {
+                if (i > 0 && !mbarWait(sm.empty + ln, (i + 1) & 1, a.err)) break;  // stage still in use by item i-1
+                bool fwd;
+                const int tile = itemTile(ln, nMine, i, fwd);
+                const int t0 = d0.x, nRows = d0.y, nSl = nRows >> 5;
+                const int e0[2] = {d1.x, d1.y}, lo[2] = {d1.z, d1.w}, ne[2] = {d2.x, d2.y}, nc[2] = {d2.z, d2.w};
+                unsigned bytes = (unsigned)nRows * (4 + 4 + 4 + 8 + 5 * 8) + 64;
+                for (int sl = 0; sl < nSl; sl++) bytes += (unsigned)ne[sl] * 25 * 32 * 8 + (unsigned)nc[sl] * 32 * 4;
+                mbarExpectTx(sm.full + ln, bytes);
+                tmaLoad1D(S.desc, (fwd ? a.tileDescF : a.tileDescR) + (size_t)16 * tile, 64, sm.full + ln);
+                for (int sl = 0; sl < nSl; sl++) {
+                    if (ne[sl] > 0) tmaLoad1D(&S.blocks[sl][0][0][0], a.offd + ((size_t)e0[sl] + lo[sl]) * 25 * 32, (unsigned)ne[sl] * 25 * 32 * 8, sm.full + ln);
+                    if (nc[sl] > 0) tmaLoad1D(&S.cols[sl][0][0], a.col + (size_t)e0[sl] * 32, (unsigned)nc[sl] * 32 * 4, sm.full + ln);
+                }
+                tmaLoad1D(S.nLow, a.rowNLow + t0, (unsigned)nRows * 4, sm.full + ln);
+                tmaLoad1D(S.nInt, a.rowNInt + t0, (unsigned)nRows * 4, sm.full + ln);
+                tmaLoad1D(S.lev, (fwd ? a.rowLevF : a.rowLevR) + t0, (unsigned)nRows * 4, sm.full + ln);
+                tmaLoad1D(S.rD, a.rD + t0, (unsigned)nRows * 8, sm.full + ln);
+                const double* src = fwd ? a.x : a.y;
+                for (int k = 0; k < 5; k++) tmaLoad1D(&S.own[k][0], src + k * a.NPH + t0, (unsigned)nRows * 8, sm.full + ln);
+                if (i + 1 < nItems) loadDesc(i + 1);
+            }
+        }
+        return;
+    }
+    // ---------------- consumers: lane ln, thread r owns row t0 + r of the lane's current tile ----------------
+    const int ln = tid / TT_ROWS, r = tid % TT_ROWS;
+    const int nMine = nMineOf(ln), nItems = 2 * nMine;
+    TTStage& S = sm.st[ln];
+    for (int i = 0; i < nItems; i++) {
+        bool fwd;
+        const int tile = itemTile(ln, nMine, i, fwd);
+        const double* buf = fwd ? a.y : a.z;
+        const int* hint = fwd ? a.hintF : a.hintR;
+        const int sl = r >> 5;
+        mbarWait(sm.full + ln, i & 1, a.err);
+        const int t0 = S.desc[0], t1 = t0 + S.desc[1], nLev = S.desc[2];
+        const int p = t0 + r;
+        const int sle = min(sl, (S.desc[1] >> 5) - 1);
+        const int stageLo = S.desc[6 + sle];
+        const size_t sliceE0 = (size_t)S.desc[4 + sle];
+        const bool inRange = r < t1 - t0;
+        const int myLev = inRange ? S.lev[r] : -1;  // -1: padding row, never swept
+        const bool active = myLev >= 0;
+        const int nLow = active ? S.nLow[r] : 0, nInt = active ? S.nInt[r] : 0;
+        const int jBeg = fwd ? 0 : nLow, jEnd = fwd ? nLow : nInt;
+        const int n = min(jEnd - jBeg, LCH);
+        const double rd = (active && !fwd) ? S.rD[r] : 1.0;
+        double xr[5] = {0, 0, 0, 0, 0};
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) xr[k] = S.own[k][r];
+        }
+        int q[LCH], jj[LCH];
+        bool inTile[LCH];
+        double dlo[LCH][5];
+#pragma unroll
+        for (int t = 0; t < LCH; t++) {
+            q[t] = -1; jj[t] = 0; inTile[t] = true;
+            if (t < n) {
+                jj[t] = fwd ? (jBeg + t) : (jEnd - 1 - t);
+                q[t] = S.cols[sl][jj[t]][lane];
+                inTile[t] = q[t] >= t0 && q[t] < t1;
+            }
+        }
+        // out-of-tile neighbours: always in tiles of a lower tile level (forward) / higher (reverse).  All hints of the thread
+        // are polled together, then all values together (two L2 round trips per tile when the predecessors are done)
+        double sco[LCH];
+        unsigned int pend = 0;
+#pragma unroll
+        for (int t = 0; t < LCH; t++) {
+            const bool out = t < n && !inTile[t];
+            sco[t] = (out && fwd) ? a.rD[q[t]] : 1.0;
+            if (out) pend |= 1u << t;
+        }
+        {
+            unsigned int spins = 0;
+            while (pend) {
+                int hv[LCH];
+#pragma unroll
+                for (int t = 0; t < LCH; t++) hv[t] = (pend >> t & 1u) ? ldHint(hint + a.sliceTile[q[t] >> 5]) : 0;
+                unsigned int ready = 0;
+#pragma unroll
+                for (int t = 0; t < LCH; t++)
+                    if ((pend >> t & 1u) && hv[t] == a.epoch) {
+                        ready |= 1u << t;
+#pragma unroll
+                        for (int k = 0; k < 5; k++) dlo[t][k] = ldPoll(buf + k * a.NPH + q[t]);
+                    }
+#pragma unroll
+                for (int t = 0; t < LCH; t++)
+                    if (ready >> t & 1u) {
+                        bool ok = true;
+#pragma unroll
+                        for (int k = 0; k < 5; k++) ok &= !isSentinel(dlo[t][k]);
+                        if (ok) pend &= ~(1u << t);
+                    }
+                if (pend) {
+                    if (++spins > (1u << 24)) { *a.err = 1; break; }
+                    if (spins > 64) __nanosleep(100);
+                }
+            }
+        }
+        if (fwd) {
+#pragma unroll
+            for (int t = 0; t < LCH; t++)
+                if (t < n && !inTile[t]) {
+#pragma unroll
+                    for (int k = 0; k < 5; k++) dlo[t][k] = sco[t] * dlo[t][k];  // dW*_q = rD_q x_q (lusgs.C:194-216)
+                }
+        }
+        if (active && !fwd) {  // own forward value: normally published long before the bulk copy read it
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 5; k++) ok &= !isSentinel(xr[k]);
+            if (!ok) pollTile(a.y, a.hintF, a.sliceTile, a.epoch, a.NPH, p, xr, a.err);
+        }
+        // the tile's levels, one lane barrier each
+        for (int L = 0; L < nLev; L++) {
+            if (myLev == L) {
+#pragma unroll
+                for (int t = 0; t < LCH; t++)
+                    if (t < n) {
+                        double dl[5];
+                        if (inTile[t]) {
+                            const int qr = q[t] - t0;
+                            const double sc = fwd ? S.rD[qr] : 1.0;
+#pragma unroll
+                            for (int k = 0; k < 5; k++) dl[k] = fwd ? sc * S.xs[k][qr] : S.xs[k][qr];
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 5; k++) dl[k] = dlo[t][k];
+                        }
+                        const int js = jj[t] - stageLo;
+                        if (js >= 0 && js < TT_SE) lusgsSubSmem(xr, &S.blocks[sl][js][0][lane], dl);
+                        else subBlockGlobal(xr, a.offd + ((sliceE0 + jj[t]) * 25) * 32 + lane, dl);
+                    }
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const double v = fwd ? xr[k] : rd * xr[k];
+                    S.xs[k][r] = v;
+                    __stcg((fwd ? a.y : a.z) + k * a.NPH + p, v);
+                    if (!fwd) a.x[k * a.NPH + p] = v;
+                }
+            }
+            laneBarrier(ln);
+        }
+        if (nLev == 0) laneBarrier(ln);
+        if (r == 0) {
+            __stcg((fwd ? a.hintF : a.hintR) + tile, a.epoch);
+            mbarArrive(sm.empty + ln);  // every consumer of the lane is past its last read of the stage
+        }
+    }
+}
+
 __global__ void k_fill_sentinel(size_t n, unsigned long long* __restrict__ a, unsigned long long* __restrict__ b)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1212,6 +1457,30 @@ int ics_lusgs(icsb200_ctx* c, double* x)
         if ((r = devAlloc(c, &c->d_lusgsHint, (size_t)2 * c->nSlices))) return r;
         CUDA_TRY(c, cudaMemsetAsync(c->d_lusgsHint, 0, sizeof(int) * 2 * c->nSlices, c->stream));
         c->lusgsEpoch = 0;
+    }
+    if (c->tileMode && c->tileTma) {
+        TileTmaArgs t{};
+        t.nTiles = c->nTiles;
+        t.sliceTile = c->d_sliceTile;
+        t.rowLevF = c->d_rowLevF; t.rowLevR = c->d_rowLevR; t.tileDescF = c->d_tileDescF; t.tileDescR = c->d_tileDescR;
+        t.rowNLow = c->d_rowNLow; t.rowNInt = c->d_rowNInt; t.col = c->d_col;
+        t.offd = c->d_offd; t.rD = c->d_rD; t.x = x; t.NPH = c->NPH;
+        t.y = c->d_lusgsYZ; t.z = c->d_lusgsYZ + V5;
+        t.hintF = c->d_lusgsHint; t.hintR = c->d_lusgsHint + c->nSlices; t.epoch = ++c->lusgsEpoch;
+        t.err = (int*)c->d_counter + 48;
+        const size_t smem = sizeof(TTShared) + 128;
+        static bool attrSet = false;
+        if (!attrSet) {
+            CUDA_TRY(c, cudaFuncSetAttribute(k_lusgs_tile_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attrSet = true;
+        }
+        const int grid = std::min(c->numSMs, std::max(1, (c->nTiles + TT_LANES - 1) / TT_LANES));
+        LaunchScope ls(c, TM_LUSGS);
+        k_fill_sentinel<<<gridFor(V5, 256), 256, 0, c->stream>>>(V5, (unsigned long long*)t.y, (unsigned long long*)t.z);
+        c->launches++;
+        void* targs[] = {&t};
+        CUDA_TRY(c, cudaLaunchCooperativeKernel((void*)k_lusgs_tile_tma, dim3(grid), dim3(TT_LANES * (TT_ROWS + 32)), targs, smem, c->stream));
+        return 0;
     }
     if (c->tileMode) {
         TileArgs t{};

@@ -207,12 +207,17 @@ def test_iterate_host_round_trip(gpu_context):
     assert rel_err(p, sa["p"]) < 1e-9 and rel_err(U, sa["U"]) < 1e-9 and rel_err(T, sa["T"]) < 1e-9
 
 
-def test_lusgs_tile_mode_is_bit_identical(gpu_context, monkeypatch):
-    """ICSB200_LUSGS_MODE=tile (blocked wavefront schedule) must reproduce the level pipeline and the oracle bit for bit."""
-    monkeypatch.setenv("ICSB200_LUSGS_MODE", "tile")
-    case = cases.onera_box(20)
+@pytest.mark.parametrize("mode,make", [("tile", lambda: cases.onera_box(20)), ("tile64", lambda: cases.onera_box(20)),
+                                       ("tile64", lambda: cases.onera_box(13)), ("tile64", lambda: cases.bump(24, 20)),
+                                       ("tile64", lambda: cases.periodic_box(9, "ROE", "vanLeer", seed=61, mu=0.05))])
+def test_lusgs_tile_mode_is_bit_identical(gpu_context, monkeypatch, mode, make):
+    """ICSB200_LUSGS_MODE=tile / tile64 (blocked wavefront schedules; tile64 = 64-row tiles swept by the TMA tile kernel) must
+    reproduce the level pipeline and the oracle bit for bit."""
+    monkeypatch.setenv("ICSB200_LUSGS_MODE", mode)
+    case = make()
     g = case.apply(gpu_context())
     assert g.schedule_info()["tile_mode"] and g.schedule_info()["n_tiles"] >= 8
+    assert g.schedule_info()["tile_tma"] == (mode == "tile64")
     monkeypatch.delenv("ICSB200_LUSGS_MODE")
     o = case.apply(Oracle())
     for api in (g, o):
