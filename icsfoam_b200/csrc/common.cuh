@@ -132,7 +132,9 @@ struct icsb200_ctx {
     double *d_rdt = nullptr, *d_co = nullptr, *d_ddtCoeff = nullptr;  // [NP]
     double *d_Wold = nullptr, *d_Wold2 = nullptr, *d_Wprev = nullptr; // [5*NP] each
     double *d_src = nullptr, *d_dW = nullptr;                         // [5*NPH]
-    double* d_faceFlux = nullptr;                                     // [5*NFG] GPU face order (only when requested)
+    double* d_faceFlux = nullptr;                                     // [5*NFG] face fluxes, GPU face order
+    double* d_faceRecon = nullptr;                                    // [8*NFG] limited L/R states U_l U_r E_l E_r of every face (for k_jac)
+    bool reconValid = false;                                          // d_faceRecon belongs to the current state and schemes
     double* d_gradE = nullptr;                                        // [3*NPH] gradient of eCalc (viscous runs only)
     double* d_visc = nullptr;                                         // [8*NP] per-row viscous divergences: lapU(3) divTau(3) divSigmaU lapE
     int* d_bad = nullptr;                                              // [NPH] boundLocalTimeStep flags

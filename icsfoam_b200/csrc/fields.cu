@@ -330,6 +330,7 @@ int ics_eval_bc(icsb200_ctx* c, bool /*init*/)
 
 int ics_primitives(icsb200_ctx* c)
 {
+    c->reconValid = false;  // the state changed: stored face reconstructions are stale
     {
         LaunchScope ls(c, TM_PRIM);
         int n = c->NP + c->NB;

@@ -309,7 +309,8 @@ struct FluxArgs {
     DdtPrm ddt;
     const double *rdt, *Wold, *Wold2;  // [NP], [5*NP]
     double* src;                       // [5*NPH]
-    double* faceFlux;                  // [5*NFG] or null
+    double* faceFlux;                  // [5*NFG]
+    double* recon;                     // [8*NFG] limited U_l U_r E_l E_r per face, reused by the Jacobian kernel
     double* phiB;                      // [NB]
     const double* visc;                // [8*NP] viscous divergences (already divided by V) or null
 };
@@ -372,6 +373,12 @@ k_flux_faces(FluxArgs a)
         a.faceFlux[g] = F.phi; a.faceFlux[a.NFG + g] = F.phiUp.x; a.faceFlux[2 * a.NFG + g] = F.phiUp.y;
         a.faceFlux[3 * a.NFG + g] = F.phiUp.z; a.faceFlux[4 * a.NFG + g] = F.phiEp;
         if (type == ET_PHYS) a.phiB[b] = F.phi;
+        else {
+            // the same limited states feed createConvectiveJacobian (convectiveFluxScheme.C:387-400)
+            a.recon[g] = s.U_l.x; a.recon[a.NFG + g] = s.U_l.y; a.recon[2 * a.NFG + g] = s.U_l.z;
+            a.recon[3 * a.NFG + g] = s.U_r.x; a.recon[4 * a.NFG + g] = s.U_r.y; a.recon[5 * a.NFG + g] = s.U_r.z;
+            a.recon[6 * a.NFG + g] = s.E_l; a.recon[7 * a.NFG + g] = s.E_r;
+        }
     }
 }
 
@@ -638,6 +645,10 @@ int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
         int r = devAlloc(c, &c->d_faceFlux, (size_t)5 * c->NFG);
         if (r) return r;
     }
+    if (!c->d_faceRecon) {
+        int r = devAlloc(c, &c->d_faceRecon, (size_t)8 * c->NFG);
+        if (r) return r;
+    }
     FluxArgs a{};
     a.NP = c->NP; a.NB = c->NB; a.F = c->F;
     a.pos2cell = c->d_pos2cell; a.sliceOff = c->d_sliceOff; a.rowNAll = c->d_rowNAll; a.rowNLow = c->d_rowNLow; a.col = c->d_col; a.meta = c->d_meta; a.gfid = c->d_gfid;
@@ -649,6 +660,7 @@ int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
     a.rdt = c->d_rdt; a.Wold = c->d_Wold; a.Wold2 = c->d_Wold2;
     a.src = c->d_src;
     a.faceFlux = c->d_faceFlux;
+    a.recon = c->d_faceRecon;
     a.phiB = c->d_phiB;
     a.visc = nullptr;
     if (c->mu > 0) {  // if (!inviscid)  (createFields.H:37-45)
@@ -677,6 +689,7 @@ int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
     }
     CUDA_TRY(c, cudaGetLastError());
     c->fluxValid = true;
+    c->reconValid = true;
     return ics_hb_source(c);  // Harmonic Balance: sources += -V sum_K D[J][K] W_K
 }
 

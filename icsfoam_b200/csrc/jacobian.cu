@@ -52,6 +52,7 @@ struct JacArgs {
     double mu, alphaEff;  // viscous LF Jacobian (mu > 0)
     const double* src;    // unused here (sources live in d_src)
     double *offd, *diag, *rD, *rdt, *ddtCoeff;
+    const double* recon;  // [8*NFG] limited face states stored by k_flux_faces (REUSE instantiation)
 };
 
 // analytic Euler flux Jacobian d(F.n)/dW at state (U, E) — convectiveFluxScheme.C:402-464
@@ -80,6 +81,7 @@ __device__ __forceinline__ void eulerJacobian(V3 U, double E, V3 n, double gamma
 
 __device__ __forceinline__ bool isDiagEntry(int k) { return k == 0 || k == 6 || k == 12 || k == 18 || k == 24; }
 
+template <bool REUSE>
 __global__ void __launch_bounds__(128, 3)
 k_jac(JacArgs a)
 {
@@ -130,6 +132,12 @@ k_jac(JacArgs a)
         else d = {a.C[N] - a.C[P], a.C[a.NPH + N] - a.C[a.NPH + P], a.C[2 * a.NPH + N] - a.C[2 * a.NPH + P]};
         // limited reconstruction of U (3 comps) and E on both sides (convectiveFluxScheme.C:387-400)
         double L[4], R[4];
+        if (REUSE) {
+            // the limited L/R states of this face were stored by the flux kernel for this very state
+            L[0] = a.recon[g]; L[1] = a.recon[a.NFG + g]; L[2] = a.recon[2 * a.NFG + g];
+            R[0] = a.recon[3 * a.NFG + g]; R[1] = a.recon[4 * a.NFG + g]; R[2] = a.recon[5 * a.NFG + g];
+            L[3] = a.recon[6 * a.NFG + g]; R[3] = a.recon[7 * a.NFG + g];
+        } else
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int k = (q < 3) ? (Q_UX + q) : Q_E;
@@ -439,7 +447,9 @@ int ics_jacobian(icsb200_ctx* c, bool useStoredRdt)
     }
     {
         LaunchScope ls(c, TM_JAC);
-        k_jac<<<gridFor(c->NP, 128), 128, 0, c->stream>>>(a);
+        a.recon = c->d_faceRecon;
+        if (c->reconValid && c->d_faceRecon) k_jac<true><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(a);
+        else k_jac<false><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(a);
     }
     CUDA_TRY(c, cudaGetLastError());
     c->matrixSet = true;

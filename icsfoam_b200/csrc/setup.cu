@@ -135,7 +135,7 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
                     c->d_bfGeo, c->d_bc, c->d_phiB, c->d_vic, c->d_sendBuf, c->d_recvBuf, c->d_fields, c->d_grad, c->d_rdt, c->d_co,
                     c->d_ddtCoeff, c->d_Wold, c->d_Wold2, c->d_Wprev, c->d_src, c->d_dW, c->d_faceFlux, c->d_bad, c->d_offd, c->d_diag,
                     c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage, c->d_lusgsYZ, c->d_lusgsHint, c->d_sliceRange,
-                    c->d_gradE, c->d_visc, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
+                    c->d_faceRecon, c->d_gradE, c->d_visc, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
     if (c->h_scal) cudaFreeHost(c->h_scal);
@@ -202,6 +202,7 @@ extern "C" int icsb200_schedule_info(icsb200_ctx* c, int out[8])
 // ------------------------------------------------------------------------------------------------ selectors
 extern "C" int icsb200_thermo_set(icsb200_ctx* c, double R, double Cp, double mu, double Pr)
 {
+    c->reconValid = false;
     if (!(R > 0) || !(Cp > R)) return ics_fail(c, ICSB200_EINVAL, "thermo: need Cp > R > 0");
     c->R = R; c->Cp = Cp; c->Cv = Cp - R; c->gamma = Cp / c->Cv; c->mu = mu; c->Pr = Pr;
     c->thermoSet = true;
@@ -210,6 +211,7 @@ extern "C" int icsb200_thermo_set(icsb200_ctx* c, double R, double Cp, double mu
 
 extern "C" int icsb200_schemes_set(icsb200_ctx* c, const icsb200_schemes* s)
 {
+    c->reconValid = false;
     // newConvectiveFluxScheme.C:56-66: unknown type is a fatal error listing the valid ones
     if (s->flux_scheme < 0 || s->flux_scheme > ICSB200_FLUX_AUSMPLUSUP)
         return ics_fail(c, ICSB200_EINVAL, "Unknown convectiveFluxScheme type; valid types are: AUSMPlusUp HLLC ROE");
@@ -224,6 +226,7 @@ extern "C" int icsb200_schemes_set(icsb200_ctx* c, const icsb200_schemes* s)
 
 extern "C" int icsb200_bc_set(icsb200_ctx* c, int patch, int field, int kind, const double* params, int n_params)
 {
+    c->reconValid = false;
     if (!c->meshSet) return ics_fail(c, ICSB200_ESTATE, "bc_set: mesh not set");
     if (patch < 0 || patch >= (int)c->patches.size() || field < 0 || field > 2 || n_params < 0 || n_params > 8 || kind < 0 ||
         kind > ICSB200_BC_COUPLED)
@@ -738,6 +741,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     c->lusgsTileGrid = 0;
     c->meshSet = true;
     c->stateSet = c->matrixSet = c->fluxValid = false;
+    c->reconValid = false;
     c->hbNO = 1;  // a new mesh drops the Harmonic Balance setup (icsb200_hb_set must follow mesh_set)
     return 0;
 }
