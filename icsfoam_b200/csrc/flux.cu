@@ -253,7 +253,7 @@ __device__ __forceinline__ Flux5 faceFlux(const FaceState& s, V3 Sf, double magS
 // ------------------------------------------------------------------------------------------------ k_grad
 // gaussGrad::gradf for the NQ reconstructed scalars.  f: fields [Q_COUNT][NX]; grad: [NQ*3][NPH]
 template <int NQ>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, NQ > 4 ? 4 : 8)
 k_grad(int NP, const int* __restrict__ pos2cell, const int* __restrict__ sliceOff, const int* __restrict__ rowNAll, const int* __restrict__ col,
        const int* __restrict__ meta, const int* __restrict__ gfid, const double* __restrict__ geo, size_t NFG, const double* __restrict__ V,
        const double* __restrict__ f, size_t NX, double* __restrict__ grad, size_t NPH)
@@ -618,8 +618,13 @@ int ics_gradients(icsb200_ctx* c)
 {
     {
         LaunchScope ls(c, TM_GRAD);
-        k_grad<NQ><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_col, c->d_meta, c->d_gfid,
-                                                              c->d_geo, c->NFG, c->d_V, c->d_fields, c->NX, c->d_grad, c->NPH);
+        // two passes of 4 scalars: half the registers, twice the resident warps to hide the neighbour gathers
+        static_assert(NQ == 8, "k_grad passes assume 8 reconstructed scalars");
+        for (int half = 0; half < 2; half++)
+            k_grad<4><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_col, c->d_meta, c->d_gfid,
+                                                                 c->d_geo, c->NFG, c->d_V, c->d_fields + (size_t)half * 4 * c->NX, c->NX,
+                                                                 c->d_grad + (size_t)half * 12 * c->NPH, c->NPH);
+        c->launches++;
     }
     CUDA_TRY(c, cudaGetLastError());
     int r = ics_halo_fields(c, c->d_grad, c->NPH, NQ * 3);
