@@ -224,7 +224,7 @@ class HBCase:
 
 
 def hb_box(n=6, n_instants=3, omega=2 * np.pi * 40.0, flux="ROE", limiter="vanLeer", cyl=False, zoned=False, seed=0, co=5.0,
-           cyclic=True):
+           cyclic=True, mu=0.0):
     """Small 3-D box with a cyclic pair, a wall, a symmetry plane and an inlet whose total state oscillates at `omega`:
     n_instants = 2*harmonics+1 time instances coupled by the HB operator D (one frequency, uniform snapshots over one
     period, `selectedPeriod` = 2 pi / omega).  `zoned`: only the cells with x > 0.4 belong to the HB zone (cellZone
@@ -235,7 +235,7 @@ def hb_box(n=6, n_instants=3, omega=2 * np.pi * 40.0, flux="ROE", limiter="vanLe
     snaps, Ds = hb.set_instants([omegas], n_instants, selected_period=2 * np.pi / omega)
     insts = []
     for K, t in enumerate(snaps):
-        c = periodic_box(n, flux, limiter, seed + 17 * K, cyclic=cyclic)
+        c = periodic_box(n, flux, limiter, seed + 17 * K, cyclic=cyclic, mu=mu)
         s = np.sin(omega * t)
         c.bcs["ymax"] = {"p": ("fixedValue", (1.05e5 * (1 + 0.03 * s),)), "U": ("inletOutlet", (50.0 + 15.0 * s, 10.0, 0.0)),
                          "T": ("inletOutlet", (310.0 + 4.0 * s,))}

@@ -235,3 +235,15 @@ int main()
     assert np.allclose(rows[2].reshape(5, 5), Ds[1], rtol=1e-9, atol=1e-9)
     _, (D3,) = hb.set_instants([hb.omega_list([251.0], [1])], 3, selected_period=2 * np.pi / 251.0)
     assert np.allclose(rows[3].reshape(3, 3), D3, rtol=1e-10, atol=1e-10 * 251)
+
+
+def test_hb_oracle_reproduces_golden_fixture():
+    """Drift pin of the reference-structured HB oracle (tests/golden/make_golden_hb.py)."""
+    import os
+    from tests.common import GOLDEN
+    from tests.golden import make_golden_hb as mg
+    case = mg.make_case()
+    got = mg.run(HB(case), case, case.mesh.n_cells)
+    gold = np.load(os.path.join(GOLDEN, "hb_box_roe_3instants.npz"))
+    for k in gold.files:
+        assert np.array_equal(got[k], gold[k]), k
