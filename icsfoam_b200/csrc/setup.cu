@@ -260,6 +260,14 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
         if (p.start < F || p.start + p.size > FT) return ics_fail(c, ICSB200_EINVAL, "mesh_set: patch range outside boundary faces");
         if ((p.kind == ICSB200_CYCLIC) && (p.nbr_patch < 0 || p.nbr_patch >= n_patches || patches[p.nbr_patch].size != p.size))
             return ics_fail(c, ICSB200_EINVAL, "mesh_set: cyclic patch without a matching neighbour patch");
+        if (p.kind == ICSB200_CYCLIC) {
+            // translational cyclics only: a rotational pair needs the component-wise transform of U, grad and rhoU in
+            // patchNeighbourField (originalOFFiles/constraintFvPatchFields/cyclic/cyclicFvPatchField.C:130-190) — SURVEY 8f-4
+            static const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            for (int k = 0; k < 9; k++)
+                if (std::fabs(p.forwardT[k] - I9[k]) > 1e-12)
+                    return ics_fail(c, ICSB200_EINVAL, "mesh_set: rotational cyclic patches (forwardT != I) are not supported");
+        }
         if (p.kind == ICSB200_PROCESSOR && (p.nbr_rank < 0 || p.nbr_rank >= c->nRanks || c->nRanks == 1))
             return ics_fail(c, ICSB200_EINVAL, "mesh_set: processor patch needs a multi-rank context");
         if ((p.kind == ICSB200_CYCLIC || p.kind == ICSB200_PROCESSOR) && !Cf) return ics_fail(c, ICSB200_EINVAL, "mesh_set: coupled patches need Cf");

@@ -37,7 +37,7 @@ typedef struct {
     int start, size;    /* face range [start, start+size) in the global face list */
     int nbr_rank;       /* PROCESSOR: neighbProcNo */
     int nbr_patch;      /* CYCLIC: index of the neighbour patch */
-    double forwardT[9]; /* CYCLIC: rotation tensor (identity for translational) */
+    double forwardT[9]; /* CYCLIC: rotation tensor; must be the identity (translational pair) in this build, else EINVAL */
 } icsb200_patch;
 
 /* run-time selectors — same words as the reference dictionaries */

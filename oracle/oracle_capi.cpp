@@ -104,6 +104,9 @@ int orc_mesh_set(Ctx* c, int n_cells, int n_internal_faces, int n_faces, const i
         p.kind = patches[i].kind; p.start = patches[i].start; p.size = patches[i].size;
         p.nbrRank = patches[i].nbr_rank; p.nbrPatch = patches[i].nbr_patch;
         std::memcpy(p.forwardT, patches[i].forwardT, sizeof(p.forwardT));
+        if (p.kind == ICSB200_CYCLIC)
+            for (int k = 0; k < 9; k++)
+                if (std::fabs(p.forwardT[k] - (k % 4 == 0 ? 1.0 : 0.0)) > 1e-12) return fail(c, ICSB200_EINVAL, "rotational cyclic patches (forwardT != I) are not supported");
         m.patches.push_back(p);
     }
     for (int d = 0; d < 3; d++) m.solutionD[d] = solutionD[d];

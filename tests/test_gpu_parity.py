@@ -267,3 +267,13 @@ def test_forward_step_c2_polyhedral_mesh(gpu_context):
     so, sg = o.state_get(), g.state_get()
     for k in STATE_KEYS:
         assert rel_err(sg[k], so[k]) <= TOL_STATE, k
+
+
+def test_rotational_cyclic_is_refused(gpu_context):
+    """forwardT != I would silently give translational results: both implementations must refuse it."""
+    case = cases.periodic_box(4)
+    for p in case.mesh.patches:
+        if p["kind"] == capi.CYCLIC:
+            p["forwardT"] = [0, -1, 0, 1, 0, 0, 0, 0, 1]
+    with pytest.raises(capi.ApiError):
+        case.apply(gpu_context())

@@ -423,3 +423,12 @@ def test_viscous_residual_known_answers():
     case = cases.Case("k", mesh, 287.0, 1005.0, sch, capi.solver_controls(), {}, np.full(N, 1e5), U, np.full(N, 300.0))
     o = case.apply(Oracle()); o.calc_flux()
     assert np.abs(o.residual()[1][:, 0] / mesh.V)[interior].max() < 1e-9
+
+
+def test_rotational_cyclic_is_refused_by_the_oracle():
+    case = cases.periodic_box(4)
+    for p in case.mesh.patches:
+        if p["kind"] == capi.CYCLIC:
+            p["forwardT"] = [0, -1, 0, 1, 0, 0, 0, 0, 1]
+    with pytest.raises(capi.ApiError):
+        case.apply(Oracle())
