@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 # --- enums (include/icsb200.h) ---
-PATCH, WALL, EMPTY, SYMMETRYPLANE, CYCLIC, PROCESSOR = range(6)
+PATCH, WALL, EMPTY, SYMMETRYPLANE, CYCLIC, PROCESSOR, CYCLICAMI = range(7)
 FLUX_HLLC, FLUX_ROE, FLUX_AUSMPLUSUP = range(3)
 FLUX_NAMES = {"HLLC": FLUX_HLLC, "ROE": FLUX_ROE, "AUSMPlusUp": FLUX_AUSMPLUSUP}
 LIM_UPWIND, LIM_VANLEER, LIM_MINMOD, LIM_LINEAR = range(4)
@@ -110,6 +110,7 @@ SHARED_SIGNATURES = {
     "last_error": (C.c_char_p, [C.c_void_p]),
     "mesh_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
                            C.c_int, C.POINTER(Patch), _ip]),
+    "ami_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _dp]),
     "thermo_set": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]),
     "schemes_set": (C.c_int, [C.c_void_p, C.POINTER(Schemes)]),
     "bc_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
@@ -185,6 +186,11 @@ class Api:
             patches[i].nbr_rank, patches[i].nbr_patch = p.get("nbr_rank", -1), p.get("nbr_patch", -1)
             for k, v in enumerate(p.get("forwardT", [1, 0, 0, 0, 1, 0, 0, 0, 1])):
                 patches[i].forwardT[k] = v
+        for i, p in enumerate(mesh.patches):
+            if p["kind"] == CYCLICAMI and "ami" in p:   # AMI addressing / weights must be known when the mesh is set
+                start, face, weight = p["ami"]
+                self._call("ami_set", i, p["size"], iptr(np.ascontiguousarray(start, np.int32)), iptr(np.ascontiguousarray(face, np.int32)),
+                           dptr(np.ascontiguousarray(weight, np.float64)))
         sd = np.asarray(mesh.solutionD, dtype=np.int32)
         self._call("mesh_set", mesh.n_cells, mesh.n_internal_faces, mesh.n_faces, iptr(mesh.owner), iptr(mesh.neighbour),
                    dptr(mesh.Sf), dptr(mesh.magSf), dptr(mesh.weights), dptr(mesh.deltaCoeffs),

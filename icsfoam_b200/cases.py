@@ -123,11 +123,13 @@ def onera_box(n=48, co=100.0, flux="HLLC", parts=None, rank=0, mu=0.0, Pr=0.71):
     return Case("onera-box", mesh, R, Cp, sch, ctl, bcs, p, U, T, mu=mu, Pr=Pr, n_iter_default=20)
 
 
-def periodic_box(n=8, flux="HLLC", limiter="vanLeer", seed=0, nz=None, cyclic=True, mu=0.0, Pr=0.71):
+def periodic_box(n=8, flux="HLLC", limiter="vanLeer", seed=0, nz=None, cyclic=True, mu=0.0, Pr=0.71, ami_shift=None):
     """Small randomised box with a translational cyclic pair in x — a parity-test workhorse, not a tutorial."""
     mesh = mt.structured(1, n, n, nz or n, 0, (0, 0, 0), (1.0, 1.2, 0.9),
                          patch_kinds=(capi.PATCH, capi.PATCH, capi.WALL, capi.PATCH, capi.SYMMETRYPLANE, capi.PATCH))
-    if cyclic:
+    if cyclic and ami_shift is not None:
+        mesh.set_cyclic_ami("xmin", "xmax", ami_shift)   # non-conformal periodic pair (cyclicAMI)
+    elif cyclic:
         mesh.set_cyclic("xmin", "xmax")
     rng = np.random.default_rng(seed)
     N = mesh.n_cells

@@ -61,6 +61,15 @@ struct ProcPatchDev {
     int* d_sendPos;  // positions of faceCells
 };
 
+// cyclicAMI patch on the device: halo slots [NP+haloStart, +size) receive sum_k w_k phi[srcPos_k] (CSR over the faces)
+struct AmiPatchDev {
+    int size, haloStart;
+    int* d_start;    // [size+1]
+    int* d_srcPos;   // [nnz] positions of the neighbour patch's face cells
+    double* d_w;     // [nnz]
+};
+struct AmiTable { std::vector<int> start, face; std::vector<double> weight; };
+
 struct icsb200_ctx {
     int device = 0, rank = 0, nRanks = 1;
     cudaStream_t stream = nullptr, commStream = nullptr;
@@ -116,6 +125,8 @@ struct icsb200_ctx {
     double *d_vic = nullptr;                // [5*NB] pVIC, uVIC(3), tVIC frozen at BC evaluation
     // processor patches
     std::vector<ProcPatchDev> procs;
+    std::vector<AmiPatchDev> amis;                 // cyclicAMI patches (local weighted gathers into halo slots)
+    std::vector<std::pair<int, AmiTable>> pendingAmi;  // icsb200_ami_set tables waiting for mesh_set
     double *d_sendBuf = nullptr, *d_recvBuf = nullptr;
 
     // ---- thermo / schemes ----

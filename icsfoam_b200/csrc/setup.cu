@@ -138,6 +138,7 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
                     c->d_faceRecon, c->d_gradE, c->d_visc, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
+    for (auto& am : c->amis) { cudaFree(am.d_start); cudaFree(am.d_srcPos); cudaFree(am.d_w); }
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaEventDestroy(c->ev0);
@@ -238,6 +239,19 @@ extern "C" int icsb200_bc_set(icsb200_ctx* c, int patch, int field, int kind, co
 }
 
 // ------------------------------------------------------------------------------------------------ mesh
+extern "C" int icsb200_ami_set(icsb200_ctx* c, int patch, int n_faces, const int* face_start, const int* nbr_face, const double* weight)
+{
+    if (patch < 0 || n_faces < 0 || !face_start || (face_start[n_faces] > 0 && (!nbr_face || !weight)))
+        return ics_fail(c, ICSB200_EINVAL, "ami_set: bad arguments");
+    AmiTable t;
+    t.start.assign(face_start, face_start + n_faces + 1);
+    t.face.assign(nbr_face, nbr_face + face_start[n_faces]);
+    t.weight.assign(weight, weight + face_start[n_faces]);
+    for (auto& pa : c->pendingAmi) if (pa.first == patch) { pa.second = t; return 0; }
+    c->pendingAmi.emplace_back(patch, t);
+    return 0;
+}
+
 extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int* owner, const int* neighbour, const double* Sf,
                                 const double* magSf, const double* weights, const double* deltaCoeffs, const double* nonOrthDeltaCoeffs,
                                 const double* C, const double* V, const double* Cf, int n_patches, const icsb200_patch* patches,
@@ -260,7 +274,15 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
         if (p.start < F || p.start + p.size > FT) return ics_fail(c, ICSB200_EINVAL, "mesh_set: patch range outside boundary faces");
         if ((p.kind == ICSB200_CYCLIC) && (p.nbr_patch < 0 || p.nbr_patch >= n_patches || patches[p.nbr_patch].size != p.size))
             return ics_fail(c, ICSB200_EINVAL, "mesh_set: cyclic patch without a matching neighbour patch");
-        if (p.kind == ICSB200_CYCLIC) {
+        if (p.kind == ICSB200_CYCLICAMI) {
+            if (p.nbr_patch < 0 || p.nbr_patch >= n_patches || patches[p.nbr_patch].kind != ICSB200_CYCLICAMI)
+                return ics_fail(c, ICSB200_EINVAL, "mesh_set: cyclicAMI patch without a cyclicAMI neighbour patch");
+            const AmiTable* t = nullptr;
+            for (auto& pa : c->pendingAmi) if (pa.first == pi) t = &pa.second;
+            if (!t || (int)t->start.size() != p.size + 1) return ics_fail(c, ICSB200_EINVAL, "mesh_set: cyclicAMI patch without a matching icsb200_ami_set");
+            for (int fidx : t->face) if (fidx < 0 || fidx >= patches[p.nbr_patch].size) return ics_fail(c, ICSB200_EINVAL, "mesh_set: cyclicAMI address outside the neighbour patch");
+        }
+        if (p.kind == ICSB200_CYCLIC || p.kind == ICSB200_CYCLICAMI) {
             // translational cyclics only: a rotational pair needs the component-wise transform of U, grad and rhoU in
             // patchNeighbourField (originalOFFiles/constraintFvPatchFields/cyclic/cyclicFvPatchField.C:130-190) — SURVEY 8f-4
             static const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -270,7 +292,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
         }
         if (p.kind == ICSB200_PROCESSOR && (p.nbr_rank < 0 || p.nbr_rank >= c->nRanks || c->nRanks == 1))
             return ics_fail(c, ICSB200_EINVAL, "mesh_set: processor patch needs a multi-rank context");
-        if ((p.kind == ICSB200_CYCLIC || p.kind == ICSB200_PROCESSOR) && !Cf) return ics_fail(c, ICSB200_EINVAL, "mesh_set: coupled patches need Cf");
+        if ((p.kind == ICSB200_CYCLIC || p.kind == ICSB200_PROCESSOR || p.kind == ICSB200_CYCLICAMI) && !Cf) return ics_fail(c, ICSB200_EINVAL, "mesh_set: coupled patches need Cf");
         if (p.kind != ICSB200_EMPTY) for (int f = p.start; f < p.start + p.size; f++) c->bfacePatch[f - F] = pi;
     }
 
@@ -415,7 +437,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     int NH = 0;
     std::vector<int> patchHaloStart(n_patches, -1);
     for (int pi = 0; pi < n_patches; pi++)
-        if (patches[pi].kind == ICSB200_PROCESSOR) { patchHaloStart[pi] = NH; NH += patches[pi].size; }
+        if (patches[pi].kind == ICSB200_PROCESSOR || patches[pi].kind == ICSB200_CYCLICAMI) { patchHaloStart[pi] = NH; NH += patches[pi].size; }
     NH += NH & 1;  // keep NPH even: every component array of a cell vector then starts 16-byte aligned (TMA bulk copies)
     c->NH = NH; c->NPH = NP + NH; c->NX = NP + NH + NB;
 
@@ -464,7 +486,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                 int nbrFace = patches[pa.nbr_patch].start + (f - pa.start);
                 c->h_col[sb] = c->cell2pos[owner[nbrFace]];
                 c->h_meta[sb] = ET_COUPLED | (f << 2);
-            } else if (pa.kind == ICSB200_PROCESSOR) {
+            } else if (pa.kind == ICSB200_PROCESSOR || pa.kind == ICSB200_CYCLICAMI) {
                 c->h_col[sb] = NP + patchHaloStart[pi] + (f - pa.start);
                 c->h_meta[sb] = ET_COUPLED | (f << 2);
             } else {
@@ -552,7 +574,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     std::vector<double> ownDelta((size_t)3 * std::max(NB, 1), 0.0);
     for (int pi = 0; pi < n_patches; pi++) {
         const icsb200_patch& pa = patches[pi];
-        if (pa.kind != ICSB200_CYCLIC && pa.kind != ICSB200_PROCESSOR) continue;
+        if (pa.kind != ICSB200_CYCLIC && pa.kind != ICSB200_PROCESSOR && pa.kind != ICSB200_CYCLICAMI) continue;
         for (int f = pa.start; f < pa.start + pa.size; f++)
             for (int d = 0; d < 3; d++) ownDelta[3 * (size_t)(f - F) + d] = Cf[3 * (size_t)f + d] - C[3 * (size_t)owner[f] + d];
     }
@@ -563,9 +585,22 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             const icsb200_patch& qa = patches[pa.nbr_patch];
             for (int i = 0; i < pa.size; i++)
                 for (int d = 0; d < 3; d++) nbrDelta[3 * (size_t)(pa.start + i - F) + d] = ownDelta[3 * (size_t)(qa.start + i - F) + d];
+        } else if (pa.kind == ICSB200_CYCLICAMI) {
+            // cyclicAMIFvPatch::delta(): patchD - interpolate(nbrPatch.coupledFvPatch::delta())
+            const icsb200_patch& qa = patches[pa.nbr_patch];
+            const AmiTable* t = nullptr;
+            for (auto& pe : c->pendingAmi) if (pe.first == pi) t = &pe.second;
+            for (int i = 0; i < pa.size; i++)
+                for (int d = 0; d < 3; d++) {
+                    double acc = 0.0;
+                    for (int k = t->start[i]; k < t->start[i + 1]; k++) acc += t->weight[k] * ownDelta[3 * (size_t)(qa.start + t->face[k] - F) + d];
+                    nbrDelta[3 * (size_t)(pa.start + i - F) + d] = acc;
+                }
         }
     }
-    if (NH > 0) {
+    bool anyProc = false;
+    for (int pi = 0; pi < n_patches; pi++) anyProc |= patches[pi].kind == ICSB200_PROCESSOR;
+    if (NH > 0 && anyProc) {
         // exchange processor-patch deltas through NCCL (device staging)
         double *dS = nullptr, *dR = nullptr;
         CUDA_TRY(c, cudaMalloc((void**)&dS, sizeof(double) * 3 * NH));
@@ -695,6 +730,21 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
         r |= devUpload(c, &pp.d_sendPos, sp);
         c->procs.push_back(pp);
     }
+    for (auto& am : c->amis) { cudaFree(am.d_start); cudaFree(am.d_srcPos); cudaFree(am.d_w); }
+    c->amis.clear();
+    for (int pi = 0; pi < n_patches; pi++) {
+        if (patches[pi].kind != ICSB200_CYCLICAMI) continue;
+        const AmiTable* t = nullptr;
+        for (auto& pe : c->pendingAmi) if (pe.first == pi) t = &pe.second;
+        AmiPatchDev am{};
+        am.size = patches[pi].size; am.haloStart = patchHaloStart[pi];
+        std::vector<int> sp(t->face.size());
+        for (size_t k = 0; k < sp.size(); k++) sp[k] = c->cell2pos[owner[patches[patches[pi].nbr_patch].start + t->face[k]]];
+        r |= devUpload(c, &am.d_start, t->start);
+        r |= devUpload(c, &am.d_srcPos, sp);
+        r |= devUpload(c, &am.d_w, t->weight);
+        c->amis.push_back(am);
+    }
     if (NH > 0) {
         r |= devAlloc(c, &c->d_sendBuf, (size_t)NH * 40);
         r |= devAlloc(c, &c->d_recvBuf, (size_t)NH * 40);
@@ -703,7 +753,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     // ---- BCs default: zeroGradient on physical patches
     c->h_bc.assign(n_patches, BCDev{});
     for (int pi = 0; pi < n_patches; pi++) {
-        int k = (patches[pi].kind == ICSB200_CYCLIC || patches[pi].kind == ICSB200_PROCESSOR) ? ICSB200_BC_COUPLED
+        int k = (patches[pi].kind == ICSB200_CYCLIC || patches[pi].kind == ICSB200_PROCESSOR || patches[pi].kind == ICSB200_CYCLICAMI) ? ICSB200_BC_COUPLED
                 : patches[pi].kind == ICSB200_EMPTY ? ICSB200_BC_EMPTY : ICSB200_BC_ZEROGRADIENT;
         for (int fl = 0; fl < 3; fl++) c->h_bc[pi].kind[fl] = k;
     }

@@ -46,9 +46,38 @@ __global__ void k_unpack(int n, int nArrays, int slot0, const double* __restrict
 }  // namespace
 
 // exchange the processor-patch halo of nArrays SoA arrays (patchNeighbourField of every coupled field at once)
+// cyclicAMIFvPatchField::patchNeighbourField (cyclicAMIFvPatchField.C:146-209): halo slot = sum_k w_k phi[srcPos_k], summed in
+// the order of the AMI address list (AMIInterpolation::interpolateToSource with plusEqOp: result = 0; result += w*phi)
+__global__ void k_ami_gather(int n, int nArrays, int slot0, const int* __restrict__ start, const int* __restrict__ srcPos, const double* __restrict__ w,
+                             double* __restrict__ base, size_t stride)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * nArrays) return;
+    const int a = t / n, i = t - a * n;
+    double acc = 0.0;
+    for (int k = start[i]; k < start[i + 1]; k++) acc += w[k] * base[(size_t)a * stride + srcPos[k]];
+    base[(size_t)a * stride + slot0 + i] = acc;
+}
+
+static int amiGather(icsb200_ctx* c, double* base, size_t stride, int nArrays)
+{
+    if (c->amis.empty()) return 0;
+    LaunchScope ls(c, TM_HALO);
+    for (auto& am : c->amis)
+        k_ami_gather<<<gridFor((long long)am.size * nArrays, 128), 128, 0, c->stream>>>(am.size, nArrays, c->NP + am.haloStart, am.d_start, am.d_srcPos, am.d_w, base, stride);
+    c->launches += (long long)c->amis.size() - 1;
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+}
+
 int ics_halo_fields(icsb200_ctx* c, double* base, size_t stride, int nArrays)
 {
-    if (c->NH == 0 || c->procs.empty()) return 0;
+    if (c->NH == 0) return 0;
+    {
+        int r = amiGather(c, base, stride, nArrays);
+        if (r) return r;
+    }
+    if (c->procs.empty()) return 0;
     if (nArrays > 40) return ics_fail(c, ICSB200_EINVAL, "halo: too many arrays");
     LaunchScope ls(c, TM_HALO);
     for (auto& pp : c->procs)

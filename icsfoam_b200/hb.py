@@ -105,7 +105,7 @@ class ReplicatedMesh:
                 q["name"] = f"{p['name']}@{K}"
                 q["start"] = n * F + K * NB + (p["start"] - F)
                 if q.get("nbr_patch", -1) >= 0:
-                    q["nbr_patch"] = q["nbr_patch"] + K * np0
+                    q["nbr_patch"] = q["nbr_patch"] + K * np0   # cyclic / cyclicAMI partner of the same instance ("ami" tables are patch-local)
                 self.patches.append(q)
         self.cell_global = None
         self.face_global = None

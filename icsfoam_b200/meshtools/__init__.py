@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-from ..capi import CYCLIC, EMPTY, PATCH, PROCESSOR, SYMMETRYPLANE, WALL  # noqa: F401
+from ..capi import CYCLIC, CYCLICAMI, EMPTY, PATCH, PROCESSOR, SYMMETRYPLANE, WALL  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -93,6 +93,68 @@ class Mesh:
             db = np.abs(np.einsum("ij,ij->i", nfb, self.Cf[fb] - self.C[self.owner[fb]]))
             self.weights[fa] = db / (da + db)
             d = (self.Cf[fa] - self.C[self.owner[fa]]) - (self.Cf[fb] - self.C[self.owner[fb]])
+            md = np.linalg.norm(d, axis=1)
+            self.deltaCoeffs[fa] = 1.0 / md
+            self.nonOrthDeltaCoeffs[fa] = 1.0 / np.maximum(np.einsum("ij,ij->i", nfa, d), 0.05 * md)
+
+    def set_cyclic_ami(self, a, b, shift=0.5):
+        """Turn two plane patches into a translational cyclicAMI pair whose faces do not match: the neighbour patch is
+        shifted by `shift` cells along the first in-plane direction (periodic wrap), so every face overlaps two
+        neighbour faces with weights (1 - shift, shift).  shift = 0 gives a one-to-one AMI (== plain cyclic).
+        Stand-in for OpenFOAM's AMIInterpolation on the synthetic meshes; fills weights / deltaCoeffs /
+        nonOrthDeltaCoeffs of the patch faces as cyclicAMIFvPatch::makeWeights / delta() do."""
+        ia, ib = self.patch_index(a), self.patch_index(b)
+        tables = {}
+        for (i0, i1) in ((ia, ib), (ib, ia)):
+            pa, pb = self.patches[i0], self.patches[i1]
+            fa = np.arange(pa["start"], pa["start"] + pa["size"])
+            fb = np.arange(pb["start"], pb["start"] + pb["size"])
+            na = np.abs(self.Sf[fa[0]] / self.magSf[fa[0]])
+            axes = [d for d in range(3) if na[d] < 0.5]          # the two in-plane directions
+            def grid(faces):
+                u = np.unique(np.round(self.Cf[faces][:, axes[0]], 9)); v = np.unique(np.round(self.Cf[faces][:, axes[1]], 9))
+                iu = np.searchsorted(u, np.round(self.Cf[faces][:, axes[0]], 9)); iv = np.searchsorted(v, np.round(self.Cf[faces][:, axes[1]], 9))
+                return len(u), len(v), iu, iv
+            nu, nv, iua, iva = grid(fa)
+            nub, nvb, iub, ivb = grid(fb)
+            assert (nu, nv) == (nub, nvb) and nu * nv == pa["size"]
+            lookup = -np.ones((nu, nv), np.int64)
+            lookup[iub, ivb] = np.arange(pb["size"])
+            sgn = 1 if i0 == ia else -1                          # the two sides see opposite shifts
+            start, face, weight = [0], [], []
+            for i in range(pa["size"]):
+                if shift == 0:
+                    pairs = [(lookup[iua[i], iva[i]], 1.0)]
+                else:
+                    j0 = lookup[iua[i], iva[i]]
+                    j1 = lookup[(iua[i] + sgn) % nu, iva[i]]
+                    pairs = [(j0, 1.0 - shift), (j1, shift)]
+                for j, w in pairs:
+                    face.append(int(j)); weight.append(float(w))
+                start.append(len(face))
+            tables[i0] = (np.array(start, np.int32), np.array(face, np.int32), np.array(weight, np.float64))
+        lib = _lib()
+        lib.icsmesh_set_patch_kind(self._h, ia, CYCLICAMI, ib)
+        lib.icsmesh_set_patch_kind(self._h, ib, CYCLICAMI, ia)
+        self.patches[ia].update(kind=CYCLICAMI, nbr_patch=ib, ami=tables[ia])
+        self.patches[ib].update(kind=CYCLICAMI, nbr_patch=ia, ami=tables[ib])
+        for (i0, i1) in ((ia, ib), (ib, ia)):
+            pa, pb = self.patches[i0], self.patches[i1]
+            start, face, weight = pa["ami"]
+            fa = np.arange(pa["start"], pa["start"] + pa["size"])
+            fb = pb["start"] + face
+            nfa = self.Sf[fa] / self.magSf[fa, None]
+            da = np.einsum("ij,ij->i", nfa, self.Cf[fa] - self.C[self.owner[fa]])
+            nfb = self.Sf[fb] / self.magSf[fb, None]
+            dbj = np.einsum("ij,ij->i", nfb, self.Cf[fb] - self.C[self.owner[fb]])
+            deltab = self.Cf[fb] - self.C[self.owner[fb]]
+            dn = np.zeros(pa["size"]); dvec = np.zeros((pa["size"], 3))
+            for i in range(pa["size"]):
+                for k in range(start[i], start[i + 1]):
+                    dn[i] += weight[k] * dbj[k]
+                    dvec[i] += weight[k] * deltab[k]
+            self.weights[fa] = dn / (da + dn)
+            d = (self.Cf[fa] - self.C[self.owner[fa]]) - dvec
             md = np.linalg.norm(d, axis=1)
             self.deltaCoeffs[fa] = 1.0 / md
             self.nonOrthDeltaCoeffs[fa] = 1.0 / np.maximum(np.einsum("ij,ij->i", nfa, d), 0.05 * md)

@@ -30,7 +30,8 @@ enum {
 };
 
 /* fvPatch kinds as the hot path distinguishes them (convectiveFluxScheme.C:243, setCoAndDeltaT.H:72-86) */
-enum { ICSB200_PATCH = 0, ICSB200_WALL = 1, ICSB200_EMPTY = 2, ICSB200_SYMMETRYPLANE = 3, ICSB200_CYCLIC = 4, ICSB200_PROCESSOR = 5 };
+enum { ICSB200_PATCH = 0, ICSB200_WALL = 1, ICSB200_EMPTY = 2, ICSB200_SYMMETRYPLANE = 3, ICSB200_CYCLIC = 4, ICSB200_PROCESSOR = 5,
+    ICSB200_CYCLICAMI = 6 /* cyclicAMI: patchNeighbourField = weighted sum over neighbour-patch faces (icsb200_ami_set) */ };
 
 typedef struct {
     int kind;           /* ICSB200_PATCH ... */
@@ -114,6 +115,14 @@ int icsb200_mesh_set(icsb200_ctx* ctx, int n_cells, int n_internal_faces, int n_
                      const int* neighbour, const double* Sf, const double* magSf, const double* weights,
                      const double* deltaCoeffs, const double* nonOrthDeltaCoeffs, const double* C, const double* V,
                      const double* Cf, int n_patches, const icsb200_patch* patches, const int solutionD[3]);
+/* cyclicAMI interpolation of patch `patch` (kind ICSB200_CYCLICAMI, neighbour = nbr_patch): for face i of the patch,
+ * patchNeighbourField[i] = sum_{k in [face_start[i], face_start[i+1])} weight[k] * phi[faceCells(nbr_patch)[nbr_face[k]]]
+ * in this order (AMIInterpolation::interpolateToSource/Target with plusEqOp; originalOFFiles/constraintFvPatchFields/
+ * cyclicAMI/cyclicAMIFvPatchField.C:146-209, no lowWeightCorrection, translational: forwardT must be I).  The addressing
+ * and weights are OpenFOAM's (cyclicAMIPolyPatch::AMI().srcAddress()/srcWeights()); the mesh arrays weights /
+ * deltaCoeffs / nonOrthDeltaCoeffs of the patch faces are cyclicAMIFvPatch's.  Call BEFORE icsb200_mesh_set, once per
+ * cyclicAMI patch; both patches of a pair live on the same rank. */
+int icsb200_ami_set(icsb200_ctx* ctx, int patch, int n_faces, const int* face_start, const int* nbr_face, const double* weight);
 /* hePsiThermo<pureMixture<constTransport<hConst<perfectGas>>>>, sensibleInternalEnergy (createFields.H:17-35).
  * mu > 0 makes the run viscous (createFields.H:37-45 `inviscid`): icsb200_residual / iterate then add the laminar
  * viscous terms of residualsUpdate.H:16-43 (laplacian(muEff,U), div(tauMC), div(sigmaDotU & Sf), laplacian(alphaEff,e),

@@ -33,6 +33,9 @@ inline double stabilise(double x, double y) { return x < 0 ? x - y : x + y; }
 struct Patch {
     int kind, start, size, nbrRank, nbrPatch;
     double forwardT[9];
+    // cyclicAMI: CSR over the patch faces of (face index within the neighbour patch, weight)
+    veci amiStart, amiFace;
+    vecd amiWeight;
 };
 
 struct Mesh {
@@ -44,7 +47,7 @@ struct Mesh {
     // primitiveMesh::cells(): faces a cell owns (ascending) then faces where it is neighbour (ascending)
     veci cellFaceStart, cellFaces;
     vecd dCoupled;  // [3*NB] delta vector of coupled boundary faces (own delta - neighbour delta)
-    bool coupled(const Patch& p) const { return p.kind == ICSB200_CYCLIC || p.kind == ICSB200_PROCESSOR; }
+    bool coupled(const Patch& p) const { return p.kind == ICSB200_CYCLIC || p.kind == ICSB200_PROCESSOR || p.kind == ICSB200_CYCLICAMI; }
     bool empty(const Patch& p) const { return p.kind == ICSB200_EMPTY; }
 };
 
@@ -106,6 +109,8 @@ struct Ctx {
     // coupledMatrix(mesh, 2, 1): block ids as in icsb200_matrix_get_ldu
     Blk blk[9];
     // Roe dissipation members (roeFluxScheme.H:61-71) are temporaries here
+    // cyclicAMI tables handed over by orc_ami_set before orc_mesh_set: patch -> (start, face, weight)
+    std::vector<std::pair<int, Patch>> pendingAmi;
     std::string err;
 };
 

@@ -104,7 +104,13 @@ int orc_mesh_set(Ctx* c, int n_cells, int n_internal_faces, int n_faces, const i
         p.kind = patches[i].kind; p.start = patches[i].start; p.size = patches[i].size;
         p.nbrRank = patches[i].nbr_rank; p.nbrPatch = patches[i].nbr_patch;
         std::memcpy(p.forwardT, patches[i].forwardT, sizeof(p.forwardT));
-        if (p.kind == ICSB200_CYCLIC)
+        if (p.kind == ICSB200_CYCLICAMI) {
+            bool found = false;
+            for (auto& pa : c->pendingAmi)
+                if (pa.first == i) { p.amiStart = pa.second.amiStart; p.amiFace = pa.second.amiFace; p.amiWeight = pa.second.amiWeight; found = true; }
+            if (!found || (int)p.amiStart.size() != p.size + 1) return fail(c, ICSB200_EINVAL, "cyclicAMI patch without a matching orc_ami_set");
+        }
+        if (p.kind == ICSB200_CYCLIC || p.kind == ICSB200_CYCLICAMI)
             for (int k = 0; k < 9; k++)
                 if (std::fabs(p.forwardT[k] - (k % 4 == 0 ? 1.0 : 0.0)) > 1e-12) return fail(c, ICSB200_EINVAL, "rotational cyclic patches (forwardT != I) are not supported");
         m.patches.push_back(p);
@@ -113,6 +119,17 @@ int orc_mesh_set(Ctx* c, int n_cells, int n_internal_faces, int n_faces, const i
     for (int f = 0; f < m.F; f++) if (m.owner[f] >= m.neighbour[f]) return fail(c, ICSB200_EINVAL, "mesh is not in upper-triangular order");
     meshFinalize(*c);
     c->meshSet = true;
+    return 0;
+}
+
+int orc_ami_set(Ctx* c, int patch, int n_faces, const int* face_start, const int* nbr_face, const double* weight)
+{
+    Patch p{};
+    p.amiStart.assign(face_start, face_start + n_faces + 1);
+    p.amiFace.assign(nbr_face, nbr_face + face_start[n_faces]);
+    p.amiWeight.assign(weight, weight + face_start[n_faces]);
+    for (auto& pa : c->pendingAmi) if (pa.first == patch) { pa.second = p; return 0; }
+    c->pendingAmi.emplace_back(patch, p);
     return 0;
 }
 

@@ -42,6 +42,15 @@ void meshFinalize(Ctx& c)
                 for (int d = 0; d < 3; d++) nbr[3 * (p.start + i - m.F) + d] = own[3 * (q.start + i - m.F) + d];
         } else if (p.kind == ICSB200_PROCESSOR) {
             c.comm->exchange(p.nbrRank, &own[3 * (p.start - m.F)], &nbr[3 * (p.start - m.F)], 3 * p.size);
+        } else if (p.kind == ICSB200_CYCLICAMI) {
+            // cyclicAMIFvPatch::delta: patchD - interpolate(nbrPatch.coupledFvPatch::delta())
+            auto& q = m.patches[p.nbrPatch];
+            for (int i = 0; i < p.size; i++)
+                for (int d = 0; d < 3; d++) {
+                    double acc = 0.0;
+                    for (int k = p.amiStart[i]; k < p.amiStart[i + 1]; k++) acc += p.amiWeight[k] * own[3 * (q.start + p.amiFace[k] - m.F) + d];
+                    nbr[3 * (p.start + i - m.F) + d] = acc;
+                }
         }
     }
     for (auto& p : m.patches)
@@ -66,6 +75,15 @@ void syncCoupled(Ctx& c, vecd& vf, int nc)
                 int nb = m.owner[q.start + i];
                 for (int d = 0; d < nc; d++) vf[(size_t)nc * (m.N + p.start - m.F + i) + d] = vf[(size_t)nc * nb + d];
             }
+        } else if (p.kind == ICSB200_CYCLICAMI) {
+            // cyclicAMIFvPatchField::patchNeighbourField = AMI.interpolate(neighbour cell values): result = 0; result += w*phi
+            auto& q = m.patches[p.nbrPatch];
+            for (int i = 0; i < p.size; i++)
+                for (int d = 0; d < nc; d++) {
+                    double acc = 0.0;
+                    for (int k = p.amiStart[i]; k < p.amiStart[i + 1]; k++) acc += p.amiWeight[k] * vf[(size_t)nc * m.owner[q.start + p.amiFace[k]] + d];
+                    vf[(size_t)nc * (m.N + p.start - m.F + i) + d] = acc;
+                }
         } else if (p.kind == ICSB200_PROCESSOR) {
             vecd send((size_t)nc * p.size), recv((size_t)nc * p.size);
             for (int i = 0; i < p.size; i++)

@@ -71,6 +71,12 @@ void derivedFields(Ctx& c, Derived& d, int cKind /*0: max(sqrt(gamma/psi),VSMALL
     for (auto& p : m.patches)
         if (m.empty(p))
             for (int f = p.start; f < p.start + p.size; f++) { size_t s = m.N + f - m.F; d.c[s] = d.E[s] = d.H[s] = 0; }
+    // coupled patches: patchNeighbourField of an expression field is taken from ITS internal field (cyclic / processor: the
+    // neighbour cell's value, identical to evaluating the expression on the copied primitives; cyclicAMI: the
+    // AMI-interpolated cell values, which is not the expression of the interpolated primitives)
+    syncCoupled(c, d.c, 1);
+    syncCoupled(c, d.E, 1);
+    syncCoupled(c, d.H, 1);
 }
 
 struct Recon {
@@ -417,6 +423,7 @@ void viscousResidual(Ctx& c, vecd& rhoUR, vecd& rhoER)
         const double* u = &c.U[3 * i];
         eCalc[i] = c.rho[i] != 0.0 ? c.rhoE[i] / c.rho[i] - 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) : 0.0;
     }
+    syncCoupled(c, eCalc, 1);  // coupled patches: patchNeighbourField of eCalc's internal field (AMI: interpolated cell values)
     gradGauss(c, eCalc, gE);
     auto gradUOf = [&](size_t i, double g[9]) {  // g[3*i+j] = d_i U_j
         for (int d = 0; d < 3; d++) for (int j = 0; j < 3; j++) g[3 * d + j] = gU[j][3 * i + d];
@@ -541,6 +548,7 @@ static void spectralRadius(Ctx& c, vecd& lambda)
     vecd cc(n), comp(n), cf, uf[3];
     for (size_t i = 0; i < n; i++) cc[i] = std::sqrt(c.gamma / c.psi[i]);
     for (auto& p : m.patches) if (m.empty(p)) for (int f = p.start; f < p.start + p.size; f++) cc[m.N + f - m.F] = 0;
+    syncCoupled(c, cc, 1);  // patchNeighbourField of sqrt(gamma/psi) (see derivedFields)
     interpolateLinear(c, cc, cf);
     for (int d = 0; d < 3; d++) {
         for (size_t i = 0; i < n; i++) comp[i] = c.U[3 * i + d];

@@ -12,7 +12,7 @@ from oracle.pyoracle import Oracle
 
 def test_fixture_set_is_complete():
     have = {os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))}
-    assert have == set(CASES)
+    assert have == set(CASES) | {"hb_box_roe_3instants"}   # the HB fixture has its own generator (make_golden_hb.py)
 
 
 @pytest.mark.parametrize("name", sorted(CASES))

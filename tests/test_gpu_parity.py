@@ -55,6 +55,9 @@ LIVE = {
     "box-viscous-hllc": lambda: cases.periodic_box(5, "HLLC", "Minmod", seed=52, mu=0.2, Pr=1.3),
     "bump-viscous": lambda: cases.bump(15, 10, mu=0.02),
     "scrambled-viscous": lambda: cases.scrambled_box(5, "HLLC", "vanLeer", seed=53, mu=0.1),
+    # cyclicAMI (non-conformal periodic pair: every face sees two neighbour faces, weights 0.5/0.5 and 0.7/0.3)
+    "box-ami-roe": lambda: cases.periodic_box(6, "ROE", "vanLeer", seed=71, ami_shift=0.5),
+    "box-ami-hllc-viscous": lambda: cases.periodic_box(5, "HLLC", "Minmod", seed=72, ami_shift=0.3, mu=0.1),
     "shocktube-ausm": lambda: cases.shock_tube(64, "AUSMPlusUp"),
     "shocktube-roe": lambda: cases.shock_tube(50, "ROE"),
 }

@@ -432,3 +432,34 @@ def test_rotational_cyclic_is_refused_by_the_oracle():
             p["forwardT"] = [0, -1, 0, 1, 0, 0, 0, 0, 1]
     with pytest.raises(capi.ApiError):
         case.apply(Oracle())
+
+
+def test_cyclic_ami_one_to_one_equals_cyclic_and_preserves_free_stream():
+    """cyclicAMI (cyclicAMIFvPatchField.C:146-209): with a one-to-one address list and unit weights the AMI pair must
+    reproduce the plain cyclic pair bit for bit; with a half-cell shift (every face sees two neighbour faces, 0.5/0.5) a
+    uniform state must stay a solution (interpolation weights sum to 1) and the run must stay finite."""
+    from tests.common import run_sequence
+    a = cases.periodic_box(5, "HLLC", "vanLeer", seed=7)
+    b = cases.periodic_box(5, "HLLC", "vanLeer", seed=7, ami_shift=0)
+    ra, rb = run_sequence(a.apply(Oracle()), a, 2), run_sequence(b.apply(Oracle()), b, 2)
+    for k in ra:
+        assert np.array_equal(ra[k], rb[k]), k
+    c = cases.periodic_box(5, "ROE", "vanLeer", seed=7, ami_shift=0.5, mu=0.05)
+    c.p[:] = 1e5; c.T[:] = 300.0; c.U[:] = [30.0, 0, 0]
+    for k in list(c.bcs):
+        c.bcs[k] = {"p": ("zeroGradient", ()), "U": ("slip", ()), "T": ("zeroGradient", ())}
+    o = c.apply(Oracle())
+    phi = o.calc_flux()[0]
+    r = o.residual()
+    scale = np.abs(phi).max()
+    assert np.abs(r[0]).max() <= 1e-12 * scale and np.abs(r[1]).max() <= 1e-9 * scale * 30
+    d = cases.periodic_box(5, "ROE", "vanLeer", seed=9, ami_shift=0.5)
+    out = run_sequence(d.apply(Oracle()), d, 3)
+    assert np.isfinite(out["rho"]).all() and out["history"][-1, 0] < out["history"][0, 0]
+    # a cyclicAMI patch without its table is refused
+    m = cases.periodic_box(4, ami_shift=0.5)
+    for p in m.mesh.patches:
+        if p["kind"] == capi.CYCLICAMI:
+            del p["ami"]
+    with pytest.raises(capi.ApiError):
+        m.apply(Oracle())
