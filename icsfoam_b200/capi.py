@@ -125,6 +125,8 @@ SHARED_SIGNATURES = {
     "matrix_get_ldu": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp]),
     "matrix_set_ldu": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp]),
     "source_set": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
+    "source_get": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
+    "mrf_set": (C.c_int, [C.c_void_p, _dp, _dp]),
     "matrix_mul": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp]),
     "precondition": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp]),
     "solve_delta": (C.c_int, [C.c_void_p, C.POINTER(SolverControls), _dp, _dp, _dp, C.POINTER(Residuals)]),
@@ -269,6 +271,21 @@ class Api:
     def source_set(self, sRho, sRhoU, sRhoE):
         self._call("source_set", dptr(np.ascontiguousarray(sRho)), dptr(np.ascontiguousarray(sRhoU)),
                    dptr(np.ascontiguousarray(sRhoE)))
+
+    def source_get(self):
+        """sources of the assembled system as the solver sees them (R*V, HB and MRF terms)"""
+        N = self.mesh.n_cells
+        a, b, c = np.zeros(N), np.zeros((N, 3)), np.zeros(N)
+        self._call("source_get", dptr(a), dptr(b), dptr(c))
+        return a, b, c
+
+    def mrf_set(self, face_velocity=None, omega=None):
+        """flux.MRFFaceVelocity() [n_faces] and flux.MRFOmega() [n_cells,3] (outerLoop.H:18-21); None = zero field"""
+        fv = None if face_velocity is None else np.ascontiguousarray(face_velocity, np.float64)
+        om = None if omega is None else np.ascontiguousarray(omega, np.float64)
+        assert fv is None or fv.size == self.mesh.n_faces
+        assert om is None or om.size == 3 * self.mesh.n_cells
+        self._call("mrf_set", dptr(fv), dptr(om))
 
     def matrix_mul(self, xRho, xRhoU, xRhoE):
         N = self.mesh.n_cells

@@ -21,6 +21,28 @@ class Case:
         self.U = np.ascontiguousarray(U, np.float64)
         self.T = np.ascontiguousarray(T, np.float64)
         self.n_iter_default = n_iter_default
+        self.mrf = None   # (omega[3], origin[3], translation velocity[3], zone predicate on points or None): see with_mrf
+
+    def with_mrf(self, omega=(0, 0, 0), origin=(0, 0, 0), velocity=(0, 0, 0), zone=None):
+        """Frame motion of an MRFCoupledZone (rotation `omega` about `origin`) plus an MRFTranslatingZone (`velocity`),
+        restricted to the points where zone(xyz) is true (None: whole mesh)."""
+        self.mrf = (np.asarray(omega, float), np.asarray(origin, float), np.asarray(velocity, float), zone)
+        return self
+
+    def mrf_fields(self, m):
+        """flux.MRFFaceVelocity() = (MRF.faceU() + MRFTrans.faceU()) & Sf/magSf and flux.MRFOmega() of mesh `m`
+        (outerLoop.H:18-21; host set-up, src/cfdTools/MRFCoupled/MRFCoupledZone.C faceU / omega)."""
+        omega, origin, vel, zone = self.mrf
+        faceU = np.cross(omega, m.Cf - origin) + vel
+        om = np.tile(omega, (m.n_cells, 1))
+        if zone is not None:
+            faceU[~zone(m.Cf)] = 0.0
+            om[~zone(m.C)] = 0.0
+        fv = (faceU * (m.Sf / m.magSf[:, None])).sum(1)
+        for p in m.patches:
+            if p["kind"] == capi.EMPTY:
+                fv[p["start"]:p["start"] + p["size"]] = 0.0
+        return np.ascontiguousarray(fv), np.ascontiguousarray(om)
 
     def apply(self, api, mesh=None, cells=None):
         """Configure `api` with this case.  `mesh`/`cells` select a partition (cells = global cell ids)."""
@@ -34,6 +56,8 @@ class Case:
                 continue
             for field, (kind, params) in fields.items():
                 api.bc_set(patch, {"p": capi.FIELD_P, "U": capi.FIELD_U, "T": capi.FIELD_T}[field], kind, params)
+        if self.mrf is not None:
+            api.mrf_set(*self.mrf_fields(m))
         if cells is None:
             api.state_set(self.p, self.U, self.T)
         else:

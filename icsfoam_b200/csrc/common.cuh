@@ -148,6 +148,10 @@ struct icsb200_ctx {
     bool reconValid = false;                                          // d_faceRecon belongs to the current state and schemes
     double* d_gradE = nullptr;                                        // [3*NPH] gradient of eCalc (viscous runs only)
     double* d_visc = nullptr;                                         // [8*NP] per-row viscous divergences: lapU(3) divTau(3) divSigmaU lapE
+    // MRF (icsb200_mrf_set): flux.MRFFaceVelocity() in GPU face order and flux.MRFOmega() by position; null = zero field
+    double* d_mrfFace = nullptr;                                      // [NFG]
+    double* d_mrfOmega = nullptr;                                     // [3*NP]
+    bool srcMrfApplied = false;                                       // addMRFSource's Coriolis term is already in d_src
     int* d_bad = nullptr;                                              // [NPH] boundLocalTimeStep flags
     // ---- matrix ----
     double* d_offd = nullptr;  // [nEntries*25*32]
@@ -273,6 +277,7 @@ int ics_copy_prev(icsb200_ctx* c);
 int ics_state_from_primitives(icsb200_ctx* c);
 int ics_allreduce_max_int(icsb200_ctx* c, int* d, int n);
 // hb.cu
+int ics_mrf_source(icsb200_ctx* c);       // src(rhoU) -= (Omega ^ rho U) V, once per residual evaluation (jacobian.cu)
 int ics_hb_source(icsb200_ctx* c);        // src += HB source (after the flux residual)
 int ics_hb_diag(icsb200_ctx* c);          // diag += V D[J][J] (after the Jacobian)
 int ics_hb_rdiag(icsb200_ctx* c);         // shared lusgs rDiagCoeff over all instances

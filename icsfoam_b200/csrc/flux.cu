@@ -66,14 +66,15 @@ struct Flux5 { double phi; V3 phiUp; double phiEp; };
 struct SchemePrm { double gamma, entropyFix; int lowMach; };
 
 // ---- HLLC (hllcFluxScheme.C:125-238) ----
-__device__ __forceinline__ Flux5 fluxHLLC(const FaceState& s, V3 Sf, double magSf, const SchemePrm& pr)
+__device__ __forceinline__ Flux5 fluxHLLC(const FaceState& s, V3 Sf, double magSf, double mrf, const SchemePrm& pr)
 {
     const V3 n = Sf / magSf;
     const double coefR = sqrt(fmax(ICS_VSMALL, s.rho_r) / fmax(ICS_VSMALL, s.rho_l));
     const V3 uAvg = (coefR * s.U_r + s.U_l) / (coefR + 1.0);
     const double HAvg = (coefR * s.H_r + s.H_l) / (coefR + 1.0);
     const double cAvg = sqrt(fabs((pr.gamma - 1.0) * (HAvg - 0.5 * magSqr(uAvg))));
-    const double uMag_l = dot(s.U_l, n), uMag_r = dot(s.U_r, n), uMagAvg = dot(uAvg, n);
+    // contravariant velocities relative to the frame: -= MRFFaceVelocity (hllcFluxScheme.C:157-161)
+    const double uMag_l = dot(s.U_l, n) - mrf, uMag_r = dot(s.U_r, n) - mrf, uMagAvg = dot(uAvg, n) - mrf;
     const double Sl = fmin(uMag_l - s.c_l, uMagAvg - cAvg);
     const double Sr = fmax(uMag_r + s.c_r, uMagAvg + cAvg);
     const double Sm = (s.rho_r * uMag_r * (Sr - uMag_r) - s.rho_l * uMag_l * (Sl - uMag_l) + s.p_l - s.p_r) /
@@ -99,8 +100,8 @@ __device__ __forceinline__ Flux5 fluxHLLC(const FaceState& s, V3 Sf, double magS
     {
         const double rhoEStar_l = 1.0 / (Sl - Sm) * ((Sl - uMag_l) * (s.rho_l * s.E_l) - s.p_l * uMag_l + pStar_l * Sm);
         const double rhoEStar_r = 1.0 / (Sr - Sm) * ((Sr - uMag_r) * (s.rho_r * s.E_r) - s.p_r * uMag_r + pStar_r * Sm);
-        const double fl = Sm * (rhoEStar_l + pStar_l);
-        const double fr = Sm * (rhoEStar_r + pStar_r);
+        const double fl = Sm * (rhoEStar_l + pStar_l) + pStar_l * mrf;  // hllcFluxScheme.C:217-218
+        const double fr = Sm * (rhoEStar_r + pStar_r) + pStar_r * mrf;
         F.phiEp = (coefSl * s.rho_l * s.H_l * uMag_l + coefSlm * fl + coefSmr * fr + coefSr * s.rho_r * s.H_r * uMag_r) * magSf;
     }
     return F;
@@ -120,7 +121,7 @@ __device__ __forceinline__ T9 mulTT(const T9& a, const T9& b)
             a.zx * b.xx + a.zy * b.yx + a.zz * b.zx, a.zx * b.xy + a.zy * b.yy + a.zz * b.zy, a.zx * b.xz + a.zy * b.yz + a.zz * b.zz};
 }
 
-__device__ __forceinline__ Flux5 fluxROE(const FaceState& s, V3 Sf, double magSf, const SchemePrm& pr)
+__device__ __forceinline__ Flux5 fluxROE(const FaceState& s, V3 Sf, double magSf, double mrf, const SchemePrm& pr)
 {
     const V3 n = Sf / magSf;
     const double coefR = sqrt(fmax(ICS_VSMALL, s.rho_r) / fmax(ICS_VSMALL, s.rho_l));
@@ -129,7 +130,7 @@ __device__ __forceinline__ Flux5 fluxROE(const FaceState& s, V3 Sf, double magSf
     const double HT = (coefR * s.H_r + s.H_l) / (coefR + 1.0);
     const double cT = sqrt(fabs((pr.gamma - 1.0) * (HT - 0.5 * magSqr(uT))));
     const double uMag_l = dot(s.U_l, n), uMag_r = dot(s.U_r, n);
-    const double uProj = dot(uT, n);
+    const double uProj = dot(uT, n) - mrf;  // uProjRoe -= MRFFaceVelocity (roeFluxScheme.C:363)
     const V3 rhoU_l = s.rho_l * s.U_l, rhoU_r = s.rho_r * s.U_r;
     const double rhoE_l = s.rho_l * s.E_l, rhoE_r = s.rho_r * s.E_r;
     // eigen-decomposition in conservative variables
@@ -194,13 +195,17 @@ __device__ __forceinline__ Flux5 fluxROE(const FaceState& s, V3 Sf, double magSf
     F.phi += 0.5 * magSf * (rhoUNorm_l + rhoUNorm_r);
     F.phiUp = F.phiUp + (0.5 * magSf) * (rhoUNorm_l * s.U_l + rhoUNorm_r * s.U_r + n * (s.p_l + s.p_r));
     F.phiEp += 0.5 * magSf * (rhoUNorm_l * s.H_l + rhoUNorm_r * s.H_r);
+    // roeFluxScheme.C:406-408
+    F.phi -= 0.5 * magSf * mrf * (s.rho_l + s.rho_r);
+    F.phiUp = F.phiUp - (0.5 * magSf * mrf) * (rhoU_l + rhoU_r);
+    F.phiEp -= 0.5 * magSf * mrf * (rhoE_l + rhoE_r);
     return F;
 }
 
 // ---- AUSM+up (ausmPlusUpFluxScheme.C:93-292) ----
-__device__ __forceinline__ Flux5 fluxAUSM(const FaceState& s, V3 Sf, double magSf, const SchemePrm& pr)
+__device__ __forceinline__ Flux5 fluxAUSM(const FaceState& s, V3 Sf, double magSf, double mrf, const SchemePrm& pr)
 {
-    const double un_L = dot(s.U_l, Sf) / magSf, un_R = dot(s.U_r, Sf) / magSf;
+    const double un_L = dot(s.U_l, Sf) / magSf - mrf, un_R = dot(s.U_r, Sf) / magSf - mrf;  // ausmPlusUpFluxScheme.C:101-102
     const double c_L = sqr(s.c_l) / fmax(s.c_l, un_L);
     const double c_R = sqr(s.c_r) / fmax(s.c_r, -un_R);
     const double c_face = fmin(c_L, c_R);
@@ -238,16 +243,16 @@ __device__ __forceinline__ Flux5 fluxAUSM(const FaceState& s, V3 Sf, double magS
     Flux5 F;
     F.phi = rhoa * magSf;
     F.phiUp = rhoaU * magSf + p12 * Sf;
-    F.phiEp = rhoah * magSf;
+    F.phiEp = rhoah * magSf + p12 * mrf * magSf;  // ausmPlusUpFluxScheme.C:293
     return F;
 }
 
 template <int SCHEME>
-__device__ __forceinline__ Flux5 faceFlux(const FaceState& s, V3 Sf, double magSf, const SchemePrm& pr)
+__device__ __forceinline__ Flux5 faceFlux(const FaceState& s, V3 Sf, double magSf, double mrf, const SchemePrm& pr)
 {
-    if (SCHEME == ICSB200_FLUX_HLLC) return fluxHLLC(s, Sf, magSf, pr);
-    if (SCHEME == ICSB200_FLUX_ROE) return fluxROE(s, Sf, magSf, pr);
-    return fluxAUSM(s, Sf, magSf, pr);
+    if (SCHEME == ICSB200_FLUX_HLLC) return fluxHLLC(s, Sf, magSf, mrf, pr);
+    if (SCHEME == ICSB200_FLUX_ROE) return fluxROE(s, Sf, magSf, mrf, pr);
+    return fluxAUSM(s, Sf, magSf, mrf, pr);
 }
 
 // ------------------------------------------------------------------------------------------------ k_grad
@@ -313,6 +318,7 @@ struct FluxArgs {
     double* recon;                     // [8*NFG] limited U_l U_r E_l E_r per face, reused by the Jacobian kernel
     double* phiB;                      // [NB]
     const double* visc;                // [8*NP] viscous divergences (already divided by V) or null
+    const double* mrf;                 // [NFG] MRFFaceVelocity in GPU face order or null (zero field)
 };
 
 // reconstruct all NQ scalars of one face.  rowIsOwner: the row cell is the face's owner (P)
@@ -369,7 +375,8 @@ k_flux_faces(FluxArgs a)
         reconstructFace(a, p, c, type, g, b, needC, s);
         const V3 Sf = {a.geo[G_SFX * a.NFG + g], a.geo[G_SFY * a.NFG + g], a.geo[G_SFZ * a.NFG + g]};
         const double magSf = a.geo[G_MAGSF * a.NFG + g];
-        const Flux5 F = faceFlux<SCHEME>(s, Sf, magSf, a.sp);
+        const double mrf = a.mrf ? a.mrf[g] : 0.0;
+        const Flux5 F = faceFlux<SCHEME>(s, Sf, magSf, mrf, a.sp);
         a.faceFlux[g] = F.phi; a.faceFlux[a.NFG + g] = F.phiUp.x; a.faceFlux[2 * a.NFG + g] = F.phiUp.y;
         a.faceFlux[3 * a.NFG + g] = F.phiUp.z; a.faceFlux[4 * a.NFG + g] = F.phiEp;
         if (type == ET_PHYS) a.phiB[b] = F.phi;
@@ -667,6 +674,7 @@ int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
     a.faceFlux = c->d_faceFlux;
     a.recon = c->d_faceRecon;
     a.phiB = c->d_phiB;
+    a.mrf = c->d_mrfFace;
     a.visc = nullptr;
     if (c->mu > 0) {  // if (!inviscid)  (createFields.H:37-45)
         if (!c->d_visc) { int r = devAlloc(c, &c->d_visc, (size_t)8 * c->NP); if (r) return r; }
@@ -695,6 +703,7 @@ int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
     CUDA_TRY(c, cudaGetLastError());
     c->fluxValid = true;
     c->reconValid = true;
+    c->srcMrfApplied = false;
     return ics_hb_source(c);  // Harmonic Balance: sources += -V sum_K D[J][K] W_K
 }
 

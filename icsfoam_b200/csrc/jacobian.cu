@@ -53,6 +53,7 @@ struct JacArgs {
     const double* src;    // unused here (sources live in d_src)
     double *offd, *diag, *rD, *rdt, *ddtCoeff;
     const double* recon;  // [8*NFG] limited face states stored by k_flux_faces (REUSE instantiation)
+    const double *mrf, *mrfOmega;  // MRFFaceVelocity [NFG] (GPU face order) and MRFOmega [3*NP]; null = zero field
 };
 
 // analytic Euler flux Jacobian d(F.n)/dW at state (U, E) — convectiveFluxScheme.C:402-464
@@ -92,7 +93,7 @@ k_jac(JacArgs a)
     const int nAll = a.rowNAll[p];
     const bool lim4U = a.limU == ICSB200_LIM_VANLEER || a.limU == ICSB200_LIM_MINMOD;
     const bool lim4T = a.limT == ICSB200_LIM_VANLEER || a.limT == ICSB200_LIM_MINMOD;
-    double conv[25], dissAcc = 0.0, viscAcc = 0.0, rdt = 0.0;
+    double conv[25], dissAcc = 0.0, viscAcc = 0.0, mrfAcc = 0.0, rdt = 0.0;
 #pragma unroll
     for (int k = 0; k < 25; k++) conv[k] = 0.0;
     bool hasPhys = false;
@@ -107,16 +108,17 @@ k_jac(JacArgs a)
         const double magSf = a.geo[G_MAGSF * a.NFG + g];
         const V3 n = Sf / magSf;
         double* blk = a.offd + ((base + j) * 25) * 32 + lane;
+        const double mrf = a.mrf ? a.mrf[g] : 0.0;  // flux.MRFFaceVelocity() of this face
         if (type == ET_PHYS) {
             hasPhys = true;
             // lambdaConv boundary value: c_b + |U_b & n|  (interpolate() returns the patch value)
             const V3 Ub = {a.f[(size_t)Q_UX * a.NX + c], a.f[(size_t)Q_UY * a.NX + c], a.f[(size_t)Q_UZ * a.NX + c]};
-            const double lam = a.f[(size_t)Q_C * a.NX + c] + fabs(dot(Ub, n) - 0.0);
+            const double lam = a.f[(size_t)Q_C * a.NX + c] + fabs(dot(Ub, n) - mrf);
             const double dl = 0.5 * magSf * lam;
             dissAcc -= dl;  // mx.diag[own] -= interfacesLower (physical boundaries included, blockFvMatrix.C:310-321)
             if (a.bfKind[b] == ICSB200_WALL) {
                 // setCoAndDeltaT.H:87-138: wall patches use the cell state with a factor 1/2
-                const double pLambda = 0.5 * a.geo[G_NONORTH * a.NFG + g] * (cOwn + fabs(dot(UOwn, n) - 0.0));
+                const double pLambda = 0.5 * a.geo[G_NONORTH * a.NFG + g] * (cOwn + fabs(dot(UOwn, n) - mrf));
                 rdt = fmax(rdt, pLambda);
             }
 #pragma unroll
@@ -170,7 +172,16 @@ k_jac(JacArgs a)
                 cf = w * (cP - cN) + cN;
                 uf = {w * (UP.x - UN.x) + UN.x, w * (UP.y - UN.y) + UN.y, w * (UP.z - UN.z) + UN.z};
             }
-            lam = cf + fabs(dot(uf, n) - 0.0);
+            lam = cf + fabs(dot(uf, n) - mrf);
+        }
+        // MRFdivMeshPhi = fvj::div(w, MRFFaceVelocity*magSf) (convectiveFluxScheme.C:477-481, blockFvOperatorsTemplates.C:146-201):
+        // upper = sf (1 - w), lower = -sf w, negSumDiag; subtracted from the three diagonal-variable blocks
+        double mrfOff = 0.0;
+        if (a.mrf) {
+            const double sfm = mrf * magSf;
+            const double mU = sfm * (1 - w), mL = -sfm * w;
+            if (rowIsP) { mrfOff = mU; mrfAcc -= mL; }
+            else { mrfOff = mL; mrfAcc -= mU; }
         }
         rdt = fmax(rdt, a.geo[G_NONORTH * a.NFG + g] * lam);
         const double dl = 0.5 * magSf * lam;
@@ -195,7 +206,7 @@ k_jac(JacArgs a)
             double off;
             if (rowIsP) { off = hasConv ? (0.0 + upp) : 0.0; if (hasConv) conv[k] -= low; }
             else { off = hasConv ? (0.0 + low) : 0.0; if (hasConv) conv[k] -= upp; }
-            if (isDiagEntry(k)) { off -= dl; if (a.mu > 0) off -= sf2 * 1.0; }
+            if (isDiagEntry(k)) { if (a.mrf) off -= mrfOff * 1.0; off -= dl; if (a.mu > 0) off -= sf2 * 1.0; }
             blk[(size_t)k * 32] = off;
         }
     }
@@ -215,7 +226,7 @@ k_jac(JacArgs a)
 #pragma unroll
     for (int k = 0; k < 25; k++) {
         dg[k] = 0.0 + conv[k];
-        if (isDiagEntry(k)) dg[k] -= dissAcc;
+        if (isDiagEntry(k)) { if (a.mrf) dg[k] -= mrfAcc * 1.0; dg[k] -= dissAcc; }
     }
     if (hasPhys) {
         const double rhoI = a.f[(size_t)Q_RHO * a.NX + p];
@@ -244,7 +255,7 @@ k_jac(JacArgs a)
             const double rhoB = a.f[(size_t)Q_RHO * a.NX + c], pB = a.f[(size_t)Q_P * a.NX + c], TB = a.f[(size_t)Q_T * a.NX + c];
             const V3 UB = {a.f[(size_t)Q_UX * a.NX + c], a.f[(size_t)Q_UY * a.NX + c], a.f[(size_t)Q_UZ * a.NX + c]};
             double UrelBdotSf = dot(UB, SfB);
-            UrelBdotSf -= 0.0 * a.geo[G_MAGSF * a.NFG + g];
+            UrelBdotSf -= (a.mrf ? a.mrf[g] : 0.0) * a.geo[G_MAGSF * a.NFG + g];
             const double rhoEB = rhoB * (a.Cv * TB + 0.5 * magSqr(UB));
             const double cvB = a.Cv;
             // boundaryJacobian (convectiveFluxScheme.C:96-117)
@@ -307,6 +318,10 @@ k_jac(JacArgs a)
     }
     const double diagCoeff = ddtCoeff * vol;
     dg[0] += diagCoeff; dg[6] += diagCoeff * 1.0; dg[12] += diagCoeff * 1.0; dg[18] += diagCoeff * 1.0; dg[24] += diagCoeff;
+    if (a.mrfOmega) {  // addMRFSource, diagonal part (convectiveFluxScheme.C:130-137)
+        const double ox = a.mrfOmega[p], oy = a.mrfOmega[(size_t)a.NP + p], oz = a.mrfOmega[2 * (size_t)a.NP + p];
+        dg[7] -= oz * vol; dg[8] += oy * vol; dg[11] += oz * vol; dg[13] -= ox * vol; dg[16] -= oy * vol; dg[17] += ox * vol;
+    }
     if (a.mu > 0) { dg[0] -= viscAcc * 1.0; dg[6] -= viscAcc * 1.0; dg[12] -= viscAcc * 1.0; dg[18] -= viscAcc * 1.0; dg[24] -= viscAcc * 1.0; }
 #pragma unroll
     for (int k = 0; k < 25; k++) a.diag[(size_t)k * a.NP + p] = dg[k];
@@ -323,7 +338,8 @@ k_jac(JacArgs a)
 // non-local time stepping: max over faces of deltaCoeffs*lambda (setCoAndDeltaT.H:143-146)
 __global__ void k_lambda_max(int NP, const int* __restrict__ pos2cell, const int* __restrict__ sliceOff, const int* __restrict__ rowNAll,
                              const int* __restrict__ rowNLow, const int* __restrict__ col, const int* __restrict__ meta, const int* __restrict__ gfid,
-                             const double* __restrict__ geo, size_t NFG, const double* __restrict__ f, size_t NX, unsigned long long* __restrict__ out)
+                             const double* __restrict__ geo, size_t NFG, const double* __restrict__ f, size_t NX, const double* __restrict__ mrf,
+                             unsigned long long* __restrict__ out)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     double mx = 0.0;
@@ -344,7 +360,7 @@ __global__ void k_lambda_max(int NP, const int* __restrict__ pos2cell, const int
             if (type == ET_PHYS) { cf = cN; uf = UN; }
             else if (type == ET_COUPLED) { cf = w * cP + (1.0 - w) * cN; uf = {w * UP.x + (1.0 - w) * UN.x, w * UP.y + (1.0 - w) * UN.y, w * UP.z + (1.0 - w) * UN.z}; }
             else { cf = w * (cP - cN) + cN; uf = {w * (UP.x - UN.x) + UN.x, w * (UP.y - UN.y) + UN.y, w * (UP.z - UN.z) + UN.z}; }
-            mx = fmax(mx, geo[G_DELTA * NFG + g] * (cf + fabs(dot(uf, n) - 0.0)));
+            mx = fmax(mx, geo[G_DELTA * NFG + g] * (cf + fabs(dot(uf, n) - (mrf ? mrf[g] : 0.0))));
         }
     }
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -437,7 +453,7 @@ int ics_jacobian(icsb200_ctx* c, bool useStoredRdt)
         {
             LaunchScope ls(c, TM_JAC);
             k_lambda_max<<<gridFor(c->NP, 128), 128, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_sliceOff, c->d_rowNAll, c->d_rowNLow, c->d_col, c->d_meta,
-                                                                    c->d_gfid, c->d_geo, c->NFG, c->d_fields, c->NX, d_max);
+                                                                    c->d_gfid, c->d_geo, c->NFG, c->d_fields, c->NX, c->d_mrfFace, d_max);
         }
         double mx = 0.0;
         CUDA_TRY(c, cudaMemcpyAsync(&mx, d_max, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -448,6 +464,7 @@ int ics_jacobian(icsb200_ctx* c, bool useStoredRdt)
     {
         LaunchScope ls(c, TM_JAC);
         a.recon = c->d_faceRecon;
+        a.mrf = c->d_mrfFace; a.mrfOmega = c->d_mrfOmega;
         if (c->reconValid && c->d_faceRecon) k_jac<true><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(a);
         else k_jac<false><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(a);
     }
@@ -455,7 +472,41 @@ int ics_jacobian(icsb200_ctx* c, bool useStoredRdt)
     c->matrixSet = true;
     c->rDValid = true;
     c->invDValid = false;
+    int r = ics_mrf_source(c);
+    if (r) return r;
     if (c->hbNO > 1) return ics_hb_diag(c);  // HB.addBlock(J,J) + the shared lusgs diagonal
+    return 0;
+}
+
+// addMRFSource, source part (convectiveFluxScheme.C:125-128): dVByV(0,0).source() -= (MRFOmega ^ (rho U)) V.  The reference
+// applies it to the fresh eqSystem of every outer iteration; here the sources live in d_src from the residual evaluation
+// to the solve, so the flag keeps a repeated assemble() from subtracting it twice.
+namespace {
+__global__ void k_mrf_source(int NP, const int* __restrict__ pos2cell, const double* __restrict__ omega, const double* __restrict__ f, size_t NX,
+                             const double* __restrict__ V, double* __restrict__ src, size_t NPH)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= NP || pos2cell[p] < 0) return;
+    const double ox = omega[p], oy = omega[(size_t)NP + p], oz = omega[2 * (size_t)NP + p];
+    const double rho = f[(size_t)Q_RHO * NX + p];
+    const double rux = rho * f[(size_t)Q_UX * NX + p], ruy = rho * f[(size_t)Q_UY * NX + p], ruz = rho * f[(size_t)Q_UZ * NX + p];
+    const double cx = oy * ruz - oz * ruy, cy = oz * rux - ox * ruz, cz = ox * ruy - oy * rux;
+    const double vol = V[p];
+    src[NPH + p] -= cx * vol;
+    src[2 * NPH + p] -= cy * vol;
+    src[3 * NPH + p] -= cz * vol;
+}
+}  // namespace
+
+int ics_mrf_source(icsb200_ctx* c)
+{
+    if (!c->d_mrfOmega || c->srcMrfApplied) return 0;
+    {
+        LaunchScope ls(c, TM_JAC);
+        k_mrf_source<<<gridFor(c->NP, 256), 256, 0, c->stream>>>(c->NP, c->d_pos2cell, c->d_mrfOmega, c->d_fields, c->NX, c->d_V, c->d_src, c->NPH);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    c->srcMrfApplied = true;
     return 0;
 }
 
@@ -542,6 +593,39 @@ extern "C" int icsb200_source_set(icsb200_ctx* c, const double* sRho, const doub
     if ((r = ics_upload_cells(c, sRhoU, 3, c->d_src + c->NPH, c->NPH))) return r;
     if ((r = ics_upload_cells(c, sRhoE, 1, c->d_src + 4 * (size_t)c->NPH, c->NPH))) return r;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->srcMrfApplied = true;  // caller-provided sources are final (they already carry addMRFSource's term)
+    return 0;
+}
+
+extern "C" int icsb200_source_get(icsb200_ctx* c, double* sRho, double* sRhoU, double* sRhoE)
+{
+    if (!c->meshSet) return ics_fail(c, ICSB200_ESTATE, "source_get: mesh not set");
+    int r = 0;
+    if (sRho && (r = ics_download_cells(c, sRho, 1, c->d_src, c->NPH))) return r;
+    if (sRhoU && (r = ics_download_cells(c, sRhoU, 3, c->d_src + c->NPH, c->NPH))) return r;
+    if (sRhoE && (r = ics_download_cells(c, sRhoE, 1, c->d_src + 4 * (size_t)c->NPH, c->NPH))) return r;
+    return 0;
+}
+
+// flux.MRFFaceVelocity() / flux.MRFOmega() as the solver sets them every outer iteration (outerLoop.H:18-21)
+extern "C" int icsb200_mrf_set(icsb200_ctx* c, const double* mrf_face_velocity, const double* mrf_omega)
+{
+    if (!c->meshSet) return ics_fail(c, ICSB200_ESTATE, "mrf_set: mesh not set");
+    cudaSetDevice(c->device);
+    int r;
+    if (mrf_face_velocity) {
+        std::vector<double> h((size_t)c->NFG);
+        for (int g = 0; g < c->NFG; g++) h[g] = mrf_face_velocity[c->h_gf2ref[g]];
+        if ((r = devUpload(c, &c->d_mrfFace, h))) return r;
+    } else if ((r = devAlloc(c, &c->d_mrfFace, 0))) return r;
+    if (mrf_omega) {
+        if (!c->d_mrfOmega && (r = devAlloc(c, &c->d_mrfOmega, (size_t)3 * c->NP))) return r;
+        CUDA_TRY(c, cudaMemsetAsync(c->d_mrfOmega, 0, sizeof(double) * 3 * c->NP, c->stream));
+        if ((r = ics_upload_cells(c, mrf_omega, 3, c->d_mrfOmega, c->NP))) return r;
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    } else if ((r = devAlloc(c, &c->d_mrfOmega, 0))) return r;
+    c->fluxValid = false;  // fluxes, sources and matrix of the previous frame velocity are stale
+    c->matrixSet = false;
     return 0;
 }
 

@@ -132,6 +132,18 @@ int icsb200_schemes_set(icsb200_ctx* ctx, const icsb200_schemes* s);
 /* fvPatchField of p, U or T on one patch (0/p, 0/U, 0/T boundaryField entries) */
 int icsb200_bc_set(icsb200_ctx* ctx, int patch, int field, int kind, const double* params, int n_params);
 
+/* Multiple reference frames: the two fields the solver hands to the flux scheme every outer iteration
+ * (applications/solvers/dbnsFoam/outerLoop.H:18-21): mrf_face_velocity[n_faces] = flux.MRFFaceVelocity() =
+ * (MRF.faceU() + MRFTrans.faceU()) & Sf/magSf, in each face's own orientation (boundary faces outward), and
+ * mrf_omega[3*n_cells] = flux.MRFOmega().  NULL = zero field (the default).  They enter the three flux schemes
+ * (hllcFluxScheme.C:157-161,217-218; roeFluxScheme.C:362-363,404-408; ausmPlusUpFluxScheme.C:101-102,293), the spectral
+ * radius of the pseudo time step and of the dissipation Jacobian (setCoAndDeltaT.H:39-55,97-125;
+ * convectiveFluxScheme.C:498-524), the boundary Jacobian (convectiveFluxScheme.C:94), the fvj::div(w, MRFFaceVelocity
+ * magSf) blocks (convectiveFluxScheme.C:477-481; blockFvOperatorsTemplates.C:146-201) and addMRFSource
+ * (convectiveFluxScheme.C:123-139: Coriolis source and the skew momentum-diagonal entries).  MRF zone set-up
+ * (MRFCoupledZone faceU/omega, correctBoundaryVelocity) stays on the host.  Call after icsb200_mesh_set. */
+int icsb200_mrf_set(icsb200_ctx* ctx, const double* mrf_face_velocity, const double* mrf_omega);
+
 /* ---- state --------------------------------------------------------------------------------- */
 /* internal fields p[N], U[3N], T[N]; evaluates BCs + thermo and builds rho, rhoU, rhoE (createFields.H:75-131) */
 int icsb200_state_set(icsb200_ctx* ctx, const double* p, const double* U, const double* T);
@@ -163,6 +175,8 @@ int icsb200_matrix_get_ldu(icsb200_ctx* ctx, int block, double* diag, double* up
 int icsb200_matrix_set_ldu(icsb200_ctx* ctx, int block, const double* diag, const double* upper, const double* lower);
 /* sources of the three equations (dSByS(0,0), dVByV(0,0), dSByS(1,1) .source(); residualsUpdate.H:81-83) */
 int icsb200_source_set(icsb200_ctx* ctx, const double* sRho, const double* sRhoU, const double* sRhoE);
+/* the sources the solver sees: R*V (+ HB source, + the MRF Coriolis term after icsb200_assemble); NULL skips */
+int icsb200_source_get(icsb200_ctx* ctx, double* sRho, double* sRhoU, double* sRhoE);
 /* coupledMatrix::matrixMul (coupledMatrix.C:66-123): y = A x for x = (rho[N], rhoU[3N], rhoE[N]) */
 int icsb200_matrix_mul(icsb200_ctx* ctx, const double* xRho, const double* xRhoU, const double* xRhoE, double* yRho,
                        double* yRhoU, double* yRhoE);

@@ -111,6 +111,11 @@ struct Ctx {
     // Roe dissipation members (roeFluxScheme.H:61-71) are temporaries here
     // cyclicAMI tables handed over by orc_ami_set before orc_mesh_set: patch -> (start, face, weight)
     std::vector<std::pair<int, Patch>> pendingAmi;
+    // MRF (convectiveFluxScheme.H MRFFaceVelocity_/MRFOmega_, set by the solver at outerLoop.H:18-21): frame velocity
+    // normal to each face [FT] (face orientation) and frame angular velocity per cell [3N]; empty = zero fields
+    vecd mrfFaceVel, mrfOmega;
+    bool srcMrfApplied = false;  // the Coriolis source has been subtracted from the current srcRhoU
+    double mrfAt(int f) const { return mrfFaceVel.empty() ? 0.0 : mrfFaceVel[f]; }
     std::string err;
 };
 

@@ -257,6 +257,26 @@ int orc_source_set(Ctx* c, const double* sRho, const double* sRhoU, const double
 {
     const int N = c->m.N;
     c->srcRho.assign(sRho, sRho + N); c->srcRhoU.assign(sRhoU, sRhoU + 3 * (size_t)N); c->srcRhoE.assign(sRhoE, sRhoE + N);
+    c->srcMrfApplied = true;  // caller-provided sources are final (they already carry addMRFSource's term)
+    return 0;
+}
+
+int orc_source_get(Ctx* c, double* sRho, double* sRhoU, double* sRhoE)
+{
+    const int N = c->m.N;
+    if ((int)c->srcRho.size() != N) return fail(c, ICSB200_ESTATE, "no sources yet");
+    if (sRho) std::memcpy(sRho, c->srcRho.data(), sizeof(double) * N);
+    if (sRhoU) std::memcpy(sRhoU, c->srcRhoU.data(), sizeof(double) * 3 * N);
+    if (sRhoE) std::memcpy(sRhoE, c->srcRhoE.data(), sizeof(double) * N);
+    return 0;
+}
+
+// flux.MRFFaceVelocity() [n_faces] and flux.MRFOmega() [3*n_cells] (outerLoop.H:18-21); NULL = zero field
+int orc_mrf_set(Ctx* c, const double* mrf_face_velocity, const double* mrf_omega)
+{
+    if (!c->meshSet) return fail(c, ICSB200_ESTATE, "mesh not set");
+    if (mrf_face_velocity) c->mrfFaceVel.assign(mrf_face_velocity, mrf_face_velocity + c->m.FT); else c->mrfFaceVel.clear();
+    if (mrf_omega) c->mrfOmega.assign(mrf_omega, mrf_omega + 3 * (size_t)c->m.N); else c->mrfOmega.clear();
     return 0;
 }
 

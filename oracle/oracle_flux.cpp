@@ -306,7 +306,7 @@ void calcFlux(Ctx& c)
         V3 Sf = {m.Sf[3 * f], m.Sf[3 * f + 1], m.Sf[3 * f + 2]};
         double phi, phiEp;
         V3 phiUp;
-        const double mrf = 0.0;  // MRFFaceVelocity: zero in every shipped case (out of scope)
+        const double mrf = c.mrfAt(f);  // flux.MRFFaceVelocity() (outerLoop.H:18-21)
         if (scheme == ICSB200_FLUX_HLLC) fluxHLLC(c, s, Sf, m.magSf[f], mrf, phi, phiUp, phiEp);
         else if (scheme == ICSB200_FLUX_ROE) fluxROE(c, s, Sf, m.magSf[f], mrf, phi, phiUp, phiEp);
         else fluxAUSM(c, s, Sf, m.magSf[f], mrf, phi, phiUp, phiEp);
@@ -538,6 +538,7 @@ void residualsUpdate(Ctx& c)
         for (int d = 0; d < 3; d++) c.srcRhoU[3 * (size_t)i + d] = rhoUR[3 * (size_t)i + d] * m.V[i];
         c.srcRhoE[i] = rhoER[i] * m.V[i];
     }
+    c.srcMrfApplied = false;
 }
 
 // lambda = interpolate(sqrt(gamma/psi)) + mag((interpolate(U) & Sf/magSf) - MRFFaceVelocity)
@@ -560,7 +561,7 @@ static void spectralRadius(Ctx& c, vecd& lambda)
         if (!faceActive(m, f, em)) continue;
         V3 nn = V3{m.Sf[3 * f], m.Sf[3 * f + 1], m.Sf[3 * f + 2]} / m.magSf[f];
         V3 u = {uf[0][f], uf[1][f], uf[2][f]};
-        lambda[f] = cf[f] + std::fabs((u & nn) - 0.0);
+        lambda[f] = cf[f] + std::fabs((u & nn) - c.mrfAt(f));
     }
 }
 
@@ -611,7 +612,7 @@ void pseudoDeltaT(Ctx& c)
                     int o = m.owner[f];
                     V3 nn = V3{m.Sf[3 * f], m.Sf[3 * f + 1], m.Sf[3 * f + 2]} / m.magSf[f];
                     V3 u = {c.U[3 * (size_t)o], c.U[3 * (size_t)o + 1], c.U[3 * (size_t)o + 2]};
-                    double pLambda = 0.5 * m.nonOrthDeltaCoeffs[f] * (std::sqrt(c.gamma / c.psi[o]) + std::fabs((u & nn) - 0.0));
+                    double pLambda = 0.5 * m.nonOrthDeltaCoeffs[f] * (std::sqrt(c.gamma / c.psi[o]) + std::fabs((u & nn) - c.mrfAt(f)));
                     c.rPseudoDeltaT[o] = std::max(c.rPseudoDeltaT[o], pLambda);
                 }
             }
@@ -750,6 +751,26 @@ void subtractLaplacianOne(const Mesh& m, Blk& A, const vecd& sf, std::initialize
     }
 }
 
+// fvj::div(w, sf) for a face scalar already dotted with Sf (blockFvOperatorsTemplates.C:146-201), then A -= mx [* I]
+void subtractDivFace(const Mesh& m, Blk& A, const vecd& sf, std::initializer_list<int> pattern)
+{
+    const int nc = A.nc;
+    vecd upp(m.F), low(m.F), diag(m.N, 0.0), iu(m.NB, 0.0), il(m.NB, 0.0);
+    for (int f = 0; f < m.F; f++) { upp[f] = sf[f] * (1 - m.w[f]); low[f] = -sf[f] * m.w[f]; }
+    for (int f = 0; f < m.F; f++) { diag[m.owner[f]] -= low[f]; diag[m.neighbour[f]] -= upp[f]; }
+    for (auto& p : m.patches) {
+        if (m.empty(p)) continue;
+        for (int f = p.start; f < p.start + p.size; f++) { iu[f - m.F] = sf[f] * (1 - m.w[f]); il[f - m.F] = -sf[f] * m.w[f]; }
+        if (m.coupled(p)) for (int f = p.start; f < p.start + p.size; f++) diag[m.owner[f]] -= il[f - m.F];
+    }
+    ensureOff(A, m);
+    for (int k : pattern) {
+        for (int i = 0; i < m.N; i++) A.diag[(size_t)nc * i + k] -= diag[i] * 1.0;
+        for (int f = 0; f < m.F; f++) { A.upper[(size_t)nc * f + k] -= upp[f] * 1.0; A.lower[(size_t)nc * f + k] -= low[f] * 1.0; }
+        for (int b = 0; b < m.NB; b++) { A.intUpper[(size_t)nc * b + k] -= iu[b] * 1.0; A.intLower[(size_t)nc * b + k] -= il[b] * 1.0; }
+    }
+}
+
 }  // namespace
 
 // convectiveFluxScheme::createConvectiveJacobian + viscousFluxScheme::createViscousJacobian (LF branch)
@@ -808,7 +829,15 @@ void createJacobian(Ctx& c)
     insertBlock(m, dEnergyByRho, enRho_l, enRho_r);
     insertBlock(m, dEnergyByRhoU, enRhoU_l, enRhoU_r);
     insertBlock(m, dEnergyByRhoE, enRhoE_l, enRhoE_r);
-    // (moving-mesh and MRF fvj::div terms are identically zero here: MRFFaceVelocity == 0, static mesh)
+    // (the moving-mesh fvj::div term is identically zero here: static mesh)
+    // MRFdivMeshPhi = fvj::div(w, MRFFaceVelocity*magSf) (convectiveFluxScheme.C:477-481)
+    if (!c.mrfFaceVel.empty()) {
+        vecd sfm(FT, 0.0);
+        for (size_t f = 0; f < FT; f++) if (faceActive(m, (int)f, em)) sfm[f] = c.mrfFaceVel[f] * m.magSf[f];
+        subtractDivFace(m, dContByRho, sfm, {0});
+        subtractDivFace(m, dMomByRhoU, sfm, {0, 4, 8});
+        subtractDivFace(m, dEnergyByRhoE, sfm, {0});
+    }
 
     // ---- addDissipationJacobian (convectiveFluxScheme.C:487-534)
     vecd lambdaConv;
@@ -830,7 +859,7 @@ void createJacobian(Ctx& c)
             double rhoB = c.rho[s];
             V3 UB = {c.U[3 * (size_t)s], c.U[3 * (size_t)s + 1], c.U[3 * (size_t)s + 2]};
             double UrelBdotSf = UB & SfB;
-            UrelBdotSf -= 0.0 * m.magSf[f];
+            UrelBdotSf -= c.mrfAt(f) * m.magSf[f];
             double pB = c.p[s], TB = c.T[s];
             // rhoEn = rho*(he(p,T) + 0.5 magSqr(U)) evaluated on the boundary
             double rhoEB = rhoB * (c.Cv * TB + 0.5 * magSqr(UB));
@@ -903,7 +932,14 @@ void createJacobian(Ctx& c)
         for (int k = 0; k < 9; k++) dMomByRhoU.diag[9 * (size_t)i + k] += diagCoeff * I9.v[k];
         dEnergyByRhoE.diag[i] += diagCoeff;
     }
-    // addMRFSource: MRFOmega == 0 (out of scope)
+    // addMRFSource, diagonal part (convectiveFluxScheme.C:130-137)
+    if (!c.mrfOmega.empty())
+        for (int i = 0; i < m.N; i++) {
+            const double ox = c.mrfOmega[3 * (size_t)i], oy = c.mrfOmega[3 * (size_t)i + 1], oz = c.mrfOmega[3 * (size_t)i + 2];
+            double* md = &dMomByRhoU.diag[9 * (size_t)i];
+            md[1] -= oz * m.V[i]; md[2] += oy * m.V[i]; md[3] += oz * m.V[i];
+            md[5] -= ox * m.V[i]; md[6] -= oy * m.V[i]; md[7] += ox * m.V[i];
+        }
 
     // ---- viscousFluxScheme::addFluxTerms, LaxFriedrichJacobian branch (viscousFluxScheme.C:220-246)
     if (c.mu > 0) {
@@ -916,6 +952,19 @@ void createJacobian(Ctx& c)
         subtractLaplacianOne(m, dContByRho, half, {0});
         subtractLaplacianOne(m, dMomByRhoU, half, {0, 4, 8});
         subtractLaplacianOne(m, dEnergyByRhoE, half, {0});
+    }
+    // addMRFSource, source part (convectiveFluxScheme.C:125-128): rhoU = rho*U, source -= (Omega ^ rhoU)*V.  The reference
+    // applies it once to the fresh eqSystem of the iteration; the flag keeps a repeated assemble() from doing it twice.
+    if (!c.mrfOmega.empty() && !c.srcMrfApplied) {
+        for (int i = 0; i < m.N; i++) {
+            const V3 om = {c.mrfOmega[3 * (size_t)i], c.mrfOmega[3 * (size_t)i + 1], c.mrfOmega[3 * (size_t)i + 2]};
+            const V3 ru = c.rho[i] * V3{c.U[3 * (size_t)i], c.U[3 * (size_t)i + 1], c.U[3 * (size_t)i + 2]};
+            const V3 cr = {om.y * ru.z - om.z * ru.y, om.z * ru.x - om.x * ru.z, om.x * ru.y - om.y * ru.x};
+            c.srcRhoU[3 * (size_t)i] -= cr.x * m.V[i];
+            c.srcRhoU[3 * (size_t)i + 1] -= cr.y * m.V[i];
+            c.srcRhoU[3 * (size_t)i + 2] -= cr.z * m.V[i];
+        }
+        c.srcMrfApplied = true;
     }
     // sources (residualsUpdate.H:81-83)
     dContByRho.source = c.srcRho;

@@ -25,6 +25,8 @@ def setup_world(case, n_parts, mode="x"):
             if patch in names:
                 for field, (kind, params) in fields.items():
                     o.bc_set(patch, {"p": 0, "U": 1, "T": 2}[field], kind, params)
+        if case.mrf is not None:
+            o.mrf_set(*case.mrf_fields(meshes[r]))
     w.state_set([case.p[m.cell_global] for m in meshes], [case.U[m.cell_global] for m in meshes], [case.T[m.cell_global] for m in meshes])
     return w, meshes
 
@@ -48,12 +50,15 @@ def test_partition_processor_patches_match():
             assert np.allclose(m.weights[fa] + other.weights[fb], 1.0, atol=1e-14)
 
 
-@pytest.mark.parametrize("n_parts,mode,mu", [(2, "x", 0.0), (4, (2, 2, 1), 0.0), (4, (2, 2, 1), 0.5)])
-def test_partitioned_oracle_matches_single_domain(n_parts, mode, mu):
+@pytest.mark.parametrize("n_parts,mode,mu,mrf", [(2, "x", 0.0, False), (4, (2, 2, 1), 0.0, False), (4, (2, 2, 1), 0.5, False),
+                                                 (4, (2, 2, 1), 0.0, True)])
+def test_partitioned_oracle_matches_single_domain(n_parts, mode, mu, mrf):
     """Fluxes / residuals / SpMV do not depend on the decomposition (only LU-SGS and hence the GMRES history do —
     lusgs.C:149,181 keeps the sweeps rank-local).  mu > 0 adds the viscous residual, whose processor-patch faces need the
     neighbour's gradients of U and eCalc."""
     case = cases.onera_box(6, mu=mu)
+    if mrf:  # rotating zone in half of the domain: MRFFaceVelocity on processor faces is each side's own (outward) value
+        case.with_mrf(omega=(0.0, 40.0, 90.0), origin=(0.5, 0.0, 1.5), zone=lambda x: x[:, 0] > 0.2)
     single = case.apply(Oracle())
     phi, phiUp, phiEp = single.calc_flux()
     src = single.residual()
