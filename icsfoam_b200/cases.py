@@ -213,6 +213,28 @@ def forward_step(polymesh_dir):
     return Case("forwardStep", mesh, R, Cp, sch, ctl, bcs, p, U, T, n_iter_default=50)
 
 
+def vki_ls89(polymesh_dir, mu=1.5e-5, co=10.0):
+    """C5 tutorials/VKI-LS89: turbine cascade on the shipped 2-D mesh (28 059 cells, translational cyclic pair
+    Upper/Lower_periodicity, no-slip isothermal blade), ROE + vanLeer, steady dual time with local time stepping
+    (pseudoCoNum 10, max 50), GMRES m=8 maxIter 10 relTol 1e-3, LU-SGS (system/fvSchemes, system/fvSolution, 0/p 0/U 0/T,
+    constant/thermophysicalProperties).  The tutorial runs RAS kOmegaSST; here muEff = mu (laminar).
+    The mesh is read from `polymesh_dir` (the reference's constant/polyMesh — input data, never copied into this repository)."""
+    mesh = mt.read_polymesh(polymesh_dir)
+    R, Cp = RR / 28.966, 1005.0
+    p, U, T = _uniform(mesh, 1e5, (100.0, 0, 0), 400.0)
+    sch = capi.default_schemes(flux_scheme="ROE", limiter_rho="vanLeer", limiter_U="vanLeer", limiter_T="vanLeer", entropy_fix_coeff=0.05,
+                               ddt_scheme="steadyState", pseudo_co_num=co, pseudo_co_num_max=50.0)
+    ctl = capi.solver_controls("LUSGS", n_directions=8, max_iter=10, tolerance=1e-12, rel_tol=1e-3)
+    zg = ("zeroGradient", ())
+    piov = ("pressureInletOutletVelocity", (0, 0, 0))
+    bcs = {
+        "inlet": {"p": ("totalPressure", (160500.0, 1.4)), "U": piov, "T": ("totalTemperature", (420.0, 1.4))},
+        "outlet": {"p": ("fixedValue", (82000.0,)), "U": piov, "T": ("inletOutlet", (400.0,))},
+        "blade": {"p": zg, "U": ("fixedValue", (0, 0, 0)), "T": ("fixedValue", (301.0,))},     # noSlip
+    }
+    return Case("VKI-LS89", mesh, R, Cp, sch, ctl, bcs, p, U, T, mu=mu, Pr=0.72, n_iter_default=20)
+
+
 class HBCase:
     """Harmonic Balance configuration (C5 'vki-HB' stand-in; dbnsFullyImplicitHBFoam): one base `Case` per time instance
     (same mesh, instance-specific boundary values and initial fields) plus the HBZone set-up.
@@ -278,3 +300,22 @@ def hb_box(n=6, n_instants=3, omega=2 * np.pi * 40.0, flux="ROE", limiter="vanLe
     if cyl:
         kw = dict(cyl_coords=[1], rotation_axis=[0.0, 0.0, 2.0], rotation_centre=[0.5, -2.0, 0.0])
     return HBCase("hb-box", insts, snaps, Ds[0], zone, **kw)
+
+
+def vki_hb(polymesh_dir, n_instants=3, omega=2 * np.pi * 2000.0, amp=0.02, mu=1.5e-5, co=10.0):
+    """C5 (ii): Harmonic Balance on the shipped VKI-LS89 mesh (dbnsFullyImplicitHBFoam, `allMesh` zone, one frequency,
+    n_instants = 2*harmonics+1 instances over one period): the inlet total pressure oscillates by +-amp at `omega`
+    (an incoming wake / potential disturbance stand-in; the tutorial itself ships no HBProperties)."""
+    from . import hb
+    harmonics = (n_instants - 1) // 2
+    omegas = hb.omega_list([omega], [harmonics])
+    snaps, Ds = hb.set_instants([omegas], n_instants, selected_period=2 * np.pi / omega)
+    insts = []
+    for K, t in enumerate(snaps):
+        c = vki_ls89(polymesh_dir, mu=mu, co=co) if K == 0 else None
+        if c is None:
+            b = insts[0]
+            c = Case(b.name, b.mesh, b.R, b.Cp, b.schemes, b.controls, {k: dict(v) for k, v in b.bcs.items()}, b.p, b.U, b.T, mu=b.mu, Pr=b.Pr)
+        c.bcs["inlet"] = dict(c.bcs["inlet"], p=("totalPressure", (160500.0 * (1 + amp * np.sin(omega * t)), 1.4)))
+        insts.append(c)
+    return HBCase("vki-HB", insts, snaps, Ds[0])

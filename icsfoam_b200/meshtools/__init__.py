@@ -83,7 +83,11 @@ class Mesh:
         lib.icsmesh_set_patch_kind(self._h, ib, CYCLIC, ia)
         self.patches[ia].update(kind=CYCLIC, nbr_patch=ib)
         self.patches[ib].update(kind=CYCLIC, nbr_patch=ia)
-        # coupled weights: cyclicFvPatch::makeWeights — own/neighbour normal distances
+        self._cyclic_geometry(ia, ib)
+
+    def _cyclic_geometry(self, ia, ib):
+        """weights / deltaCoeffs / nonOrthDeltaCoeffs of a translational cyclic pair (face i of one patch matches face i of
+        the other): cyclicFvPatch::makeWeights (own/neighbour normal distances) and cyclicFvPatch::delta()."""
         for pa, pb in ((self.patches[ia], self.patches[ib]), (self.patches[ib], self.patches[ia])):
             fa = np.arange(pa["start"], pa["start"] + pa["size"])
             fb = np.arange(pb["start"], pb["start"] + pb["size"])
@@ -246,7 +250,11 @@ def structured_part(n, parts, rank, kind=0, lo=(0, 0, 0), hi=(1, 1, 1), grad_y=1
 
 
 def read_polymesh(directory):
-    return Mesh(_lib().icsmesh_read_polymesh(directory.encode()))
+    m = Mesh(_lib().icsmesh_read_polymesh(directory.encode()))
+    for i, p in enumerate(m.patches):      # cyclic pairs as written by OpenFOAM (neighbourPatch entries)
+        if p["kind"] == CYCLIC and i < p["nbr_patch"]:
+            m._cyclic_geometry(i, p["nbr_patch"])
+    return m
 
 
 # ---- the named configurations of BASELINE.json (SURVEY.md §8d "Configs as concrete synthetic inputs") ----

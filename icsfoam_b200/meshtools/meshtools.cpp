@@ -382,21 +382,31 @@ Mesh* readPolyMesh(const std::string& dir)
     {
         std::istringstream is(sb);
         int np; is >> np; std::string tok; is >> tok;  // "("
+        std::vector<std::string> nbrNames;
         for (int p = 0; p < np; p++) {
             Patch pa; is >> pa.name; is >> tok;  // "{"
-            std::string type;
+            std::string type, nbrName;
             int depth = 1;
             while (depth > 0 && (is >> tok)) {
                 if (tok == "{") depth++;
                 else if (tok == "}") depth--;
                 else if (tok == "type") { is >> type; if (!type.empty() && type.back() == ';') type.pop_back(); }
+                else if (tok == "neighbourPatch") { is >> nbrName; if (!nbrName.empty() && nbrName.back() == ';') nbrName.pop_back(); }
+                else if (tok == "transform") { is >> tok; if (!tok.empty() && tok.back() == ';') tok.pop_back(); if (tok == "rotational") m.error = "rotational cyclic patch " + pa.name + " is not supported"; }
                 else if (tok == "nFaces") { is >> tok; pa.size = std::atoi(tok.c_str()); }
                 else if (tok == "startFace") { is >> tok; pa.start = std::atoi(tok.c_str()); }
             }
             pa.kind = type == "wall" ? PK_WALL : type == "empty" ? PK_EMPTY : type == "symmetryPlane" ? PK_SYMMETRYPLANE
                       : type == "cyclic" ? PK_CYCLIC : type == "processor" ? PK_PROCESSOR : PK_PATCH;
             m.patches.push_back(pa);
+            nbrNames.push_back(nbrName);
         }
+        // cyclic pairs: neighbourPatch names -> patch indices (face i of a patch matches face i of its neighbour patch)
+        for (int p = 0; p < np; p++)
+            if (m.patches[p].kind == PK_CYCLIC) {
+                for (int q = 0; q < np; q++) if (m.patches[q].name == nbrNames[p]) m.patches[p].nbrPatch = q;
+                if (m.patches[p].nbrPatch < 0) m.error = "cyclic patch " + m.patches[p].name + " has no neighbourPatch";
+            }
     }
     m.Sf.resize(m.nFaces);
     m.Cf.resize(m.nFaces);

@@ -167,3 +167,38 @@ def test_hb_against_golden_fixture(gpu_context):
     assert rel_err(got["history"][:, :-1], gold["history"][:, :-1]) <= 1e-8
     for k in ("rho", "rhoU", "rhoE"):
         assert rel_err(got[k], gold[k]) <= 1e-8, k
+
+
+import os  # noqa: E402
+
+LOCAL_VKI = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cases_local", "VKI-LS89", "constant", "polyMesh")
+
+
+@pytest.mark.skipif(not os.path.isdir(LOCAL_VKI), reason="VKI-LS89 tutorial mesh not staged (cases_local/ is not part of the repository)")
+def test_hb_vki_ls89_c5(gpu_context):
+    """C5 (ii): Harmonic Balance with 3 time instances on the shipped VKI-LS89 mesh (84 177 coupled cells, cyclic pair,
+    laminar viscous, ROE): HB sources and pseudo time step bit for bit, then 4 outer iterations of the (2 nO, nO) system."""
+    case = cases.vki_hb(LOCAL_VKI, 3)
+    H = HB(case)
+    g = case.apply(gpu_context())
+    g.calc_flux()
+    src_g = g.residual()
+    rdt_g, _ = g.pseudo_dt()
+    g.assemble()
+    H.assemble()
+    for a, b in zip(src_g, H.residual()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(rdt_g, H.pseudo()[0])
+    for blk in (0, 3, 8):
+        for a, b in zip(g.matrix_get_ldu(blk), H.matrix_get_ldu(blk)):
+            assert np.array_equal(a, b), blk
+    for it in range(4):
+        rg = g.iterate(case.controls)
+        ro = H.iterate(case.controls)
+        gr = g.hb_residuals()
+        assert rg.n_iterations == ro["n_iterations"], it
+        assert rel_err(gr["s_init"], ro["s_init"]) <= 1e-8, it
+        assert rel_err(gr["v_init"][np.arange(9) % 3 != 2], ro["v_init"][np.arange(9) % 3 != 2]) <= 1e-8, it
+    sg, so = g.state_get(), H.state_get()
+    for k in ("rho", "rhoU", "rhoE"):
+        assert rel_err(sg[k], so[k]) <= 1e-8, k

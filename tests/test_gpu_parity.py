@@ -311,3 +311,40 @@ def test_rotational_cyclic_is_refused(gpu_context):
             p["forwardT"] = [0, -1, 0, 1, 0, 0, 0, 0, 1]
     with pytest.raises(capi.ApiError):
         case.apply(gpu_context())
+
+
+LOCAL_VKI = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cases_local", "VKI-LS89", "constant", "polyMesh")
+
+
+@pytest.mark.skipif(not os.path.isdir(LOCAL_VKI), reason="VKI-LS89 tutorial mesh not staged (cases_local/ is not part of the repository)")
+def test_vki_ls89_c5_shipped_mesh(gpu_context):
+    """C5 (i) on the reference's own mesh: translational cyclic pair on the device, no-slip isothermal blade, laminar
+    viscous residual + LF viscous Jacobian, ROE + vanLeer, GMRES(8)/LU-SGS — every reduction-free stage bit for bit, then
+    the residual history and fields of 8 outer iterations."""
+    case = cases.vki_ls89(LOCAL_VKI)
+    o, g = case.apply(Oracle()), case.apply(gpu_context())
+    for a, b in zip(g.calc_flux(), o.calc_flux()):
+        assert np.array_equal(a, b)
+    for a, b in zip(g.residual(), o.residual()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(g.pseudo_dt()[0], o.pseudo_dt()[0])
+    g.assemble(); o.assemble()
+    for blk in range(9):
+        for a, b in zip(g.matrix_get_ldu(blk), o.matrix_get_ldu(blk)):
+            assert np.array_equal(a, b), blk
+    rng = np.random.default_rng(6)
+    N = case.mesh.n_cells
+    x = (rng.standard_normal(N), rng.standard_normal((N, 3)), rng.standard_normal(N))
+    x[1][:, 2] = 0
+    for a, b in zip(g.matrix_mul(*x), o.matrix_mul(*x)):
+        assert np.array_equal(a, b)
+    for pk in ("LUSGS", "Jacobi"):
+        for a, b in zip(g.precondition(pk, *x), o.precondition(pk, *x)):
+            assert np.array_equal(a, b), pk
+    for it in range(8):
+        ro, rg = o.iterate(case.controls), g.iterate(case.controls)
+        assert ro.n_iterations == rg.n_iterations, it
+        assert rel_err(list(rg.s_init) + list(rg.v_init)[:2], list(ro.s_init) + list(ro.v_init)[:2]) <= 1e-8, it
+    so, sg = o.state_get(), g.state_get()
+    for k in STATE_KEYS + ["p", "T"]:
+        assert rel_err(sg[k], so[k]) <= TOL_STATE, k

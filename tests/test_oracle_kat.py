@@ -555,3 +555,41 @@ def test_mrf_jacobian_is_linearisation_of_the_relative_rusanov_flux():
     cor = np.cross(Om, st["rho"][:, None] * st["U"]) * m.V[:, None]
     assert np.array_equal(s[0], r0[0]) and np.array_equal(s[2], r0[2])
     assert np.abs(s[1] - (r0[1] - cor)).max() <= 1e-12 * np.abs(r0[1]).max()
+
+
+REF_VKI = "/root/reference/tutorials/VKI-LS89/constant/polyMesh"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_VKI), reason="reference tutorial mesh not present on this machine")
+def test_vki_ls89_shipped_mesh_c5():
+    """C5 (i): the shipped VKI-LS89 polyMesh loads with its translational cyclic pair (faces matched one to one, separation
+    (0 0.0575 0)), is closed, and the laminar ROE/vanLeer run accelerates through the passage while the coupled residual falls."""
+    c = cases.vki_ls89(REF_VKI)
+    m = c.mesh
+    assert (m.n_cells, m.n_internal_faces) == (28059, 55615)       # SURVEY.md §8a
+    assert m.solutionD == [1, 1, -1]
+    up, lo = m.patches[m.patch_index("Upper_periodicity")], m.patches[m.patch_index("Lower_periodicity")]
+    assert up["kind"] == capi.CYCLIC and up["nbr_patch"] == m.patch_index("Lower_periodicity") and up["size"] == lo["size"] == 215
+    fa, fb = np.arange(up["start"], up["start"] + 215), np.arange(lo["start"], lo["start"] + 215)
+    assert np.abs(m.Cf[fa] - m.Cf[fb] - [0, 0.0575, 0]).max() < 1e-6
+    assert np.abs(m.Sf[fa] + m.Sf[fb]).max() < 1e-8
+    assert np.abs(m.weights[fa] + m.weights[fb] - 1).max() < 1e-12
+    s = np.zeros((m.n_cells, 3))
+    np.add.at(s, m.owner, m.Sf)
+    np.add.at(s, m.neighbour, -m.Sf[: m.n_internal_faces])
+    assert np.abs(s).max() < 1e-9
+    o = c.apply(Oracle())
+    first = None
+    for it in range(12):
+        r = o.iterate(c.controls)
+        first = first or max(r.s_init)
+    st = o.state_get()
+    assert max(r.s_init) < 0.25 * first
+    assert np.isfinite(st["rho"]).all() and st["rho"].min() > 0.3 and st["T"].min() > 250.0
+    mach = np.linalg.norm(st["U"], axis=1) / np.sqrt(1.4 * (cases.RR / 28.966) * st["T"])
+    assert 0.9 < mach.max() < 1.6                                   # transonic passage (p0/p_out = 1.96)
+    assert np.abs(st["U"][:, 2]).max() == 0.0                       # empty direction stays untouched
+    # the periodic pair really is periodic: the face values either side of the pair are each other's cell values
+    bnd = o.boundary_get()
+    F = m.n_internal_faces
+    assert np.array_equal(bnd["p"][fa - F], st["p"][m.owner[fb]]) and np.array_equal(bnd["p"][fb - F], st["p"][m.owner[fa]])
