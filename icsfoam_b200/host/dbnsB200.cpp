@@ -54,11 +54,16 @@ std::vector<double> numbers(const std::vector<std::string>& toks)
 }
 
 // fvPatchField type name -> ICSB200_BC_* + parameters (the BC set of the five tutorials)
-BcSpec bcFromDict(const dictionary& d, int field, const std::vector<double>& Uinf)
+BcSpec bcFromDict(const dictionary& d, int field, const std::vector<double>& Uinf, const dictionary& top)
 {
     const std::string type = d.word("type");
     BcSpec b{ICSB200_BC_ZEROGRADIENT, {}};
-    auto val = [&](const char* k) { return numbers(d.lookup(k)); };
+    // `$internalField`-style macros refer to entries of the enclosing field file
+    auto val = [&](const char* k) {
+        std::vector<std::string> toks = d.lookup(k);
+        if (!toks.empty() && toks[0].size() > 1 && toks[0][0] == '$') toks = top.lookup(toks[0].substr(1));
+        return numbers(toks);
+    };
     if (type == "zeroGradient") b.kind = ICSB200_BC_ZEROGRADIENT;
     else if (type == "fixedValue") { b.kind = ICSB200_BC_FIXEDVALUE; b.prm = val("value"); }
     else if (type == "slip" || type == "symmetryPlane" || type == "symmetry") b.kind = ICSB200_BC_SLIP;
@@ -121,7 +126,6 @@ int main(int argc, char** argv)
             ml.patch(mh, i, o, name);
             patchNames[i] = name;
             patches[i] = icsb200_patch{o[0], o[1], o[2], o[3], o[4], {1, 0, 0, 0, 1, 0, 0, 0, 1}};
-            if (o[0] == ICSB200_CYCLIC) throw FatalError("cyclic patches need the neighbourPatch entry: not wired in the standalone reader yet");
         }
         std::cout << "Mesh: " << N << " cells, " << F << " internal faces, " << nP << " patches\n";
 
@@ -136,7 +140,7 @@ int main(int argc, char** argv)
         const double mu = mix.subDict("transport").get<double>("mu"), Pr = mix.subDict("transport").get<double>("Pr");
         if (mix.subDict("thermodynamics").getOrDefault<double>("Tref", 0.0) != 0.0) throw FatalError("Tref != 0 is not supported");
         check(ctx, icsb200_thermo_set(ctx, 8314.46261815324 / W, Cp, mu, Pr), "thermo_set");
-        if (mu > 0) std::cout << "Viscous analysis detected: only the Lax-Friedrichs viscous Jacobian is on the device (viscous residual: next round)\n";
+        if (mu > 0) std::cout << "Viscous analysis detected: laminar viscous residual + Lax-Friedrichs viscous Jacobian (turbulence model not on the device)\n";
 
         // ---- schemes (fvSchemes / fvSolution pseudoTime; initialise.H:39-71, beginTimeStep.H:8-45, updateFields.H:11-35)
         auto flux = convectiveFluxScheme::New(ctx, fvSchemes);
@@ -174,11 +178,12 @@ int main(int argc, char** argv)
         const std::vector<double> U0 = numbers(UDict.lookup("internalField"));
         const double p0 = numbers(pDict.lookup("internalField")).at(0), T0 = numbers(TDict.lookup("internalField")).at(0);
         if (UDict.lookup("internalField").at(0) != "uniform") throw FatalError("only uniform internalField is supported by the standalone reader");
+        const dictionary *top[3] = {&pDict, &UDict, &TDict};
         const dictionary *bf[3] = {&pDict.subDict("boundaryField"), &UDict.subDict("boundaryField"), &TDict.subDict("boundaryField")};
         for (int pi = 0; pi < nP; pi++)
             for (int fld = 0; fld < 3; fld++) {
                 if (!bf[fld]->isDict(patchNames[pi])) throw FatalError("patch " + patchNames[pi] + " missing in boundaryField");
-                BcSpec b = bcFromDict(bf[fld]->subDict(patchNames[pi]), fld, U0);
+                BcSpec b = bcFromDict(bf[fld]->subDict(patchNames[pi]), fld, U0, *top[fld]);
                 if (b.kind == ICSB200_BC_EMPTY || b.kind == ICSB200_BC_COUPLED) continue;
                 check(ctx, icsb200_bc_set(ctx, pi, fld, b.kind, b.prm.data(), (int)b.prm.size()), "bc_set");
             }

@@ -87,7 +87,8 @@ class Mesh:
 
     def _cyclic_geometry(self, ia, ib):
         """weights / deltaCoeffs / nonOrthDeltaCoeffs of a translational cyclic pair (face i of one patch matches face i of
-        the other): cyclicFvPatch::makeWeights (own/neighbour normal distances) and cyclicFvPatch::delta()."""
+        the other): cyclicFvPatch::makeWeights (own/neighbour normal distances) and cyclicFvPatch::delta().  Used by the
+        synthetic meshes; polyMesh directories get the same from the reader (meshtools.cpp cyclicGeometry)."""
         for pa, pb in ((self.patches[ia], self.patches[ib]), (self.patches[ib], self.patches[ia])):
             fa = np.arange(pa["start"], pa["start"] + pa["size"])
             fb = np.arange(pb["start"], pb["start"] + pb["size"])
@@ -250,11 +251,7 @@ def structured_part(n, parts, rank, kind=0, lo=(0, 0, 0), hi=(1, 1, 1), grad_y=1
 
 
 def read_polymesh(directory):
-    m = Mesh(_lib().icsmesh_read_polymesh(directory.encode()))
-    for i, p in enumerate(m.patches):      # cyclic pairs as written by OpenFOAM (neighbourPatch entries)
-        if p["kind"] == CYCLIC and i < p["nbr_patch"]:
-            m._cyclic_geometry(i, p["nbr_patch"])
-    return m
+    return Mesh(_lib().icsmesh_read_polymesh(directory.encode()))   # cyclic pairs (neighbourPatch) get their coupled geometry there
 
 
 # ---- the named configurations of BASELINE.json (SURVEY.md §8d "Configs as concrete synthetic inputs") ----

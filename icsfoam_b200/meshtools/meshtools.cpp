@@ -147,6 +147,27 @@ void finishGeometry(Mesh& m)
     }
 }
 
+// weights / deltaCoeffs / nonOrthDeltaCoeffs of a translational cyclic pair (face i of patch ia matches face i of patch ib):
+// cyclicFvPatch::makeWeights (own / neighbour normal distances) and cyclicFvPatch::delta() = own delta - neighbour delta
+void cyclicGeometry(Mesh& m, int ia, int ib)
+{
+    for (int side = 0; side < 2; side++) {
+        const Patch& pa = m.patches[side == 0 ? ia : ib];
+        const Patch& pb = m.patches[side == 0 ? ib : ia];
+        for (int i = 0; i < pa.size; i++) {
+            const int fa = pa.start + i, fb = pb.start + i;
+            const V3 nfa = (1.0 / m.magSf[fa]) * m.Sf[fa], nfb = (1.0 / m.magSf[fb]) * m.Sf[fb];
+            const V3 dA = m.Cf[fa] - m.C[m.owner[fa]], dB = m.Cf[fb] - m.C[m.owner[fb]];
+            const double da = std::fabs(dot(nfa, dA)), db = std::fabs(dot(nfb, dB));
+            m.weights[fa] = db / (da + db);
+            const V3 d = dA - dB;
+            const double md = mag(d);
+            m.deltaCoeffs[fa] = 1.0 / md;
+            m.nonOrthDeltaCoeffs[fa] = 1.0 / std::max(dot(nfa, d), 0.05 * md);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- structured generator
 // A block-structured hex mesh made of nb blocks stacked along x, each (nxb x ny x nz) cells,
 // numbered block by block with i fastest (blockMesh cell numbering).  Points come from a mapping
@@ -427,6 +448,11 @@ Mesh* readPolyMesh(const std::string& dir)
     double tot = emptyN[0] + emptyN[1] + emptyN[2];
     for (int d = 0; d < 3; d++) m.solutionD[d] = (tot > 0 && emptyN[d] > 0.5 * tot / 1.5 && emptyN[d] / tot > 0.9) ? -1 : 1;
     finishGeometry(m);
+    for (int p = 0; p < (int)m.patches.size(); p++)
+        if (m.patches[p].kind == PK_CYCLIC && p < m.patches[p].nbrPatch) {
+            if (m.patches[p].size != m.patches[m.patches[p].nbrPatch].size) { m.error = "cyclic pair " + m.patches[p].name + " has patches of different size"; return mp; }
+            cyclicGeometry(m, p, m.patches[p].nbrPatch);
+        }
     return mp;
 }
 
@@ -570,6 +596,9 @@ void icsmesh_set_patch_kind(void* h, int i, int kind, int nbrPatch)
     m.patches[i].kind = kind;
     m.patches[i].nbrPatch = nbrPatch;
 }
+
+// coupled geometry of a translational cyclic pair (after both patches were given kind CYCLIC)
+void icsmesh_cyclic_geometry(void* h, int ia, int ib) { cyclicGeometry(*(Mesh*)h, ia, ib); }
 
 // copy arrays out (caller allocates): owner[nFaces], neighbour[nInternalFaces], Sf[3nFaces], Cf[3nFaces],
 // magSf, weights, deltaCoeffs, nonOrthDeltaCoeffs [nFaces], C[3nCells], V[nCells]

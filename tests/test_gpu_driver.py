@@ -1,0 +1,57 @@
+"""The standalone driver icsfoam_b200/host/dbnsB200 (dbnsFoam's loop over the C ABI, reading OpenFOAM case directories
+verbatim) against the Python host path on the two tutorials whose meshes the reference ships: it must read the same
+case out of the dictionaries (0/p,U,T incl. `$internalField` macros, fvSchemes, fvSolution, thermophysicalProperties,
+polyMesh incl. the cyclic pair) that icsfoam_b200.cases builds by hand, i.e. print the same residual history.  GPU only."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from icsfoam_b200 import cases
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "icsfoam_b200", "host", "dbnsB200")
+MESHLIB = os.path.join(ROOT, "icsfoam_b200", "meshtools", "libicsmesh.so")
+
+
+def run_driver(case_dir, steps):
+    r = subprocess.run([DRIVER, case_dir, "-maxSteps", str(steps)], env=dict(os.environ, ICSMESH_LIB=MESHLIB), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.rstrip().endswith("End")
+    init = [[float(x) for x in re.findall(r"[-+0-9.eE]+", ln.split("=", 1)[1])] for ln in r.stdout.splitlines() if ln.startswith("Initial residual")]
+    its = [int(ln.split()[-1]) for ln in r.stdout.splitlines() if ln.startswith("No Iterations")]
+    return np.array(init), its
+
+
+def staged(name):
+    return os.path.join(ROOT, "cases_local", name)
+
+
+@pytest.mark.skipif(not os.path.isdir(staged("VKI-LS89") + "/system"), reason="VKI-LS89 tutorial not staged (cases_local/ is not part of the repository)")
+def test_driver_runs_vki_ls89_tutorial_directory(gpu_context):
+    init, its = run_driver(staged("VKI-LS89"), 6)
+    case = cases.vki_ls89(staged("VKI-LS89") + "/constant/polyMesh")
+    g = case.apply(gpu_context())
+    for k in range(6):
+        r = g.iterate(case.controls)
+        assert its[k] == r.n_iterations, k
+        want = np.array(list(r.s_init) + list(r.v_init))
+        assert np.abs(init[k][:4] - want[:4]).max() <= 1e-5 * np.abs(want[:4]).max(), (k, init[k], want)   # 6 printed digits
+
+
+@pytest.mark.skipif(not os.path.isdir(staged("forwardStep") + "/system"), reason="forwardStep tutorial not staged (cases_local/ is not part of the repository)")
+def test_driver_runs_forward_step_tutorial_directory(gpu_context):
+    init, its = run_driver(staged("forwardStep"), 1)     # one physical time step = up to nPseudoCorr pseudo iterations
+    case = cases.forward_step(staged("forwardStep") + "/constant/polyMesh")
+    g = case.apply(gpu_context())
+    g.new_time_step()
+    assert len(its) >= 3
+    for k in range(min(len(its), 5)):
+        r = g.iterate(case.controls)
+        assert its[k] == r.n_iterations, k
+        want = np.array(list(r.s_init) + list(r.v_init))
+        assert np.abs(init[k][:4] - want[:4]).max() <= 1e-5 * np.abs(want[:4]).max(), (k, init[k], want)
