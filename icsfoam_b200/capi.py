@@ -127,6 +127,7 @@ SHARED_SIGNATURES = {
     "source_set": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
     "source_get": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
     "mrf_set": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "transport_set": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp]),
     "matrix_mul": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp]),
     "precondition": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp]),
     "solve_delta": (C.c_int, [C.c_void_p, C.POINTER(SolverControls), _dp, _dp, _dp, C.POINTER(Residuals)]),
@@ -286,6 +287,16 @@ class Api:
         assert fv is None or fv.size == self.mesh.n_faces
         assert om is None or om.size == 3 * self.mesh.n_cells
         self._call("mrf_set", dptr(fv), dptr(om))
+
+    def transport_set(self, muEff=None, muEff_b=None, alphaEff=None, alphaEff_b=None):
+        """turbulence->muEff() / alphaEff(): cell [n_cells] and boundary-face [n_faces - n_internal_faces] values; None = laminar"""
+        if muEff is None:
+            self._call("transport_set", None, None, None, None)
+            return
+        arrs = [np.ascontiguousarray(a, np.float64) for a in (muEff, muEff_b, alphaEff, alphaEff_b)]
+        NB = self.mesh.n_faces - self.mesh.n_internal_faces
+        assert arrs[0].size == arrs[2].size == self.mesh.n_cells and arrs[1].size == arrs[3].size == NB
+        self._call("transport_set", *[dptr(a) for a in arrs])
 
     def matrix_mul(self, xRho, xRhoU, xRhoE):
         N = self.mesh.n_cells

@@ -22,12 +22,25 @@ class Case:
         self.T = np.ascontiguousarray(T, np.float64)
         self.n_iter_default = n_iter_default
         self.mrf = None   # (omega[3], origin[3], translation velocity[3], zone predicate on points or None): see with_mrf
+        self.transport = None  # callable(points[n,3]) -> (muEff, alphaEff): stands in for a turbulence model's fields
 
     def with_mrf(self, omega=(0, 0, 0), origin=(0, 0, 0), velocity=(0, 0, 0), zone=None):
         """Frame motion of an MRFCoupledZone (rotation `omega` about `origin`) plus an MRFTranslatingZone (`velocity`),
         restricted to the points where zone(xyz) is true (None: whole mesh)."""
         self.mrf = (np.asarray(omega, float), np.asarray(origin, float), np.asarray(velocity, float), zone)
         return self
+
+    def with_transport(self, fn):
+        """Effective viscosity / thermal diffusivity fields as a turbulence model would hand them over every outer iteration
+        (turbulence->muEff(), alphaEff()): fn(points) -> (muEff, alphaEff), evaluated at cell and boundary-face centres."""
+        self.transport = fn
+        return self
+
+    def transport_fields(self, m):
+        F = m.n_internal_faces
+        mu_c, al_c = self.transport(m.C)
+        mu_b, al_b = self.transport(m.Cf[F:])
+        return tuple(np.ascontiguousarray(a, np.float64) for a in (mu_c, mu_b, al_c, al_b))
 
     def mrf_fields(self, m):
         """flux.MRFFaceVelocity() = (MRF.faceU() + MRFTrans.faceU()) & Sf/magSf and flux.MRFOmega() of mesh `m`
@@ -58,6 +71,8 @@ class Case:
                 api.bc_set(patch, {"p": capi.FIELD_P, "U": capi.FIELD_U, "T": capi.FIELD_T}[field], kind, params)
         if self.mrf is not None:
             api.mrf_set(*self.mrf_fields(m))
+        if self.transport is not None:
+            api.transport_set(*self.transport_fields(m))
         if cells is None:
             api.state_set(self.p, self.U, self.T)
         else:

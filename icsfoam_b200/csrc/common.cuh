@@ -152,6 +152,9 @@ struct icsb200_ctx {
     double* d_mrfFace = nullptr;                                      // [NFG]
     double* d_mrfOmega = nullptr;                                     // [3*NP]
     bool srcMrfApplied = false;                                       // addMRFSource's Coriolis term is already in d_src
+    // turbulence->muEff() / alphaEff() from the caller (icsb200_transport_set): [2][NX] over positions, halo and boundary
+    // slots; null = the laminar constants mu and gamma mu / Pr
+    double* d_transport = nullptr;
     int* d_bad = nullptr;                                              // [NPH] boundLocalTimeStep flags
     // ---- matrix ----
     double* d_offd = nullptr;  // [nEntries*25*32]

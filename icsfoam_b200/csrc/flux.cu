@@ -455,6 +455,7 @@ struct ViscArgs {
     const double *geo, *dCoupled, *C, *V, *f, *grad, *gradE, *vic;
     size_t NFG, NX, NPH;
     double mu, alphaEff;
+    const double* tr;  // [2][NX] muEff, alphaEff fields (cells, halo and boundary slots) or null: laminar constants
     double* out;  // [8*NP]
 };
 
@@ -515,10 +516,12 @@ k_visc(ViscArgs a)
             auto lin = [&](double x, double y) { return coupled ? w * x + (1.0 - w) * y : w * (x - y) + y; };
             double gP[9], gN[9], gf[9], tP[9], tN[9], tf[9];
             gradUAt(a, P, gP); gradUAt(a, N, gN);
-            dev2T(gP, a.mu, tP); dev2T(gN, a.mu, tN);
+            const double muP = a.tr ? a.tr[P] : a.mu, muN = a.tr ? a.tr[N] : a.mu;
+            const double alP = a.tr ? a.tr[a.NX + P] : a.alphaEff, alN = a.tr ? a.tr[a.NX + N] : a.alphaEff;
+            dev2T(gP, muP, tP); dev2T(gN, muN, tN);
 #pragma unroll
             for (int k = 0; k < 9; k++) { gf[k] = lin(gP[k], gN[k]); tf[k] = lin(tP[k], tN[k]); }
-            const double muf = lin(a.mu, a.mu), alf = lin(a.alphaEff, a.alphaEff);
+            const double muf = lin(muP, muN), alf = lin(alP, alN);
             double UP[3], UN[3], Uf[3];
 #pragma unroll
             for (int d = 0; d < 3; d++) { UP[d] = a.f[(size_t)(Q_UX + d) * a.NX + P]; UN[d] = a.f[(size_t)(Q_UX + d) * a.NX + N]; Uf[d] = lin(UP[d], UN[d]); }
@@ -574,21 +577,22 @@ k_visc(ViscArgs a)
 #pragma unroll
                 for (int i = 0; i < 3; i++) gb[3 * i + jj] = gP[3 * i + jj] + nf[i] * (sn[jj] - ng);
             }
-            dev2T(gb, a.mu, tb);
+            const double muB = a.tr ? a.tr[c] : a.mu, alB = a.tr ? a.tr[a.NX + c] : a.alphaEff;  // patch values of muEff / alphaEff
+            dev2T(gb, muB, tb);
 #pragma unroll
             for (int d = 0; d < 3; d++) {
-                fl[d] = a.mu * sn[d] * magSf;
+                fl[d] = muB * sn[d] * magSf;
                 ft[d] = Sf[0] * tb[d] + Sf[1] * tb[3 + d] + Sf[2] * tb[6 + d];
             }
             double sd[3];
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-                const double a0 = a.mu * gb[3 * i] + tb[3 * i], a1 = a.mu * gb[3 * i + 1] + tb[3 * i + 1], a2 = a.mu * gb[3 * i + 2] + tb[3 * i + 2];
+                const double a0 = muB * gb[3 * i] + tb[3 * i], a1 = muB * gb[3 * i + 1] + tb[3 * i + 1], a2 = muB * gb[3 * i + 2] + tb[3 * i + 2];
                 sd[i] = a0 * Ub[0] + a1 * Ub[1] + a2 * Ub[2];
             }
             fs = sd[0] * Sf[0] + sd[1] * Sf[1] + sd[2] * Sf[2];
             const double eP = a.f[(size_t)Q_EC * a.NX + p], eB = a.f[(size_t)Q_EC * a.NX + c];
-            fe = a.alphaEff * (dc * (eB - eP)) * magSf;
+            fe = alB * (dc * (eB - eP)) * magSf;
         }
         if (type == ET_LOWER) {
             lap[0] -= fl[0]; lap[1] -= fl[1]; lap[2] -= fl[2]; dtau[0] -= ft[0]; dtau[1] -= ft[1]; dtau[2] -= ft[2]; sg -= fs; le -= fe;
@@ -685,6 +689,7 @@ int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
         v.geo = c->d_geo; v.dCoupled = c->d_dCoupled; v.C = c->d_C; v.V = c->d_V; v.f = c->d_fields; v.grad = c->d_grad; v.gradE = c->d_gradE; v.vic = c->d_vic;
         v.NFG = c->NFG; v.NX = c->NX; v.NPH = c->NPH;
         v.mu = c->mu; v.alphaEff = c->gamma * (c->mu / c->Pr);
+        v.tr = c->d_transport;
         v.out = c->d_visc;
         LaunchScope ls(c, TM_FLUX);
         k_visc<<<gridFor(c->NP, 128), 128, 0, c->stream>>>(v);

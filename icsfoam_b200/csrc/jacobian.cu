@@ -53,6 +53,7 @@ struct JacArgs {
     const double* src;    // unused here (sources live in d_src)
     double *offd, *diag, *rD, *rdt, *ddtCoeff;
     const double* recon;  // [8*NFG] limited face states stored by k_flux_faces (REUSE instantiation)
+    const double* tr;              // [2][NX] muEff, alphaEff fields or null (laminar constants)
     const double *mrf, *mrfOmega;  // MRFFaceVelocity [NFG] (GPU face order) and MRFOmega [3*NP]; null = zero field
 };
 
@@ -190,7 +191,13 @@ k_jac(JacArgs a)
         if (a.mu > 0) {
             const double rP = a.f[(size_t)Q_RHO * a.NX + P], rN = a.f[(size_t)Q_RHO * a.NX + N];
             const double rhof = coupled ? (w * rP + (1.0 - w) * rN) : (w * (rP - rN) + rN);
-            const double lambdaVisc = (a.mu + a.alphaEff) / rhof;
+            double muf = a.mu, alf = a.alphaEff;
+            if (a.tr) {  // fvc::interpolate(turbulence.muEff()), fvc::interpolate(turbulence.alphaEff()) (viscousFluxScheme.C:222-223)
+                const double muP = a.tr[P], muN = a.tr[N], alP = a.tr[a.NX + P], alN = a.tr[a.NX + N];
+                muf = coupled ? (w * muP + (1.0 - w) * muN) : (w * (muP - muN) + muN);
+                alf = coupled ? (w * alP + (1.0 - w) * alN) : (w * (alP - alN) + alN);
+            }
+            const double lambdaVisc = (muf + alf) / rhof;
             sf2 = (0.5 * lambdaVisc) * magSf * a.geo[G_DELTA * a.NFG + g];
             viscAcc -= sf2;
         }
@@ -465,6 +472,7 @@ int ics_jacobian(icsb200_ctx* c, bool useStoredRdt)
         LaunchScope ls(c, TM_JAC);
         a.recon = c->d_faceRecon;
         a.mrf = c->d_mrfFace; a.mrfOmega = c->d_mrfOmega;
+        a.tr = c->d_transport;
         if (c->reconValid && c->d_faceRecon) k_jac<true><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(a);
         else k_jac<false><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(a);
     }
@@ -604,6 +612,35 @@ extern "C" int icsb200_source_get(icsb200_ctx* c, double* sRho, double* sRhoU, d
     if (sRho && (r = ics_download_cells(c, sRho, 1, c->d_src, c->NPH))) return r;
     if (sRhoU && (r = ics_download_cells(c, sRhoU, 3, c->d_src + c->NPH, c->NPH))) return r;
     if (sRhoE && (r = ics_download_cells(c, sRhoE, 1, c->d_src + 4 * (size_t)c->NPH, c->NPH))) return r;
+    return 0;
+}
+
+// turbulence->muEff() / turbulence->alphaEff() (viscousFluxScheme.C:222-223, residualsUpdate.H:16-43) from the caller's
+// turbulence model: cell values [N] and boundary-face values [NB]; coupled boundary entries are ignored (the halo /
+// neighbour cell provides the patchNeighbourField).  NULL muEff switches back to the laminar constants.
+extern "C" int icsb200_transport_set(icsb200_ctx* c, const double* muEff, const double* muEff_b, const double* alphaEff, const double* alphaEff_b)
+{
+    if (!c->meshSet) return ics_fail(c, ICSB200_ESTATE, "transport_set: mesh not set");
+    cudaSetDevice(c->device);
+    int r;
+    c->fluxValid = false;
+    c->matrixSet = false;
+    if (!muEff) return devAlloc(c, &c->d_transport, 0);
+    if (!muEff_b || !alphaEff || !alphaEff_b) return ics_fail(c, ICSB200_EINVAL, "transport_set: all four arrays or none");
+    if (!(c->mu > 0)) return ics_fail(c, ICSB200_ESTATE, "transport_set: the run is inviscid (thermo_set mu = 0)");
+    if (!c->d_transport) {
+        if ((r = devAlloc(c, &c->d_transport, (size_t)2 * c->NX))) return r;
+        CUDA_TRY(c, cudaMemsetAsync(c->d_transport, 0, sizeof(double) * 2 * c->NX, c->stream));
+    }
+    if ((r = ics_upload_cells(c, muEff, 1, c->d_transport, c->NX))) return r;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // the staging buffer is reused by the next upload
+    if ((r = ics_upload_cells(c, alphaEff, 1, c->d_transport + c->NX, c->NX))) return r;
+    if (c->NB > 0) {
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_transport + c->NP + c->NH, muEff_b, sizeof(double) * c->NB, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_transport + c->NX + c->NP + c->NH, alphaEff_b, sizeof(double) * c->NB, cudaMemcpyHostToDevice, c->stream));
+    }
+    if ((r = ics_halo_fields(c, c->d_transport, c->NX, 2))) return r;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -144,6 +144,15 @@ int icsb200_bc_set(icsb200_ctx* ctx, int patch, int field, int kind, const doubl
  * (MRFCoupledZone faceU/omega, correctBoundaryVelocity) stays on the host.  Call after icsb200_mesh_set. */
 int icsb200_mrf_set(icsb200_ctx* ctx, const double* mrf_face_velocity, const double* mrf_omega);
 
+/* Effective transport properties from the caller's turbulence model: turbulence->muEff() and turbulence->alphaEff() as
+ * viscousFluxScheme::addFluxTerms (viscousFluxScheme.C:222-223) and residualsUpdate.H:16-43 read them every outer
+ * iteration — cell values [n_cells] and boundary-face values [n_faces - n_internal_faces] (wall functions etc.; entries of
+ * coupled and empty patches are ignored).  The turbulence transport equations themselves (OpenFOAM's
+ * compressible::turbulenceModel, dbnsFoam.C:126-134) stay with the caller.  NULL muEff = laminar constants mu and
+ * gamma mu / Pr from icsb200_thermo_set (the default).  Needs mu > 0 (a viscous run).  Call after icsb200_mesh_set. */
+int icsb200_transport_set(icsb200_ctx* ctx, const double* muEff, const double* muEff_boundary, const double* alphaEff,
+                          const double* alphaEff_boundary);
+
 /* ---- state --------------------------------------------------------------------------------- */
 /* internal fields p[N], U[3N], T[N]; evaluates BCs + thermo and builds rho, rhoU, rhoE (createFields.H:75-131) */
 int icsb200_state_set(icsb200_ctx* ctx, const double* p, const double* U, const double* T);

@@ -114,6 +114,9 @@ struct Ctx {
     // MRF (convectiveFluxScheme.H MRFFaceVelocity_/MRFOmega_, set by the solver at outerLoop.H:18-21): frame velocity
     // normal to each face [FT] (face orientation) and frame angular velocity per cell [3N]; empty = zero fields
     vecd mrfFaceVel, mrfOmega;
+    // turbulence->muEff() / alphaEff() handed over by the caller (cells then boundary faces, [N+NB]); empty = laminar
+    // constants mu and gamma mu / Pr.  Coupled boundary slots are filled with the patchNeighbourField.
+    vecd muEffField, alphaEffField;
     bool srcMrfApplied = false;  // the Coriolis source has been subtracted from the current srcRhoU
     double mrfAt(int f) const { return mrfFaceVel.empty() ? 0.0 : mrfFaceVel[f]; }
     std::string err;

@@ -271,6 +271,18 @@ int orc_source_get(Ctx* c, double* sRho, double* sRhoU, double* sRhoE)
     return 0;
 }
 
+// turbulence->muEff() / alphaEff(): cell values [n_cells] and boundary-face values [n_faces - n_internal_faces]; NULL = laminar
+int orc_transport_set(Ctx* c, const double* muEff, const double* muEff_b, const double* alphaEff, const double* alphaEff_b)
+{
+    if (!c->meshSet) return fail(c, ICSB200_ESTATE, "mesh not set");
+    if (!muEff) { c->muEffField.clear(); c->alphaEffField.clear(); return 0; }
+    if (!muEff_b || !alphaEff || !alphaEff_b) return fail(c, ICSB200_EINVAL, "transport_set: all four arrays or none");
+    const int N = c->m.N, NB = c->m.NB;
+    c->muEffField.assign(muEff, muEff + N); c->muEffField.insert(c->muEffField.end(), muEff_b, muEff_b + NB);
+    c->alphaEffField.assign(alphaEff, alphaEff + N); c->alphaEffField.insert(c->alphaEffField.end(), alphaEff_b, alphaEff_b + NB);
+    return 0;
+}
+
 // flux.MRFFaceVelocity() [n_faces] and flux.MRFOmega() [3*n_cells] (outerLoop.H:18-21); NULL = zero field
 int orc_mrf_set(Ctx* c, const double* mrf_face_velocity, const double* mrf_omega)
 {

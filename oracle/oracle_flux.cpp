@@ -412,7 +412,9 @@ void viscousResidual(Ctx& c, vecd& rhoUR, vecd& rhoER)
 {
     const Mesh& m = c.m;
     const size_t n = (size_t)m.N + m.NB;
-    const double mu = c.mu, alphaEff = c.gamma * (c.mu / c.Pr);
+    // muEff / alphaEff: laminar constants, or the turbulence model's fields (orc_transport_set)
+    vecd muV(n, c.mu), alV(n, c.gamma * (c.mu / c.Pr));
+    if (!c.muEffField.empty()) { muV = c.muEffField; alV = c.alphaEffField; syncCoupled(c, muV, 1); syncCoupled(c, alV, 1); }
     // gradients of the components of U and of eCalc (cells + coupled boundary slots)
     vecd comp(n), gU[3], eCalc(n), gE;
     for (int d = 0; d < 3; d++) {
@@ -439,9 +441,9 @@ void viscousResidual(Ctx& c, vecd& rhoUR, vecd& rhoER)
         auto lin = [&](double a, double b) { return coupled ? w * a + (1.0 - w) * b : w * (a - b) + b; };
         double gP[9], gN[9], gf[9], tP[9], tN[9], tf[9];
         gradUOf(P, gP); gradUOf(Ns, gN);
-        dev2T(gP, mu, tP); dev2T(gN, mu, tN);
+        dev2T(gP, muV[P], tP); dev2T(gN, muV[Ns], tN);
         for (int k = 0; k < 9; k++) { gf[k] = lin(gP[k], gN[k]); tf[k] = lin(tP[k], tN[k]); }
-        const double muf = lin(mu, mu), alf = lin(alphaEff, alphaEff);
+        const double muf = lin(muV[P], muV[Ns]), alf = lin(alV[P], alV[Ns]);
         double Uf[3];
         for (int j = 0; j < 3; j++) Uf[j] = lin(c.U[3 * (size_t)P + j], c.U[3 * Ns + j]);
         for (int j = 0; j < 3; j++) {
@@ -484,6 +486,7 @@ void viscousResidual(Ctx& c, vecd& rhoUR, vecd& rhoER)
                 const double ng = nf[0] * gP[j] + nf[1] * gP[3 + j] + nf[2] * gP[6 + j];
                 for (int i = 0; i < 3; i++) gb[3 * i + j] = gP[3 * i + j] + nf[i] * (sn[j] - ng);
             }
+            const double mu = muV[s], alphaEff = alV[s];  // patch values of muEff / alphaEff
             dev2T(gb, mu, tb);
             const double* Ub = &c.U[3 * s];
             for (int j = 0; j < 3; j++) {
@@ -945,6 +948,7 @@ void createJacobian(Ctx& c)
     if (c.mu > 0) {
         size_t n = (size_t)m.N + m.NB;
         vecd muEff(n, c.mu), alphaEff(n, c.gamma * (c.mu / c.Pr)), muf, alf, rhof, half(m.FT, 0.0);
+        if (!c.muEffField.empty()) { muEff = c.muEffField; alphaEff = c.alphaEffField; syncCoupled(c, muEff, 1); syncCoupled(c, alphaEff, 1); }
         interpolateLinear(c, muEff, muf);
         interpolateLinear(c, alphaEff, alf);
         interpolateLinear(c, c.rho, rhof);

@@ -39,6 +39,12 @@ def test_against_golden_fixtures(name, gpu_context):
     assert g.launch_count() > 0
 
 
+def TURB(x):
+    """smooth positive muEff / alphaEff fields standing in for mu + mut, alpha + alphat of a turbulence model"""
+    mu = 0.05 * (1.5 + np.sin(3.0 * x[:, 0]) * np.cos(2.0 * x[:, 1] + 0.5) + 0.3 * x[:, 2])
+    return mu, 1.7 * mu * (1.0 + 0.2 * np.cos(4.0 * x[:, 1]))
+
+
 LIVE = {
     "box-hllc-minmod": lambda: cases.periodic_box(7, "HLLC", "Minmod", seed=21),
     "box-roe-vanleer": lambda: cases.periodic_box(6, "ROE", "vanLeer", seed=22),
@@ -65,6 +71,11 @@ LIVE = {
     "box-mrf-ausm": lambda: cases.periodic_box(5, "AUSMPlusUp", "vanLeer", seed=83).with_mrf((10.0, 60.0, 0.0), velocity=(0.0, 0.0, 35.0)),
     "bump-mrf": lambda: cases.bump(15, 10).with_mrf((0.0, 0.0, 25.0), (1.5, -3.0, 0.0)),
     "scrambled-mrf": lambda: cases.scrambled_box(5, "HLLC", "vanLeer", seed=84).with_mrf((40.0, 0.0, -70.0), (0.2, 0.2, 0.2)),
+    # muEff / alphaEff fields from a (stand-in) turbulence model: cyclic, AMI halo, wall patches, non-orthogonal, scrambled; with MRF
+    "box-transport-roe": lambda: cases.periodic_box(6, "ROE", "vanLeer", seed=91, mu=0.05).with_transport(TURB),
+    "box-transport-ami-hllc": lambda: cases.periodic_box(5, "HLLC", "Minmod", seed=92, mu=0.1, ami_shift=0.3).with_transport(TURB),
+    "bump-transport": lambda: cases.bump(15, 10, mu=0.02).with_transport(TURB),
+    "scrambled-transport-mrf": lambda: cases.scrambled_box(5, "HLLC", "vanLeer", seed=93, mu=0.1).with_transport(TURB).with_mrf((40.0, 0.0, -70.0), (0.2, 0.2, 0.2)),
     "shocktube-ausm": lambda: cases.shock_tube(64, "AUSMPlusUp"),
     "shocktube-roe": lambda: cases.shock_tube(50, "ROE"),
 }
@@ -124,6 +135,33 @@ def test_mrf_is_bitwise_and_applies_the_coriolis_source_once(gpu_context):
     a, b = run_sequence(plain.apply(gpu_context()), plain), run_sequence(zero.apply(gpu_context()), zero)
     for k in EXACT_KEYS + SOLVE_KEYS + STATE_KEYS:
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_transport_fields_bitwise(gpu_context):
+    """icsb200_transport_set: viscous sources, all LDU arrays and the matrix product are bit-identical to the oracle with
+    variable muEff / alphaEff; a uniform field reproduces the laminar constants; NULL switches back."""
+    case = cases.periodic_box(6, "ROE", "vanLeer", seed=95, mu=0.05).with_transport(TURB)
+    o, g = case.apply(Oracle()), case.apply(gpu_context())
+    for a, b in zip(g.calc_flux(), o.calc_flux()):
+        assert np.array_equal(a, b)
+    for a, b in zip(g.residual(), o.residual()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(g.pseudo_dt()[0], o.pseudo_dt()[0])
+    g.assemble(); o.assemble()
+    for blk in range(9):
+        for a, b in zip(g.matrix_get_ldu(blk), o.matrix_get_ldu(blk)):
+            assert np.array_equal(a, b), blk
+    lam = cases.periodic_box(6, "ROE", "vanLeer", seed=95, mu=0.05)
+    gam = lam.Cp / (lam.Cp - lam.R)
+    uni = cases.periodic_box(6, "ROE", "vanLeer", seed=95, mu=0.05).with_transport(lambda x: (np.full(len(x), 0.05), np.full(len(x), gam * (0.05 / lam.Pr))))
+    a, b = run_sequence(lam.apply(gpu_context()), lam), run_sequence(uni.apply(gpu_context()), uni)
+    for k in EXACT_KEYS + SOLVE_KEYS + STATE_KEYS:
+        assert np.array_equal(a[k], b[k]), k
+    g.transport_set()   # back to the laminar constants
+    g.calc_flux()
+    ref = lam.apply(gpu_context()); ref.calc_flux()
+    for x, y in zip(g.residual(), ref.residual()):
+        assert np.array_equal(x, y)
 
 
 def test_transient_dual_time_euler_and_backward(gpu_context):

@@ -593,3 +593,49 @@ def test_vki_ls89_shipped_mesh_c5():
     bnd = o.boundary_get()
     F = m.n_internal_faces
     assert np.array_equal(bnd["p"][fa - F], st["p"][m.owner[fb]]) and np.array_equal(bnd["p"][fb - F], st["p"][m.owner[fa]])
+
+
+# ---------------------------------------------------------------------------------------------- muEff / alphaEff fields
+def test_transport_fields_known_answers():
+    """turbulence->muEff() / alphaEff() as fields (residualsUpdate.H:16-43 with a turbulence model; orc_transport_set):
+    a uniform field reproduces the laminar constants bit for bit; for U = (a y, 0, 0), T = T0 + t1 y, muEff = m0 + m1 y,
+    alphaEff = k0 + k1 y on an orthogonal box the interior residuals are exact:
+    x-momentum d/dy(muEff a) = m1 a;  energy d/dy(muEff a^2 y) + d/dy(alphaEff Cv t1) = a^2 (m0 + 2 m1 y) + k1 Cv t1."""
+    mu, Pr = 0.05, 0.71
+    gam = 1005.0 / (1005.0 - 287.0)
+    c0 = cases.periodic_box(5, "ROE", "vanLeer", seed=3, mu=mu, Pr=Pr)
+    c1 = cases.periodic_box(5, "ROE", "vanLeer", seed=3, mu=mu, Pr=Pr).with_transport(lambda x: (np.full(len(x), mu), np.full(len(x), gam * (mu / Pr))))
+    ra, rb = run_sequence(c0.apply(Oracle()), c0, 2), run_sequence(c1.apply(Oracle()), c1, 2)
+    for k in ra:
+        assert np.array_equal(ra[k], rb[k]), k
+    n, a, t1, m0, m1, k0, k1 = 8, 3.0, 20.0, 0.7, 0.4, 0.9, -0.5
+    mesh = mt.structured(1, n, n, n, 0, (0, 0, 0), (1.0, 1.0, 1.0), patch_kinds=(capi.PATCH,) * 6)
+    N = mesh.n_cells
+    interior = np.all((mesh.C > 0.2) & (mesh.C < 0.8), axis=1)
+    sch = capi.default_schemes(flux_scheme="HLLC", limiter_rho="linear", limiter_U="linear", limiter_T="linear")
+    U = np.zeros((N, 3)); U[:, 0] = a * mesh.C[:, 1]
+    T = 300.0 + t1 * mesh.C[:, 1]
+    case = cases.Case("k", mesh, 287.0, 1005.0, sch, capi.solver_controls(), {}, np.full(N, 1e5), U, T, mu=1.0, Pr=1.0)
+    case.with_transport(lambda x: (m0 + m1 * x[:, 1], k0 + k1 * x[:, 1]))
+    o = case.apply(Oracle())
+    o.calc_flux()
+    r = o.residual()
+    y = mesh.C[:, 1]
+    Cv = 1005.0 - 287.0
+    assert np.allclose((r[1][:, 0] / mesh.V)[interior], m1 * a, rtol=1e-9)
+    assert np.abs((r[1][:, 1:] / mesh.V[:, None])[interior]).max() < 1e-9
+    assert np.allclose((r[2] / mesh.V)[interior], (a * a * (m0 + 2 * m1 * y) + k1 * Cv * t1)[interior], rtol=1e-9)
+    # LF viscous Jacobian: lambdaVisc = (muEff_f + alphaEff_f)/rho_f on the three diagonal-variable blocks (viscousFluxScheme.C:228-240)
+    o.pseudo_dt(); o.assemble()
+    d_v, u_v, _ = o.matrix_get_ldu(0)
+    case.transport = None
+    case.mu = 0.0
+    o2 = case.apply(Oracle()); o2.calc_flux(); o2.residual(); o2.pseudo_dt(); o2.assemble()
+    d_i, u_i, _ = o2.matrix_get_ldu(0)
+    F = mesh.n_internal_faces
+    own, nei = mesh.owner[:F], mesh.neighbour
+    st = o.state_get()
+    yf = mesh.Cf[:F, 1]
+    rhof = 0.5 * (st["rho"][own] + st["rho"][nei])
+    want = 0.5 * ((m0 + m1 * yf) + (k0 + k1 * yf)) / rhof * mesh.magSf[:F] * mesh.deltaCoeffs[:F]
+    assert np.allclose((u_i - u_v)[:, 0], want, rtol=1e-9)

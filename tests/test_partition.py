@@ -27,6 +27,8 @@ def setup_world(case, n_parts, mode="x"):
                     o.bc_set(patch, {"p": 0, "U": 1, "T": 2}[field], kind, params)
         if case.mrf is not None:
             o.mrf_set(*case.mrf_fields(meshes[r]))
+        if case.transport is not None:
+            o.transport_set(*case.transport_fields(meshes[r]))
     w.state_set([case.p[m.cell_global] for m in meshes], [case.U[m.cell_global] for m in meshes], [case.T[m.cell_global] for m in meshes])
     return w, meshes
 
@@ -51,13 +53,15 @@ def test_partition_processor_patches_match():
 
 
 @pytest.mark.parametrize("n_parts,mode,mu,mrf", [(2, "x", 0.0, False), (4, (2, 2, 1), 0.0, False), (4, (2, 2, 1), 0.5, False),
-                                                 (4, (2, 2, 1), 0.0, True)])
+                                                 (4, (2, 2, 1), 0.0, True), (4, (2, 2, 1), 0.5, "transport")])
 def test_partitioned_oracle_matches_single_domain(n_parts, mode, mu, mrf):
     """Fluxes / residuals / SpMV do not depend on the decomposition (only LU-SGS and hence the GMRES history do —
     lusgs.C:149,181 keeps the sweeps rank-local).  mu > 0 adds the viscous residual, whose processor-patch faces need the
     neighbour's gradients of U and eCalc."""
     case = cases.onera_box(6, mu=mu)
-    if mrf:  # rotating zone in half of the domain: MRFFaceVelocity on processor faces is each side's own (outward) value
+    if mrf == "transport":  # muEff / alphaEff fields: processor halos carry the neighbour's cell values
+        case.with_transport(lambda x: (0.5 * (1.2 + np.sin(2.0 * x[:, 0]) * np.cos(x[:, 2])), 0.8 * (1.1 + np.cos(1.5 * x[:, 1]))))
+    elif mrf:  # rotating zone in half of the domain: MRFFaceVelocity on processor faces is each side's own (outward) value
         case.with_mrf(omega=(0.0, 40.0, 90.0), origin=(0.5, 0.0, 1.5), zone=lambda x: x[:, 0] > 0.2)
     single = case.apply(Oracle())
     phi, phiUp, phiEp = single.calc_flux()
