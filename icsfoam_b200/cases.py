@@ -189,6 +189,33 @@ def periodic_box(n=8, flux="HLLC", limiter="vanLeer", seed=0, nz=None, cyclic=Tr
     return Case("periodic-box", mesh, 287.0, 1005.0, sch, ctl, bcs, p, U, T, mu=mu, Pr=Pr)
 
 
+def rot_box(n=6, flux="HLLC", limiter="vanLeer", seed=0, nz=None):
+    """A 90-degree sector: the cube [0,1]^2 x [0,0.9] whose faces x=0 and y=0 form a ROTATIONAL cyclic pair about the z axis
+    through the corner (four copies tile the plane around it).  forwardT of `xmin` is the rotation by +90 degrees about z
+    (it turns the outward normal -y of `ymin` into +x).  Random state: a parity workhorse for
+    cyclicFvPatchField::patchNeighbourField with doTransform() — SURVEY 8f-4."""
+    mesh = mt.structured(1, n, n, nz or n, 0, (0, 0, 0), (1.0, 1.0, 0.9),
+                         patch_kinds=(capi.PATCH, capi.PATCH, capi.PATCH, capi.PATCH, capi.SYMMETRYPLANE, capi.PATCH))
+    mesh.set_cyclic_rotational("xmin", "ymin", [[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    rng = np.random.default_rng(seed)
+    N = mesh.n_cells
+    p = 1e5 * (1 + 0.2 * rng.random(N))
+    T = 300 * (1 + 0.2 * rng.random(N))
+    U = 150 * (rng.random((N, 3)) - 0.3)
+    sch = capi.default_schemes(flux_scheme=flux, limiter_rho=limiter, limiter_U=limiter, limiter_T=limiter,
+                               ddt_scheme="steadyState", pseudo_co_num=5.0, pseudo_co_num_max=50.0)
+    ctl = capi.solver_controls("LUSGS", n_directions=5, max_iter=10, tolerance=1e-10, rel_tol=1e-3)
+    zg, slip = ("zeroGradient", ()), ("slip", ())
+    bcs = {
+        "xmax": {"p": zg, "U": slip, "T": zg},
+        "ymax": {"p": ("fixedValue", (1.05e5,)), "U": ("inletOutlet", (50.0, 10.0, 0.0)), "T": ("inletOutlet", (310.0,))},
+        "zmin": {"p": slip, "U": slip, "T": slip},
+        "zmax": {"p": ("freestreamPressure", (1.0e5, 50.0, 10.0, 20.0)), "U": ("freestream", (50.0, 10.0, 20.0)),
+                 "T": ("fixedValue", (305.0,))},
+    }
+    return Case("rot-box", mesh, 287.0, 1005.0, sch, ctl, bcs, p, U, T)
+
+
 def scrambled_box(n=6, flux="HLLC", limiter="vanLeer", seed=0, mu=0.0):
     """A box whose cells are renumbered at random: irregular LU-SGS levels, rows with up to 6 lower (or upper)
     neighbours, no structure for the tile heuristics to find — the 'unstructured numbering' stress case."""

@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -68,6 +69,13 @@ struct AmiPatchDev {
     int* d_srcPos;   // [nnz] positions of the neighbour patch's face cells
     double* d_w;     // [nnz]
 };
+// rotational cyclic patch on the device: halo slots [NP+haloStart, +size) receive transform(forwardT, phi[srcPos_i]) —
+// vector triples rotated, scalars copied (cyclicFvPatchField::patchNeighbourField with doTransform())
+struct RotPatchDev {
+    int size, haloStart;
+    int* d_srcPos;   // [size] positions of the neighbour patch's face cells
+    double T[9];     // forwardT, row-major
+};
 struct AmiTable { std::vector<int> start, face; std::vector<double> weight; };
 
 struct icsb200_ctx {
@@ -83,6 +91,7 @@ struct icsb200_ctx {
     std::vector<int> owner, neighbour;
     std::vector<icsb200_patch> patches;
     std::vector<int> bfacePatch;  // [NB] patch of a boundary face (-1: empty)
+    std::vector<int> bfNbrSlot;   // [NB] coupled faces: extended slot holding the patchNeighbourField (neighbour cell or halo slot); else -1
     int solutionD[3] = {1, 1, 1};
     bool meshSet = false, stateSet = false, matrixSet = false, fluxValid = false, thermoSet = false;
 
@@ -126,6 +135,7 @@ struct icsb200_ctx {
     // processor patches
     std::vector<ProcPatchDev> procs;
     std::vector<AmiPatchDev> amis;                 // cyclicAMI patches (local weighted gathers into halo slots)
+    std::vector<RotPatchDev> rots;                 // rotational cyclic patches (local gathers + rotation of the vector triples)
     std::vector<std::pair<int, AmiTable>> pendingAmi;  // icsb200_ami_set tables waiting for mesh_set
     double *d_sendBuf = nullptr, *d_recvBuf = nullptr;
 
@@ -263,7 +273,14 @@ int ics_upload_cells(icsb200_ctx* c, const double* host, int nc, double* dst, si
 int ics_download_cells(icsb200_ctx* c, double* host, int nc, const double* src, size_t stride);
 int ics_eval_bc(icsb200_ctx* c, bool init);
 int ics_primitives(icsb200_ctx* c);  // derived fields from p,T,U,rho (cells + boundary slots)
-int ics_halo_fields(icsb200_ctx* c, double* base, size_t stride, int nArrays);
+// vecMask: bit a set = arrays a, a+1, a+2 are the components of a vector (rotated on rotational cyclic patches)
+int ics_halo_fields(icsb200_ctx* c, double* base, size_t stride, int nArrays, unsigned vecMask = 0u);
+inline bool ics_is_rotational(const icsb200_patch& p)
+{
+    if (p.kind != ICSB200_CYCLIC && p.kind != ICSB200_CYCLICAMI) return false;
+    for (int k = 0; k < 9; k++) if (std::fabs(p.forwardT[k] - (k % 4 == 0 ? 1.0 : 0.0)) > 1e-12) return true;
+    return false;
+}
 int ics_gradients(icsb200_ctx* c);
 int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux);
 int ics_pseudo_ser(icsb200_ctx* c);

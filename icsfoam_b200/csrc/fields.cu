@@ -303,11 +303,12 @@ __global__ void k_fill(int n, double v, double* __restrict__ dst)
     if (p < n) dst[p] = v;
 }
 
-__global__ void k_gather_boundary(int NB, int off, const double* __restrict__ f, size_t NX, double* __restrict__ out)
+__global__ void k_gather_boundary(int NB, int off, const int* __restrict__ nbrSlot, const double* __restrict__ f, size_t NX, double* __restrict__ out)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= NB) return;
-    size_t s = (size_t)off + b;
+    // coupled faces report the patchNeighbourField (neighbour cell / halo slot), as the boundaryField of a coupled patch does
+    size_t s = (nbrSlot && nbrSlot[b] >= 0) ? (size_t)nbrSlot[b] : (size_t)off + b;
     out[b] = f[Q_RHO * NX + s];
     out[NB + 3 * (size_t)b] = f[Q_UX * NX + s]; out[NB + 3 * (size_t)b + 1] = f[Q_UY * NX + s]; out[NB + 3 * (size_t)b + 2] = f[Q_UZ * NX + s];
     out[4 * (size_t)NB + b] = f[Q_P * NX + s];
@@ -339,7 +340,7 @@ int ics_primitives(icsb200_ctx* c)
     }
     CUDA_TRY(c, cudaGetLastError());
     // neighbour-rank copies of the arrays the face kernels gather: rho p Ux Uy Uz cR E H c (+ eCalc) (contiguous ids 0..9)
-    return ics_halo_fields(c, c->d_fields, c->NX, c->mu > 0 ? 10 : 9);
+    return ics_halo_fields(c, c->d_fields, c->NX, c->mu > 0 ? 10 : 9, 1u << Q_UX);
 }
 
 // conserved variables + boundary + derived fields from freshly uploaded p, U, T (host-facing iterate)
@@ -479,13 +480,20 @@ extern "C" int icsb200_boundary_get(icsb200_ctx* c, double* rho_b, double* U_b, 
     if (NB == 0) return 0;
     int r = ics_ensure_stage(c, sizeof(double) * 6 * (size_t)NB);
     if (r) return r;
+    int* d_nbr = nullptr;
+    if (c->NH > 0 && (r = ics_halo_fields(c, c->q(Q_T), c->NX, 1))) return r;   // T is not part of the per-iteration halo set
+    if ((int)c->bfNbrSlot.size() == NB) {
+        CUDA_TRY(c, cudaMalloc((void**)&d_nbr, sizeof(int) * NB));
+        CUDA_TRY(c, cudaMemcpyAsync(d_nbr, c->bfNbrSlot.data(), sizeof(int) * NB, cudaMemcpyHostToDevice, c->stream));
+    }
     {
         LaunchScope ls(c, TM_PERM);
-        k_gather_boundary<<<gridFor(NB, 128), 128, 0, c->stream>>>(NB, c->NP + c->NH, c->d_fields, c->NX, c->d_stage);
+        k_gather_boundary<<<gridFor(NB, 128), 128, 0, c->stream>>>(NB, c->NP + c->NH, d_nbr, c->d_fields, c->NX, c->d_stage);
     }
     std::vector<double> h(6 * (size_t)NB);
     CUDA_TRY(c, cudaMemcpyAsync(h.data(), c->d_stage, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (d_nbr) cudaFree(d_nbr);
     if (rho_b) std::copy(h.begin(), h.begin() + NB, rho_b);
     if (U_b) std::copy(h.begin() + NB, h.begin() + 4 * (size_t)NB, U_b);
     if (p_b) std::copy(h.begin() + 4 * (size_t)NB, h.begin() + 5 * (size_t)NB, p_b);

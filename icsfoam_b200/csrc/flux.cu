@@ -638,7 +638,11 @@ int ics_gradients(icsb200_ctx* c)
         c->launches++;
     }
     CUDA_TRY(c, cudaGetLastError());
-    int r = ics_halo_fields(c, c->d_grad, c->NPH, NQ * 3);
+    // every gradient is a vector: on rotational cyclic patches each is rotated on its own (transform(forwardT, grad(phi)), also
+    // for phi = "U.component(i)": cyclicFvPatchField<vector> of a field whose name does not start with "U")
+    unsigned gradMask = 0;
+    for (int k = 0; k < NQ; k++) gradMask |= 1u << (3 * k);
+    int r = ics_halo_fields(c, c->d_grad, c->NPH, NQ * 3, gradMask);
     if (r || !(c->mu > 0)) return r;
     // viscous runs: gradient of eCalc for the non-orthogonal correction of laplacian(alphaEff, e)
     if (!c->d_gradE) {
@@ -651,7 +655,7 @@ int ics_gradients(icsb200_ctx* c)
                                                              c->d_geo, c->NFG, c->d_V, c->q(Q_EC), c->NX, c->d_gradE, c->NPH);
     }
     CUDA_TRY(c, cudaGetLastError());
-    return ics_halo_fields(c, c->d_gradE, c->NPH, 3);
+    return ics_halo_fields(c, c->d_gradE, c->NPH, 3, 1u);
 }
 
 int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)

@@ -139,6 +139,7 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
     for (auto& am : c->amis) { cudaFree(am.d_start); cudaFree(am.d_srcPos); cudaFree(am.d_w); }
+    for (auto& ro : c->rots) cudaFree(ro.d_srcPos);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaEventDestroy(c->ev0);
@@ -205,6 +206,7 @@ extern "C" int icsb200_thermo_set(icsb200_ctx* c, double R, double Cp, double mu
 {
     c->reconValid = false;
     if (!(R > 0) || !(Cp > R)) return ics_fail(c, ICSB200_EINVAL, "thermo: need Cp > R > 0");
+    if (mu > 0 && !c->rots.empty()) return ics_fail(c, ICSB200_EINVAL, "thermo: viscous runs with rotational cyclic patches are not supported");
     c->R = R; c->Cp = Cp; c->Cv = Cp - R; c->gamma = Cp / c->Cv; c->mu = mu; c->Pr = Pr;
     c->thermoSet = true;
     return 0;
@@ -282,14 +284,12 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             if (!t || (int)t->start.size() != p.size + 1) return ics_fail(c, ICSB200_EINVAL, "mesh_set: cyclicAMI patch without a matching icsb200_ami_set");
             for (int fidx : t->face) if (fidx < 0 || fidx >= patches[p.nbr_patch].size) return ics_fail(c, ICSB200_EINVAL, "mesh_set: cyclicAMI address outside the neighbour patch");
         }
-        if (p.kind == ICSB200_CYCLIC || p.kind == ICSB200_CYCLICAMI) {
-            // translational cyclics only: a rotational pair needs the component-wise transform of U, grad and rhoU in
-            // patchNeighbourField (originalOFFiles/constraintFvPatchFields/cyclic/cyclicFvPatchField.C:130-190) — SURVEY 8f-4
-            static const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-            for (int k = 0; k < 9; k++)
-                if (std::fabs(p.forwardT[k] - I9[k]) > 1e-12)
-                    return ics_fail(c, ICSB200_EINVAL, "mesh_set: rotational cyclic patches (forwardT != I) are not supported");
-        }
+        // rotational pairs (forwardT != I): plain cyclic only; patchNeighbourField = transform(forwardT, neighbour value)
+        // (originalOFFiles/constraintFvPatchFields/cyclic/cyclicFvPatchField.C:130-190) through local halo slots
+        if (p.kind == ICSB200_CYCLICAMI && ics_is_rotational(p))
+            return ics_fail(c, ICSB200_EINVAL, "mesh_set: rotational cyclicAMI patches (forwardT != I) are not supported");
+        if (p.kind == ICSB200_CYCLIC && ics_is_rotational(p) && c->mu > 0)
+            return ics_fail(c, ICSB200_EINVAL, "mesh_set: viscous runs with rotational cyclic patches are not supported");
         if (p.kind == ICSB200_PROCESSOR && (p.nbr_rank < 0 || p.nbr_rank >= c->nRanks || c->nRanks == 1))
             return ics_fail(c, ICSB200_EINVAL, "mesh_set: processor patch needs a multi-rank context");
         if ((p.kind == ICSB200_CYCLIC || p.kind == ICSB200_PROCESSOR || p.kind == ICSB200_CYCLICAMI) && !Cf) return ics_fail(c, ICSB200_EINVAL, "mesh_set: coupled patches need Cf");
@@ -437,7 +437,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     int NH = 0;
     std::vector<int> patchHaloStart(n_patches, -1);
     for (int pi = 0; pi < n_patches; pi++)
-        if (patches[pi].kind == ICSB200_PROCESSOR || patches[pi].kind == ICSB200_CYCLICAMI) { patchHaloStart[pi] = NH; NH += patches[pi].size; }
+        if (patches[pi].kind == ICSB200_PROCESSOR || patches[pi].kind == ICSB200_CYCLICAMI || ics_is_rotational(patches[pi])) { patchHaloStart[pi] = NH; NH += patches[pi].size; }
     NH += NH & 1;  // keep NPH even: every component array of a cell vector then starts 16-byte aligned (TMA bulk copies)
     c->NH = NH; c->NPH = NP + NH; c->NX = NP + NH + NB;
 
@@ -476,15 +476,19 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             size_t su = slot(po, nLowC[o] + fillUp[o]++);
             c->h_col[su] = pn; c->h_meta[su] = ET_UPPER | (f << 2);
         }
+        c->bfNbrSlot.assign(NB, -1);
         for (int b = 0; b < NB; b++) {
             int pi = c->bfacePatch[b];
             if (pi < 0) continue;
             int f = F + b, o = owner[f], po = c->cell2pos[o];
             size_t sb = slot(po, nLowC[o] + nUpC[o] + fillB[o]++);
             const icsb200_patch& pa = patches[pi];
-            if (pa.kind == ICSB200_CYCLIC) {
+            if (pa.kind == ICSB200_CYCLIC && !ics_is_rotational(pa)) {
                 int nbrFace = patches[pa.nbr_patch].start + (f - pa.start);
                 c->h_col[sb] = c->cell2pos[owner[nbrFace]];
+                c->h_meta[sb] = ET_COUPLED | (f << 2);
+            } else if (pa.kind == ICSB200_CYCLIC) {   // rotational: the transformed neighbour values live in a local halo slot
+                c->h_col[sb] = NP + patchHaloStart[pi] + (f - pa.start);
                 c->h_meta[sb] = ET_COUPLED | (f << 2);
             } else if (pa.kind == ICSB200_PROCESSOR || pa.kind == ICSB200_CYCLICAMI) {
                 c->h_col[sb] = NP + patchHaloStart[pi] + (f - pa.start);
@@ -493,6 +497,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                 c->h_col[sb] = NP + NH + b;  // boundary-value slot
                 c->h_meta[sb] = ET_PHYS | (f << 2);
             }
+            if ((c->h_meta[sb] & 3) == ET_COUPLED) c->bfNbrSlot[b] = c->h_col[sb];
         }
     }
     // per-slice entry ranges the LU-SGS sweeps touch: forward [0, max nLow), reverse [min nLow over rows with uppers, max nInt)
@@ -583,8 +588,18 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
         const icsb200_patch& pa = patches[pi];
         if (pa.kind == ICSB200_CYCLIC) {
             const icsb200_patch& qa = patches[pa.nbr_patch];
-            for (int i = 0; i < pa.size; i++)
-                for (int d = 0; d < 3; d++) nbrDelta[3 * (size_t)(pa.start + i - F) + d] = ownDelta[3 * (size_t)(qa.start + i - F) + d];
+            const bool rot = ics_is_rotational(pa);   // cyclicFvPatch::delta(): patchD - transform(forwardT, nbrPatchD)
+            const double* T = pa.forwardT;
+            for (int i = 0; i < pa.size; i++) {
+                const double* s3 = &ownDelta[3 * (size_t)(qa.start + i - F)];
+                double* d3 = &nbrDelta[3 * (size_t)(pa.start + i - F)];
+                if (rot) {
+                    d3[0] = T[0] * s3[0] + T[1] * s3[1] + T[2] * s3[2];
+                    d3[1] = T[3] * s3[0] + T[4] * s3[1] + T[5] * s3[2];
+                    d3[2] = T[6] * s3[0] + T[7] * s3[1] + T[8] * s3[2];
+                } else
+                    for (int d = 0; d < 3; d++) d3[d] = s3[d];
+            }
         } else if (pa.kind == ICSB200_CYCLICAMI) {
             // cyclicAMIFvPatch::delta(): patchD - interpolate(nbrPatch.coupledFvPatch::delta())
             const icsb200_patch& qa = patches[pa.nbr_patch];
@@ -729,6 +744,18 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
         for (int i = 0; i < pp.size; i++) sp[i] = c->cell2pos[owner[patches[pi].start + i]];
         r |= devUpload(c, &pp.d_sendPos, sp);
         c->procs.push_back(pp);
+    }
+    for (auto& ro : c->rots) cudaFree(ro.d_srcPos);
+    c->rots.clear();
+    for (int pi = 0; pi < n_patches; pi++) {
+        if (!ics_is_rotational(patches[pi])) continue;
+        RotPatchDev ro{};
+        ro.size = patches[pi].size; ro.haloStart = patchHaloStart[pi]; ro.d_srcPos = nullptr;
+        std::memcpy(ro.T, patches[pi].forwardT, sizeof(ro.T));
+        std::vector<int> sp(ro.size);
+        for (int i = 0; i < ro.size; i++) sp[i] = c->cell2pos[owner[patches[patches[pi].nbr_patch].start + i]];
+        r |= devUpload(c, &ro.d_srcPos, sp);
+        c->rots.push_back(ro);
     }
     for (auto& am : c->amis) { cudaFree(am.d_start); cudaFree(am.d_srcPos); cudaFree(am.d_w); }
     c->amis.clear();

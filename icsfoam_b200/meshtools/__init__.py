@@ -102,6 +102,31 @@ class Mesh:
             self.deltaCoeffs[fa] = 1.0 / md
             self.nonOrthDeltaCoeffs[fa] = 1.0 / np.maximum(np.einsum("ij,ij->i", nfa, d), 0.05 * md)
 
+    def set_cyclic_rotational(self, a, b, T):
+        """Turn two equally-sized patches into a ROTATIONAL cyclic pair: face i of `a` coincides with face i of `b` after
+        rotating b's frame by T (forwardT of `a`: a vector seen from b's side becomes T.v on a's side; forwardT of `b` is T^T).
+        Weights / deltas as cyclicFvPatch::makeWeights and cyclicFvPatch::delta() = patchD - transform(forwardT, nbrPatchD)."""
+        T = np.asarray(T, float).reshape(3, 3)
+        ia, ib = self.patch_index(a), self.patch_index(b)
+        lib = _lib()
+        lib.icsmesh_set_patch_kind(self._h, ia, CYCLIC, ib)
+        lib.icsmesh_set_patch_kind(self._h, ib, CYCLIC, ia)
+        self.patches[ia].update(kind=CYCLIC, nbr_patch=ib, forwardT=[float(v) for v in T.reshape(-1)])
+        self.patches[ib].update(kind=CYCLIC, nbr_patch=ia, forwardT=[float(v) for v in T.T.reshape(-1)])
+        for pa, pb, R in ((self.patches[ia], self.patches[ib], T), (self.patches[ib], self.patches[ia], T.T)):
+            fa = np.arange(pa["start"], pa["start"] + pa["size"])
+            fb = np.arange(pb["start"], pb["start"] + pb["size"])
+            nfa = self.Sf[fa] / self.magSf[fa, None]
+            nfb = self.Sf[fb] / self.magSf[fb, None]
+            dA, dB = self.Cf[fa] - self.C[self.owner[fa]], self.Cf[fb] - self.C[self.owner[fb]]
+            da = np.abs(np.einsum("ij,ij->i", nfa, dA))
+            db = np.abs(np.einsum("ij,ij->i", nfb, dB))
+            self.weights[fa] = db / (da + db)
+            d = dA - dB @ R.T
+            md = np.linalg.norm(d, axis=1)
+            self.deltaCoeffs[fa] = 1.0 / md
+            self.nonOrthDeltaCoeffs[fa] = 1.0 / np.maximum(np.einsum("ij,ij->i", nfa, d), 0.05 * md)
+
     def set_cyclic_ami(self, a, b, shift=0.5):
         """Turn two plane patches into a translational cyclicAMI pair whose faces do not match: the neighbour patch is
         shifted by `shift` cells along the first in-plane direction (periodic wrap), so every face overlaps two

@@ -38,7 +38,9 @@ typedef struct {
     int start, size;    /* face range [start, start+size) in the global face list */
     int nbr_rank;       /* PROCESSOR: neighbProcNo */
     int nbr_patch;      /* CYCLIC: index of the neighbour patch */
-    double forwardT[9]; /* CYCLIC: rotation tensor; must be the identity (translational pair) in this build, else EINVAL */
+    double forwardT[9]; /* CYCLIC: cyclicPolyPatch::forwardT() row-major — patchNeighbourField = transform(forwardT, neighbour
+                         * value) (cyclicFvPatchField.C:130-190): identity = translational pair; a rotation = rotational pair
+                         * (inviscid runs; viscous + rotational and rotational CYCLICAMI return EINVAL) */
 } icsb200_patch;
 
 /* run-time selectors — same words as the reference dictionaries */

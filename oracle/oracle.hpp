@@ -33,6 +33,7 @@ inline double stabilise(double x, double y) { return x < 0 ? x - y : x + y; }
 struct Patch {
     int kind, start, size, nbrRank, nbrPatch;
     double forwardT[9];
+    bool rotational = false;  // cyclic with forwardT != I: patchNeighbourField = transform(forwardT, neighbour cell value)
     // cyclicAMI: CSR over the patch faces of (face index within the neighbour patch, weight)
     veci amiStart, amiFace;
     vecd amiWeight;

@@ -69,6 +69,14 @@ struct ThreadComm : Comm {
 
 int fail(Ctx* c, int code, const char* msg) { c->err = msg; return code; }
 
+// the viscous terms need transform(forwardT, tensor) of grad(U) / tauMC on rotational cyclic patches: not restated
+bool rotationalViscous(const Ctx* c)
+{
+    if (!(c->mu > 0)) return false;
+    for (auto& p : c->m.patches) if (p.rotational) return true;
+    return false;
+}
+
 }  // namespace
 
 extern "C" {
@@ -112,13 +120,15 @@ int orc_mesh_set(Ctx* c, int n_cells, int n_internal_faces, int n_faces, const i
         }
         if (p.kind == ICSB200_CYCLIC || p.kind == ICSB200_CYCLICAMI)
             for (int k = 0; k < 9; k++)
-                if (std::fabs(p.forwardT[k] - (k % 4 == 0 ? 1.0 : 0.0)) > 1e-12) return fail(c, ICSB200_EINVAL, "rotational cyclic patches (forwardT != I) are not supported");
+                if (std::fabs(p.forwardT[k] - (k % 4 == 0 ? 1.0 : 0.0)) > 1e-12) p.rotational = true;
+        if (p.rotational && p.kind == ICSB200_CYCLICAMI) return fail(c, ICSB200_EINVAL, "rotational cyclicAMI patches (forwardT != I) are not supported");
         m.patches.push_back(p);
     }
     for (int d = 0; d < 3; d++) m.solutionD[d] = solutionD[d];
     for (int f = 0; f < m.F; f++) if (m.owner[f] >= m.neighbour[f]) return fail(c, ICSB200_EINVAL, "mesh is not in upper-triangular order");
     meshFinalize(*c);
     c->meshSet = true;
+    if (rotationalViscous(c)) return fail(c, ICSB200_EINVAL, "viscous runs with rotational cyclic patches are not supported");
     return 0;
 }
 
@@ -136,6 +146,7 @@ int orc_ami_set(Ctx* c, int patch, int n_faces, const int* face_start, const int
 int orc_thermo_set(Ctx* c, double R, double Cp, double mu, double Pr)
 {
     c->R = R; c->Cp = Cp; c->Cv = Cp - R; c->gamma = Cp / c->Cv; c->mu = mu; c->Pr = Pr;
+    if (rotationalViscous(c)) return fail(c, ICSB200_EINVAL, "viscous runs with rotational cyclic patches are not supported");
     return 0;
 }
 

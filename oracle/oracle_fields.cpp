@@ -39,7 +39,17 @@ void meshFinalize(Ctx& c)
         if (p.kind == ICSB200_CYCLIC) {
             auto& q = m.patches[p.nbrPatch];
             for (int i = 0; i < p.size; i++)
-                for (int d = 0; d < 3; d++) nbr[3 * (p.start + i - m.F) + d] = own[3 * (q.start + i - m.F) + d];
+                {   // cyclicFvPatch::delta(): patchD - transform(forwardT, nbrPatchD)
+                    const double* s3 = &own[3 * (size_t)(q.start + i - m.F)];
+                    double* d3 = &nbr[3 * (size_t)(p.start + i - m.F)];
+                    if (p.rotational) {
+                        const double* T = p.forwardT;
+                        d3[0] = T[0] * s3[0] + T[1] * s3[1] + T[2] * s3[2];
+                        d3[1] = T[3] * s3[0] + T[4] * s3[1] + T[5] * s3[2];
+                        d3[2] = T[6] * s3[0] + T[7] * s3[1] + T[8] * s3[2];
+                    } else
+                        for (int d = 0; d < 3; d++) d3[d] = s3[d];
+                }
         } else if (p.kind == ICSB200_PROCESSOR) {
             c.comm->exchange(p.nbrRank, &own[3 * (p.start - m.F)], &nbr[3 * (p.start - m.F)], 3 * p.size);
         } else if (p.kind == ICSB200_CYCLICAMI) {
@@ -70,10 +80,23 @@ void syncCoupled(Ctx& c, vecd& vf, int nc)
     Mesh& m = c.m;
     for (auto& p : m.patches) {
         if (p.kind == ICSB200_CYCLIC) {
+            // cyclicFvPatchField::patchNeighbourField (originalOFFiles/constraintFvPatchFields/cyclic/cyclicFvPatchField.C:130-190):
+            // transform(forwardT, neighbour cell value) when the pair is rotational — vectors are rotated, scalars unchanged;
+            // the scalar fields "U.component(i)" take component i of the rotated cell velocity, which is what the callers
+            // get by extracting the components AFTER this call on U itself
             auto& q = m.patches[p.nbrPatch];
+            const double* T = p.forwardT;
             for (int i = 0; i < p.size; i++) {
                 int nb = m.owner[q.start + i];
-                for (int d = 0; d < nc; d++) vf[(size_t)nc * (m.N + p.start - m.F + i) + d] = vf[(size_t)nc * nb + d];
+                double* dst = &vf[(size_t)nc * (m.N + p.start - m.F + i)];
+                const double* src = &vf[(size_t)nc * nb];
+                if (p.rotational && nc == 3) {
+                    const double v0 = src[0], v1 = src[1], v2 = src[2];
+                    dst[0] = T[0] * v0 + T[1] * v1 + T[2] * v2;
+                    dst[1] = T[3] * v0 + T[4] * v1 + T[5] * v2;
+                    dst[2] = T[6] * v0 + T[7] * v1 + T[8] * v2;
+                } else
+                    for (int d = 0; d < nc; d++) dst[d] = src[d];
             }
         } else if (p.kind == ICSB200_CYCLICAMI) {
             // cyclicAMIFvPatchField::patchNeighbourField = AMI.interpolate(neighbour cell values): result = 0; result += w*phi

@@ -76,6 +76,10 @@ LIVE = {
     "box-transport-ami-hllc": lambda: cases.periodic_box(5, "HLLC", "Minmod", seed=92, mu=0.1, ami_shift=0.3).with_transport(TURB),
     "bump-transport": lambda: cases.bump(15, 10, mu=0.02).with_transport(TURB),
     "scrambled-transport-mrf": lambda: cases.scrambled_box(5, "HLLC", "vanLeer", seed=93, mu=0.1).with_transport(TURB).with_mrf((40.0, 0.0, -70.0), (0.2, 0.2, 0.2)),
+    # rotational cyclic pair (90-degree sector): U, gradients and the rhoU operand rotated across the pair
+    "rot-hllc-vanleer": lambda: cases.rot_box(6, "HLLC", "vanLeer", seed=62),
+    "rot-roe-minmod": lambda: cases.rot_box(5, "ROE", "Minmod", seed=63, nz=4),
+    "rot-ausm-mrf": lambda: cases.rot_box(5, "AUSMPlusUp", "vanLeer", seed=64).with_mrf((0.0, 0.0, 60.0)),
     "shocktube-ausm": lambda: cases.shock_tube(64, "AUSMPlusUp"),
     "shocktube-roe": lambda: cases.shock_tube(50, "ROE"),
 }
@@ -94,6 +98,13 @@ def test_bitwise_equality_of_reduction_free_kernels(gpu_context):
     SpMV, LU-SGS and block-Jacobi."""
     case = cases.periodic_box(6, "HLLC", "vanLeer", seed=31)
     o, g = case.apply(Oracle()), case.apply(gpu_context())
+    bo, bg = o.boundary_get(), g.boundary_get()       # coupled faces report the patchNeighbourField
+    for k in ("rho", "U", "p", "T"):
+        assert np.array_equal(bo[k], bg[k]), k
+    ami = cases.periodic_box(5, "ROE", "vanLeer", seed=32, ami_shift=0.3)
+    bo, bg = ami.apply(Oracle()).boundary_get(), ami.apply(gpu_context()).boundary_get()
+    for k in ("rho", "U", "p", "T"):
+        assert rel_err(bg[k], bo[k]) <= 1e-14, k          # T and rho are interpolated separately on the two sides
     for a, b in zip(g.calc_flux(), o.calc_flux()):
         assert np.array_equal(a, b)
     for a, b in zip(g.residual(), o.residual()):
@@ -341,14 +352,42 @@ def test_forward_step_c2_polyhedral_mesh(gpu_context):
         assert rel_err(sg[k], so[k]) <= TOL_STATE, k
 
 
-def test_rotational_cyclic_is_refused(gpu_context):
-    """forwardT != I would silently give translational results: both implementations must refuse it."""
-    case = cases.periodic_box(4)
-    for p in case.mesh.patches:
-        if p["kind"] == capi.CYCLIC:
+def test_rotational_cyclic_bitwise_and_refusals(gpu_context):
+    """Rotational cyclic pairs on the device (local halo slots filled by k_rot_gather: vector triples rotated by forwardT,
+    scalars copied): every reduction-free stage bit for bit against the oracle; rotational cyclicAMI and viscous runs with
+    rotational pairs are refused by both."""
+    case = cases.rot_box(6, "HLLC", "vanLeer", seed=61)
+    o, g = case.apply(Oracle()), case.apply(gpu_context())
+    bo, bg = o.boundary_get(), g.boundary_get()
+    for k in ("rho", "U", "p", "T"):
+        assert np.array_equal(bo[k], bg[k]), k
+    for a, b in zip(g.calc_flux(), o.calc_flux()):
+        assert np.array_equal(a, b)
+    for a, b in zip(g.residual(), o.residual()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(g.pseudo_dt()[0], o.pseudo_dt()[0])
+    g.assemble(); o.assemble()
+    for blk in range(9):
+        for a, b in zip(g.matrix_get_ldu(blk), o.matrix_get_ldu(blk)):
+            assert np.array_equal(a, b), blk
+    rng = np.random.default_rng(0)
+    N = case.mesh.n_cells
+    x = (rng.standard_normal(N), rng.standard_normal((N, 3)), rng.standard_normal(N))
+    for a, b in zip(g.matrix_mul(*x), o.matrix_mul(*x)):      # the rhoU part of the operand is rotated across the pair
+        assert np.array_equal(a, b)
+    for pk in ("LUSGS", "Jacobi"):
+        for a, b in zip(g.precondition(pk, *x), o.precondition(pk, *x)):
+            assert np.array_equal(a, b), pk
+    visc = cases.rot_box(4)
+    visc.mu = 0.1
+    with pytest.raises(capi.ApiError):
+        visc.apply(gpu_context())
+    ami = cases.periodic_box(4, ami_shift=0.5)
+    for p in ami.mesh.patches:
+        if p["kind"] == capi.CYCLICAMI:
             p["forwardT"] = [0, -1, 0, 1, 0, 0, 0, 0, 1]
     with pytest.raises(capi.ApiError):
-        case.apply(gpu_context())
+        ami.apply(gpu_context())
 
 
 LOCAL_VKI = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cases_local", "VKI-LS89", "constant", "polyMesh")
