@@ -189,7 +189,7 @@ def periodic_box(n=8, flux="HLLC", limiter="vanLeer", seed=0, nz=None, cyclic=Tr
     return Case("periodic-box", mesh, 287.0, 1005.0, sch, ctl, bcs, p, U, T, mu=mu, Pr=Pr)
 
 
-def rot_box(n=6, flux="HLLC", limiter="vanLeer", seed=0, nz=None):
+def rot_box(n=6, flux="HLLC", limiter="vanLeer", seed=0, nz=None, mu=0.0):
     """A 90-degree sector: the cube [0,1]^2 x [0,0.9] whose faces x=0 and y=0 form a ROTATIONAL cyclic pair about the z axis
     through the corner (four copies tile the plane around it).  forwardT of `xmin` is the rotation by +90 degrees about z
     (it turns the outward normal -y of `ymin` into +x).  Random state: a parity workhorse for
@@ -213,7 +213,45 @@ def rot_box(n=6, flux="HLLC", limiter="vanLeer", seed=0, nz=None):
         "zmax": {"p": ("freestreamPressure", (1.0e5, 50.0, 10.0, 20.0)), "U": ("freestream", (50.0, 10.0, 20.0)),
                  "T": ("fixedValue", (305.0,))},
     }
-    return Case("rot-box", mesh, 287.0, 1005.0, sch, ctl, bcs, p, U, T)
+    return Case("rot-box", mesh, 287.0, 1005.0, sch, ctl, bcs, p, U, T, mu=mu, Pr=0.71)
+
+
+def sector_and_annulus(n=6, mu=0.0, flux="ROE", limiter="upwind", seed=3):
+    """A 90-degree sector with a ROTATIONAL cyclic pair and the full annulus it stands for: the square [-1,1]^2 tiled by four
+    rotated copies of the sector [0,1]^2, with the rotation-symmetric copy of the sector's (random) state and rotation-
+    covariant boundary conditions (slip walls).  Returns (sector case, annulus case, annulus cells of the first quadrant,
+    matching sector cells).  2-D (empty z patches).  Both runs must agree wherever the reference's treatment of the pair is
+    exact: first-order reconstruction (see DESIGN Q13 for the limited one) and all viscous terms."""
+    T = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    kinds = (capi.PATCH, capi.PATCH, capi.PATCH, capi.PATCH, capi.EMPTY, capi.EMPTY)
+    sec = mt.structured(1, n, n, 1, 0, (0, 0, 0), (1.0, 1.0, 0.1), patch_kinds=kinds)
+    sec.set_cyclic_rotational("xmin", "ymin", T)
+    full = mt.structured(1, 2 * n, 2 * n, 1, 0, (-1.0, -1.0, 0), (1.0, 1.0, 0.1), patch_kinds=kinds)
+    rng = np.random.default_rng(seed)
+    N = sec.n_cells
+    p0, T0 = 1e5 * (1 + 0.1 * rng.random(N)), 300 * (1 + 0.1 * rng.random(N))
+    U0 = 80 * (rng.random((N, 3)) - 0.4)
+    U0[:, 2] = 0
+    Xk, turns = full.C.copy(), np.zeros(full.n_cells, int)
+    for _ in range(3):                                   # rotate back by -90 degrees until the centre lies in the sector
+        todo = ~((Xk[:, 0] > 0) & (Xk[:, 1] > 0))
+        Xk[todo] = Xk[todo] @ T
+        turns[todo] += 1
+    key = lambda P: np.round(P[:, 0] * n - 0.5).astype(int) + n * np.round(P[:, 1] * n - 0.5).astype(int)
+    lut = np.empty(N, int)
+    lut[key(sec.C)] = np.arange(N)
+    src = lut[key(Xk)]
+    UF = U0[src].copy()
+    for q in range(1, 4):
+        UF[turns == q] = UF[turns == q] @ np.linalg.matrix_power(T, q).T
+    sch = capi.default_schemes(flux_scheme=flux, limiter_rho=limiter, limiter_U=limiter, limiter_T=limiter, ddt_scheme="steadyState",
+                               pseudo_co_num=5.0, pseudo_co_num_max=50.0)
+    ctl = capi.solver_controls("Jacobi", n_directions=6, max_iter=40, tolerance=1e-14, rel_tol=1e-10)
+    wall = {"p": ("zeroGradient", ()), "U": ("slip", ()), "T": ("zeroGradient", ())}
+    cs = Case("sector", sec, 287.0, 1005.0, sch, ctl, {nm: dict(wall) for nm in ("xmax", "ymax")}, p0, U0, T0, mu=mu, Pr=0.71)
+    cf = Case("annulus", full, 287.0, 1005.0, sch, ctl, {nm: dict(wall) for nm in ("xmin", "xmax", "ymin", "ymax")}, p0[src], UF, T0[src], mu=mu, Pr=0.71)
+    first = np.nonzero(turns == 0)[0]
+    return cs, cf, first, src[first]
 
 
 def scrambled_box(n=6, flux="HLLC", limiter="vanLeer", seed=0, mu=0.0):

@@ -136,6 +136,8 @@ struct icsb200_ctx {
     std::vector<ProcPatchDev> procs;
     std::vector<AmiPatchDev> amis;                 // cyclicAMI patches (local weighted gathers into halo slots)
     std::vector<RotPatchDev> rots;                 // rotational cyclic patches (local gathers + rotation of the vector triples)
+    int* d_bfNbrPos = nullptr;                     // [NB] rotational cyclic faces: position of the neighbour patch's face cell; else -1
+    double* d_patchRot = nullptr;                  // [10*nPatches] (rotational ? 1 : 0, forwardT[9]) per patch (viscous terms)
     std::vector<std::pair<int, AmiTable>> pendingAmi;  // icsb200_ami_set tables waiting for mesh_set
     double *d_sendBuf = nullptr, *d_recvBuf = nullptr;
 

@@ -456,6 +456,8 @@ struct ViscArgs {
     size_t NFG, NX, NPH;
     double mu, alphaEff;
     const double* tr;  // [2][NX] muEff, alphaEff fields (cells, halo and boundary slots) or null: laminar constants
+    const int* bfNbrPos;      // [NB] rotational cyclic faces: position of the neighbour patch's face cell
+    const double* patchRot;   // [10*nPatches] (rotational flag, forwardT[9])
     double* out;  // [8*NP]
 };
 
@@ -518,7 +520,32 @@ k_visc(ViscArgs a)
             gradUAt(a, P, gP); gradUAt(a, N, gN);
             const double muP = a.tr ? a.tr[P] : a.mu, muN = a.tr ? a.tr[N] : a.mu;
             const double alP = a.tr ? a.tr[a.NX + P] : a.alphaEff, alN = a.tr ? a.tr[a.NX + N] : a.alphaEff;
-            dev2T(gP, muP, tP); dev2T(gN, muN, tN);
+            dev2T(gP, muP, tP);
+            const double* rot = coupled ? a.patchRot + (size_t)10 * a.bfPatch[b] : nullptr;
+            if (coupled && rot[0] != 0.0) {
+                // rotational cyclic pair: cyclicFvPatchField<tensor>::patchNeighbourField = transform(forwardT, t) = (T & t) & T.T()
+                // (cyclicFvPatchField.C:130-190).  The halo slot holds transform(forwardT, grad(U_j)) per component, i.e. T & gradU;
+                // tauMC is a cell field, so the neighbour CELL's tensor is rotated.
+                const double* T = rot + 1;
+                double h[9], gRaw[9], tr[9], hr[9];
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) h[3 * i + j] = gN[3 * i] * T[3 * j] + gN[3 * i + 1] * T[3 * j + 1] + gN[3 * i + 2] * T[3 * j + 2];
+#pragma unroll
+                for (int k = 0; k < 9; k++) gN[k] = h[k];
+                gradUAt(a, a.bfNbrPos[b], gRaw);
+                dev2T(gRaw, muN, tr);
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int l = 0; l < 3; l++) hr[3 * i + l] = T[3 * i] * tr[l] + T[3 * i + 1] * tr[3 + l] + T[3 * i + 2] * tr[6 + l];
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) tN[3 * i + j] = hr[3 * i] * T[3 * j] + hr[3 * i + 1] * T[3 * j + 1] + hr[3 * i + 2] * T[3 * j + 2];
+            } else
+                dev2T(gN, muN, tN);
 #pragma unroll
             for (int k = 0; k < 9; k++) { gf[k] = lin(gP[k], gN[k]); tf[k] = lin(tP[k], tN[k]); }
             const double muf = lin(muP, muN), alf = lin(alP, alN);
@@ -694,6 +721,7 @@ int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
         v.NFG = c->NFG; v.NX = c->NX; v.NPH = c->NPH;
         v.mu = c->mu; v.alphaEff = c->gamma * (c->mu / c->Pr);
         v.tr = c->d_transport;
+        v.bfNbrPos = c->d_bfNbrPos; v.patchRot = c->d_patchRot;
         v.out = c->d_visc;
         LaunchScope ls(c, TM_FLUX);
         k_visc<<<gridFor(c->NP, 128), 128, 0, c->stream>>>(v);

@@ -135,7 +135,7 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
                     c->d_bfGeo, c->d_bc, c->d_phiB, c->d_vic, c->d_sendBuf, c->d_recvBuf, c->d_fields, c->d_grad, c->d_rdt, c->d_co,
                     c->d_ddtCoeff, c->d_Wold, c->d_Wold2, c->d_Wprev, c->d_src, c->d_dW, c->d_faceFlux, c->d_bad, c->d_offd, c->d_diag,
                     c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage, c->d_lusgsYZ, c->d_lusgsHint, c->d_sliceRange,
-                    c->d_faceRecon, c->d_gradE, c->d_visc, c->d_mrfFace, c->d_mrfOmega, c->d_transport, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
+                    c->d_faceRecon, c->d_gradE, c->d_visc, c->d_mrfFace, c->d_mrfOmega, c->d_transport, c->d_bfNbrPos, c->d_patchRot, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
     for (auto& am : c->amis) { cudaFree(am.d_start); cudaFree(am.d_srcPos); cudaFree(am.d_w); }
@@ -206,7 +206,6 @@ extern "C" int icsb200_thermo_set(icsb200_ctx* c, double R, double Cp, double mu
 {
     c->reconValid = false;
     if (!(R > 0) || !(Cp > R)) return ics_fail(c, ICSB200_EINVAL, "thermo: need Cp > R > 0");
-    if (mu > 0 && !c->rots.empty()) return ics_fail(c, ICSB200_EINVAL, "thermo: viscous runs with rotational cyclic patches are not supported");
     c->R = R; c->Cp = Cp; c->Cv = Cp - R; c->gamma = Cp / c->Cv; c->mu = mu; c->Pr = Pr;
     c->thermoSet = true;
     return 0;
@@ -288,8 +287,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
         // (originalOFFiles/constraintFvPatchFields/cyclic/cyclicFvPatchField.C:130-190) through local halo slots
         if (p.kind == ICSB200_CYCLICAMI && ics_is_rotational(p))
             return ics_fail(c, ICSB200_EINVAL, "mesh_set: rotational cyclicAMI patches (forwardT != I) are not supported");
-        if (p.kind == ICSB200_CYCLIC && ics_is_rotational(p) && c->mu > 0)
-            return ics_fail(c, ICSB200_EINVAL, "mesh_set: viscous runs with rotational cyclic patches are not supported");
+
         if (p.kind == ICSB200_PROCESSOR && (p.nbr_rank < 0 || p.nbr_rank >= c->nRanks || c->nRanks == 1))
             return ics_fail(c, ICSB200_EINVAL, "mesh_set: processor patch needs a multi-rank context");
         if ((p.kind == ICSB200_CYCLIC || p.kind == ICSB200_PROCESSOR || p.kind == ICSB200_CYCLICAMI) && !Cf) return ics_fail(c, ICSB200_EINVAL, "mesh_set: coupled patches need Cf");
@@ -747,6 +745,19 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     }
     for (auto& ro : c->rots) cudaFree(ro.d_srcPos);
     c->rots.clear();
+    {
+        // viscous terms across a rotational pair need the neighbour CELL (tauMC is rotated as a cell tensor) and forwardT
+        std::vector<int> nbrPos((size_t)std::max(NB, 1), -1);
+        std::vector<double> prot((size_t)10 * std::max(n_patches, 1), 0.0);
+        for (int pi = 0; pi < n_patches; pi++) {
+            if (!ics_is_rotational(patches[pi])) continue;
+            prot[(size_t)10 * pi] = 1.0;
+            for (int k = 0; k < 9; k++) prot[(size_t)10 * pi + 1 + k] = patches[pi].forwardT[k];
+            for (int i = 0; i < patches[pi].size; i++) nbrPos[patches[pi].start + i - F] = c->cell2pos[owner[patches[patches[pi].nbr_patch].start + i]];
+        }
+        r |= devUpload(c, &c->d_bfNbrPos, nbrPos);
+        r |= devUpload(c, &c->d_patchRot, prot);
+    }
     for (int pi = 0; pi < n_patches; pi++) {
         if (!ics_is_rotational(patches[pi])) continue;
         RotPatchDev ro{};

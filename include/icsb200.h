@@ -40,7 +40,7 @@ typedef struct {
     int nbr_patch;      /* CYCLIC: index of the neighbour patch */
     double forwardT[9]; /* CYCLIC: cyclicPolyPatch::forwardT() row-major — patchNeighbourField = transform(forwardT, neighbour
                          * value) (cyclicFvPatchField.C:130-190): identity = translational pair; a rotation = rotational pair
-                         * (inviscid runs; viscous + rotational and rotational CYCLICAMI return EINVAL) */
+                         * (tensors grad(U), tauMC of the viscous terms: transform(forwardT, t)); rotational CYCLICAMI: EINVAL */
 } icsb200_patch;
 
 /* run-time selectors — same words as the reference dictionaries */

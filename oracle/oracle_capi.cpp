@@ -69,14 +69,6 @@ struct ThreadComm : Comm {
 
 int fail(Ctx* c, int code, const char* msg) { c->err = msg; return code; }
 
-// the viscous terms need transform(forwardT, tensor) of grad(U) / tauMC on rotational cyclic patches: not restated
-bool rotationalViscous(const Ctx* c)
-{
-    if (!(c->mu > 0)) return false;
-    for (auto& p : c->m.patches) if (p.rotational) return true;
-    return false;
-}
-
 }  // namespace
 
 extern "C" {
@@ -128,7 +120,6 @@ int orc_mesh_set(Ctx* c, int n_cells, int n_internal_faces, int n_faces, const i
     for (int f = 0; f < m.F; f++) if (m.owner[f] >= m.neighbour[f]) return fail(c, ICSB200_EINVAL, "mesh is not in upper-triangular order");
     meshFinalize(*c);
     c->meshSet = true;
-    if (rotationalViscous(c)) return fail(c, ICSB200_EINVAL, "viscous runs with rotational cyclic patches are not supported");
     return 0;
 }
 
@@ -146,7 +137,6 @@ int orc_ami_set(Ctx* c, int patch, int n_faces, const int* face_start, const int
 int orc_thermo_set(Ctx* c, double R, double Cp, double mu, double Pr)
 {
     c->R = R; c->Cp = Cp; c->Cv = Cp - R; c->gamma = Cp / c->Cv; c->mu = mu; c->Pr = Pr;
-    if (rotationalViscous(c)) return fail(c, ICSB200_EINVAL, "viscous runs with rotational cyclic patches are not supported");
     return 0;
 }
 

@@ -433,7 +433,10 @@ void viscousResidual(Ctx& c, vecd& rhoUR, vecd& rhoER)
     const size_t FT = m.FT;
     vecd lapU(3 * FT, 0.0), divTau(3 * FT, 0.0), sig(FT, 0.0), lapE(FT, 0.0);
     auto em = emptyMask(m);
-    auto faceCoupledOrInternal = [&](int f, int P, size_t Ns, const double* dvec, bool coupled) {
+    // rot != nullptr: face of a rotational cyclic patch; nbCell = the neighbour patch's face cell.  The boundary slot Ns then
+    // holds transform(forwardT, grad(U_j)) per component, i.e. (T & gradU); cyclicFvPatchField<tensor>::patchNeighbourField
+    // of grad(U) and of tauMC is transform(forwardT, tensor) = (T & t) & T.T() (originalOFFiles/.../cyclicFvPatchField.C:130-190)
+    auto faceCoupledOrInternal = [&](int f, int P, size_t Ns, const double* dvec, bool coupled, const double* rot, int nbCell) {
         const double w = m.w[f], magSf = m.magSf[f], dcn = m.nonOrthDeltaCoeffs[f];
         double nf[3], corr[3];
         for (int d = 0; d < 3; d++) nf[d] = m.Sf[3 * f + d] / magSf;
@@ -441,7 +444,21 @@ void viscousResidual(Ctx& c, vecd& rhoUR, vecd& rhoER)
         auto lin = [&](double a, double b) { return coupled ? w * a + (1.0 - w) * b : w * (a - b) + b; };
         double gP[9], gN[9], gf[9], tP[9], tN[9], tf[9];
         gradUOf(P, gP); gradUOf(Ns, gN);
-        dev2T(gP, muV[P], tP); dev2T(gN, muV[Ns], tN);
+        dev2T(gP, muV[P], tP);
+        if (rot) {
+            double h[9], tr[9], hr[9];
+            for (int i = 0; i < 3; i++)           // (T & gradU) & T.T(): the slot already holds the left product
+                for (int j = 0; j < 3; j++) h[3 * i + j] = gN[3 * i] * rot[3 * j] + gN[3 * i + 1] * rot[3 * j + 1] + gN[3 * i + 2] * rot[3 * j + 2];
+            for (int k = 0; k < 9; k++) gN[k] = h[k];
+            double gRaw[9];
+            gradUOf((size_t)nbCell, gRaw);         // tauMC is a cell field: rotate the neighbour CELL's tensor
+            dev2T(gRaw, muV[Ns], tr);
+            for (int i = 0; i < 3; i++)
+                for (int l = 0; l < 3; l++) hr[3 * i + l] = rot[3 * i] * tr[l] + rot[3 * i + 1] * tr[3 + l] + rot[3 * i + 2] * tr[6 + l];
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) tN[3 * i + j] = hr[3 * i] * rot[3 * j] + hr[3 * i + 1] * rot[3 * j + 1] + hr[3 * i + 2] * rot[3 * j + 2];
+        } else
+            dev2T(gN, muV[Ns], tN);
         for (int k = 0; k < 9; k++) { gf[k] = lin(gP[k], gN[k]); tf[k] = lin(tP[k], tN[k]); }
         const double muf = lin(muV[P], muV[Ns]), alf = lin(alV[P], alV[Ns]);
         double Uf[3];
@@ -466,7 +483,7 @@ void viscousResidual(Ctx& c, vecd& rhoUR, vecd& rhoER)
     for (int f = 0; f < m.F; f++) {
         const int P = m.owner[f], N = m.neighbour[f];
         const double dvec[3] = {m.C[3 * (size_t)N] - m.C[3 * (size_t)P], m.C[3 * (size_t)N + 1] - m.C[3 * (size_t)P + 1], m.C[3 * (size_t)N + 2] - m.C[3 * (size_t)P + 2]};
-        faceCoupledOrInternal(f, P, (size_t)N, dvec, false);
+        faceCoupledOrInternal(f, P, (size_t)N, dvec, false, nullptr, -1);
     }
     for (size_t pi = 0; pi < m.patches.size(); pi++) {
         const Patch& p = m.patches[pi];
@@ -475,7 +492,12 @@ void viscousResidual(Ctx& c, vecd& rhoUR, vecd& rhoER)
             if (!faceActive(m, f, em)) continue;
             const int b = f - m.F, P = m.owner[f];
             const size_t s = (size_t)m.N + b;
-            if (m.coupled(p)) { faceCoupledOrInternal(f, P, s, &m.dCoupled[3 * (size_t)b], true); continue; }
+            if (m.coupled(p)) {
+                const bool rot = p.kind == ICSB200_CYCLIC && p.rotational;
+                faceCoupledOrInternal(f, P, s, &m.dCoupled[3 * (size_t)b], true, rot ? p.forwardT : nullptr,
+                                      rot ? m.owner[m.patches[p.nbrPatch].start + (f - p.start)] : -1);
+                continue;
+            }
             const double magSf = m.magSf[f];
             double nf[3], sn[3], gP[9], gb[9], tb[9];
             for (int d = 0; d < 3; d++) nf[d] = m.Sf[3 * f + d] / magSf;

@@ -80,6 +80,7 @@ LIVE = {
     "rot-hllc-vanleer": lambda: cases.rot_box(6, "HLLC", "vanLeer", seed=62),
     "rot-roe-minmod": lambda: cases.rot_box(5, "ROE", "Minmod", seed=63, nz=4),
     "rot-ausm-mrf": lambda: cases.rot_box(5, "AUSMPlusUp", "vanLeer", seed=64).with_mrf((0.0, 0.0, 60.0)),
+    "rot-viscous-hllc": lambda: cases.rot_box(5, "HLLC", "Minmod", seed=66, mu=0.1),
     "shocktube-ausm": lambda: cases.shock_tube(64, "AUSMPlusUp"),
     "shocktube-roe": lambda: cases.shock_tube(50, "ROE"),
 }
@@ -354,8 +355,8 @@ def test_forward_step_c2_polyhedral_mesh(gpu_context):
 
 def test_rotational_cyclic_bitwise_and_refusals(gpu_context):
     """Rotational cyclic pairs on the device (local halo slots filled by k_rot_gather: vector triples rotated by forwardT,
-    scalars copied): every reduction-free stage bit for bit against the oracle; rotational cyclicAMI and viscous runs with
-    rotational pairs are refused by both."""
+    scalars copied): every reduction-free stage bit for bit against the oracle, incl. the viscous terms; rotational cyclicAMI is
+    refused by both."""
     case = cases.rot_box(6, "HLLC", "vanLeer", seed=61)
     o, g = case.apply(Oracle()), case.apply(gpu_context())
     bo, bg = o.boundary_get(), g.boundary_get()
@@ -378,10 +379,20 @@ def test_rotational_cyclic_bitwise_and_refusals(gpu_context):
     for pk in ("LUSGS", "Jacobi"):
         for a, b in zip(g.precondition(pk, *x), o.precondition(pk, *x)):
             assert np.array_equal(a, b), pk
-    visc = cases.rot_box(4)
+    # viscous terms across the pair: transform(forwardT, .) of grad(U) and tauMC, with a muEff field
+    visc = cases.rot_box(5, "ROE", "vanLeer", seed=65)
     visc.mu = 0.1
-    with pytest.raises(capi.ApiError):
-        visc.apply(gpu_context())
+    visc.with_transport(TURB)
+    ov, gv = visc.apply(Oracle()), visc.apply(gpu_context())
+    gv.calc_flux(); ov.calc_flux()
+    for a, b in zip(gv.residual(), ov.residual()):
+        assert np.array_equal(a, b)
+    # ... and the device reproduces the full annulus the sector stands for (oracle KAT test_rotational_cyclic_known_answers)
+    cs, cf, fcells, scells = cases.sector_and_annulus(6, 0.5)
+    gs, gf = cs.apply(gpu_context()), cf.apply(gpu_context())
+    gs.calc_flux(); gf.calc_flux()
+    for a, b in zip(gs.residual(), gf.residual()):
+        assert np.abs(a[scells] - b[fcells]).max() <= 1e-12 * np.abs(a).max()
     ami = cases.periodic_box(4, ami_shift=0.5)
     for p in ami.mesh.patches:
         if p["kind"] == capi.CYCLICAMI:
