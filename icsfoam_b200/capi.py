@@ -124,6 +124,8 @@ SHARED_SIGNATURES = {
     "assemble": (C.c_int, [C.c_void_p]),
     "matrix_get_ldu": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp]),
     "matrix_set_ldu": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp]),
+    "matrix_get_interfaces": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "matrix_set_interfaces": (C.c_int, [C.c_void_p, C.c_int, _dp]),
     "source_set": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
     "source_get": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
     "mrf_set": (C.c_int, [C.c_void_p, _dp, _dp]),
@@ -268,6 +270,15 @@ class Api:
         self._call("matrix_set_ldu", block, dptr(np.ascontiguousarray(diag)),
                    dptr(np.ascontiguousarray(upper)) if upper is not None else None,
                    dptr(np.ascontiguousarray(lower)) if lower is not None else None)
+
+    def matrix_get_interfaces(self, block):
+        NB = self.mesh.n_faces - self.mesh.n_internal_faces
+        a = np.zeros((NB, BLOCK_NC[block]))
+        self._call("matrix_get_interfaces", block, dptr(a))
+        return a
+
+    def matrix_set_interfaces(self, block, int_upper):
+        self._call("matrix_set_interfaces", block, dptr(np.ascontiguousarray(int_upper, np.float64)))
 
     def source_set(self, sRho, sRhoU, sRhoE):
         self._call("source_set", dptr(np.ascontiguousarray(sRho)), dptr(np.ascontiguousarray(sRhoU)),

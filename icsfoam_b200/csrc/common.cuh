@@ -298,6 +298,7 @@ int ics_update(icsb200_ctx* c);
 int ics_copy_prev(icsb200_ctx* c);
 int ics_state_from_primitives(icsb200_ctx* c);
 int ics_allreduce_max_int(icsb200_ctx* c, int* d, int n);
+int ics_allreduce_max_double(icsb200_ctx* c, double* d, int n);
 // hb.cu
 int ics_mrf_source(icsb200_ctx* c);       // src(rhoU) -= (Omega ^ rho U) V, once per residual evaluation (jacobian.cu)
 int ics_hb_source(icsb200_ctx* c);        // src += HB source (after the flux residual)

@@ -401,6 +401,27 @@ __global__ void k_ldu_offdiag(long long nE32, const int* __restrict__ meta, cons
         }
 }
 
+// thread per (entry slot): interfacesUpper coefficients of the coupled boundary faces <-> intUpper[NB*nc] (boundary-face order)
+__global__ void k_ldu_interface(long long nE32, const int* __restrict__ meta, int blk, int F, bool toHost, double* __restrict__ offd,
+                                double* __restrict__ intUpper)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nE32) return;
+    const int m = meta[i], type = m & 3, fc = m >> 2;
+    if (type != ET_COUPLED || fc < F) return;
+    const long long ent = i >> 5;
+    const int lane = (int)(i & 31);
+    int r0, c0;
+    const int rows = blockRows(blk, &r0), cols = blockCols(blk, &c0), nc = rows * cols;
+    const size_t b = (size_t)(fc - F);
+    for (int r = 0; r < rows; r++)
+        for (int cc = 0; cc < cols; cc++) {
+            double* v = offd + ((size_t)ent * 25 + (r0 + r) * 5 + (c0 + cc)) * 32 + lane;
+            if (toHost) intUpper[b * nc + r * cols + cc] = *v;
+            else *v = intUpper[b * nc + r * cols + cc];
+        }
+}
+
 __global__ void k_ldu_diag(int NP, const int* __restrict__ pos2cell, int blk, bool toHost, double* __restrict__ diag, double* __restrict__ out)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -463,9 +484,11 @@ int ics_jacobian(icsb200_ctx* c, bool useStoredRdt)
                                                                     c->d_gfid, c->d_geo, c->NFG, c->d_fields, c->NX, c->d_mrfFace, d_max);
         }
         double mx = 0.0;
+        // gMax over all ranks (setCoAndDeltaT.H:143-146); the maximum is non-negative, so its bit pattern orders like the double
+        int rr = ics_allreduce_max_double(c, (double*)d_max, 1);
+        if (rr) return rr;
         CUDA_TRY(c, cudaMemcpyAsync(&mx, d_max, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        if (c->nRanks > 1) return ics_fail(c, ICSB200_ESTATE, "global time stepping is single-rank only in this build");
         a.rdtUniform = mx / c->pseudoCoNum;
     }
     {
@@ -590,6 +613,46 @@ extern "C" int icsb200_matrix_set_ldu(icsb200_ctx* c, int block, const double* d
     c->matrixSet = true;
     c->rDValid = false;
     c->invDValid = false;
+    return 0;
+}
+
+// interfacesUpper() of one sub-block on the coupled patches (blockFvMatrix.C:248-266; consumed by Amul at blockFvMatrix.C:383-599)
+extern "C" int icsb200_matrix_get_interfaces(icsb200_ctx* c, int block, double* intUpper)
+{
+    if (!c->matrixSet) return ics_fail(c, ICSB200_ESTATE, "matrix_get_interfaces: matrix not assembled");
+    if (block < 0 || block > 8 || !intUpper) return ics_fail(c, ICSB200_EINVAL, "matrix_get_interfaces: bad argument");
+    const size_t n = (size_t)kBlockNc[block] * c->NB;
+    if (n == 0) return 0;
+    int r = ics_ensure_stage(c, sizeof(double) * n);
+    if (r) return r;
+    CUDA_TRY(c, cudaMemsetAsync(c->d_stage, 0, sizeof(double) * n, c->stream));
+    const long long nE32 = c->nEntries * 32;
+    {
+        LaunchScope ls(c, TM_PERM);
+        k_ldu_interface<<<gridFor(nE32, 256), 256, 0, c->stream>>>(nE32, c->d_meta, block, c->F, true, c->d_offd, c->d_stage);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(intUpper, c->d_stage, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int icsb200_matrix_set_interfaces(icsb200_ctx* c, int block, const double* intUpper)
+{
+    if (!c->meshSet) return ics_fail(c, ICSB200_ESTATE, "matrix_set_interfaces: mesh not set");
+    if (block < 0 || block > 8 || !intUpper) return ics_fail(c, ICSB200_EINVAL, "matrix_set_interfaces: bad argument");
+    const size_t n = (size_t)kBlockNc[block] * c->NB;
+    if (n == 0) return 0;
+    int r = ics_ensure_stage(c, sizeof(double) * n);
+    if (r) return r;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_stage, intUpper, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    const long long nE32 = c->nEntries * 32;
+    {
+        LaunchScope ls(c, TM_PERM);
+        k_ldu_interface<<<gridFor(nE32, 256), 256, 0, c->stream>>>(nE32, c->d_meta, block, c->F, false, c->d_offd, c->d_stage);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 

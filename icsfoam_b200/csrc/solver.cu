@@ -139,6 +139,13 @@ static int allreduceSum(icsb200_ctx* c, double* d, int n)
     return 0;
 }
 
+int ics_allreduce_max_double(icsb200_ctx* c, double* d, int n)
+{
+    if (c->nRanks == 1) return 0;
+    if (ncclAllReduce(d, d, n, ncclDouble, ncclMax, (ncclComm_t)c->nccl, c->stream) != ncclSuccess) return ics_fail(c, ICSB200_ECUDA, "ncclAllReduce failed");
+    return 0;
+}
+
 int ics_allreduce_max_int(icsb200_ctx* c, int* d, int n)
 {
     if (c->nRanks == 1) return 0;

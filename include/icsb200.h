@@ -184,6 +184,12 @@ int icsb200_assemble(icsb200_ctx* ctx);
 int icsb200_matrix_get_ldu(icsb200_ctx* ctx, int block, double* diag, double* upper, double* lower);
 /* accept a HOST-assembled coupledMatrix (solver-only drop-in); NULL upper/lower = no off-diagonal */
 int icsb200_matrix_set_ldu(icsb200_ctx* ctx, int block, const double* diag, const double* upper, const double* lower);
+/* interfacesUpper() of one sub-block on the coupled patches (processor, cyclic, cyclicAMI), the coefficients Amul applies to
+ * the patchNeighbourField (blockFvMatrix.C:248-266, 383-599): intUpper[nc * (n_faces - n_internal_faces)] in boundary-face
+ * order; entries of non-coupled faces are written as 0 by get and ignored by set.  A solver-only adapter on a decomposed
+ * or periodic case calls set after icsb200_matrix_set_ldu for every sub-block that has interfaces. */
+int icsb200_matrix_get_interfaces(icsb200_ctx* ctx, int block, double* intUpper);
+int icsb200_matrix_set_interfaces(icsb200_ctx* ctx, int block, const double* intUpper);
 /* sources of the three equations (dSByS(0,0), dVByV(0,0), dSByS(1,1) .source(); residualsUpdate.H:81-83) */
 int icsb200_source_set(icsb200_ctx* ctx, const double* sRho, const double* sRhoU, const double* sRhoE);
 /* the sources the solver sees: R*V (+ HB source, + the MRF Coriolis term after icsb200_assemble); NULL skips */

@@ -254,6 +254,31 @@ int orc_matrix_set_ldu(Ctx* c, int block, const double* diag, const double* uppe
     return 0;
 }
 
+int orc_matrix_get_interfaces(Ctx* c, int block, double* intUpper)
+{
+    if (!c->matrixSet) return fail(c, ICSB200_ESTATE, "matrix not assembled");
+    const Blk& b = c->blk[block];
+    const Mesh& m = c->m;
+    std::memset(intUpper, 0, sizeof(double) * b.nc * m.NB);
+    if (!b.hasInt) return 0;
+    for (auto& p : m.patches)
+        if (m.coupled(p))
+            for (int f = p.start; f < p.start + p.size; f++)
+                for (int k = 0; k < b.nc; k++) intUpper[(size_t)b.nc * (f - m.F) + k] = b.intUpper[(size_t)b.nc * (f - m.F) + k];
+    return 0;
+}
+
+int orc_matrix_set_interfaces(Ctx* c, int block, const double* intUpper)
+{
+    if (!c->meshSet) return fail(c, ICSB200_ESTATE, "mesh not set");
+    Blk& b = c->blk[block];
+    const Mesh& m = c->m;
+    b.intUpper.assign(intUpper, intUpper + (size_t)b.nc * m.NB);
+    b.intLower.assign((size_t)b.nc * m.NB, 0.0);   // only enters the diagonal at assembly (negSumDiag), not the product
+    b.hasInt = true;
+    return 0;
+}
+
 int orc_source_set(Ctx* c, const double* sRho, const double* sRhoU, const double* sRhoE)
 {
     const int N = c->m.N;

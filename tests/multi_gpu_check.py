@@ -22,7 +22,17 @@ def main():
     mu = float(os.environ.get("ICS_MULTI_MU", "0"))   # > 0: laminar viscous residual (halo of eCalc and its gradient)
     ids = [Context.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
-    case = cases.onera_box(n, parts=parts, rank=rank, mu=mu)
+    variant = os.environ.get("ICS_MULTI_VARIANT", "")   # "globaldt": non-local time stepping (gMax over ranks); "mrf": rotating zone
+
+    def make(r):
+        c = cases.onera_box(n, parts=parts, rank=r, mu=mu)
+        if variant == "globaldt":
+            c.schemes.local_timestepping = 0
+        if variant == "mrf":
+            c.with_mrf(omega=(0.0, 40.0, 90.0), origin=(0.5, 0.0, 1.5), zone=lambda x: x[:, 0] > 0.2)
+        return c
+
+    case = make(rank)
     ctx = case.apply(Context(device=local, nccl_id=ids[0], rank=rank, n_ranks=world))
     hist = []
     flux0 = ctx.calc_flux()
@@ -36,7 +46,7 @@ def main():
     ok = True
     if rank == 0:
         from oracle.pyoracle import World
-        meshes = [cases.onera_box(n, parts=parts, rank=r, mu=mu) for r in range(world)]
+        meshes = [make(r) for r in range(world)]
         w = World(world)
         w.mesh_set([c.mesh for c in meshes])
         for o, c in zip(w.ranks, meshes):
@@ -47,6 +57,8 @@ def main():
                 if patch in names:
                     for field, (kind, params) in fields.items():
                         o.bc_set(patch, {"p": 0, "U": 1, "T": 2}[field], kind, params)
+            if c.mrf is not None:
+                o.mrf_set(*c.mrf_fields(c.mesh))
         w.state_set([c.p for c in meshes], [c.U for c in meshes], [c.T for c in meshes])
         ohist = []
         for _ in range(n_iter):

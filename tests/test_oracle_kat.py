@@ -686,3 +686,25 @@ def test_transport_fields_known_answers():
     rhof = 0.5 * (st["rho"][own] + st["rho"][nei])
     want = 0.5 * ((m0 + m1 * yf) + (k0 + k1 * yf)) / rhof * mesh.magSf[:F] * mesh.deltaCoeffs[:F]
     assert np.allclose((u_i - u_v)[:, 0], want, rtol=1e-9)
+
+
+def test_solver_only_interfaces_roundtrip_on_the_oracle():
+    """matrix_set_ldu + matrix_set_interfaces rebuild a coupledMatrix whose product equals the assembled one (cyclic pair)."""
+    case = cases.periodic_box(5, "ROE", "vanLeer", seed=33)
+    a = case.apply(Oracle())
+    a.calc_flux(); a.residual(); a.pseudo_dt(); a.assemble()
+    b = case.apply(Oracle())
+    for blk in range(9):
+        d, u, l = a.matrix_get_ldu(blk)
+        b.matrix_set_ldu(blk, d, u, l)
+        b.matrix_set_interfaces(blk, a.matrix_get_interfaces(blk))
+    rng = np.random.default_rng(1)
+    N = case.mesh.n_cells
+    x = (rng.standard_normal(N), rng.standard_normal((N, 3)), rng.standard_normal(N))
+    ya, yb = a.matrix_mul(*x), b.matrix_mul(*x)
+    for p, q in zip(ya, yb):
+        assert np.array_equal(p, q)
+    c = case.apply(Oracle())
+    for blk in range(9):
+        c.matrix_set_ldu(blk, *a.matrix_get_ldu(blk))
+    assert not np.array_equal(c.matrix_mul(*x)[0], ya[0])        # without the interfaces the cyclic coupling is missing
