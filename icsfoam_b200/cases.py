@@ -336,6 +336,20 @@ class HBCase:
         self.U = np.concatenate([c.U for c in instances])
         self.T = np.concatenate([c.T for c in instances])
 
+    def partition(self, n_parts, mode="x"):
+        """One HBCase per rank: every instance case restricted to the same spatial decomposition (HB instants are not sharded
+        across ranks — SURVEY §8e — each rank holds all instances of its cells)."""
+        part, meshes = self.base.partition(n_parts, mode)
+        out = []
+        for r, m in enumerate(meshes):
+            insts = []
+            for c in self.instances:
+                g = m.cell_global
+                insts.append(Case(c.name, m, c.R, c.Cp, c.schemes, c.controls, {k: dict(v) for k, v in c.bcs.items()}, c.p[g], c.U[g], c.T[g], mu=c.mu, Pr=c.Pr))
+            zone = None if self.zone_of_cell is None else self.zone_of_cell[m.cell_global]
+            out.append(HBCase(self.name, insts, self.snapshots, self.D, zone, self.cyl_coords, self.rotation_axis, self.rotation_centre))
+        return out
+
     def apply(self, api):
         b = self.base
         api.mesh_set(self.mesh)

@@ -319,7 +319,8 @@ extern "C" int icsb200_hb_set(icsb200_ctx* c, int n_instants, int n_zones, const
     if (!c->meshSet) return ics_fail(c, ICSB200_ESTATE, "hb_set: mesh not set");
     cudaSetDevice(c->device);
     if (n_instants <= 1) { c->hbNO = 1; return 0; }
-    if (c->nRanks > 1) return ics_fail(c, ICSB200_EINVAL, "hb_set: Harmonic Balance is single-rank in this build");
+    // multi-rank: every rank holds all n_instants instances of its own cells (HB instants are not sharded); halos
+    // run per replicated processor patch, residual sums and dot products are all-reduced like in the single-instance solver
     if (n_instants > 16) return ics_fail(c, ICSB200_EINVAL, "hb_set: at most 16 time instances");
     if (n_zones < 1 || !D) return ics_fail(c, ICSB200_EINVAL, "hb_set: no HB zone");
     const int nO = n_instants;

@@ -227,7 +227,9 @@ int icsb200_iterate_host(icsb200_ctx* ctx, const icsb200_solver_controls* c, dou
  * Effect: residual adds S_J = -V sum_K D[J][K] W_K; assemble adds V D[J][J] to the (rho,rho), (rhoU,rhoU), (rhoE,rhoE)
  * diagonals; matrix_mul / solve_delta include the inter-instance diagonal coupling V D[J][K]; LU-SGS uses the shared
  * rDiagCoeff over all instances (lusgs.C:50-123); the SER ratio uses the residual norm over all instances
- * (outerLoop.H:32-64); residuals are per instance (icsb200_hb_residuals_get). n_instants = 1 switches HB off. */
+ * (outerLoop.H:32-64); residuals are per instance (icsb200_hb_residuals_get). n_instants = 1 switches HB off.
+ * Multi-rank: every rank passes the n_instants copies of ITS partition (processor patches replicated per instance,
+ * instance-major like all other patches); instances are never split across ranks. */
 int icsb200_hb_set(icsb200_ctx* ctx, int n_instants, int n_zones, const double* D, const int* zone_of_cell,
                    const int* cyl_coords, const double* rotation_axis, const double* rotation_centre);
 /* residualsIO of the last solve for all instances: s_* [2 n_instants] = (rho_0, rhoE_0, rho_1, ...), v_* [3 n_instants]

@@ -9,6 +9,8 @@
 // Structure kept from the reference: nO separate time-instance meshes/contexts ("subTimeLevelK"), one global system
 // whose only inter-instance coupling is the diagonal V*D[J][K] of the (rho,rho), (rhoU,rhoU), (rhoE,rhoE) blocks.
 // The CUDA product instead runs the nO instances as ONE mesh of nO disconnected copies; comparing the two is the test.
+#include <thread>
+
 #include "oracle_internal.hpp"
 
 namespace orc {
@@ -694,6 +696,22 @@ int orc_hb_iterate(void* hb, const icsb200_solver_controls* ctl, int n_iter)
 }
 
 // the sources of the global system after orc_hb_assemble / inside an iteration: R*V + HB source, instance-major
+// P ranks, each with its own HB system over its partition (instance contexts attached to the same World): one thread per
+// rank runs n_iter outer iterations SPMD — halos per instance through the mailboxes, reductions in rank order
+int orc_world_hb_iterate(void** hbs, int n, const icsb200_solver_controls* ctl, int n_iter)
+{
+    std::vector<std::thread> th;
+    std::vector<int> rc(n, 0);
+    for (int r = 0; r < n; r++)
+        th.emplace_back([&, r] {
+            HBSys& h = *(HBSys*)hbs[r];
+            for (int it = 0; it < n_iter && rc[r] == 0; it++) rc[r] = hbIterate(h, *ctl);
+        });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < n; r++) if (rc[r]) return rc[r];
+    return 0;
+}
+
 int orc_hb_system_sources(void* hb, double* sRho, double* sRhoU, double* sRhoE)
 {
     HBSys& h = *(HBSys*)hb;

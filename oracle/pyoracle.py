@@ -111,12 +111,12 @@ class HB:
     """The reference-structured Harmonic Balance system: nO oracle contexts (one per time-instance mesh) and the global
     (2 nO, nO) coupled solve of dbnsFullyImplicitHBFoam (oracle/oracle_hb.cpp).  Arrays are instance-major."""
 
-    def __init__(self, hbcase):
+    def __init__(self, hbcase, inst=None):
         L = lib()
         L.orc_hb_create.restype = C.c_void_p
         self.case = hbcase
         self.n = hbcase.n_instants
-        self.inst = [c.apply(Oracle()) for c in hbcase.instances]
+        self.inst = inst if inst is not None else [c.apply(Oracle()) for c in hbcase.instances]
         ctxs = (C.c_void_p * self.n)(*[o.h for o in self.inst])
         self._h = C.c_void_p(L.orc_hb_create(ctxs, self.n))
         N = hbcase.base.mesh.n_cells
@@ -201,3 +201,39 @@ class HB:
         a, b = np.zeros(n * N), np.zeros(n * N)
         self._chk(lib().orc_hb_pseudo(self._h, capi.dptr(a), capi.dptr(b)), "pseudo")
         return a, b
+
+
+class HBWorld:
+    """P ranks, each holding the Harmonic Balance system of its partition (one HBCase per rank): the stand-in for an MPI run of
+    dbnsFullyImplicitHBFoam.  Instance K of every rank forms one World view (halo exchange between the ranks' K-th contexts)."""
+
+    def __init__(self, hbcases):
+        self.n = len(hbcases)
+        nO = hbcases[0].n_instants
+        self._w = C.c_void_p(lib().orc_world_create(self.n))
+        ctxs = [[Oracle() for _ in range(nO)] for _ in range(self.n)]
+        for r in range(self.n):
+            for o in ctxs[r]:
+                lib().orc_attach(o.h, self._w, r)
+        fid = {"p": capi.FIELD_P, "U": capi.FIELD_U, "T": capi.FIELD_T}
+        for K in range(nO):
+            view = World.__new__(World)
+            view.n, view._w, view.ranks = self.n, self._w, [ctxs[r][K] for r in range(self.n)]
+            insts = [hc.instances[K] for hc in hbcases]
+            view.mesh_set([c.mesh for c in insts])
+            for o, c in zip(view.ranks, insts):
+                o.thermo_set(c.R, c.Cp, c.mu, c.Pr)
+                o.schemes_set(c.schemes)
+                names = [p["name"] for p in c.mesh.patches]
+                for patch, fields in c.bcs.items():
+                    if patch in names:
+                        for field, (kind, params) in fields.items():
+                            o.bc_set(patch, fid[field], kind, params)
+            view.state_set([c.p for c in insts], [c.U for c in insts], [c.T for c in insts])
+        self.ranks = [HB(hc, inst=ctxs[r]) for r, hc in enumerate(hbcases)]
+
+    def iterate(self, ctl, n_iter=1):
+        hbs = (C.c_void_p * self.n)(*[h._h for h in self.ranks])
+        rc = lib().orc_world_hb_iterate(hbs, self.n, C.byref(ctl), int(n_iter))
+        assert rc == 0, rc
+        return [h.residuals() for h in self.ranks]

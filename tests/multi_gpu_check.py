@@ -12,6 +12,51 @@ from icsfoam_b200 import capi, cases  # noqa: E402
 from icsfoam_b200.context import Context  # noqa: E402
 
 
+def main_hb(rank, world, local, ids):
+    """Harmonic Balance on P GPUs: every rank holds all time instances of its partition; parity against the P-rank HB oracle world."""
+    from oracle.pyoracle import HBWorld
+    n_iter = int(os.environ.get("ICS_MULTI_ITERS", "4"))
+    full = cases.hb_box(6, 3, flux="ROE", cyclic=False, seed=21)
+    parts = full.partition(world, "x")
+    mine = parts[rank]
+    ctx = mine.apply(Context(device=local, nccl_id=ids[0], rank=rank, n_ranks=world))
+    ctl = capi.solver_controls("LUSGS", n_directions=5, max_iter=10, tolerance=1e-10, rel_tol=1e-3)
+    hist = []
+    for _ in range(n_iter):
+        r = ctx.iterate(ctl)
+        hr = ctx.hb_residuals()
+        hist.append(list(hr["s_init"]) + list(hr["v_init"]) + [r.n_iterations])
+    st = ctx.state_get()
+    payload = {"rho": st["rho"], "rhoU": st["rhoU"], "rhoE": st["rhoE"], "hist": hist}
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(payload, gathered, dst=0)
+    ok = True
+    if rank == 0:
+        W = HBWorld(parts)
+        ohist = []
+        for _ in range(n_iter):
+            rr = W.iterate(ctl)[0]
+            ohist.append(list(rr["s_init"]) + list(rr["v_init"]) + [rr["n_iterations"]])
+        ohist, ghist = np.array(ohist), np.array(gathered[0]["hist"])
+        print("oracle HB history", ohist[:, [0, 1, -1]].tolist())
+        print("gpu    HB history", ghist[:, [0, 1, -1]].tolist())
+        ok &= np.array_equal(ohist[:, -1], ghist[:, -1])
+        ok &= np.allclose(ohist[:, :-1], ghist[:, :-1], rtol=1e-8, atol=1e-14)
+        for r_, (h, g) in enumerate(zip(W.ranks, gathered)):
+            so = h.state_get()
+            for k in ("rho", "rhoU", "rhoE"):
+                err = np.abs(g[k] - so[k]).max() / np.abs(so[k]).max()
+                print(f"rank {r_} {k} rel err {err:.3e}")
+                ok &= err <= 1e-8
+        print("MULTI_GPU_PARITY", "OK" if ok else "FAILED")
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
 def main():
     n = int(os.environ.get("ICS_MULTI_N", "10"))
     n_iter = int(os.environ.get("ICS_MULTI_ITERS", "4"))
@@ -22,7 +67,9 @@ def main():
     mu = float(os.environ.get("ICS_MULTI_MU", "0"))   # > 0: laminar viscous residual (halo of eCalc and its gradient)
     ids = [Context.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
-    variant = os.environ.get("ICS_MULTI_VARIANT", "")   # "globaldt": non-local time stepping (gMax over ranks); "mrf": rotating zone
+    variant = os.environ.get("ICS_MULTI_VARIANT", "")   # "globaldt": non-local time stepping (gMax over ranks); "mrf": rotating zone; "hb"
+    if variant == "hb":
+        return main_hb(rank, world, local, ids)
 
     def make(r):
         c = cases.onera_box(n, parts=parts, rank=r, mu=mu)

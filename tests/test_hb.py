@@ -247,3 +247,26 @@ def test_hb_oracle_reproduces_golden_fixture():
     gold = np.load(os.path.join(GOLDEN, "hb_box_roe_3instants.npz"))
     for k in gold.files:
         assert np.array_equal(got[k], gold[k]), k
+
+
+def test_partitioned_hb_oracle_matches_single_domain():
+    """Multi-rank Harmonic Balance: every rank holds all instances of its partition (HB instants are not sharded).
+    With block-Jacobi preconditioning the P-rank HB world reproduces the single-domain HB run."""
+    from icsfoam_b200 import capi
+    from oracle.pyoracle import HBWorld
+    case = cases.hb_box(5, 3, flux="ROE", cyclic=False, seed=3)
+    ctl = capi.solver_controls("Jacobi", n_directions=5, max_iter=30, tolerance=1e-14, rel_tol=1e-9)
+    H = HB(case)
+    parts = case.partition(2, "x")
+    W = HBWorld(parts)
+    for it in range(3):
+        r1, r2 = H.iterate(ctl), W.iterate(ctl)
+        assert r1["n_iterations"] == r2[0]["n_iterations"] == r2[1]["n_iterations"]
+        assert np.abs(r1["s_init"] - r2[0]["s_init"]).max() <= 1e-10
+    s1 = H.state_get()
+    N = case.base.mesh.n_cells
+    for r, hc in enumerate(parts):
+        s2 = W.ranks[r].state_get()
+        idx = np.concatenate([K * N + hc.base.mesh.cell_global for K in range(3)])
+        for k in ("rho", "rhoU", "rhoE"):
+            assert np.abs(s2[k] - s1[k][idx]).max() <= 1e-9 * np.abs(s1[k]).max(), (r, k)
