@@ -45,7 +45,7 @@ class Schemes(C.Structure):
                 ("local_timestepping_lower_bound", C.c_double), ("pseudo_co_num", C.c_double),
                 ("pseudo_co_num_min", C.c_double), ("pseudo_co_num_max", C.c_double),
                 ("pseudo_co_num_max_incr", C.c_double), ("pseudo_co_num_min_decr", C.c_double),
-                ("rho_min", C.c_double), ("T_min", C.c_double), ("T_max", C.c_double)]
+                ("rho_min", C.c_double), ("T_min", C.c_double), ("T_max", C.c_double), ("viscous_full_jacobian", C.c_int)]
 
 
 def default_schemes(**kw):
@@ -54,7 +54,7 @@ def default_schemes(**kw):
                 low_mach_ausm=1, entropy_fix_coeff=0.05, ddt_scheme=DDT_STEADY, delta_t=1.0,
                 local_timestepping=1, local_timestepping_bounding=1, local_timestepping_lower_bound=0.95,
                 pseudo_co_num=1.0, pseudo_co_num_min=0.1, pseudo_co_num_max=25.0, pseudo_co_num_max_incr=1.25,
-                pseudo_co_num_min_decr=0.1, rho_min=-GREAT, T_min=SMALL, T_max=GREAT)
+                pseudo_co_num_min_decr=0.1, rho_min=-GREAT, T_min=SMALL, T_max=GREAT, viscous_full_jacobian=0)
     for k, v in kw.items():
         if k == "flux_scheme" and isinstance(v, str):
             v = FLUX_NAMES[v]

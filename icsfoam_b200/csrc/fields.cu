@@ -80,6 +80,9 @@ __global__ void k_bc(int NB, int off, const int* __restrict__ bfOwnerPos, const 
     const double psiOld = f[Q_PSI * NX + s];
     double Ub[3] = {f[Q_UX * NX + s], f[Q_UY * NX + s], f[Q_UZ * NX + s]};  // previous boundary velocity (totalPressure reads it)
     double pb = pP, Tb = TP, pVIC = 1.0, tVIC = 1.0, uVIC[3] = {1.0, 1.0, 1.0};
+    // gradientInternalCoeffs = -deltaCoeffs * g (viscousFluxScheme.C:58-59): g = 1 fixedValue family, 0 zeroGradient, valueFraction for
+    // mixed, snGradTransformDiag for the transform family (|nHat_d| symmetry, sqrt|valueFraction_dd| directionMixed; scalars 0)
+    double gU[3] = {1.0, 1.0, 1.0}, gT = 1.0;
     const double vfracPhi = 1.0 - pos0(phi);
     // ---- p
     {
@@ -117,18 +120,18 @@ __global__ void k_bc(int NB, int off, const int* __restrict__ bfOwnerPos, const 
     {
         const double* prm = bc.prm[1];
         switch (bc.kind[1]) {
-            case ICSB200_BC_ZEROGRADIENT: for (int d = 0; d < 3; d++) { Ub[d] = UP[d]; uVIC[d] = 1.0; } break;
+            case ICSB200_BC_ZEROGRADIENT: for (int d = 0; d < 3; d++) { Ub[d] = UP[d]; uVIC[d] = 1.0; gU[d] = 0.0; } break;
             case ICSB200_BC_FIXEDVALUE: for (int d = 0; d < 3; d++) { Ub[d] = prm[d]; uVIC[d] = 0.0; } break;
             case ICSB200_BC_SLIP: {
                 // basicSymmetryFvPatchField<vector>::evaluate
                 double xx = 1.0 - 2.0 * (n[0] * n[0]), xy = 0.0 - 2.0 * (n[0] * n[1]), xz = 0.0 - 2.0 * (n[0] * n[2]);
                 double yy = 1.0 - 2.0 * (n[1] * n[1]), yz = 0.0 - 2.0 * (n[1] * n[2]), zz = 1.0 - 2.0 * (n[2] * n[2]);
                 double t[3] = {xx * UP[0] + xy * UP[1] + xz * UP[2], xy * UP[0] + yy * UP[1] + yz * UP[2], xz * UP[0] + yz * UP[1] + zz * UP[2]};
-                for (int d = 0; d < 3; d++) { Ub[d] = (UP[d] + t[d]) / 2.0; uVIC[d] = 1.0 - fabs(n[d]); }
+                for (int d = 0; d < 3; d++) { Ub[d] = (UP[d] + t[d]) / 2.0; uVIC[d] = 1.0 - fabs(n[d]); gU[d] = fabs(n[d]); }
                 break;
             }
             case ICSB200_BC_INLETOUTLET:
-                for (int d = 0; d < 3; d++) { Ub[d] = vfracPhi * prm[d] + (1.0 - vfracPhi) * (UP[d] + 0.0); uVIC[d] = 1.0 * (1.0 - vfracPhi); }
+                for (int d = 0; d < 3; d++) { Ub[d] = vfracPhi * prm[d] + (1.0 - vfracPhi) * (UP[d] + 0.0); uVIC[d] = 1.0 * (1.0 - vfracPhi); gU[d] = vfracPhi; }
                 break;
             case ICSB200_BC_PRESSUREINLETOUTLETVELOCITY: {
                 double sgn = negf(phi);
@@ -142,7 +145,7 @@ __global__ void k_bc(int NB, int off, const int* __restrict__ bfOwnerPos, const 
                 double iv[6] = {1.0 - vf[0], 0.0 - vf[1], 0.0 - vf[2], 1.0 - vf[3], 0.0 - vf[4], 1.0 - vf[5]};
                 double tg[3] = {iv[0] * g[0] + iv[1] * g[1] + iv[2] * g[2], iv[1] * g[0] + iv[3] * g[1] + iv[4] * g[2],
                                 iv[2] * g[0] + iv[4] * g[1] + iv[5] * g[2]};
-                for (int d = 0; d < 3; d++) { Ub[d] = nv[d] + tg[d]; uVIC[d] = 1.0 - sqrt(fabs(sgn * (1.0 - n[d] * n[d]))); }
+                for (int d = 0; d < 3; d++) { Ub[d] = nv[d] + tg[d]; uVIC[d] = 1.0 - sqrt(fabs(sgn * (1.0 - n[d] * n[d]))); gU[d] = sqrt(fabs(sgn * (1.0 - n[d] * n[d]))); }
                 break;
             }
             default: for (int d = 0; d < 3; d++) { Ub[d] = UP[d]; uVIC[d] = 0.0; } break;
@@ -154,9 +157,9 @@ __global__ void k_bc(int NB, int off, const int* __restrict__ bfOwnerPos, const 
         const double* prm = bc.prm[2];
         switch (bc.kind[2]) {
             case ICSB200_BC_ZEROGRADIENT:
-            case ICSB200_BC_SLIP: Tb = TP; tVIC = 1.0; break;
+            case ICSB200_BC_SLIP: Tb = TP; tVIC = 1.0; gT = 0.0; break;
             case ICSB200_BC_FIXEDVALUE: Tb = prm[0]; tVIC = 0.0; fixesT = true; break;
-            case ICSB200_BC_INLETOUTLET: Tb = vfracPhi * prm[0] + (1.0 - vfracPhi) * (TP + 0.0); tVIC = 1.0 * (1.0 - vfracPhi); break;
+            case ICSB200_BC_INLETOUTLET: Tb = vfracPhi * prm[0] + (1.0 - vfracPhi) * (TP + 0.0); tVIC = 1.0 * (1.0 - vfracPhi); gT = vfracPhi; break;
             case ICSB200_BC_TOTALTEMPERATURE: {
                 double T0 = prm[0], g = prm[1];
                 double gM1ByG = (g - 1) / g;
@@ -180,6 +183,7 @@ __global__ void k_bc(int NB, int off, const int* __restrict__ bfOwnerPos, const 
     f[Q_RHO * NX + s] = psib * pb;
     f[Q_UX * NX + s] = Ub[0]; f[Q_UY * NX + s] = Ub[1]; f[Q_UZ * NX + s] = Ub[2];
     vic[b] = pVIC; vic[NB + b] = uVIC[0]; vic[2 * (size_t)NB + b] = uVIC[1]; vic[3 * (size_t)NB + b] = uVIC[2]; vic[4 * (size_t)NB + b] = tVIC;
+    vic[5 * (size_t)NB + b] = gU[0]; vic[6 * (size_t)NB + b] = gU[1]; vic[7 * (size_t)NB + b] = gU[2]; vic[8 * (size_t)NB + b] = gT;
 }
 
 // derived fields E, H, cR, c on cell positions and physical boundary slots
@@ -340,7 +344,8 @@ int ics_primitives(icsb200_ctx* c)
     }
     CUDA_TRY(c, cudaGetLastError());
     // neighbour-rank copies of the arrays the face kernels gather: rho p Ux Uy Uz cR E H c (+ eCalc) (contiguous ids 0..9)
-    return ics_halo_fields(c, c->d_fields, c->NX, c->mu > 0 ? 10 : 9, 1u << Q_UX);
+    // + T (id 10) for the stored coupled-patch values of the full viscous Jacobian
+    return ics_halo_fields(c, c->d_fields, c->NX, c->mu > 0 ? (c->sch.viscous_full_jacobian ? 11 : 10) : 9, 1u << Q_UX);
 }
 
 // conserved variables + boundary + derived fields from freshly uploaded p, U, T (host-facing iterate)

@@ -54,6 +54,7 @@ struct JacArgs {
     double *offd, *diag, *rD, *rdt, *ddtCoeff;
     const double* recon;  // [8*NFG] limited face states stored by k_flux_faces (REUSE instantiation)
     const double* tr;              // [2][NX] muEff, alphaEff fields or null (laminar constants)
+    double R, TMin;                // thermo / bounds for the values stored on coupled patches (full viscous Jacobian)
     const double *mrf, *mrfOmega;  // MRFFaceVelocity [NFG] (GPU face order) and MRFOmega [3*NP]; null = zero field
 };
 
@@ -83,7 +84,10 @@ __device__ __forceinline__ void eulerJacobian(V3 U, double E, V3 n, double gamma
 
 __device__ __forceinline__ bool isDiagEntry(int k) { return k == 0 || k == 6 || k == 12 || k == 18 || k == 24; }
 
-template <bool REUSE>
+// FULLV: LaxFriedrichJacobian false — viscousFluxScheme::addFluxTerms :248-261 (five fvj::laplacian(sf, vf) blocks,
+// blockFvOperatorsTemplates.C:387-450,575-637: upper = vf[nei] sf2, lower = vf[own] sf2, negSumDiag, coupled: diag[own] -=
+// vf[own] sf2_b, interfacesUpper = vf_b sf2_b with the values STORED on the patch) and addBoundaryTerms :120-215
+template <bool REUSE, bool FULLV>
 __global__ void __launch_bounds__(128, 3)
 k_jac(JacArgs a)
 {
@@ -100,6 +104,14 @@ k_jac(JacArgs a)
     bool hasPhys = false;
     const double cOwn = a.f[(size_t)Q_C * a.NX + p];
     const V3 UOwn = {a.f[(size_t)Q_UX * a.NX + p], a.f[(size_t)Q_UY * a.NX + p], a.f[(size_t)Q_UZ * a.NX + p]};
+    // full viscous Jacobian: vf = -U/rho, 1/rho, -E/rho + |U|^2/rho at the row cell and the negSumDiag accumulators of the five blocks
+    double vRowU[3] = {0, 0, 0}, vRowInv = 0.0, vRowE = 0.0, aMomRho[3] = {0, 0, 0}, aMomU = 0.0, aERho = 0.0, aEU[3] = {0, 0, 0}, aEE = 0.0;
+    if (FULLV) {
+        const double rho = a.f[(size_t)Q_RHO * a.NX + p], E = a.f[(size_t)Q_E * a.NX + p];
+        vRowU[0] = -UOwn.x / rho; vRowU[1] = -UOwn.y / rho; vRowU[2] = -UOwn.z / rho;
+        vRowInv = 1.0 / rho;
+        vRowE = -E / rho + (UOwn.x * UOwn.x + UOwn.y * UOwn.y + UOwn.z * UOwn.z) / rho;
+    }
     for (int j = 0; j < nAll; j++) {
         const size_t e = (base + j) * 32 + lane;
         const int c = a.col[e], m = a.meta[e], type = m & 3;
@@ -187,19 +199,50 @@ k_jac(JacArgs a)
         rdt = fmax(rdt, a.geo[G_NONORTH * a.NFG + g] * lam);
         const double dl = 0.5 * magSf * lam;
         dissAcc -= dl;
-        double sf2 = 0.0;
+        double sf2 = 0.0, sf2mu = 0.0, sf2al = 0.0, vColU[3] = {0, 0, 0}, vColInv = 0.0, vColE = 0.0;
         if (a.mu > 0) {
             const double rP = a.f[(size_t)Q_RHO * a.NX + P], rN = a.f[(size_t)Q_RHO * a.NX + N];
             const double rhof = coupled ? (w * rP + (1.0 - w) * rN) : (w * (rP - rN) + rN);
-            double muf = a.mu, alf = a.alphaEff;
-            if (a.tr) {  // fvc::interpolate(turbulence.muEff()), fvc::interpolate(turbulence.alphaEff()) (viscousFluxScheme.C:222-223)
-                const double muP = a.tr[P], muN = a.tr[N], alP = a.tr[a.NX + P], alN = a.tr[a.NX + N];
-                muf = coupled ? (w * muP + (1.0 - w) * muN) : (w * (muP - muN) + muN);
-                alf = coupled ? (w * alP + (1.0 - w) * alN) : (w * (alP - alN) + alN);
+            // fvc::interpolate(turbulence.muEff()), fvc::interpolate(turbulence.alphaEff()) (viscousFluxScheme.C:222-223)
+            const double muP = a.tr ? a.tr[P] : a.mu, muN = a.tr ? a.tr[N] : a.mu;
+            const double alP = a.tr ? a.tr[a.NX + P] : a.alphaEff, alN = a.tr ? a.tr[a.NX + N] : a.alphaEff;
+            const double muf = coupled ? (w * muP + (1.0 - w) * muN) : (w * (muP - muN) + muN);
+            const double alf = coupled ? (w * alP + (1.0 - w) * alN) : (w * (alP - alN) + alN);
+            if (!FULLV) {
+                const double lambdaVisc = (muf + alf) / rhof;
+                sf2 = (0.5 * lambdaVisc) * magSf * a.geo[G_DELTA * a.NFG + g];
+                viscAcc -= sf2;
+            } else {
+                sf2mu = muf * magSf * a.geo[G_DELTA * a.NFG + g];
+                sf2al = alf * magSf * a.geo[G_DELTA * a.NFG + g];
+                // vf at the column: the neighbour cell, or the values stored on the coupled patch (updateFields.H:80-104):
+                // cyclic / cyclicAMI store w*internal + (1-w)*patchNeighbourField, processor patches the neighbour values;
+                // then T = THE(he(T)), psi = 1/(R T), rho = psi p, E = he + 0.5 |U|^2
+                double rhoC, EC, UC[3] = {a.f[(size_t)Q_UX * a.NX + c], a.f[(size_t)Q_UY * a.NX + c], a.f[(size_t)Q_UZ * a.NX + c]};
+                if (!coupled) {
+                    rhoC = a.f[(size_t)Q_RHO * a.NX + c];
+                    EC = a.f[(size_t)Q_E * a.NX + c];
+                } else {
+                    double pb = a.f[(size_t)Q_P * a.NX + c], Tb = a.f[(size_t)Q_T * a.NX + c];
+                    if (a.bfKind[b] != ICSB200_PROCESSOR) {
+                        pb = w * a.f[(size_t)Q_P * a.NX + p] + (1.0 - w) * pb;
+                        Tb = w * a.f[(size_t)Q_T * a.NX + p] + (1.0 - w) * Tb;
+                        UC[0] = w * UOwn.x + (1.0 - w) * UC[0]; UC[1] = w * UOwn.y + (1.0 - w) * UC[1]; UC[2] = w * UOwn.z + (1.0 - w) * UC[2];
+                    }
+                    Tb = fmax(Tb, a.TMin);
+                    const double eb = a.Cv * Tb;
+                    Tb = eb / a.Cv;
+                    const double psib = 1.0 / (a.R * Tb);
+                    rhoC = psib * pb;
+                    EC = a.Cv * Tb + 0.5 * (UC[0] * UC[0] + UC[1] * UC[1] + UC[2] * UC[2]);
+                }
+                vColU[0] = -UC[0] / rhoC; vColU[1] = -UC[1] / rhoC; vColU[2] = -UC[2] / rhoC;
+                vColInv = 1.0 / rhoC;
+                vColE = -EC / rhoC + (UC[0] * UC[0] + UC[1] * UC[1] + UC[2] * UC[2]) / rhoC;
+#pragma unroll
+                for (int d = 0; d < 3; d++) { aMomRho[d] -= vRowU[d] * sf2mu; aEU[d] -= vRowU[d] * sf2al; }
+                aMomU -= vRowInv * sf2mu; aERho -= vRowE * sf2al; aEE -= vRowInv * sf2al;
             }
-            const double lambdaVisc = (muf + alf) / rhof;
-            sf2 = (0.5 * lambdaVisc) * magSf * a.geo[G_DELTA * a.NFG + g];
-            viscAcc -= sf2;
         }
         double JL[25], JR[25];
         eulerJacobian({L[0], L[1], L[2]}, L[3], n, a.gamma, JL);
@@ -213,7 +256,14 @@ k_jac(JacArgs a)
             double off;
             if (rowIsP) { off = hasConv ? (0.0 + upp) : 0.0; if (hasConv) conv[k] -= low; }
             else { off = hasConv ? (0.0 + low) : 0.0; if (hasConv) conv[k] -= upp; }
-            if (isDiagEntry(k)) { if (a.mrf) off -= mrfOff * 1.0; off -= dl; if (a.mu > 0) off -= sf2 * 1.0; }
+            if (isDiagEntry(k)) { if (a.mrf) off -= mrfOff * 1.0; off -= dl; if (!FULLV && a.mu > 0) off -= sf2 * 1.0; }
+            if (FULLV) {
+                if (k == 5 || k == 10 || k == 15) off -= vColU[k / 5 - 1] * sf2mu;        // dMomByRho
+                else if (k == 6 || k == 12 || k == 18) off -= vColInv * sf2mu;            // dMomByRhoU (* I)
+                else if (k == 20) off -= vColE * sf2al;                                   // dEnergyByRho
+                else if (k >= 21 && k <= 23) off -= vColU[k - 21] * sf2al;                // dEnergyByRhoU
+                else if (k == 24) off -= vColInv * sf2al;                                 // dEnergyByRhoE
+            }
             blk[(size_t)k * 32] = off;
         }
     }
@@ -329,7 +379,47 @@ k_jac(JacArgs a)
         const double ox = a.mrfOmega[p], oy = a.mrfOmega[(size_t)a.NP + p], oz = a.mrfOmega[2 * (size_t)a.NP + p];
         dg[7] -= oz * vol; dg[8] += oy * vol; dg[11] += oz * vol; dg[13] -= ox * vol; dg[16] -= oy * vol; dg[17] += ox * vol;
     }
-    if (a.mu > 0) { dg[0] -= viscAcc * 1.0; dg[6] -= viscAcc * 1.0; dg[12] -= viscAcc * 1.0; dg[18] -= viscAcc * 1.0; dg[24] -= viscAcc * 1.0; }
+    if (!FULLV && a.mu > 0) { dg[0] -= viscAcc * 1.0; dg[6] -= viscAcc * 1.0; dg[12] -= viscAcc * 1.0; dg[18] -= viscAcc * 1.0; dg[24] -= viscAcc * 1.0; }
+    if (FULLV) {
+        dg[5] -= aMomRho[0]; dg[10] -= aMomRho[1]; dg[15] -= aMomRho[2];
+        dg[6] -= aMomU; dg[12] -= aMomU; dg[18] -= aMomU;
+        dg[20] -= aERho; dg[21] -= aEU[0]; dg[22] -= aEU[1]; dg[23] -= aEU[2]; dg[24] -= aEE;
+        if (hasPhys) {
+            // viscousFluxScheme::addBoundaryTerms (:120-215): wall terms through gradientInternalCoeffs of U and T
+            const double rhoI = a.f[(size_t)Q_RHO * a.NX + p], TI = a.f[(size_t)Q_T * a.NX + p], cvI = a.Cv;
+            const V3 UI = UOwn;
+            const double EI = a.Cv * TI + 0.5 * magSqr(UI);
+            const V3 dUdRho = -1.0 * UI / rhoI;
+            const double dTdRho = -1.0 / (cvI * rhoI) * (EI - magSqr(UI));
+            const double dUdRhoU = 1.0 / rhoI * 1.0;
+            const V3 dTdRhoU = -1.0 * UI / (cvI * rhoI);
+            const double dTdRhoE = 1.0 / (cvI * rhoI);
+            const double du[3] = {dUdRho.x, dUdRho.y, dUdRho.z}, dtu[3] = {dTdRhoU.x, dTdRhoU.y, dTdRhoU.z};
+            for (int j = 0; j < nAll; j++) {
+                const size_t e = (base + j) * 32 + lane;
+                const int m = a.meta[e];
+                if ((m & 3) != ET_PHYS) continue;
+                const int c = a.col[e];
+                const size_t g = a.gfid[e];
+                const int b = (m >> 2) - a.F;
+                const double magSfB = a.geo[G_MAGSF * a.NFG + g], dcB = a.geo[G_DELTA * a.NFG + g];
+                const double muB = a.tr ? a.tr[c] : a.mu, alB = a.tr ? a.tr[a.NX + c] : a.alphaEff;
+                const double TGIC = -dcB * a.vic[8 * (size_t)a.NB + b];
+                const double dEnergyFluxdT = -alB * a.Cv * TGIC * magSfB;
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const double uGIC = -dcB * a.vic[(size_t)(5 + d) * a.NB + b];
+                    const double dMomFluxdU = -muB * uGIC * magSfB;
+                    dg[5 + 5 * d] += dMomFluxdU * du[d];
+                    dg[6 + 6 * d] += dMomFluxdU * dUdRhoU;
+                    dg[9 + 5 * d] += dMomFluxdU * 0.0;
+                }
+                dg[20] += dEnergyFluxdT * dTdRho;
+                dg[21] += dEnergyFluxdT * dtu[0]; dg[22] += dEnergyFluxdT * dtu[1]; dg[23] += dEnergyFluxdT * dtu[2];
+                dg[24] += dEnergyFluxdT * dTdRhoE;
+            }
+        }
+    }
 #pragma unroll
     for (int k = 0; k < 25; k++) a.diag[(size_t)k * a.NP + p] = dg[k];
     // lusgs ctor (lusgs.C:50-125): rDiagCoeff = 1/max(|diag entries of the S-S and V-V diagonal blocks|)
@@ -496,8 +586,13 @@ int ics_jacobian(icsb200_ctx* c, bool useStoredRdt)
         a.recon = c->d_faceRecon;
         a.mrf = c->d_mrfFace; a.mrfOmega = c->d_mrfOmega;
         a.tr = c->d_transport;
-        if (c->reconValid && c->d_faceRecon) k_jac<true><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(a);
-        else k_jac<false><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(a);
+        a.R = c->R; a.TMin = c->sch.T_min;
+        const bool reuse = c->reconValid && c->d_faceRecon, fullv = c->mu > 0 && c->sch.viscous_full_jacobian;
+        if (fullv) {
+            if (reuse) k_jac<true, true><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(a);
+            else k_jac<false, true><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(a);
+        } else if (reuse) k_jac<true, false><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(a);
+        else k_jac<false, false><<<gridFor(c->NP, 128), 128, 0, c->stream>>>(a);
     }
     CUDA_TRY(c, cudaGetLastError());
     c->matrixSet = true;

@@ -810,7 +810,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     r |= devAlloc(c, &c->d_dW, (size_t)5 * NPH);
     r |= devAlloc(c, &c->d_bad, (size_t)NPH);
     r |= devAlloc(c, &c->d_phiB, (size_t)std::max(NB, 1));
-    r |= devAlloc(c, &c->d_vic, (size_t)5 * std::max(NB, 1));
+    r |= devAlloc(c, &c->d_vic, (size_t)9 * std::max(NB, 1));
     r |= devAlloc(c, &c->d_offd, nE32 * 25);
     r |= devAlloc(c, &c->d_diag, (size_t)25 * NP);
     r |= devAlloc(c, &c->d_rD, (size_t)NP);
@@ -831,7 +831,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     CUDA_TRY(c, cudaMemset(c->d_co, 0, sizeof(double) * NP));
     CUDA_TRY(c, cudaMemset(c->d_ddtCoeff, 0, sizeof(double) * NP));
     CUDA_TRY(c, cudaMemset(c->d_phiB, 0, sizeof(double) * std::max(NB, 1)));
-    CUDA_TRY(c, cudaMemset(c->d_vic, 0, sizeof(double) * 5 * std::max(NB, 1)));
+    CUDA_TRY(c, cudaMemset(c->d_vic, 0, sizeof(double) * 9 * std::max(NB, 1)));
     CUDA_TRY(c, cudaMemset(c->d_bad, 0, sizeof(int) * NPH));
     c->lusgsGrid = 0;
     c->lusgsTileGrid = 0;

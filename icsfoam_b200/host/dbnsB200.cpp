@@ -171,6 +171,7 @@ int main(int argc, char** argv)
         sch.rho_min = pseudo.getOrDefault<double>("rhoMin", -1e15);
         sch.T_min = pseudo.getOrDefault<double>("TMin", 1e-15);
         sch.T_max = pseudo.getOrDefault<double>("TMax", 1e15);
+        sch.viscous_full_jacobian = viscousFluxScheme(ctx, fvSchemes).fullJacobian();
         check(ctx, icsb200_schemes_set(ctx, &sch), "schemes_set");
         std::cout << (steadyState ? "Steady-state analysis detected\n" : "Transient analysis detected\n");
 

@@ -81,6 +81,9 @@ typedef struct {
     double pseudo_co_num_min, pseudo_co_num_max;          /* beginTimeStep.H:29-33 */
     double pseudo_co_num_max_incr, pseudo_co_num_min_decr; /* beginTimeStep.H:35-45 */
     double rho_min, T_min, T_max;                          /* updateFields.H:11-35 */
+    int viscous_full_jacobian; /* 0 (default): viscousFluxScheme/LaxFriedrichJacobian true (viscousFluxScheme.C:228-240);
+                                * 1: LaxFriedrichJacobian false — the fvj::laplacian blocks of :248-261 and the wall terms of
+                                * viscousFluxScheme::addBoundaryTerms (:120-215, gradientInternalCoeffs) */
 } icsb200_schemes;
 
 typedef struct {

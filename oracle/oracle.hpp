@@ -90,6 +90,8 @@ struct Ctx {
     // valueInternalCoeffs of p/U/T per boundary face, frozen when the BCs were last evaluated
     // (mixedFvPatchField keeps valueFraction_ from its last updateCoeffs)
     vecd vicP, vicU, vicT;
+    // gradientInternalCoeffs of U / T per boundary face, frozen with them (viscousFluxScheme.C:58-59, full viscous Jacobian)
+    vecd gicU, gicT;
     // old-time levels of the conserved variables (cells only)
     vecd rho0, rhoU0, rhoE0, rho00, rhoU00, rhoE00;
     int timeIndex = 0;

@@ -393,12 +393,14 @@ void correctBoundary(Ctx& c)
     for (size_t pi = 0; pi < m.patches.size(); pi++) if (!m.empty(m.patches[pi]) && !m.coupled(m.patches[pi])) evalU(c, (int)pi);
     for (size_t pi = 0; pi < m.patches.size(); pi++) if (!m.empty(m.patches[pi]) && !m.coupled(m.patches[pi])) evalT(c, (int)pi);
     c.vicP.assign(m.NB, 0.0); c.vicU.assign(3 * (size_t)m.NB, 0.0); c.vicT.assign(m.NB, 0.0);
+    c.gicU.assign(3 * (size_t)m.NB, 0.0); c.gicT.assign(m.NB, 0.0);
     for (size_t pi = 0; pi < m.patches.size(); pi++) {
         auto& p = m.patches[pi];
         if (m.empty(p) || m.coupled(p)) continue;
         for (int f = p.start; f < p.start + p.size; f++) {
             int b = f - m.F;
             valueInternalCoeffs(c, (int)pi, f, c.vicP[b], &c.vicU[3 * (size_t)b], c.vicT[b]);
+            gradientInternalCoeffs(c, (int)pi, f, &c.gicU[3 * (size_t)b], c.gicT[b]);
         }
     }
     syncCoupled(c, c.p, 1);
@@ -473,6 +475,37 @@ void valueInternalCoeffs(const Ctx& c, int pi, int f, double& pVIC, double uVIC[
         case ICSB200_BC_ZEROGRADIENT: case ICSB200_BC_SLIP: tVIC = 1.0; break;
         case ICSB200_BC_INLETOUTLET: tVIC = 1.0 * (1.0 - vfracPhi()); break;
         default: tVIC = 0.0; break;
+    }
+}
+
+// gradientInternalCoeffs of the U / T patch fields (viscousFluxScheme.C:58-59): fixedValue -deltaCoeffs; zeroGradient 0;
+// mixed -valueFraction deltaCoeffs; transform (basicSymmetry, directionMixed) -deltaCoeffs snGradTransformDiag(), with
+// snGradTransformDiag = |nHat_d| for the symmetry family and sqrt(|valueFraction_dd|) for directionMixed; scalars on
+// transform patches 0 (transformFvPatchScalarField)
+void gradientInternalCoeffs(const Ctx& c, int pi, int f, double uGIC[3], double& tGIC)
+{
+    const Mesh& m = c.m;
+    const double dc = m.deltaCoeffs[f];
+    auto vfracPhi = [&]() { return 1.0 - pos0(c.phi[f]); };
+    const BC& bu = c.bc[pi][ICSB200_FIELD_U];
+    switch (bu.kind) {
+        case ICSB200_BC_ZEROGRADIENT: uGIC[0] = uGIC[1] = uGIC[2] = 0.0; break;
+        case ICSB200_BC_SLIP: { double n[3]; nHat(m, f, n); for (int d = 0; d < 3; d++) uGIC[d] = -dc * std::fabs(n[d]); break; }
+        case ICSB200_BC_INLETOUTLET: for (int d = 0; d < 3; d++) uGIC[d] = -1.0 * vfracPhi() * dc; break;
+        case ICSB200_BC_PRESSUREINLETOUTLETVELOCITY: {
+            double n[3];
+            nHat(m, f, n);
+            double sgn = neg(c.phi[f]);
+            for (int d = 0; d < 3; d++) uGIC[d] = -dc * std::sqrt(std::fabs(sgn * (1.0 - n[d] * n[d])));
+            break;
+        }
+        default: uGIC[0] = uGIC[1] = uGIC[2] = -1.0 * dc; break;  // fixedValue family
+    }
+    const BC& bt = c.bc[pi][ICSB200_FIELD_T];
+    switch (bt.kind) {
+        case ICSB200_BC_ZEROGRADIENT: case ICSB200_BC_SLIP: tGIC = 0.0; break;
+        case ICSB200_BC_INLETOUTLET: tGIC = -1.0 * vfracPhi() * dc; break;
+        default: tGIC = -1.0 * dc; break;  // fixedValue, totalTemperature
     }
 }
 

@@ -796,7 +796,152 @@ void subtractDivFace(const Mesh& m, Blk& A, const vecd& sf, std::initializer_lis
     }
 }
 
+// fvj::laplacian(sf, vf) (blockFvOperatorsTemplates.C:387-450 / :575-637), then A -= mx [* I]: vf is a cell field with nv
+// components over cells and boundary slots (boundary = the values STORED on the patch, see storedCoupledValues), sf2 = sf |Sf|
+// deltaCoeffs; upper = vf[nei] sf2, lower = vf[own] sf2, negSumDiag, coupled patches: diag[own] -= vf[own] sf2_b
+void subtractLaplacianField(const Mesh& m, Blk& A, const vecd& sf2, const vecd& vf, int nv, const int* slots)
+{
+    const int nc = A.nc;
+    vecd upp((size_t)nv * m.F), low((size_t)nv * m.F), diag((size_t)nv * m.N, 0.0), iu((size_t)nv * m.NB, 0.0), il((size_t)nv * m.NB, 0.0);
+    for (int f = 0; f < m.F; f++)
+        for (int k = 0; k < nv; k++) {
+            upp[(size_t)nv * f + k] = vf[(size_t)nv * m.neighbour[f] + k] * sf2[f];
+            low[(size_t)nv * f + k] = vf[(size_t)nv * m.owner[f] + k] * sf2[f];
+        }
+    for (int f = 0; f < m.F; f++)
+        for (int k = 0; k < nv; k++) {
+            diag[(size_t)nv * m.owner[f] + k] -= low[(size_t)nv * f + k];
+            diag[(size_t)nv * m.neighbour[f] + k] -= upp[(size_t)nv * f + k];
+        }
+    for (auto& p : m.patches) {
+        if (m.empty(p)) continue;
+        for (int f = p.start; f < p.start + p.size; f++)
+            for (int k = 0; k < nv; k++) {
+                iu[(size_t)nv * (f - m.F) + k] = vf[(size_t)nv * (m.N + f - m.F) + k] * sf2[f];
+                il[(size_t)nv * (f - m.F) + k] = vf[(size_t)nv * m.owner[f] + k] * sf2[f];
+            }
+        if (m.coupled(p))
+            for (int f = p.start; f < p.start + p.size; f++)
+                for (int k = 0; k < nv; k++) diag[(size_t)nv * m.owner[f] + k] -= il[(size_t)nv * (f - m.F) + k];
+    }
+    ensureOff(A, m);
+    // slots[k]: coefficient slot of A receiving component k (vector blocks: 0,1,2; scalar into tensor: one call per 0,4,8 with * 1.0)
+    for (int k = 0; k < nv; k++) {
+        const int s = slots[k];
+        for (int i = 0; i < m.N; i++) A.diag[(size_t)nc * i + s] -= diag[(size_t)nv * i + k];
+        for (int f = 0; f < m.F; f++) { A.upper[(size_t)nc * f + s] -= upp[(size_t)nv * f + k]; A.lower[(size_t)nc * f + s] -= low[(size_t)nv * f + k]; }
+        for (int b = 0; b < m.NB; b++) { A.intUpper[(size_t)nc * b + s] -= iu[(size_t)nv * b + k]; A.intLower[(size_t)nc * b + s] -= il[(size_t)nv * b + k]; }
+    }
+}
+
 }  // namespace
+
+// Values STORED on the boundary patches of p, U, T, rho, E as the solver leaves them (updateFields.H:80-104): physical
+// patches carry their boundary condition value; a coupledFvPatchField (cyclic, cyclicAMI) stores
+// w*internal + (1-w)*patchNeighbourField after evaluate(), a processor patch stores the neighbour values; then T = THE(he(T)),
+// psi = 1/(R T), rho = psi p and E = he(p,T) + 0.5 |U|^2 are formed from those.  vf.boundaryField() of the expression fields
+// handed to fvj::laplacian reads exactly these.
+static void storedBoundaryValues(const Ctx& c, vecd& rho, vecd& U, vecd& E)
+{
+    const Mesh& m = c.m;
+    const size_t n = (size_t)m.N + m.NB;
+    rho = c.rho; U = c.U; E.assign(n, 0.0);
+    for (size_t i = 0; i < n; i++) {
+        const double* u = &c.U[3 * i];
+        E[i] = c.Cv * c.T[i] + 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    }
+    for (auto& p : m.patches) {
+        if (!m.coupled(p)) continue;
+        const bool interp = p.kind != ICSB200_PROCESSOR;
+        for (int f = p.start; f < p.start + p.size; f++) {
+            const size_t s = (size_t)m.N + f - m.F;
+            const int o = m.owner[f];
+            const double w = m.w[f];
+            double pb = c.p[s], Tb = c.T[s], Ub[3] = {c.U[3 * s], c.U[3 * s + 1], c.U[3 * s + 2]};
+            if (interp) {
+                pb = w * c.p[o] + (1.0 - w) * c.p[s];
+                Tb = w * c.T[o] + (1.0 - w) * c.T[s];
+                for (int d = 0; d < 3; d++) Ub[d] = w * c.U[3 * (size_t)o + d] + (1.0 - w) * c.U[3 * s + d];
+            }
+            Tb = std::max(Tb, c.sch.T_min);
+            const double eb = c.Cv * Tb;
+            Tb = eb / c.Cv;                       // thermo.correct(): T = THE(he, p, T0) on patches that do not fix the value
+            const double psib = 1.0 / (c.R * Tb);
+            rho[s] = psib * pb;
+            for (int d = 0; d < 3; d++) U[3 * s + d] = Ub[d];
+            E[s] = c.Cv * Tb + 0.5 * (Ub[0] * Ub[0] + Ub[1] * Ub[1] + Ub[2] * Ub[2]);
+        }
+    }
+}
+
+// viscousFluxScheme::addFluxTerms, LaxFriedrichJacobian false (viscousFluxScheme.C:248-261), and addBoundaryTerms (:120-215)
+void fullViscousJacobian(Ctx& c)
+{
+    const Mesh& m = c.m;
+    const size_t n = (size_t)m.N + m.NB;
+    Blk& dEnergyByRho = c.blk[2]; Blk& dEnergyByRhoE = c.blk[3]; Blk& dEnergyByRhoU = c.blk[5]; Blk& dMomByRho = c.blk[6];
+    Blk& dMomByRhoE = c.blk[7]; Blk& dMomByRhoU = c.blk[8];
+    vecd muEff(n, c.mu), alphaEff(n, c.gamma * (c.mu / c.Pr)), muf, alf;
+    if (!c.muEffField.empty()) { muEff = c.muEffField; alphaEff = c.alphaEffField; syncCoupled(c, muEff, 1); syncCoupled(c, alphaEff, 1); }
+    interpolateLinear(c, muEff, muf);
+    interpolateLinear(c, alphaEff, alf);
+    auto em = emptyMask(m);
+    vecd sf2mu(m.FT, 0.0), sf2al(m.FT, 0.0);
+    for (int f = 0; f < m.FT; f++)
+        if (faceActive(m, f, em)) { sf2mu[f] = muf[f] * m.magSf[f] * m.deltaCoeffs[f]; sf2al[f] = alf[f] * m.magSf[f] * m.deltaCoeffs[f]; }
+    vecd rho, U, E;
+    storedBoundaryValues(c, rho, U, E);
+    vecd mURho(3 * n), invRho(n), eRho(n);
+    for (size_t i = 0; i < n; i++) {
+        if (rho[i] == 0.0) { mURho[3 * i] = mURho[3 * i + 1] = mURho[3 * i + 2] = invRho[i] = eRho[i] = 0.0; continue; }  // empty-patch slots
+        const double* u = &U[3 * i];
+        for (int d = 0; d < 3; d++) mURho[3 * i + d] = -u[d] / rho[i];
+        invRho[i] = 1.0 / rho[i];
+        eRho[i] = -E[i] / rho[i] + (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) / rho[i];
+    }
+    static const int v3[3] = {0, 1, 2}, s0[1] = {0}, s4[1] = {4}, s8[1] = {8};
+    subtractLaplacianField(m, dMomByRho, sf2mu, mURho, 3, v3);
+    subtractLaplacianField(m, dMomByRhoU, sf2mu, invRho, 1, s0);   // fvj::laplacian(muEff, 1/rho) * tensor::I
+    subtractLaplacianField(m, dMomByRhoU, sf2mu, invRho, 1, s4);
+    subtractLaplacianField(m, dMomByRhoU, sf2mu, invRho, 1, s8);
+    subtractLaplacianField(m, dEnergyByRho, sf2al, eRho, 1, s0);
+    subtractLaplacianField(m, dEnergyByRhoU, sf2al, mURho, 3, v3);
+    subtractLaplacianField(m, dEnergyByRhoE, sf2al, invRho, 1, s0);
+    // ---- addBoundaryTerms: physical patches, gradientInternalCoeffs of U and T
+    for (size_t pi = 0; pi < m.patches.size(); pi++) {
+        auto& p = m.patches[pi];
+        if (m.coupled(p) || m.empty(p)) continue;
+        for (int f = p.start; f < p.start + p.size; f++) {
+            const int b = f - m.F, iIntCell = m.owner[f];
+            const double magSfB = m.magSf[f], cvB = c.Cv;
+            const double* uGIC = &c.gicU[3 * (size_t)b];
+            const double TGIC = c.gicT[b];
+            // dMomFluxdUDiag = -muEff_b*uGIC*magSfB ; dEnergyFluxdT = -alphaEff_b*cvB*TGIC*magSfB
+            double dMomFluxdU[3];
+            for (int d = 0; d < 3; d++) dMomFluxdU[d] = -muf[f] * uGIC[d] * magSfB;
+            const double dEnergyFluxdT = -alf[f] * cvB * TGIC * magSfB;
+            const double rhoI = c.rho[iIntCell], cvI = c.Cv;
+            const V3 UI = {c.U[3 * (size_t)iIntCell], c.U[3 * (size_t)iIntCell + 1], c.U[3 * (size_t)iIntCell + 2]};
+            const double EI = c.Cv * c.T[iIntCell] + 0.5 * magSqr(UI);
+            const V3 dUdRho = -1.0 * UI / rhoI;
+            const double dTdRho = -1.0 / (cvI * rhoI) * (EI - magSqr(UI));
+            const double dUdRhoU = 1.0 / rhoI * 1.0;
+            const V3 dTdRhoU = -1.0 * UI / (cvI * rhoI);
+            const double dTdRhoE = 1.0 / (cvI * rhoI);
+            const double du[3] = {dUdRho.x, dUdRho.y, dUdRho.z};
+            for (int d = 0; d < 3; d++) {
+                dMomByRho.diag[3 * (size_t)iIntCell + d] += dMomFluxdU[d] * du[d];          // tensor (diagonal) & vector
+                dMomByRhoU.diag[9 * (size_t)iIntCell + 4 * d] += dMomFluxdU[d] * dUdRhoU;    // tensor & sphericalTensor
+                dMomByRhoE.diag[3 * (size_t)iIntCell + d] += dMomFluxdU[d] * 0.0;            // dUdRhoE = 0
+            }
+            dEnergyByRho.diag[iIntCell] += dEnergyFluxdT * dTdRho;
+            dEnergyByRhoU.diag[3 * (size_t)iIntCell] += dEnergyFluxdT * dTdRhoU.x;
+            dEnergyByRhoU.diag[3 * (size_t)iIntCell + 1] += dEnergyFluxdT * dTdRhoU.y;
+            dEnergyByRhoU.diag[3 * (size_t)iIntCell + 2] += dEnergyFluxdT * dTdRhoU.z;
+            dEnergyByRhoE.diag[iIntCell] += dEnergyFluxdT * dTdRhoE;
+        }
+    }
+}
 
 // convectiveFluxScheme::createConvectiveJacobian + viscousFluxScheme::createViscousJacobian (LF branch)
 void createJacobian(Ctx& c)
@@ -967,7 +1112,7 @@ void createJacobian(Ctx& c)
         }
 
     // ---- viscousFluxScheme::addFluxTerms, LaxFriedrichJacobian branch (viscousFluxScheme.C:220-246)
-    if (c.mu > 0) {
+    if (c.mu > 0 && !c.sch.viscous_full_jacobian) {
         size_t n = (size_t)m.N + m.NB;
         vecd muEff(n, c.mu), alphaEff(n, c.gamma * (c.mu / c.Pr)), muf, alf, rhof, half(m.FT, 0.0);
         if (!c.muEffField.empty()) { muEff = c.muEffField; alphaEff = c.alphaEffField; syncCoupled(c, muEff, 1); syncCoupled(c, alphaEff, 1); }
@@ -979,6 +1124,8 @@ void createJacobian(Ctx& c)
         subtractLaplacianOne(m, dMomByRhoU, half, {0, 4, 8});
         subtractLaplacianOne(m, dEnergyByRhoE, half, {0});
     }
+    // ---- LaxFriedrichJacobian false: viscousFluxScheme::addFluxTerms :248-261 + addBoundaryTerms :120-215
+    if (c.mu > 0 && c.sch.viscous_full_jacobian) fullViscousJacobian(c);
     // addMRFSource, source part (convectiveFluxScheme.C:125-128): rhoU = rho*U, source -= (Omega ^ rhoU)*V.  The reference
     // applies it once to the fresh eqSystem of the iteration; the flag keeps a repeated assemble() from doing it twice.
     if (!c.mrfOmega.empty() && !c.srcMrfApplied) {

@@ -17,6 +17,7 @@ void interpolateLimitedLR(Ctx& c, const vecd& vf, int lim, vecd& sfL, vecd& sfR)
 void surfaceIntegrate(const Ctx& c, const vecd& ssf, int nc, vecd& div);
 void correctBoundary(Ctx& c);
 void valueInternalCoeffs(const Ctx& c, int pi, int f, double& pVIC, double uVIC[3], double& tVIC);
+void gradientInternalCoeffs(const Ctx& c, int pi, int f, double uGIC[3], double& tGIC);
 void stateInit(Ctx& c, const double* p, const double* U, const double* T);
 
 // oracle_flux.cpp
@@ -27,6 +28,7 @@ void serUpdate(Ctx& c);
 void pseudoDeltaT(Ctx& c);
 void computeDdtCoeff(Ctx& c);
 void createJacobian(Ctx& c);
+void fullViscousJacobian(Ctx& c);
 void updateFields(Ctx& c);
 void boundLocalTimeStep(Ctx& c);
 void newTimeStep(Ctx& c);

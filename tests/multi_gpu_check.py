@@ -75,6 +75,8 @@ def main():
         c = cases.onera_box(n, parts=parts, rank=r, mu=mu)
         if variant == "globaldt":
             c.schemes.local_timestepping = 0
+        if variant == "fullvisc":
+            c.schemes.viscous_full_jacobian = 1
         if variant == "mrf":
             c.with_mrf(omega=(0.0, 40.0, 90.0), origin=(0.5, 0.0, 1.5), zone=lambda x: x[:, 0] > 0.2)
         return c

@@ -39,6 +39,11 @@ def test_against_golden_fixtures(name, gpu_context):
     assert g.launch_count() > 0
 
 
+def FULLV(case):
+    case.schemes.viscous_full_jacobian = 1
+    return case
+
+
 def TURB(x):
     """smooth positive muEff / alphaEff fields standing in for mu + mut, alpha + alphat of a turbulence model"""
     mu = 0.05 * (1.5 + np.sin(3.0 * x[:, 0]) * np.cos(2.0 * x[:, 1] + 0.5) + 0.3 * x[:, 2])
@@ -81,6 +86,14 @@ LIVE = {
     "rot-roe-minmod": lambda: cases.rot_box(5, "ROE", "Minmod", seed=63, nz=4),
     "rot-ausm-mrf": lambda: cases.rot_box(5, "AUSMPlusUp", "vanLeer", seed=64).with_mrf((0.0, 0.0, 60.0)),
     "rot-viscous-hllc": lambda: cases.rot_box(5, "HLLC", "Minmod", seed=66, mu=0.1),
+    # LaxFriedrichJacobian false: full viscous Jacobian (five fvj::laplacian blocks + wall terms) on cyclic / wall / symmetry /
+    # mixed patches, AMI and rotational pairs (values stored on coupled patches), non-orthogonal bump, muEff field, scrambled
+    "fullvisc-box-roe": lambda: FULLV(cases.periodic_box(6, "ROE", "vanLeer", seed=101, mu=0.05)),
+    "fullvisc-box-hllc-transport": lambda: FULLV(cases.periodic_box(5, "HLLC", "Minmod", seed=102, mu=0.2, Pr=1.3).with_transport(TURB)),
+    "fullvisc-ami": lambda: FULLV(cases.periodic_box(5, "HLLC", "Minmod", seed=103, ami_shift=0.3, mu=0.1)),
+    "fullvisc-rot": lambda: FULLV(cases.rot_box(5, "ROE", "vanLeer", seed=104, mu=0.1)),
+    "fullvisc-bump": lambda: FULLV(cases.bump(15, 10, mu=0.02)),
+    "fullvisc-scrambled": lambda: FULLV(cases.scrambled_box(5, "HLLC", "vanLeer", seed=105, mu=0.1)),
     "shocktube-ausm": lambda: cases.shock_tube(64, "AUSMPlusUp"),
     "shocktube-roe": lambda: cases.shock_tube(50, "ROE"),
 }
@@ -174,6 +187,19 @@ def test_transport_fields_bitwise(gpu_context):
     ref = lam.apply(gpu_context()); ref.calc_flux()
     for x, y in zip(g.residual(), ref.residual()):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("name", ["fullvisc-box-roe", "fullvisc-ami", "fullvisc-rot", "fullvisc-bump"])
+def test_full_viscous_jacobian_bitwise(name, gpu_context):
+    """All 27 LDU arrays and the interface coefficients of the full viscous Jacobian are bit-identical to the oracle."""
+    case = LIVE[name]()
+    o, g = case.apply(Oracle()), case.apply(gpu_context())
+    for api in (o, g):
+        api.calc_flux(); api.residual(); api.pseudo_dt(); api.assemble()
+    for blk in range(9):
+        for a, b in zip(g.matrix_get_ldu(blk), o.matrix_get_ldu(blk)):
+            assert np.array_equal(a, b), blk
+        assert np.array_equal(g.matrix_get_interfaces(blk), o.matrix_get_interfaces(blk)), blk
 
 
 def test_transient_dual_time_euler_and_backward(gpu_context):

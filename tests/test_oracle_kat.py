@@ -708,3 +708,77 @@ def test_solver_only_interfaces_roundtrip_on_the_oracle():
     for blk in range(9):
         c.matrix_set_ldu(blk, *a.matrix_get_ldu(blk))
     assert not np.array_equal(c.matrix_mul(*x)[0], ya[0])        # without the interfaces the cyclic coupling is missing
+
+
+def test_full_viscous_jacobian_known_answers():
+    """LaxFriedrichJacobian false (viscousFluxScheme.C:248-261): the five fvj::laplacian blocks are the exact linearisation of
+    laplacian(muEff, U) and laplacian(alphaEff, e) in the conserved variables (dU/dW = (-U/rho, 1/rho, 0),
+    de/dW = (-E/rho + |U|^2/rho, -U/rho, 1/rho)) on an orthogonal mesh: compare (A_full - A_inviscid) dW with the finite
+    difference of those two Laplacians on interior cells.  Wall terms (:120-215): a no-slip isothermal wall adds
+    muEff deltaCoeffs |Sf| / rho to the (rhoU, rhoU) diagonal and alphaEff Cv deltaCoeffs |Sf| dT/dW to the energy row."""
+    def build(mu, full, bcs=None):
+        c = cases.periodic_box(5, "HLLC", "upwind", seed=5)
+        c.bcs = bcs or {}
+        c.mesh = mt.structured(1, 5, 5, 5, 0, (0, 0, 0), (1.0, 1.2, 0.9))
+        N = c.mesh.n_cells
+        rng = np.random.default_rng(5)
+        c.p, c.T, c.U = 1e5 * (1 + 0.1 * rng.random(N)), 300 * (1 + 0.1 * rng.random(N)), 100 * (rng.random((N, 3)) - 0.3)
+        c.mu, c.Pr = mu, 0.71
+        c.schemes.viscous_full_jacobian = full
+        return c
+
+    mu = 0.3
+    cv, ci = build(mu, 1), build(0.0, 0)
+    ov, oi = cv.apply(Oracle()), ci.apply(Oracle())
+    for o in (ov, oi):
+        o.calc_flux(); o.residual(); o.pseudo_dt(); o.assemble()
+    m = cv.mesh
+    N, F = m.n_cells, m.n_internal_faces
+    own, nei = m.owner[:F], m.neighbour
+    st = ov.state_get()
+    W0 = np.column_stack([st["rho"], st["rhoU"], st["rhoE"]])
+    gam = 1005.0 / (1005.0 - 287.0)
+    alpha = gam * (mu / 0.71)
+    sf2 = m.magSf[:F] * m.deltaCoeffs[:F]
+
+    def lap(W):
+        rho, rU, rE = W[:, 0], W[:, 1:4], W[:, 4]
+        U = rU / rho[:, None]
+        e = rE / rho - 0.5 * (U * U).sum(1)
+        out = np.zeros_like(W)
+        fU, fe = mu * sf2[:, None] * (U[nei] - U[own]), alpha * sf2 * (e[nei] - e[own])
+        np.add.at(out[:, 1:4], own, fU); np.add.at(out[:, 1:4], nei, -fU)
+        np.add.at(out[:, 4], own, fe); np.add.at(out[:, 4], nei, -fe)
+        return out
+
+    rng = np.random.default_rng(7)
+    dW = rng.standard_normal((N, 5)) * W0 * 1e-3
+    eps = 1e-6
+    fd = (lap(W0 + eps * dW) - lap(W0 - eps * dW)) / (2 * eps)
+    x = (dW[:, 0].copy(), dW[:, 1:4].copy(), dW[:, 4].copy())
+    yv, yi = ov.matrix_mul(*x), oi.matrix_mul(*x)
+    A = np.column_stack([yv[0] - yi[0], yv[1] - yi[1], yv[2] - yi[2]])
+    interior = np.ones(N, bool)
+    interior[m.owner[F:]] = False
+    assert np.abs(A[interior, 0]).max() == 0.0
+    assert (np.abs(A[interior, 1:] + fd[interior, 1:]).max(0) <= 1e-6 * np.abs(fd[interior, 1:]).max(0)).all()
+    # wall terms on a no-slip isothermal wall (fixedValue U and T: gradientInternalCoeffs = -deltaCoeffs): against the inviscid
+    # matrix of the same case, the (rhoU, rhoU) and (rhoE, rhoE) diagonals of a wall cell gain the negSumDiag part of the
+    # Laplacian over its internal faces plus muEff deltaCoeffs |Sf| / rho resp. alphaEff deltaCoeffs |Sf| / rho from the wall
+    wall = {"ymin": {"p": ("zeroGradient", ()), "U": ("fixedValue", (0, 0, 0)), "T": ("fixedValue", (310.0,))}}
+    cw, c0 = build(mu, 1, wall), build(0.0, 0, wall)
+    ow, o0 = cw.apply(Oracle()), c0.apply(Oracle())
+    for o in (ow, o0):
+        o.calc_flux(); o.residual(); o.pseudo_dt(); o.assemble()
+    fw = m.patch_faces("ymin")
+    cells = m.owner[fw]
+    rho = ow.state_get()["rho"]
+    lapdiag = np.zeros(N)
+    np.add.at(lapdiag, own, sf2)
+    np.add.at(lapdiag, nei, sf2)
+    gain8 = (ow.matrix_get_ldu(8)[0] - o0.matrix_get_ldu(8)[0])[cells][:, [0, 4, 8]]
+    want8 = mu * (lapdiag[cells] + m.magSf[fw] * m.deltaCoeffs[fw]) / rho[cells]
+    assert np.allclose(gain8, want8[:, None], rtol=1e-10)
+    gain3 = (ow.matrix_get_ldu(3)[0] - o0.matrix_get_ldu(3)[0])[cells][:, 0]
+    want3 = alpha * (lapdiag[cells] + m.magSf[fw] * m.deltaCoeffs[fw]) / rho[cells]     # dT/d(rhoE) = 1/(Cv rho), times alphaEff Cv
+    assert np.allclose(gain3, want3, rtol=1e-10)
