@@ -131,7 +131,8 @@ int icsb200_ami_set(icsb200_ctx* ctx, int patch, int n_faces, const int* face_st
 /* hePsiThermo<pureMixture<constTransport<hConst<perfectGas>>>>, sensibleInternalEnergy (createFields.H:17-35).
  * mu > 0 makes the run viscous (createFields.H:37-45 `inviscid`): icsb200_residual / iterate then add the laminar
  * viscous terms of residualsUpdate.H:16-43 (laplacian(muEff,U), div(tauMC), div(sigmaDotU & Sf), laplacian(alphaEff,e),
- * `Gauss linear corrected`) and icsb200_assemble the Lax-Friedrichs viscous Jacobian (viscousFluxScheme.C:220-246). */
+ * `Gauss linear corrected`) and icsb200_assemble the viscous Jacobian — the Lax-Friedrichs branch (viscousFluxScheme.C:220-246)
+ * or, with icsb200_schemes::viscous_full_jacobian, the full one (:248-261 + addBoundaryTerms :120-215). */
 int icsb200_thermo_set(icsb200_ctx* ctx, double R, double Cp, double mu, double Pr);
 int icsb200_schemes_set(icsb200_ctx* ctx, const icsb200_schemes* s);
 /* fvPatchField of p, U or T on one patch (0/p, 0/U, 0/T boundaryField entries) */
