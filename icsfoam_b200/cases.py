@@ -189,14 +189,17 @@ def periodic_box(n=8, flux="HLLC", limiter="vanLeer", seed=0, nz=None, cyclic=Tr
     return Case("periodic-box", mesh, 287.0, 1005.0, sch, ctl, bcs, p, U, T, mu=mu, Pr=Pr)
 
 
-def rot_box(n=6, flux="HLLC", limiter="vanLeer", seed=0, nz=None, mu=0.0):
+def rot_box(n=6, flux="HLLC", limiter="vanLeer", seed=0, nz=None, mu=0.0, ami_shift=None):
     """A 90-degree sector: the cube [0,1]^2 x [0,0.9] whose faces x=0 and y=0 form a ROTATIONAL cyclic pair about the z axis
     through the corner (four copies tile the plane around it).  forwardT of `xmin` is the rotation by +90 degrees about z
     (it turns the outward normal -y of `ymin` into +x).  Random state: a parity workhorse for
     cyclicFvPatchField::patchNeighbourField with doTransform() — SURVEY 8f-4."""
     mesh = mt.structured(1, n, n, nz or n, 0, (0, 0, 0), (1.0, 1.0, 0.9),
                          patch_kinds=(capi.PATCH, capi.PATCH, capi.PATCH, capi.PATCH, capi.SYMMETRYPLANE, capi.PATCH))
-    mesh.set_cyclic_rotational("xmin", "ymin", [[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    if ami_shift is None:
+        mesh.set_cyclic_rotational("xmin", "ymin", [[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    else:   # non-conformal rotational pair (rotational cyclicAMI): every face sees two rotated neighbour faces
+        mesh.set_cyclic_ami_rotational("xmin", "ymin", [[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]], ami_shift)
     rng = np.random.default_rng(seed)
     N = mesh.n_cells
     p = 1e5 * (1 + 0.2 * rng.random(N))

@@ -65,6 +65,8 @@ struct ProcPatchDev {
 // cyclicAMI patch on the device: halo slots [NP+haloStart, +size) receive sum_k w_k phi[srcPos_k] (CSR over the faces)
 struct AmiPatchDev {
     int size, haloStart;
+    bool rot;        // rotational pair: transform(forwardT, interpolated value) (cyclicAMIFvPatchField.C:171-203)
+    double T[9];
     int* d_start;    // [size+1]
     int* d_srcPos;   // [nnz] positions of the neighbour patch's face cells
     double* d_w;     // [nnz]
@@ -137,6 +139,9 @@ struct icsb200_ctx {
     std::vector<AmiPatchDev> amis;                 // cyclicAMI patches (local weighted gathers into halo slots)
     std::vector<RotPatchDev> rots;                 // rotational cyclic patches (local gathers + rotation of the vector triples)
     int* d_bfNbrPos = nullptr;                     // [NB] rotational cyclic faces: position of the neighbour patch's face cell; else -1
+    int* d_bfAmiStart = nullptr;                   // [NB+1] CSR offsets of the AMI stencil of a boundary face (empty range: not an AMI face)
+    int* d_amiAllSrc = nullptr;                    // concatenated stencil positions / weights of all cyclicAMI patches (viscous terms)
+    double* d_amiAllW = nullptr;
     double* d_patchRot = nullptr;                  // [10*nPatches] (rotational ? 1 : 0, forwardT[9]) per patch (viscous terms)
     std::vector<std::pair<int, AmiTable>> pendingAmi;  // icsb200_ami_set tables waiting for mesh_set
     double *d_sendBuf = nullptr, *d_recvBuf = nullptr;

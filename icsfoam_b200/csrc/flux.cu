@@ -457,6 +457,9 @@ struct ViscArgs {
     double mu, alphaEff;
     const double* tr;  // [2][NX] muEff, alphaEff fields (cells, halo and boundary slots) or null: laminar constants
     const int* bfNbrPos;      // [NB] rotational cyclic faces: position of the neighbour patch's face cell
+    const int* bfAmiStart;    // [NB+1] AMI stencil of a boundary face (empty: not an AMI face), positions and weights
+    const int* amiSrc;
+    const double* amiW;
     const double* patchRot;   // [10*nPatches] (rotational flag, forwardT[9])
     double* out;  // [8*NP]
 };
@@ -522,28 +525,52 @@ k_visc(ViscArgs a)
             const double alP = a.tr ? a.tr[a.NX + P] : a.alphaEff, alN = a.tr ? a.tr[a.NX + N] : a.alphaEff;
             dev2T(gP, muP, tP);
             const double* rot = coupled ? a.patchRot + (size_t)10 * a.bfPatch[b] : nullptr;
-            if (coupled && rot[0] != 0.0) {
-                // rotational cyclic pair: cyclicFvPatchField<tensor>::patchNeighbourField = transform(forwardT, t) = (T & t) & T.T()
-                // (cyclicFvPatchField.C:130-190).  The halo slot holds transform(forwardT, grad(U_j)) per component, i.e. T & gradU;
-                // tauMC is a cell field, so the neighbour CELL's tensor is rotated.
+            const bool isRot = coupled && rot[0] != 0.0;
+            const int amiBeg = coupled ? a.bfAmiStart[b] : 0, amiEnd = coupled ? a.bfAmiStart[b + 1] : 0;
+            if (isRot || amiEnd > amiBeg) {
+                // cyclicFvPatchField / cyclicAMIFvPatchField<tensor>::patchNeighbourField: transform(forwardT, t) = (T & t) & T.T() on
+                // rotational pairs (cyclicFvPatchField.C:130-190).  The halo slot holds transform(forwardT, grad(U_j)) per component,
+                // i.e. T & gradU; tauMC is a cell field, so it is the neighbour CELL's tensor (cyclic) or the AMI interpolation of
+                // the neighbour cells' tensors (result = 0; result += w_k tau_k) that is taken, then rotated.
                 const double* T = rot + 1;
                 double h[9], gRaw[9], tr[9], hr[9];
+                if (isRot) {
 #pragma unroll
-                for (int i = 0; i < 3; i++)
+                    for (int i = 0; i < 3; i++)
 #pragma unroll
-                    for (int j = 0; j < 3; j++) h[3 * i + j] = gN[3 * i] * T[3 * j] + gN[3 * i + 1] * T[3 * j + 1] + gN[3 * i + 2] * T[3 * j + 2];
+                        for (int j = 0; j < 3; j++) h[3 * i + j] = gN[3 * i] * T[3 * j] + gN[3 * i + 1] * T[3 * j + 1] + gN[3 * i + 2] * T[3 * j + 2];
 #pragma unroll
-                for (int k = 0; k < 9; k++) gN[k] = h[k];
-                gradUAt(a, a.bfNbrPos[b], gRaw);
-                dev2T(gRaw, muN, tr);
+                    for (int k = 0; k < 9; k++) gN[k] = h[k];
+                }
+                if (amiEnd > amiBeg) {
 #pragma unroll
-                for (int i = 0; i < 3; i++)
+                    for (int k = 0; k < 9; k++) tr[k] = 0.0;
+                    for (int q = amiBeg; q < amiEnd; q++) {
+                        const int pk = a.amiSrc[q];
+                        double tk[9];
+                        gradUAt(a, pk, gRaw);
+                        dev2T(gRaw, a.tr ? a.tr[pk] : a.mu, tk);
+                        const double wk = a.amiW[q];
 #pragma unroll
-                    for (int l = 0; l < 3; l++) hr[3 * i + l] = T[3 * i] * tr[l] + T[3 * i + 1] * tr[3 + l] + T[3 * i + 2] * tr[6 + l];
+                        for (int k = 0; k < 9; k++) tr[k] += wk * tk[k];
+                    }
+                } else {
+                    gradUAt(a, a.bfNbrPos[b], gRaw);
+                    dev2T(gRaw, muN, tr);
+                }
+                if (!isRot) {
 #pragma unroll
-                for (int i = 0; i < 3; i++)
+                    for (int k = 0; k < 9; k++) tN[k] = tr[k];
+                } else {
 #pragma unroll
-                    for (int j = 0; j < 3; j++) tN[3 * i + j] = hr[3 * i] * T[3 * j] + hr[3 * i + 1] * T[3 * j + 1] + hr[3 * i + 2] * T[3 * j + 2];
+                    for (int i = 0; i < 3; i++)
+#pragma unroll
+                        for (int l = 0; l < 3; l++) hr[3 * i + l] = T[3 * i] * tr[l] + T[3 * i + 1] * tr[3 + l] + T[3 * i + 2] * tr[6 + l];
+#pragma unroll
+                    for (int i = 0; i < 3; i++)
+#pragma unroll
+                        for (int j = 0; j < 3; j++) tN[3 * i + j] = hr[3 * i] * T[3 * j] + hr[3 * i + 1] * T[3 * j + 1] + hr[3 * i + 2] * T[3 * j + 2];
+                }
             } else
                 dev2T(gN, muN, tN);
 #pragma unroll
@@ -722,6 +749,7 @@ int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
         v.mu = c->mu; v.alphaEff = c->gamma * (c->mu / c->Pr);
         v.tr = c->d_transport;
         v.bfNbrPos = c->d_bfNbrPos; v.patchRot = c->d_patchRot;
+        v.bfAmiStart = c->d_bfAmiStart; v.amiSrc = c->d_amiAllSrc; v.amiW = c->d_amiAllW;
         v.out = c->d_visc;
         LaunchScope ls(c, TM_FLUX);
         k_visc<<<gridFor(c->NP, 128), 128, 0, c->stream>>>(v);

@@ -135,7 +135,7 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
                     c->d_bfGeo, c->d_bc, c->d_phiB, c->d_vic, c->d_sendBuf, c->d_recvBuf, c->d_fields, c->d_grad, c->d_rdt, c->d_co,
                     c->d_ddtCoeff, c->d_Wold, c->d_Wold2, c->d_Wprev, c->d_src, c->d_dW, c->d_faceFlux, c->d_bad, c->d_offd, c->d_diag,
                     c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage, c->d_lusgsYZ, c->d_lusgsHint, c->d_sliceRange,
-                    c->d_faceRecon, c->d_gradE, c->d_visc, c->d_mrfFace, c->d_mrfOmega, c->d_transport, c->d_bfNbrPos, c->d_patchRot, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
+                    c->d_faceRecon, c->d_gradE, c->d_visc, c->d_mrfFace, c->d_mrfOmega, c->d_transport, c->d_bfNbrPos, c->d_patchRot, c->d_bfAmiStart, c->d_amiAllSrc, c->d_amiAllW, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
     for (auto& am : c->amis) { cudaFree(am.d_start); cudaFree(am.d_srcPos); cudaFree(am.d_w); }
@@ -285,8 +285,6 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
         }
         // rotational pairs (forwardT != I): plain cyclic only; patchNeighbourField = transform(forwardT, neighbour value)
         // (originalOFFiles/constraintFvPatchFields/cyclic/cyclicFvPatchField.C:130-190) through local halo slots
-        if (p.kind == ICSB200_CYCLICAMI && ics_is_rotational(p))
-            return ics_fail(c, ICSB200_EINVAL, "mesh_set: rotational cyclicAMI patches (forwardT != I) are not supported");
 
         if (p.kind == ICSB200_PROCESSOR && (p.nbr_rank < 0 || p.nbr_rank >= c->nRanks || c->nRanks == 1))
             return ics_fail(c, ICSB200_EINVAL, "mesh_set: processor patch needs a multi-rank context");
@@ -609,6 +607,15 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                     for (int k = t->start[i]; k < t->start[i + 1]; k++) acc += t->weight[k] * ownDelta[3 * (size_t)(qa.start + t->face[k] - F) + d];
                     nbrDelta[3 * (size_t)(pa.start + i - F) + d] = acc;
                 }
+            if (ics_is_rotational(pa))   // ... - transform(forwardT, interpolated neighbour delta)
+                for (int i = 0; i < pa.size; i++) {
+                    double* d3 = &nbrDelta[3 * (size_t)(pa.start + i - F)];
+                    const double* T = pa.forwardT;
+                    const double v0 = d3[0], v1 = d3[1], v2 = d3[2];
+                    d3[0] = T[0] * v0 + T[1] * v1 + T[2] * v2;
+                    d3[1] = T[3] * v0 + T[4] * v1 + T[5] * v2;
+                    d3[2] = T[6] * v0 + T[7] * v1 + T[8] * v2;
+                }
         }
     }
     bool anyProc = false;
@@ -753,13 +760,14 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             if (!ics_is_rotational(patches[pi])) continue;
             prot[(size_t)10 * pi] = 1.0;
             for (int k = 0; k < 9; k++) prot[(size_t)10 * pi + 1 + k] = patches[pi].forwardT[k];
-            for (int i = 0; i < patches[pi].size; i++) nbrPos[patches[pi].start + i - F] = c->cell2pos[owner[patches[patches[pi].nbr_patch].start + i]];
+            if (patches[pi].kind == ICSB200_CYCLIC)
+                for (int i = 0; i < patches[pi].size; i++) nbrPos[patches[pi].start + i - F] = c->cell2pos[owner[patches[patches[pi].nbr_patch].start + i]];
         }
         r |= devUpload(c, &c->d_bfNbrPos, nbrPos);
         r |= devUpload(c, &c->d_patchRot, prot);
     }
     for (int pi = 0; pi < n_patches; pi++) {
-        if (!ics_is_rotational(patches[pi])) continue;
+        if (patches[pi].kind != ICSB200_CYCLIC || !ics_is_rotational(patches[pi])) continue;
         RotPatchDev ro{};
         ro.size = patches[pi].size; ro.haloStart = patchHaloStart[pi]; ro.d_srcPos = nullptr;
         std::memcpy(ro.T, patches[pi].forwardT, sizeof(ro.T));
@@ -776,12 +784,36 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
         for (auto& pe : c->pendingAmi) if (pe.first == pi) t = &pe.second;
         AmiPatchDev am{};
         am.size = patches[pi].size; am.haloStart = patchHaloStart[pi];
+        am.rot = ics_is_rotational(patches[pi]);
+        std::memcpy(am.T, patches[pi].forwardT, sizeof(am.T));
         std::vector<int> sp(t->face.size());
         for (size_t k = 0; k < sp.size(); k++) sp[k] = c->cell2pos[owner[patches[patches[pi].nbr_patch].start + t->face[k]]];
         r |= devUpload(c, &am.d_start, t->start);
         r |= devUpload(c, &am.d_srcPos, sp);
         r |= devUpload(c, &am.d_w, t->weight);
         c->amis.push_back(am);
+    }
+    {
+        // per-boundary-face view of the AMI stencils: tauMC's patchNeighbourField interpolates the neighbour CELLS' tensors (k_visc)
+        std::vector<int> bfStart((size_t)NB + 1, 0), allSrc;
+        std::vector<double> allW;
+        for (int b = 0; b < NB; b++) {
+            const int pi = c->bfacePatch[b];
+            bfStart[b] = (int)allSrc.size();
+            if (pi < 0 || patches[pi].kind != ICSB200_CYCLICAMI) continue;
+            const AmiTable* t = nullptr;
+            for (auto& pe : c->pendingAmi) if (pe.first == pi) t = &pe.second;
+            const int i = F + b - patches[pi].start;
+            for (int k = t->start[i]; k < t->start[i + 1]; k++) {
+                allSrc.push_back(c->cell2pos[owner[patches[patches[pi].nbr_patch].start + t->face[k]]]);
+                allW.push_back(t->weight[k]);
+            }
+        }
+        bfStart[NB] = (int)allSrc.size();
+        if (allSrc.empty()) { allSrc.push_back(0); allW.push_back(0.0); }
+        r |= devUpload(c, &c->d_bfAmiStart, bfStart);
+        r |= devUpload(c, &c->d_amiAllSrc, allSrc);
+        r |= devUpload(c, &c->d_amiAllW, allW);
     }
     if (NH > 0) {
         r |= devAlloc(c, &c->d_sendBuf, (size_t)NH * 40);

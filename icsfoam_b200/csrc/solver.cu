@@ -59,12 +59,35 @@ __global__ void k_ami_gather(int n, int nArrays, int slot0, const int* __restric
     base[(size_t)a * stride + slot0 + i] = acc;
 }
 
-static int amiGather(icsb200_ctx* c, double* base, size_t stride, int nArrays)
+// rotational cyclicAMI: transform(forwardT, interpolated value) of the vector triples, in place on the halo slots
+__global__ void k_rot_inplace(int n, int nArrays, int slot0, double t0, double t1, double t2, double t3, double t4, double t5, double t6, double t7,
+                              double t8, unsigned vecMask, double* __restrict__ base, size_t stride)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int dst = slot0 + i;
+    for (int a = 0; a + 2 < nArrays; a++) {
+        if (!(vecMask >> a & 1u)) continue;
+        const double v0 = base[(size_t)a * stride + dst], v1 = base[(size_t)(a + 1) * stride + dst], v2 = base[(size_t)(a + 2) * stride + dst];
+        base[(size_t)a * stride + dst] = t0 * v0 + t1 * v1 + t2 * v2;
+        base[(size_t)(a + 1) * stride + dst] = t3 * v0 + t4 * v1 + t5 * v2;
+        base[(size_t)(a + 2) * stride + dst] = t6 * v0 + t7 * v1 + t8 * v2;
+        a += 2;
+    }
+}
+
+static int amiGather(icsb200_ctx* c, double* base, size_t stride, int nArrays, unsigned vecMask)
 {
     if (c->amis.empty()) return 0;
     LaunchScope ls(c, TM_HALO);
-    for (auto& am : c->amis)
+    for (auto& am : c->amis) {
         k_ami_gather<<<gridFor((long long)am.size * nArrays, 128), 128, 0, c->stream>>>(am.size, nArrays, c->NP + am.haloStart, am.d_start, am.d_srcPos, am.d_w, base, stride);
+        if (am.rot && vecMask) {
+            k_rot_inplace<<<gridFor(am.size, 128), 128, 0, c->stream>>>(am.size, nArrays, c->NP + am.haloStart, am.T[0], am.T[1], am.T[2], am.T[3], am.T[4],
+                                                                      am.T[5], am.T[6], am.T[7], am.T[8], vecMask, base, stride);
+            c->launches++;
+        }
+    }
     c->launches += (long long)c->amis.size() - 1;
     CUDA_TRY(c, cudaGetLastError());
     return 0;
@@ -110,7 +133,7 @@ int ics_halo_fields(icsb200_ctx* c, double* base, size_t stride, int nArrays, un
 {
     if (c->NH == 0) return 0;
     {
-        int r = amiGather(c, base, stride, nArrays);
+        int r = amiGather(c, base, stride, nArrays, vecMask);
         if (r) return r;
         if ((r = rotGather(c, base, stride, nArrays, vecMask))) return r;
     }

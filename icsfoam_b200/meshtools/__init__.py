@@ -189,6 +189,64 @@ class Mesh:
             self.deltaCoeffs[fa] = 1.0 / md
             self.nonOrthDeltaCoeffs[fa] = 1.0 / np.maximum(np.einsum("ij,ij->i", nfa, d), 0.05 * md)
 
+    def set_cyclic_ami_rotational(self, a, b, T, shift=0.5):
+        """ROTATIONAL cyclicAMI pair: as set_cyclic_ami, but patch `b` coincides with patch `a` only after rotating b's frame by T
+        (forwardT of `a`; forwardT of `b` is T^T).  Neighbour faces are located in the rotated frame; weights / deltas as
+        cyclicAMIFvPatch::makeWeights and delta() = patchD - transform(forwardT, interpolate(nbrPatchD))."""
+        T = np.asarray(T, float).reshape(3, 3)
+        ia, ib = self.patch_index(a), self.patch_index(b)
+        tables = {}
+        for (i0, i1, R) in ((ia, ib, T), (ib, ia, T.T)):
+            pa, pb = self.patches[i0], self.patches[i1]
+            fa = np.arange(pa["start"], pa["start"] + pa["size"])
+            fb = np.arange(pb["start"], pb["start"] + pb["size"])
+            na = np.abs(self.Sf[fa[0]] / self.magSf[fa[0]])
+            axes = [d for d in range(3) if na[d] < 0.5]
+            Xa, Xb = self.Cf[fa], self.Cf[fb] @ R.T          # b's face centres seen from a's side
+            def grid(X):
+                u = np.unique(np.round(X[:, axes[0]], 9)); v = np.unique(np.round(X[:, axes[1]], 9))
+                return len(u), len(v), np.searchsorted(u, np.round(X[:, axes[0]], 9)), np.searchsorted(v, np.round(X[:, axes[1]], 9))
+            nu, nv, iua, iva = grid(Xa)
+            nub, nvb, iub, ivb = grid(Xb)
+            assert (nu, nv) == (nub, nvb) and nu * nv == pa["size"]
+            lookup = -np.ones((nu, nv), np.int64)
+            lookup[iub, ivb] = np.arange(pb["size"])
+            sgn = 1 if i0 == ia else -1
+            start, face, weight = [0], [], []
+            for i in range(pa["size"]):
+                pairs = [(lookup[iua[i], iva[i]], 1.0)] if shift == 0 else [(lookup[iua[i], iva[i]], 1.0 - shift), (lookup[(iua[i] + sgn) % nu, iva[i]], shift)]
+                for j, w in pairs:
+                    face.append(int(j)); weight.append(float(w))
+                start.append(len(face))
+            tables[i0] = (np.array(start, np.int32), np.array(face, np.int32), np.array(weight, np.float64), R)
+        lib = _lib()
+        lib.icsmesh_set_patch_kind(self._h, ia, CYCLICAMI, ib)
+        lib.icsmesh_set_patch_kind(self._h, ib, CYCLICAMI, ia)
+        for i0, i1 in ((ia, ib), (ib, ia)):
+            st, fc, wt, R = tables[i0]
+            self.patches[i0].update(kind=CYCLICAMI, nbr_patch=i1, ami=(st, fc, wt), forwardT=[float(v) for v in R.reshape(-1)])
+        for (i0, i1) in ((ia, ib), (ib, ia)):
+            pa, pb = self.patches[i0], self.patches[i1]
+            start, face, weight = pa["ami"]
+            R = np.array(pa["forwardT"]).reshape(3, 3)
+            fa = np.arange(pa["start"], pa["start"] + pa["size"])
+            fb = pb["start"] + face
+            nfa = self.Sf[fa] / self.magSf[fa, None]
+            da = np.einsum("ij,ij->i", nfa, self.Cf[fa] - self.C[self.owner[fa]])
+            nfb = self.Sf[fb] / self.magSf[fb, None]
+            dbj = np.einsum("ij,ij->i", nfb, self.Cf[fb] - self.C[self.owner[fb]])
+            deltab = self.Cf[fb] - self.C[self.owner[fb]]
+            dn = np.zeros(pa["size"]); dvec = np.zeros((pa["size"], 3))
+            for i in range(pa["size"]):
+                for k in range(start[i], start[i + 1]):
+                    dn[i] += weight[k] * dbj[k]
+                    dvec[i] += weight[k] * deltab[k]
+            self.weights[fa] = dn / (da + dn)
+            d = (self.Cf[fa] - self.C[self.owner[fa]]) - dvec @ R.T
+            md = np.linalg.norm(d, axis=1)
+            self.deltaCoeffs[fa] = 1.0 / md
+            self.nonOrthDeltaCoeffs[fa] = 1.0 / np.maximum(np.einsum("ij,ij->i", nfa, d), 0.05 * md)
+
     def renumber(self, perm):
         """renumberMesh stand-in: new cell id = perm[old id]; faces re-sorted into upper-triangular order."""
         perm = np.ascontiguousarray(perm, np.int32)

@@ -40,7 +40,8 @@ typedef struct {
     int nbr_patch;      /* CYCLIC: index of the neighbour patch */
     double forwardT[9]; /* CYCLIC: cyclicPolyPatch::forwardT() row-major — patchNeighbourField = transform(forwardT, neighbour
                          * value) (cyclicFvPatchField.C:130-190): identity = translational pair; a rotation = rotational pair
-                         * (tensors grad(U), tauMC of the viscous terms: transform(forwardT, t)); rotational CYCLICAMI: EINVAL */
+                         * (tensors grad(U), tauMC of the viscous terms: transform(forwardT, t)); CYCLICAMI: applied after the
+                         * interpolation (cyclicAMIFvPatchField.C:171-203) */
 } icsb200_patch;
 
 /* run-time selectors — same words as the reference dictionaries */
@@ -123,7 +124,7 @@ int icsb200_mesh_set(icsb200_ctx* ctx, int n_cells, int n_internal_faces, int n_
 /* cyclicAMI interpolation of patch `patch` (kind ICSB200_CYCLICAMI, neighbour = nbr_patch): for face i of the patch,
  * patchNeighbourField[i] = sum_{k in [face_start[i], face_start[i+1])} weight[k] * phi[faceCells(nbr_patch)[nbr_face[k]]]
  * in this order (AMIInterpolation::interpolateToSource/Target with plusEqOp; originalOFFiles/constraintFvPatchFields/
- * cyclicAMI/cyclicAMIFvPatchField.C:146-209, no lowWeightCorrection, translational: forwardT must be I).  The addressing
+ * cyclicAMI/cyclicAMIFvPatchField.C:146-209, no lowWeightCorrection; a rotational pair then applies transform(forwardT, .)).  The addressing
  * and weights are OpenFOAM's (cyclicAMIPolyPatch::AMI().srcAddress()/srcWeights()); the mesh arrays weights /
  * deltaCoeffs / nonOrthDeltaCoeffs of the patch faces are cyclicAMIFvPatch's.  Call BEFORE icsb200_mesh_set, once per
  * cyclicAMI patch; both patches of a pair live on the same rank. */

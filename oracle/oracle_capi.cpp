@@ -113,7 +113,6 @@ int orc_mesh_set(Ctx* c, int n_cells, int n_internal_faces, int n_faces, const i
         if (p.kind == ICSB200_CYCLIC || p.kind == ICSB200_CYCLICAMI)
             for (int k = 0; k < 9; k++)
                 if (std::fabs(p.forwardT[k] - (k % 4 == 0 ? 1.0 : 0.0)) > 1e-12) p.rotational = true;
-        if (p.rotational && p.kind == ICSB200_CYCLICAMI) return fail(c, ICSB200_EINVAL, "rotational cyclicAMI patches (forwardT != I) are not supported");
         m.patches.push_back(p);
     }
     for (int d = 0; d < 3; d++) m.solutionD[d] = solutionD[d];

@@ -55,12 +55,21 @@ void meshFinalize(Ctx& c)
         } else if (p.kind == ICSB200_CYCLICAMI) {
             // cyclicAMIFvPatch::delta: patchD - interpolate(nbrPatch.coupledFvPatch::delta())
             auto& q = m.patches[p.nbrPatch];
-            for (int i = 0; i < p.size; i++)
+            for (int i = 0; i < p.size; i++) {
+                double* d3 = &nbr[3 * (size_t)(p.start + i - m.F)];
                 for (int d = 0; d < 3; d++) {
                     double acc = 0.0;
                     for (int k = p.amiStart[i]; k < p.amiStart[i + 1]; k++) acc += p.amiWeight[k] * own[3 * (q.start + p.amiFace[k] - m.F) + d];
-                    nbr[3 * (p.start + i - m.F) + d] = acc;
+                    d3[d] = acc;
                 }
+                if (p.rotational) {   // ... - transform(forwardT, interpolated neighbour delta)
+                    const double* T = p.forwardT;
+                    const double v0 = d3[0], v1 = d3[1], v2 = d3[2];
+                    d3[0] = T[0] * v0 + T[1] * v1 + T[2] * v2;
+                    d3[1] = T[3] * v0 + T[4] * v1 + T[5] * v2;
+                    d3[2] = T[6] * v0 + T[7] * v1 + T[8] * v2;
+                }
+            }
         }
     }
     for (auto& p : m.patches)
@@ -102,11 +111,21 @@ void syncCoupled(Ctx& c, vecd& vf, int nc)
             // cyclicAMIFvPatchField::patchNeighbourField = AMI.interpolate(neighbour cell values): result = 0; result += w*phi
             auto& q = m.patches[p.nbrPatch];
             for (int i = 0; i < p.size; i++)
+            {
+                double* dst = &vf[(size_t)nc * (m.N + p.start - m.F + i)];
                 for (int d = 0; d < nc; d++) {
                     double acc = 0.0;
                     for (int k = p.amiStart[i]; k < p.amiStart[i + 1]; k++) acc += p.amiWeight[k] * vf[(size_t)nc * m.owner[q.start + p.amiFace[k]] + d];
-                    vf[(size_t)nc * (m.N + p.start - m.F + i) + d] = acc;
+                    dst[d] = acc;
                 }
+                if (p.rotational && nc == 3) {   // cyclicAMIFvPatchField.C:171-203: transform(forwardT, interpolated value)
+                    const double* T = p.forwardT;
+                    const double v0 = dst[0], v1 = dst[1], v2 = dst[2];
+                    dst[0] = T[0] * v0 + T[1] * v1 + T[2] * v2;
+                    dst[1] = T[3] * v0 + T[4] * v1 + T[5] * v2;
+                    dst[2] = T[6] * v0 + T[7] * v1 + T[8] * v2;
+                }
+            }
         } else if (p.kind == ICSB200_PROCESSOR) {
             vecd send((size_t)nc * p.size), recv((size_t)nc * p.size);
             for (int i = 0; i < p.size; i++)

@@ -436,7 +436,9 @@ void viscousResidual(Ctx& c, vecd& rhoUR, vecd& rhoER)
     // rot != nullptr: face of a rotational cyclic patch; nbCell = the neighbour patch's face cell.  The boundary slot Ns then
     // holds transform(forwardT, grad(U_j)) per component, i.e. (T & gradU); cyclicFvPatchField<tensor>::patchNeighbourField
     // of grad(U) and of tauMC is transform(forwardT, tensor) = (T & t) & T.T() (originalOFFiles/.../cyclicFvPatchField.C:130-190)
-    auto faceCoupledOrInternal = [&](int f, int P, size_t Ns, const double* dvec, bool coupled, const double* rot, int nbCell) {
+    // ami != nullptr: face i of a cyclicAMI patch — tauMC is a cell field, so its patchNeighbourField is the AMI interpolation
+    // of the neighbour cells' tensors (result = 0; result += w_k tau_k), not the tensor of the interpolated gradient
+    auto faceCoupledOrInternal = [&](int f, int P, size_t Ns, const double* dvec, bool coupled, const double* rot, int nbCell, const Patch* ami) {
         const double w = m.w[f], magSf = m.magSf[f], dcn = m.nonOrthDeltaCoeffs[f];
         double nf[3], corr[3];
         for (int d = 0; d < 3; d++) nf[d] = m.Sf[3 * f + d] / magSf;
@@ -445,18 +447,36 @@ void viscousResidual(Ctx& c, vecd& rhoUR, vecd& rhoER)
         double gP[9], gN[9], gf[9], tP[9], tN[9], tf[9];
         gradUOf(P, gP); gradUOf(Ns, gN);
         dev2T(gP, muV[P], tP);
-        if (rot) {
+        if (rot || ami) {
             double h[9], tr[9], hr[9];
-            for (int i = 0; i < 3; i++)           // (T & gradU) & T.T(): the slot already holds the left product
-                for (int j = 0; j < 3; j++) h[3 * i + j] = gN[3 * i] * rot[3 * j] + gN[3 * i + 1] * rot[3 * j + 1] + gN[3 * i + 2] * rot[3 * j + 2];
-            for (int k = 0; k < 9; k++) gN[k] = h[k];
+            if (rot) {
+                for (int i = 0; i < 3; i++)           // (T & gradU) & T.T(): the slot already holds the left product
+                    for (int j = 0; j < 3; j++) h[3 * i + j] = gN[3 * i] * rot[3 * j] + gN[3 * i + 1] * rot[3 * j + 1] + gN[3 * i + 2] * rot[3 * j + 2];
+                for (int k = 0; k < 9; k++) gN[k] = h[k];
+            }
             double gRaw[9];
-            gradUOf((size_t)nbCell, gRaw);         // tauMC is a cell field: rotate the neighbour CELL's tensor
-            dev2T(gRaw, muV[Ns], tr);
+            if (ami) {
+                const Patch& q = m.patches[ami->nbrPatch];
+                const int i = f - ami->start;
+                for (int k = 0; k < 9; k++) tr[k] = 0.0;
+                for (int a = ami->amiStart[i]; a < ami->amiStart[i + 1]; a++) {
+                    const int cellK = m.owner[q.start + ami->amiFace[a]];
+                    double tk[9];
+                    gradUOf((size_t)cellK, gRaw);
+                    dev2T(gRaw, muV[cellK], tk);
+                    for (int k = 0; k < 9; k++) tr[k] += ami->amiWeight[a] * tk[k];
+                }
+            } else {
+                gradUOf((size_t)nbCell, gRaw);         // tauMC is a cell field: rotate the neighbour CELL's tensor
+                dev2T(gRaw, muV[Ns], tr);
+            }
+            if (!rot) { for (int k = 0; k < 9; k++) tN[k] = tr[k]; }
+            else {
             for (int i = 0; i < 3; i++)
                 for (int l = 0; l < 3; l++) hr[3 * i + l] = rot[3 * i] * tr[l] + rot[3 * i + 1] * tr[3 + l] + rot[3 * i + 2] * tr[6 + l];
             for (int i = 0; i < 3; i++)
                 for (int j = 0; j < 3; j++) tN[3 * i + j] = hr[3 * i] * rot[3 * j] + hr[3 * i + 1] * rot[3 * j + 1] + hr[3 * i + 2] * rot[3 * j + 2];
+            }
         } else
             dev2T(gN, muV[Ns], tN);
         for (int k = 0; k < 9; k++) { gf[k] = lin(gP[k], gN[k]); tf[k] = lin(tP[k], tN[k]); }
@@ -483,7 +503,7 @@ void viscousResidual(Ctx& c, vecd& rhoUR, vecd& rhoER)
     for (int f = 0; f < m.F; f++) {
         const int P = m.owner[f], N = m.neighbour[f];
         const double dvec[3] = {m.C[3 * (size_t)N] - m.C[3 * (size_t)P], m.C[3 * (size_t)N + 1] - m.C[3 * (size_t)P + 1], m.C[3 * (size_t)N + 2] - m.C[3 * (size_t)P + 2]};
-        faceCoupledOrInternal(f, P, (size_t)N, dvec, false, nullptr, -1);
+        faceCoupledOrInternal(f, P, (size_t)N, dvec, false, nullptr, -1, nullptr);
     }
     for (size_t pi = 0; pi < m.patches.size(); pi++) {
         const Patch& p = m.patches[pi];
@@ -493,9 +513,10 @@ void viscousResidual(Ctx& c, vecd& rhoUR, vecd& rhoER)
             const int b = f - m.F, P = m.owner[f];
             const size_t s = (size_t)m.N + b;
             if (m.coupled(p)) {
-                const bool rot = p.kind == ICSB200_CYCLIC && p.rotational;
+                const bool rot = p.rotational && (p.kind == ICSB200_CYCLIC || p.kind == ICSB200_CYCLICAMI);
+                const bool isAmi = p.kind == ICSB200_CYCLICAMI;
                 faceCoupledOrInternal(f, P, s, &m.dCoupled[3 * (size_t)b], true, rot ? p.forwardT : nullptr,
-                                      rot ? m.owner[m.patches[p.nbrPatch].start + (f - p.start)] : -1);
+                                      (rot && !isAmi) ? m.owner[m.patches[p.nbrPatch].start + (f - p.start)] : -1, isAmi ? &p : nullptr);
                 continue;
             }
             const double magSf = m.magSf[f];

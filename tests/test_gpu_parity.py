@@ -86,6 +86,8 @@ LIVE = {
     "rot-roe-minmod": lambda: cases.rot_box(5, "ROE", "Minmod", seed=63, nz=4),
     "rot-ausm-mrf": lambda: cases.rot_box(5, "AUSMPlusUp", "vanLeer", seed=64).with_mrf((0.0, 0.0, 60.0)),
     "rot-viscous-hllc": lambda: cases.rot_box(5, "HLLC", "Minmod", seed=66, mu=0.1),
+    "rot-ami-roe": lambda: cases.rot_box(6, "ROE", "vanLeer", seed=68, ami_shift=0.5),
+    "rot-ami-viscous-full": lambda: FULLV(cases.rot_box(5, "HLLC", "Minmod", seed=69, mu=0.1, ami_shift=0.3)),
     # LaxFriedrichJacobian false: full viscous Jacobian (five fvj::laplacian blocks + wall terms) on cyclic / wall / symmetry /
     # mixed patches, AMI and rotational pairs (values stored on coupled patches), non-orthogonal bump, muEff field, scrambled
     "fullvisc-box-roe": lambda: FULLV(cases.periodic_box(6, "ROE", "vanLeer", seed=101, mu=0.05)),
@@ -418,8 +420,8 @@ def test_forward_step_c2_polyhedral_mesh(gpu_context):
 
 def test_rotational_cyclic_bitwise_and_refusals(gpu_context):
     """Rotational cyclic pairs on the device (local halo slots filled by k_rot_gather: vector triples rotated by forwardT,
-    scalars copied): every reduction-free stage bit for bit against the oracle, incl. the viscous terms; rotational cyclicAMI is
-    refused by both."""
+    scalars copied): every reduction-free stage bit for bit against the oracle, incl. the viscous terms; rotational
+    cyclicAMI likewise."""
     case = cases.rot_box(6, "HLLC", "vanLeer", seed=61)
     o, g = case.apply(Oracle()), case.apply(gpu_context())
     bo, bg = o.boundary_get(), g.boundary_get()
@@ -456,12 +458,19 @@ def test_rotational_cyclic_bitwise_and_refusals(gpu_context):
     gs.calc_flux(); gf.calc_flux()
     for a, b in zip(gs.residual(), gf.residual()):
         assert np.abs(a[scells] - b[fcells]).max() <= 1e-12 * np.abs(a).max()
-    ami = cases.periodic_box(4, ami_shift=0.5)
-    for p in ami.mesh.patches:
-        if p["kind"] == capi.CYCLICAMI:
-            p["forwardT"] = [0, -1, 0, 1, 0, 0, 0, 0, 1]
-    with pytest.raises(capi.ApiError):
-        ami.apply(gpu_context())
+    # rotational cyclicAMI: interpolate, then rotate; viscous terms interpolate the neighbour cells' tauMC tensors
+    ami = cases.rot_box(5, "HLLC", "vanLeer", seed=67, mu=0.1, ami_shift=0.3).with_transport(TURB)
+    oa, ga = ami.apply(Oracle()), ami.apply(gpu_context())
+    for a, b in zip(ga.calc_flux(), oa.calc_flux()):
+        assert np.array_equal(a, b)
+    for a, b in zip(ga.residual(), oa.residual()):
+        assert np.array_equal(a, b)
+    ga.pseudo_dt(); oa.pseudo_dt(); ga.assemble(); oa.assemble()
+    for blk in range(9):
+        for a, b in zip(ga.matrix_get_ldu(blk), oa.matrix_get_ldu(blk)):
+            assert np.array_equal(a, b), blk
+    for a, b in zip(ga.matrix_mul(*x), oa.matrix_mul(*x)) if ami.mesh.n_cells == N else []:
+        assert np.array_equal(a, b)
 
 
 LOCAL_VKI = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cases_local", "VKI-LS89", "constant", "polyMesh")
