@@ -149,6 +149,7 @@ PRODUCT_SIGNATURES = {
     "timer_begin": (C.c_int, [C.c_void_p]),
     "timer_end": (C.c_int, [C.c_void_p, _dp]),
     "hb_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _ip, _ip, _dp, _dp]),
+    "phaselag_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp]),
     "hb_residuals_get": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp]),
 }
 

@@ -338,6 +338,23 @@ class HBCase:
         self.p = np.concatenate([c.p for c in instances])
         self.U = np.concatenate([c.U for c in instances])
         self.T = np.concatenate([c.T for c in instances])
+        self.omegas = None        # omega list of the (single) HB zone, needed for phase-lag patches
+        self.phase_lag = []       # [(owner patch, neighbour patch, IBPA)]: phaseLagCyclic pairs (cyclic pairs of the base mesh)
+
+    def with_phase_lag(self, owner_patch, neighbour_patch, ibpa, omegas):
+        """Make the cyclic pair (owner_patch, neighbour_patch) a phaseLagCyclic pair with inter-blade phase angle `ibpa`."""
+        self.omegas = np.asarray(omegas, float)
+        self.phase_lag.append((owner_patch, neighbour_patch, float(ibpa)))
+        return self
+
+    def phase_lag_operators(self):
+        """[(patch index in the base mesh, D_pl)] for both sides of every pair (owner +IBPA, neighbour -IBPA)."""
+        from . import hb
+        out = []
+        for a, b, ibpa in self.phase_lag:
+            out.append((self.base.mesh.patch_index(a), hb.phase_lag_operator(self.snapshots, self.omegas, ibpa)))
+            out.append((self.base.mesh.patch_index(b), hb.phase_lag_operator(self.snapshots, self.omegas, -ibpa)))
+        return out
 
     def partition(self, n_parts, mode="x"):
         """One HBCase per rank: every instance case restricted to the same spatial decomposition (HB instants are not sharded
@@ -355,6 +372,10 @@ class HBCase:
 
     def apply(self, api):
         b = self.base
+        np0 = len(b.mesh.patches)
+        for patch, Dpl in self.phase_lag_operators():     # before mesh_set: phase-lag pairs need local halo slots
+            for K in range(self.n_instants):
+                api.phaselag_set(K * np0 + patch, Dpl[K])
         api.mesh_set(self.mesh)
         api.thermo_set(b.R, b.Cp, b.mu, b.Pr)
         api.schemes_set(self.schemes)

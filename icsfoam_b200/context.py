@@ -96,6 +96,11 @@ class Context(capi.Api):
         self._call("hb_set", int(n_instants), int(nz), capi.dptr(D), capi.iptr(zoc), capi.iptr(cyl), capi.dptr(ax), capi.dptr(ce))
         self.n_instants = int(n_instants)
 
+    def phaselag_set(self, patch, weights):
+        """phaseLagCyclic: row of D_pl for replicated patch `patch` (icsb200_phaselag_set; call before mesh_set)"""
+        w = np.ascontiguousarray(weights, np.float64)
+        self._call("phaselag_set", int(patch), int(w.size), capi.dptr(w))
+
     def hb_residuals(self):
         n = self.n_instants
         out = {"s_init": np.zeros(2 * n), "v_init": np.zeros(3 * n), "s_final": np.zeros(2 * n), "v_final": np.zeros(3 * n)}

@@ -73,10 +73,17 @@ struct AmiPatchDev {
 };
 // rotational cyclic patch on the device: halo slots [NP+haloStart, +size) receive transform(forwardT, phi[srcPos_i]) —
 // vector triples rotated, scalars copied (cyclicFvPatchField::patchNeighbourField with doTransform())
+struct LagWeights { double w[16]; };
 struct RotPatchDev {
     int size, haloStart;
     int* d_srcPos;   // [size] positions of the neighbour patch's face cells
     double T[9];     // forwardT, row-major
+    bool rotate;     // forwardT != I
+    // phase lag (icsb200_phaselag_set): the listed fields take sum_J lagW[J] * value at d_lagSrc[J*size + i] (instance J's copy
+    // of the neighbour cell); nLag = 0: plain cyclic
+    int nLag;
+    int* d_lagSrc;
+    LagWeights lagW;
 };
 struct AmiTable { std::vector<int> start, face; std::vector<double> weight; };
 
@@ -144,6 +151,7 @@ struct icsb200_ctx {
     double* d_amiAllW = nullptr;
     double* d_patchRot = nullptr;                  // [10*nPatches] (rotational ? 1 : 0, forwardT[9]) per patch (viscous terms)
     std::vector<std::pair<int, AmiTable>> pendingAmi;  // icsb200_ami_set tables waiting for mesh_set
+    std::vector<std::pair<int, std::vector<double>>> pendingLag;  // icsb200_phaselag_set rows waiting for mesh_set
     double *d_sendBuf = nullptr, *d_recvBuf = nullptr;
 
     // ---- thermo / schemes ----
@@ -281,7 +289,8 @@ int ics_download_cells(icsb200_ctx* c, double* host, int nc, const double* src, 
 int ics_eval_bc(icsb200_ctx* c, bool init);
 int ics_primitives(icsb200_ctx* c);  // derived fields from p,T,U,rho (cells + boundary slots)
 // vecMask: bit a set = arrays a, a+1, a+2 are the components of a vector (rotated on rotational cyclic patches)
-int ics_halo_fields(icsb200_ctx* c, double* base, size_t stride, int nArrays, unsigned vecMask = 0u);
+// lagMask: bit a set = array a is one of the fields phase-lag patches mix over the time instances (rho p U cR E H c)
+int ics_halo_fields(icsb200_ctx* c, double* base, size_t stride, int nArrays, unsigned vecMask = 0u, unsigned lagMask = 0u);
 inline bool ics_is_rotational(const icsb200_patch& p)
 {
     if (p.kind != ICSB200_CYCLIC && p.kind != ICSB200_CYCLICAMI) return false;

@@ -345,7 +345,8 @@ int ics_primitives(icsb200_ctx* c)
     CUDA_TRY(c, cudaGetLastError());
     // neighbour-rank copies of the arrays the face kernels gather: rho p Ux Uy Uz cR E H c (+ eCalc) (contiguous ids 0..9)
     // + T (id 10) for the stored coupled-patch values of the full viscous Jacobian
-    return ics_halo_fields(c, c->d_fields, c->NX, c->mu > 0 ? (c->sch.viscous_full_jacobian ? 11 : 10) : 9, 1u << Q_UX);
+    // phase-lag patches mix the time instances for rho p U cR E H c (ids 0..8), not for eCalc / T
+    return ics_halo_fields(c, c->d_fields, c->NX, c->mu > 0 ? (c->sch.viscous_full_jacobian ? 11 : 10) : 9, 1u << Q_UX, 0x1FFu);
 }
 
 // conserved variables + boundary + derived fields from freshly uploaded p, U, T (host-facing iterate)

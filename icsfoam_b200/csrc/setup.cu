@@ -139,7 +139,7 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
     for (auto& am : c->amis) { cudaFree(am.d_start); cudaFree(am.d_srcPos); cudaFree(am.d_w); }
-    for (auto& ro : c->rots) cudaFree(ro.d_srcPos);
+    for (auto& ro : c->rots) { cudaFree(ro.d_srcPos); if (ro.d_lagSrc) cudaFree(ro.d_lagSrc); }
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaEventDestroy(c->ev0);
@@ -253,6 +253,15 @@ extern "C" int icsb200_ami_set(icsb200_ctx* c, int patch, int n_faces, const int
     return 0;
 }
 
+extern "C" int icsb200_phaselag_set(icsb200_ctx* c, int patch, int n_instants, const double* weights)
+{
+    if (patch < 0 || n_instants < 2 || n_instants > 16 || !weights) return ics_fail(c, ICSB200_EINVAL, "phaselag_set: bad arguments");
+    std::vector<double> w(weights, weights + n_instants);
+    for (auto& pe : c->pendingLag) if (pe.first == patch) { pe.second = w; return 0; }
+    c->pendingLag.emplace_back(patch, w);
+    return 0;
+}
+
 extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int* owner, const int* neighbour, const double* Sf,
                                 const double* magSf, const double* weights, const double* deltaCoeffs, const double* nonOrthDeltaCoeffs,
                                 const double* C, const double* V, const double* Cf, int n_patches, const icsb200_patch* patches,
@@ -270,6 +279,16 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     for (int d = 0; d < 3; d++) c->solutionD[d] = solutionD[d];
     const int NB = c->NB;
     c->bfacePatch.assign(NB, -1);
+    auto lagOf = [&](int pi) -> const std::vector<double>* {
+        for (auto& pe : c->pendingLag) if (pe.first == pi) return &pe.second;
+        return nullptr;
+    };
+    // cyclic patches whose neighbour values are not a plain copy live in local halo slots: rotational pairs and phase-lag pairs
+    auto localHalo = [&](int pi) { return patches[pi].kind == ICSB200_CYCLIC && (ics_is_rotational(patches[pi]) || lagOf(pi)); };
+    for (auto& pe : c->pendingLag) {
+        if (pe.first >= n_patches || patches[pe.first].kind != ICSB200_CYCLIC) return ics_fail(c, ICSB200_EINVAL, "mesh_set: phaselag_set on a patch that is not cyclic");
+        if (N % (int)pe.second.size()) return ics_fail(c, ICSB200_EINVAL, "mesh_set: phase-lag patch on a mesh that is not made of n_instants copies");
+    }
     for (int pi = 0; pi < n_patches; pi++) {
         const icsb200_patch& p = patches[pi];
         if (p.start < F || p.start + p.size > FT) return ics_fail(c, ICSB200_EINVAL, "mesh_set: patch range outside boundary faces");
@@ -433,7 +452,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     int NH = 0;
     std::vector<int> patchHaloStart(n_patches, -1);
     for (int pi = 0; pi < n_patches; pi++)
-        if (patches[pi].kind == ICSB200_PROCESSOR || patches[pi].kind == ICSB200_CYCLICAMI || ics_is_rotational(patches[pi])) { patchHaloStart[pi] = NH; NH += patches[pi].size; }
+        if (patches[pi].kind == ICSB200_PROCESSOR || patches[pi].kind == ICSB200_CYCLICAMI || localHalo(pi)) { patchHaloStart[pi] = NH; NH += patches[pi].size; }
     NH += NH & 1;  // keep NPH even: every component array of a cell vector then starts 16-byte aligned (TMA bulk copies)
     c->NH = NH; c->NPH = NP + NH; c->NX = NP + NH + NB;
 
@@ -479,11 +498,11 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             int f = F + b, o = owner[f], po = c->cell2pos[o];
             size_t sb = slot(po, nLowC[o] + nUpC[o] + fillB[o]++);
             const icsb200_patch& pa = patches[pi];
-            if (pa.kind == ICSB200_CYCLIC && !ics_is_rotational(pa)) {
+            if (pa.kind == ICSB200_CYCLIC && !localHalo(pi)) {
                 int nbrFace = patches[pa.nbr_patch].start + (f - pa.start);
                 c->h_col[sb] = c->cell2pos[owner[nbrFace]];
                 c->h_meta[sb] = ET_COUPLED | (f << 2);
-            } else if (pa.kind == ICSB200_CYCLIC) {   // rotational: the transformed neighbour values live in a local halo slot
+            } else if (pa.kind == ICSB200_CYCLIC) {   // rotational / phase lag: the neighbour values live in a local halo slot
                 c->h_col[sb] = NP + patchHaloStart[pi] + (f - pa.start);
                 c->h_meta[sb] = ET_COUPLED | (f << 2);
             } else if (pa.kind == ICSB200_PROCESSOR || pa.kind == ICSB200_CYCLICAMI) {
@@ -750,7 +769,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
         r |= devUpload(c, &pp.d_sendPos, sp);
         c->procs.push_back(pp);
     }
-    for (auto& ro : c->rots) cudaFree(ro.d_srcPos);
+    for (auto& ro : c->rots) { cudaFree(ro.d_srcPos); if (ro.d_lagSrc) cudaFree(ro.d_lagSrc); }
     c->rots.clear();
     {
         // viscous terms across a rotational pair need the neighbour CELL (tauMC is rotated as a cell tensor) and forwardT
@@ -767,13 +786,24 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
         r |= devUpload(c, &c->d_patchRot, prot);
     }
     for (int pi = 0; pi < n_patches; pi++) {
-        if (patches[pi].kind != ICSB200_CYCLIC || !ics_is_rotational(patches[pi])) continue;
+        if (!localHalo(pi)) continue;
         RotPatchDev ro{};
-        ro.size = patches[pi].size; ro.haloStart = patchHaloStart[pi]; ro.d_srcPos = nullptr;
+        ro.size = patches[pi].size; ro.haloStart = patchHaloStart[pi]; ro.d_srcPos = nullptr; ro.d_lagSrc = nullptr; ro.nLag = 0;
+        ro.rotate = ics_is_rotational(patches[pi]);
         std::memcpy(ro.T, patches[pi].forwardT, sizeof(ro.T));
         std::vector<int> sp(ro.size);
         for (int i = 0; i < ro.size; i++) sp[i] = c->cell2pos[owner[patches[patches[pi].nbr_patch].start + i]];
         r |= devUpload(c, &ro.d_srcPos, sp);
+        if (const std::vector<double>* lw = lagOf(pi)) {
+            // instance J's copy of the neighbour cell: the mesh is n_instants copies of NC cells, instance-major (icsb200_hb_set)
+            ro.nLag = (int)lw->size();
+            const int NC = N / ro.nLag;
+            for (int J = 0; J < ro.nLag; J++) ro.lagW.w[J] = (*lw)[J];
+            std::vector<int> ls((size_t)ro.nLag * ro.size);
+            for (int J = 0; J < ro.nLag; J++)
+                for (int i = 0; i < ro.size; i++) ls[(size_t)J * ro.size + i] = c->cell2pos[J * NC + owner[patches[patches[pi].nbr_patch].start + i] % NC];
+            r |= devUpload(c, &ro.d_lagSrc, ls);
+        }
         c->rots.push_back(ro);
     }
     for (auto& am : c->amis) { cudaFree(am.d_start); cudaFree(am.d_srcPos); cudaFree(am.d_w); }
@@ -871,6 +901,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     c->stateSet = c->matrixSet = c->fluxValid = false;
     c->reconValid = false;
     c->hbNO = 1;  // a new mesh drops the Harmonic Balance setup (icsb200_hb_set must follow mesh_set)
+    c->pendingLag.clear();               // consumed: a later mesh needs its own icsb200_phaselag_set calls
     r |= devAlloc(c, &c->d_mrfFace, 0);  // ... and the MRF fields (icsb200_mrf_set must follow mesh_set)
     r |= devAlloc(c, &c->d_mrfOmega, 0);
     r |= devAlloc(c, &c->d_transport, 0);

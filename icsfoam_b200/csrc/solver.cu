@@ -97,45 +97,55 @@ static int amiGather(icsb200_ctx* c, double* base, size_t stride, int nArrays, u
 // cyclicFvPatchField.C:130-190): halo slot = transform(forwardT, neighbour cell value) — the arrays flagged in vecMask are
 // the x components of vector triples (U, gradients, the rhoU part of a solver vector) and are rotated, scalars are copied.
 // The reference's scalar fields "U.component(i)" take component i of the rotated cell velocity: the same numbers.
+// Phase-lag pairs (phaseLagCyclicFvPatchField.C:160-398): the arrays flagged in lagMask take sum_J w_J * (value of time instance J at
+// the neighbour cell), J ascending from zero, before the rotation; the others the plain neighbour value.
 __global__ void k_rot_gather(int n, int nArrays, int slot0, const int* __restrict__ srcPos, double t0, double t1, double t2, double t3, double t4,
-                             double t5, double t6, double t7, double t8, unsigned vecMask, double* __restrict__ base, size_t stride)
+                             double t5, double t6, double t7, double t8, unsigned vecMask, unsigned lagMask, int nLag, const int* __restrict__ lagSrc,
+                             LagWeights lw, double* __restrict__ base, size_t stride)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int src = srcPos[i], dst = slot0 + i;
+    auto fetch = [&](int a) {
+        if (nLag == 0 || !(lagMask >> a & 1u)) return base[(size_t)a * stride + src];
+        double acc = 0.0;
+        for (int J = 0; J < nLag; J++) acc += lw.w[J] * base[(size_t)a * stride + lagSrc[(size_t)J * n + i]];
+        return acc;
+    };
     for (int a = 0; a < nArrays;) {
         if (a + 2 < nArrays && (vecMask >> a & 1u)) {
-            const double v0 = base[(size_t)a * stride + src], v1 = base[(size_t)(a + 1) * stride + src], v2 = base[(size_t)(a + 2) * stride + src];
+            const double v0 = fetch(a), v1 = fetch(a + 1), v2 = fetch(a + 2);
             base[(size_t)a * stride + dst] = t0 * v0 + t1 * v1 + t2 * v2;
             base[(size_t)(a + 1) * stride + dst] = t3 * v0 + t4 * v1 + t5 * v2;
             base[(size_t)(a + 2) * stride + dst] = t6 * v0 + t7 * v1 + t8 * v2;
             a += 3;
         } else {
-            base[(size_t)a * stride + dst] = base[(size_t)a * stride + src];
+            base[(size_t)a * stride + dst] = fetch(a);
             a += 1;
         }
     }
 }
 
-static int rotGather(icsb200_ctx* c, double* base, size_t stride, int nArrays, unsigned vecMask)
+static int rotGather(icsb200_ctx* c, double* base, size_t stride, int nArrays, unsigned vecMask, unsigned lagMask)
 {
     if (c->rots.empty()) return 0;
     LaunchScope ls(c, TM_HALO);
     for (auto& ro : c->rots)
         k_rot_gather<<<gridFor(ro.size, 128), 128, 0, c->stream>>>(ro.size, nArrays, c->NP + ro.haloStart, ro.d_srcPos, ro.T[0], ro.T[1], ro.T[2], ro.T[3],
-                                                                  ro.T[4], ro.T[5], ro.T[6], ro.T[7], ro.T[8], vecMask, base, stride);
+                                                                  ro.T[4], ro.T[5], ro.T[6], ro.T[7], ro.T[8], ro.rotate ? vecMask : 0u, lagMask, ro.nLag,
+                                                                  ro.d_lagSrc, ro.lagW, base, stride);
     c->launches += (long long)c->rots.size() - 1;
     CUDA_TRY(c, cudaGetLastError());
     return 0;
 }
 
-int ics_halo_fields(icsb200_ctx* c, double* base, size_t stride, int nArrays, unsigned vecMask)
+int ics_halo_fields(icsb200_ctx* c, double* base, size_t stride, int nArrays, unsigned vecMask, unsigned lagMask)
 {
     if (c->NH == 0) return 0;
     {
         int r = amiGather(c, base, stride, nArrays, vecMask);
         if (r) return r;
-        if ((r = rotGather(c, base, stride, nArrays, vecMask))) return r;
+        if ((r = rotGather(c, base, stride, nArrays, vecMask, lagMask))) return r;
     }
     if (c->procs.empty()) return 0;
     if (nArrays > 40) return ics_fail(c, ICSB200_EINVAL, "halo: too many arrays");

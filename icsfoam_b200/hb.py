@@ -50,6 +50,21 @@ def operators(snapshots, omegas):
     return EInv, E, np.ascontiguousarray(D)
 
 
+def phase_lag_operator(snapshots, omegas, ibpa):
+    """phaseLagCyclicFvPatchField::phaseLaggedField (phaseLagCyclicFvPatchField.C:282-330): D_pl = Re(EInv M E) with
+    M = diag(1, e^{i n IBPA} for the +n harmonics, conjugates for the -n ones): the neighbour value of instance l is
+    sum_m D_pl[l][m] * (value of instance m), i.e. the time signal shifted by the inter-blade phase angle."""
+    EInv, E, _ = operators(snapshots, omegas)
+    nF = len(omegas)
+    nH = (nF - 1) // 2
+    M = np.zeros((nF, nF), complex)
+    M[0, 0] = 1.0
+    for n in range(1, nH + 1):
+        M[n, n] = np.cos(n * ibpa) + 1j * np.sin(n * ibpa)
+        M[nF - n, nF - n] = np.conj(M[n, n])
+    return np.ascontiguousarray((EInv @ (M @ E)).real)
+
+
 def set_instants(omega_lists, n_instants, selected_period=None, oversampling=False):
     """HBZoneList::setInstants: the snapshot times (uniform over `selectedPeriod`, or over the period in [T0, 5 T0]
     with the smallest worst-zone condition number) and every zone's D matrix."""

@@ -129,6 +129,14 @@ int icsb200_mesh_set(icsb200_ctx* ctx, int n_cells, int n_internal_faces, int n_
  * deltaCoeffs / nonOrthDeltaCoeffs of the patch faces are cyclicAMIFvPatch's.  Call BEFORE icsb200_mesh_set, once per
  * cyclicAMI patch; both patches of a pair live on the same rank. */
 int icsb200_ami_set(icsb200_ctx* ctx, int patch, int n_faces, const int* face_start, const int* nbr_face, const double* weight);
+/* phaseLagCyclic pair (src/fields/fvPatchFields/constraint/phaseLagCyclic/phaseLagCyclicFvPatchField.C:160-398) in a Harmonic
+ * Balance run: `patch` is a CYCLIC patch of time instance K of the instance-replicated mesh (see icsb200_hb_set) and
+ * weights[n_instants] is row K of D_pl = Re(EInv M(IBPA) E) for that side of the pair (owner +IBPA, neighbour -IBPA; host set-up,
+ * icsfoam_b200/hb.py phase_lag_operator).  The patchNeighbourField of the fields the reference lists by name (rho, p, U, E, H, c) is
+ * then sum_J weights[J] * (value of instance J at the neighbour cell), followed by transform(forwardT, .) on rotational pairs;
+ * all other fields (gradients, solver operands, T) keep the plain cyclic value.  Call BEFORE icsb200_mesh_set, once per replicated
+ * patch; n_instants <= 16. */
+int icsb200_phaselag_set(icsb200_ctx* ctx, int patch, int n_instants, const double* weights);
 /* hePsiThermo<pureMixture<constTransport<hConst<perfectGas>>>>, sensibleInternalEnergy (createFields.H:17-35).
  * mu > 0 makes the run viscous (createFields.H:37-45 `inviscid`): icsb200_residual / iterate then add the laminar
  * viscous terms of residualsUpdate.H:16-43 (laplacian(muEff,U), div(tauMC), div(sigmaDotU & Sf), laplacian(alphaEff,e),

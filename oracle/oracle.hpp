@@ -12,6 +12,7 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -120,6 +121,12 @@ struct Ctx {
     // turbulence->muEff() / alphaEff() handed over by the caller (cells then boundary faces, [N+NB]); empty = laminar
     // constants mu and gamma mu / Pr.  Coupled boundary slots are filled with the patchNeighbourField.
     vecd muEffField, alphaEffField;
+    // phase-lag cyclic patches (src/fields/fvPatchFields/constraint/phaseLagCyclic): this context is time instance hbIndex of
+    // hbSiblings; lagRow[patch] = row hbIndex of D_pl = Re(EInv M(IBPA) E) for that patch side.  The patchNeighbourField of the
+    // listed fields (U*, p, rho, E, H, c) is sum_J lagRow[J] * (field of instance J at the neighbour cell)
+    std::vector<Ctx*> hbSiblings;
+    int hbIndex = 0;
+    std::map<int, vecd> lagRow;
     bool srcMrfApplied = false;  // the Coriolis source has been subtracted from the current srcRhoU
     double mrfAt(int f) const { return mrfFaceVel.empty() ? 0.0 : mrfFaceVel[f]; }
     std::string err;

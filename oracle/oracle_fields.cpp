@@ -137,6 +137,79 @@ void syncCoupled(Ctx& c, vecd& vf, int nc)
     }
 }
 
+// phaseLagCyclicFvPatchField::patchNeighbourField / phaseLaggedField (phaseLagCyclicFvPatchField.C:160-398): for the fields
+// the reference lists by name (U*, p, rho, E, H, c, gamma) the neighbour value of time instance K is
+//   phaseLag = Zero; phaseLag += D_pl[K][J] * (field of instance J at the neighbour cell), J ascending; then transform(forwardT, .)
+// — every other field (gradients, solver operands, T, ...) goes through the plain cyclic path of syncCoupled.
+static double lagCellValue(const Ctx& s, int tag, int cell, int d)
+{
+    const double* u = &s.U[3 * (size_t)cell];
+    switch (tag) {
+        case LAG_P: return s.p[cell];
+        case LAG_U: return u[d];
+        case LAG_RHO: return s.rho[cell];
+        default: break;
+    }
+    const double he = s.Cv * s.T[cell];
+    const double E = he + 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    if (tag == LAG_E) return E;
+    const double H = std::max(E, SMALL) + std::max(s.p[cell] / s.rho[cell], SMALL);
+    if (tag == LAG_H) return H;
+    if (tag == LAG_C2) return std::sqrt(2.0 * (s.gamma - 1.0) / (s.gamma + 1.0) * H);
+    double cc = std::sqrt(s.gamma / s.psi[cell]);
+    if (tag == LAG_C0) cc = std::max(cc, VSMALL);
+    return cc;
+}
+
+void applyPhaseLag(Ctx& c, vecd& vf, int nc, int tag)
+{
+    if (c.lagRow.empty()) return;
+    Mesh& m = c.m;
+    for (auto& kv : c.lagRow) {
+        const Patch& p = m.patches[kv.first];
+        const Patch& q = m.patches[p.nbrPatch];
+        const vecd& w = kv.second;
+        for (int i = 0; i < p.size; i++) {
+            const int nb = m.owner[q.start + i];
+            double* dst = &vf[(size_t)nc * (m.N + p.start - m.F + i)];
+            for (int d = 0; d < nc; d++) {
+                double acc = 0.0;
+                for (size_t J = 0; J < c.hbSiblings.size(); J++) acc += w[J] * lagCellValue(*c.hbSiblings[J], tag, nb, d);
+                dst[d] = acc;
+            }
+            if (p.rotational && nc == 3) {
+                const double* T = p.forwardT;
+                const double v0 = dst[0], v1 = dst[1], v2 = dst[2];
+                dst[0] = T[0] * v0 + T[1] * v1 + T[2] * v2;
+                dst[1] = T[3] * v0 + T[4] * v1 + T[5] * v2;
+                dst[2] = T[6] * v0 + T[7] * v1 + T[8] * v2;
+            }
+        }
+    }
+}
+
+// the coupled-patch part of correctBoundary alone: patchNeighbourField caches of p, U, T, e, psi, rho, rhoU, rhoE.  With
+// phase-lag patches the neighbour values mix all time instances, so they are refreshed once every instance has been updated
+// (the reference evaluates patchNeighbourField() live whenever a face value is needed)
+void resyncCoupledState(Ctx& c)
+{
+    Mesh& m = c.m;
+    syncCoupled(c, c.p, 1); applyPhaseLag(c, c.p, 1, LAG_P);
+    syncCoupled(c, c.U, 3); applyPhaseLag(c, c.U, 3, LAG_U);
+    syncCoupled(c, c.T, 1);
+    for (auto& p : m.patches) {
+        if (!m.coupled(p)) continue;
+        for (int f = p.start; f < p.start + p.size; f++) {
+            int s = m.N + f - m.F;
+            c.e[s] = c.Cv * c.T[s];
+            c.psi[s] = 1.0 / (c.R * c.T[s]);
+        }
+    }
+    syncCoupled(c, c.rho, 1); applyPhaseLag(c, c.rho, 1, LAG_RHO);
+    syncCoupled(c, c.rhoU, 3);
+    syncCoupled(c, c.rhoE, 1);
+}
+
 // ------------------------------------------------------------------------------------------------ operators
 // surfaceInterpolationScheme::interpolate with linear weights: sf = w*(vfP - vfN) + vfN; boundary: patch value,
 // coupled: w*P + (1-w)*N
@@ -422,8 +495,8 @@ void correctBoundary(Ctx& c)
             gradientInternalCoeffs(c, (int)pi, f, &c.gicU[3 * (size_t)b], c.gicT[b]);
         }
     }
-    syncCoupled(c, c.p, 1);
-    syncCoupled(c, c.U, 3);
+    syncCoupled(c, c.p, 1); applyPhaseLag(c, c.p, 1, LAG_P);
+    syncCoupled(c, c.U, 3); applyPhaseLag(c, c.U, 3, LAG_U);
     syncCoupled(c, c.T, 1);
     for (size_t pi = 0; pi < m.patches.size(); pi++) {
         auto& p = m.patches[pi];
@@ -449,7 +522,7 @@ void correctBoundary(Ctx& c)
             c.rhoE[s] = c.rho[s] * (c.e[s] + 0.5 * (Ub[0] * Ub[0] + Ub[1] * Ub[1] + Ub[2] * Ub[2]));
         }
     }
-    syncCoupled(c, c.rho, 1);
+    syncCoupled(c, c.rho, 1); applyPhaseLag(c, c.rho, 1, LAG_RHO);
     syncCoupled(c, c.rhoU, 3);
     syncCoupled(c, c.rhoE, 1);
 }

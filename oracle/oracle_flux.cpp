@@ -74,9 +74,9 @@ void derivedFields(Ctx& c, Derived& d, int cKind /*0: max(sqrt(gamma/psi),VSMALL
     // coupled patches: patchNeighbourField of an expression field is taken from ITS internal field (cyclic / processor: the
     // neighbour cell's value, identical to evaluating the expression on the copied primitives; cyclicAMI: the
     // AMI-interpolated cell values, which is not the expression of the interpolated primitives)
-    syncCoupled(c, d.c, 1);
-    syncCoupled(c, d.E, 1);
-    syncCoupled(c, d.H, 1);
+    syncCoupled(c, d.c, 1); applyPhaseLag(c, d.c, 1, cKind == 2 ? LAG_C2 : (cKind == 1 ? LAG_C1 : LAG_C0));
+    syncCoupled(c, d.E, 1); applyPhaseLag(c, d.E, 1, LAG_E);
+    syncCoupled(c, d.H, 1); applyPhaseLag(c, d.H, 1, LAG_H);
 }
 
 struct Recon {
@@ -596,6 +596,7 @@ static void spectralRadius(Ctx& c, vecd& lambda)
     for (size_t i = 0; i < n; i++) cc[i] = std::sqrt(c.gamma / c.psi[i]);
     for (auto& p : m.patches) if (m.empty(p)) for (int f = p.start; f < p.start + p.size; f++) cc[m.N + f - m.F] = 0;
     syncCoupled(c, cc, 1);  // patchNeighbourField of sqrt(gamma/psi) (see derivedFields)
+    applyPhaseLag(c, cc, 1, LAG_C1);
     interpolateLinear(c, cc, cf);
     for (int d = 0; d < 3; d++) {
         for (size_t i = 0; i < n; i++) comp[i] = c.U[3 * i + d];

@@ -567,6 +567,8 @@ int hbIterate(HBSys& h, const icsb200_solver_controls& ctl)
         updateFields(c);
         c.firstIter = false;
     }
+    // phase-lag patches read every instance: refresh the patchNeighbourField caches once all instances are updated
+    for (int K = 0; K < nO; K++) if (!h.inst[K]->lagRow.empty()) resyncCoupledState(*h.inst[K]);
     h.firstIter = false;
     return 0;
 }
@@ -709,6 +711,22 @@ int orc_world_hb_iterate(void** hbs, int n, const icsb200_solver_controls* ctl, 
         });
     for (auto& t : th) t.join();
     for (int r = 0; r < n; r++) if (rc[r]) return rc[r];
+    return 0;
+}
+
+// phase-lag cyclic patch `patch` (index in the instance mesh): Dpl = Re(EInv M(IBPA) E), n x n row-major, for THIS side of the pair
+// (owner +IBPA, neighbour -IBPA; phaseLagCyclicFvPatchField.C:166-330).  Call once per patch after all instances are initialised.
+int orc_hb_phaselag_set(void* hb, int patch, const double* Dpl)
+{
+    HBSys& h = *(HBSys*)hb;
+    const int nO = h.nO;
+    for (int K = 0; K < nO; K++) {
+        Ctx& c = *h.inst[K];
+        c.hbSiblings.assign(h.inst.begin(), h.inst.end());
+        c.hbIndex = K;
+        c.lagRow[patch] = vecd(Dpl + (size_t)K * nO, Dpl + (size_t)(K + 1) * nO);
+    }
+    for (int K = 0; K < nO; K++) resyncCoupledState(*h.inst[K]);
     return 0;
 }
 

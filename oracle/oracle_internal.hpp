@@ -11,6 +11,10 @@ namespace orc {
 // oracle_fields.cpp
 void meshFinalize(Ctx& c);
 void syncCoupled(Ctx& c, vecd& vf, int nc);
+// phase-lag patches: overwrite the boundary slots of a LISTED field with the phase-lagged neighbour values
+enum { LAG_P = 0, LAG_U, LAG_RHO, LAG_E, LAG_H, LAG_C0, LAG_C1, LAG_C2 /* c with derivedFields' cKind 0/1/2 */ };
+void applyPhaseLag(Ctx& c, vecd& vf, int nc, int tag);
+void resyncCoupledState(Ctx& c);
 void interpolateLinear(const Ctx& c, const vecd& vf, vecd& sf);
 void gradGauss(Ctx& c, const vecd& vf, vecd& grad);
 void interpolateLimitedLR(Ctx& c, const vecd& vf, int lim, vecd& sfL, vecd& sfR);

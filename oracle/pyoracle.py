@@ -134,6 +134,10 @@ class HB:
             rc = L.orc_hb_zone_add(self._h, capi.dptr(D), n_cells, capi.iptr(cells), cyl, capi.dptr(ax), capi.dptr(ce))
             assert rc == 0
 
+        for patch, Dpl in getattr(hbcase, "phase_lag_operators", lambda: [])():
+            rc = L.orc_hb_phaselag_set(self._h, int(patch), capi.dptr(np.ascontiguousarray(Dpl)))
+            assert rc == 0
+
     def _chk(self, rc, what):
         if rc != 0:
             raise capi.ApiError(f"orc_hb_{what} failed ({rc})")

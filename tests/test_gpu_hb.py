@@ -14,12 +14,22 @@ from tests.common import rel_err
 
 pytestmark = pytest.mark.gpu
 
+def _phase_lag(case, ibpa):
+    from icsfoam_b200 import hb
+    om = 2 * np.pi * 40.0            # hb_box default omega
+    harmonics = (case.n_instants - 1) // 2
+    return case.with_phase_lag("xmin", "xmax", ibpa, hb.omega_list([om], [harmonics]))
+
+
 CASES = {
     "roe-allmesh": lambda: cases.hb_box(6, 3, flux="ROE"),
     "hllc-zoned": lambda: cases.hb_box(5, 3, flux="HLLC", limiter="Minmod", zoned=True, seed=5),
     "roe-cyl": lambda: cases.hb_box(5, 3, flux="ROE", cyl=True, seed=7),
     "ausm-5-instants": lambda: cases.hb_box(4, 5, flux="AUSMPlusUp", seed=9),
     "roe-viscous": lambda: cases.hb_box(5, 3, flux="ROE", seed=11, mu=0.05),   # C5: laminar viscous + HB
+    # phaseLagCyclic pair: the neighbour values of rho p U E H c mix the time instances through D_pl = Re(EInv M(IBPA) E)
+    "roe-phaselag": lambda: _phase_lag(cases.hb_box(5, 3, flux="ROE", seed=13), 0.7),
+    "hllc-phaselag-viscous": lambda: _phase_lag(cases.hb_box(4, 5, flux="HLLC", limiter="Minmod", seed=15, mu=0.05), -1.1),
 }
 
 
@@ -64,7 +74,8 @@ def test_hb_piecewise_bitwise(name, gpu_context):
         assert rel_err(gr[k], ores[k]) <= 1e-8, k
 
 
-@pytest.mark.parametrize("name,precond", [("roe-allmesh", "LUSGS"), ("hllc-zoned", "LUSGS"), ("roe-cyl", "Jacobi"), ("roe-viscous", "LUSGS")])
+@pytest.mark.parametrize("name,precond", [("roe-allmesh", "LUSGS"), ("hllc-zoned", "LUSGS"), ("roe-cyl", "Jacobi"), ("roe-viscous", "LUSGS"),
+                                          ("roe-phaselag", "LUSGS"), ("hllc-phaselag-viscous", "LUSGS")])
 def test_hb_outer_iterations(name, precond, gpu_context):
     case = CASES[name]()
     ctl = capi.solver_controls(precond, n_directions=5, max_iter=10, tolerance=1e-10, rel_tol=1e-3)

@@ -270,3 +270,35 @@ def test_partitioned_hb_oracle_matches_single_domain():
         idx = np.concatenate([K * N + hc.base.mesh.cell_global for K in range(3)])
         for k in ("rho", "rhoU", "rhoE"):
             assert np.abs(s2[k] - s1[k][idx]).max() <= 1e-9 * np.abs(s1[k]).max(), (r, k)
+
+
+def test_phase_lag_cyclic_travelling_wave():
+    """phaseLagCyclic (phaseLagCyclicFvPatchField.C:160-398): D_pl = Re(EInv M(IBPA) E) shifts a single-harmonic time signal by the
+    inter-blade phase angle, so with p_K(cell) = p0 + a cos(omega t_K + phi_cell) in every time instance the value a face sees
+    across the pair is p0 + a cos(omega t_K + phi_neighbour +- IBPA) — owner side +, neighbour side - — to rounding; IBPA = 0
+    gives back the plain cyclic pair; the run stays finite."""
+    om = 2 * np.pi * 40.0
+    omegas = hb.omega_list([om], [1])
+    assert np.allclose(hb.phase_lag_operator(np.arange(3) / 3 * (2 * np.pi / om), omegas, 0.0), np.eye(3), atol=1e-14)
+    case = cases.hb_box(5, 3, omega=om, flux="ROE", seed=3)
+    ibpa = 0.7
+    N = case.base.mesh.n_cells
+    phi = np.random.default_rng(0).random(N) * 2 * np.pi
+    for c, t in zip(case.instances, case.snapshots):
+        c.p = 1e5 + 3e3 * np.cos(om * t + phi)
+        c.U = np.stack([50 + 10 * np.cos(om * t + phi + 0.3), 5 * np.cos(om * t + phi), 0 * phi], 1)
+    case.p = np.concatenate([c.p for c in case.instances])
+    case.U = np.concatenate([c.U for c in case.instances])
+    case.with_phase_lag("xmin", "xmax", ibpa, omegas)
+    H = HB(case)
+    m = case.base.mesh
+    F = m.n_internal_faces
+    fa, fb = m.patch_faces("xmin"), m.patch_faces("xmax")
+    for K, t in enumerate(case.snapshots):
+        b = H.inst[K].boundary_get()
+        assert np.abs(b["p"][fa - F] - (1e5 + 3e3 * np.cos(om * t + phi[m.owner[fb]] + ibpa))).max() <= 1e-12 * 1e5
+        assert np.abs(b["p"][fb - F] - (1e5 + 3e3 * np.cos(om * t + phi[m.owner[fa]] - ibpa))).max() <= 1e-12 * 1e5
+        assert np.abs(b["U"][fa - F, 0] - (50 + 10 * np.cos(om * t + phi[m.owner[fb]] + 0.3 + ibpa))).max() <= 1e-12 * 60
+        assert np.array_equal(b["T"][fa - F], H.inst[K].state_get()["T"][m.owner[fb]])     # T is not a phase-lagged field
+    r = H.iterate(case.controls, 3)
+    assert np.isfinite(H.state_get()["rho"]).all() and r["s_init"].max() < 1.0
