@@ -94,6 +94,13 @@ class Case:
                 q = np.quantile(C[:, d], np.linspace(0, 1, n + 1)[1:-1]) if n > 1 else []
                 part += stride * np.searchsorted(q, C[:, d]).astype(np.int32)
                 stride *= n
+        # decomposeParDict `preservePatches` (VKI-LS89/system/decomposeParDict:27-35): both cells of every cyclic face pair on one rank
+        for i, pa in enumerate(self.mesh.patches):
+            if pa["kind"] == capi.CYCLIC and i < pa["nbr_patch"]:
+                pb = self.mesh.patches[pa["nbr_patch"]]
+                fa = np.arange(pa["start"], pa["start"] + pa["size"])
+                fb = np.arange(pb["start"], pb["start"] + pb["size"])
+                part[self.mesh.owner[fb]] = part[self.mesh.owner[fa]]
         meshes = [self.mesh.extract_part(part, r) for r in range(n_parts)]
         return part, meshes
 

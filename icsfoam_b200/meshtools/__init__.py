@@ -276,6 +276,20 @@ class Mesh:
             md = np.linalg.norm(d, axis=1)
             sub.deltaCoeffs[f] = 1.0 / md
             sub.nonOrthDeltaCoeffs[f] = 1.0 / np.maximum(np.einsum("ij,ij->i", nf, d), 0.05 * md)
+        # cyclic pairs kept whole on this rank (decomposePar `preservePatches`): same coupled geometry as in the parent mesh
+        for i, (p, q0) in enumerate(zip(sub.patches, self.patches)):
+            if "forwardT" in q0:
+                p["forwardT"] = list(q0["forwardT"])
+            if p["kind"] != CYCLIC or p["size"] == 0:
+                continue
+            q = sub.patches[p["nbr_patch"]]
+            fa = np.arange(p["start"], p["start"] + p["size"])
+            fb = np.arange(q["start"], q["start"] + q["size"])
+            pa0, pb0 = self.patches[i], self.patches[p["nbr_patch"]]
+            if p["size"] != q["size"] or not np.array_equal(sub.face_global[fa] - pa0["start"], sub.face_global[fb] - pb0["start"]):
+                raise RuntimeError(f"meshtools: the decomposition splits the cyclic pair {p['name']} (use preserve_cyclic)")
+            gf = sub.face_global[fa]
+            sub.weights[fa], sub.deltaCoeffs[fa], sub.nonOrthDeltaCoeffs[fa] = self.weights[gf], self.deltaCoeffs[gf], self.nonOrthDeltaCoeffs[gf]
         return sub
 
     def __del__(self):

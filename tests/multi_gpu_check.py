@@ -57,6 +57,61 @@ def main_hb(rank, world, local, ids):
     sys.exit(0 if int(flag.item()) == 1 else 1)
 
 
+def main_vki(rank, world, local, ids):
+    """C5 across GPUs: the shipped VKI-LS89 mesh decomposed with its cyclic pair kept whole per rank (decomposeParDict
+    preservePatches), laminar viscous ROE run; parity against the P-rank oracle world of the same decomposition."""
+    from oracle.pyoracle import World
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    case = cases.vki_ls89(os.path.join(root, "cases_local", "VKI-LS89", "constant", "polyMesh"))
+    n_iter = int(os.environ.get("ICS_MULTI_ITERS", "4"))
+    part, meshes = case.partition(world, "x")
+    m = meshes[rank]
+    ctx = case.apply(Context(device=local, nccl_id=ids[0], rank=rank, n_ranks=world), mesh=m, cells=m.cell_global)
+    hist = []
+    for _ in range(n_iter):
+        r = ctx.iterate(case.controls)
+        hist.append(list(r.s_init) + list(r.v_init)[:2] + [r.n_iterations])
+    st = ctx.state_get()
+    payload = {"rho": st["rho"], "rhoU": st["rhoU"], "rhoE": st["rhoE"], "hist": hist}
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(payload, gathered, dst=0)
+    ok = True
+    if rank == 0:
+        w = World(world)
+        w.mesh_set(meshes)
+        for o, mm in zip(w.ranks, meshes):
+            o.thermo_set(case.R, case.Cp, case.mu, case.Pr)
+            o.schemes_set(case.schemes)
+            names = [p["name"] for p in mm.patches]
+            for patch, fields in case.bcs.items():
+                if patch in names:
+                    for field, (kind, params) in fields.items():
+                        o.bc_set(patch, {"p": 0, "U": 1, "T": 2}[field], kind, params)
+        w.state_set([case.p[mm.cell_global] for mm in meshes], [case.U[mm.cell_global] for mm in meshes], [case.T[mm.cell_global] for mm in meshes])
+        ohist = []
+        for _ in range(n_iter):
+            rr = w.iterate(case.controls, 1)
+            ohist.append(list(rr.s_init) + list(rr.v_init)[:2] + [rr.n_iterations])
+        ohist, ghist = np.array(ohist), np.array(gathered[0]["hist"])
+        print("oracle VKI history", ohist[:, [0, 1, -1]].tolist())
+        print("gpu    VKI history", ghist[:, [0, 1, -1]].tolist())
+        ok &= np.array_equal(ohist[:, -1], ghist[:, -1])
+        ok &= np.allclose(ohist[:, :-1], ghist[:, :-1], rtol=1e-8, atol=1e-14)
+        for r_, (o, g) in enumerate(zip(w.ranks, gathered)):
+            so = o.state_get()
+            for k in ("rho", "rhoU", "rhoE"):
+                err = np.abs(g[k] - so[k]).max() / np.abs(so[k]).max()
+                print(f"rank {r_} {k} rel err {err:.3e}")
+                ok &= err <= 1e-8
+        print("MULTI_GPU_PARITY", "OK" if ok else "FAILED")
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
 def main():
     n = int(os.environ.get("ICS_MULTI_N", "10"))
     n_iter = int(os.environ.get("ICS_MULTI_ITERS", "4"))
@@ -70,6 +125,8 @@ def main():
     variant = os.environ.get("ICS_MULTI_VARIANT", "")   # "globaldt": non-local time stepping (gMax over ranks); "mrf": rotating zone; "hb"
     if variant == "hb":
         return main_hb(rank, world, local, ids)
+    if variant == "vki":
+        return main_vki(rank, world, local, ids)
 
     def make(r):
         c = cases.onera_box(n, parts=parts, rank=r, mu=mu)

@@ -83,6 +83,30 @@ def test_partitioned_oracle_matches_single_domain(n_parts, mode, mu, mrf):
             assert np.abs(sr[k] - st[k][m.cell_global]).max() <= 1e-8 * np.abs(st[k]).max(), k
 
 
+REF_VKI = "/root/reference/tutorials/VKI-LS89/constant/polyMesh"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_VKI), reason="reference tutorial mesh not present on this machine")
+def test_vki_ls89_decomposed_with_preserved_cyclic_pair():
+    """C5 decomposed: the cyclic pair of the shipped VKI-LS89 mesh stays whole on each rank (decomposeParDict preservePatches,
+    VKI-LS89/system/decomposeParDict:27-35); with block-Jacobi preconditioning the 2-rank world equals the single-domain run."""
+    case = cases.vki_ls89(REF_VKI)
+    ctl = capi.solver_controls("Jacobi", n_directions=8, max_iter=30, tolerance=1e-14, rel_tol=1e-8)
+    single = case.apply(Oracle())
+    w, meshes = setup_world(case, 2, "x")
+    for m in meshes:
+        up, lo = m.patches[m.patch_index("Upper_periodicity")], m.patches[m.patch_index("Lower_periodicity")]
+        assert up["size"] == lo["size"] > 0 and up["kind"] == capi.CYCLIC
+    for _ in range(2):
+        rw, rs = w.iterate(ctl, 1), single.iterate(ctl)
+        assert rw.n_iterations == rs.n_iterations
+    st = single.state_get()
+    for o, m in zip(w.ranks, meshes):
+        sr = o.state_get()
+        for k in ("rho", "rhoU", "rhoE"):
+            assert np.abs(sr[k] - st[k][m.cell_global]).max() <= 1e-10 * np.abs(st[k]).max(), k
+
+
 def test_lusgs_is_rank_local():
     """With LU-SGS the partitioned run is a different (block-Jacobi-of-LU-SGS) preconditioner: histories differ, results
     still converge to the same update within the linear tolerance."""
