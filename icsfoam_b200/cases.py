@@ -392,6 +392,15 @@ class HBCase:
                 for field, (kind, params) in fields.items():
                     api.bc_set(f"{patch}@{K}", fid[field], kind, params)
         api.hb_set(self.n_instants, self.D, self.zone_of_cell, self.cyl_coords, self.rotation_axis, self.rotation_centre)
+        # per-instance MRF / transport fields in the instance-major layout of the replicated mesh:
+        # faces = [internal faces of instance 0, 1, ...][boundary faces of instance 0, 1, ...]
+        F = b.mesh.n_internal_faces
+        if any(c.mrf is not None for c in self.instances):
+            fv, om = zip(*[c.mrf_fields(b.mesh) if c.mrf is not None else (np.zeros(b.mesh.n_faces), np.zeros((b.mesh.n_cells, 3))) for c in self.instances])
+            api.mrf_set(np.concatenate([x[:F] for x in fv] + [x[F:] for x in fv]), np.concatenate(om))
+        if any(c.transport is not None for c in self.instances):
+            tr = [c.transport_fields(b.mesh) for c in self.instances]
+            api.transport_set(*[np.concatenate([t[k] for t in tr]) for k in range(4)])
         api.state_set(self.p, self.U, self.T)
         return api
 
