@@ -114,6 +114,7 @@ SHARED_SIGNATURES = {
     "thermo_set": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]),
     "schemes_set": (C.c_int, [C.c_void_p, C.POINTER(Schemes)]),
     "bc_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
+    "bc_set_nonuniform": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
     "state_set": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
     "state_get": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp]),
     "boundary_get": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp]),
@@ -215,6 +216,11 @@ class Api:
             patch = [p["name"] for p in self.mesh.patches].index(patch)
         if isinstance(kind, str):
             kind = BC_NAMES[kind]
+        if isinstance(params, np.ndarray) and params.ndim == 2:      # one row per face: nonuniform List<...>
+            prm = np.ascontiguousarray(params, np.float64)
+            assert prm.shape[0] == self.mesh.patches[patch]["size"]
+            self._call("bc_set_nonuniform", patch, field, kind, dptr(prm), int(prm.shape[1]))
+            return
         prm = np.asarray(list(params), dtype=np.float64)
         self._call("bc_set", patch, field, kind, dptr(prm) if prm.size else None, int(prm.size))
 

@@ -68,6 +68,10 @@ class Case:
             if patch not in names:
                 continue
             for field, (kind, params) in fields.items():
+                if isinstance(params, np.ndarray) and params.ndim == 2 and m is not self.mesh:
+                    # non-uniform entries on a partition: the rows of the faces this rank keeps
+                    rows = m.face_global[m.patch_faces(patch)] - self.mesh.patches[self.mesh.patch_index(patch)]["start"]
+                    params = np.ascontiguousarray(params[rows])
                 api.bc_set(patch, {"p": capi.FIELD_P, "U": capi.FIELD_U, "T": capi.FIELD_T}[field], kind, params)
         if self.mrf is not None:
             api.mrf_set(*self.mrf_fields(m))
@@ -262,6 +266,30 @@ def sector_and_annulus(n=6, mu=0.0, flux="ROE", limiter="upwind", seed=3):
     cf = Case("annulus", full, 287.0, 1005.0, sch, ctl, {nm: dict(wall) for nm in ("xmin", "xmax", "ymin", "ymax")}, p0[src], UF, T0[src], mu=mu, Pr=0.71)
     first = np.nonzero(turns == 0)[0]
     return cs, cf, first, src[first]
+
+
+def with_inlet_profiles(case, patch, p_kind="fixedValue"):
+    """Replace the uniform entries of `patch` by non-uniform ones (`nonuniform List<...>`): a pressure (or total pressure)
+    profile, a velocity profile for the inletOutlet `inletValue` and a temperature profile — what a radially varying
+    turbomachinery inlet looks like in 0/p, 0/U, 0/T."""
+    m = case.mesh
+    x = m.Cf[m.patch_faces(patch)]
+    s = 0.5 + 0.5 * np.sin(3.0 * x[:, 0] + 2.0 * x[:, 2])
+    if p_kind == "totalPressure":
+        p_rows = np.column_stack([101300.0 * (1.0 + 0.04 * s), np.full(len(s), 1.4)])
+    else:
+        p_rows = (1.05e5 * (1.0 + 0.03 * s))[:, None]
+    case.bcs[patch] = dict(case.bcs[patch])
+    case.bcs[patch]["p"] = (p_kind, np.ascontiguousarray(p_rows))
+    ukind = case.bcs[patch]["U"][0]
+    if ukind in ("inletOutlet", "fixedValue", "freestream"):
+        case.bcs[patch]["U"] = (ukind, np.ascontiguousarray(np.column_stack([50.0 + 20.0 * s, 10.0 - 5.0 * s, 3.0 * s])))
+    tkind = case.bcs[patch]["T"][0]
+    if tkind == "totalTemperature":
+        case.bcs[patch]["T"] = (tkind, np.ascontiguousarray(np.column_stack([288.15 * (1.0 + 0.02 * s), np.full(len(s), 1.4)])))
+    else:
+        case.bcs[patch]["T"] = (tkind, np.ascontiguousarray((310.0 + 8.0 * s)[:, None]))
+    return case
 
 
 def scrambled_box(n=6, flux="HLLC", limiter="vanLeer", seed=0, mu=0.0):

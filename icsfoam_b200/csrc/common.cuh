@@ -47,6 +47,10 @@ enum {
 struct BCDev {
     int kind[3];       // p, U, T
     double prm[3][8];
+    // non-uniform entries (icsb200_bc_set_nonuniform): 8 doubles per face of the patch, or null; bstart = first boundary-face index
+    const double* prmFace[3];
+    int bstart;
+    __host__ __device__ const double* P(int field, int b) const { return prmFace[field] ? prmFace[field] + (size_t)8 * (b - bstart) : prm[field]; }
 };
 
 // timer classes

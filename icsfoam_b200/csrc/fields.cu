@@ -86,7 +86,7 @@ __global__ void k_bc(int NB, int off, const int* __restrict__ bfOwnerPos, const 
     const double vfracPhi = 1.0 - pos0(phi);
     // ---- p
     {
-        const double* prm = bc.prm[0];
+        const double* prm = bc.P(0, b);
         switch (bc.kind[0]) {
             case ICSB200_BC_ZEROGRADIENT:
             case ICSB200_BC_SLIP: pb = pP; pVIC = 1.0; break;
@@ -118,7 +118,7 @@ __global__ void k_bc(int NB, int off, const int* __restrict__ bfOwnerPos, const 
     }
     // ---- U
     {
-        const double* prm = bc.prm[1];
+        const double* prm = bc.P(1, b);
         switch (bc.kind[1]) {
             case ICSB200_BC_ZEROGRADIENT: for (int d = 0; d < 3; d++) { Ub[d] = UP[d]; uVIC[d] = 1.0; gU[d] = 0.0; } break;
             case ICSB200_BC_FIXEDVALUE: for (int d = 0; d < 3; d++) { Ub[d] = prm[d]; uVIC[d] = 0.0; } break;
@@ -154,7 +154,7 @@ __global__ void k_bc(int NB, int off, const int* __restrict__ bfOwnerPos, const 
     // ---- T
     bool fixesT = false;
     {
-        const double* prm = bc.prm[2];
+        const double* prm = bc.P(2, b);
         switch (bc.kind[2]) {
             case ICSB200_BC_ZEROGRADIENT:
             case ICSB200_BC_SLIP: Tb = TP; tVIC = 1.0; gT = 0.0; break;

@@ -435,12 +435,6 @@ k_flux_gather(FluxArgs a)
     }
 }
 
-__global__ void k_zero(size_t n, double* __restrict__ x)
-{
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) x[i] = 0.0;
-}
-
 
 // ------------------------------------------------------------------------------------------------ k_visc
 // Viscous part of residualsUpdate.H:16-43 (laminar): per row, in ascending face id, the four surface integrals
@@ -619,7 +613,7 @@ k_visc(ViscArgs a)
             } else if (kind == ICSB200_BC_INLETOUTLET) {
                 const double vfrac = 1.0 - a.vic[a.NB + b];
 #pragma unroll
-                for (int d = 0; d < 3; d++) sn[d] = vfrac * (bc.prm[ICSB200_FIELD_U][d] - Ui[d]) * dc + (1.0 - vfrac) * 0.0;
+                for (int d = 0; d < 3; d++) sn[d] = vfrac * (bc.P(ICSB200_FIELD_U, b)[d] - Ui[d]) * dc + (1.0 - vfrac) * 0.0;
             } else {
                 sn[0] = sn[1] = sn[2] = 0.0;
             }

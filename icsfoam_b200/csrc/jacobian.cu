@@ -50,7 +50,6 @@ struct JacArgs {
     int ddtScheme;
     double rDeltaT, coefft;
     double mu, alphaEff;  // viscous LF Jacobian (mu > 0)
-    const double* src;    // unused here (sources live in d_src)
     double *offd, *diag, *rD, *rdt, *ddtCoeff;
     const double* recon;  // [8*NFG] limited face states stored by k_flux_faces (REUSE instantiation)
     const double* tr;              // [2][NX] muEff, alphaEff fields or null (laminar constants)

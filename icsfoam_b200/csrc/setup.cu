@@ -140,6 +140,7 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
     for (auto& am : c->amis) { cudaFree(am.d_start); cudaFree(am.d_srcPos); cudaFree(am.d_w); }
     for (auto& ro : c->rots) { cudaFree(ro.d_srcPos); if (ro.d_lagSrc) cudaFree(ro.d_lagSrc); }
+    for (auto& hb : c->h_bc) for (int fl = 0; fl < 3; fl++) if (hb.prmFace[fl]) cudaFree((void*)hb.prmFace[fl]);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaEventDestroy(c->ev0);
@@ -235,6 +236,31 @@ extern "C" int icsb200_bc_set(icsb200_ctx* c, int patch, int field, int kind, co
         return ics_fail(c, ICSB200_EINVAL, "bc_set: bad argument");
     c->h_bc[patch].kind[field] = kind;
     for (int i = 0; i < 8; i++) c->h_bc[patch].prm[field][i] = i < n_params ? params[i] : 0.0;
+    if (c->h_bc[patch].prmFace[field]) { cudaFree((void*)c->h_bc[patch].prmFace[field]); c->h_bc[patch].prmFace[field] = nullptr; }
+    CUDA_TRY(c, cudaMemcpy(c->d_bc, c->h_bc.data(), sizeof(BCDev) * c->h_bc.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// non-uniform patch-field entries (`nonuniform List<...>` of value / p0 / T0 / inletValue / tangentialVelocity in 0/p, 0/U, 0/T):
+// params[size of the patch][n_params], one row per face in patch face order
+extern "C" int icsb200_bc_set_nonuniform(icsb200_ctx* c, int patch, int field, int kind, const double* params, int n_params)
+{
+    c->reconValid = false;
+    if (!c->meshSet) return ics_fail(c, ICSB200_ESTATE, "bc_set: mesh not set");
+    if (patch < 0 || patch >= (int)c->patches.size() || field < 0 || field > 2 || n_params < 1 || n_params > 8 || kind < 0 ||
+        kind > ICSB200_BC_COUPLED || !params)
+        return ics_fail(c, ICSB200_EINVAL, "bc_set: bad argument");
+    cudaSetDevice(c->device);
+    const int n = c->patches[patch].size;
+    std::vector<double> h((size_t)8 * std::max(n, 1), 0.0);
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < n_params; k++) h[(size_t)8 * i + k] = params[(size_t)n_params * i + k];
+    double* d = const_cast<double*>(c->h_bc[patch].prmFace[field]);
+    int r = devUpload(c, &d, h);
+    if (r) return r;
+    c->h_bc[patch].kind[field] = kind;
+    c->h_bc[patch].prmFace[field] = d;
+    c->h_bc[patch].bstart = c->patches[patch].start - c->F;
     CUDA_TRY(c, cudaMemcpy(c->d_bc, c->h_bc.data(), sizeof(BCDev) * c->h_bc.size(), cudaMemcpyHostToDevice));
     return 0;
 }
@@ -851,7 +877,9 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     }
     // halo centres are never read (coupled faces use dCoupled)
     // ---- BCs default: zeroGradient on physical patches
+    for (auto& hb : c->h_bc) for (int fl = 0; fl < 3; fl++) if (hb.prmFace[fl]) cudaFree((void*)hb.prmFace[fl]);
     c->h_bc.assign(n_patches, BCDev{});
+    for (int pi = 0; pi < n_patches; pi++) c->h_bc[pi].bstart = patches[pi].start - F;
     for (int pi = 0; pi < n_patches; pi++) {
         int k = (patches[pi].kind == ICSB200_CYCLIC || patches[pi].kind == ICSB200_PROCESSOR || patches[pi].kind == ICSB200_CYCLICAMI) ? ICSB200_BC_COUPLED
                 : patches[pi].kind == ICSB200_EMPTY ? ICSB200_BC_EMPTY : ICSB200_BC_ZEROGRADIENT;

@@ -146,6 +146,9 @@ int icsb200_thermo_set(icsb200_ctx* ctx, double R, double Cp, double mu, double 
 int icsb200_schemes_set(icsb200_ctx* ctx, const icsb200_schemes* s);
 /* fvPatchField of p, U or T on one patch (0/p, 0/U, 0/T boundaryField entries) */
 int icsb200_bc_set(icsb200_ctx* ctx, int patch, int field, int kind, const double* params, int n_params);
+/* the same with non-uniform entries (`nonuniform List<...>` of value, p0, T0, inletValue, tangentialVelocity ...): params is
+ * [patch size][n_params], one row per face of the patch in its face order — inlet profiles, radially varying total pressure */
+int icsb200_bc_set_nonuniform(icsb200_ctx* ctx, int patch, int field, int kind, const double* params, int n_params);
 
 /* Multiple reference frames: the two fields the solver hands to the flux scheme every outer iteration
  * (applications/solvers/dbnsFoam/outerLoop.H:18-21): mrf_face_velocity[n_faces] = flux.MRFFaceVelocity() =

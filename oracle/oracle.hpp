@@ -56,6 +56,9 @@ struct Mesh {
 struct BC {
     int kind = ICSB200_BC_ZEROGRADIENT;
     double prm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // non-uniform entries (`nonuniform List<...>` of p0, T0, value, inletValue, ...): 8 doubles per face of the patch, or empty
+    vecd prmFace;
+    const double* P(int faceInPatch) const { return prmFace.empty() ? prm : &prmFace[(size_t)8 * faceInPatch]; }
 };
 
 // one LDU sub-block of the coupledMatrix: blockFvMatrix<sourceType, blockType> (blockFvMatrix.H)

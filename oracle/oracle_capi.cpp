@@ -151,7 +151,22 @@ int orc_bc_set(Ctx* c, int patch, int field, int kind, const double* params, int
     if (!c->meshSet) return fail(c, ICSB200_ESTATE, "mesh not set");
     if (patch < 0 || patch >= (int)c->bc.size() || field < 0 || field > 2 || n_params > 8) return fail(c, ICSB200_EINVAL, "bad bc");
     c->bc[patch][field].kind = kind;
+    c->bc[patch][field].prmFace.clear();
     for (int i = 0; i < n_params; i++) c->bc[patch][field].prm[i] = params[i];
+    return 0;
+}
+
+// non-uniform entries: params[size of the patch][n_params], one row per face (nonuniform List<...> in 0/p, 0/U, 0/T)
+int orc_bc_set_nonuniform(Ctx* c, int patch, int field, int kind, const double* params, int n_params)
+{
+    if (!c->meshSet) return fail(c, ICSB200_ESTATE, "mesh not set");
+    if (patch < 0 || patch >= (int)c->bc.size() || field < 0 || field > 2 || n_params < 1 || n_params > 8 || !params) return fail(c, ICSB200_EINVAL, "bad bc");
+    BC& b = c->bc[patch][field];
+    const int n = c->m.patches[patch].size;
+    b.kind = kind;
+    b.prmFace.assign((size_t)8 * n, 0.0);
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < n_params; k++) b.prmFace[(size_t)8 * i + k] = params[(size_t)n_params * i + k];
     return 0;
 }
 

@@ -367,15 +367,15 @@ void evalP(Ctx& c, int pi)
         switch (bc.kind) {
             case ICSB200_BC_ZEROGRADIENT:
             case ICSB200_BC_SLIP: c.p[s] = c.p[o]; break;
-            case ICSB200_BC_FIXEDVALUE: c.p[s] = bc.prm[0]; break;
+            case ICSB200_BC_FIXEDVALUE: c.p[s] = bc.P(f - p.start)[0]; break;
             case ICSB200_BC_INLETOUTLET: {
                 double vfrac = 1.0 - pos0(c.phi[f]);
-                c.p[s] = vfrac * bc.prm[0] + (1.0 - vfrac) * (c.p[o] + 0.0);
+                c.p[s] = vfrac * bc.P(f - p.start)[0] + (1.0 - vfrac) * (c.p[o] + 0.0);
                 break;
             }
             case ICSB200_BC_TOTALPRESSURE: {
                 // totalPressureFvPatchScalarField::updateCoeffs, high-speed compressible branch
-                double p0 = bc.prm[0], g = bc.prm[1];
+                double p0 = bc.P(f - p.start)[0], g = bc.P(f - p.start)[1];
                 const double* Up = &c.U[3 * (size_t)s];
                 double magSqrUp = Up[0] * Up[0] + Up[1] * Up[1] + Up[2] * Up[2];
                 double psip = c.psi[s];
@@ -389,13 +389,13 @@ void evalP(Ctx& c, int pi)
             }
             case ICSB200_BC_FREESTREAMPRESSURE: {
                 // freestreamPressureFvPatchScalarField::updateCoeffs (subsonic branch) + mixed evaluate
-                const double* Ui = &bc.prm[1];
+                const double* Ui = &bc.P(f - p.start)[1];
                 double magUp = std::sqrt(Ui[0] * Ui[0] + Ui[1] * Ui[1] + Ui[2] * Ui[2]);
                 double n[3];
                 nHat(m, f, n);
                 double vfrac = 0.5;
                 if (magUp > VSMALL) vfrac = 0.5 + 0.5 * (Ui[0] * n[0] + Ui[1] * n[1] + Ui[2] * n[2]) / magUp;
-                c.p[s] = vfrac * bc.prm[0] + (1.0 - vfrac) * (c.p[o] + 0.0);
+                c.p[s] = vfrac * bc.P(f - p.start)[0] + (1.0 - vfrac) * (c.p[o] + 0.0);
                 break;
             }
             default: break;
@@ -414,11 +414,11 @@ void evalU(Ctx& c, int pi)
         const double* UP = &c.U[3 * (size_t)o];
         switch (bc.kind) {
             case ICSB200_BC_ZEROGRADIENT: for (int d = 0; d < 3; d++) Ub[d] = UP[d]; break;
-            case ICSB200_BC_FIXEDVALUE: for (int d = 0; d < 3; d++) Ub[d] = bc.prm[d]; break;
+            case ICSB200_BC_FIXEDVALUE: for (int d = 0; d < 3; d++) Ub[d] = bc.P(f - p.start)[d]; break;
             case ICSB200_BC_SLIP: { double n[3]; nHat(m, f, n); symmetryVector(n, UP, Ub); break; }
             case ICSB200_BC_INLETOUTLET: {
                 double vfrac = 1.0 - pos0(c.phi[f]);
-                for (int d = 0; d < 3; d++) Ub[d] = vfrac * bc.prm[d] + (1.0 - vfrac) * (UP[d] + 0.0);
+                for (int d = 0; d < 3; d++) Ub[d] = vfrac * bc.P(f - p.start)[d] + (1.0 - vfrac) * (UP[d] + 0.0);
                 break;
             }
             case ICSB200_BC_PRESSUREINLETOUTLETVELOCITY: {
@@ -428,7 +428,7 @@ void evalU(Ctx& c, int pi)
                 double sgn = neg(c.phi[f]);
                 double vf[6] = {sgn * (1.0 - n[0] * n[0]), sgn * (0.0 - n[0] * n[1]), sgn * (0.0 - n[0] * n[2]),
                                 sgn * (1.0 - n[1] * n[1]), sgn * (0.0 - n[1] * n[2]), sgn * (1.0 - n[2] * n[2])};
-                const double* tv = bc.prm;
+                const double* tv = bc.P(f - p.start);
                 double ntv = n[0] * tv[0] + n[1] * tv[1] + n[2] * tv[2];
                 double ref[3] = {tv[0] - n[0] * ntv, tv[1] - n[1] * ntv, tv[2] - n[2] * ntv};
                 double nv[3] = {vf[0] * ref[0] + vf[1] * ref[1] + vf[2] * ref[2], vf[1] * ref[0] + vf[3] * ref[1] + vf[4] * ref[2],
@@ -455,14 +455,14 @@ void evalT(Ctx& c, int pi)
         switch (bc.kind) {
             case ICSB200_BC_ZEROGRADIENT:
             case ICSB200_BC_SLIP: c.T[s] = c.T[o]; break;
-            case ICSB200_BC_FIXEDVALUE: c.T[s] = bc.prm[0]; break;
+            case ICSB200_BC_FIXEDVALUE: c.T[s] = bc.P(f - p.start)[0]; break;
             case ICSB200_BC_INLETOUTLET: {
                 double vfrac = 1.0 - pos0(c.phi[f]);
-                c.T[s] = vfrac * bc.prm[0] + (1.0 - vfrac) * (c.T[o] + 0.0);
+                c.T[s] = vfrac * bc.P(f - p.start)[0] + (1.0 - vfrac) * (c.T[o] + 0.0);
                 break;
             }
             case ICSB200_BC_TOTALTEMPERATURE: {
-                double T0 = bc.prm[0], g = bc.prm[1];
+                double T0 = bc.P(f - p.start)[0], g = bc.P(f - p.start)[1];
                 double gM1ByG = (g - 1) / g;
                 const double* Up = &c.U[3 * (size_t)s];
                 double magSqrUp = Up[0] * Up[0] + Up[1] * Up[1] + Up[2] * Up[2];
@@ -537,7 +537,7 @@ void valueInternalCoeffs(const Ctx& c, int pi, int f, double& pVIC, double uVIC[
         case ICSB200_BC_ZEROGRADIENT: case ICSB200_BC_SLIP: pVIC = 1.0; break;
         case ICSB200_BC_INLETOUTLET: pVIC = 1.0 * (1.0 - vfracPhi()); break;
         case ICSB200_BC_FREESTREAMPRESSURE: {
-            const double* Ui = &bp.prm[1];
+            const double* Ui = &bp.P(f - m.patches[pi].start)[1];
             double magUp = std::sqrt(Ui[0] * Ui[0] + Ui[1] * Ui[1] + Ui[2] * Ui[2]);
             double n[3];
             nHat(m, f, n);

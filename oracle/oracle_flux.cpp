@@ -386,7 +386,7 @@ void snGradUPatch(const Ctx& c, int pi, int f, double out[3])
         case ICSB200_BC_INLETOUTLET: {  // mixedFvPatchField::snGrad, refGrad = 0; valueFraction as frozen at the last evaluation
             const double vfrac = 1.0 - c.vicU[3 * (size_t)b];
             const BC& bc = c.bc[pi][ICSB200_FIELD_U];
-            for (int d = 0; d < 3; d++) out[d] = vfrac * (bc.prm[d] - Ui[d]) * dc + (1.0 - vfrac) * 0.0;
+            for (int d = 0; d < 3; d++) out[d] = vfrac * (bc.P(f - c.m.patches[pi].start)[d] - Ui[d]) * dc + (1.0 - vfrac) * 0.0;
             break;
         }
         default:  // zeroGradient

@@ -96,6 +96,9 @@ LIVE = {
     "fullvisc-rot": lambda: FULLV(cases.rot_box(5, "ROE", "vanLeer", seed=104, mu=0.1)),
     "fullvisc-bump": lambda: FULLV(cases.bump(15, 10, mu=0.02)),
     "fullvisc-scrambled": lambda: FULLV(cases.scrambled_box(5, "HLLC", "vanLeer", seed=105, mu=0.1)),
+    # non-uniform patch entries (inlet profiles): fixedValue / inletOutlet rows, totalPressure p0 and totalTemperature T0 rows
+    "box-profiles-roe-viscous": lambda: cases.with_inlet_profiles(cases.periodic_box(6, "ROE", "vanLeer", seed=111, mu=0.05), "ymax"),
+    "bump-profiles": lambda: cases.with_inlet_profiles(cases.bump(15, 10), "INLE1", "totalPressure"),
     "shocktube-ausm": lambda: cases.shock_tube(64, "AUSMPlusUp"),
     "shocktube-roe": lambda: cases.shock_tube(50, "ROE"),
 }

@@ -24,6 +24,9 @@ def setup_world(case, n_parts, mode="x"):
         for patch, fields in case.bcs.items():
             if patch in names:
                 for field, (kind, params) in fields.items():
+                    if isinstance(params, np.ndarray) and params.ndim == 2:   # non-uniform entries: the rows of this rank's faces
+                        m = meshes[r]
+                        params = np.ascontiguousarray(params[m.face_global[m.patch_faces(patch)] - case.mesh.patches[case.mesh.patch_index(patch)]["start"]])
                     o.bc_set(patch, {"p": 0, "U": 1, "T": 2}[field], kind, params)
         if case.mrf is not None:
             o.mrf_set(*case.mrf_fields(meshes[r]))
@@ -53,13 +56,19 @@ def test_partition_processor_patches_match():
 
 
 @pytest.mark.parametrize("n_parts,mode,mu,mrf", [(2, "x", 0.0, False), (4, (2, 2, 1), 0.0, False), (4, (2, 2, 1), 0.5, False),
-                                                 (4, (2, 2, 1), 0.0, True), (4, (2, 2, 1), 0.5, "transport")])
+                                                 (4, (2, 2, 1), 0.0, True), (4, (2, 2, 1), 0.5, "transport"), (4, (2, 2, 1), 0.0, "profiles")])
 def test_partitioned_oracle_matches_single_domain(n_parts, mode, mu, mrf):
     """Fluxes / residuals / SpMV do not depend on the decomposition (only LU-SGS and hence the GMRES history do —
     lusgs.C:149,181 keeps the sweeps rank-local).  mu > 0 adds the viscous residual, whose processor-patch faces need the
     neighbour's gradients of U and eCalc."""
     case = cases.onera_box(6, mu=mu)
-    if mrf == "transport":  # muEff / alphaEff fields: processor halos carry the neighbour's cell values
+    if mrf == "profiles":     # non-uniform freestream entries on the inlet patch, split over the ranks
+        n = case.mesh.patches[case.mesh.patch_index("inlet")]["size"]
+        y = case.mesh.Cf[case.mesh.patch_faces("inlet")][:, 1]
+        case.bcs["inlet"] = dict(case.bcs["inlet"])
+        case.bcs["inlet"]["U"] = ("freestream", np.ascontiguousarray(np.column_stack([285.6 * (1 + 0.02 * np.sin(y)), np.full(n, 15.268), np.zeros(n)])))
+        case.bcs["inlet"]["T"] = ("inletOutlet", np.ascontiguousarray((288.15 + 3.0 * np.cos(y))[:, None]))
+    elif mrf == "transport":  # muEff / alphaEff fields: processor halos carry the neighbour's cell values
         case.with_transport(lambda x: (0.5 * (1.2 + np.sin(2.0 * x[:, 0]) * np.cos(x[:, 2])), 0.8 * (1.1 + np.cos(1.5 * x[:, 1]))))
     elif mrf:  # rotating zone in half of the domain: MRFFaceVelocity on processor faces is each side's own (outward) value
         case.with_mrf(omega=(0.0, 40.0, 90.0), origin=(0.5, 0.0, 1.5), zone=lambda x: x[:, 0] > 0.2)
