@@ -813,3 +813,27 @@ def test_nonuniform_patch_entries():
         r = o.iterate(c.controls)
     assert np.isfinite(o.state_get()["rho"]).all()
     assert np.array_equal(o.boundary_get()["p"][f], c.bcs["ymax"]["p"][1][:, 0])
+
+
+def test_bump_c3_transonic_physics():
+    """C3 at the tutorial's own resolution (3 x 66 x 54 cells, circularArcBump/transonic: M = 0.675 over a 10 % arc, HLLC + Minmod,
+    Co = 200): the residual falls by two orders in 120 pseudo-time iterations, the outflow balances the inflow, and the supersonic
+    pocket over the bump peaks at the Mach number the literature gives for this case (Ni 1982: about 1.3 to 1.4)."""
+    c = cases.bump(66, 54)
+    o = c.apply(Oracle())
+    m = c.mesh
+    first = None
+    for it in range(120):
+        r = o.iterate(c.controls)
+        first = first or max(r.s_init)
+    assert max(r.s_init) < 1e-2 * first
+    phi, _, _ = o.calc_flux()
+    fin, fout = m.patch_faces("INLE1"), m.patch_faces("PRES2")
+    assert phi[fin].sum() < 0 < phi[fout].sum()
+    assert abs(phi[fin].sum() + phi[fout].sum()) < 5e-4 * phi[fout].sum()
+    walls = np.concatenate([m.patch_faces("WALL3"), m.patch_faces("WALL4")])
+    assert np.abs(phi[walls]).max() < 1e-9 * phi[fout].sum()          # slip walls carry no mass flux
+    st = o.state_get()
+    mach = np.linalg.norm(st["U"], axis=1) / np.sqrt(1.4 * (cases.RR / 28.966) * st["T"])
+    assert 1.30 < mach.max() < 1.45
+    assert np.abs(st["U"][:, 2]).max() == 0.0
