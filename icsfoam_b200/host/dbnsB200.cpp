@@ -5,7 +5,11 @@
 // It exists because OpenFOAM v2112 is not available in this image (the OpenFOAM adapter is shown in INTEGRATION.md);
 // the dictionary keys are the reference's (SURVEY.md §5 "Config / flags").
 //
-//   dbnsB200 <caseDir> [-maxSteps N] [-device D]
+// Fields may be `uniform` or `nonuniform List<scalar|vector>` (internalField of a written time directory; value / p0 / T0 /
+// inletValue profiles on patches).  -writeFields writes p, U, T of the last step as <caseDir>/<time>/{p,U,T} (ascii, boundary
+// patches as `calculated` with their values; copy the internalField into 0/ to restart).  -parseOnly stops after reading the case.
+//
+//   dbnsB200 <caseDir> [-maxSteps N] [-device D] [-writeFields] [-parseOnly]
 #include <dlfcn.h>
 
 #include <cstdio>
@@ -40,7 +44,7 @@ struct MeshLib {
     }
 };
 
-struct BcSpec { int kind; std::vector<double> prm; };
+struct BcSpec { int kind; std::vector<double> prm; int nRows = 0; /* > 0: prm holds nRows x (prm.size()/nRows) non-uniform rows */ };
 
 std::vector<double> numbers(const std::vector<std::string>& toks)
 {
@@ -53,8 +57,55 @@ std::vector<double> numbers(const std::vector<std::string>& toks)
     return v;
 }
 
+// `uniform v...` -> n copies of the nc components; `nonuniform List<...> n ( ... )` -> the n x nc listed values
+std::vector<double> fieldValues(const std::vector<std::string>& toks, int nc, int n, const std::string& what)
+{
+    std::vector<double> nums = numbers(toks), out((size_t)nc * n);
+    if (!toks.empty() && toks[0] == "nonuniform") {
+        if (nums.empty() || (long)nums[0] != n || (long)nums.size() != 1 + (long)nc * n)
+            throw FatalError("nonuniform " + what + ": expected " + std::to_string(n) + " x " + std::to_string(nc) + " values");
+        std::copy(nums.begin() + 1, nums.end(), out.begin());
+    } else {
+        if ((int)nums.size() != nc) throw FatalError("uniform " + what + ": expected " + std::to_string(nc) + " components");
+        for (int i = 0; i < n; i++) for (int k = 0; k < nc; k++) out[(size_t)nc * i + k] = nums[k];
+    }
+    return out;
+}
+
+void writeField(const std::string& path, const char* cls, const char* name, const char* dims, int nc, const std::vector<double>& cells,
+                const std::vector<std::string>& patchNames, const std::vector<icsb200_patch>& patches, int F, const std::vector<double>& bnd)
+{
+    std::ofstream os(path);
+    if (!os) throw FatalError("cannot write " + path);
+    os.precision(17);
+    auto list = [&](const double* v, size_t n) {
+        os << "nonuniform List<" << (nc == 1 ? "scalar" : "vector") << "> " << n << "\n(\n";
+        for (size_t i = 0; i < n; i++) {
+            if (nc == 1) os << v[i] << "\n";
+            else os << "(" << v[3 * i] << " " << v[3 * i + 1] << " " << v[3 * i + 2] << ")\n";
+        }
+        os << ")";
+    };
+    os << "FoamFile\n{\n    version 2.0;\n    format ascii;\n    class " << cls << ";\n    object " << name << ";\n}\n\ndimensions " << dims
+       << ";\n\ninternalField ";
+    list(cells.data(), cells.size() / nc);
+    os << ";\n\nboundaryField\n{\n";
+    for (size_t pi = 0; pi < patches.size(); pi++) {
+        os << "    " << patchNames[pi] << "\n    {\n";
+        if (patches[pi].kind == ICSB200_EMPTY) os << "        type empty;\n";
+        else if (patches[pi].kind == ICSB200_CYCLIC) os << "        type cyclic;\n";
+        else {
+            os << "        type calculated;\n        value ";
+            list(bnd.data() + (size_t)nc * (patches[pi].start - F), patches[pi].size);
+            os << ";\n";
+        }
+        os << "    }\n";
+    }
+    os << "}\n";
+}
+
 // fvPatchField type name -> ICSB200_BC_* + parameters (the BC set of the five tutorials)
-BcSpec bcFromDict(const dictionary& d, int field, const std::vector<double>& Uinf, const dictionary& top)
+BcSpec bcFromDict(const dictionary& d, int field, const std::vector<double>& Uinf, const dictionary& top, int nFaces)
 {
     const std::string type = d.word("type");
     BcSpec b{ICSB200_BC_ZEROGRADIENT, {}};
@@ -82,7 +133,21 @@ BcSpec bcFromDict(const dictionary& d, int field, const std::vector<double>& Uin
     else if (type == "cyclic" || type == "processor") b.kind = ICSB200_BC_COUPLED;
     else throw FatalError("unsupported patch field type " + type + " (supported: zeroGradient fixedValue slip symmetryPlane empty inletOutlet "
                           "freestream totalPressure totalTemperature pressureInletOutletVelocity freestreamPressure noSlip)");
-    (void)field;
+    // non-uniform entries: value (fixedValue), p0 / T0 (+ gamma), inletValue — one row per face
+    const int nc = field == 1 ? 3 : 1;
+    const char* key = type == "fixedValue" ? "value" : type == "totalPressure" ? "p0" : type == "totalTemperature" ? "T0"
+                      : type == "inletOutlet" ? "inletValue" : nullptr;
+    if (key && d.found(key) && !d.lookup(key).empty() && d.lookup(key)[0] == "nonuniform") {
+        const std::vector<double> v = fieldValues(d.lookup(key), nc, nFaces, std::string(key));
+        const bool withGamma = type == "totalPressure" || type == "totalTemperature";
+        const int np = nc + (withGamma ? 1 : 0);
+        b.prm.assign((size_t)np * nFaces, 0.0);
+        for (int i = 0; i < nFaces; i++) {
+            for (int k = 0; k < nc; k++) b.prm[(size_t)np * i + k] = v[(size_t)nc * i + k];
+            if (withGamma) b.prm[(size_t)np * i + nc] = d.get<double>("gamma");
+        }
+        b.nRows = nFaces;
+    }
     return b;
 }
 
@@ -94,9 +159,12 @@ int main(int argc, char** argv)
         if (argc < 2) { std::fprintf(stderr, "usage: dbnsB200 <caseDir> [-maxSteps N] [-device D]\n"); return 2; }
         const std::string caseDir = argv[1];
         int maxSteps = 1 << 30, device = 0;
-        for (int i = 2; i + 1 < argc; i += 2) {
-            if (!std::strcmp(argv[i], "-maxSteps")) maxSteps = std::atoi(argv[i + 1]);
-            else if (!std::strcmp(argv[i], "-device")) device = std::atoi(argv[i + 1]);
+        bool writeFields = false, parseOnly = false;
+        for (int i = 2; i < argc; i++) {
+            if (!std::strcmp(argv[i], "-maxSteps") && i + 1 < argc) maxSteps = std::atoi(argv[++i]);
+            else if (!std::strcmp(argv[i], "-device") && i + 1 < argc) device = std::atoi(argv[++i]);
+            else if (!std::strcmp(argv[i], "-writeFields")) writeFields = true;
+            else if (!std::strcmp(argv[i], "-parseOnly")) parseOnly = true;
         }
         const char* libEnv = std::getenv("ICSMESH_LIB");
         MeshLib ml(libEnv ? libEnv : "libicsmesh.so");
@@ -128,6 +196,30 @@ int main(int argc, char** argv)
             patches[i] = icsb200_patch{o[0], o[1], o[2], o[3], o[4], {1, 0, 0, 0, 1, 0, 0, 0, 1}};
         }
         std::cout << "Mesh: " << N << " cells, " << F << " internal faces, " << nP << " patches\n";
+
+        // ---- initial fields and boundary conditions (parsed before the device is touched)
+        const std::vector<double> U0 = numbers(UDict.lookup("internalField")).size() >= 3 && UDict.lookup("internalField").at(0) == "uniform"
+                                           ? numbers(UDict.lookup("internalField")) : std::vector<double>{0, 0, 0};
+        std::vector<double> p = fieldValues(pDict.lookup("internalField"), 1, N, "internalField of p");
+        std::vector<double> U = fieldValues(UDict.lookup("internalField"), 3, N, "internalField of U");
+        std::vector<double> T = fieldValues(TDict.lookup("internalField"), 1, N, "internalField of T");
+        const dictionary *top[3] = {&pDict, &UDict, &TDict};
+        const dictionary *bf[3] = {&pDict.subDict("boundaryField"), &UDict.subDict("boundaryField"), &TDict.subDict("boundaryField")};
+        std::vector<BcSpec> bcs((size_t)3 * nP);
+        int nNonuniform = 0;
+        for (int pi = 0; pi < nP; pi++)
+            for (int fld = 0; fld < 3; fld++) {
+                if (!bf[fld]->isDict(patchNames[pi])) throw FatalError("patch " + patchNames[pi] + " missing in boundaryField");
+                bcs[(size_t)3 * pi + fld] = bcFromDict(bf[fld]->subDict(patchNames[pi]), fld, U0, *top[fld], patches[pi].size);
+                nNonuniform += bcs[(size_t)3 * pi + fld].nRows > 0;
+            }
+        if (parseOnly) {
+            double pmin = 1e300, pmax = -1e300;
+            for (double v : p) { pmin = std::min(pmin, v); pmax = std::max(pmax, v); }
+            std::cout << "parse ok: p in [" << pmin << ", " << pmax << "], " << nNonuniform << " non-uniform patch entries\nEnd\n";
+            ml.free_(mh);
+            return 0;
+        }
 
         icsb200_ctx* ctx = nullptr;
         check(nullptr, icsb200_create(&ctx, device, nullptr, 0, 1), "icsb200_create (needs a B200; there is no CPU fallback)");
@@ -176,20 +268,13 @@ int main(int argc, char** argv)
         std::cout << (steadyState ? "Steady-state analysis detected\n" : "Transient analysis detected\n");
 
         // ---- boundary conditions and initial fields
-        const std::vector<double> U0 = numbers(UDict.lookup("internalField"));
-        const double p0 = numbers(pDict.lookup("internalField")).at(0), T0 = numbers(TDict.lookup("internalField")).at(0);
-        if (UDict.lookup("internalField").at(0) != "uniform") throw FatalError("only uniform internalField is supported by the standalone reader");
-        const dictionary *top[3] = {&pDict, &UDict, &TDict};
-        const dictionary *bf[3] = {&pDict.subDict("boundaryField"), &UDict.subDict("boundaryField"), &TDict.subDict("boundaryField")};
         for (int pi = 0; pi < nP; pi++)
             for (int fld = 0; fld < 3; fld++) {
-                if (!bf[fld]->isDict(patchNames[pi])) throw FatalError("patch " + patchNames[pi] + " missing in boundaryField");
-                BcSpec b = bcFromDict(bf[fld]->subDict(patchNames[pi]), fld, U0, *top[fld]);
+                const BcSpec& b = bcs[(size_t)3 * pi + fld];
                 if (b.kind == ICSB200_BC_EMPTY || b.kind == ICSB200_BC_COUPLED) continue;
-                check(ctx, icsb200_bc_set(ctx, pi, fld, b.kind, b.prm.data(), (int)b.prm.size()), "bc_set");
+                if (b.nRows > 0) check(ctx, icsb200_bc_set_nonuniform(ctx, pi, fld, b.kind, b.prm.data(), (int)(b.prm.size() / b.nRows)), "bc_set_nonuniform");
+                else check(ctx, icsb200_bc_set(ctx, pi, fld, b.kind, b.prm.data(), (int)b.prm.size()), "bc_set");
             }
-        std::vector<double> p(N, p0), T(N, T0), U(3 * (size_t)N);
-        for (int i = 0; i < N; i++) for (int d = 0; d < 3; d++) U[3 * (size_t)i + d] = U0.at(d);
         check(ctx, icsb200_state_set(ctx, p.data(), U.data(), T.data()), "state_set");
 
         // ---- solver controls (fvSolution/flowSolver) and pseudo-time control (pseudotimeControl.C:42-69)
@@ -246,6 +331,21 @@ int main(int argc, char** argv)
         check(ctx, icsb200_state_get(ctx, rho.data(), nullptr, nullptr, nullptr, nullptr, nullptr), "state_get");
         double rmin = 1e300, rmax = -1e300;
         for (double v : rho) { rmin = std::min(rmin, v); rmax = std::max(rmax, v); }
+        if (writeFields) {
+            // time directory of the last step (dbnsFoam: runTime.write()): p, U, T with the boundary values as `calculated` patches
+            const int NBf = FT - F;
+            std::vector<double> pb(NBf), Ub(3 * (size_t)NBf), Tb(NBf);
+            check(ctx, icsb200_state_get(ctx, nullptr, nullptr, nullptr, p.data(), U.data(), T.data()), "state_get");
+            check(ctx, icsb200_boundary_get(ctx, nullptr, Ub.data(), pb.data(), Tb.data()), "boundary_get");
+            std::ostringstream tn;
+            tn << time;
+            const std::string dir = caseDir + "/" + tn.str();
+            if (std::system(("mkdir -p '" + dir + "'").c_str()) != 0) throw FatalError("cannot create " + dir);
+            writeField(dir + "/p", "volScalarField", "p", "[1 -1 -2 0 0 0 0]", 1, p, patchNames, patches, F, pb);
+            writeField(dir + "/U", "volVectorField", "U", "[0 1 -1 0 0 0 0]", 3, U, patchNames, patches, F, Ub);
+            writeField(dir + "/T", "volScalarField", "T", "[0 0 0 1 0 0 0]", 1, T, patchNames, patches, F, Tb);
+            std::cout << "fields written to " << dir << "\n";
+        }
         std::cout << "rho min/max: " << rmin << " " << rmax << "\nkernel launches: " << icsb200_launch_count(ctx) << "\nEnd\n";
         icsb200_destroy(ctx);
         ml.free_(mh);

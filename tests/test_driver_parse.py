@@ -1,0 +1,51 @@
+"""Host-side parsing of the standalone driver dbnsB200 (no GPU needed: -parseOnly stops before the device is touched):
+OpenFOAM dictionaries of the shipped VKI-LS89 tutorial with `nonuniform List<...>` entries spliced in — the internalField of a
+written time directory and a total-pressure profile on the inlet."""
+import os
+import re
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "icsfoam_b200", "host", "dbnsB200")
+MESHLIB = os.path.join(ROOT, "icsfoam_b200", "meshtools", "libicsmesh.so")
+REF = "/root/reference/tutorials/VKI-LS89"
+
+
+def run(case_dir, *flags):
+    return subprocess.run([DRIVER, case_dir, *flags], env=dict(os.environ, ICSMESH_LIB=MESHLIB), capture_output=True, text=True, timeout=300)
+
+
+def foam_list(values):
+    values = np.asarray(values)
+    if values.ndim == 1:
+        body = "\n".join(repr(float(v)) for v in values)
+        return f"nonuniform List<scalar> {len(values)}\n(\n{body}\n)"
+    body = "\n".join("(" + " ".join(repr(float(x)) for x in v) + ")" for v in values)
+    return f"nonuniform List<vector> {len(values)}\n(\n{body}\n)"
+
+
+@pytest.mark.skipif(not (os.path.isdir(REF) and os.path.exists(DRIVER)), reason="reference tutorial or driver binary not present")
+def test_driver_parses_nonuniform_fields(tmp_path):
+    case = tmp_path / "vki"
+    shutil.copytree(REF, case)
+    r = run(str(case), "-parseOnly")
+    assert r.returncode == 0 and "parse ok: p in [100000, 100000], 0 non-uniform patch entries" in r.stdout, r.stdout + r.stderr
+    N = 28059
+    pvals = 1e5 + np.arange(N) * 0.5
+    ptxt = (case / "0" / "p").read_text()
+    ptxt = ptxt.replace("internalField   uniform 1e5;", "internalField   " + foam_list(pvals) + ";")
+    ptxt = re.sub(r"p0\s+uniform 160500;", "p0 " + foam_list(160500.0 + np.arange(105)) + ";", ptxt)
+    (case / "0" / "p").write_text(ptxt)
+    utxt = (case / "0" / "U").read_text().replace("internalField   uniform (100 0 0);", "internalField   " + foam_list(np.tile([100.0, 1.0, 0.0], (N, 1))) + ";")
+    (case / "0" / "U").write_text(utxt)
+    r = run(str(case), "-parseOnly")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"parse ok: p in [100000, {1e5 + (N - 1) * 0.5:g}], 1 non-uniform patch entries" in r.stdout, r.stdout
+    # a list of the wrong length is an error, not a silent truncation
+    (case / "0" / "T").write_text((case / "0" / "T").read_text().replace("internalField   uniform 400;", "internalField   " + foam_list(np.full(7, 400.0)) + ";"))
+    r = run(str(case), "-parseOnly")
+    assert r.returncode != 0 and "nonuniform internalField of T" in r.stderr

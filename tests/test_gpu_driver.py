@@ -55,3 +55,39 @@ def test_driver_runs_forward_step_tutorial_directory(gpu_context):
         assert its[k] == r.n_iterations, k
         want = np.array(list(r.s_init) + list(r.v_init))
         assert np.abs(init[k][:4] - want[:4]).max() <= 1e-5 * np.abs(want[:4]).max(), (k, init[k], want)
+
+
+@pytest.mark.skipif(not os.path.isdir(staged("VKI-LS89") + "/system"), reason="VKI-LS89 tutorial not staged (cases_local/ is not part of the repository)")
+def test_driver_writes_a_time_directory_that_it_can_read_back(gpu_context, tmp_path):
+    """-writeFields: p, U, T of the last step as <case>/<time>/{p,U,T}; the written internalField lists equal the state of the
+    Python host path after the same 3 iterations to the 17 printed digits, and the files parse as `nonuniform List<...>` fields
+    when spliced into 0/ (restart)."""
+    import shutil
+    case_dir = str(tmp_path / "vki")
+    shutil.copytree(staged("VKI-LS89"), case_dir)
+    r = subprocess.run([DRIVER, case_dir, "-maxSteps", "3", "-writeFields"], env=dict(os.environ, ICSMESH_LIB=MESHLIB), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "fields written to" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    case = cases.vki_ls89(staged("VKI-LS89") + "/constant/polyMesh")
+    g = case.apply(gpu_context())
+    for _ in range(3):
+        g.iterate(case.controls)
+    st = g.state_get()
+
+    def internal(path, nc):
+        txt = open(path).read()
+        body = txt[txt.index("internalField"):txt.index("boundaryField")]
+        nums = np.array([float(x) for x in re.findall(r"[-+]?\d[\d.]*(?:[eE][-+]?\d+)?", body.split("\n(\n", 1)[1])])
+        return nums.reshape(-1, nc) if nc > 1 else nums
+
+    assert np.array_equal(internal(os.path.join(case_dir, "3", "p"), 1), st["p"])
+    assert np.array_equal(internal(os.path.join(case_dir, "3", "T"), 1), st["T"])
+    assert np.array_equal(internal(os.path.join(case_dir, "3", "U"), 3), st["U"])
+    # restart: splice the written internalField into 0/p and let the driver parse it
+    ptxt = open(os.path.join(case_dir, "3", "p")).read()
+    written = ptxt[ptxt.index("internalField"):ptxt.index("boundaryField")]
+    p0 = open(os.path.join(case_dir, "0", "p")).read().replace("internalField   uniform 1e5;", written)
+    open(os.path.join(case_dir, "0", "p"), "w").write(p0)
+    r = subprocess.run([DRIVER, case_dir, "-parseOnly"], env=dict(os.environ, ICSMESH_LIB=MESHLIB), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "parse ok" in r.stdout, r.stdout + r.stderr
+    lo, hi = [float(x) for x in re.search(r"p in \[([^,]+), ([^\]]+)\]", r.stdout).groups()]
+    assert abs(lo - st["p"].min()) <= 1e-5 * st["p"].min() and abs(hi - st["p"].max()) <= 1e-5 * st["p"].max()
