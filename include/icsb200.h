@@ -176,7 +176,10 @@ int icsb200_transport_set(icsb200_ctx* ctx, const double* muEff, const double* m
 int icsb200_state_set(icsb200_ctx* ctx, const double* p, const double* U, const double* T);
 /* any pointer may be NULL.  Cell arrays [N]/[3N]. */
 int icsb200_state_get(icsb200_ctx* ctx, double* rho, double* rhoU, double* rhoE, double* p, double* U, double* T);
-/* boundary values, indexed by (face - n_internal_faces); any pointer may be NULL */
+/* boundary values, indexed by (face - n_internal_faces); any pointer may be NULL.  Faces of coupled patches report the
+ * patchNeighbourField (neighbour cell value: interpolated for cyclicAMI, rotated on rotational pairs, phase-lagged where that
+ * applies).  With processor patches this call exchanges a halo, i.e. it is COLLECTIVE over the ranks (as are icsb200_state_set,
+ * icsb200_transport_set and every iterate / matrix_mul / solve call). */
 int icsb200_boundary_get(icsb200_ctx* ctx, double* rho_b, double* U_b, double* p_b, double* T_b);
 /* transient: shift W -> W.old -> W.oldOld (runTime++ of dbnsFoam.C:103) */
 int icsb200_new_time_step(icsb200_ctx* ctx);
