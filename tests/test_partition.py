@@ -168,3 +168,43 @@ def test_gloo_world_size_2_halo_consistency(tmp_path):
                         "--master-port", "29533", str(script)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+GLOO_HB_SCRIPT = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["ICS_ROOT"])
+from icsfoam_b200 import cases, capi
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# Harmonic Balance across ranks: every rank replicates ITS partition n_instants times; the processor patches of the
+# replicated meshes must pair up instance by instance, in the same order on both sides (one NCCL group per exchange)
+full = cases.hb_box(5, 3, flux="ROE", cyclic=False, seed=3)
+mine = full.partition(world, "x")[rank]
+m = mine.mesh                                  # hb.ReplicatedMesh of this rank's partition
+procs = [p for p in m.patches if p["kind"] == capi.PROCESSOR]
+assert len(procs) == 3 * (world - 1) and [p["name"].split("@")[1] for p in procs] == ["0", "1", "2"][: len(procs)]
+for p in procs:
+    f = np.arange(p["start"], p["start"] + p["size"])
+    send = torch.from_numpy(np.ascontiguousarray(m.Cf[f]))
+    recv = torch.empty_like(send)
+    reqs = [dist.isend(send, p["nbr_rank"]), dist.irecv(recv, p["nbr_rank"])]
+    [r.wait() for r in reqs]
+    assert torch.allclose(send, recv, atol=0), "replicated processor patches are not matched in order"
+    assert (m.owner[f] // mine.base.mesh.n_cells == int(p["name"].split("@")[1])).all()     # faces of instance K touch cells of instance K
+n = torch.tensor([mine.base.mesh.n_cells], dtype=torch.int64)
+dist.all_reduce(n)
+assert int(n) == full.base.mesh.n_cells
+print("rank", rank, "ok")
+'''
+
+
+def test_gloo_world_size_2_hb_replicated_partitions(tmp_path):
+    script = tmp_path / "gloo_hb_check.py"
+    script.write_text(GLOO_HB_SCRIPT)
+    env = dict(os.environ, ICS_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29537")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29537", str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
