@@ -837,3 +837,54 @@ def test_bump_c3_transonic_physics():
     mach = np.linalg.norm(st["U"], axis=1) / np.sqrt(1.4 * (cases.RR / 28.966) * st["T"])
     assert 1.30 < mach.max() < 1.45
     assert np.abs(st["U"][:, 2]).max() == 0.0
+
+
+def test_patch_field_closed_forms():
+    """The OpenFOAM patch fields the tutorials use, against their closed forms: totalPressure /
+    totalTemperature isentropic relations with the lagged flux switch, inletOutlet / freestream switching on the sign of phi,
+    basicSymmetry (slip) removing the normal component, pressureInletOutletVelocity keeping only the normal component on
+    inflow, freestreamPressure blending with 0.5 + 0.5 (U_inf.n)/|U_inf|."""
+    mesh = mt.structured(1, 4, 3, 3, 0, (0, 0, 0), (1.0, 1.0, 1.0), patch_kinds=(capi.PATCH,) * 6)
+    N = mesh.n_cells
+    rng = np.random.default_rng(2)
+    p, T = 1e5 * (1 + 0.05 * rng.random(N)), 300 * (1 + 0.05 * rng.random(N))
+    U = np.tile([60.0, 25.0, -10.0], (N, 1)) * (1 + 0.1 * rng.random((N, 1)))
+    Uinf = (80.0, 10.0, 5.0)
+    bcs = {
+        "xmin": {"p": ("totalPressure", (1.2e5, 1.4)), "U": ("pressureInletOutletVelocity", (0.0, 4.0, 0.0)), "T": ("totalTemperature", (330.0, 1.4))},
+        "xmax": {"p": ("fixedValue", (0.9e5,)), "U": ("inletOutlet", (1.0, 2.0, 3.0)), "T": ("inletOutlet", (290.0,))},
+        "ymin": {"p": ("zeroGradient", ()), "U": ("slip", ()), "T": ("zeroGradient", ())},
+        "ymax": {"p": ("freestreamPressure", (1.01e5,) + Uinf), "U": ("freestream", Uinf), "T": ("fixedValue", (305.0,))},
+    }
+    sch = capi.default_schemes(flux_scheme="HLLC")
+    case = cases.Case("bc", mesh, 287.0, 1005.0, sch, capi.solver_controls(), bcs, p, U, T)
+    o = case.apply(Oracle())
+    b = o.boundary_get()
+    F = mesh.n_internal_faces
+    g, R = 1.4, 287.0
+
+    def faces(name):
+        f = mesh.patch_faces(name)
+        return f, f - F, mesh.owner[f], mesh.Sf[f] / mesh.magSf[f][:, None]
+
+    # x-min: flow enters (U.x > 0 against the outward normal -x): phi < 0
+    f, fb, own, n = faces("xmin")
+    Ub = b["U"][fb]
+    assert np.allclose(Ub, n * (U[own] * n).sum(1)[:, None] + [0.0, 4.0, 0.0], rtol=1e-13)          # normal part of the cell velocity + tangential
+    psi = 1.0 / (R * b["T"][fb])
+    # the total conditions use the boundary velocity and psi of the PREVIOUS evaluation; state_set evaluates twice, so they are consistent to first order
+    assert np.allclose(b["T"][fb], 330.0 / (1 + 0.5 * psi * (g - 1) / g * (Ub * Ub).sum(1)), rtol=2e-3)
+    assert np.allclose(b["p"][fb], 1.2e5 / (1 + 0.5 * psi * (g - 1) / g * (Ub * Ub).sum(1)) ** (g / (g - 1)), rtol=5e-3)
+    # x-max: flow leaves: inletOutlet = zeroGradient, pressure fixed
+    f, fb, own, n = faces("xmax")
+    assert np.array_equal(b["U"][fb], U[own]) and np.array_equal(b["T"][fb], T[own]) and (b["p"][fb] == 0.9e5).all()
+    # y-min: slip removes the normal component, scalars zero-gradient
+    f, fb, own, n = faces("ymin")
+    assert np.allclose(b["U"][fb], U[own] - n * (U[own] * n).sum(1)[:, None], rtol=1e-13, atol=1e-12)
+    assert np.array_equal(b["p"][fb], p[own])
+    # y-max: cell flow leaves through it (U.y > 0): freestream velocity = zeroGradient there; freestreamPressure blends with the free-stream direction
+    f, fb, own, n = faces("ymax")
+    assert np.array_equal(b["U"][fb], U[own]) and (b["T"][fb] == 305.0).all()
+    vf = 0.5 + 0.5 * (np.array(Uinf) * n).sum(1) / np.linalg.norm(Uinf)
+    assert np.allclose(b["p"][fb], vf * 1.01e5 + (1 - vf) * p[own], rtol=1e-13)
+    assert np.allclose(b["rho"][fb], b["p"][fb] / (R * b["T"][fb]), rtol=1e-13)
