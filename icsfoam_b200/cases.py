@@ -108,6 +108,24 @@ class Case:
         meshes = [self.mesh.extract_part(part, r) for r in range(n_parts)]
         return part, meshes
 
+    def decomposed(self, case_dir):
+        """The partition OpenFOAM's decomposePar wrote under `case_dir/processor*`: same return value as
+        `partition`.  `self.mesh` must be the undecomposed mesh of that case (cellProcAddressing refers to it)."""
+        from .meshtools import foamcase
+        n = foamcase.n_processors(case_dir)
+        if n == 0:
+            raise RuntimeError(f"no processor directories under {case_dir}")
+        cache = {}
+        meshes = [foamcase.read_decomposed(case_dir, r, cache) for r in range(n)]
+        part = np.full(self.mesh.n_cells, -1, np.int32)
+        for r, m in enumerate(meshes):
+            if m.cell_global is None:
+                raise RuntimeError(f"processor{r} has no cellProcAddressing")
+            part[m.cell_global] = r
+        if (part < 0).any():
+            raise RuntimeError("the processor directories do not cover the mesh")
+        return part, meshes
+
 
 def _uniform(mesh, p, U, T):
     N = mesh.n_cells

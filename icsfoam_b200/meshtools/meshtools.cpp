@@ -414,11 +414,13 @@ Mesh* readPolyMesh(const std::string& dir)
                 else if (tok == "type") { is >> type; if (!type.empty() && type.back() == ';') type.pop_back(); }
                 else if (tok == "neighbourPatch") { is >> nbrName; if (!nbrName.empty() && nbrName.back() == ';') nbrName.pop_back(); }
                 else if (tok == "transform") { is >> tok; if (!tok.empty() && tok.back() == ';') tok.pop_back(); if (tok == "rotational") m.error = "rotational cyclic patch " + pa.name + " is not supported"; }
+                else if (tok == "neighbProcNo") { is >> tok; pa.nbrRank = std::atoi(tok.c_str()); }   // processorPolyPatch (decomposePar output)
                 else if (tok == "nFaces") { is >> tok; pa.size = std::atoi(tok.c_str()); }
                 else if (tok == "startFace") { is >> tok; pa.start = std::atoi(tok.c_str()); }
             }
             pa.kind = type == "wall" ? PK_WALL : type == "empty" ? PK_EMPTY : type == "symmetryPlane" ? PK_SYMMETRYPLANE
                       : type == "cyclic" ? PK_CYCLIC : type == "processor" ? PK_PROCESSOR : PK_PATCH;
+            if (type == "processorCyclic") m.error = "processorCyclic patch " + pa.name + " is not supported (decompose with preservePatches)";
             m.patches.push_back(pa);
             nbrNames.push_back(nbrName);
         }
