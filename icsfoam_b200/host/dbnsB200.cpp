@@ -9,7 +9,10 @@
 // inletValue profiles on patches).  -writeFields writes p, U, T of the last step as <caseDir>/<time>/{p,U,T} (ascii, boundary
 // patches as `calculated` with their values; copy the internalField into 0/ to restart).  -parseOnly stops after reading the case.
 //
-//   dbnsB200 <caseDir> [-maxSteps N] [-device D] [-writeFields] [-parseOnly]
+//   dbnsB200 <caseDir> [-maxSteps N] [-device D] [-writeFields] [-writeFlux] [-parseOnly]
+// -writeFlux (implies -writeFields) adds rho and the face fluxes phi, phiUp, phiEp of the LAST outer iteration (evaluated, as in
+// outerLoop.H:51-57, from the state that iteration started from — what dbnsFoam's AUTO_WRITE phi holds at runTime.write()), so
+// that a time directory of the reference run on an OpenFOAM machine can be compared file by file (tools/foamdiff.py).
 #include <dlfcn.h>
 
 #include <cstdio>
@@ -159,11 +162,12 @@ int main(int argc, char** argv)
         if (argc < 2) { std::fprintf(stderr, "usage: dbnsB200 <caseDir> [-maxSteps N] [-device D]\n"); return 2; }
         const std::string caseDir = argv[1];
         int maxSteps = 1 << 30, device = 0;
-        bool writeFields = false, parseOnly = false;
+        bool writeFields = false, writeFlux = false, parseOnly = false;
         for (int i = 2; i < argc; i++) {
             if (!std::strcmp(argv[i], "-maxSteps") && i + 1 < argc) maxSteps = std::atoi(argv[++i]);
             else if (!std::strcmp(argv[i], "-device") && i + 1 < argc) device = std::atoi(argv[++i]);
             else if (!std::strcmp(argv[i], "-writeFields")) writeFields = true;
+            else if (!std::strcmp(argv[i], "-writeFlux")) writeFields = writeFlux = true;
             else if (!std::strcmp(argv[i], "-parseOnly")) parseOnly = true;
         }
         const char* libEnv = std::getenv("ICSMESH_LIB");
@@ -288,6 +292,7 @@ int main(int argc, char** argv)
 
         // ---- time loop (dbnsFoam.C:88-151)
         residualsIO residuals, initResiduals;
+        std::vector<double> phiH(writeFlux ? FT : 0), phiUpH(writeFlux ? 3 * (size_t)FT : 0), phiEpH(writeFlux ? FT : 0);
         bool haveInit = false;
         int corr = 0, step = 0;  // steady: corr runs over the whole run (pseudotimeControl::loop, Q7)
         while (time < endTime - 1e-12 * std::fabs(endTime) && step < maxSteps) {
@@ -319,6 +324,7 @@ int main(int argc, char** argv)
                 if (converged) { std::cout << "pseudoTime: converged in " << corr - 1 << " iterations\n"; break; }
                 std::cout << "pseudoTime: iteration " << corr << "\n";
                 icsb200_residuals r;
+                if (writeFlux) check(ctx, icsb200_calc_flux(ctx, phiH.data(), phiUpH.data(), phiEpH.data()), "calc_flux");
                 check(ctx, icsb200_iterate_dev(ctx, &ctl, &r), "outerLoop");   // outerLoop.H + updateFields.H on the device
                 residuals = residualsIO(r);
                 std::cout << "GMRES : Solving for (  rhoIncr rhoEIncr rhoUIncr ) \n";
@@ -344,6 +350,40 @@ int main(int argc, char** argv)
             writeField(dir + "/p", "volScalarField", "p", "[1 -1 -2 0 0 0 0]", 1, p, patchNames, patches, F, pb);
             writeField(dir + "/U", "volVectorField", "U", "[0 1 -1 0 0 0 0]", 3, U, patchNames, patches, F, Ub);
             writeField(dir + "/T", "volScalarField", "T", "[0 0 0 1 0 0 0]", 1, T, patchNames, patches, F, Tb);
+            if (writeFlux) {
+                std::vector<double> rhob(NBf);
+                check(ctx, icsb200_boundary_get(ctx, rhob.data(), nullptr, nullptr, nullptr), "boundary_get");
+                writeField(dir + "/rho", "volScalarField", "rho", "[1 -3 0 0 0 0 0]", 1, rho, patchNames, patches, F, rhob);
+                auto surf = [&](const char* name, const char* cls, const char* dims, int nc, const std::vector<double>& v) {
+                    const std::vector<double> in(v.begin(), v.begin() + (size_t)nc * F), bd(v.begin() + (size_t)nc * F, v.end());
+                    writeField(dir + "/" + name, cls, name, dims, nc, in, patchNames, patches, F, bd);
+                };
+                surf("phi", "surfaceScalarField", "[1 0 -1 0 0 0 0]", 1, phiH);
+                surf("phiUp", "surfaceVectorField", "[1 1 -2 0 0 0 0]", 3, phiUpH);
+                surf("phiEp", "surfaceScalarField", "[1 2 -3 0 0 0 0]", 1, phiEpH);
+                // LDU arrays of the nine sub-blocks of the last outer iteration's coupledMatrix (coupledMatrix.H:399-421), one ASCII
+                // list per array: <time>/eqSystem/<block>_<diag|upper|lower> (tools/openfoam_golden/compare_matrix.py)
+                static const char* blockNames[9] = {"dSByS_0_0", "dSByS_0_1", "dSByS_1_0", "dSByS_1_1", "dSByV_0_0", "dSByV_1_0", "dVByS_0_0", "dVByS_0_1", "dVByV_0_0"};
+                static const int blockNc[9] = {1, 1, 1, 1, 3, 3, 3, 3, 9};
+                if (std::system(("mkdir -p '" + dir + "/eqSystem'").c_str()) != 0) throw FatalError("cannot create " + dir + "/eqSystem");
+                for (int b = 0; b < 9; b++) {
+                    const int nc = blockNc[b];
+                    std::vector<double> dg((size_t)nc * N), up((size_t)nc * F), lw((size_t)nc * F);
+                    check(ctx, icsb200_matrix_get_ldu(ctx, b, dg.data(), up.data(), lw.data()), "matrix_get_ldu");
+                    auto dump = [&](const char* part, const std::vector<double>& v) {
+                        std::ofstream os(dir + "/eqSystem/" + blockNames[b] + "_" + part);
+                        os.precision(17);
+                        const size_t n = v.size() / nc;
+                        os << n << "\n(\n";
+                        for (size_t i = 0; i < n; i++) {
+                            if (nc == 1) os << v[i] << "\n";
+                            else { os << "("; for (int k = 0; k < nc; k++) os << (k ? " " : "") << v[i * nc + k]; os << ")\n"; }
+                        }
+                        os << ")\n";
+                    };
+                    dump("diag", dg); dump("upper", up); dump("lower", lw);
+                }
+            }
             std::cout << "fields written to " << dir << "\n";
         }
         std::cout << "rho min/max: " << rmin << " " << rmax << "\nkernel launches: " << icsb200_launch_count(ctx) << "\nEnd\n";
