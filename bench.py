@@ -273,24 +273,40 @@ def main():
 
     # ---- end to end through host buffers (pinned), p,U,T in and out every step
     e2e = None
-    if not args.no_e2e and not multi:
+    if not args.no_e2e:
+        # every rank feeds its own partition from its own pinned buffers (iterate_host is collective like iterate: halo
+        # exchanges and reductions inside); wall clock between barriers, max over ranks
         st = ctx.state_get()
         Nc = ctx.mesh.n_cells
         hp = torch.empty(Nc, dtype=torch.float64).pin_memory()
         hU = torch.empty((Nc, 3), dtype=torch.float64).pin_memory()
         hT = torch.empty(Nc, dtype=torch.float64).pin_memory()
         hp.numpy()[:] = st["p"]; hU.numpy()[:] = st["U"]; hT.numpy()[:] = st["T"]
-        for _ in range(2):
-            ctx.iterate_host(ctl, hp.numpy(), hU.numpy(), hT.numpy())
         e_steps = max(3, args.steps // 2)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            ctx.iterate_host(ctl, hp.numpy(), hU.numpy(), hT.numpy())
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        e2e = {"value": N_total * e_steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 40 * Nc, "d2h_bytes_per_step": 40 * Nc,
+        e_err = None
+        try:
+            for _ in range(2):
+                ctx.iterate_host(ctl, hp.numpy(), hU.numpy(), hT.numpy())
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                ctx.iterate_host(ctl, hp.numpy(), hU.numpy(), hT.numpy())
+            barrier()
+            dt = time.perf_counter() - t0
+        except Exception as ex:      # reported, never silently replaced by the device-resident number
+            e_err, dt = str(ex), float("inf")
+        nbytes = 40 * Nc
+        if multi:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            b = torch.tensor([nbytes], device="cuda", dtype=torch.int64)
+            dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            nbytes = int(b.item())
+        e2e = {"value": N_total * e_steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                "steps": e_steps}
+        if e_err is not None or not np.isfinite(dt):
+            e2e = {"value": None, "unit": UNIT, "error": e_err or "failed on another rank"}
 
     if rank != 0:
         if multi:
