@@ -96,3 +96,22 @@ def test_compare_matrix_reads_openfoam_lists(tmp_path):
     assert np.array_equal(cm.read_list(str(a / "u")), np.tile([1.0, 2.0, 3.0], 5))
     assert cm.main([str(a), str(b)]) == 0
     assert cm.main([str(a), str(b), "--rtol", "1e-15"]) == 1
+
+
+def test_general_cluster_schedule_on_ldu_addressing():
+    """The clustered LU-SGS schedule built from owner / neighbour alone (structured and randomly renumbered meshes): intra-slab
+    dependencies strictly descend in level, cross-slab ones are `lag` steps old, and the replay equals the sequential sweep."""
+    from icsfoam_b200 import cases
+    m = _load("lusgs_cluster_schedule")
+    box = cases.onera_box(12).mesh
+    F = box.n_internal_faces
+    s = m.general_schedule(box.n_cells, box.owner[:F], box.neighbour, n_slabs=4, n_clusters=4, lag=2)
+    r = m.check_general(box.n_cells, box.owner[:F], box.neighbour, s)
+    assert r["global_levels"] == 3 * 12 - 2
+    # 4 slabs of thickness 3: (12 + 12 + 3 - 2) levels per slab, each slab starts lag + 1 steps behind its predecessor
+    assert list(s["depth"]) == [25] * 4 and list(s["off"]) == [0, 4, 8, 12] and r["chain"] == 25 + 12
+    scr = cases.scrambled_box(6).mesh
+    F = scr.n_internal_faces
+    s = m.general_schedule(scr.n_cells, scr.owner[:F], scr.neighbour, n_slabs=6, n_clusters=3, lag=3)
+    r = m.check_general(scr.n_cells, scr.owner[:F], scr.neighbour, s)
+    assert r["chain"] >= r["global_levels"] // 2
