@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DRIVER = os.path.join(ROOT, "icsfoam_b200", "host", "dbnsB200")
 MESHLIB = os.path.join(ROOT, "icsfoam_b200", "meshtools", "libicsmesh.so")
-STAGED = os.path.join(ROOT, "cases_local", "forwardStep")
+STAGED = os.path.join(ROOT, "cases_local", "VKI-LS89")
 
 
 def _load(path, name):
@@ -27,22 +27,22 @@ def _load(path, name):
     return mod
 
 
-@pytest.mark.skipif(not os.path.isdir(STAGED + "/system"), reason="forwardStep tutorial not staged (cases_local/ is not part of the repository)")
+@pytest.mark.skipif(not os.path.isdir(STAGED + "/system"), reason="VKI-LS89 tutorial not staged (cases_local/ is not part of the repository)")
 def test_write_flux_directory_matches_the_host_path(gpu_context, tmp_path):
     fd = _load(os.path.join(ROOT, "tools", "foamdiff.py"), "foamdiff")
     cm = _load(os.path.join(ROOT, "tools", "openfoam_golden", "compare_matrix.py"), "compare_matrix")
-    case_dir = str(tmp_path / "fs")
+    case_dir = str(tmp_path / "vki")
     shutil.copytree(STAGED, case_dir)
-    r = subprocess.run([DRIVER, case_dir, "-maxSteps", "1", "-writeFlux"], env=dict(os.environ, ICSMESH_LIB=MESHLIB), capture_output=True, text=True, timeout=600)
+    r = subprocess.run([DRIVER, case_dir, "-maxSteps", "2", "-writeFlux"], env=dict(os.environ, ICSMESH_LIB=MESHLIB), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "fields written to" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
     tdir = r.stdout.split("fields written to", 1)[1].split()[0]
-    case = cases.forward_step(STAGED + "/constant/polyMesh")
+    case = cases.vki_ls89(STAGED + "/constant/polyMesh")     # steady: one outer iteration per "time step" (same set-up as test_gpu_driver)
     g = case.apply(gpu_context())
     n_pseudo = sum(1 for ln in r.stdout.splitlines() if ln.startswith("pseudoTime: iteration"))
-    g.new_time_step()
+    assert n_pseudo == 2
     for it in range(n_pseudo):
         if it == n_pseudo - 1:
-            phi, phiUp, phiEp = g.calc_flux()
+            phi, phiUp, phiEp = g.calc_flux()        # the flux the last iteration starts from: what dbnsFoam's phi holds at write time
         g.iterate(case.controls)
     st = g.state_get()
     F = case.mesh.n_internal_faces
