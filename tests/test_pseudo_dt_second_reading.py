@@ -1,0 +1,50 @@
+"""A second, independent reading of the local pseudo time step (dbnsFoam/setCoAndDeltaT.H:45-145) in numpy against the oracle:
+lambda = interpolate(c) + |interpolate(U) . n| on the faces, the face-wise max of nonOrthDeltaCoeffs * lambda into both cells, the
+coupled-patch and the wall (half-weight, cell values) contributions, division by the pseudo-Courant field.  Same purpose as
+tests/test_flux_second_reading.py."""
+import numpy as np
+import pytest
+
+from icsfoam_b200 import capi, cases
+from oracle.pyoracle import Oracle
+
+
+def local_pseudo_dt(mesh, R, Cp, st, co):
+    F, N = mesh.n_internal_faces, mesh.n_cells
+    gamma = Cp / (Cp - R)
+    c = np.sqrt(gamma / (1.0 / (R * st["T"])))                   # sqrt(gamma / psi)
+    U = st["U"]
+    n = mesh.Sf / mesh.magSf[:, None]
+    own, nei, w = mesh.owner, mesh.neighbour, mesh.weights
+    lin = lambda f, P, Nb, wf: wf * P + (1.0 - wf) * Nb if P.ndim == 1 else wf[:, None] * P + (1.0 - wf)[:, None] * Nb
+    lam = lin(None, c[own[:F]], c[nei], w[:F]) + np.abs((lin(None, U[own[:F]], U[nei], w[:F]) * n[:F]).sum(1))
+    frdt = mesh.nonOrthDeltaCoeffs[:F] * lam
+    rdt = np.zeros(N)
+    np.maximum.at(rdt, own[:F], frdt)
+    np.maximum.at(rdt, nei, frdt)
+    for p in mesh.patches:
+        f = np.arange(p["start"], p["start"] + p["size"])
+        if p["size"] == 0:
+            continue
+        fc = own[f]
+        if p["kind"] == capi.CYCLIC:
+            q = mesh.patches[p["nbr_patch"]]
+            nb = own[np.arange(q["start"], q["start"] + q["size"])]             # patchNeighbourField: the cells across the pair
+            lam_b = lin(None, c[fc], c[nb], w[f]) + np.abs((lin(None, U[fc], U[nb], w[f]) * n[f]).sum(1))
+            np.maximum.at(rdt, fc, mesh.nonOrthDeltaCoeffs[f] * lam_b)
+        elif p["kind"] == capi.WALL:
+            np.maximum.at(rdt, fc, 0.5 * mesh.nonOrthDeltaCoeffs[f] * (c[fc] + np.abs((U[fc] * n[f]).sum(1))))
+    return rdt / co
+
+
+@pytest.mark.parametrize("make", [lambda: cases.onera_box(7), lambda: cases.bump(12, 9), lambda: cases.periodic_box(6, "ROE", "vanLeer", seed=3),
+                                  lambda: cases.scrambled_box(5, "HLLC", "vanLeer", seed=4)])
+def test_local_pseudo_time_step_second_reading(make):
+    case = make()
+    o = case.apply(Oracle())
+    o.calc_flux()
+    o.residual()
+    rdt, co = o.pseudo_dt()
+    assert np.all(co == case.schemes.pseudo_co_num)              # first iteration: no SER update yet
+    mine = local_pseudo_dt(case.mesh, case.R, case.Cp, o.state_get(), co)
+    assert np.allclose(rdt, mine, rtol=1e-13, atol=0.0)
