@@ -1,0 +1,68 @@
+"""A second, independent numpy reading of the laminar viscous residual (residualsUpdate.H:16-43) against the oracle, on the cells of
+an orthogonal box that are two layers away from every boundary (their stencil — Gauss gradients of the neighbours included —
+sees cell values only, and the non-orthogonal correction of `Gauss linear corrected` vanishes):
+tauMC = mu dev2(T(grad U)),  rhoUR += laplacian(mu, U) + div(tauMC),
+rhoER += div(((mu grad U)_f + tauMC_f) & U_f & Sf) + laplacian(alphaEff, eCalc)  with alphaEff = gamma mu / Pr (heThermo::alphaEff for an
+internal-energy thermo).
+Same purpose as tests/test_flux_second_reading.py."""
+import numpy as np
+import pytest
+
+from icsfoam_b200 import cases
+from oracle.pyoracle import Oracle
+
+
+def viscous_sources(mesh, st, mu, alpha):
+    F, N = mesh.n_internal_faces, mesh.n_cells
+    own, nei, w = mesh.owner[:F], mesh.neighbour, mesh.weights[:F]
+    Sf, magSf, dc, V = mesh.Sf[:F], mesh.magSf[:F], mesh.nonOrthDeltaCoeffs[:F], mesh.V
+    U = st["U"]
+    lin = lambda a: (w.reshape((-1,) + (1,) * (a.ndim - 1))) * a[own] + ((1 - w).reshape((-1,) + (1,) * (a.ndim - 1))) * a[nei]
+
+    def integrate(ff):                                   # sum of outward face values (internal faces only: deep-interior cells)
+        out = np.zeros((N,) + ff.shape[1:])
+        np.add.at(out, own, ff)
+        np.subtract.at(out, nei, ff)
+        return out
+
+    gradU = integrate(Sf[:, :, None] * lin(U)[:, None, :]) / V[:, None, None]          # (grad U)_ij = d_i U_j
+    tr = np.trace(gradU, axis1=1, axis2=2)
+    tauMC = mu * (np.swapaxes(gradU, 1, 2) - (2.0 / 3.0) * tr[:, None, None] * np.eye(3))
+    lapU = integrate((mu * magSf * dc)[:, None] * (U[nei] - U[own]))
+    div_tau = integrate(np.einsum("fi,fij->fj", Sf, lin(tauMC)))
+    rhoUR = lapU + div_tau
+    sigma = mu * lin(gradU) + lin(tauMC)
+    sigma_dot_u = np.einsum("fij,fj->fi", sigma, lin(U))
+    e = st["rhoE"] / st["rho"] - 0.5 * (U * U).sum(1)
+    rhoER = integrate((sigma_dot_u * Sf).sum(1)) + integrate(alpha * magSf * dc * (e[nei] - e[own]))
+    return rhoUR, rhoER
+
+
+@pytest.mark.parametrize("flux,seed", [("ROE", 31), ("HLLC", 32)])
+def test_viscous_residual_second_reading(flux, seed):
+    mu, Pr = 0.07, 0.9
+    visc = cases.periodic_box(8, flux, "vanLeer", seed=seed, mu=mu, Pr=Pr)
+    invisc = cases.periodic_box(8, flux, "vanLeer", seed=seed)
+    mesh = visc.mesh
+    out = []
+    for case in (visc, invisc):
+        o = case.apply(Oracle())
+        o.calc_flux()
+        out.append((o.residual(), o.state_get()))
+    (sv, st), (si, _) = out
+    assert np.array_equal(sv[0], si[0])                                  # the continuity source has no viscous part
+    F = mesh.n_internal_faces
+    layer = np.zeros(mesh.n_cells, bool)
+    layer[mesh.owner[F:]] = True
+    near = layer.copy()
+    near[mesh.owner[:F][layer[mesh.neighbour]]] = True
+    near[mesh.neighbour[layer[mesh.owner[:F]]]] = True
+    deep = np.flatnonzero(~near)
+    assert len(deep) >= 27
+    assert np.allclose(mesh.nonOrthDeltaCoeffs[:F], mesh.deltaCoeffs[:F], rtol=1e-12)          # orthogonal: no correction term
+    gamma = visc.Cp / (visc.Cp - visc.R)
+    rhoUR, rhoER = viscous_sources(mesh, st, mu, gamma * (mu / Pr))
+    got_U, got_E = sv[1] - si[1], sv[2] - si[2]
+    assert np.abs(got_U[deep]).max() > 0 and np.abs(got_E[deep]).max() > 0
+    assert np.abs(got_U[deep] - rhoUR[deep]).max() <= 1e-10 * np.abs(sv[1]).max()
+    assert np.abs(got_E[deep] - rhoER[deep]).max() <= 1e-10 * np.abs(sv[2]).max()
