@@ -82,3 +82,84 @@ def test_jacobian_second_reading(make):
         assert np.abs(u[f] - mu[f]).max() <= 1e-12 * scale, ("upper", b)
         assert np.abs(l[f] - ml[f]).max() <= 1e-12 * scale, ("lower", b)
         assert np.abs(d[cells] - md[cells]).max() <= 1e-12 * scale, ("diag", b)
+
+
+def boundary_terms(mesh, st, R, Cp):
+    """convectiveFluxScheme::boundaryJacobian + addBoundaryTerms (convectiveFluxScheme.C:47-120,219-352) for patches whose p, U, T are
+    all zeroGradient (valueInternalCoeffs = 1, boundary values = cell values), plus the dissipation block's boundary part
+    (blockFvMatrix.C:300-320, physical patches included).  -> {block: diag contribution (N, nc)}"""
+    F, N = mesh.n_internal_faces, mesh.n_cells
+    fc = mesh.owner[F:]
+    Sf, magSf = mesh.Sf[F:], mesh.magSf[F:]
+    cv, g = Cp - R, Cp / (Cp - R)
+    rho, U, p, T, rhoE = st["rho"][fc], st["U"][fc], st["p"][fc], st["T"][fc], st["rhoE"][fc]
+    V = lambda a: a[:, None]
+    outer = lambda a, b: a[:, :, None] * b[:, None, :]
+    one = np.ones_like(U)
+    UdS = (U * Sf).sum(1)
+    dCp, dCU, dCT = rho / p * UdS, V(rho) * Sf * one, -rho / T * UdS
+    dMp = V(rho / p * UdS) * U + Sf
+    dMU = V(rho)[:, :, None] * outer(U, Sf * one) + (rho * UdS)[:, None, None] * np.eye(3)[None] * one[:, :, None]
+    dMT = V(-rho / T * UdS) * U
+    dEp = rhoE / p * UdS + UdS
+    dEU = Sf * one * V(rhoE + p) + V(rho * UdS) * U * one
+    dET = UdS * (rho * cv - rhoE / T)
+    magU2 = (U * U).sum(1)
+    dPdRho, dUdRho, dTdRho = 0.5 * (g - 1) * magU2, -U / V(rho), -1.0 / (cv * rho) * (rhoE / rho - magU2)
+    dPdRhoU, dUdRhoU, dTdRhoU = -(g - 1) * U, 1.0 / rho, -U / V(cv * rho)
+    dPdRhoE, dTdRhoE = (g - 1) * np.ones_like(rho), 1.0 / (cv * rho)
+    Tv = lambda M, v: np.einsum("fij,fj->fi", M, v)
+    dot = lambda a, b: (a * b).sum(1)
+    face = {
+        0: dCp * dPdRho + dot(dCU, dUdRho) + dCT * dTdRho,
+        4: V(dCp) * dPdRhoU + dCU * V(dUdRhoU) + V(dCT) * dTdRhoU,
+        1: dCp * dPdRhoE + dCT * dTdRhoE,
+        6: dMp * V(dPdRho) + Tv(dMU, dUdRho) + dMT * V(dTdRho),
+        8: outer(dMp, dPdRhoU) + dMU * dUdRhoU[:, None, None] + outer(dMT, dTdRhoU),
+        7: dMp * V(dPdRhoE) + dMT * V(dTdRhoE),
+        2: dEp * dPdRho + dot(dEU, dUdRho) + dET * dTdRho,
+        5: V(dEp) * dPdRhoU + dEU * V(dUdRhoU) + V(dET) * dTdRhoU,
+        3: dEp * dPdRhoE + dET * dTdRhoE,
+    }
+    lam = np.sqrt(g * R * T) + np.abs(UdS / magSf)
+    for b in (0, 3):
+        face[b] = face[b] + 0.5 * magSf * lam
+    face[8] = face[8] + (0.5 * magSf * lam)[:, None, None] * np.eye(3)[None]
+    out = {}
+    for b, v in face.items():
+        acc = np.zeros((N,) + v.shape[1:])
+        np.add.at(acc, fc, v)
+        out[b] = acc.reshape(N, -1)
+    # dSByS(0,1): its two terms cancel analytically for a perfect gas ((gamma - 1) rho / p = 1 / (cv T)); what is left is rounding
+    out["term_scale_1"] = np.abs(dCp * dPdRhoE).max()
+    return out
+
+
+def test_jacobian_second_reading_with_zero_gradient_boundaries():
+    """every patch zeroGradient in p, U, T: the limited states of ALL faces follow from cell values, so every cell's diagonal —
+    boundary terms included — is checked."""
+    from icsfoam_b200 import meshtools as mt
+    mesh = mt.structured(1, 6, 5, 4, 0, (0, 0, 0), (1.2, 1.0, 0.8), patch_kinds=(capi.PATCH,) * 6)
+    rng = np.random.default_rng(12)
+    N = mesh.n_cells
+    p = 1e5 * (1 + 0.1 * rng.random(N))
+    T = 300.0 * (1 + 0.1 * rng.random(N))
+    U = np.column_stack([150.0 + 40 * rng.random(N), 30 * rng.standard_normal(N), 30 * rng.standard_normal(N)])
+    names = [q["name"] for q in mesh.patches]
+    bcs = {nm: {"p": ("zeroGradient", ()), "U": ("zeroGradient", ()), "T": ("zeroGradient", ())} for nm in names}
+    case = cases.Case("zg", mesh, 287.0, 1005.0, capi.default_schemes(flux_scheme="HLLC"), capi.solver_controls(), bcs, p, U, T)
+    o = case.apply(Oracle())
+    o.calc_flux(); o.residual(); rdt, _ = o.pseudo_dt(); o.assemble()
+    st = o.state_get()
+    s = face_states(o, case, case.schemes.limiter_U)
+    mine = second_reading(mesh, s, st, case.R, case.Cp, rdt)
+    bnd = boundary_terms(mesh, st, case.R, case.Cp)
+    for b in range(9):
+        d, u, l = o.matrix_get_ldu(b)
+        md, mu, ml = mine[b]
+        scale = max(np.abs(d).max(), np.abs(u).max(), np.abs(l).max())
+        if b == 1:
+            scale = bnd["term_scale_1"]
+            assert np.abs(d).max() <= 1e-12 * scale
+        assert np.abs(u - mu).max() <= 1e-12 * scale and np.abs(l - ml).max() <= 1e-12 * scale, b
+        assert np.abs(d - (md + bnd[b])).max() <= 1e-12 * scale, ("diag", b, np.abs(d - (md + bnd[b])).max() / scale)
