@@ -7,7 +7,10 @@
 // PARITY UNPINNED: the reference ships no golden vectors and cannot be compiled here (OpenFOAM v2112
 // is absent — SURVEY.md §0.9/§8c).  The arithmetic that lives in OpenFOAM itself (Gauss gradient, NVD/TVD
 // limited interpolation, thermo, boundary conditions, LduMatrix) is restated from SURVEY.md Appendix A
-// and pinned only by the analytic known-answer tests in tests/test_oracle_*.py.
+// and pinned only by the analytic known-answer tests in tests/test_oracle_*.py; the formulas that live in /root/reference
+// itself (flux schemes, Jacobian, pseudo time step, residual / update, viscous residual, GMRES + preconditioners) are
+// cross-checked against independent numpy second readings (tests/test_*_second_reading.py).  How to pin it against a real
+// ICSFoam build: tools/openfoam_golden/README.md.
 #pragma once
 #include <array>
 #include <cmath>
