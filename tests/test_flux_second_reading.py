@@ -38,8 +38,8 @@ def face_states(o, case, lim):
     return out
 
 
-def hllc(s, Sf, magSf):
-    """hllcFluxScheme.C:70-240 (static mesh, MRFFaceVelocity = 0)"""
+def hllc(s, Sf, magSf, mrf=0.0):
+    """hllcFluxScheme.C:70-240 (static mesh; mrf = MRFFaceVelocity per face)"""
     n = Sf / magSf[:, None]
     dot = lambda a, b: (a * b).sum(1)
     rho_l, rho_r, p_l, p_r, U_l, U_r = s["rho_l"], s["rho_r"], s["p_l"], s["p_r"], s["U_l"], s["U_r"]
@@ -48,7 +48,7 @@ def hllc(s, Sf, magSf):
     uAvg = (coefR[:, None] * U_r + U_l) / (coefR + 1.0)[:, None]
     HAvg = (coefR * H_r + H_l) / (coefR + 1.0)
     cAvg = np.sqrt(np.abs((s["gamma"] - 1.0) * (HAvg - 0.5 * dot(uAvg, uAvg))))
-    uMag_l, uMag_r, uMagAvg = dot(U_l, n), dot(U_r, n), dot(uAvg, n)
+    uMag_l, uMag_r, uMagAvg = dot(U_l, n) - mrf, dot(U_r, n) - mrf, dot(uAvg, n) - mrf
     Sl = np.minimum(uMag_l - c_l, uMagAvg - cAvg)
     Sr = np.maximum(uMag_r + c_r, uMagAvg + cAvg)
     Sm = (rho_r * uMag_r * (Sr - uMag_r) - rho_l * uMag_l * (Sl - uMag_l) + p_l - p_r) / (rho_r * (Sr - uMag_r) - rho_l * (Sl - uMag_l))
@@ -71,13 +71,13 @@ def hllc(s, Sf, magSf):
              + V(coefSr) * (V(rho_r * uMag_r) * U_r + V(p_r) * n)) * V(magSf)
     rhoEStar_l = 1.0 / (Sl - Sm) * ((Sl - uMag_l) * (rho_l * E_l) - p_l * uMag_l + pStar_l * Sm)
     rhoEStar_r = 1.0 / (Sr - Sm) * ((Sr - uMag_r) * (rho_r * E_r) - p_r * uMag_r + pStar_r * Sm)
-    fluxRhoEStar_l = Sm * (rhoEStar_l + pStar_l)
-    fluxRhoEStar_r = Sm * (rhoEStar_r + pStar_r)
+    fluxRhoEStar_l = Sm * (rhoEStar_l + pStar_l) + pStar_l * mrf
+    fluxRhoEStar_r = Sm * (rhoEStar_r + pStar_r) + pStar_r * mrf
     phiEp = (coefSl * rho_l * H_l * uMag_l + coefSlm * fluxRhoEStar_l + coefSmr * fluxRhoEStar_r + coefSr * rho_r * H_r * uMag_r) * magSf
     return phi, phiUp, phiEp
 
 
-def roe(s, Sf, magSf, entropy_fix):
+def roe(s, Sf, magSf, entropy_fix, mrf=0.0):
     """roeFluxScheme.C:276-409 with getRoeDissipation :41-241 (P |Lambda| P^-1 assembled block by block as there)"""
     n = Sf / magSf[:, None]
     dot = lambda a, b: (a * b).sum(1)
@@ -92,7 +92,7 @@ def roe(s, Sf, magSf, entropy_fix):
     Hroe = (coefR * H_r + H_l) / (coefR + 1.0)
     a1 = s["gamma"] - 1.0
     c = np.sqrt(np.abs(a1 * (Hroe - 0.5 * dot(u, u))))
-    uMag_l, uMag_r, un = dot(U_l, n), dot(U_r, n), dot(u, n)
+    uMag_l, uMag_r, un = dot(U_l, n), dot(U_r, n), dot(u, n) - mrf             # only uProjRoe is made relative (roeFluxScheme.C:355-367)
     # getRoeDissipation
     theta = 0.5 * a1 * dot(u, u)
     c2 = c * c
@@ -149,15 +149,18 @@ def roe(s, Sf, magSf, entropy_fix):
     phi = phi + 0.5 * magSf * (rn_l + rn_r)
     phiUp = phiUp + 0.5 * V(magSf) * (V(rn_l) * U_l + V(rn_r) * U_r + n * V(p_l + p_r))
     phiEp = phiEp + 0.5 * magSf * (rn_l * H_l + rn_r * H_r)
+    phi = phi - 0.5 * magSf * mrf * (rho_l + rho_r)
+    phiUp = phiUp - 0.5 * V(magSf * mrf) * (rhoU_l + rhoU_r)
+    phiEp = phiEp - 0.5 * magSf * mrf * (rhoE_l + rhoE_r)
     return phi, phiUp, phiEp
 
 
-def ausm_plus_up(s, Sf, magSf, low_mach):
+def ausm_plus_up(s, Sf, magSf, low_mach, mrf=0.0):
     """ausmPlusUpFluxScheme.C:73-299 (beta = 1/8, alpha = 3/16, Kp = 0.25, Ku = 0.25 as coded there)"""
     dot = lambda a, b: (a * b).sum(1)
     V = lambda a: a[:, None]
     U_L, U_R = s["U_l"], s["U_r"]
-    un_L, un_R = dot(U_L, Sf) / magSf, dot(U_R, Sf) / magSf
+    un_L, un_R = dot(U_L, Sf) / magSf - mrf, dot(U_R, Sf) / magSf - mrf
     c_L, c_R = s["cCrit_l"], s["cCrit_r"]
     c_L = c_L * c_L / np.maximum(c_L, un_L)
     c_R = c_R * c_R / np.maximum(c_R, -un_R)
@@ -183,7 +186,7 @@ def ausm_plus_up(s, Sf, magSf, low_mach):
     rhoa = M12 * c_f * np.where(left, rho_L, rho_R)
     phi = rhoa * magSf
     phiUp = V(rhoa) * np.where(V(left), U_L, U_R) * V(magSf) + V(p12) * Sf
-    phiEp = rhoa * np.where(left, s["H_l"], s["H_r"]) * magSf
+    phiEp = rhoa * np.where(left, s["H_l"], s["H_r"]) * magSf + p12 * mrf * magSf
     return phi, phiUp, phiEp
 
 
@@ -237,3 +240,21 @@ def test_second_reading_covers_every_branch():
             for a, b in zip(mine, ref):
                 scale = np.abs(b[f]).max()
                 assert np.abs(a[f] - b[f]).max() <= 1e-12 * scale, (flux, vel)
+
+
+@pytest.mark.parametrize("flux", ["HLLC", "ROE", "AUSMPlusUp"])
+def test_second_reading_in_a_rotating_and_translating_frame(flux):
+    """MRFFaceVelocity enters hllcFluxScheme.C:157-161,217-218, roeFluxScheme.C:366-367,402-408, ausmPlusUpFluxScheme.C:104-105,294"""
+    case = cases.periodic_box(7, flux, "vanLeer", seed=17).with_mrf((30.0, -50.0, 80.0), (0.3, 0.5, -0.2), (20.0, 5.0, -10.0))
+    o = case.apply(Oracle())
+    ref = o.calc_flux()
+    s = face_states(o, case, capi.LIM_VANLEER)
+    mesh = case.mesh
+    mrf = case.mrf_fields(mesh)[0]
+    assert np.abs(mrf).max() > 10.0
+    mine = {"HLLC": lambda: hllc(s, mesh.Sf, mesh.magSf, mrf), "ROE": lambda: roe(s, mesh.Sf, mesh.magSf, case.schemes.entropy_fix_coeff, mrf),
+            "AUSMPlusUp": lambda: ausm_plus_up(s, mesh.Sf, mesh.magSf, bool(case.schemes.low_mach_ausm), mrf)}[flux]()
+    f = interior_faces(mesh)
+    for a, b in zip(mine, ref):
+        scale = np.abs(b[f]).max()
+        assert np.abs(a[f] - b[f]).max() <= 1e-12 * scale, flux

@@ -10,7 +10,7 @@ from oracle.pyoracle import Oracle
 from tests.test_flux_second_reading import face_states, interior_faces
 
 
-def second_reading(mesh, s, st, R, Cp, rdt):
+def second_reading(mesh, s, st, R, Cp, rdt, mrf=None, omega=None):
     """-> {block: (diag contribution per cell, upper, lower)} with blocks numbered as icsb200_matrix_get_ldu"""
     F, N = mesh.n_internal_faces, mesh.n_cells
     own, nei = mesh.owner[:F], mesh.neighbour
@@ -31,7 +31,8 @@ def second_reading(mesh, s, st, R, Cp, rdt):
                      2: proj * (theta - a1), 5: n * V(a1) - a2 * U * V(proj), 3: g * proj}
     c = np.sqrt(g * R * st["T"])
     w = mesh.weights[:F]
-    lam = (w * c[own] + (1 - w) * c[nei]) + np.abs(((V(w) * st["U"][own] + V(1 - w) * st["U"][nei]) * n).sum(1))
+    mrf = np.zeros(F) if mrf is None else mrf[:F]
+    lam = (w * c[own] + (1 - w) * c[nei]) + np.abs(((V(w) * st["U"][own] + V(1 - w) * st["U"][nei]) * n).sum(1) - mrf)
     out = {}
     shape = {0: (), 1: (), 2: (), 3: (), 4: (3,), 5: (3,), 6: (3,), 7: (3,), 8: (3, 3)}
     for b, sh in shape.items():
@@ -52,6 +53,18 @@ def second_reading(mesh, s, st, R, Cp, rdt):
             np.add.at(diag, own, dd)
             np.add.at(diag, nei, dd)
             diag += (rdt * mesh.V)[ex] * (eye if b == 8 else 1.0)
+            # fvj::div(w, MRFFaceVelocity magSf) subtracted (convectiveFluxScheme.C:477-481, blockFvOperatorsTemplates.C:146-200)
+            sf = (mrf * magSf)[ex] * (eye if b == 8 else 1.0)
+            upper -= sf * (1 - w)[ex]
+            lower += sf * w[ex]
+            np.subtract.at(diag, own, sf * w[ex])
+            np.add.at(diag, nei, sf * (1 - w)[ex])
+        if b == 8 and omega is not None:                     # addMRFSource: diag += V [omega x] (convectiveFluxScheme.C:123-139)
+            K = np.zeros((N, 3, 3))
+            K[:, 0, 1], K[:, 0, 2] = -omega[:, 2], omega[:, 1]
+            K[:, 1, 0], K[:, 1, 2] = omega[:, 2], -omega[:, 0]
+            K[:, 2, 0], K[:, 2, 1] = -omega[:, 1], omega[:, 0]
+            diag += mesh.V[:, None, None] * K
         out[b] = (diag.reshape(N, -1), upper.reshape(F, -1), lower.reshape(F, -1))
     return out
 
@@ -163,3 +176,25 @@ def test_jacobian_second_reading_with_zero_gradient_boundaries():
             assert np.abs(d).max() <= 1e-12 * scale
         assert np.abs(u - mu).max() <= 1e-12 * scale and np.abs(l - ml).max() <= 1e-12 * scale, b
         assert np.abs(d - (md + bnd[b])).max() <= 1e-12 * scale, ("diag", b, np.abs(d - (md + bnd[b])).max() / scale)
+
+
+def test_jacobian_second_reading_in_a_rotating_frame():
+    case = cases.periodic_box(7, "HLLC", "vanLeer", seed=23).with_mrf((30.0, -50.0, 80.0), (0.3, 0.5, -0.2), (20.0, 5.0, -10.0))
+    o = case.apply(Oracle())
+    o.calc_flux(); o.residual(); rdt, _ = o.pseudo_dt(); o.assemble()
+    mesh = case.mesh
+    s = face_states(o, case, case.schemes.limiter_U)
+    fv, om = case.mrf_fields(mesh)
+    mine = second_reading(mesh, s, o.state_get(), case.R, case.Cp, rdt, mrf=fv, omega=om)
+    f = interior_faces(mesh)
+    F = mesh.n_internal_faces
+    touches = np.zeros(mesh.n_cells, bool)
+    touches[mesh.owner[F:]] = True
+    cells = np.flatnonzero(~touches)
+    for b in (0, 2, 3, 4, 5, 6, 7, 8):
+        d, u, l = o.matrix_get_ldu(b)
+        md, mu, ml = mine[b]
+        scale = max(np.abs(d).max(), np.abs(u).max(), np.abs(l).max())
+        assert np.abs(u[f] - mu[f]).max() <= 1e-12 * scale, ("upper", b)
+        assert np.abs(l[f] - ml[f]).max() <= 1e-12 * scale, ("lower", b)
+        assert np.abs(d[cells] - md[cells]).max() <= 1e-12 * scale, ("diag", b)

@@ -9,7 +9,7 @@ from icsfoam_b200 import capi, cases
 from oracle.pyoracle import Oracle
 
 
-def local_pseudo_dt(mesh, R, Cp, st, co):
+def local_pseudo_dt(mesh, R, Cp, st, co, mrf=None):
     F, N = mesh.n_internal_faces, mesh.n_cells
     gamma = Cp / (Cp - R)
     c = np.sqrt(gamma / (1.0 / (R * st["T"])))                   # sqrt(gamma / psi)
@@ -17,7 +17,8 @@ def local_pseudo_dt(mesh, R, Cp, st, co):
     n = mesh.Sf / mesh.magSf[:, None]
     own, nei, w = mesh.owner, mesh.neighbour, mesh.weights
     lin = lambda f, P, Nb, wf: wf * P + (1.0 - wf) * Nb if P.ndim == 1 else wf[:, None] * P + (1.0 - wf)[:, None] * Nb
-    lam = lin(None, c[own[:F]], c[nei], w[:F]) + np.abs((lin(None, U[own[:F]], U[nei], w[:F]) * n[:F]).sum(1))
+    mrf = np.zeros(mesh.n_faces) if mrf is None else mrf
+    lam = lin(None, c[own[:F]], c[nei], w[:F]) + np.abs((lin(None, U[own[:F]], U[nei], w[:F]) * n[:F]).sum(1) - mrf[:F])
     frdt = mesh.nonOrthDeltaCoeffs[:F] * lam
     rdt = np.zeros(N)
     np.maximum.at(rdt, own[:F], frdt)
@@ -30,10 +31,10 @@ def local_pseudo_dt(mesh, R, Cp, st, co):
         if p["kind"] == capi.CYCLIC:
             q = mesh.patches[p["nbr_patch"]]
             nb = own[np.arange(q["start"], q["start"] + q["size"])]             # patchNeighbourField: the cells across the pair
-            lam_b = lin(None, c[fc], c[nb], w[f]) + np.abs((lin(None, U[fc], U[nb], w[f]) * n[f]).sum(1))
+            lam_b = lin(None, c[fc], c[nb], w[f]) + np.abs((lin(None, U[fc], U[nb], w[f]) * n[f]).sum(1) - mrf[f])
             np.maximum.at(rdt, fc, mesh.nonOrthDeltaCoeffs[f] * lam_b)
         elif p["kind"] == capi.WALL:
-            np.maximum.at(rdt, fc, 0.5 * mesh.nonOrthDeltaCoeffs[f] * (c[fc] + np.abs((U[fc] * n[f]).sum(1))))
+            np.maximum.at(rdt, fc, 0.5 * mesh.nonOrthDeltaCoeffs[f] * (c[fc] + np.abs((U[fc] * n[f]).sum(1) - mrf[f])))
     return rdt / co
 
 
@@ -48,3 +49,16 @@ def test_local_pseudo_time_step_second_reading(make):
     assert np.all(co == case.schemes.pseudo_co_num)              # first iteration: no SER update yet
     mine = local_pseudo_dt(case.mesh, case.R, case.Cp, o.state_get(), co)
     assert np.allclose(rdt, mine, rtol=1e-13, atol=0.0)
+
+
+def test_local_pseudo_time_step_in_a_rotating_frame():
+    for make in (lambda: cases.periodic_box(6, "ROE", "vanLeer", seed=3), lambda: cases.bump(12, 9)):
+        case = make().with_mrf((0.0, 0.0, 120.0), (0.5, 0.6, 0.0), (20.0, 5.0, -10.0))
+        o = case.apply(Oracle())
+        o.calc_flux()
+        o.residual()
+        rdt, co = o.pseudo_dt()
+        fv = case.mrf_fields(case.mesh)[0]
+        mine = local_pseudo_dt(case.mesh, case.R, case.Cp, o.state_get(), co, fv)
+        plain = local_pseudo_dt(case.mesh, case.R, case.Cp, o.state_get(), co)
+        assert np.allclose(rdt, mine, rtol=1e-13, atol=0.0) and not np.allclose(rdt, plain, rtol=1e-6)
