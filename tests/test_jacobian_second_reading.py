@@ -198,3 +198,76 @@ def test_jacobian_second_reading_in_a_rotating_frame():
         assert np.abs(u[f] - mu[f]).max() <= 1e-12 * scale, ("upper", b)
         assert np.abs(l[f] - ml[f]).max() <= 1e-12 * scale, ("lower", b)
         assert np.abs(d[cells] - md[cells]).max() <= 1e-12 * scale, ("diag", b)
+
+
+def viscous_jacobian(mesh, st, mu, alpha, full):
+    """viscousFluxScheme::addFluxTerms (viscousFluxScheme.C:218-262) with fvj::laplacian (blockFvOperatorsTemplates.C:387-450): the
+    contributions SUBTRACTED from the blocks, constant muEff / alphaEff.  -> {block: (diag, upper, lower)} to add to the inviscid part"""
+    F, N = mesh.n_internal_faces, mesh.n_cells
+    own, nei, w = mesh.owner[:F], mesh.neighbour, mesh.weights[:F]
+    rho, U = st["rho"], st["U"]
+    E = st["rhoE"] / rho
+    out = {}
+
+    def lap(sf_face, vf, b, tensor_I=False):
+        sf2 = sf_face * mesh.magSf[:F] * mesh.deltaCoeffs[:F]
+        ex = (slice(None),) + (None,) * (vf.ndim - 1)
+        upp, low = vf[nei] * sf2[ex], vf[own] * sf2[ex]
+        diag = np.zeros((N,) + vf.shape[1:])
+        np.subtract.at(diag, own, low)
+        np.subtract.at(diag, nei, upp)
+        if tensor_I:
+            I = np.eye(3)[None]
+            upp, low, diag = upp[:, None, None] * I, low[:, None, None] * I, diag[:, None, None] * I
+        d0, u0, l0 = out.get(b, (0.0, 0.0, 0.0))
+        out[b] = (d0 - diag.reshape(N, -1), u0 - upp.reshape(F, -1), l0 - low.reshape(F, -1))     # block -= laplacian
+
+    if not full:
+        rho_f = w * rho[own] + (1 - w) * rho[nei]
+        lam = 0.5 * (mu + alpha) / rho_f
+        one = np.ones(N)
+        lap(lam, one, 0)
+        lap(lam, one, 8, tensor_I=True)
+        lap(lam, one, 3)
+    else:
+        muf, alf = np.full(F, mu), np.full(F, alpha)
+        lap(muf, -U / rho[:, None], 6)
+        lap(muf, 1.0 / rho, 8, tensor_I=True)
+        lap(alf, -E / rho + (U * U).sum(1) / rho, 2)
+        lap(alf, -U / rho[:, None], 5)
+        lap(alf, 1.0 / rho, 3)
+    return out
+
+
+@pytest.mark.parametrize("full", [False, True])
+def test_viscous_jacobian_second_reading(full):
+    mu, Pr = 0.06, 0.8
+    case = cases.periodic_box(7, "ROE", "vanLeer", seed=27, mu=mu, Pr=Pr)
+    case.schemes.viscous_full_jacobian = int(full)
+    o = case.apply(Oracle())
+    o.calc_flux(); o.residual(); rdt, _ = o.pseudo_dt(); o.assemble()
+    mesh = case.mesh
+    st = o.state_get()
+    s = face_states(o, case, case.schemes.limiter_U)
+    inv = second_reading(mesh, s, st, case.R, case.Cp, rdt)
+    gamma = case.Cp / (case.Cp - case.R)
+    visc = viscous_jacobian(mesh, st, mu, gamma * (mu / Pr), full)
+    f = interior_faces(mesh)
+    F = mesh.n_internal_faces
+    touches = np.zeros(mesh.n_cells, bool)
+    touches[mesh.owner[F:]] = True
+    cells = np.flatnonzero(~touches)
+    assert np.allclose(mesh.nonOrthDeltaCoeffs[:F], mesh.deltaCoeffs[:F], rtol=1e-12)
+    changed = 0
+    for b in (0, 2, 3, 4, 5, 6, 7, 8):
+        d, u, l = o.matrix_get_ldu(b)
+        md, mu_, ml = inv[b]
+        if b in visc:
+            vd, vu, vl = visc[b]
+            changed += int(np.abs(vu).max() > 1e-6 * np.abs(u).max())
+            md, mu_, ml = md + vd, mu_ + vu, ml + vl
+        scale = max(np.abs(d).max(), np.abs(u).max(), np.abs(l).max())
+        assert np.abs(u[f] - mu_[f]).max() <= 1e-12 * scale, ("upper", b)
+        assert np.abs(l[f] - ml[f]).max() <= 1e-12 * scale, ("lower", b)
+        assert np.abs(d[cells] - md[cells]).max() <= 1e-12 * scale, ("diag", b)
+    assert changed >= 3
