@@ -62,3 +62,54 @@ def test_local_pseudo_time_step_in_a_rotating_frame():
         mine = local_pseudo_dt(case.mesh, case.R, case.Cp, o.state_get(), co, fv)
         plain = local_pseudo_dt(case.mesh, case.R, case.Cp, o.state_get(), co)
         assert np.allclose(rdt, mine, rtol=1e-13, atol=0.0) and not np.allclose(rdt, plain, rtol=1e-6)
+
+
+def test_switched_evolution_relaxation_second_reading():
+    """setCoAndDeltaT.H:1-35: from the third outer iteration on, Co *= clip(|res_{k-2}| / |res_{k-1}|, minDecr, maxIncr), clipped to
+    [CoMin, CoMax], with |res| the 2-norm of the (rho, rhoE, |rhoU|) initial residuals of the linear solves."""
+    case = cases.onera_box(6)
+    sc = case.schemes
+    sc.pseudo_co_num, sc.pseudo_co_num_max, sc.pseudo_co_num_min = 5.0, 12.0, 0.5
+    o = case.apply(Oracle())
+    norms, seen = [], []
+    for k in range(7):
+        o.calc_flux(); o.residual(); _, co = o.pseudo_dt(); o.assemble()
+        _, res = o.solve_delta(case.controls)
+        o.update_fields()
+        assert co.min() == co.max()
+        seen.append(co.max())
+        norms.append(np.sqrt(res.s_init[0] ** 2 + res.s_init[1] ** 2 + sum(v * v for v in res.v_init)))
+    co, want = 5.0, []
+    for k in range(7):
+        if k >= 2:
+            ratio = max(min(norms[k - 2] / norms[k - 1], sc.pseudo_co_num_max_incr), sc.pseudo_co_num_min_decr)
+            co = max(min(co * ratio, sc.pseudo_co_num_max), sc.pseudo_co_num_min)
+        want.append(co)
+    assert np.allclose(seen, want, rtol=1e-13) and seen[2] > seen[1] and seen[-1] == 12.0
+
+
+def test_global_pseudo_time_step_second_reading():
+    """localTimestepping false: rPseudoDeltaT = max(deltaCoeffs * lambda) / pseudoCoNum over all faces (setCoAndDeltaT.H:147-151); on
+    a box whose patches are all zeroGradient the boundary values of c and U are the cell values."""
+    from icsfoam_b200 import meshtools as mt
+    mesh = mt.structured(1, 6, 5, 4, 0, (0, 0, 0), (1.2, 1.0, 0.8), patch_kinds=(capi.PATCH,) * 6)
+    rng = np.random.default_rng(12)
+    N = mesh.n_cells
+    p, T = 1e5 * (1 + 0.1 * rng.random(N)), 300.0 * (1 + 0.1 * rng.random(N))
+    U = np.column_stack([150.0 + 40 * rng.random(N), 30 * rng.standard_normal(N), 30 * rng.standard_normal(N)])
+    bcs = {q["name"]: {"p": ("zeroGradient", ()), "U": ("zeroGradient", ()), "T": ("zeroGradient", ())} for q in mesh.patches}
+    sch = capi.default_schemes(flux_scheme="HLLC", local_timestepping=0, pseudo_co_num=3.0)
+    case = cases.Case("zg", mesh, 287.0, 1005.0, sch, capi.solver_controls(), bcs, p, U, T)
+    o = case.apply(Oracle())
+    o.calc_flux(); o.residual()
+    rdt, _ = o.pseudo_dt()
+    st = o.state_get()
+    F = mesh.n_internal_faces
+    g = case.Cp / (case.Cp - case.R)
+    c = np.sqrt(g * case.R * st["T"])
+    n = mesh.Sf / mesh.magSf[:, None]
+    own, nei, w = mesh.owner, mesh.neighbour, mesh.weights
+    lam_i = (w[:F] * c[own[:F]] + (1 - w[:F]) * c[nei]) + np.abs(((w[:F, None] * st["U"][own[:F]] + (1 - w[:F, None]) * st["U"][nei]) * n[:F]).sum(1))
+    lam_b = c[own[F:]] + np.abs((st["U"][own[F:]] * n[F:]).sum(1))
+    want = max((mesh.deltaCoeffs[:F] * lam_i).max(), (mesh.deltaCoeffs[F:] * lam_b).max()) / 3.0
+    assert rdt.min() == rdt.max() and np.isclose(rdt[0], want, rtol=1e-13)
