@@ -57,14 +57,47 @@ def main_hb(rank, world, local, ids):
     sys.exit(0 if int(flag.item()) == 1 else 1)
 
 
-def main_vki(rank, world, local, ids):
+def decomposed_case(rank, world):
+    """A warped hex box written as an OpenFOAM case and decomposed into processor<r> directories in decomposePar's layout
+    (icsfoam_b200/meshtools/foamcase.py); every rank reads the directories back (variant "decomposed", not in the round-1 test list:
+    added after the last multi-GPU call of the round)."""
+    import tempfile
+    from icsfoam_b200.meshtools import foamcase, read_polymesh
+    box = [tempfile.mkdtemp(prefix="icsb200_decomposed_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    case_dir = box[0]
+    pts, faces, own, nei, patches = foamcase.box_polymesh(10, 8, 6, lo=(-1.0, 0.0, 0.0), hi=(2.0, 1.5, 1.0), warp=0.15)
+    if rank == 0:
+        foamcase.write_polymesh(os.path.join(case_dir, "constant", "polyMesh"), pts, faces, own, nei, patches)
+    dist.barrier()
+    whole = read_polymesh(os.path.join(case_dir, "constant", "polyMesh"))
+    if rank == 0:
+        order = np.argsort(whole.C[:, 0], kind="stable")
+        part = np.empty(whole.n_cells, np.int32)
+        part[order] = (np.arange(whole.n_cells) * world // whole.n_cells).astype(np.int32)
+        foamcase.decompose(case_dir, pts, faces, own, nei, patches, part)
+    dist.barrier()
+    rng = np.random.default_rng(5)
+    N = whole.n_cells
+    p, T = 1e5 * (1 + 0.05 * rng.random(N)), 300.0 * (1 + 0.05 * rng.random(N))
+    U = np.column_stack([120.0 + 10 * rng.random(N), 8 * rng.random(N), 5 * rng.random(N)])
+    bcs = {q["name"]: {"p": ("zeroGradient", ()), "U": ("zeroGradient", ()), "T": ("zeroGradient", ())} for q in whole.patches}
+    case = cases.Case("decomposed", whole, 287.0, 1005.0, capi.default_schemes(flux_scheme="ROE"),
+                      capi.solver_controls("LUSGS", n_directions=5, max_iter=10, tolerance=1e-10, rel_tol=1e-3), bcs, p, U, T, mu=0.3)
+    return case, case.decomposed(case_dir)[1]
+
+
+def main_vki(rank, world, local, ids, prepared=None):
     """C5 across GPUs: the shipped VKI-LS89 mesh decomposed with its cyclic pair kept whole per rank (decomposeParDict
     preservePatches), laminar viscous ROE run; parity against the P-rank oracle world of the same decomposition."""
     from oracle.pyoracle import World
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    case = cases.vki_ls89(os.path.join(root, "cases_local", "VKI-LS89", "constant", "polyMesh"))
     n_iter = int(os.environ.get("ICS_MULTI_ITERS", "4"))
-    part, meshes = case.partition(world, "x")
+    if prepared is not None:
+        case, meshes = prepared
+    else:
+        case = cases.vki_ls89(os.path.join(root, "cases_local", "VKI-LS89", "constant", "polyMesh"))
+        part, meshes = case.partition(world, "x")
     m = meshes[rank]
     ctx = case.apply(Context(device=local, nccl_id=ids[0], rank=rank, n_ranks=world), mesh=m, cells=m.cell_global)
     hist = []
@@ -127,6 +160,8 @@ def main():
         return main_hb(rank, world, local, ids)
     if variant == "vki":
         return main_vki(rank, world, local, ids)
+    if variant == "decomposed":
+        return main_vki(rank, world, local, ids, prepared=decomposed_case(rank, world))
 
     def make(r):
         c = cases.onera_box(n, parts=parts, rank=r, mu=mu)
