@@ -17,7 +17,8 @@ LIM_UPWIND, LIM_VANLEER, LIM_MINMOD, LIM_LINEAR = range(4)
 LIM_NAMES = {"upwind": LIM_UPWIND, "vanLeer": LIM_VANLEER, "Minmod": LIM_MINMOD, "linear": LIM_LINEAR}
 DDT_STEADY, DDT_EULER, DDT_BACKWARD = range(3)
 DDT_NAMES = {"steadyState": DDT_STEADY, "Euler": DDT_EULER, "backward": DDT_BACKWARD}
-SOLVER_GMRES = 0
+SOLVER_GMRES, SOLVER_SMOOTH = range(2)
+SOLVER_NAMES = {"GMRES": SOLVER_GMRES, "smoothSolverCoupled": SOLVER_SMOOTH}
 PRECOND_LUSGS, PRECOND_JACOBI = range(2)
 PRECOND_NAMES = {"LUSGS": PRECOND_LUSGS, "Jacobi": PRECOND_JACOBI}
 (BC_ZEROGRADIENT, BC_FIXEDVALUE, BC_SLIP, BC_EMPTY, BC_INLETOUTLET, BC_TOTALPRESSURE, BC_TOTALTEMPERATURE,
@@ -71,10 +72,16 @@ class SolverControls(C.Structure):
                 ("min_iter", C.c_int), ("tolerance", C.c_double), ("rel_tol", C.c_double)]
 
 
-def solver_controls(preconditioner="LUSGS", n_directions=5, max_iter=1000, min_iter=0, tolerance=1e-12, rel_tol=1e-2):
+def solver_controls(preconditioner="LUSGS", n_directions=5, max_iter=1000, min_iter=0, tolerance=1e-12, rel_tol=1e-2, solver="GMRES",
+                    n_sweeps=None):
+    """fvSolution/flowSolver.  solver "smoothSolverCoupled" (smoother Jacobi): n_sweeps travels in the n_directions slot."""
     if isinstance(preconditioner, str):
         preconditioner = PRECOND_NAMES[preconditioner]
-    return SolverControls(SOLVER_GMRES, preconditioner, n_directions, max_iter, min_iter, tolerance, rel_tol)
+    if isinstance(solver, str):
+        solver = SOLVER_NAMES[solver]
+    if solver == SOLVER_SMOOTH:
+        n_directions = n_sweeps if n_sweeps is not None else 1
+    return SolverControls(solver, preconditioner, n_directions, max_iter, min_iter, tolerance, rel_tol)
 
 
 class Residuals(C.Structure):

@@ -1780,11 +1780,13 @@ static int precond(icsb200_ctx* c, int kind, double* x)
 int ics_gmres(icsb200_ctx* c, const icsb200_solver_controls* ctl, icsb200_residuals* res)
 {
     const int m = ctl->n_directions;
-    if (ctl->solver != ICSB200_SOLVER_GMRES) return ics_fail(c, ICSB200_EINVAL, "Unknown solver; valid types are: GMRES");
-    if (m < 1 || m > 50) return ics_fail(c, ICSB200_EINVAL, "nDirections out of range");
+    const bool smooth = ctl->solver == ICSB200_SOLVER_SMOOTH;   // smoothSolverCoupled: m = nSweeps, no Krylov space
+    if (ctl->solver != ICSB200_SOLVER_GMRES && !smooth) return ics_fail(c, ICSB200_EINVAL, "Unknown solver; valid types are: GMRES smoothSolverCoupled");
+    if (m < 1 || m > 50) return ics_fail(c, ICSB200_EINVAL, smooth ? "nSweeps out of range" : "nDirections out of range");
+    if (smooth && c->hbNO > 1) return ics_fail(c, ICSB200_EINVAL, "smoothSolverCoupled is not available for the Harmonic Balance system");
     const int NP = c->NP;
     const size_t NPH = c->NPH, V5 = 5 * NPH;
-    if (c->mAlloc < m) {
+    if (!smooth && c->mAlloc < m) {
         int r = devAlloc(c, &c->d_kry, (size_t)m * V5);
         if (r) return r;
         CUDA_TRY(c, cudaMemsetAsync(c->d_kry, 0, sizeof(double) * m * V5, c->stream));
@@ -1862,6 +1864,20 @@ int ics_gmres(icsb200_ctx* c, const icsb200_solver_controls* ctl, icsb200_residu
     if (ctl->preconditioner == ICSB200_PRECOND_JACOBI) c->invDValid = c->invDValid && true;
     bool stop = false;
     do {
+      if (smooth) {
+        // JacobiSmoother::smooth (JacobiSmoother.C:120-203): x <- D^-1 (b - (A - D) x), evaluated as x + D^-1 (b - A x) with the
+        // full product and the block-Jacobi kernels (equal up to rounding; the solver bar is 1e-8)
+        {
+            LaunchScope ls(c, TM_VEC);
+            k_set<<<1, 32, 0, c->stream>>>(1, 1.0, sc + L.Y);
+        }
+        for (int sweep = 0; sweep < m; sweep++) {
+            if ((r = ics_spmv(c, c->d_x, c->d_w, c->d_src))) return r;
+            if ((r = precond(c, ICSB200_PRECOND_JACOBI, c->d_w))) return r;
+            LaunchScope ls(c, TM_VEC);
+            k_update_x<<<g256, 256, 0, c->stream>>>(NP, NPH, 1, c->d_w, sc + L.Y, c->d_x);
+        }
+      } else {
         if ((r = precond(c, ctl->preconditioner, c->d_w))) return r;
         {
             LaunchScope ls(c, TM_RED);
@@ -1907,6 +1923,7 @@ int ics_gmres(icsb200_ctx* c, const icsb200_solver_controls* ctl, icsb200_residu
             k_update_x<<<g256, 256, 0, c->stream>>>(NP, NPH, m, c->d_kry, sc + L.Y, c->d_x);
             c->launches++;
         }
+      }
         // true residual r = b - A dW
         if ((r = ics_spmv(c, c->d_x, c->d_w, c->d_src))) return r;
         {
@@ -1924,7 +1941,7 @@ int ics_gmres(icsb200_ctx* c, const icsb200_solver_controls* ctl, icsb200_residu
                 if (c->solutionD[d] == -1) vFinal[3 * I + d] = 0.0;
             }
         }
-        res->n_iterations++;
+        res->n_iterations += smooth ? m : 1;      // smoothSolverCoupled.C:511 counts sweeps, gmres.C:1104 restarts
         publish();
         // solver::stop (coupledMatrixSolver.C:198-221) with residualsIO::max / maxRel over every variable
         if (res->n_iterations < ctl->min_iter) stop = false;

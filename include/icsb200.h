@@ -48,7 +48,8 @@ typedef struct {
 enum { ICSB200_FLUX_HLLC = 0, ICSB200_FLUX_ROE = 1, ICSB200_FLUX_AUSMPLUSUP = 2 };    /* fvSchemes convectiveFluxScheme/fluxScheme */
 enum { ICSB200_LIM_UPWIND = 0, ICSB200_LIM_VANLEER = 1, ICSB200_LIM_MINMOD = 2, ICSB200_LIM_LINEAR = 3 }; /* interpolationSchemes reconstruct(.) */
 enum { ICSB200_DDT_STEADY = 0, ICSB200_DDT_EULER = 1, ICSB200_DDT_BACKWARD = 2 };       /* ddtSchemes: dualTime rPseudoDeltaT <inner> */
-enum { ICSB200_SOLVER_GMRES = 0 };                                                       /* fvSolution flowSolver/solver */
+enum { ICSB200_SOLVER_GMRES = 0, ICSB200_SOLVER_SMOOTH = 1 };                            /* fvSolution flowSolver/solver: GMRES,
+                                                                                          * smoothSolverCoupled (smoother Jacobi) */
 enum { ICSB200_PRECOND_LUSGS = 0, ICSB200_PRECOND_JACOBI = 1 };                          /* flowSolver/<solver>/preconditioner */
 
 /* boundary-condition kinds for p, U, T (OpenFOAM fvPatchField type names) */
@@ -88,9 +89,10 @@ typedef struct {
 } icsb200_schemes;
 
 typedef struct {
-    int solver;         /* ICSB200_SOLVER_GMRES */
+    int solver;         /* ICSB200_SOLVER_*  (coupledMatrixSolver.C:41-67; gmres.C:772-1110, smoothSolverCoupled.C:385-515) */
     int preconditioner; /* ICSB200_PRECOND_*   (coupledMatrixPreconditioner.C:41-64) */
-    int n_directions;   /* nDirections         (gmres.C:81) */
+    int n_directions;   /* GMRES: nDirections (gmres.C:81); smoothSolverCoupled: nSweeps (smoothSolverCoupled.C:57), the block-Jacobi
+                         * sweeps of JacobiSmoother::smooth (JacobiSmoother.C:120-203) between two residual evaluations */
     int max_iter;       /* maxIter, default 1000 (coupledMatrixSolver.C:81, coupledMatrix.C:40) */
     int min_iter;       /* minIter, default 0 */
     double tolerance;   /* tolerance */

@@ -336,7 +336,35 @@ int solveDelta(Ctx& c, const icsb200_solver_controls& ctl, icsb200_residuals& re
         if (ctl.preconditioner == ICSB200_PRECOND_LUSGS) lusgsPrecondition(c, rD, a, v, b);
         else jacobiPrecondition(c, a, v, b);
     };
+    const bool smooth = ctl.solver == ICSB200_SOLVER_SMOOTH;
     do {
+      if (smooth) {
+        // smoothSolverCoupled::solveDelta (smoothSolverCoupled.C:449-515) with JacobiSmoother::smooth (JacobiSmoother.C:120-203):
+        // nSweeps times  x <- D^-1 ( -(matrixMulNoDiag(x) - b) ).  matrixMulNoDiag is restated as matrixMul minus the product
+        // with the diagonal blocks (variable order of the dense block: rho, rhoE, rhoU).
+        for (int sweep = 0; sweep < nDirs; sweep++) {
+            matrixMul(c, dsRho, dvRhoU, dsRhoE, sTmp0, vTmp, sTmp1);
+            for (int k = 0; k < N; k++) {
+                const size_t k3 = 3 * (size_t)k, k9 = 9 * (size_t)k;
+                double d0 = c.blk[0].diag[k] * dsRho[k] + c.blk[1].diag[k] * dsRhoE[k];
+                double d1 = c.blk[2].diag[k] * dsRho[k] + c.blk[3].diag[k] * dsRhoE[k];
+                double dv[3];
+                for (int d = 0; d < 3; d++) {
+                    d0 += c.blk[4].diag[k3 + d] * dvRhoU[k3 + d];
+                    d1 += c.blk[5].diag[k3 + d] * dvRhoU[k3 + d];
+                    dv[d] = c.blk[6].diag[k3 + d] * dsRho[k] + c.blk[7].diag[k3 + d] * dsRhoE[k];
+                    for (int e = 0; e < 3; e++) dv[d] += c.blk[8].diag[k9 + 3 * d + e] * dvRhoU[k3 + e];
+                }
+                sTmp0[k] = -((sTmp0[k] - d0) - sSrc0[k]);
+                sTmp1[k] = -((sTmp1[k] - d1) - sSrc1[k]);
+                for (int d = 0; d < 3; d++) vTmp[k3 + d] = -((vTmp[k3 + d] - dv[d]) - vSrc[k3 + d]);
+            }
+            sTmp0.resize(N); sTmp1.resize(N); vTmp.resize(3 * (size_t)N);
+            jacobiPrecondition(c, sTmp0, vTmp, sTmp1);                 // D^-1 applied to the bracket (zero-start sweep == D^-1 b)
+            for (int k = 0; k < N; k++) { dsRho[k] = sTmp0[k]; dsRhoE[k] = sTmp1[k]; }
+            for (size_t k = 0; k < 3 * (size_t)N; k++) dvRhoU[k] = vTmp[k];
+        }
+      } else {
         precon(sTmp0, vTmp, sTmp1);
         double beta = 0.0;
         beta += gSumSqr(c, sTmp0, N);
@@ -385,6 +413,7 @@ int solveDelta(Ctx& c, const icsb200_solver_controls& ctl, icsb200_residuals& re
             for (int k = 0; k < N; k++) { dsRho[k] += yi * V0[i][k]; dsRhoE[k] += yi * V1[i][k]; }
             for (size_t k = 0; k < 3 * (size_t)N; k++) dvRhoU[k] += yi * VV[i][k];
         }
+      }
         matrixMul(c, dsRho, dvRhoU, dsRhoE, sTmp0, vTmp, sTmp1);
         for (int k = 0; k < N; k++) { sTmp0[k] = sSrc0[k] - sTmp0[k]; sTmp1[k] = sSrc1[k] - sTmp1[k]; }
         for (size_t k = 0; k < 3 * (size_t)N; k++) vTmp[k] = vSrc[k] - vTmp[k];
@@ -393,7 +422,7 @@ int solveDelta(Ctx& c, const icsb200_solver_controls& ctl, icsb200_residuals& re
         double cs[3] = {0, 0, 0};
         for (int k = 0; k < N; k++) for (int d = 0; d < 3; d++) cs[d] += std::fabs(vTmp[3 * (size_t)k + d]);
         for (int d = 0; d < 3; d++) { res.v_final[d] = c.comm->sum(cs[d]) / vNorm; if (m.solutionD[d] == -1) res.v_final[d] = 0.0; }
-        res.n_iterations++;
+        res.n_iterations += smooth ? nDirs : 1;
     } while (!stop(c, ctl, res));
     // coupledMatrix::solveForIncr: zero the increment in non-solved directions (coupledMatrix.C:371-382)
     for (int d = 0; d < 3; d++)

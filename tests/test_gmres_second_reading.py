@@ -122,3 +122,44 @@ def test_gmres_second_reading_agrees_restart_by_restart(precond):
         assert np.allclose(got_init[:5], init, rtol=1e-10), (precond, k)
         assert np.allclose(got_final[:5], final, rtol=1e-7, atol=1e-14), (precond, k)
     assert history[-1][1][0] < init[0]
+
+
+def test_smooth_solver_second_reading():
+    """smoothSolverCoupled::solveDelta (smoothSolverCoupled.C:385-515) with JacobiSmoother::smooth (JacobiSmoother.C:120-203) in dense
+    numpy: nSweeps block-Jacobi sweeps x <- D^-1 (b - (A - D) x) between two residual evaluations, nIterations counted in sweeps,
+    the same residual normalisation as GMRES."""
+    case = cases.onera_box(5)
+    o = case.apply(Oracle())
+    o.calc_flux(); src = o.residual(); o.pseudo_dt(); o.assemble()
+    N = case.mesh.n_cells
+    A = dense_from_ldu(o, case.mesh)
+    blocks = A.reshape(N, 5, N, 5)
+    D = np.zeros_like(A)
+    for i in range(N):
+        D[5 * i:5 * i + 5, 5 * i:5 * i + 5] = blocks[i, :, i, :]
+    Dinv = np.linalg.inv(D)
+    st = o.state_get()
+    W = np.column_stack([st["rho"], st["rhoU"], st["rhoE"]])
+    b = np.column_stack(src).reshape(-1)
+    tmp = (A @ (W - W.mean(axis=0)).reshape(-1)).reshape(N, 5)
+    bb = b.reshape(N, 5)
+    sN = [np.abs(tmp[:, k]).sum() + np.abs(bb[:, k]).sum() + VSMALL for k in (0, 4)]
+    vN = (np.linalg.norm(tmp[:, 1:4], axis=1) + np.linalg.norm(bb[:, 1:4], axis=1)).sum() + VSMALL
+    n_sweeps = 2
+    x = np.zeros(5 * N)
+    for outer in range(1, 4):
+        for _ in range(n_sweeps):
+            x = Dinv @ (b - (A - D) @ x)
+        r = (b - A @ x).reshape(N, 5)
+        final = [np.abs(r[:, 0]).sum() / sN[0], np.abs(r[:, 4]).sum() / sN[1]] + list(np.abs(r[:, 1:4]).sum(axis=0) / vN)
+        ctl = capi.solver_controls(solver="smoothSolverCoupled", n_sweeps=n_sweeps, max_iter=outer * n_sweeps, min_iter=outer * n_sweeps,
+                                   tolerance=1e-300, rel_tol=0.0)
+        (dr, dru, dre), res = o.solve_delta(ctl)
+        assert res.n_iterations == outer * n_sweeps
+        got = np.column_stack([dr, dru, dre]).reshape(-1)
+        assert np.abs(got - x).max() <= 1e-11 * np.abs(x).max(), outer
+        assert np.allclose(list(res.s_final) + list(res.v_final), final, rtol=1e-9), outer
+    assert final[0] < np.abs(bb[:, 0]).sum() / sN[0]                      # the sweeps reduce the residual on this diagonally dominant system
+    # one zero-start sweep is the Jacobi preconditioner (Jacobi.C:55-132)
+    z = o.precondition("Jacobi", bb[:, 0].copy(), bb[:, 1:4].copy(), bb[:, 4].copy())
+    assert np.allclose(np.column_stack(z).reshape(-1), Dinv @ b, rtol=1e-9, atol=1e-12 * np.abs(Dinv @ b).max())
