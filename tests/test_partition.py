@@ -208,3 +208,20 @@ def test_gloo_world_size_2_hb_replicated_partitions(tmp_path):
                         "--master-port", "29537", str(script)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_smooth_solver_is_partition_independent():
+    """smoothSolverCoupled with the Jacobi smoother has no rank-local sweep: the 4-rank world follows the single domain sweep by sweep."""
+    case = cases.onera_box(6)
+    ctl = capi.solver_controls(solver="smoothSolverCoupled", n_sweeps=2, max_iter=8, tolerance=1e-14, rel_tol=1e-6)
+    single = case.apply(Oracle())
+    w, meshes = setup_world(case, 4, (2, 2, 1))
+    for _ in range(2):
+        rw, rs = w.iterate(ctl, 1), single.iterate(ctl)
+        assert rw.n_iterations == rs.n_iterations == 8
+        assert np.allclose(list(rw.s_final) + list(rw.v_final), list(rs.s_final) + list(rs.v_final), rtol=1e-9)
+    st = single.state_get()
+    for o, m in zip(w.ranks, meshes):
+        sr = o.state_get()
+        for k in ("rho", "rhoU", "rhoE"):
+            assert np.abs(sr[k] - st[k][m.cell_global]).max() <= 1e-11 * np.abs(st[k]).max(), k
