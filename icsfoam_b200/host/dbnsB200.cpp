@@ -234,7 +234,10 @@ int main(int argc, char** argv)
         const dictionary& mix = thermoDict.subDict("mixture");
         const double W = mix.subDict("specie").get<double>("molWeight"), Cp = mix.subDict("thermodynamics").get<double>("Cp");
         const double mu = mix.subDict("transport").get<double>("mu"), Pr = mix.subDict("transport").get<double>("Pr");
-        if (mix.subDict("thermodynamics").getOrDefault<double>("Tref", 0.0) != 0.0) throw FatalError("Tref != 0 is not supported");
+        // hConstThermo (v2112): Hs = Cp (T - Tref) + Hsref with Tref defaulting to Tstd = 298.15 K when the entry is absent, so
+        // e = Cv T - Cp Tref + Hsref.  The device thermo is e = Cv T: every shipped tutorial says `Tref 0`; anything else is refused.
+        if (mix.subDict("thermodynamics").getOrDefault<double>("Tref", 298.15) != 0.0 || mix.subDict("thermodynamics").getOrDefault<double>("Hsref", 0.0) != 0.0)
+            throw FatalError("thermodynamics: only `Tref 0` (stated explicitly; OpenFOAM defaults to Tstd) with Hsref 0 is supported");
         check(ctx, icsb200_thermo_set(ctx, 8314.46261815324 / W, Cp, mu, Pr), "thermo_set");
         if (mu > 0) std::cout << "Viscous analysis detected: laminar viscous residual + Lax-Friedrichs viscous Jacobian (turbulence model not on the device)\n";
 
