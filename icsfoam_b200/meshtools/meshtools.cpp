@@ -138,11 +138,15 @@ void finishGeometry(Mesh& m)
     for (int f = F; f < FT; f++) {
         int o = m.owner[f];
         m.weights[f] = 1.0;
-        V3 d = m.Cf[f] - m.C[o];
-        double md = mag(d);
-        if (md < VSMALL || m.magSf[f] < VSMALL) { m.deltaCoeffs[f] = 0; m.nonOrthDeltaCoeffs[f] = 0; continue; }
-        m.deltaCoeffs[f] = 1.0 / md;
+        // fvPatch::delta() of a non-coupled patch is the PATCH-NORMAL delta nHat (nHat & (Cf - Cn)) (OpenFOAM fvPatch.C), so both
+        // coefficients are 1 / (nHat & (Cf - Cn)); coupled patches overwrite theirs with the cell-to-cell delta (cyclicGeometry, extract_part)
+        V3 d0 = m.Cf[f] - m.C[o];
+        if (mag(d0) < VSMALL || m.magSf[f] < VSMALL) { m.deltaCoeffs[f] = 0; m.nonOrthDeltaCoeffs[f] = 0; continue; }
         V3 nh = (1.0 / m.magSf[f]) * m.Sf[f];
+        V3 d = dot(nh, d0) * nh;
+        double md = mag(d);
+        if (md < VSMALL) { m.deltaCoeffs[f] = 0; m.nonOrthDeltaCoeffs[f] = 0; continue; }
+        m.deltaCoeffs[f] = 1.0 / md;
         m.nonOrthDeltaCoeffs[f] = 1.0 / std::max(dot(nh, d), 0.05 * md);
     }
 }
