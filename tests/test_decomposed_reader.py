@@ -34,9 +34,12 @@ def test_box_polymesh_is_a_valid_mesh(tmp_path):
     assert (whole.nonOrthDeltaCoeffs[: whole.n_internal_faces] != whole.deltaCoeffs[: whole.n_internal_faces]).any()   # warped: non-orthogonal
 
 
-@pytest.mark.parametrize("n_parts", [2, 4])
+@pytest.mark.parametrize("n_parts", [2, 4, 8])
 def test_read_decomposed_equals_extract_part(tmp_path, n_parts):
-    split = (lambda m: (m.C[:, 0] > 0.5).astype(int)) if n_parts == 2 else (lambda m: (m.C[:, 0] > 0.5).astype(int) + 2 * (m.C[:, 1] > 0.7).astype(int))
+    split = {2: lambda m: (m.C[:, 0] > 0.5).astype(int),
+             4: lambda m: (m.C[:, 0] > 0.5).astype(int) + 2 * (m.C[:, 1] > 0.7).astype(int),
+             # 8 uneven blocks: ranks with up to seven neighbours? no - face neighbours only (<= 3 here), small and large parts
+             8: lambda m: (m.C[:, 0] > 0.2).astype(int) + 2 * (m.C[:, 1] > 0.9).astype(int) + 4 * (m.C[:, 2] > 0.3).astype(int)}[n_parts]
     case_dir, whole, part = _case_dir(tmp_path, split)
     assert foamcase.n_processors(case_dir) == n_parts
     cache = {}
