@@ -66,3 +66,72 @@ def test_viscous_residual_second_reading(flux, seed):
     assert np.abs(got_U[deep]).max() > 0 and np.abs(got_E[deep]).max() > 0
     assert np.abs(got_U[deep] - rhoUR[deep]).max() <= 1e-10 * np.abs(sv[1]).max()
     assert np.abs(got_E[deep] - rhoER[deep]).max() <= 1e-10 * np.abs(sv[2]).max()
+
+
+def viscous_sources_corrected(mesh, st, mu, alpha):
+    """as viscous_sources, with the non-orthogonal correction of `Gauss linear corrected` (OpenFOAM correctedSnGrad, component-wise for
+    vectors): snGrad = nonOrthDeltaCoeffs (phi_N - phi_P) + (n - delta nonOrthDeltaCoeffs) . linearInterpolate(grad phi)"""
+    F, N = mesh.n_internal_faces, mesh.n_cells
+    own, nei, w = mesh.owner[:F], mesh.neighbour, mesh.weights[:F]
+    Sf, magSf, ndc, V = mesh.Sf[:F], mesh.magSf[:F], mesh.nonOrthDeltaCoeffs[:F], mesh.V
+    n = Sf / magSf[:, None]
+    corr = n - (mesh.C[nei] - mesh.C[own]) * ndc[:, None]
+    U = st["U"]
+    lin = lambda a: (w.reshape((-1,) + (1,) * (a.ndim - 1))) * a[own] + ((1 - w).reshape((-1,) + (1,) * (a.ndim - 1))) * a[nei]
+
+    def integrate(ff):
+        out = np.zeros((N,) + ff.shape[1:])
+        np.add.at(out, own, ff)
+        np.subtract.at(out, nei, ff)
+        return out
+
+    def grad(phi):                                           # Gauss linear, (N,3) for a scalar, (N,3,3) [i: derivative, j: component] for a vector
+        pf = lin(phi)
+        ff = Sf * pf[:, None] if phi.ndim == 1 else Sf[:, :, None] * pf[:, None, :]
+        return integrate(ff) / V.reshape((-1,) + (1,) * (ff.ndim - 1))
+
+    gradU = grad(U)
+    sn_U = ndc[:, None] * (U[nei] - U[own]) + np.einsum("fi,fij->fj", corr, lin(gradU))
+    tr = np.trace(gradU, axis1=1, axis2=2)
+    tauMC = mu * (np.swapaxes(gradU, 1, 2) - (2.0 / 3.0) * tr[:, None, None] * np.eye(3))
+    rhoUR = integrate((mu * magSf)[:, None] * sn_U) + integrate(np.einsum("fi,fij->fj", Sf, lin(tauMC)))
+    sigma = mu * lin(gradU) + lin(tauMC)
+    e = st["rhoE"] / st["rho"] - 0.5 * (U * U).sum(1)
+    sn_e = ndc * (e[nei] - e[own]) + (corr * lin(grad(e))).sum(1)
+    rhoER = integrate((np.einsum("fij,fj->fi", sigma, lin(U)) * Sf).sum(1)) + integrate(alpha * magSf * sn_e)
+    return rhoUR, rhoER
+
+
+def test_viscous_residual_second_reading_on_a_non_orthogonal_mesh():
+    mu, Pr = 0.04, 0.75
+    visc, invisc = cases.bump(15, 12, mu=mu, Pr=Pr), cases.bump(15, 12)
+    mesh = visc.mesh
+    rng = np.random.default_rng(41)                          # a non-trivial state: the tutorial's initial field is uniform
+    for c in (visc, invisc):
+        c.U = c.U * (1 + 0.05 * np.sin(7 * mesh.C[:, :1]) * np.cos(5 * mesh.C[:, 1:2])) + np.column_stack([np.zeros(mesh.n_cells), 15 * np.sin(3 * mesh.C[:, 0]), np.zeros(mesh.n_cells)])
+        c.T = c.T * (1 + 0.03 * np.cos(4 * mesh.C[:, 0] + 2 * mesh.C[:, 1]))
+    out = []
+    for case in (visc, invisc):
+        o = case.apply(Oracle())
+        o.calc_flux()
+        out.append((o.residual(), o.state_get()))
+    (sv, st), (si, _) = out
+    F = mesh.n_internal_faces
+    from icsfoam_b200 import capi
+    layer = np.zeros(mesh.n_cells, bool)
+    for p in mesh.patches:
+        if p["kind"] != capi.EMPTY:
+            layer[mesh.owner[p["start"]:p["start"] + p["size"]]] = True
+    near = layer.copy()
+    near[mesh.owner[:F][layer[mesh.neighbour]]] = True
+    near[mesh.neighbour[layer[mesh.owner[:F]]]] = True
+    deep = np.flatnonzero(~near)
+    assert len(deep) >= 100
+    assert not np.allclose(mesh.nonOrthDeltaCoeffs[:F], mesh.deltaCoeffs[:F], rtol=1e-6)      # the correction term is active
+    gamma = visc.Cp / (visc.Cp - visc.R)
+    rhoUR, rhoER = viscous_sources_corrected(mesh, st, mu, gamma * (mu / Pr))
+    plainU, _ = viscous_sources(mesh, st, mu, gamma * (mu / Pr))
+    got_U, got_E = sv[1] - si[1], sv[2] - si[2]
+    assert np.abs(got_U[deep][:, :2] - rhoUR[deep][:, :2]).max() <= 1e-9 * np.abs(got_U[deep]).max()
+    assert np.abs(got_E[deep] - rhoER[deep]).max() <= 1e-9 * np.abs(got_E[deep]).max()
+    assert np.abs(got_U[deep][:, :2] - plainU[deep][:, :2]).max() > 1e-6 * np.abs(got_U[deep]).max()   # ... and matters
