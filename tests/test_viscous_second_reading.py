@@ -135,3 +135,73 @@ def test_viscous_residual_second_reading_on_a_non_orthogonal_mesh():
     assert np.abs(got_U[deep][:, :2] - rhoUR[deep][:, :2]).max() <= 1e-9 * np.abs(got_U[deep]).max()
     assert np.abs(got_E[deep] - rhoER[deep]).max() <= 1e-9 * np.abs(got_E[deep]).max()
     assert np.abs(got_U[deep][:, :2] - plainU[deep][:, :2]).max() > 1e-6 * np.abs(got_U[deep]).max()   # ... and matters
+
+
+def test_viscous_residual_second_reading_with_walls():
+    """Every cell of an orthogonal box with an isothermal no-slip wall (fixedValue U and T) and zeroGradient elsewhere: boundary-face
+    contributions restated from OpenFOAM's own rules — fixedValue snGrad = deltaCoeffs (phi_b - phi_P); the patch values of a Gauss
+    gradient after gaussGrad::correctBoundaryConditions, grad_b = grad_P + n (snGrad_b - n . grad_P); tauMC and sigmaDotU evaluated
+    from boundary values on boundary faces; eCalc = rhoE / rho - 0.5 |U|^2 as a calculated field."""
+    from icsfoam_b200 import capi
+    from icsfoam_b200 import meshtools as mt
+    mu, Pr = 0.05, 0.72
+    mesh = mt.structured(1, 6, 5, 4, 0, (0, 0, 0), (1.2, 1.0, 0.8), patch_kinds=(capi.PATCH, capi.PATCH, capi.WALL, capi.PATCH, capi.PATCH, capi.PATCH))
+    rng = np.random.default_rng(51)
+    N, F = mesh.n_cells, mesh.n_internal_faces
+    p = 1e5 * (1 + 0.1 * rng.random(N))
+    T = 300.0 * (1 + 0.1 * rng.random(N))
+    U = np.column_stack([90.0 + 40 * rng.random(N), 30 * rng.standard_normal(N), 30 * rng.standard_normal(N)])
+    names = [q["name"] for q in mesh.patches]
+    zg = ("zeroGradient", ())
+    bcs = {nm: {"p": zg, "U": zg, "T": zg} for nm in names}
+    wall = names[2]
+    Tw = 320.0
+    bcs[wall] = {"p": zg, "U": ("fixedValue", (0.0, 0.0, 0.0)), "T": ("fixedValue", (Tw,))}
+    out = []
+    for m_ in (mu, 0.0):
+        case = cases.Case("wall", mesh, 287.0, 1005.0, capi.default_schemes(flux_scheme="ROE"), capi.solver_controls(), bcs, p, U, T, mu=m_, Pr=Pr)
+        o = case.apply(Oracle())
+        o.calc_flux()
+        out.append((o.residual(), o.state_get(), o.boundary_get()))
+    (sv, st, bd), (si, _, _) = out
+    R, Cp = 287.0, 1005.0
+    Cv, gamma = Cp - R, Cp / (Cp - R)
+    alpha = gamma * (mu / Pr)
+    own, nei, w = mesh.owner, mesh.neighbour, mesh.weights[:F]
+    Sf, magSf, dc, V = mesh.Sf, mesh.magSf, mesh.deltaCoeffs, mesh.V
+    nb = Sf[F:] / magSf[F:, None]
+    fc = own[F:]
+    Ub, Tb = bd["U"], bd["T"]
+    wallf = mesh.patch_faces(wall) - F
+    assert np.abs(Ub[wallf]).max() == 0.0 and (Tb[wallf] == Tw).all()
+    Uc = st["U"]
+    e = st["rhoE"] / st["rho"] - 0.5 * (Uc * Uc).sum(1)
+    eb = Cv * Tb                                             # he(p, T) on the patch; 0.5 |U_b|^2 cancels in eCalc
+    lin = lambda a: (w.reshape((-1,) + (1,) * (a.ndim - 1))) * a[own[:F]] + ((1 - w).reshape((-1,) + (1,) * (a.ndim - 1))) * a[nei]
+
+    def integrate(fi, fb):
+        acc = np.zeros((N,) + fi.shape[1:])
+        np.add.at(acc, own[:F], fi)
+        np.subtract.at(acc, nei, fi)
+        np.add.at(acc, fc, fb)
+        return acc
+
+    gradU = integrate(Sf[:F, :, None] * lin(Uc)[:, None, :], Sf[F:, :, None] * Ub[:, None, :]) / V[:, None, None]
+    snU_b = dc[F:, None] * (Ub - Uc[fc])                     # zeroGradient faces: U_b = U_P -> 0
+    gP = gradU[fc]
+    gradU_b = gP + nb[:, :, None] * (snU_b - np.einsum("fi,fij->fj", nb, gP))[:, None, :]
+    dev2T = lambda g: np.swapaxes(g, 1, 2) - (2.0 / 3.0) * np.trace(g, axis1=1, axis2=2)[:, None, None] * np.eye(3)
+    tau, tau_b = mu * dev2T(gradU), mu * dev2T(gradU_b)
+    lapU = integrate((mu * magSf[:F] * dc[:F])[:, None] * (Uc[nei] - Uc[own[:F]]), (mu * magSf[F:])[:, None] * snU_b)
+    divTau = integrate(np.einsum("fi,fij->fj", Sf[:F], lin(tau)), np.einsum("fi,fij->fj", Sf[F:], tau_b))
+    sig_i = np.einsum("fij,fj->fi", mu * lin(gradU) + lin(tau), lin(Uc))
+    sig_b = np.einsum("fij,fj->fi", mu * gradU_b + tau_b, Ub)
+    rhoER = integrate((sig_i * Sf[:F]).sum(1), (sig_b * Sf[F:]).sum(1))
+    rhoER = rhoER + integrate(alpha * magSf[:F] * dc[:F] * (e[nei] - e[own[:F]]), alpha * magSf[F:] * dc[F:] * (eb - e[fc]))
+    rhoUR = lapU + divTau
+    got_U, got_E = sv[1] - si[1], sv[2] - si[2]
+    assert np.abs(got_U - rhoUR).max() <= 1e-10 * np.abs(got_U).max()
+    assert np.abs(got_E - rhoER).max() <= 1e-10 * np.abs(got_E).max()
+    wall_heat = alpha * magSf[F:][wallf] * dc[F:][wallf] * (eb[wallf] - e[fc[wallf]])
+    assert np.abs(wall_heat).max() > 1e-2 * np.abs(got_E).max()                 # the wall terms are a visible part of what was compared
+    assert np.abs((mu * magSf[F:])[wallf, None] * snU_b[wallf]).max() > 1e-2 * np.abs(got_U).max()
