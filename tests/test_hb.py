@@ -302,3 +302,32 @@ def test_phase_lag_cyclic_travelling_wave():
         assert np.array_equal(b["T"][fa - F], H.inst[K].state_get()["T"][m.owner[fb]])     # T is not a phase-lagged field
     r = H.iterate(case.controls, 3)
     assert np.isfinite(H.state_get()["rho"]).all() and r["s_init"].max() < 1.0
+
+
+def test_cylindrical_momentum_source_second_reading():
+    """HBZone::addSource for vectors with cylCoords (HBZone.C:521-651) read a second time in numpy: every instance's momentum is
+    decomposed along (rHat, axisHat x rHat, axisHat) at ITS cell centre, mixed by D, and the sum is turned back into Cartesian
+    components at the centre of the receiving instance."""
+    case = cases.hb_box(4, 3, cyl=True)
+    H = HB(case)
+    got = H.sources()[1].reshape(3, H.N, 3)
+    st = H.state_get()
+    W = st["rhoU"].reshape(3, H.N, 3)
+    V = case.base.mesh.V
+    D = case.D[0]
+    axis = np.array(case.rotation_axis[:3], float)
+    a = axis / np.linalg.norm(axis)
+    centre = np.array(case.rotation_centre[:3], float)
+    C = case.base.mesh.C                                     # the instance meshes are copies: same centres
+    r = C - centre
+    r = r - (r @ a)[:, None] * a
+    rhat = r / np.linalg.norm(r, axis=1)[:, None]
+    that = np.cross(a, rhat)
+    want = np.zeros_like(got)
+    for J in range(3):
+        cyl = np.zeros((H.N, 3))
+        for K in range(3):
+            ucyl = np.column_stack([(W[K] * rhat).sum(1), (W[K] * that).sum(1), W[K] @ a])
+            cyl += (V * D[J, K])[:, None] * ucyl
+        want[J] = -(cyl[:, :1] * rhat + cyl[:, 1:2] * that + cyl[:, 2:3] * a)
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
