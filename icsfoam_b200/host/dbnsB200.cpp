@@ -217,6 +217,16 @@ int main(int argc, char** argv)
                 bcs[(size_t)3 * pi + fld] = bcFromDict(bf[fld]->subDict(patchNames[pi]), fld, U0, *top[fld], patches[pi].size);
                 nNonuniform += bcs[(size_t)3 * pi + fld].nRows > 0;
             }
+        // ---- thermo: hePsiThermo<pureMixture<constTransport<hConst<perfectGas>>>>, sensibleInternalEnergy (createFields.H:17-35)
+        const dictionary& mix = thermoDict.subDict("mixture");
+        const double W = mix.subDict("specie").get<double>("molWeight"), Cp = mix.subDict("thermodynamics").get<double>("Cp");
+        const double mu = mix.subDict("transport").get<double>("mu"), Pr = mix.subDict("transport").get<double>("Pr");
+        // hConstThermo (v2112): Hs = Cp (T - Tref) + Hsref with Tref defaulting to Tstd = 298.15 K when the entry is absent, so
+        // e = Cv T - Cp Tref + Hsref.  The device thermo is e = Cv T: every shipped tutorial says `Tref 0`; anything else is refused.
+        if (mix.subDict("thermodynamics").getOrDefault<double>("Tref", 298.15) != 0.0 || mix.subDict("thermodynamics").getOrDefault<double>("Hsref", 0.0) != 0.0)
+            throw FatalError("thermodynamics: only `Tref 0` (stated explicitly; OpenFOAM defaults to Tstd) with Hsref 0 is supported");
+        // ---- solver controls (fvSolution/flowSolver): read before -parseOnly returns so that dictionary errors surface without a GPU
+        const icsb200_solver_controls ctl = coupledMatrix::controlsFromDict(fvSolution.subDict("flowSolver"));
         if (parseOnly) {
             double pmin = 1e300, pmax = -1e300;
             for (double v : p) { pmin = std::min(pmin, v); pmax = std::max(pmax, v); }
@@ -230,14 +240,6 @@ int main(int argc, char** argv)
         check(ctx, icsb200_mesh_set(ctx, N, F, FT, owner.data(), neighbour.data(), Sf.data(), magSf.data(), w.data(), dc.data(), nodc.data(),
                                     C.data(), V.data(), Cf.data(), nP, patches.data(), sz + 4), "mesh_set");
 
-        // ---- thermo: hePsiThermo<pureMixture<constTransport<hConst<perfectGas>>>>, sensibleInternalEnergy (createFields.H:17-35)
-        const dictionary& mix = thermoDict.subDict("mixture");
-        const double W = mix.subDict("specie").get<double>("molWeight"), Cp = mix.subDict("thermodynamics").get<double>("Cp");
-        const double mu = mix.subDict("transport").get<double>("mu"), Pr = mix.subDict("transport").get<double>("Pr");
-        // hConstThermo (v2112): Hs = Cp (T - Tref) + Hsref with Tref defaulting to Tstd = 298.15 K when the entry is absent, so
-        // e = Cv T - Cp Tref + Hsref.  The device thermo is e = Cv T: every shipped tutorial says `Tref 0`; anything else is refused.
-        if (mix.subDict("thermodynamics").getOrDefault<double>("Tref", 298.15) != 0.0 || mix.subDict("thermodynamics").getOrDefault<double>("Hsref", 0.0) != 0.0)
-            throw FatalError("thermodynamics: only `Tref 0` (stated explicitly; OpenFOAM defaults to Tstd) with Hsref 0 is supported");
         check(ctx, icsb200_thermo_set(ctx, 8314.46261815324 / W, Cp, mu, Pr), "thermo_set");
         if (mu > 0) std::cout << "Viscous analysis detected: laminar viscous residual + Lax-Friedrichs viscous Jacobian (turbulence model not on the device)\n";
 
@@ -285,7 +287,6 @@ int main(int argc, char** argv)
         check(ctx, icsb200_state_set(ctx, p.data(), U.data(), T.data()), "state_set");
 
         // ---- solver controls (fvSolution/flowSolver) and pseudo-time control (pseudotimeControl.C:42-69)
-        const icsb200_solver_controls ctl = coupledMatrix::controlsFromDict(fvSolution.subDict("flowSolver"));
         coupledMatrix eqSystem(ctx);
         (void)eqSystem;
         const int nCorrOuter = pseudo.getOrDefault<int>("nPseudoCorr", 20), nCorrOuterMin = pseudo.getOrDefault<int>("nPseudoCorrMin", 1);

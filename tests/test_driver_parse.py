@@ -49,3 +49,32 @@ def test_driver_parses_nonuniform_fields(tmp_path):
     (case / "0" / "T").write_text((case / "0" / "T").read_text().replace("internalField   uniform 400;", "internalField   " + foam_list(np.full(7, 400.0)) + ";"))
     r = run(str(case), "-parseOnly")
     assert r.returncode != 0 and "nonuniform internalField of T" in r.stderr
+
+
+@pytest.mark.skipif(not (os.path.isdir(REF) and os.path.exists(DRIVER)), reason="reference tutorial or driver binary not present")
+def test_driver_refuses_an_implicit_tref_and_reads_the_smooth_solver(tmp_path):
+    """hConst without `Tref` means Tstd in OpenFOAM v2112 (e = Cv T - Cp Tstd): refused, not silently read as 0; the solver
+    dictionary of smoothSolverCoupled (smoother Jacobi; nSweeps) is accepted, an unknown smoother is a FatalError."""
+    case = tmp_path / "vki"
+    shutil.copytree(REF, case)
+    thermo = case / "constant" / "thermophysicalProperties"
+    txt = thermo.read_text()
+    assert re.search(r"Tref\s+0;", txt)
+    thermo.write_text(re.sub(r"Tref\s+0;", "", txt))
+    r = run(str(case), "-parseOnly")
+    assert r.returncode != 0 and "Tref 0" in r.stderr, r.stdout + r.stderr
+    thermo.write_text(txt)
+    sol = case / "system" / "fvSolution"
+    stxt = sol.read_text()
+    m = re.search(r"flowSolver\s*\{", stxt)
+    depth, i = 1, m.end()
+    while depth:
+        depth += (stxt[i] == "{") - (stxt[i] == "}")
+        i += 1
+    new = "flowSolver\n{\n    solver smoothSolverCoupled;\n    smoothSolverCoupled\n    {\n        smoother %s;\n        nSweeps 2;\n        maxIter 8;\n        tolerance 1e-12;\n        relTol 1e-3;\n    }\n}\n"
+    sol.write_text(stxt[:m.start()] + new % "Jacobi" + stxt[i:])
+    r = run(str(case), "-parseOnly")
+    assert r.returncode == 0 and "parse ok" in r.stdout, r.stdout + r.stderr
+    sol.write_text(stxt[:m.start()] + new % "GaussSeidel" + stxt[i:])
+    r = run(str(case), "-parseOnly")
+    assert r.returncode != 0 and "Unknown smoother type GaussSeidel" in r.stderr, r.stdout + r.stderr
