@@ -288,3 +288,23 @@ def test_second_reading_on_cyclic_faces(flux):
     for a, b in zip(mine, ref):
         scale = np.abs(b[faces]).max()
         assert scale > 0 and np.abs(a[faces] - b[faces]).max() <= 1e-12 * scale, flux
+
+
+def test_second_reading_follows_the_scheme_switches():
+    """lowMachAusm false (ausmPlusUpFluxScheme.C:259-268 skipped) and another entropyFixCoeff (roeFluxScheme.C:255)"""
+    for flux, attr, value in (("AUSMPlusUp", "low_mach_ausm", 0), ("ROE", "entropy_fix_coeff", 0.2)):
+        case = cases.periodic_box(7, flux, "vanLeer", seed=29)
+        case.U = case.U * 0.05 + np.array((8.0, -3.0, 2.0))           # low speed: both switches matter
+        setattr(case.schemes, attr, value)
+        o = case.apply(Oracle())
+        ref = o.calc_flux()
+        s = face_states(o, case, capi.LIM_VANLEER)
+        mesh = case.mesh
+        f = interior_faces(mesh)
+        if flux == "ROE":
+            mine, other = roe(s, mesh.Sf, mesh.magSf, 0.2), roe(s, mesh.Sf, mesh.magSf, 0.05)
+        else:
+            mine, other = ausm_plus_up(s, mesh.Sf, mesh.magSf, False), ausm_plus_up(s, mesh.Sf, mesh.magSf, True)
+        for a, b in zip(mine, ref):
+            assert np.abs(a[f] - b[f]).max() <= 1e-12 * np.abs(b[f]).max(), flux
+        assert max(np.abs(a[f] - b[f]).max() / np.abs(b[f]).max() for a, b in zip(other, ref)) > 1e-6, flux
