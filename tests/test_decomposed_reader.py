@@ -91,3 +91,45 @@ def test_world_on_decomposed_directories_matches_single_domain(tmp_path):
         sr = o.state_get()
         for k in ("rho", "rhoU", "rhoE"):
             assert np.abs(sr[k] - st[k][m.cell_global]).max() <= 1e-8 * np.abs(st[k]).max(), k
+
+
+GLOO_DECOMPOSED = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["ICS_ROOT"])
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+import tests.multi_gpu_check as m
+from icsfoam_b200 import capi
+case, meshes = m.decomposed_case(rank, world)           # rank 0 writes the case and the processor directories, everybody reads them
+mine = meshes[rank]
+for p in mine.patches:
+    if p["kind"] != capi.PROCESSOR:
+        continue
+    f = np.arange(p["start"], p["start"] + p["size"])
+    send = torch.from_numpy(np.ascontiguousarray(np.column_stack([mine.Cf[f], mine.weights[f]])))
+    recv = torch.empty_like(send)
+    reqs = [dist.isend(send, p["nbr_rank"]), dist.irecv(recv, p["nbr_rank"])]
+    [r.wait() for r in reqs]
+    assert torch.allclose(send[:, :3], recv[:, :3], atol=1e-12), "processor faces are not matched in order"
+    assert torch.allclose(send[:, 3] + recv[:, 3], torch.ones(len(f), dtype=torch.float64), atol=1e-13), "weights of the two sides do not add up to 1"
+n = torch.tensor([mine.n_cells], dtype=torch.int64)
+dist.all_reduce(n)
+assert int(n) == case.mesh.n_cells
+print("rank", rank, "ok")
+'''
+
+
+def test_gloo_ranks_share_a_decomposed_case(tmp_path):
+    """the file handshake of tests/multi_gpu_check.py's `decomposed` variant (rank 0 writes, barrier, all ranks read) with 2 gloo ranks"""
+    import subprocess
+    import sys
+    from tests.conftest import ROOT
+    script = tmp_path / "gloo_decomposed.py"
+    script.write_text(GLOO_DECOMPOSED)
+    env = dict(os.environ, ICS_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29537")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29537", str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2
