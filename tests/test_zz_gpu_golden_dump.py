@@ -41,8 +41,7 @@ def test_write_flux_directory_matches_the_host_path(gpu_context, tmp_path):
     n_pseudo = sum(1 for ln in r.stdout.splitlines() if ln.startswith("pseudoTime: iteration"))
     assert n_pseudo == 2
     for it in range(n_pseudo):
-        if it == n_pseudo - 1:
-            phi, phiUp, phiEp = g.calc_flux()        # the flux the last iteration starts from: what dbnsFoam's phi holds at write time
+        phi, phiUp, phiEp = g.calc_flux()            # as the driver does before every iteration; the last one is what dbnsFoam's phi holds at write time
         g.iterate(case.controls)
     st = g.state_get()
     F = case.mesh.n_internal_faces
