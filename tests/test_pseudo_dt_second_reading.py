@@ -113,3 +113,26 @@ def test_global_pseudo_time_step_second_reading():
     lam_b = c[own[F:]] + np.abs((st["U"][own[F:]] * n[F:]).sum(1))
     want = max((mesh.deltaCoeffs[:F] * lam_i).max(), (mesh.deltaCoeffs[F:] * lam_b).max()) / 3.0
     assert rdt.min() == rdt.max() and np.isclose(rdt[0], want, rtol=1e-13)
+
+
+def test_local_time_step_bounding_as_coded():
+    """boundLocalTimeStep.H:1-98 runs right after solveForIncr and BEFORE updateFields.H adds the increments (outerLoop.H:88-99,
+    dbnsFoam.C:112-118), so `rho` still equals scalarVarsPrevIter[0]: the tests rho < lowerBound rhoPrev and e < lowerBound ePrev
+    cannot fire for a positive state and only a non-positive internal energy of the CURRENT state reduces the pseudo-Courant
+    number.  The oracle (and the device) follow the reference as coded: cells whose density or energy drops by more than 5 % in
+    the update keep their Courant number."""
+    case = cases.periodic_box(6, "ROE", "vanLeer", seed=3)
+    case.schemes.pseudo_co_num = 0.5
+    case.schemes.pseudo_co_num_min = 0.01
+    o = case.apply(Oracle())
+    prev = o.state_get()
+    o.iterate(case.controls)
+    new = o.state_get()
+    o.calc_flux()
+    o.residual()
+    _, co1 = o.pseudo_dt()                                    # second outer iteration: no SER update yet
+    lb = case.schemes.local_timestepping_lower_bound
+    e_of = lambda s: s["rhoE"] / s["rho"] - 0.5 * ((s["rhoU"] / s["rho"][:, None]) ** 2).sum(1)
+    dropped = (new["rho"] < lb * prev["rho"]) | (e_of(new) < lb * e_of(prev))
+    assert dropped.sum() >= 10 and (e_of(prev) > 0).all() and (e_of(new) > 0).all()
+    assert (co1 == 0.5).all()
