@@ -83,7 +83,7 @@ class Context(capi.Api):
         out = (C.c_int * 8)()
         self._call("schedule_info", out)
         return {"n_levels_fwd": out[0], "n_levels_rev": out[1], "max_width": out[2], "n_positions": out[3],
-                "tile_mode": bool(out[4]), "n_tiles": out[5], "n_tile_levels": out[6], "tile_tma": bool(out[7])}
+                "tile_mode": bool(out[4]), "n_tiles": out[5], "n_tile_levels": out[6], "tile_tma": out[7] == 1, "blk": out[7] == 2}
 
     # ---- Harmonic Balance (icsb200_hb_set): the mesh must be an `hb.ReplicatedMesh`
     def hb_set(self, n_instants, D, zone_of_cell=None, cyl_coords=None, rotation_axis=None, rotation_centre=None):

@@ -28,6 +28,13 @@
 #define ICS_GREAT 1e15
 #define ICS_VGREAT 1e300
 #define ICS_TILE_MAXROWS 1024  // rows a LU-SGS tile may hold (shared-memory staging of 5 doubles per row)
+// block tiles (k_lusgs_blk): rows per tile, out-of-tile neighbours per sweep, intra-tile levels, tiles waited for, staged entries per slice
+#define ICS_BLK_MR 512
+#define ICS_BLK_MH 256
+#define ICS_BLK_MAXLEV 127
+#define ICS_BLK_MAXDEP 32
+#define ICS_BLK_SE 3
+#define ICS_BLK_MAXLW 160  // widest intra-tile level
 
 constexpr int NQ = 8;   // reconstructed scalars: rho, p, Ux, Uy, Uz, cR, E, H
 constexpr int NG = 7;   // geometry doubles per face (SoA over GPU face ids)
@@ -132,6 +139,15 @@ struct icsb200_ctx {
     int nTiles = 0, nTileLevels = 0;
     int tileMaxRows = 0, lusgsTileGrid = 0;
     int* d_sliceTile = nullptr;  // [nSlices] tile of a slice
+    // block-tile sweep (k_lusgs_blk, the default schedule when the mesh allows it; solver.cu "block tiles")
+    bool blkMode = false;
+    int* d_blkDesc = nullptr;    // [nTiles][16] tile descriptor (BD_*)
+    short* d_blkLcol = nullptr;  // [6][NP] local neighbour index of a row: 0..2 lower (entry order), 3..5 upper (descending entry order); -1 none
+    int* d_blkHalo = nullptr;    // concatenated out-of-tile neighbour positions (forward lists, then reverse lists)
+    int* d_blkDep = nullptr;     // concatenated flag indices a tile waits for (forward lists, then reverse lists)
+    int* d_blkStage = nullptr;   // [2][nSlices][2] per sweep and slice: first staged block entry, number of staged entries
+    int* d_blkFlag = nullptr;    // [2*nTiles] completion epochs: forward sweep of tile t, reverse sweep of tile t
+    int blkEpoch = 0;
     int *d_rowLevF = nullptr, *d_rowLevR = nullptr;      // [NP] intra-tile level of a row in the forward / reverse sweep (-1 padding)
     int *d_tileNLevF = nullptr, *d_tileNLevR = nullptr;  // [nTiles] number of intra-tile levels
     int *d_tileDescF = nullptr, *d_tileDescR = nullptr;  // [nTiles][16] bulk-copy descriptors of a tile's sweep (solver.cu TT_DESC_*)
@@ -308,6 +324,7 @@ int ics_jacobian(icsb200_ctx* c, bool useStoredRdt);
 int ics_rdiag(icsb200_ctx* c);
 int ics_spmv(icsb200_ctx* c, const double* x, double* y, const double* b /*nullable: y = b - A x*/);
 int ics_lusgs(icsb200_ctx* c, double* x);
+int ics_lusgs_blk(icsb200_ctx* c, double* x);  // lusgs_blk.cu
 int ics_jacobi_prepare(icsb200_ctx* c);
 int ics_jacobi(icsb200_ctx* c, double* x);
 int ics_gmres(icsb200_ctx* c, const icsb200_solver_controls* ctl, icsb200_residuals* res);

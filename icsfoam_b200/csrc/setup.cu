@@ -135,7 +135,7 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
                     c->d_bfGeo, c->d_bc, c->d_phiB, c->d_vic, c->d_sendBuf, c->d_recvBuf, c->d_fields, c->d_grad, c->d_rdt, c->d_co,
                     c->d_ddtCoeff, c->d_Wold, c->d_Wold2, c->d_Wprev, c->d_src, c->d_dW, c->d_faceFlux, c->d_bad, c->d_offd, c->d_diag,
                     c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage, c->d_lusgsYZ, c->d_lusgsHint, c->d_sliceRange,
-                    c->d_faceRecon, c->d_gradE, c->d_visc, c->d_mrfFace, c->d_mrfOmega, c->d_transport, c->d_bfNbrPos, c->d_patchRot, c->d_bfAmiStart, c->d_amiAllSrc, c->d_amiAllW, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
+                    c->d_faceRecon, c->d_gradE, c->d_visc, c->d_mrfFace, c->d_mrfOmega, c->d_transport, c->d_bfNbrPos, c->d_patchRot, c->d_bfAmiStart, c->d_amiAllSrc, c->d_amiAllW, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_blkDesc, c->d_blkLcol, c->d_blkHalo, c->d_blkDep, c->d_blkStage, c->d_blkFlag, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
     for (auto& am : c->amis) { cudaFree(am.d_start); cudaFree(am.d_srcPos); cudaFree(am.d_w); }
@@ -198,7 +198,7 @@ extern "C" int icsb200_timer_end(icsb200_ctx* c, double* elapsed_ms)
 extern "C" int icsb200_schedule_info(icsb200_ctx* c, int out[8])
 {
     out[0] = c->nLevF; out[1] = c->nLevR; out[2] = c->maxWidth; out[3] = c->NP;
-    out[4] = c->tileMode ? 1 : 0; out[5] = c->nTiles; out[6] = c->nTileLevels; out[7] = c->tileTma ? 1 : 0;
+    out[4] = c->tileMode ? 1 : 0; out[5] = c->nTiles; out[6] = c->nTileLevels; out[7] = c->blkMode ? 2 : (c->tileTma ? 1 : 0);
     return 0;
 }
 
@@ -357,14 +357,23 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     std::vector<int> tileOf;  // per cell
     int nTiles = 0;
     c->tileMode = false;
+    bool blkWanted = false;
     {
         const char* env = getenv("ICSB200_LUSGS_MODE");
-        // tile mode is correct (bit-identical) but not yet faster than the level pipeline: opt-in
-        // "tile64": 64-row tiles for the TMA tile kernel (chain-bound sizes); "tile": the older ~512-row tiles
-        const bool want64 = env && std::string(env) == "tile64";
-        const bool wantTiles = env && (std::string(env) == "tile" || want64) && N >= 64;
+        const std::string mode = env ? std::string(env) : std::string("auto");
+        // "auto" / "blk": ~512-row block tiles swept by k_lusgs_blk (lusgs_blk.cu) — the default whenever the mesh allows it;
+        // "level": the level pipeline (k_lusgs_tma); "tile64": 64-row tiles for the TMA tile kernel; "tile": the older ~512-row tiles
+        const bool want64 = mode == "tile64";
+        bool wantBlk = mode == "auto" || mode == "blk";
+        if (wantBlk) {
+            // the block-tile kernel stages at most 3 lower and 3 upper neighbours per row (hex-like cells)
+            std::vector<unsigned char> nl(N, 0), nu(N, 0);
+            for (int f = 0; f < F && wantBlk; f++)
+                if (++nl[neighbour[f]] > 3 || ++nu[owner[f]] > 3) wantBlk = false;
+        }
+        const bool wantTiles = (mode == "tile" || want64 || wantBlk) && N >= 64;
         const double tileTarget = want64 ? 64.0 : 512.0;
-        const int tileRowCap = want64 ? 64 : ICS_TILE_MAXROWS - 32;
+        const int tileRowCap = want64 ? 64 : (wantBlk ? ICS_BLK_MR : ICS_TILE_MAXROWS - 32);
         c->tileTma = false;
         if (wantTiles) {
             // logical coordinates from the graph alone: u_d = longest path using only faces whose normal is mostly along
@@ -380,7 +389,21 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             }
             int active = 0;
             for (int d = 0; d < 3; d++) if (umax[d] + 1 >= 4) active++;
-            const int side = active > 0 ? std::max(2, (int)std::lround(std::pow(tileTarget, 1.0 / active))) : (int)tileTarget;
+            int side = active > 0 ? std::max(2, (int)std::lround(std::pow(tileTarget, 1.0 / active))) : (int)tileTarget;
+            if (wantBlk && active > 0) side = std::max(2, (int)std::floor(std::pow(tileTarget, 1.0 / active) + 1e-9));  // side^active <= cap
+            // disconnected copies of a mesh (Harmonic Balance instances) share logical coordinates: the connected component
+            // is a fourth tile coordinate (block tiles only; the older modes keep their layout)
+            std::vector<int> comp;
+            int nComp = 1;
+            if (wantBlk) {
+                std::vector<int> parent(N);
+                for (int i = 0; i < N; i++) parent[i] = i;
+                auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+                for (int f = 0; f < F; f++) { int a = find(owner[f]), b = find(neighbour[f]); if (a != b) parent[std::max(a, b)] = std::min(a, b); }
+                comp.assign(N, -1);
+                nComp = 0;
+                for (int i = 0; i < N; i++) { int r0 = find(i); if (comp[r0] < 0) comp[r0] = nComp++; comp[i] = comp[r0]; }
+            }
             int nb[3];
             std::vector<int> bin[3];
             for (int d = 0; d < 3; d++) {
@@ -393,15 +416,20 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             for (int f = 0; f < F && ok; f++)
                 for (int d = 0; d < 3; d++)
                     if (bin[d][neighbour[f]] < bin[d][owner[f]]) { ok = false; break; }
+            const long long nb3 = (long long)nb[0] * nb[1] * nb[2];
+            const long long nbAll = nb3 * nComp;
+            if (nbAll > (1ll << 30)) ok = false;
             if (ok) {
-                // dense tile numbering sorted by (tile level, a, b, c)
-                const long long nbAll = (long long)nb[0] * nb[1] * nb[2];
+                // dense tile numbering sorted by (tile level, component, a, b, c)
                 std::vector<int> key(N);
                 std::vector<int> cntT(nbAll, 0);
-                for (int i = 0; i < N; i++) { key[i] = bin[0][i] + nb[0] * (bin[1][i] + nb[1] * bin[2][i]); cntT[key[i]]++; }
+                for (int i = 0; i < N; i++) {
+                    key[i] = bin[0][i] + nb[0] * (bin[1][i] + nb[1] * bin[2][i]) + (nComp > 1 ? (int)(nb3 * comp[i]) : 0);
+                    cntT[key[i]]++;
+                }
                 std::vector<int> order;
                 for (long long t = 0; t < nbAll; t++) if (cntT[t] > 0) order.push_back((int)t);
-                auto tl = [&](int t) { return t % nb[0] + (t / nb[0]) % nb[1] + t / (nb[0] * nb[1]); };
+                auto tl = [&](int t) { const int t3 = (int)(t % nb3); return t3 % nb[0] + (t3 / nb[0]) % nb[1] + t3 / (nb[0] * nb[1]); };
                 std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tl(x) < tl(y); });
                 int maxRows = 0, maxTL = 0;
                 for (int t : order) { maxRows = std::max(maxRows, cntT[t]); maxTL = std::max(maxTL, tl(t)); }
@@ -413,6 +441,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                     nTiles = (int)order.size();
                     c->tileMode = true;
                     c->tileTma = want64;
+                    blkWanted = wantBlk;
                     c->nTileLevels = maxTL + 1;
                 }
             }
@@ -773,6 +802,100 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                 }
             r |= devUpload(c, &c->d_tileDescF, descF);
             r |= devUpload(c, &c->d_tileDescR, descR);
+        }
+    }
+    c->blkMode = false;
+    if (c->tileMode && blkWanted) {
+        // ---- block tiles (k_lusgs_blk): per-tile halo lists, dependency flags, local neighbour indices, staging ranges
+        const int nT = c->nTiles;
+        bool ok = true;
+        std::vector<int> sliceTile2(NP / 32, 0);
+        for (int t = 0; t < nT; t++) for (int s = tileStart[t] / 32; s < tileStart[t + 1] / 32; s++) sliceTile2[s] = t;
+        std::vector<int> desc((size_t)16 * nT, 0), haloL[2], depL[2];
+        std::vector<short> lcol((size_t)6 * NP, (short)-1);
+        auto slotOf = [&](int p, int j) { return ((size_t)c->h_sliceOff[p / 32] + j) * 32 + (p % 32); };
+        std::vector<int> tmp, tls;
+        for (int t = 0; t < nT && ok; t++) {
+            const int t0 = tileStart[t], t1 = tileStart[t + 1];
+            const int nLev = tileFPtr[t + 1] - tileFPtr[t] - 1;
+            if (t1 - t0 > ICS_BLK_MR || nLev > ICS_BLK_MAXLEV || nLev < 1) { ok = false; break; }
+            // the slices one level touches must fit in the block ring together (lusgs_blk.cu: 9 stages)
+            for (int L = 0; L < nLev; L++) if (tileFLev[tileFPtr[t] + L + 1] - tileFLev[tileFPtr[t] + L] > ICS_BLK_MAXLW) ok = false;
+            if (!ok) break;
+            int* d = desc.data() + (size_t)16 * t;
+            d[0] = t0; d[1] = t1 - t0; d[2] = tileFLev[tileFPtr[t + 1] - 1]; d[3] = nLev; d[4] = tileFPtr[t];
+            for (int sw = 0; sw < 2 && ok; sw++) {
+                tmp.clear();
+                for (int p = t0; p < t1; p++) {
+                    if (c->pos2cell[p] < 0) continue;
+                    const int nLow = c->h_rowNLow[p], nInt = c->h_rowNInt[p];
+                    if (nLow > 3 || nInt - nLow > 3) { ok = false; break; }
+                    for (int j = sw == 0 ? 0 : nLow; j < (sw == 0 ? nLow : nInt); j++) {
+                        const int q = c->h_col[slotOf(p, j)];
+                        if (q >= t0 && q < t1) continue;
+                        if (sw == 0 ? q >= t0 : q < t1) ok = false;  // the tile order must be a topological order
+                        tmp.push_back(q);
+                    }
+                }
+                std::sort(tmp.begin(), tmp.end());
+                tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+                if ((int)tmp.size() > ICS_BLK_MH) ok = false;
+                tls.clear();
+                for (int q : tmp) tls.push_back(sliceTile2[q >> 5] + (sw == 0 ? 0 : nT));  // flag index: forward t, reverse nT + t
+                std::sort(tls.begin(), tls.end());
+                tls.erase(std::unique(tls.begin(), tls.end()), tls.end());
+                if (sw == 1) tls.push_back(t);  // the reverse sweep starts from the tile's own forward values
+                if ((int)tls.size() > ICS_BLK_MAXDEP) ok = false;
+                d[5 + 2 * sw] = (int)haloL[sw].size(); d[6 + 2 * sw] = (int)tmp.size();
+                d[9 + 2 * sw] = (int)depL[sw].size(); d[10 + 2 * sw] = (int)tls.size();
+                // local neighbour indices: in-tile row, or ICS_BLK_MR + halo slot
+                for (int p = t0; p < t1 && ok; p++) {
+                    if (c->pos2cell[p] < 0) continue;
+                    const int nLow = c->h_rowNLow[p], nInt = c->h_rowNInt[p];
+                    const int n = sw == 0 ? nLow : nInt - nLow;
+                    for (int k = 0; k < n; k++) {
+                        const int j = sw == 0 ? k : nInt - 1 - k;
+                        const int q = c->h_col[slotOf(p, j)];
+                        int li;
+                        if (q >= t0 && q < t1) li = q - t0;
+                        else li = ICS_BLK_MR + (int)(std::lower_bound(tmp.begin(), tmp.end(), q) - tmp.begin());
+                        lcol[(size_t)(3 * sw + k) * NP + p] = (short)li;
+                    }
+                }
+                haloL[sw].insert(haloL[sw].end(), tmp.begin(), tmp.end());
+                depL[sw].insert(depL[sw].end(), tls.begin(), tls.end());
+            }
+        }
+        if (ok) {
+            const int hOff = (int)haloL[0].size(), dOff = (int)depL[0].size();
+            for (int t = 0; t < nT; t++) { desc[(size_t)16 * t + 7] += hOff; desc[(size_t)16 * t + 11] += dOff; }
+            haloL[0].insert(haloL[0].end(), haloL[1].begin(), haloL[1].end());
+            depL[0].insert(depL[0].end(), depL[1].begin(), depL[1].end());
+            if (haloL[0].empty()) haloL[0].push_back(0);
+            // bulk-copy ranges per sweep and slice: first staged entry (absolute entry index) and number of staged entries
+            std::vector<int> stage((size_t)4 * nSlices, 0);
+            for (int s2 = 0; s2 < nSlices; s2++) {
+                int fHi = 0, rLo = 1 << 20, rHi = 0;
+                for (int l = 0; l < 32; l++) {
+                    const int p2 = s2 * 32 + l;
+                    fHi = std::max(fHi, c->h_rowNLow[p2]);
+                    if (c->h_rowNInt[p2] > c->h_rowNLow[p2]) { rLo = std::min(rLo, c->h_rowNLow[p2]); rHi = std::max(rHi, c->h_rowNInt[p2]); }
+                }
+                if (rHi == 0) rLo = 0;
+                stage[2 * (size_t)s2] = c->h_sliceOff[s2];
+                stage[2 * (size_t)s2 + 1] = std::min(fHi, ICS_BLK_SE);
+                stage[2 * ((size_t)nSlices + s2)] = c->h_sliceOff[s2] + rLo;
+                stage[2 * ((size_t)nSlices + s2) + 1] = std::max(0, std::min(rHi - rLo, ICS_BLK_SE));
+            }
+            r |= devUpload(c, &c->d_blkDesc, desc);
+            r |= devUpload(c, &c->d_blkLcol, lcol);
+            r |= devUpload(c, &c->d_blkHalo, haloL[0]);
+            r |= devUpload(c, &c->d_blkDep, depL[0]);
+            r |= devUpload(c, &c->d_blkStage, stage);
+            r |= devAlloc(c, &c->d_blkFlag, (size_t)2 * nT);
+            if (!r) CUDA_TRY(c, cudaMemset(c->d_blkFlag, 0, sizeof(int) * 2 * nT));
+            c->blkEpoch = 0;
+            c->blkMode = true;
         }
     }
     r |= devUpload(c, &c->d_bfOwnerPos, bfOwnerPos);

@@ -1552,6 +1552,7 @@ int ics_spmv(icsb200_ctx* c, const double* x, double* y, const double* b)
 int ics_lusgs(icsb200_ctx* c, double* x)
 {
     if (!c->rDValid) { int r = ics_rdiag(c); if (r) return r; }
+    if (c->blkMode) return ics_lusgs_blk(c, x);  // block tiles, in place (lusgs_blk.cu)
     const size_t V5 = (size_t)5 * c->NPH;
     if (c->lusgsGrid == 0) {
         int perSM = 0;

@@ -361,15 +361,25 @@ def test_iterate_host_round_trip(gpu_context):
 
 @pytest.mark.parametrize("mode,make", [("tile", lambda: cases.onera_box(20)), ("tile64", lambda: cases.onera_box(20)),
                                        ("tile64", lambda: cases.onera_box(13)), ("tile64", lambda: cases.bump(24, 20)),
-                                       ("tile64", lambda: cases.periodic_box(9, "ROE", "vanLeer", seed=61, mu=0.05))])
+                                       ("tile64", lambda: cases.periodic_box(9, "ROE", "vanLeer", seed=61, mu=0.05)),
+                                       ("blk", lambda: cases.onera_box(20)), ("blk", lambda: cases.onera_box(13)),
+                                       ("blk", lambda: cases.onera_box(33)), ("blk", lambda: cases.bump(24, 20)),
+                                       ("blk", lambda: cases.bump(60, 50)),
+                                       ("blk", lambda: cases.periodic_box(9, "ROE", "vanLeer", seed=61, mu=0.05)),
+                                       ("level", lambda: cases.onera_box(13))])
 def test_lusgs_tile_mode_is_bit_identical(gpu_context, monkeypatch, mode, make):
-    """ICSB200_LUSGS_MODE=tile / tile64 (blocked wavefront schedules; tile64 = 64-row tiles swept by the TMA tile kernel) must
-    reproduce the level pipeline and the oracle bit for bit."""
+    """Every LU-SGS schedule must reproduce the sequential sweeps of the oracle (lusgs.C:220-382) bit for bit:
+    ICSB200_LUSGS_MODE=blk (block tiles swept in place by k_lusgs_blk — what `auto`, the default, picks on hex-like meshes),
+    level (the level pipeline), tile / tile64 (the older blocked wavefront schedules)."""
     monkeypatch.setenv("ICSB200_LUSGS_MODE", mode)
     case = make()
     g = case.apply(gpu_context())
-    assert g.schedule_info()["tile_mode"] and g.schedule_info()["n_tiles"] >= 8
-    assert g.schedule_info()["tile_tma"] == (mode == "tile64")
+    info = g.schedule_info()
+    if mode == "level":
+        assert not info["tile_mode"] and not info["blk"]
+    else:
+        assert info["tile_mode"] and info["n_tiles"] >= 8
+        assert info["tile_tma"] == (mode == "tile64") and info["blk"] == (mode == "blk")
     monkeypatch.delenv("ICSB200_LUSGS_MODE")
     o = case.apply(Oracle())
     for api in (g, o):
