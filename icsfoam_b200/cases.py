@@ -5,6 +5,8 @@ A `Case` bundles a mesh, thermo, schemes, solver controls, boundary conditions a
 (`icsfoam_b200.context.Context`) or the test-only oracle.  Dictionary key names follow the tutorial
 dictionaries (fvSchemes / fvSolution / thermophysicalProperties / 0/*).
 """
+import os
+
 import numpy as np
 
 from . import capi
@@ -126,6 +128,47 @@ class Case:
             raise RuntimeError("the processor directories do not cover the mesh")
         return part, meshes
 
+
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def reference_tutorials():
+    """Directory holding the reference's tutorials (input data): $ICSFOAM_REF/tutorials, else /root/reference/tutorials."""
+    for base in (os.environ.get("ICSFOAM_REF"), "/root/reference"):
+        if base and os.path.isdir(os.path.join(base, "tutorials")):
+            return os.path.join(base, "tutorials")
+    return None
+
+
+def tutorial_dir(name):
+    """Case directory of a shipped tutorial (`forwardStep`, `VKI-LS89`): the reference checkout when this machine has one,
+    else the copy `stage_tutorials()` left under cases_local/ (a GPU box has no /root/reference).  None if neither exists."""
+    ref = reference_tutorials()
+    for d in ((os.path.join(ref, name) if ref else None), os.path.join(_ROOT, "cases_local", name)):
+        if d and os.path.isdir(os.path.join(d, "constant", "polyMesh")):
+            return d
+    return None
+
+
+def stage_tutorials(names=("forwardStep", "VKI-LS89")):
+    """Copy the tutorial directories the C2 / C5 tests run on from the reference checkout into cases_local/ (git-ignored
+    input data — meshes and dictionaries, no sources — that travels to the GPU box with the working tree).  Called by
+    __graft_entry__.build(); a no-op on a machine without the reference."""
+    import shutil
+    ref = reference_tutorials()
+    if not ref:
+        return []
+    done = []
+    for n in names:
+        src, dst = os.path.join(ref, n), os.path.join(_ROOT, "cases_local", n)
+        if os.path.isdir(src) and not os.path.isdir(os.path.join(dst, "constant", "polyMesh")):
+            shutil.copytree(src, dst, dirs_exist_ok=True)
+            for r, ds, fs in os.walk(dst):   # the reference tree is read-only; the copy must be removable
+                for x in ds + fs:
+                    os.chmod(os.path.join(r, x), 0o755 if x in ds or os.access(os.path.join(r, x), os.X_OK) else 0o644)
+            done.append(n)
+    return done
 
 def _uniform(mesh, p, U, T):
     N = mesh.n_cells

@@ -34,7 +34,8 @@
 #define ICS_BLK_MAXLEV 127
 #define ICS_BLK_MAXDEP 32
 #define ICS_BLK_SE 3
-#define ICS_BLK_MAXLW 160  // widest intra-tile level
+#define ICS_BLK_MAXLW 128  // widest intra-tile level
+#define ICS_BLK_TAB 768    // ints of a tile's table
 
 constexpr int NQ = 8;   // reconstructed scalars: rho, p, Ux, Uy, Uz, cR, E, H
 constexpr int NG = 7;   // geometry doubles per face (SoA over GPU face ids)
@@ -141,10 +142,10 @@ struct icsb200_ctx {
     int* d_sliceTile = nullptr;  // [nSlices] tile of a slice
     // block-tile sweep (k_lusgs_blk, the default schedule when the mesh allows it; solver.cu "block tiles")
     bool blkMode = false;
-    int* d_blkDesc = nullptr;    // [nTiles][16] tile descriptor (BD_*)
-    short* d_blkLcol = nullptr;  // [6][NP] local neighbour index of a row: 0..2 lower (entry order), 3..5 upper (descending entry order); -1 none
-    int* d_blkHalo = nullptr;    // concatenated out-of-tile neighbour positions (forward lists, then reverse lists)
-    int* d_blkDep = nullptr;     // concatenated flag indices a tile waits for (forward lists, then reverse lists)
+    int* d_blkTab = nullptr;     // per-tile tables (setup.cu "block tiles")
+    int* d_blkIdx = nullptr;     // [nTiles][4] table offset, table length, first position, rows
+    unsigned long long* d_blkInfo = nullptr;  // [2][NP] packed per-row neighbour info of the forward / reverse sweep
+    long long* d_blkProf = nullptr;           // optional per-CTA phase cycle counters (ICSB200_LUSGS_PROF)
     int* d_blkStage = nullptr;   // [2][nSlices][2] per sweep and slice: first staged block entry, number of staged entries
     int* d_blkFlag = nullptr;    // [2*nTiles] completion epochs: forward sweep of tile t, reverse sweep of tile t
     int blkEpoch = 0;

@@ -135,7 +135,7 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
                     c->d_bfGeo, c->d_bc, c->d_phiB, c->d_vic, c->d_sendBuf, c->d_recvBuf, c->d_fields, c->d_grad, c->d_rdt, c->d_co,
                     c->d_ddtCoeff, c->d_Wold, c->d_Wold2, c->d_Wprev, c->d_src, c->d_dW, c->d_faceFlux, c->d_bad, c->d_offd, c->d_diag,
                     c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage, c->d_lusgsYZ, c->d_lusgsHint, c->d_sliceRange,
-                    c->d_faceRecon, c->d_gradE, c->d_visc, c->d_mrfFace, c->d_mrfOmega, c->d_transport, c->d_bfNbrPos, c->d_patchRot, c->d_bfAmiStart, c->d_amiAllSrc, c->d_amiAllW, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_blkDesc, c->d_blkLcol, c->d_blkHalo, c->d_blkDep, c->d_blkStage, c->d_blkFlag, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
+                    c->d_faceRecon, c->d_gradE, c->d_visc, c->d_mrfFace, c->d_mrfOmega, c->d_transport, c->d_bfNbrPos, c->d_patchRot, c->d_bfAmiStart, c->d_amiAllSrc, c->d_amiAllW, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_blkTab, c->d_blkIdx, c->d_blkInfo, c->d_blkStage, c->d_blkFlag, c->d_blkProf, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
     for (auto& am : c->amis) { cudaFree(am.d_start); cudaFree(am.d_srcPos); cudaFree(am.d_w); }
@@ -806,26 +806,43 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     }
     c->blkMode = false;
     if (c->tileMode && blkWanted) {
-        // ---- block tiles (k_lusgs_blk): per-tile halo lists, dependency flags, local neighbour indices, staging ranges
+        // ---- block tiles (k_lusgs_blk, lusgs_blk.cu): everything a tile's sweep needs besides the 5x5 blocks, laid out so the
+        // kernel's producer warp can fetch it with a handful of 16-byte-aligned bulk copies:
+        //  blkTab  per tile [16 descriptor ints][level starts][forward halo positions][reverse halo positions][forward flags to
+        //          wait for][reverse flags][first entry of each slice][first reverse-staged entry of each slice], every section
+        //          padded to 4 ints (BT_* in lusgs_blk.cu);  blkIdx per tile {table offset, table length, t0, rows}
+        //  blkInfo per sweep and row, 64 bits: for neighbour t = 0..2 (forward: ascending lower entries, reverse: descending
+        //          upper entries) 10 bits local index (row of the tile, or ICS_BLK_MR + halo slot), 2 bits staged block slot
+        //          (3 = not staged: read from global), 3 bits entry index; bits 45..46 = number of neighbours
         const int nT = c->nTiles;
         bool ok = true;
         std::vector<int> sliceTile2(NP / 32, 0);
         for (int t = 0; t < nT; t++) for (int s = tileStart[t] / 32; s < tileStart[t + 1] / 32; s++) sliceTile2[s] = t;
-        std::vector<int> desc((size_t)16 * nT, 0), haloL[2], depL[2];
-        std::vector<short> lcol((size_t)6 * NP, (short)-1);
+        std::vector<int> sFwdHi(nSlices, 0), sRevLo(nSlices, 0), sRevHi(nSlices, 0);
+        for (int s2 = 0; s2 < nSlices; s2++) {
+            int fHi = 0, rLo = 1 << 20, rHi = 0;
+            for (int l = 0; l < 32; l++) {
+                const int p2 = s2 * 32 + l;
+                fHi = std::max(fHi, c->h_rowNLow[p2]);
+                if (c->h_rowNInt[p2] > c->h_rowNLow[p2]) { rLo = std::min(rLo, c->h_rowNLow[p2]); rHi = std::max(rHi, c->h_rowNInt[p2]); }
+            }
+            if (rHi == 0) rLo = 0;
+            sFwdHi[s2] = fHi; sRevLo[s2] = rLo; sRevHi[s2] = rHi;
+        }
+        std::vector<int> tab, idx((size_t)4 * nT, 0);
+        std::vector<unsigned long long> info((size_t)2 * NP, 0ull);
         auto slotOf = [&](int p, int j) { return ((size_t)c->h_sliceOff[p / 32] + j) * 32 + (p % 32); };
-        std::vector<int> tmp, tls;
+        auto pad4 = [&]() { while (tab.size() % 4) tab.push_back(0); };
+        std::vector<int> tmp[2], tls[2];
         for (int t = 0; t < nT && ok; t++) {
             const int t0 = tileStart[t], t1 = tileStart[t + 1];
             const int nLev = tileFPtr[t + 1] - tileFPtr[t] - 1;
+            const int nSl = (t1 - t0) / 32;
             if (t1 - t0 > ICS_BLK_MR || nLev > ICS_BLK_MAXLEV || nLev < 1) { ok = false; break; }
-            // the slices one level touches must fit in the block ring together (lusgs_blk.cu: 9 stages)
+            // the slices one level touches must fit in the block ring together (lusgs_blk.cu)
             for (int L = 0; L < nLev; L++) if (tileFLev[tileFPtr[t] + L + 1] - tileFLev[tileFPtr[t] + L] > ICS_BLK_MAXLW) ok = false;
-            if (!ok) break;
-            int* d = desc.data() + (size_t)16 * t;
-            d[0] = t0; d[1] = t1 - t0; d[2] = tileFLev[tileFPtr[t + 1] - 1]; d[3] = nLev; d[4] = tileFPtr[t];
             for (int sw = 0; sw < 2 && ok; sw++) {
-                tmp.clear();
+                tmp[sw].clear();
                 for (int p = t0; p < t1; p++) {
                     if (c->pos2cell[p] < 0) continue;
                     const int nLow = c->h_rowNLow[p], nInt = c->h_rowNInt[p];
@@ -834,63 +851,71 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                         const int q = c->h_col[slotOf(p, j)];
                         if (q >= t0 && q < t1) continue;
                         if (sw == 0 ? q >= t0 : q < t1) ok = false;  // the tile order must be a topological order
-                        tmp.push_back(q);
+                        tmp[sw].push_back(q);
                     }
                 }
-                std::sort(tmp.begin(), tmp.end());
-                tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-                if ((int)tmp.size() > ICS_BLK_MH) ok = false;
-                tls.clear();
-                for (int q : tmp) tls.push_back(sliceTile2[q >> 5] + (sw == 0 ? 0 : nT));  // flag index: forward t, reverse nT + t
-                std::sort(tls.begin(), tls.end());
-                tls.erase(std::unique(tls.begin(), tls.end()), tls.end());
-                if (sw == 1) tls.push_back(t);  // the reverse sweep starts from the tile's own forward values
-                if ((int)tls.size() > ICS_BLK_MAXDEP) ok = false;
-                d[5 + 2 * sw] = (int)haloL[sw].size(); d[6 + 2 * sw] = (int)tmp.size();
-                d[9 + 2 * sw] = (int)depL[sw].size(); d[10 + 2 * sw] = (int)tls.size();
-                // local neighbour indices: in-tile row, or ICS_BLK_MR + halo slot
+                std::sort(tmp[sw].begin(), tmp[sw].end());
+                tmp[sw].erase(std::unique(tmp[sw].begin(), tmp[sw].end()), tmp[sw].end());
+                if ((int)tmp[sw].size() > ICS_BLK_MH) ok = false;
+                tls[sw].clear();
+                for (int q : tmp[sw]) tls[sw].push_back(sliceTile2[q >> 5] + (sw == 0 ? 0 : nT));  // flag index: forward t, reverse nT + t
+                std::sort(tls[sw].begin(), tls[sw].end());
+                tls[sw].erase(std::unique(tls[sw].begin(), tls[sw].end()), tls[sw].end());
+                if (sw == 1) tls[sw].push_back(t);  // the reverse sweep starts from the tile's own forward values
+                if ((int)tls[sw].size() > ICS_BLK_MAXDEP) ok = false;
                 for (int p = t0; p < t1 && ok; p++) {
                     if (c->pos2cell[p] < 0) continue;
                     const int nLow = c->h_rowNLow[p], nInt = c->h_rowNInt[p];
                     const int n = sw == 0 ? nLow : nInt - nLow;
+                    const int s2 = p / 32;
+                    const int lo = sw == 0 ? 0 : sRevLo[s2];
+                    const int cnt = sw == 0 ? std::min(sFwdHi[s2], ICS_BLK_SE) : std::max(0, std::min(sRevHi[s2] - sRevLo[s2], ICS_BLK_SE));
+                    unsigned long long w = (unsigned long long)n << 45;
                     for (int k = 0; k < n; k++) {
                         const int j = sw == 0 ? k : nInt - 1 - k;
                         const int q = c->h_col[slotOf(p, j)];
                         int li;
                         if (q >= t0 && q < t1) li = q - t0;
-                        else li = ICS_BLK_MR + (int)(std::lower_bound(tmp.begin(), tmp.end(), q) - tmp.begin());
-                        lcol[(size_t)(3 * sw + k) * NP + p] = (short)li;
+                        else li = ICS_BLK_MR + (int)(std::lower_bound(tmp[sw].begin(), tmp[sw].end(), q) - tmp[sw].begin());
+                        const int js = j - lo;
+                        const int code = (js >= 0 && js < cnt) ? js : 3;
+                        if (j > 7) ok = false;
+                        w |= (unsigned long long)(li | (code << 10) | (j << 12)) << (15 * k);
                     }
+                    info[(size_t)sw * NP + p] = w;
                 }
-                haloL[sw].insert(haloL[sw].end(), tmp.begin(), tmp.end());
-                depL[sw].insert(depL[sw].end(), tls.begin(), tls.end());
             }
+            if (!ok) break;
+            pad4();
+            const int off = (int)tab.size();
+            tab.resize(off + 16, 0);
+            auto section = [&](const std::vector<int>& v) { const int o = (int)tab.size() - off; tab.insert(tab.end(), v.begin(), v.end()); pad4(); return o; };
+            std::vector<int> lv(tileFLev.begin() + tileFPtr[t], tileFLev.begin() + tileFPtr[t + 1]);
+            std::vector<int> so(c->h_sliceOff.begin() + t0 / 32, c->h_sliceOff.begin() + t0 / 32 + nSl), rl(sRevLo.begin() + t0 / 32, sRevLo.begin() + t0 / 32 + nSl);
+            int d[16] = {0};
+            d[0] = t0; d[1] = t1 - t0; d[2] = lv.back(); d[3] = nLev;
+            d[4] = section(lv);
+            d[5] = section(tmp[0]); d[6] = (int)tmp[0].size();
+            d[7] = section(tmp[1]); d[8] = (int)tmp[1].size();
+            d[9] = section(tls[0]); d[10] = (int)tls[0].size();
+            d[11] = section(tls[1]); d[12] = (int)tls[1].size();
+            d[13] = section(so); d[14] = section(rl); d[15] = nSl;
+            for (int k = 0; k < 16; k++) tab[off + k] = d[k];
+            idx[(size_t)4 * t] = off; idx[(size_t)4 * t + 1] = (int)tab.size() - off; idx[(size_t)4 * t + 2] = t0; idx[(size_t)4 * t + 3] = t1 - t0;
+            if ((int)tab.size() - off > ICS_BLK_TAB) ok = false;
         }
         if (ok) {
-            const int hOff = (int)haloL[0].size(), dOff = (int)depL[0].size();
-            for (int t = 0; t < nT; t++) { desc[(size_t)16 * t + 7] += hOff; desc[(size_t)16 * t + 11] += dOff; }
-            haloL[0].insert(haloL[0].end(), haloL[1].begin(), haloL[1].end());
-            depL[0].insert(depL[0].end(), depL[1].begin(), depL[1].end());
-            if (haloL[0].empty()) haloL[0].push_back(0);
             // bulk-copy ranges per sweep and slice: first staged entry (absolute entry index) and number of staged entries
             std::vector<int> stage((size_t)4 * nSlices, 0);
             for (int s2 = 0; s2 < nSlices; s2++) {
-                int fHi = 0, rLo = 1 << 20, rHi = 0;
-                for (int l = 0; l < 32; l++) {
-                    const int p2 = s2 * 32 + l;
-                    fHi = std::max(fHi, c->h_rowNLow[p2]);
-                    if (c->h_rowNInt[p2] > c->h_rowNLow[p2]) { rLo = std::min(rLo, c->h_rowNLow[p2]); rHi = std::max(rHi, c->h_rowNInt[p2]); }
-                }
-                if (rHi == 0) rLo = 0;
                 stage[2 * (size_t)s2] = c->h_sliceOff[s2];
-                stage[2 * (size_t)s2 + 1] = std::min(fHi, ICS_BLK_SE);
-                stage[2 * ((size_t)nSlices + s2)] = c->h_sliceOff[s2] + rLo;
-                stage[2 * ((size_t)nSlices + s2) + 1] = std::max(0, std::min(rHi - rLo, ICS_BLK_SE));
+                stage[2 * (size_t)s2 + 1] = std::min(sFwdHi[s2], ICS_BLK_SE);
+                stage[2 * ((size_t)nSlices + s2)] = c->h_sliceOff[s2] + sRevLo[s2];
+                stage[2 * ((size_t)nSlices + s2) + 1] = std::max(0, std::min(sRevHi[s2] - sRevLo[s2], ICS_BLK_SE));
             }
-            r |= devUpload(c, &c->d_blkDesc, desc);
-            r |= devUpload(c, &c->d_blkLcol, lcol);
-            r |= devUpload(c, &c->d_blkHalo, haloL[0]);
-            r |= devUpload(c, &c->d_blkDep, depL[0]);
+            r |= devUpload(c, &c->d_blkTab, tab);
+            r |= devUpload(c, &c->d_blkIdx, idx);
+            r |= devUpload(c, &c->d_blkInfo, info);
             r |= devUpload(c, &c->d_blkStage, stage);
             r |= devAlloc(c, &c->d_blkFlag, (size_t)2 * nT);
             if (!r) CUDA_TRY(c, cudaMemset(c->d_blkFlag, 0, sizeof(int) * 2 * nT));

@@ -96,7 +96,7 @@ def main_vki(rank, world, local, ids, prepared=None):
     if prepared is not None:
         case, meshes = prepared
     else:
-        case = cases.vki_ls89(os.path.join(root, "cases_local", "VKI-LS89", "constant", "polyMesh"))
+        case = cases.vki_ls89(os.path.join(cases.tutorial_dir("VKI-LS89"), "constant", "polyMesh"))
         part, meshes = case.partition(world, "x")
     m = meshes[rank]
     ctx = case.apply(Context(device=local, nccl_id=ids[0], rank=rank, n_ranks=world), mesh=m, cells=m.cell_global)

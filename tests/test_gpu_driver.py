@@ -28,10 +28,10 @@ def run_driver(case_dir, steps):
 
 
 def staged(name):
-    return os.path.join(ROOT, "cases_local", name)
+    return cases.tutorial_dir(name) or os.path.join(ROOT, "cases_local", name)
 
 
-@pytest.mark.skipif(not os.path.isdir(staged("VKI-LS89") + "/system"), reason="VKI-LS89 tutorial not staged (cases_local/ is not part of the repository)")
+@pytest.mark.skipif(not os.path.isdir(staged("VKI-LS89") + "/system"), reason="VKI-LS89 tutorial not staged ($ICSFOAM_REF, /root/reference or the copy build() stages under cases_local/)")
 def test_driver_runs_vki_ls89_tutorial_directory(gpu_context):
     init, its = run_driver(staged("VKI-LS89"), 6)
     case = cases.vki_ls89(staged("VKI-LS89") + "/constant/polyMesh")
@@ -43,7 +43,7 @@ def test_driver_runs_vki_ls89_tutorial_directory(gpu_context):
         assert np.abs(init[k][:4] - want[:4]).max() <= 1e-5 * np.abs(want[:4]).max(), (k, init[k], want)   # 6 printed digits
 
 
-@pytest.mark.skipif(not os.path.isdir(staged("forwardStep") + "/system"), reason="forwardStep tutorial not staged (cases_local/ is not part of the repository)")
+@pytest.mark.skipif(not os.path.isdir(staged("forwardStep") + "/system"), reason="forwardStep tutorial not staged ($ICSFOAM_REF, /root/reference or the copy build() stages under cases_local/)")
 def test_driver_runs_forward_step_tutorial_directory(gpu_context):
     init, its = run_driver(staged("forwardStep"), 1)     # one physical time step = up to nPseudoCorr pseudo iterations
     case = cases.forward_step(staged("forwardStep") + "/constant/polyMesh")
@@ -57,7 +57,7 @@ def test_driver_runs_forward_step_tutorial_directory(gpu_context):
         assert np.abs(init[k][:4] - want[:4]).max() <= 1e-5 * np.abs(want[:4]).max(), (k, init[k], want)
 
 
-@pytest.mark.skipif(not os.path.isdir(staged("VKI-LS89") + "/system"), reason="VKI-LS89 tutorial not staged (cases_local/ is not part of the repository)")
+@pytest.mark.skipif(not os.path.isdir(staged("VKI-LS89") + "/system"), reason="VKI-LS89 tutorial not staged ($ICSFOAM_REF, /root/reference or the copy build() stages under cases_local/)")
 def test_driver_writes_a_time_directory_that_it_can_read_back(gpu_context, tmp_path):
     """-writeFields: p, U, T of the last step as <case>/<time>/{p,U,T}; the written internalField lists equal the state of the
     Python host path after the same 3 iterations to the 17 printed digits, and the files parse as `nonuniform List<...>` fields

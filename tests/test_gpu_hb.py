@@ -193,10 +193,10 @@ def test_hb_against_golden_fixture(gpu_context):
 
 import os  # noqa: E402
 
-LOCAL_VKI = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cases_local", "VKI-LS89", "constant", "polyMesh")
+LOCAL_VKI = os.path.join(cases.tutorial_dir("VKI-LS89") or "/nonexistent", "constant", "polyMesh")
 
 
-@pytest.mark.skipif(not os.path.isdir(LOCAL_VKI), reason="VKI-LS89 tutorial mesh not staged (cases_local/ is not part of the repository)")
+@pytest.mark.skipif(not os.path.isdir(LOCAL_VKI), reason="VKI-LS89 tutorial not found ($ICSFOAM_REF, /root/reference or the copy build() stages under cases_local/)")
 def test_hb_vki_ls89_c5(gpu_context):
     """C5 (ii): Harmonic Balance with 3 time instances on the shipped VKI-LS89 mesh (84 177 coupled cells, cyclic pair,
     laminar viscous, ROE): HB sources and pseudo time step bit for bit, then 4 outer iterations of the (2 nO, nO) system."""

@@ -5,6 +5,7 @@ import sys
 
 import pytest
 
+from icsfoam_b200 import cases
 from tests.conftest import ROOT
 
 pytestmark = pytest.mark.gpu
@@ -22,8 +23,8 @@ def _ngpu():
 @pytest.mark.parametrize("world,mu,variant", [(2, "0", ""), (2, "0.3", ""), (2, "0", "globaldt"), (2, "0", "mrf"), (2, "0", "hb"), (2, "0.3", "fullvisc"), (2, "0", "vki"),
                                                  (2, "0", "decomposed")])   # decomposed: processorN directories as input (first 2-GPU run pending)
 def test_multi_gpu_matches_partitioned_oracle(world, mu, variant):
-    if variant == "vki" and not os.path.isdir(os.path.join(ROOT, "cases_local", "VKI-LS89", "constant", "polyMesh")):
-        pytest.skip("VKI-LS89 tutorial mesh not staged (cases_local/ is not part of the repository)")
+    if variant == "vki" and cases.tutorial_dir("VKI-LS89") is None:
+        pytest.skip("VKI-LS89 tutorial not found ($ICSFOAM_REF, /root/reference or the copy build() stages under cases_local/)")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29544", ICS_MULTI_MU=mu, ICS_MULTI_VARIANT=variant)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
                         "127.0.0.1", "--master-port", "29544", os.path.join(ROOT, "tests", "multi_gpu_check.py")],

@@ -24,9 +24,7 @@ def _load(path, name):
 
 
 def build_case(tutorial):
-    ref = "/root/reference/tutorials"
-    local = os.path.join(ROOT, "cases_local")
-    pick = lambda name: next((d for d in (os.path.join(local, name), os.path.join(ref, name)) if os.path.isdir(d)), None)
+    pick = cases.tutorial_dir
     if tutorial == "shockTube":
         return cases.shock_tube(500, "ROE")
     if tutorial == "bump":

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DRIVER = os.path.join(ROOT, "icsfoam_b200", "host", "dbnsB200")
 MESHLIB = os.path.join(ROOT, "icsfoam_b200", "meshtools", "libicsmesh.so")
-STAGED = os.path.join(ROOT, "cases_local", "VKI-LS89")
+STAGED = cases.tutorial_dir("VKI-LS89") or os.path.join(ROOT, "cases_local", "VKI-LS89")
 
 
 def _load(path, name):
@@ -27,7 +27,7 @@ def _load(path, name):
     return mod
 
 
-@pytest.mark.skipif(not os.path.isdir(STAGED + "/system"), reason="VKI-LS89 tutorial not staged (cases_local/ is not part of the repository)")
+@pytest.mark.skipif(not os.path.isdir(STAGED + "/system"), reason="VKI-LS89 tutorial not staged ($ICSFOAM_REF, /root/reference or the copy build() stages under cases_local/)")
 def test_write_flux_directory_matches_the_host_path(gpu_context, tmp_path):
     fd = _load(os.path.join(ROOT, "tools", "foamdiff.py"), "foamdiff")
     cm = _load(os.path.join(ROOT, "tools", "openfoam_golden", "compare_matrix.py"), "compare_matrix")
