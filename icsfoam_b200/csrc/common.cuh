@@ -29,13 +29,13 @@
 #define ICS_VGREAT 1e300
 #define ICS_TILE_MAXROWS 1024  // rows a LU-SGS tile may hold (shared-memory staging of 5 doubles per row)
 // block tiles (k_lusgs_blk): rows per tile, out-of-tile neighbours per sweep, intra-tile levels, tiles waited for, staged entries per slice
-#define ICS_BLK_MR 512
-#define ICS_BLK_MH 256
-#define ICS_BLK_MAXLEV 127
+#define ICS_BLK_MR 256
+#define ICS_BLK_MH 160
+#define ICS_BLK_MAXLEV 63
 #define ICS_BLK_MAXDEP 32
 #define ICS_BLK_SE 3
 #define ICS_BLK_MAXLW 128  // widest intra-tile level
-#define ICS_BLK_TAB 768    // ints of a tile's table
+#define ICS_BLK_TAB 512    // ints of a tile's table
 
 constexpr int NQ = 8;   // reconstructed scalars: rho, p, Ux, Uy, Uz, cR, E, H
 constexpr int NG = 7;   // geometry doubles per face (SoA over GPU face ids)
@@ -146,6 +146,7 @@ struct icsb200_ctx {
     int* d_blkIdx = nullptr;     // [nTiles][4] table offset, table length, first position, rows
     unsigned long long* d_blkInfo = nullptr;  // [2][NP] packed per-row neighbour info of the forward / reverse sweep
     long long* d_blkProf = nullptr;           // optional per-CTA phase cycle counters (ICSB200_LUSGS_PROF)
+    long long* d_blkTrace = nullptr;          // optional per-tile global-timer stamps (ICSB200_LUSGS_TRACE)
     int* d_blkStage = nullptr;   // [2][nSlices][2] per sweep and slice: first staged block entry, number of staged entries
     int* d_blkFlag = nullptr;    // [2*nTiles] completion epochs: forward sweep of tile t, reverse sweep of tile t
     int blkEpoch = 0;

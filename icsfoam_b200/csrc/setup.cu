@@ -135,7 +135,7 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
                     c->d_bfGeo, c->d_bc, c->d_phiB, c->d_vic, c->d_sendBuf, c->d_recvBuf, c->d_fields, c->d_grad, c->d_rdt, c->d_co,
                     c->d_ddtCoeff, c->d_Wold, c->d_Wold2, c->d_Wprev, c->d_src, c->d_dW, c->d_faceFlux, c->d_bad, c->d_offd, c->d_diag,
                     c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage, c->d_lusgsYZ, c->d_lusgsHint, c->d_sliceRange,
-                    c->d_faceRecon, c->d_gradE, c->d_visc, c->d_mrfFace, c->d_mrfOmega, c->d_transport, c->d_bfNbrPos, c->d_patchRot, c->d_bfAmiStart, c->d_amiAllSrc, c->d_amiAllW, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_blkTab, c->d_blkIdx, c->d_blkInfo, c->d_blkStage, c->d_blkFlag, c->d_blkProf, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
+                    c->d_faceRecon, c->d_gradE, c->d_visc, c->d_mrfFace, c->d_mrfOmega, c->d_transport, c->d_bfNbrPos, c->d_patchRot, c->d_bfAmiStart, c->d_amiAllSrc, c->d_amiAllW, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_blkTab, c->d_blkIdx, c->d_blkInfo, c->d_blkStage, c->d_blkFlag, c->d_blkProf, c->d_blkTrace, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
     for (auto& am : c->amis) { cudaFree(am.d_start); cudaFree(am.d_srcPos); cudaFree(am.d_w); }
@@ -372,7 +372,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                 if (++nl[neighbour[f]] > 3 || ++nu[owner[f]] > 3) wantBlk = false;
         }
         const bool wantTiles = (mode == "tile" || want64 || wantBlk) && N >= 64;
-        const double tileTarget = want64 ? 64.0 : 512.0;
+        const double tileTarget = want64 ? 64.0 : (wantBlk ? (double)ICS_BLK_MR : 512.0);
         const int tileRowCap = want64 ? 64 : (wantBlk ? ICS_BLK_MR : ICS_TILE_MAXROWS - 32);
         c->tileTma = false;
         if (wantTiles) {
@@ -404,45 +404,126 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                 nComp = 0;
                 for (int i = 0; i < N; i++) { int r0 = find(i); if (comp[r0] < 0) comp[r0] = nComp++; comp[i] = comp[r0]; }
             }
-            int nb[3];
-            std::vector<int> bin[3];
-            for (int d = 0; d < 3; d++) {
-                const bool act = umax[d] + 1 >= 4;
-                nb[d] = act ? (umax[d] + side) / side : 1;
-                bin[d].assign(N, 0);
-                if (act) for (int i = 0; i < N; i++) bin[d][i] = u[d][i] / side;
-            }
-            bool ok = true;
-            for (int f = 0; f < F && ok; f++)
-                for (int d = 0; d < 3; d++)
-                    if (bin[d][neighbour[f]] < bin[d][owner[f]]) { ok = false; break; }
-            const long long nb3 = (long long)nb[0] * nb[1] * nb[2];
-            const long long nbAll = nb3 * nComp;
-            if (nbAll > (1ll << 30)) ok = false;
-            if (ok) {
-                // dense tile numbering sorted by (tile level, component, a, b, c)
-                std::vector<int> key(N);
-                std::vector<int> cntT(nbAll, 0);
-                for (int i = 0; i < N; i++) {
-                    key[i] = bin[0][i] + nb[0] * (bin[1][i] + nb[1] * bin[2][i]) + (nComp > 1 ? (int)(nb3 * comp[i]) : 0);
-                    cntT[key[i]]++;
+            if (wantBlk) {
+                // ---- skewed column tiles.  The longest active axis is the sweep axis; the other active axes are cut into
+                // blocks of bx (x by) cells, which gives columns along the sweep axis.  A cell's local level is
+                // s = sum over the cross axes of (u mod b) + u_sweep — the forward hyperplane index inside its column — and a
+                // tile is `depth` consecutive local levels of one column.  Away from the column ends every intra-tile level is a
+                // full bx*by rows wide (a cube tile of the same size spends most of its levels filling and draining the
+                // wavefront: 22 levels of 23 rows on average for 8^3 against 8 levels of 64 rows), and the dependency chain
+                // between tiles stays the hyperplane count / depth.  A face that leaves a column through a block boundary goes
+                // from local level s to s - (b-1), i.e. at most ceil((b-1)/depth) chunks back, so TL = sum K_a bin_a + chunk with
+                // K_a = ceil((b_a-1)/depth) + 1 ranks the tile graph; every face is checked against it (any mesh that fails
+                // falls back to the level pipeline).
+                int sweep = -1;
+                for (int d = 0; d < 3; d++) if (umax[d] + 1 >= 4 && (sweep < 0 || umax[d] > umax[sweep])) sweep = d;
+                auto envInt = [](const char* name, int dflt) { const char* e = getenv(name); return e ? std::max(1, atoi(e)) : dflt; };
+                const int nCross = active > 0 ? active - 1 : 0;
+                int bside = nCross == 2 ? 8 : (nCross == 1 ? 16 : 1);
+                bside = envInt("ICSB200_LUSGS_BSIDE", bside);
+                int depth = nCross == 2 ? 4 : (nCross == 1 ? 16 : 32);
+                depth = envInt("ICSB200_LUSGS_DEPTH", depth);
+                int bs[3] = {1, 1, 1}, nbin[3] = {1, 1, 1}, K[3] = {0, 0, 0};
+                for (int d = 0; d < 3; d++) {
+                    if (d == sweep || umax[d] + 1 < 4) continue;
+                    bs[d] = bside;
+                    nbin[d] = umax[d] / bside + 1;
+                    K[d] = (bside - 1 + depth - 1) / depth + 1;
                 }
-                std::vector<int> order;
-                for (long long t = 0; t < nbAll; t++) if (cntT[t] > 0) order.push_back((int)t);
-                auto tl = [&](int t) { const int t3 = (int)(t % nb3); return t3 % nb[0] + (t3 / nb[0]) % nb[1] + t3 / (nb[0] * nb[1]); };
-                std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tl(x) < tl(y); });
-                int maxRows = 0, maxTL = 0;
-                for (int t : order) { maxRows = std::max(maxRows, cntT[t]); maxTL = std::max(maxTL, tl(t)); }
-                if (maxRows <= tileRowCap) {
-                    std::vector<int> dense(nbAll, -1);
-                    for (size_t k = 0; k < order.size(); k++) dense[order[k]] = (int)k;
-                    tileOf.resize(N);
-                    for (int i = 0; i < N; i++) tileOf[i] = dense[key[i]];
-                    nTiles = (int)order.size();
-                    c->tileMode = true;
-                    c->tileTma = want64;
-                    blkWanted = wantBlk;
-                    c->nTileLevels = maxTL + 1;
+                int sMax = sweep >= 0 ? umax[sweep] : 0;
+                for (int d = 0; d < 3; d++) if (d != sweep) sMax += (umax[d] + 1 < 4) ? umax[d] : bs[d] - 1;
+                const int nChunk = sMax / depth + 1;
+                const long long nb3 = (long long)nbin[0] * nbin[1] * nbin[2] * nChunk;
+                const long long nbAll = nb3 * nComp;
+                bool ok = sweep >= 0 && nbAll <= (1ll << 30) && (long long)bs[0] * bs[1] * bs[2] * depth <= tileRowCap;
+                if (ok) {
+                    std::vector<int> key(N), tlOf(N);
+                    for (int i = 0; i < N; i++) {
+                        int s2 = u[sweep][i], b3 = 0, mul = 1, tl2 = 0;
+                        for (int d = 0; d < 3; d++) {
+                            if (d == sweep) continue;
+                            // inactive axes (fewer than 4 layers) keep their full extent inside the column
+                            if (bs[d] == 1 && nbin[d] == 1) { s2 += u[d][i]; continue; }
+                            const int bn = u[d][i] / bs[d];
+                            s2 += u[d][i] - bn * bs[d];
+                            b3 += mul * bn; mul *= nbin[d];
+                            tl2 += K[d] * bn;
+                        }
+                        const int ch = std::min(s2 / depth, nChunk - 1);
+                        key[i] = b3 + mul * ch + (nComp > 1 ? (int)(nb3 * comp[i]) : 0);
+                        tlOf[i] = tl2 + ch;
+                    }
+                    for (int f = 0; f < F && ok; f++)
+                        if (key[owner[f]] != key[neighbour[f]] && tlOf[owner[f]] >= tlOf[neighbour[f]]) ok = false;
+                    if (ok) {
+                        // tile order: by tile level; inside a level by descending chunk = ascending column index sum, so that every
+                        // tile a tile waits for sits at the same or an earlier relative place of the previous level — with
+                        // round-robin dealing of tiles to CTAs that maximises the distance (in tiles) to a dependency
+                        std::vector<int> cntT(nbAll, 0), tlT(nbAll, 0), chT(nbAll, 0);
+                        for (int i = 0; i < N; i++) { cntT[key[i]]++; tlT[key[i]] = tlOf[i]; }
+                        {
+                            long long mulAll = 1;
+                            for (int d = 0; d < 3; d++) if (d != sweep && !(bs[d] == 1 && nbin[d] == 1)) mulAll *= nbin[d];
+                            for (long long t = 0; t < nbAll; t++) chT[t] = (int)((t % nb3) / mulAll);
+                        }
+                        std::vector<int> order;
+                        for (long long t = 0; t < nbAll; t++) if (cntT[t] > 0) order.push_back((int)t);
+                        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tlT[x] != tlT[y] ? tlT[x] < tlT[y] : chT[x] > chT[y]; });
+                        int maxRows = 0, maxTL = 0;
+                        for (int t : order) { maxRows = std::max(maxRows, cntT[t]); maxTL = std::max(maxTL, tlT[t]); }
+                        if (maxRows <= tileRowCap) {
+                            std::vector<int> dense(nbAll, -1);
+                            for (size_t k = 0; k < order.size(); k++) dense[order[k]] = (int)k;
+                            tileOf.resize(N);
+                            for (int i = 0; i < N; i++) tileOf[i] = dense[key[i]];
+                            nTiles = (int)order.size();
+                            c->tileMode = true;
+                            blkWanted = true;
+                            c->nTileLevels = maxTL + 1;
+                        }
+                    }
+                }
+            } else {
+                int nb[3];
+                std::vector<int> bin[3];
+                for (int d = 0; d < 3; d++) {
+                    const bool act = umax[d] + 1 >= 4;
+                    nb[d] = act ? (umax[d] + side) / side : 1;
+                    bin[d].assign(N, 0);
+                    if (act) for (int i = 0; i < N; i++) bin[d][i] = u[d][i] / side;
+                }
+                bool ok = true;
+                for (int f = 0; f < F && ok; f++)
+                    for (int d = 0; d < 3; d++)
+                        if (bin[d][neighbour[f]] < bin[d][owner[f]]) { ok = false; break; }
+                const long long nb3 = (long long)nb[0] * nb[1] * nb[2];
+                const long long nbAll = nb3 * nComp;
+                if (nbAll > (1ll << 30)) ok = false;
+                if (ok) {
+                    // dense tile numbering sorted by (tile level, component, a, b, c)
+                    std::vector<int> key(N);
+                    std::vector<int> cntT(nbAll, 0);
+                    for (int i = 0; i < N; i++) {
+                        key[i] = bin[0][i] + nb[0] * (bin[1][i] + nb[1] * bin[2][i]) + (nComp > 1 ? (int)(nb3 * comp[i]) : 0);
+                        cntT[key[i]]++;
+                    }
+                    std::vector<int> order;
+                    for (long long t = 0; t < nbAll; t++) if (cntT[t] > 0) order.push_back((int)t);
+                    auto tl = [&](int t) { const int t3 = (int)(t % nb3); return t3 % nb[0] + (t3 / nb[0]) % nb[1] + t3 / (nb[0] * nb[1]); };
+                    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tl(x) < tl(y); });
+                    int maxRows = 0, maxTL = 0;
+                    for (int t : order) { maxRows = std::max(maxRows, cntT[t]); maxTL = std::max(maxTL, tl(t)); }
+                    if (maxRows <= tileRowCap) {
+                        std::vector<int> dense(nbAll, -1);
+                        for (size_t k = 0; k < order.size(); k++) dense[order[k]] = (int)k;
+                        tileOf.resize(N);
+                        for (int i = 0; i < N; i++) tileOf[i] = dense[key[i]];
+                        nTiles = (int)order.size();
+                        c->tileMode = true;
+                        c->tileTma = want64;
+                        blkWanted = wantBlk;
+                        c->nTileLevels = maxTL + 1;
+                    }
                 }
             }
         }
@@ -841,6 +922,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             if (t1 - t0 > ICS_BLK_MR || nLev > ICS_BLK_MAXLEV || nLev < 1) { ok = false; break; }
             // the slices one level touches must fit in the block ring together (lusgs_blk.cu)
             for (int L = 0; L < nLev; L++) if (tileFLev[tileFPtr[t] + L + 1] - tileFLev[tileFPtr[t] + L] > ICS_BLK_MAXLW) ok = false;
+            int unstaged[2] = {0, 0};  // the sweep has rows whose block lies outside the slice's staged entry range
             for (int sw = 0; sw < 2 && ok; sw++) {
                 tmp[sw].clear();
                 for (int p = t0; p < t1; p++) {
@@ -856,7 +938,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                 }
                 std::sort(tmp[sw].begin(), tmp[sw].end());
                 tmp[sw].erase(std::unique(tmp[sw].begin(), tmp[sw].end()), tmp[sw].end());
-                if ((int)tmp[sw].size() > ICS_BLK_MH) ok = false;
+                if ((int)tmp[sw].size() > ICS_BLK_MH - 1) ok = false;  // the last slot of the tile's vector is the zero the absent neighbours point to
                 tls[sw].clear();
                 for (int q : tmp[sw]) tls[sw].push_back(sliceTile2[q >> 5] + (sw == 0 ? 0 : nT));  // flag index: forward t, reverse nT + t
                 std::sort(tls[sw].begin(), tls[sw].end());
@@ -871,6 +953,8 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                     const int lo = sw == 0 ? 0 : sRevLo[s2];
                     const int cnt = sw == 0 ? std::min(sFwdHi[s2], ICS_BLK_SE) : std::max(0, std::min(sRevHi[s2] - sRevLo[s2], ICS_BLK_SE));
                     unsigned long long w = (unsigned long long)n << 45;
+                    // absent neighbours (k >= n): local index of the zero slot, block slot 3 (the kernel's zero block)
+                    for (int k = n; k < 3; k++) w |= (unsigned long long)((ICS_BLK_MR + ICS_BLK_MH - 1) | (3 << 10)) << (15 * k);
                     for (int k = 0; k < n; k++) {
                         const int j = sw == 0 ? k : nInt - 1 - k;
                         const int q = c->h_col[slotOf(p, j)];
@@ -879,6 +963,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                         else li = ICS_BLK_MR + (int)(std::lower_bound(tmp[sw].begin(), tmp[sw].end(), q) - tmp[sw].begin());
                         const int js = j - lo;
                         const int code = (js >= 0 && js < cnt) ? js : 3;
+                        if (code == 3) unstaged[sw] = 1;
                         if (j > 7) ok = false;
                         w |= (unsigned long long)(li | (code << 10) | (j << 12)) << (15 * k);
                     }
@@ -899,7 +984,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             d[7] = section(tmp[1]); d[8] = (int)tmp[1].size();
             d[9] = section(tls[0]); d[10] = (int)tls[0].size();
             d[11] = section(tls[1]); d[12] = (int)tls[1].size();
-            d[13] = section(so); d[14] = section(rl); d[15] = nSl;
+            d[13] = section(so); d[14] = section(rl); d[15] = nSl | (unstaged[0] << 16) | (unstaged[1] << 17);
             for (int k = 0; k < 16; k++) tab[off + k] = d[k];
             idx[(size_t)4 * t] = off; idx[(size_t)4 * t + 1] = (int)tab.size() - off; idx[(size_t)4 * t + 2] = t0; idx[(size_t)4 * t + 3] = t1 - t0;
             if ((int)tab.size() - off > ICS_BLK_TAB) ok = false;
@@ -917,8 +1002,8 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             r |= devUpload(c, &c->d_blkIdx, idx);
             r |= devUpload(c, &c->d_blkInfo, info);
             r |= devUpload(c, &c->d_blkStage, stage);
-            r |= devAlloc(c, &c->d_blkFlag, (size_t)2 * nT);
-            if (!r) CUDA_TRY(c, cudaMemset(c->d_blkFlag, 0, sizeof(int) * 2 * nT));
+            r |= devAlloc(c, &c->d_blkFlag, (size_t)2 * nT + 2);   // + the two ticket counters (lusgs_blk.cu)
+            if (!r) CUDA_TRY(c, cudaMemset(c->d_blkFlag, 0, sizeof(int) * (2 * nT + 2)));
             c->blkEpoch = 0;
             c->blkMode = true;
         }

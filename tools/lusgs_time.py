@@ -26,13 +26,15 @@ print({k: (round(v[0] / max(v[1], 1), 3), v[1]) for k, v in t.items() if v[1]})
 if os.environ.get("ICSB200_LUSGS_PROF") and g.schedule_info().get("blk"):
     f = lib().icsb200_debug_lusgs_prof
     f.restype = C.c_int
-    buf = np.zeros((148, 8), np.int64)
+    buf = np.zeros((148, 24), np.int64)
     n = f(g.h, buf.ctypes.data_as(C.c_void_p), 148)
     p = buf[:n].astype(float)
-    names = ["meta", "deps", "halo", "levels", "publish"]
+    names = ["meta", "halo", "levels", "lvlwait", "fullwait"]
     tot = p[:, 7].mean()
-    print("prof: CTAs %d, mean cycles/CTA %.0f; share of phases:" % (n, tot),
+    print("prof: CTAs %d, mean cycles/CTA %.0f; share of phases (lvlwait, fullwait are parts of levels):" % (n, tot),
           {k: round(p[:, i].mean() / tot, 3) for i, k in enumerate(names)})
     tiles, levs = p[:, 5].sum(), p[:, 6].sum()
-    print("prof: cycles per tile-sweep %.0f (meta %.0f deps %.0f halo %.0f levels %.0f publish %.0f); cycles per level %.0f" % (
-        p[:, 7].sum() / tiles, *(p[:, i].sum() / tiles for i in range(5)), p[:, 3].sum() / levs))
+    print("prof: cycles per tile-sweep %.0f (meta %.0f halo %.0f levels %.0f lvlwait %.0f fullwait %.0f); cycles per level %.0f" % (
+        p[:, 7].sum() / tiles, *(p[:, i].sum() / tiles for i in range(5)), p[:, 2].sum() / levs))
+    print("prof: helper warps, cycles per tile-sweep: halo warp [meta wait %.0f, flag polls %.0f, fence %.0f, gather %.0f]; publish warp [wait %.0f, bulk stores %.0f, release %.0f]; metadata warp [buffer wait %.0f]" % (
+        *(p[:, i].sum() / tiles for i in (8, 9, 10, 11, 16, 17, 18, 20)),))
