@@ -85,8 +85,9 @@ class Case:
             api.state_set(self.p[cells], self.U[cells], self.T[cells])
         return api
 
-    def partition(self, n_parts, mode="x"):
-        """Slab / block decomposition of the structured mesh (decomposePar 'simple' stand-in)."""
+    def partition(self, n_parts, mode="x", only=None):
+        """Slab / block decomposition of the structured mesh (decomposePar 'simple' stand-in).  `only`: extract just that
+        rank's sub-mesh (the other list entries are None)."""
         C = self.mesh.C
         if mode == "x":
             order = np.argsort(C[:, 0], kind="stable")
@@ -107,7 +108,7 @@ class Case:
                 fa = np.arange(pa["start"], pa["start"] + pa["size"])
                 fb = np.arange(pb["start"], pb["start"] + pb["size"])
                 part[self.mesh.owner[fb]] = part[self.mesh.owner[fa]]
-        meshes = [self.mesh.extract_part(part, r) for r in range(n_parts)]
+        meshes = [self.mesh.extract_part(part, r) if only is None or r == only else None for r in range(n_parts)]
         return part, meshes
 
     def decomposed(self, case_dir):

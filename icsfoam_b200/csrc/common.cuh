@@ -34,7 +34,7 @@
 #define ICS_BLK_MAXLEV 63
 #define ICS_BLK_MAXDEP 32
 #define ICS_BLK_SE 3
-#define ICS_BLK_MAXLW 128  // widest intra-tile level
+#define ICS_BLK_MAXLW 64   // widest intra-tile level (three consecutive levels must fit in the block ring together)
 #define ICS_BLK_TAB 512    // ints of a tile's table
 
 constexpr int NQ = 8;   // reconstructed scalars: rho, p, Ux, Uy, Uz, cR, E, H

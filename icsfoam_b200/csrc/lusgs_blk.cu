@@ -45,7 +45,7 @@ constexpr int NTHREADS = NCT + 128;    // + producer, halo, publish and metadata
 constexpr int HIT = (MH + 31) / 32;    // halo entries per lane of the halo warp
 
 // a tile's table (setup.cu): 16 descriptor ints, then the sections they point to
-enum { BT_T0 = 0, BT_NROWS, BT_NREAL, BT_NLEV, BT_LEV, BT_HALOF, BT_NHALOF, BT_HALOR, BT_NHALOR, BT_DEPF, BT_NDEPF, BT_DEPR, BT_NDEPR, BT_SLICEOFF, BT_REVLO, BT_NSL };
+enum { BT_T0 = 0, BT_NROWS, BT_REG, BT_NLEV, BT_LEV, BT_HALOF, BT_NHALOF, BT_HALOR, BT_NHALOR, BT_DEPF, BT_NDEPF, BT_DEPR, BT_NDEPR, BT_SLICEOFF, BT_REVLO, BT_NSL };
 // profile slots per CTA (ICSB200_LUSGS_PROF), consumer thread 0: cycles waiting for the metadata stage, for the halo warp, in the
 // level loops, of which waiting at the level barrier / for block stages; tiles swept, levels swept, total
 enum { PF_META = 0, PF_HALO, PF_LEVELS, PF_LVLWAIT, PF_FULLWAIT, PF_TILES, PF_NLEV, PF_TOTAL };
@@ -81,7 +81,7 @@ struct BlkSmem {
     int4 itemIdx[NBUF];
     int2 itemStage[NBUF][MR / 32];
     double zeroB[160];    // the 5x5 block of an absent neighbour (element (k, lane) of a component's row at k*32 + lane)
-    unsigned long long full[NST], empty[NST], idfull[NBUF], mfull[NBUF], mempty[NBUF], hfull[NBUF], done[NBUF], lvl;
+    unsigned long long full[NST], empty[NST], idfull[NBUF], mfull[NBUF], mempty[NBUF], hfull[NBUF], done[NBUF], lvl[2];
 };
 
 __device__ __forceinline__ unsigned sAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -159,8 +159,8 @@ k_lusgs_blk(BlkArgs a)
     const int G = gridDim.x, b = blockIdx.x;
     if (tid == 0) {
         for (int s = 0; s < NST; s++) { mbInit(sm.full + s, 1); mbInit(sm.empty + s, NCW); }
-        for (int s = 0; s < NBUF; s++) { mbInit(sm.idfull + s, 1); mbInit(sm.mfull + s, 1); mbInit(sm.mempty + s, 1); mbInit(sm.hfull + s, 1); mbInit(sm.done + s, NCW); }
-        mbInit(&sm.lvl, NCW);
+        for (int s = 0; s < NBUF; s++) { mbInit(sm.idfull + s, 1); mbInit(sm.mfull + s, 1); mbInit(sm.mempty + s, 1); mbInit(sm.hfull + s, 1); mbInit(sm.done + s, NCW / 2); }
+        mbInit(sm.lvl, NCW / 2); mbInit(sm.lvl + 1, NCW / 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // the zero slot absent neighbours point to (last entry of the tile's vector and of its rD), and the zero block
@@ -364,13 +364,18 @@ k_lusgs_blk(BlkArgs a)
         return;
     }
 
-    // ---------------- consumers ----------------
+    // ---------------- consumers: two groups of five warps (one warp per component of the block row) take the levels in turn.
+    // While one group sweeps level L — the dependent part: neighbour values out of shared memory, 15 products, the ordered
+    // subtractions — the other group loads everything level L+1 needs that does not depend on the sweep (packed neighbour
+    // info, rD, right-hand side, its 15 block coefficients out of the ring) into registers, so the chain from level to level is
+    // barrier -> sweep -> barrier.  lvl[g] is arrived on by group g after each of its sweeps and waited on by the other group.
     const bool prof = PROF && tid == 0;
     long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long tStart = prof ? clock64() : 0;
-    const int r = warp % 5, rc0 = warp / 5;  // component of the block row this warp sweeps; its first chunk of 32 rows in a level
-    int base = 0;                            // ring position of the current item's first slice (all consumers count alike)
-    unsigned lvlPhase = 0;                   // completed phases of the level barrier
+    const int r = warp % 5, grp = warp / 5;
+    int base = 0;          // ring position of the current item's first slice (all consumers count alike)
+    int gl0 = 0;           // levels swept before the current item (both groups count alike): level l of the item belongs to group (gl0 + l) & 1
+    unsigned nWaits = 0;   // completed waits on the other group's level barrier
     for (int i = 0;; i++) {
         bool fwd;
         int tile;
@@ -390,10 +395,18 @@ k_lusgs_blk(BlkArgs a)
         const int* sliceOff = M.tab + d[BT_SLICEOFF];
         int relNext = 0, relSt = base % NST;  // next slice (in sweep order) and its stage this warp hands back to the producer
 
+        // hand back the stages of the first `target` slices (sweep order) of the tile
+        auto releaseTo = [&](int target) {
+            __syncwarp();  // every lane's block reads precede lane 0's arrival
+            while (relNext < target) {
+                if (lane == 0) mbArrive(sm.empty + relSt);
+                relSt = relSt + 1 == NST ? 0 : relSt + 1;
+                relNext++;
+            }
+        };
         // Everything of unit (chunk rc of level li, component r) that does not depend on the sweep.  Absent neighbours point at
-        // the zero slot of the tile's vector and at the zero block (setup.cu), so the sweep itself is branch-free.  Afterwards
-        // the stages of the slices whose rows all lie in levels <= li go back to the producer (`rel`).
-        auto loadUnit = [&](Unit& U, int li, int rc, bool rel) {
+        // the zero slot of the tile's vector and at the zero block (setup.cu), so the sweep itself is branch-free.
+        auto loadUnit = [&](Unit& U, int li, int rc) {
             const int L = fwd ? li : nLev - 1 - li;
             const int a0 = lev[L], b0 = lev[L + 1];
             const int row = a0 + rc * 32 + lane;
@@ -405,9 +418,9 @@ k_lusgs_blk(BlkArgs a)
                 U.xr = xsr[row];
                 const int sl = row >> 5, ln = row & 31;
                 const int gs = base + (fwd ? sl : nSl - 1 - sl);
-                const int q = gs / NST, st = gs - q * NST;
-                if (PROF) { const long long q0 = prof ? clock64() : 0; mbWait(sm.full + st, q & 1, a.err); if (prof) pf[PF_FULLWAIT] += clock64() - q0; }
-                else mbWait(sm.full + st, q & 1, a.err);
+                const int st = gs % NST;
+                if (PROF) { const long long q0 = prof ? clock64() : 0; mbWait(sm.full + st, (gs / NST) & 1, a.err); if (prof) pf[PF_FULLWAIT] += clock64() - q0; }
+                else mbWait(sm.full + st, (gs / NST) & 1, a.err);
                 const double* stage = &sm.ring[st][0] + r * 160 + ln;
                 const double* zb = sm.zeroB + ln;
 #pragma unroll
@@ -428,15 +441,6 @@ k_lusgs_blk(BlkArgs a)
                             U.B[t][0] = __ldcs(bp); U.B[t][1] = __ldcs(bp + 32); U.B[t][2] = __ldcs(bp + 64); U.B[t][3] = __ldcs(bp + 96); U.B[t][4] = __ldcs(bp + 128);
                         }
                     }
-                }
-            }
-            if (rel) {
-                __syncwarp();  // every lane's block reads precede lane 0's arrival
-                const int target = li == nLev - 1 ? nSl : (fwd ? (b0 >> 5) : nSl - ((a0 + 31) >> 5));
-                while (relNext < target) {
-                    if (lane == 0) mbArrive(sm.empty + relSt);
-                    relSt = relSt + 1 == NST ? 0 : relSt + 1;
-                    relNext++;
                 }
             }
         };
@@ -462,42 +466,55 @@ k_lusgs_blk(BlkArgs a)
         };
         auto chunksOf = [&](int li) { const int L = fwd ? li : nLev - 1 - li; return (lev[L + 1] - lev[L] + 31) >> 5; };
 
-        // the reverse sweep starts from the tile's own forward values, which the halo warp stages
-        Unit U;
-        if (!fwd) mbWait(sm.hfull + buf, bufPar, a.err);
-        if (prof && !fwd) { const long long t2 = clock64(); pf[PF_HALO] += t2 - tk; tk = t2; }
-        loadUnit(U, 0, rc0, chunksOf(0) <= 2);
-        if (fwd) mbWait(sm.hfull + buf, bufPar, a.err);
-        if (prof && fwd) { const long long t2 = clock64(); pf[PF_HALO] += t2 - tk; tk = t2; }
+        const int first = ((gl0 & 1) == grp) ? 0 : 1;  // this group's first level of the item
         long long* tr = nullptr;
         if (prof && a.trace) { tr = a.trace + ((size_t)(fwd ? 0 : nT) + tile) * 8; tr[3] = gtime(); }
-        for (int li = 0; li < nLev; li++) {
-            if (li > 0) {
-                if (PROF) { const long long q0 = prof ? clock64() : 0; mbWait(&sm.lvl, lvlPhase & 1, a.err); if (prof) pf[PF_LVLWAIT] += clock64() - q0; }
-                else mbWait(&sm.lvl, lvlPhase & 1, a.err);
-                lvlPhase++;
-            }
-            sweepUnit(U);
-            const int nCh = chunksOf(li);
-            if (nCh > 2) {
-                // levels wider than 64 rows: the remaining chunks of this warp, not software-pipelined
-                for (int rc = rc0 + 2; rc < nCh + 2; rc += 2) {
+        if (first < nLev) {
+            Unit U;
+            // the reverse sweep starts from the tile's own forward values, which the halo warp stages
+            if (!fwd) mbWait(sm.hfull + buf, bufPar, a.err);
+            loadUnit(U, first, 0);
+            if (fwd) mbWait(sm.hfull + buf, bufPar, a.err);
+            if (prof) { const long long t2 = clock64(); pf[PF_HALO] += t2 - tk; tk = t2; }
+            for (int li = first; li < nLev; li += 2) {
+                if (gl0 + li > 0) {   // the level before this one, swept by the other group (possibly as the last level of the previous item)
+                    if (PROF) { const long long q0 = prof ? clock64() : 0; mbWait(sm.lvl + (grp ^ 1), nWaits & 1, a.err); if (prof) pf[PF_LVLWAIT] += clock64() - q0; }
+                    else mbWait(sm.lvl + (grp ^ 1), nWaits & 1, a.err);
+                    nWaits++;
+                }
+                const long long q2 = prof ? clock64() : 0;
+                sweepUnit(U);
+                const int nCh = chunksOf(li);
+                for (int rc = 1; rc < nCh; rc++) {
+                    // levels wider than 32 rows: the remaining chunks, not software-pipelined
                     Unit V;
-                    loadUnit(V, li, rc, rc + 2 >= nCh + 2);   // the last pass (possibly empty) hands the stages back
+                    loadUnit(V, li, rc);
                     sweepUnit(V);
                 }
-            }
-            if (li + 1 < nLev) {
+                const long long q3 = prof ? clock64() : 0;
+                // the bulk stores of the publish warp read what this thread wrote: async-proxy fence after its last sweep of the item
+                if (li + 2 >= nLev) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbArrive(&sm.lvl);
-                loadUnit(U, li + 1, rc0, chunksOf(li + 1) <= 2);
+                if (lane == 0) {
+                    mbArrive(sm.lvl + grp);
+                    if (li == nLev - 1) mbArrive(sm.done + buf);  // every earlier level is ordered before this one through the level barriers
+                }
+                // The block coefficients of this level have been consumed, so the stages of the slices whose rows all lie in levels
+                // <= li go back to the producer now (an arrival right after the loads would wait for them to land instead of
+                // letting them overlap the other group's sweep).
+                {
+                    const int L = fwd ? li : nLev - 1 - li;
+                    releaseTo(li == nLev - 1 ? nSl : (fwd ? (lev[L + 1] >> 5) : nSl - ((lev[L] + 31) >> 5)));
+                }
+                const long long q4 = prof ? clock64() : 0;
+                if (li + 2 < nLev) loadUnit(U, li + 2, 0);
+                if (prof) { const long long q5 = clock64(); a.prof[(size_t)b * 24 + 12] += q3 - q2; a.prof[(size_t)b * 24 + 15] += q4 - q3; a.prof[(size_t)b * 24 + 13] += q5 - q4; a.prof[(size_t)b * 24 + 21] += 1; }
             }
         }
+        releaseTo(nSl);  // slices this group never read from (the other group's last level, or a tile without a level for this group)
         if (prof) { const long long t2 = clock64(); pf[PF_LEVELS] += t2 - tk; tk = t2; pf[PF_TILES]++; pf[PF_NLEV] += nLev; if (tr) tr[4] = gtime(); }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the bulk stores read what this thread wrote
-        __syncwarp();
-        if (lane == 0) mbArrive(sm.done + buf);
         base += nSl;
+        gl0 += nLev;
     }
     if (prof) {
         pf[PF_TOTAL] = clock64() - tStart;

@@ -419,16 +419,22 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                 for (int d = 0; d < 3; d++) if (umax[d] + 1 >= 4 && (sweep < 0 || umax[d] > umax[sweep])) sweep = d;
                 auto envInt = [](const char* name, int dflt) { const char* e = getenv(name); return e ? std::max(1, atoi(e)) : dflt; };
                 const int nCross = active > 0 ? active - 1 : 0;
+                // 3-D: 8 x 4 columns (32 rows = one warp per block-row component and level), 8 levels deep; 2-D: 16 wide, 16 deep
                 int bside = nCross == 2 ? 8 : (nCross == 1 ? 16 : 1);
                 bside = envInt("ICSB200_LUSGS_BSIDE", bside);
-                int depth = nCross == 2 ? 4 : (nCross == 1 ? 16 : 32);
+                int bside2 = nCross == 2 ? 4 : bside;
+                bside2 = envInt("ICSB200_LUSGS_BSIDE2", bside2);
+                int depth = nCross == 2 ? 8 : (nCross == 1 ? 16 : 32);
                 depth = envInt("ICSB200_LUSGS_DEPTH", depth);
                 int bs[3] = {1, 1, 1}, nbin[3] = {1, 1, 1}, K[3] = {0, 0, 0};
-                for (int d = 0; d < 3; d++) {
-                    if (d == sweep || umax[d] + 1 < 4) continue;
-                    bs[d] = bside;
-                    nbin[d] = umax[d] / bside + 1;
-                    K[d] = (bside - 1 + depth - 1) / depth + 1;
+                {
+                    int nth = 0;
+                    for (int d = 0; d < 3; d++) {
+                        if (d == sweep || umax[d] + 1 < 4) continue;
+                        bs[d] = nth++ == 0 ? bside : bside2;
+                        nbin[d] = umax[d] / bs[d] + 1;
+                        K[d] = (bs[d] - 1 + depth - 1) / depth + 1;
+                    }
                 }
                 int sMax = sweep >= 0 ? umax[sweep] : 0;
                 for (int d = 0; d < 3; d++) if (d != sweep) sMax += (umax[d] + 1 < 4) ? umax[d] : bs[d] - 1;
@@ -978,7 +984,13 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             std::vector<int> lv(tileFLev.begin() + tileFPtr[t], tileFLev.begin() + tileFPtr[t + 1]);
             std::vector<int> so(c->h_sliceOff.begin() + t0 / 32, c->h_sliceOff.begin() + t0 / 32 + nSl), rl(sRevLo.begin() + t0 / 32, sRevLo.begin() + t0 / 32 + nSl);
             int d[16] = {0};
-            d[0] = t0; d[1] = t1 - t0; d[2] = lv.back(); d[3] = nLev;
+            // regular tile: every level has the same width w (a divisor of 32, all rows real) — the kernel then derives rows, slices
+            // and stages from the level number alone; bit 8 / 9: the forward / reverse sweep may use that path (nothing unstaged)
+            int regW = lv[1] - lv[0];
+            for (int L = 0; L < nLev; L++) if (lv[L + 1] - lv[L] != regW) regW = 0;
+            if (regW < 1 || regW > 32 || 32 % regW != 0 || lv.back() != t1 - t0 - ((t1 - t0) - lv.back())) regW = 0;
+            if (regW && lv.back() != nLev * regW) regW = 0;
+            d[0] = t0; d[1] = t1 - t0; d[2] = regW ? (regW | (unstaged[0] ? 0 : 1 << 8) | (unstaged[1] ? 0 : 1 << 9)) : 0; d[3] = nLev;
             d[4] = section(lv);
             d[5] = section(tmp[0]); d[6] = (int)tmp[0].size();
             d[7] = section(tmp[1]); d[8] = (int)tmp[1].size();

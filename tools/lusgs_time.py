@@ -38,3 +38,6 @@ if os.environ.get("ICSB200_LUSGS_PROF") and g.schedule_info().get("blk"):
         p[:, 7].sum() / tiles, *(p[:, i].sum() / tiles for i in range(5)), p[:, 2].sum() / levs))
     print("prof: helper warps, cycles per tile-sweep: halo warp [meta wait %.0f, flag polls %.0f, fence %.0f, gather %.0f]; publish warp [wait %.0f, bulk stores %.0f, release %.0f]; metadata warp [buffer wait %.0f]" % (
         *(p[:, i].sum() / tiles for i in (8, 9, 10, 11, 16, 17, 18, 20)),))
+    nl = max(p[:, 21].sum(), 1)
+    print("prof: consumer thread 0, cycles per own level: sweep %.0f, fence + arrivals (level barrier, stages) %.0f, load of the next own level %.0f; own levels %d" % (
+        p[:, 12].sum() / nl, p[:, 15].sum() / nl, p[:, 13].sum() / nl, nl))
