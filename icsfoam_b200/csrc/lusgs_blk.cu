@@ -288,16 +288,15 @@ k_lusgs_blk(BlkArgs a)
                 const int h = it * 32 + lane;
                 hq[it] = h < nHalo ? halo[h] : -1;
             }
-            // relaxed polls, then one acquire read of the same flag (an L1 invalidate per poll, or a full fence with loads in
-            // flight, costs microseconds here)
+            // acquire polls, one flag per lane (nothing else of this SM lives in L1, so the invalidate that comes with each costs
+            // nothing; a separate fence after relaxed polls, with loads in flight, costs microseconds)
             for (int k = lane; k < nDep; k += 32) {
                 const int* f = a.flag + dep[k];
                 unsigned int spins = 0;
-                while (ldRelaxed(f) != a.epoch) {
+                while (ldAcquire(f) != a.epoch) {
                     if (++spins > (1u << 24)) { *a.err = 1; break; }
                     if (spins > 64) __nanosleep(32);
                 }
-                (void)ldAcquire(f);
             }
             if (PROF && lane == 0) { const long long t2 = clock64(); a.prof[(size_t)b * 24 + 9] += t2 - hk; hk = t2; }
             __syncwarp();
@@ -337,31 +336,34 @@ k_lusgs_blk(BlkArgs a)
     }
 
     if (warp == NCW + 2) {
-        // ---------------- publish warp: the consumers' stores of an item precede their arrival on done[]; the fence + release by
-        // one thread is cumulative.  The metadata stage (and with it the tile's shared-memory vector) goes back to the producer.
-        if (lane == 0) {
-            for (int i = 0;; i++) {
-                bool fwd;
-                int tile;
-                if (!getItem(i, fwd, tile)) return;
-                const int buf = i % NBUF;
-                long long pk = PROF ? clock64() : 0;
-                if (!mbWait(sm.done + buf, (i / NBUF) & 1, a.err)) return;
-                if (PROF) { const long long t2 = clock64(); a.prof[(size_t)b * 24 + 16] += t2 - pk; pk = t2; }
-                // the tile's swept values go from shared memory to x in five bulk stores (no global store sits on the
-                // consumers' dependent path); their completion is followed by an implicit generic-async proxy fence
-                const int t0 = sm.meta[buf].tab[BT_T0];
-                const unsigned rowB = (unsigned)sm.meta[buf].tab[BT_NROWS] * 8;
-                for (int k = 0; k < 5; k++) bulkStore(a.x + k * a.NPH + t0, &sm.xs[buf][k][0], rowB);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                if (PROF) { const long long t2 = clock64(); a.prof[(size_t)b * 24 + 17] += t2 - pk; pk = t2; }
+        // ---------------- publish warp: copies the tile's swept values from shared memory to x (plain coalesced stores: no global
+        // store and no proxy fence sits on the consumers' dependent path), then lane 0 releases the tile's epoch flag — the
+        // warp's stores precede it through __syncwarp, the st.release is cumulative — and the tile buffer goes back to the
+        // metadata warp.
+        for (int i = 0;; i++) {
+            bool fwd;
+            int tile;
+            if (!getItem(i, fwd, tile)) return;
+            const int buf = i % NBUF;
+            long long pk = PROF ? clock64() : 0;
+            if (!mbWait(sm.done + buf, (i / NBUF) & 1, a.err)) return;
+            if (PROF && lane == 0) { const long long t2 = clock64(); a.prof[(size_t)b * 24 + 16] += t2 - pk; pk = t2; }
+            const int t0 = sm.meta[buf].tab[BT_T0], nRp = sm.meta[buf].tab[BT_NROWS];
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const double* src = &sm.xs[buf][k][0];
+                double* dst = a.x + k * a.NPH + t0;
+                for (int rw = lane; rw < nRp; rw += 32) __stcg(dst + rw, src[rw]);
+            }
+            __syncwarp();
+            if (PROF && lane == 0) { const long long t2 = clock64(); a.prof[(size_t)b * 24 + 17] += t2 - pk; pk = t2; }
+            if (lane == 0) {
                 stRelease(a.flag + (fwd ? tile : a.nTiles + tile), a.epoch);
                 mbArrive(sm.mempty + buf);
                 if (PROF) { const long long t2 = clock64(); a.prof[(size_t)b * 24 + 18] += t2 - pk; pk = t2; if (a.trace) a.trace[((size_t)(fwd ? 0 : a.nTiles) + tile) * 8 + 5] = gtime(); }
             }
+            __syncwarp();
         }
-        return;
     }
 
     // ---------------- consumers: two groups of five warps (one warp per component of the block row) take the levels in turn.
@@ -492,8 +494,6 @@ k_lusgs_blk(BlkArgs a)
                     sweepUnit(V);
                 }
                 const long long q3 = prof ? clock64() : 0;
-                // the bulk stores of the publish warp read what this thread wrote: async-proxy fence after its last sweep of the item
-                if (li + 2 >= nLev) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {
                     mbArrive(sm.lvl + grp);

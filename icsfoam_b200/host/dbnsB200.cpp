@@ -202,8 +202,6 @@ int main(int argc, char** argv)
         std::cout << "Mesh: " << N << " cells, " << F << " internal faces, " << nP << " patches\n";
 
         // ---- initial fields and boundary conditions (parsed before the device is touched)
-        const std::vector<double> U0 = numbers(UDict.lookup("internalField")).size() >= 3 && UDict.lookup("internalField").at(0) == "uniform"
-                                           ? numbers(UDict.lookup("internalField")) : std::vector<double>{0, 0, 0};
         std::vector<double> p = fieldValues(pDict.lookup("internalField"), 1, N, "internalField of p");
         std::vector<double> U = fieldValues(UDict.lookup("internalField"), 3, N, "internalField of U");
         std::vector<double> T = fieldValues(TDict.lookup("internalField"), 1, N, "internalField of T");
@@ -214,7 +212,19 @@ int main(int argc, char** argv)
         for (int pi = 0; pi < nP; pi++)
             for (int fld = 0; fld < 3; fld++) {
                 if (!bf[fld]->isDict(patchNames[pi])) throw FatalError("patch " + patchNames[pi] + " missing in boundaryField");
-                bcs[(size_t)3 * pi + fld] = bcFromDict(bf[fld]->subDict(patchNames[pi]), fld, U0, *top[fld], patches[pi].size);
+                // freestreamPressureFvPatchScalarField blends with the velocity of the U patch field on the same patch: its
+                // freestreamValue (macros resolved against 0/U), not the internalField
+                std::vector<double> Ufs{0, 0, 0};
+                if (fld == 0 && bf[0]->subDict(patchNames[pi]).word("type") == "freestreamPressure") {
+                    const dictionary& up = bf[1]->subDict(patchNames[pi]);
+                    if (up.word("type") != "freestream") throw FatalError("patch " + patchNames[pi] + ": freestreamPressure needs a freestream U patch field");
+                    if (bf[0]->subDict(patchNames[pi]).getSwitch("supersonic", false)) throw FatalError("patch " + patchNames[pi] + ": freestreamPressure with supersonic true is not supported");
+                    std::vector<std::string> toks = up.lookup("freestreamValue");
+                    if (!toks.empty() && toks[0].size() > 1 && toks[0][0] == '$') toks = UDict.lookup(toks[0].substr(1));
+                    Ufs = numbers(toks);
+                    if (Ufs.size() < 3) throw FatalError("patch " + patchNames[pi] + ": freestreamValue of U must be a uniform vector");
+                }
+                bcs[(size_t)3 * pi + fld] = bcFromDict(bf[fld]->subDict(patchNames[pi]), fld, Ufs, *top[fld], patches[pi].size);
                 nNonuniform += bcs[(size_t)3 * pi + fld].nRows > 0;
             }
         // ---- thermo: hePsiThermo<pureMixture<constTransport<hConst<perfectGas>>>>, sensibleInternalEnergy (createFields.H:17-35)
@@ -259,7 +269,10 @@ int main(int argc, char** argv)
         if (ddt.at(0) != "dualTime") throw FatalError("ddtSchemes default must be 'dualTime rPseudoDeltaT <inner>' (dualTimeDdtScheme.H:103)");
         const std::string inner = ddt.back();
         const bool steadyState = inner == "steadyState";
+        if (!steadyState && inner != "Euler" && inner != "backward") throw FatalError("inner ddt scheme '" + inner + "' is not supported (steadyState Euler backward)");
         sch.ddt_scheme = steadyState ? ICSB200_DDT_STEADY : inner == "Euler" ? ICSB200_DDT_EULER : ICSB200_DDT_BACKWARD;
+        if (pseudo.getSwitch("resetPseudo", false)) throw FatalError("pseudoTime/resetPseudo true (beginTimeStep.H) is not supported");
+        if (controlDict.getSwitch("adjustTimeStep", false)) throw FatalError("controlDict adjustTimeStep yes is not supported");
         sch.delta_t = controlDict.get<double>("deltaT");
         sch.local_timestepping = pseudo.getSwitch("localTimestepping", true);
         sch.local_timestepping_bounding = pseudo.getSwitch("localTimesteppingBounding", true);
@@ -295,47 +308,26 @@ int main(int argc, char** argv)
         double time = controlDict.getOrDefault<double>("startTime", 0.0);
 
         // ---- time loop (dbnsFoam.C:88-151)
-        residualsIO residuals, initResiduals;
         std::vector<double> phiH(writeFlux ? FT : 0), phiUpH(writeFlux ? 3 * (size_t)FT : 0), phiEpH(writeFlux ? FT : 0);
-        bool haveInit = false;
-        int corr = 0, step = 0;  // steady: corr runs over the whole run (pseudotimeControl::loop, Q7)
+        pseudotimeControl solnControl(steadyState, nCorrOuter, nCorrOuterMin, pseudoTol, pseudoTolRel, std::cout);
+        int step = 0;
         while (time < endTime - 1e-12 * std::fabs(endTime) && step < maxSteps) {
-            time += steadyState ? 1.0 : deltaT;
+            time += deltaT;   // runTime++ (steady runs count pseudo iterations in units of controlDict's deltaT, too)
             step++;
             std::cout << "Time = " << time << "\n\n";
-            if (!steadyState) { check(ctx, icsb200_new_time_step(ctx), "new_time_step"); corr = 0; haveInit = false; }
-            bool converged = false;
-            while (true) {
-                corr++;
-                if (!steadyState && corr == nCorrOuter + 1) {
-                    std::cout << "pseudoTime: not converged within " << nCorrOuter << " iterations\n";
-                    break;
-                }
-                // criteriaSatisfied (pseudotimeControl.C:72-101): no check on the first iteration
-                if (corr > 1) {
-                    const bool storeIni = (corr == 2);
-                    if (storeIni) { initResiduals = residuals; haveInit = true; }
-                    const bool absCheck = residuals.maxInit() < pseudoTol;
-                    bool relCheck = false;
-                    if (!storeIni && haveInit) {
-                        double m = -1e300;
-                        for (int i = 0; i < 2; i++) m = std::max(m, residuals.sInitRes[i] / (initResiduals.sInitRes[i] + 1e-150));
-                        for (int d = 0; d < 3; d++) m = std::max(m, residuals.vInitRes[d] / (initResiduals.vInitRes[d] + 1e-150));
-                        relCheck = m < pseudoTolRel;
-                    }
-                    if (corr >= nCorrOuterMin && (absCheck || relCheck)) { converged = true; }
-                }
-                if (converged) { std::cout << "pseudoTime: converged in " << corr - 1 << " iterations\n"; break; }
-                std::cout << "pseudoTime: iteration " << corr << "\n";
+            if (!steadyState) check(ctx, icsb200_new_time_step(ctx), "new_time_step");   // beginTimeStep.H
+            bool notFinished;
+            while ((notFinished = solnControl.loop())) {
                 icsb200_residuals r;
                 if (writeFlux) check(ctx, icsb200_calc_flux(ctx, phiH.data(), phiUpH.data(), phiEpH.data()), "calc_flux");
                 check(ctx, icsb200_iterate_dev(ctx, &ctl, &r), "outerLoop");   // outerLoop.H + updateFields.H on the device
-                residuals = residualsIO(r);
+                const residualsIO residuals(r);
+                solnControl.setResidual(residuals);   // outerLoop.H:97
                 std::cout << "GMRES : Solving for (  rhoIncr rhoEIncr rhoUIncr ) \n";
                 residuals.print(std::cout);
                 if (steadyState) break;
             }
-            if (steadyState && converged) break;
+            if (steadyState && !notFinished) break;   // runTime.writeAndEnd()
         }
         std::vector<double> rho(N);
         check(ctx, icsb200_state_get(ctx, rho.data(), nullptr, nullptr, nullptr, nullptr, nullptr), "state_get");
