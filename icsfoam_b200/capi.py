@@ -12,7 +12,8 @@ import numpy as np
 # --- enums (include/icsb200.h) ---
 PATCH, WALL, EMPTY, SYMMETRYPLANE, CYCLIC, PROCESSOR, CYCLICAMI = range(7)
 FLUX_HLLC, FLUX_ROE, FLUX_AUSMPLUSUP = range(3)
-FLUX_NAMES = {"HLLC": FLUX_HLLC, "ROE": FLUX_ROE, "AUSMPlusUp": FLUX_AUSMPLUSUP}
+FLUX_RUSANOV = 3   # not a reference scheme (src/Make/files:47-51): the local Lax-Friedrichs flux the brief names
+FLUX_NAMES = {"HLLC": FLUX_HLLC, "ROE": FLUX_ROE, "AUSMPlusUp": FLUX_AUSMPLUSUP, "Rusanov": FLUX_RUSANOV}
 LIM_UPWIND, LIM_VANLEER, LIM_MINMOD, LIM_LINEAR = range(4)
 LIM_NAMES = {"upwind": LIM_UPWIND, "vanLeer": LIM_VANLEER, "Minmod": LIM_MINMOD, "linear": LIM_LINEAR}
 DDT_STEADY, DDT_EULER, DDT_BACKWARD = range(3)

@@ -247,18 +247,36 @@ __device__ __forceinline__ Flux5 fluxAUSM(const FaceState& s, V3 Sf, double magS
     return F;
 }
 
+// ---- Rusanov / local Lax-Friedrichs (no reference counterpart: the flux whose frozen-lambda linearisation is the reference's
+// approximate Jacobian, convectiveFluxScheme.C:402-546): central flux of the limited states in the relative frame minus
+// lambda/2 (W_R - W_L), lambda = max(|u_L| + c_L, |u_R| + c_R) with u = U.n - MRFFaceVelocity.  Same expressions, same order,
+// in oracle/oracle_flux.cpp fluxRusanov.
+__device__ __forceinline__ Flux5 fluxRusanov(const FaceState& s, V3 Sf, double magSf, double mrf, const SchemePrm&)
+{
+    const V3 n = Sf / magSf;
+    const double uL = dot(s.U_l, n) - mrf, uR = dot(s.U_r, n) - mrf;
+    const double lam = fmax(fabs(uL) + s.c_l, fabs(uR) + s.c_r);
+    const double mL = s.rho_l * uL, mR = s.rho_r * uR;
+    Flux5 F;
+    F.phi = (0.5 * (mL + mR) - 0.5 * lam * (s.rho_r - s.rho_l)) * magSf;
+    F.phiUp = (0.5 * ((mL * s.U_l + s.p_l * n) + (mR * s.U_r + s.p_r * n)) - (0.5 * lam) * (s.rho_r * s.U_r - s.rho_l * s.U_l)) * magSf;
+    F.phiEp = (0.5 * ((mL * s.H_l + s.p_l * mrf) + (mR * s.H_r + s.p_r * mrf)) - 0.5 * lam * (s.rho_r * s.E_r - s.rho_l * s.E_l)) * magSf;
+    return F;
+}
+
 template <int SCHEME>
 __device__ __forceinline__ Flux5 faceFlux(const FaceState& s, V3 Sf, double magSf, double mrf, const SchemePrm& pr)
 {
     if (SCHEME == ICSB200_FLUX_HLLC) return fluxHLLC(s, Sf, magSf, mrf, pr);
     if (SCHEME == ICSB200_FLUX_ROE) return fluxROE(s, Sf, magSf, mrf, pr);
+    if (SCHEME == ICSB200_FLUX_RUSANOV) return fluxRusanov(s, Sf, magSf, mrf, pr);
     return fluxAUSM(s, Sf, magSf, mrf, pr);
 }
 
 // ------------------------------------------------------------------------------------------------ k_grad
 // gaussGrad::gradf for the NQ reconstructed scalars.  f: fields [Q_COUNT][NX]; grad: [NQ*3][NPH]
 template <int NQ>
-__global__ void __launch_bounds__(128, NQ > 4 ? 4 : 8)
+__global__ void __launch_bounds__(128, NQ > 4 ? 4 : 5)
 k_grad(int NP, const int* __restrict__ pos2cell, const int* __restrict__ sliceOff, const int* __restrict__ rowNAll, const int* __restrict__ col,
        const int* __restrict__ meta, const int* __restrict__ gfid, const double* __restrict__ geo, size_t NFG, const double* __restrict__ V,
        const double* __restrict__ f, size_t NX, double* __restrict__ grad, size_t NPH)
@@ -271,14 +289,29 @@ k_grad(int NP, const int* __restrict__ pos2cell, const int* __restrict__ sliceOf
 #pragma unroll
     for (int k = 0; k < NQ; k++) { own[k] = f[k * NX + p]; acc[k][0] = acc[k][1] = acc[k][2] = 0.0; }
     const int nAll = rowNAll[p];
-    for (int j = 0; j < nAll; j++) {
+    // Software-pipelined over the row's faces: the indices and geometry of face j+1 are requested before face j is
+    // accumulated, so the neighbour gathers of the next face (the kernel is bound by the latency of these L2 gathers, not by
+    // bandwidth) start without waiting for an index load; the accumulation order (ascending face id) is untouched.
+    struct Face { int c, type; double Sx, Sy, Sz, w; };
+    auto fetch = [&](int j, Face& F) {
         const size_t e = (base + j) * 32 + lane;
-        const int c = col[e], type = meta[e] & 3;
+        F.c = col[e];
+        F.type = meta[e] & 3;
         const size_t g = gfid[e];
-        const double Sx = geo[G_SFX * NFG + g], Sy = geo[G_SFY * NFG + g], Sz = geo[G_SFZ * NFG + g], w = geo[G_W * NFG + g];
+        F.Sx = geo[G_SFX * NFG + g]; F.Sy = geo[G_SFY * NFG + g]; F.Sz = geo[G_SFZ * NFG + g]; F.w = geo[G_W * NFG + g];
+    };
+    Face cur, nxt;
+    if (nAll > 0) fetch(0, cur);
+    for (int j = 0; j < nAll; j++) {
+        double nbv[NQ];
+#pragma unroll
+        for (int k = 0; k < NQ; k++) nbv[k] = f[k * NX + cur.c];
+        if (j + 1 < nAll) fetch(j + 1, nxt);
+        const int type = cur.type;
+        const double Sx = cur.Sx, Sy = cur.Sy, Sz = cur.Sz, w = cur.w;
 #pragma unroll
         for (int k = 0; k < NQ; k++) {
-            const double nb = f[k * NX + c];
+            const double nb = nbv[k];
             double ssf;
             if (type == ET_UPPER) ssf = w * (own[k] - nb) + nb;            // P = row, N = col
             else if (type == ET_LOWER) ssf = w * (nb - own[k]) + own[k];   // P = col, N = row
@@ -288,6 +321,7 @@ k_grad(int NP, const int* __restrict__ pos2cell, const int* __restrict__ sliceOf
             if (type == ET_LOWER) { acc[k][0] -= tx; acc[k][1] -= ty; acc[k][2] -= tz; }
             else { acc[k][0] += tx; acc[k][1] += ty; acc[k][2] += tz; }
         }
+        cur = nxt;
     }
     const double vol = V[p];
 #pragma unroll
@@ -400,12 +434,20 @@ k_flux_gather(FluxArgs a)
     const size_t base = (size_t)a.sliceOff[p >> 5];
     double acc[5] = {0, 0, 0, 0, 0};
     const int nAll = a.rowNAll[p], nLow = a.rowNLow[p];
-    for (int j = 0; j < nAll; j++) {
+    // all face ids first, then the fluxes of the next face while the current one is added (ascending face id kept)
+    double fc[5], fn[5];
+    auto fetch = [&](int j, double* o) {
         const size_t g = a.gfid[(base + j) * 32 + lane];
-        const double f0 = a.faceFlux[g], f1 = a.faceFlux[a.NFG + g], f2 = a.faceFlux[2 * a.NFG + g], f3 = a.faceFlux[3 * a.NFG + g],
-                     f4 = a.faceFlux[4 * a.NFG + g];
-        if (j < nLow) { acc[0] -= f0; acc[1] -= f1; acc[2] -= f2; acc[3] -= f3; acc[4] -= f4; }
-        else { acc[0] += f0; acc[1] += f1; acc[2] += f2; acc[3] += f3; acc[4] += f4; }
+#pragma unroll
+        for (int k = 0; k < 5; k++) o[k] = a.faceFlux[k * a.NFG + g];
+    };
+    if (nAll > 0) fetch(0, fc);
+    for (int j = 0; j < nAll; j++) {
+        if (j + 1 < nAll) fetch(j + 1, fn);
+        if (j < nLow) { acc[0] -= fc[0]; acc[1] -= fc[1]; acc[2] -= fc[2]; acc[3] -= fc[3]; acc[4] -= fc[4]; }
+        else { acc[0] += fc[0]; acc[1] += fc[1]; acc[2] += fc[2]; acc[3] += fc[3]; acc[4] += fc[4]; }
+#pragma unroll
+        for (int k = 0; k < 5; k++) fc[k] = fn[k];
     }
     // residualsUpdate.H: R = -div(phi*) [- (ddt.diag*W - ddt.source)/V]; source = R*V
     const double vol = a.V[p];
@@ -755,6 +797,7 @@ int ics_flux_residual(icsb200_ctx* c, bool storeFaceFlux)
         const int grid = gridFor(c->NP, 128);
         if (c->sch.flux_scheme == ICSB200_FLUX_HLLC) k_flux_faces<ICSB200_FLUX_HLLC><<<grid, 128, 0, c->stream>>>(a);
         else if (c->sch.flux_scheme == ICSB200_FLUX_ROE) k_flux_faces<ICSB200_FLUX_ROE><<<grid, 128, 0, c->stream>>>(a);
+        else if (c->sch.flux_scheme == ICSB200_FLUX_RUSANOV) k_flux_faces<ICSB200_FLUX_RUSANOV><<<grid, 128, 0, c->stream>>>(a);
         else k_flux_faces<ICSB200_FLUX_AUSMPLUSUP><<<grid, 128, 0, c->stream>>>(a);
         k_flux_gather<<<gridFor(c->NP, 256), 256, 0, c->stream>>>(a);
         c->launches++;

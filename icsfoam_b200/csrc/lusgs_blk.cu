@@ -98,6 +98,12 @@ __device__ __forceinline__ void mbExpectTx(unsigned long long* b, unsigned bytes
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(sAddr(b)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbArrive(unsigned long long* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sAddr(b)) : "memory"); }
+// arrival without release semantics: for handing a ring stage back, where the only ordering needed — this warp's reads of the
+// stage have completed — holds because their values have been consumed
+__device__ __forceinline__ void mbArriveRelaxed(unsigned long long* b)
+{
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(sAddr(b)) : "memory");
+}
 __device__ __forceinline__ bool mbTry(unsigned long long* b, unsigned parity)
 {
     unsigned ok;
@@ -336,34 +342,31 @@ k_lusgs_blk(BlkArgs a)
     }
 
     if (warp == NCW + 2) {
-        // ---------------- publish warp: copies the tile's swept values from shared memory to x (plain coalesced stores: no global
-        // store and no proxy fence sits on the consumers' dependent path), then lane 0 releases the tile's epoch flag — the
-        // warp's stores precede it through __syncwarp, the st.release is cumulative — and the tile buffer goes back to the
-        // metadata warp.
-        for (int i = 0;; i++) {
-            bool fwd;
-            int tile;
-            if (!getItem(i, fwd, tile)) return;
-            const int buf = i % NBUF;
-            long long pk = PROF ? clock64() : 0;
-            if (!mbWait(sm.done + buf, (i / NBUF) & 1, a.err)) return;
-            if (PROF && lane == 0) { const long long t2 = clock64(); a.prof[(size_t)b * 24 + 16] += t2 - pk; pk = t2; }
-            const int t0 = sm.meta[buf].tab[BT_T0], nRp = sm.meta[buf].tab[BT_NROWS];
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-                const double* src = &sm.xs[buf][k][0];
-                double* dst = a.x + k * a.NPH + t0;
-                for (int rw = lane; rw < nRp; rw += 32) __stcg(dst + rw, src[rw]);
-            }
-            __syncwarp();
-            if (PROF && lane == 0) { const long long t2 = clock64(); a.prof[(size_t)b * 24 + 17] += t2 - pk; pk = t2; }
-            if (lane == 0) {
+        // ---------------- publish warp: the tile's swept values go from shared memory to x in five bulk stores (no global store
+        // sits on the consumers' dependent path; they end their last sweep of the tile with an async-proxy fence); the bulk
+        // stores' completion is followed by an implicit generic-async proxy fence, then st.release of the tile's epoch flag (the
+        // consumers' arrival on done[] and this thread's release are cumulative) and the tile buffer goes back to the metadata warp.
+        if (lane == 0) {
+            for (int i = 0;; i++) {
+                bool fwd;
+                int tile;
+                if (!getItem(i, fwd, tile)) return;
+                const int buf = i % NBUF;
+                long long pk = PROF ? clock64() : 0;
+                if (!mbWait(sm.done + buf, (i / NBUF) & 1, a.err)) return;
+                if (PROF) { const long long t2 = clock64(); a.prof[(size_t)b * 24 + 16] += t2 - pk; pk = t2; }
+                const int t0 = sm.meta[buf].tab[BT_T0];
+                const unsigned rowB = (unsigned)sm.meta[buf].tab[BT_NROWS] * 8;
+                for (int k = 0; k < 5; k++) bulkStore(a.x + k * a.NPH + t0, &sm.xs[buf][k][0], rowB);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                if (PROF) { const long long t2 = clock64(); a.prof[(size_t)b * 24 + 17] += t2 - pk; pk = t2; }
                 stRelease(a.flag + (fwd ? tile : a.nTiles + tile), a.epoch);
                 mbArrive(sm.mempty + buf);
                 if (PROF) { const long long t2 = clock64(); a.prof[(size_t)b * 24 + 18] += t2 - pk; pk = t2; if (a.trace) a.trace[((size_t)(fwd ? 0 : a.nTiles) + tile) * 8 + 5] = gtime(); }
             }
-            __syncwarp();
         }
+        return;
     }
 
     // ---------------- consumers: two groups of five warps (one warp per component of the block row) take the levels in turn.
@@ -401,7 +404,7 @@ k_lusgs_blk(BlkArgs a)
         auto releaseTo = [&](int target) {
             __syncwarp();  // every lane's block reads precede lane 0's arrival
             while (relNext < target) {
-                if (lane == 0) mbArrive(sm.empty + relSt);
+                if (lane == 0) mbArriveRelaxed(sm.empty + relSt);
                 relSt = relSt + 1 == NST ? 0 : relSt + 1;
                 relNext++;
             }
@@ -494,6 +497,8 @@ k_lusgs_blk(BlkArgs a)
                     sweepUnit(V);
                 }
                 const long long q3 = prof ? clock64() : 0;
+                // the bulk stores of the publish warp read what this thread wrote: async-proxy fence after its last sweep of the item
+                if (li + 2 >= nLev) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {
                     mbArrive(sm.lvl + grp);

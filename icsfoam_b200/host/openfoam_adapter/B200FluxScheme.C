@@ -7,9 +7,11 @@ namespace Foam
     defineTemplateTypeNameAndDebugWithName(hllcB200FluxScheme, "HLLCB200", 0);
     defineTemplateTypeNameAndDebugWithName(roeB200FluxScheme, "ROEB200", 0);
     defineTemplateTypeNameAndDebugWithName(ausmPlusUpB200FluxScheme, "AUSMPlusUpB200", 0);
+    defineTemplateTypeNameAndDebugWithName(rusanovB200FluxScheme, "RusanovB200", 0);   // no CPU counterpart in ICSFoam
     addToRunTimeSelectionTable(convectiveFluxScheme, hllcB200FluxScheme, dictionary);
     addToRunTimeSelectionTable(convectiveFluxScheme, roeB200FluxScheme, dictionary);
     addToRunTimeSelectionTable(convectiveFluxScheme, ausmPlusUpB200FluxScheme, dictionary);
+    addToRunTimeSelectionTable(convectiveFluxScheme, rusanovB200FluxScheme, dictionary);
 }
 
 template<int Scheme>

@@ -45,7 +45,10 @@ typedef struct {
 } icsb200_patch;
 
 /* run-time selectors — same words as the reference dictionaries */
-enum { ICSB200_FLUX_HLLC = 0, ICSB200_FLUX_ROE = 1, ICSB200_FLUX_AUSMPLUSUP = 2 };    /* fvSchemes convectiveFluxScheme/fluxScheme */
+enum { ICSB200_FLUX_HLLC = 0, ICSB200_FLUX_ROE = 1, ICSB200_FLUX_AUSMPLUSUP = 2,       /* fvSchemes convectiveFluxScheme/fluxScheme */
+       ICSB200_FLUX_RUSANOV = 3 };  /* NOT a reference scheme (src/Make/files:47-51 has none): the local Lax-Friedrichs flux whose
+                                       linearisation the reference's approximate Jacobian is (convectiveFluxScheme.C:402-546);
+                                       named by the project brief, parity unpinned by construction */
 enum { ICSB200_LIM_UPWIND = 0, ICSB200_LIM_VANLEER = 1, ICSB200_LIM_MINMOD = 2, ICSB200_LIM_LINEAR = 3 }; /* interpolationSchemes reconstruct(.) */
 enum { ICSB200_DDT_STEADY = 0, ICSB200_DDT_EULER = 1, ICSB200_DDT_BACKWARD = 2 };       /* ddtSchemes: dualTime rPseudoDeltaT <inner> */
 enum { ICSB200_SOLVER_GMRES = 0, ICSB200_SOLVER_SMOOTH = 1 };                            /* fvSolution flowSolver/solver: GMRES,

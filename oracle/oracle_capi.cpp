@@ -141,7 +141,7 @@ int orc_thermo_set(Ctx* c, double R, double Cp, double mu, double Pr)
 
 int orc_schemes_set(Ctx* c, const icsb200_schemes* s)
 {
-    if (s->flux_scheme < 0 || s->flux_scheme > 2) return fail(c, ICSB200_EINVAL, "Unknown convectiveFluxScheme type");
+    if (s->flux_scheme < 0 || s->flux_scheme > ICSB200_FLUX_RUSANOV) return fail(c, ICSB200_EINVAL, "Unknown convectiveFluxScheme type");
     c->sch = *s;
     return 0;
 }

@@ -289,6 +289,22 @@ inline FaceLR gatherLR(const Recon& r, int f, bool needC)
 }  // namespace
 
 // convectiveFluxScheme::calcFlux
+// ---------------------------------------------------------------------------------------------- Rusanov
+// No reference counterpart (src/Make/files:47-51 lists HLLC, ROE, AUSM+up only): the local Lax-Friedrichs flux of the limited
+// states in the relative frame — the flux whose frozen-lambda linearisation is the reference's approximate Jacobian
+// (convectiveFluxScheme.C:402-546).  Pinned by known answers only (tests/test_oracle_kat.py).
+void fluxRusanov(const Ctx&, const FaceLR& s, V3 Sf, double magSf, double mrf, double& phi, V3& phiUp, double& phiEp)
+{
+    const V3 n = Sf / magSf;
+    const double uL = (s.U_l & n) - mrf, uR = (s.U_r & n) - mrf;
+    const double lam = std::max(std::fabs(uL) + s.c_l, std::fabs(uR) + s.c_r);
+    const double mL = s.rho_l * uL, mR = s.rho_r * uR;
+    phi = (0.5 * (mL + mR) - 0.5 * lam * (s.rho_r - s.rho_l)) * magSf;
+    phiUp = (0.5 * ((mL * s.U_l + s.p_l * n) + (mR * s.U_r + s.p_r * n)) - (0.5 * lam) * (s.rho_r * s.U_r - s.rho_l * s.U_l)) * magSf;
+    phiEp = (0.5 * ((mL * s.H_l + s.p_l * mrf) + (mR * s.H_r + s.p_r * mrf)) - 0.5 * lam * (s.rho_r * s.E_r - s.rho_l * s.E_l)) * magSf;
+}
+
+// ---------------------------------------------------------------------------------------------- the face loop
 void calcFlux(Ctx& c)
 {
     const Mesh& m = c.m;
@@ -309,6 +325,7 @@ void calcFlux(Ctx& c)
         const double mrf = c.mrfAt(f);  // flux.MRFFaceVelocity() (outerLoop.H:18-21)
         if (scheme == ICSB200_FLUX_HLLC) fluxHLLC(c, s, Sf, m.magSf[f], mrf, phi, phiUp, phiEp);
         else if (scheme == ICSB200_FLUX_ROE) fluxROE(c, s, Sf, m.magSf[f], mrf, phi, phiUp, phiEp);
+        else if (scheme == ICSB200_FLUX_RUSANOV) fluxRusanov(c, s, Sf, m.magSf[f], mrf, phi, phiUp, phiEp);
         else fluxAUSM(c, s, Sf, m.magSf[f], mrf, phi, phiUp, phiEp);
         c.phi[f] = phi; c.phiEp[f] = phiEp;
         c.phiUp[3 * (size_t)f] = phiUp.x; c.phiUp[3 * (size_t)f + 1] = phiUp.y; c.phiUp[3 * (size_t)f + 2] = phiUp.z;

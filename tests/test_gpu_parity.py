@@ -54,6 +54,8 @@ LIVE = {
     "box-hllc-minmod": lambda: cases.periodic_box(7, "HLLC", "Minmod", seed=21),
     "box-roe-vanleer": lambda: cases.periodic_box(6, "ROE", "vanLeer", seed=22),
     "box-ausm-minmod": lambda: cases.periodic_box(6, "AUSMPlusUp", "Minmod", seed=23),
+    "box-rusanov-vanleer": lambda: cases.periodic_box(6, "Rusanov", "vanLeer", seed=29),
+    "box-rusanov-mrf": lambda: cases.periodic_box(5, "Rusanov", "Minmod", seed=31).with_mrf((10.0, 60.0, 0.0), velocity=(0.0, 0.0, 35.0)),
     "box-hllc-upwind": lambda: cases.periodic_box(5, "HLLC", "upwind", seed=24),
     "box-ragged": lambda: cases.periodic_box(5, "HLLC", "vanLeer", seed=25, nz=3),
     "bump": lambda: cases.bump(15, 10),

@@ -56,7 +56,8 @@ def test_no_cpu_fallback():
 
 
 def test_selector_names_follow_reference_dictionaries():
-    assert set(capi.FLUX_NAMES) == {"HLLC", "ROE", "AUSMPlusUp"}          # src/Make/files:47-51 (no Rusanov flux exists)
+    # src/Make/files:47-51: the reference has HLLC, ROE, AUSMPlusUp; "Rusanov" is this library's own addition (named by the brief)
+    assert set(capi.FLUX_NAMES) == {"HLLC", "ROE", "AUSMPlusUp", "Rusanov"}
     assert set(capi.PRECOND_NAMES) == {"LUSGS", "Jacobi"}
     assert capi.DDT_NAMES["steadyState"] == 0
     o = pyoracle.Oracle()
