@@ -5,24 +5,26 @@
 // respects the owner < neighbour DAG reproduces the sequential result bit for bit; the level pipeline (solver.cu) walks the
 // DAG one hyperplane at a time and pays one L2 round trip per level (3n-2 levels of ~3 us each on an n^3 box), which is
 // what bounded the sweeps on small partitions.  Here the mesh is cut into tiles of <= 256 rows (setup.cu: `depth`
-// consecutive hyperplanes of an 8x8 column on a structured 3-D mesh, i.e. 4 levels of 64 rows) that form a DAG of their
-// own; one CTA sweeps a whole tile out of shared memory and five kinds of warps keep every global round trip off the
-// sweep's dependent path:
-//   * 10 CONSUMER warps sweep the tile's levels.  A row is swept by FIVE threads (one per component of the 5x5 block row),
-//     so the dependent part of a level is 15 shared-memory reads, 15 products and 9 ordered subtractions per thread.
-//     Everything of a level that does not depend on the sweep (packed neighbour info, rD, the thread's 15 block
-//     coefficients, the right-hand side) is loaded into registers while the PREVIOUS level is still being swept: levels are
-//     separated by a split mbarrier (arrive after the stores, wait before the next level's first read of sweep values);
+// consecutive hyperplanes of an 8x4 column on a structured 3-D mesh, i.e. 8 or 4 levels of 32 rows; 16-wide strips on a
+// 2-D mesh) that form a DAG of their own; one CTA sweeps a whole tile out of shared memory and five kinds of warps keep
+// every global round trip off the sweep's dependent path:
+//   * 10 CONSUMER warps in two groups of five sweep the tile's levels in turn.  A row is swept by FIVE threads (one per
+//     component of the 5x5 block row, one warp per component), so the dependent part of a level is 18 shared-memory
+//     reads, 30 products and 9 ordered subtractions per thread.  While one group sweeps level L, the other loads everything
+//     level L+1 needs that does not depend on the sweep (packed neighbour info, rD, the thread's 15 block coefficients, the
+//     right-hand side) into registers; two hardware named barriers, used producer / consumer style, hand the levels over;
 //   * the PRODUCER warp streams the 5x5 blocks (600 of ~700 B per row and sweep) with cp.async.bulk (TMA) into a ring of
-//     slice stages, many slices ahead of the consumers and across tile boundaries, and bulk-copies each tile's metadata
-//     (table of levels / halo positions / flags to wait for, rD, packed row info, forward: the right-hand side) into one of
-//     two metadata stages one tile ahead;
-//   * the HALO warp works one tile ahead of the consumers: it polls the epoch flags of the tiles the next tile depends on
-//     (ld.acquire), gathers the out-of-tile neighbour values into the tile's shared-memory vector (forward: times rD) and,
-//     in the reverse sweep, bulk-copies the tile's own forward values;
-//   * the PUBLISH warp waits for the consumers' last store of a tile, then fence + st.release of the tile's epoch flag and
-//     hands the metadata stage back.  No sentinel buffers: the sweeps run IN PLACE on x exactly like the reference (the
-//     forward sweep overwrites the right-hand side with dW* D, the reverse sweep overwrites that with dW).
+//     8 slice stages, many slices ahead of the consumers and across tile boundaries;
+//   * the METADATA warp deals the tiles: it draws a ticket from a global counter whenever one of the three tile buffers is
+//     free and bulk-copies the tile's table (levels, halo positions, flags to wait for), rD, packed row info and (forward)
+//     right-hand side into it;
+//   * the HALO warp works up to two tiles ahead of the consumers: it polls the epoch flags of the tiles the tile depends on
+//     (ld.acquire), gathers the out-of-tile neighbour values into the tile's shared-memory vector and, in the reverse
+//     sweep, bulk-copies the tile's own forward values;
+//   * the PUBLISH warp waits for the consumers' last sweep of a tile, bulk-stores the tile's vector from shared memory to
+//     x, then st.release of the tile's epoch flag, and hands the tile buffer back.  No sentinel buffers: the sweeps run IN
+//     PLACE on x exactly like the reference (the forward sweep overwrites the right-hand side with dW* D, the reverse
+//     sweep overwrites that with dW).
 // Operand order per row is the reference's: neighbours in ascending (forward) / descending (reverse) face order, per
 // neighbour the S.S columns (rho, rhoE), then V.S / S.V / V.V (lusgs.C:240-303, 318-380).
 #include <algorithm>
@@ -81,7 +83,7 @@ struct BlkSmem {
     int4 itemIdx[NBUF];
     int2 itemStage[NBUF][MR / 32];
     double zeroB[160];    // the 5x5 block of an absent neighbour (element (k, lane) of a component's row at k*32 + lane)
-    unsigned long long full[NST], empty[NST], idfull[NBUF], mfull[NBUF], mempty[NBUF], hfull[NBUF], done[NBUF], lvl[2];
+    unsigned long long full[NST], empty[NST], idfull[NBUF], mfull[NBUF], mempty[NBUF], hfull[NBUF], done[NBUF];
 };
 
 __device__ __forceinline__ unsigned sAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -118,6 +120,12 @@ __device__ __forceinline__ bool mbWait(unsigned long long* b, unsigned parity, i
     }
     return true;
 }
+// Level hand-over between the two consumer groups: hardware named barriers 1 + g, producer / consumer style — the NCT / 2
+// threads of group g arrive (bar.arrive, non-blocking) after sweeping a level, the NCT / 2 threads of the other group wait
+// (bar.sync) before sweeping the next one; the barrier completes, and resets, at NCT arrivals.  Strictly alternating by
+// construction (a group cannot arrive again before the other group has passed its wait and arrived on the other barrier).
+__device__ __forceinline__ void lvlArrive(int g) { asm volatile("bar.arrive %0, %1;" ::"r"(1 + g), "n"(NCT) : "memory"); }
+__device__ __forceinline__ void lvlSync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(NCT) : "memory"); }
 __device__ __forceinline__ void bulkLoad(void* dstSmem, const void* srcGlobal, unsigned bytes, unsigned long long* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sAddr(dstSmem)), "l"(srcGlobal), "r"(bytes),
@@ -166,7 +174,6 @@ k_lusgs_blk(BlkArgs a)
     if (tid == 0) {
         for (int s = 0; s < NST; s++) { mbInit(sm.full + s, 1); mbInit(sm.empty + s, NCW); }
         for (int s = 0; s < NBUF; s++) { mbInit(sm.idfull + s, 1); mbInit(sm.mfull + s, 1); mbInit(sm.mempty + s, 1); mbInit(sm.hfull + s, 1); mbInit(sm.done + s, NCW / 2); }
-        mbInit(sm.lvl, NCW / 2); mbInit(sm.lvl + 1, NCW / 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // the zero slot absent neighbours point to (last entry of the tile's vector and of its rD), and the zero block
@@ -373,14 +380,13 @@ k_lusgs_blk(BlkArgs a)
     // While one group sweeps level L — the dependent part: neighbour values out of shared memory, 15 products, the ordered
     // subtractions — the other group loads everything level L+1 needs that does not depend on the sweep (packed neighbour
     // info, rD, right-hand side, its 15 block coefficients out of the ring) into registers, so the chain from level to level is
-    // barrier -> sweep -> barrier.  lvl[g] is arrived on by group g after each of its sweeps and waited on by the other group.
+    // barrier -> sweep -> barrier (named barrier 1 + g: group g arrives after each of its sweeps, the other group waits on it).
     const bool prof = PROF && tid == 0;
     long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long tStart = prof ? clock64() : 0;
     const int r = warp % 5, grp = warp / 5;
     int base = 0;          // ring position of the current item's first slice (all consumers count alike)
     int gl0 = 0;           // levels swept before the current item (both groups count alike): level l of the item belongs to group (gl0 + l) & 1
-    unsigned nWaits = 0;   // completed waits on the other group's level barrier
     for (int i = 0;; i++) {
         bool fwd;
         int tile;
@@ -483,9 +489,10 @@ k_lusgs_blk(BlkArgs a)
             if (prof) { const long long t2 = clock64(); pf[PF_HALO] += t2 - tk; tk = t2; }
             for (int li = first; li < nLev; li += 2) {
                 if (gl0 + li > 0) {   // the level before this one, swept by the other group (possibly as the last level of the previous item)
-                    if (PROF) { const long long q0 = prof ? clock64() : 0; mbWait(sm.lvl + (grp ^ 1), nWaits & 1, a.err); if (prof) pf[PF_LVLWAIT] += clock64() - q0; }
-                    else mbWait(sm.lvl + (grp ^ 1), nWaits & 1, a.err);
-                    nWaits++;
+                    const long long q0 = prof ? clock64() : 0;
+                    __syncwarp();
+                    lvlSync(grp ^ 1);
+                    if (prof) pf[PF_LVLWAIT] += clock64() - q0;
                 }
                 const long long q2 = prof ? clock64() : 0;
                 sweepUnit(U);
@@ -500,10 +507,9 @@ k_lusgs_blk(BlkArgs a)
                 // the bulk stores of the publish warp read what this thread wrote: async-proxy fence after its last sweep of the item
                 if (li + 2 >= nLev) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) {
-                    mbArrive(sm.lvl + grp);
-                    if (li == nLev - 1) mbArrive(sm.done + buf);  // every earlier level is ordered before this one through the level barriers
-                }
+                __threadfence_block();   // bar.arrive itself orders nothing: this thread's stores first
+                lvlArrive(grp);
+                if (lane == 0 && li == nLev - 1) mbArrive(sm.done + buf);  // every earlier level is ordered before this one through the level barriers
                 // The block coefficients of this level have been consumed, so the stages of the slices whose rows all lie in levels
                 // <= li go back to the producer now (an arrival right after the loads would wait for them to land instead of
                 // letting them overlap the other group's sweep).

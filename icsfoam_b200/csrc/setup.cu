@@ -424,9 +424,27 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                 bside = envInt("ICSB200_LUSGS_BSIDE", bside);
                 int bside2 = nCross == 2 ? 4 : bside;
                 bside2 = envInt("ICSB200_LUSGS_BSIDE2", bside2);
-                // depth: large meshes are bandwidth-bound (8 levels amortise the per-tile traffic best: 344^3 10.3 ms against 12.8 with
-                // 4), small ones are bound by the chain of tile steps, which 4-level tiles shorten (172^3 2.68 ms against 2.82)
-                int depth = nCross == 2 ? (N >= 16000000 ? 8 : 4) : (nCross == 1 ? 16 : 32);
+                // depth (3-D): 8 levels per tile amortise the per-tile traffic and hop best when the sweep is bandwidth-bound (344^3:
+                // 10.3 ms against 12.8 with 4); when it is bound by the chain of tile steps, the depth with the shorter chain wins
+                // (172^3: 193 steps of 4 levels, 2.68 ms, against 149 steps of 8 levels, 2.82 ms).  Model: step = depth x 0.6 us +
+                // 4.6 us (lusgs_blk_trace.py medians), bytes at 5.5 TB/s.
+                int depth = nCross == 2 ? 8 : (nCross == 1 ? 16 : 32);
+                if (nCross == 2) {
+                    auto steps = [&](int dep) {
+                        int n = 0, sm2 = umax[sweep], nth = 0;
+                        for (int d = 0; d < 3; d++) {
+                            if (d == sweep) continue;
+                            if (umax[d] + 1 < 4) { sm2 += umax[d]; continue; }
+                            const int b2 = nth++ == 0 ? bside : bside2;
+                            n += ((b2 - 1 + dep - 1) / dep + 1) * (umax[d] / b2);
+                            sm2 += b2 - 1;
+                        }
+                        return n + sm2 / dep + 1;
+                    };
+                    const double chain8 = steps(8) * (8 * 0.6 + 4.6), chain4 = steps(4) * (4 * 0.6 + 4.6);   // us per sweep
+                    const double bytesUs = (double)N * 710.0 / 5.5e6;   // us per sweep at 5.5 TB/s
+                    depth = (bytesUs < chain8 && chain4 < chain8) ? 4 : 8;
+                }
                 depth = envInt("ICSB200_LUSGS_DEPTH", depth);
                 int bs[3] = {1, 1, 1}, nbin[3] = {1, 1, 1}, K[3] = {0, 0, 0};
                 {

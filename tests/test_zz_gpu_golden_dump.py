@@ -38,7 +38,8 @@ def test_write_flux_directory_matches_the_host_path(gpu_context, tmp_path):
     tdir = r.stdout.split("fields written to", 1)[1].split()[0]
     case = cases.vki_ls89(STAGED + "/constant/polyMesh")     # steady: one outer iteration per "time step" (same set-up as test_gpu_driver)
     g = case.apply(gpu_context())
-    n_pseudo = sum(1 for ln in r.stdout.splitlines() if ln.startswith("pseudoTime: iteration"))
+    # the tutorial sets nPseudoCorr 1, for which pseudotimeControl::loop() prints no "pseudoTime: iteration" line (pseudotimeControl.C:229)
+    n_pseudo = sum(1 for ln in r.stdout.splitlines() if ln.startswith("GMRES : Solving for"))
     assert n_pseudo == 2
     for it in range(n_pseudo):
         phi, phiUp, phiEp = g.calc_flux()            # as the driver does before every iteration; the last one is what dbnsFoam's phi holds at write time
