@@ -149,6 +149,8 @@ struct icsb200_ctx {
     long long* d_blkTrace = nullptr;          // optional per-tile global-timer stamps (ICSB200_LUSGS_TRACE)
     int* d_blkStage = nullptr;   // [2][nSlices][2] per sweep and slice: first staged block entry, number of staged entries
     int* d_blkFlag = nullptr;    // [2*nTiles] completion epochs: forward sweep of tile t, reverse sweep of tile t
+    int* d_blkCol = nullptr;     // [nBlkCols + 1] first tile of each column (the unit of work a CTA draws; lusgs_blk.cu)
+    int nBlkCols = 0;
     int blkEpoch = 0;
     int *d_rowLevF = nullptr, *d_rowLevR = nullptr;      // [NP] intra-tile level of a row in the forward / reverse sweep (-1 padding)
     int *d_tileNLevF = nullptr, *d_tileNLevR = nullptr;  // [nTiles] number of intra-tile levels

@@ -28,6 +28,7 @@
 // Operand order per row is the reference's: neighbours in ascending (forward) / descending (reverse) face order, per
 // neighbour the S.S columns (rho, rhoE), then V.S / S.V / V.V (lusgs.C:240-303, 318-380).
 #include <algorithm>
+#include <climits>
 #include <string>
 
 #include "common.cuh"
@@ -47,14 +48,14 @@ constexpr int NTHREADS = NCT + 128;    // + producer, halo, publish and metadata
 constexpr int HIT = (MH + 31) / 32;    // halo entries per lane of the halo warp
 
 // a tile's table (setup.cu): 16 descriptor ints, then the sections they point to
-enum { BT_T0 = 0, BT_NROWS, BT_REG, BT_NLEV, BT_LEV, BT_HALOF, BT_NHALOF, BT_HALOR, BT_NHALOR, BT_DEPF, BT_NDEPF, BT_DEPR, BT_NDEPR, BT_SLICEOFF, BT_REVLO, BT_NSL };
+enum { BT_T0 = 0, BT_NROWS, BT_COL, BT_NLEV, BT_LEV, BT_HALOF, BT_NHALOF, BT_HALOR, BT_NHALOR, BT_DEPF, BT_NDEPF, BT_DEPR, BT_NDEPR, BT_SLICEOFF, BT_REVLO, BT_NSL };
 // profile slots per CTA (ICSB200_LUSGS_PROF), consumer thread 0: cycles waiting for the metadata stage, for the halo warp, in the
 // level loops, of which waiting at the level barrier / for block stages; tiles swept, levels swept, total
 enum { PF_META = 0, PF_HALO, PF_LEVELS, PF_LVLWAIT, PF_FULLWAIT, PF_TILES, PF_NLEV, PF_TOTAL };
 
 struct BlkArgs {
-    int nTiles, nSlices, NP;
-    const int *tab, *idx, *stage;
+    int nTiles, nSlices, NP, nCols;
+    const int *tab, *idx, *stage, *colStart;
     const unsigned long long* info;
     const double *offd, *rD;
     double* x;
@@ -173,7 +174,7 @@ k_lusgs_blk(BlkArgs a)
     const int G = gridDim.x, b = blockIdx.x;
     if (tid == 0) {
         for (int s = 0; s < NST; s++) { mbInit(sm.full + s, 1); mbInit(sm.empty + s, NCW); }
-        for (int s = 0; s < NBUF; s++) { mbInit(sm.idfull + s, 1); mbInit(sm.mfull + s, 1); mbInit(sm.mempty + s, 1); mbInit(sm.hfull + s, 1); mbInit(sm.done + s, NCW / 2); }
+        for (int s = 0; s < NBUF; s++) { mbInit(sm.idfull + s, 1); mbInit(sm.mfull + s, 1); mbInit(sm.mempty + s, 2); mbInit(sm.hfull + s, 1); mbInit(sm.done + s, NCW / 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // the zero slot absent neighbours point to (last entry of the tile's vector and of its rD), and the zero block
@@ -237,39 +238,50 @@ k_lusgs_blk(BlkArgs a)
     if (warp == NCW + 3) {
         // ---------------- metadata warp: draws the tickets; a tile's table, rD, packed row info and (forward) right-hand side go
         // into the tile buffer as soon as the publish warp has handed it back, independently of the block ring
-        for (int i = 0;; i++) {
-            const int buf = i % NBUF;
-            const long long q0 = PROF ? clock64() : 0;
-            if (i >= NBUF && !mbWait(sm.mempty + buf, ((i / NBUF) + 1) & 1, a.err)) return;
-            if (PROF && lane == 0) a.prof[(size_t)b * 24 + 20] += clock64() - q0;
+        // A ticket is a COLUMN (setup.cu): a run of tiles that this CTA sweeps back to back, each handing its last level to the
+        // next one in shared memory; without column mode every tile is a column of its own.
+        const int nC = a.nCols;
+        int i = 0;
+        for (;;) {
             int v = 0;
             if (lane == 0) v = atomicAdd(ticket, 1);
             v = __shfl_sync(0xffffffffu, v, 0);
-            if (v >= 2 * nT) {
+            if (v >= 2 * nC) {
+                const int buf = i % NBUF;
+                if (i >= NBUF && !mbWait(sm.mempty + buf, ((i / NBUF) + 1) & 1, a.err)) return;
                 if (lane == 0) { sm.itemTicket[buf] = -1; mbArrive(sm.idfull + buf); }
                 return;
             }
-            const bool fwd = v < nT;
-            const int tile = fwd ? v : 2 * nT - 1 - v;
-            const int4 ix = reinterpret_cast<const int4*>(a.idx)[tile];
-            const int s0 = ix.z >> 5, nSl = ix.w >> 5;
-            if (lane < nSl) {
-                const int sl = fwd ? (s0 + lane) : (s0 + nSl - 1 - lane);
-                sm.itemStage[buf][lane] = reinterpret_cast<const int2*>(a.stage)[(size_t)(fwd ? 0 : a.nSlices) + sl];
-            }
-            if (lane == 0) { sm.itemTicket[buf] = v; sm.itemIdx[buf] = ix; }
-            __syncwarp();
-            if (lane == 0) {
-                mbArrive(sm.idfull + buf);
-                Meta& M = sm.meta[buf];
-                const unsigned rowB = (unsigned)ix.w * 8, tabB = (unsigned)ix.y * 4;
-                mbArriveExpectTx(sm.mfull + buf, tabB + 2 * rowB + (fwd ? 5 * rowB : 0));
-                bulkLoad(M.tab, a.tab + ix.x, tabB, sm.mfull + buf);
-                bulkLoad(M.info, a.info + (fwd ? (size_t)0 : (size_t)a.NP) + ix.z, rowB, sm.mfull + buf);
-                bulkLoad(M.rD, a.rD + ix.z, rowB, sm.mfull + buf);
-                if (fwd) {
-                    for (int k = 0; k < 5; k++) bulkLoad(&sm.xs[buf][k][0], a.x + k * a.NPH + ix.z, rowB, sm.mfull + buf);
+            const bool fwd = v < nC;
+            const int col = fwd ? v : 2 * nC - 1 - v;
+            const int c0 = a.colStart[col], c1 = a.colStart[col + 1];
+            for (int k = 0; k < c1 - c0; k++, i++) {
+                const int tile = fwd ? c0 + k : c1 - 1 - k;
+                const int buf = i % NBUF;
+                const long long q0 = PROF ? clock64() : 0;
+                if (i >= NBUF && !mbWait(sm.mempty + buf, ((i / NBUF) + 1) & 1, a.err)) return;
+                if (PROF && lane == 0) a.prof[(size_t)b * 24 + 20] += clock64() - q0;
+                const int4 ix = reinterpret_cast<const int4*>(a.idx)[tile];
+                const int s0 = ix.z >> 5, nSl = ix.w >> 5;
+                if (lane < nSl) {
+                    const int sl = fwd ? (s0 + lane) : (s0 + nSl - 1 - lane);
+                    sm.itemStage[buf][lane] = reinterpret_cast<const int2*>(a.stage)[(size_t)(fwd ? 0 : a.nSlices) + sl];
                 }
+                if (lane == 0) { sm.itemTicket[buf] = fwd ? tile : 2 * nT - 1 - tile; sm.itemIdx[buf] = ix; }
+                __syncwarp();
+                if (lane == 0) {
+                    mbArrive(sm.idfull + buf);
+                    Meta& M = sm.meta[buf];
+                    const unsigned rowB = (unsigned)ix.w * 8, tabB = (unsigned)ix.y * 4;
+                    mbArriveExpectTx(sm.mfull + buf, tabB + 2 * rowB + (fwd ? 5 * rowB : 0));
+                    bulkLoad(M.tab, a.tab + ix.x, tabB, sm.mfull + buf);
+                    bulkLoad(M.info, a.info + (fwd ? (size_t)0 : (size_t)a.NP) + ix.z, rowB, sm.mfull + buf);
+                    bulkLoad(M.rD, a.rD + ix.z, rowB, sm.mfull + buf);
+                    if (fwd) {
+                        for (int kk = 0; kk < 5; kk++) bulkLoad(&sm.xs[buf][kk][0], a.x + kk * a.NPH + ix.z, rowB, sm.mfull + buf);
+                    }
+                }
+                __syncwarp();
             }
         }
     }
@@ -299,7 +311,7 @@ k_lusgs_blk(BlkArgs a)
 #pragma unroll
             for (int it = 0; it < HIT; it++) {
                 const int h = it * 32 + lane;
-                hq[it] = h < nHalo ? halo[h] : -1;
+                hq[it] = h < nHalo ? halo[h] : INT_MIN;   // >= 0: global position; -(row) - 1: row of the tile swept just before (column mode)
             }
             // acquire polls, one flag per lane (nothing else of this SM lives in L1, so the invalidate that comes with each costs
             // nothing; a separate fence after relaxed polls, with loads in flight, costs microseconds)
@@ -340,10 +352,29 @@ k_lusgs_blk(BlkArgs a)
                     if (fwd) M.rD[MR + it * 32 + lane] = hsc[it];  // the sweep forms dW*_q = rD_q x_q itself (lusgs.C:194-216)
                 }
             }
+            if ((d[BT_COL] >> (fwd ? 0 : 1)) & 1) {
+                // column mode: the previous item of this CTA is the neighbouring chunk of the same column; the rows of it this tile
+                // needs come out of its shared-memory vector as soon as its consumers are done — no L2 round trip on the chain
+                const int pbuf = (i - 1) % NBUF;
+                if (!mbWait(sm.done + pbuf, ((i - 1) / NBUF) & 1, a.err)) return;
+                const double(*xp)[XS] = sm.xs[pbuf];
+#pragma unroll
+                for (int it = 0; it < HIT; it++) {
+                    if (hq[it] < 0 && hq[it] != INT_MIN) {
+                        const int row = -hq[it] - 1;
+#pragma unroll
+                        for (int k = 0; k < 5; k++) xs[k][MR + it * 32 + lane] = xp[k][row];
+                        if (fwd) M.rD[MR + it * 32 + lane] = sm.meta[pbuf].rD[row];
+                    }
+                }
+            }
             __syncwarp();
             if (PROF && lane == 0) { const long long t2 = clock64(); a.prof[(size_t)b * 24 + 11] += t2 - hk; hk = t2; }
             if (PROF && tr && lane == 0) tr[2] = gtime();
-            if (lane == 0) mbArrive(sm.hfull + buf);
+            if (lane == 0) {
+                mbArrive(sm.hfull + buf);
+                if (i > 0) mbArrive(sm.mempty + (i - 1) % NBUF);   // this warp is done with the previous item's buffer, too
+            }
         }
         return;
     }
@@ -538,7 +569,7 @@ k_lusgs_blk(BlkArgs a)
 int ics_lusgs_blk(icsb200_ctx* c, double* x)
 {
     BlkArgs a{};
-    a.nTiles = c->nTiles; a.nSlices = c->nSlices; a.NP = c->NP;
+    a.nTiles = c->nTiles; a.nSlices = c->nSlices; a.NP = c->NP; a.nCols = c->nBlkCols; a.colStart = c->d_blkCol;
     a.tab = c->d_blkTab; a.idx = c->d_blkIdx; a.stage = c->d_blkStage; a.info = c->d_blkInfo;
     a.offd = c->d_offd; a.rD = c->d_rD; a.x = x; a.NPH = c->NPH;
     a.flag = c->d_blkFlag; a.ticket = c->d_blkFlag + 2 * c->nTiles; a.epoch = ++c->blkEpoch;
@@ -550,7 +581,7 @@ int ics_lusgs_blk(icsb200_ctx* c, double* x)
         CUDA_TRY(c, cudaFuncSetAttribute(k_lusgs_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attrSet = true;
     }
-    int grid = std::min(c->numSMs, std::max(1, c->nTiles));
+    int grid = std::min(c->numSMs, std::max(1, c->nBlkCols));
     {
         static const char* e3 = getenv("ICSB200_LUSGS_GRID");
         if (e3) grid = std::min(grid, std::max(1, atoi(e3)));

@@ -135,7 +135,7 @@ extern "C" int icsb200_destroy(icsb200_ctx* c)
                     c->d_bfGeo, c->d_bc, c->d_phiB, c->d_vic, c->d_sendBuf, c->d_recvBuf, c->d_fields, c->d_grad, c->d_rdt, c->d_co,
                     c->d_ddtCoeff, c->d_Wold, c->d_Wold2, c->d_Wprev, c->d_src, c->d_dW, c->d_faceFlux, c->d_bad, c->d_offd, c->d_diag,
                     c->d_rD, c->d_invD, c->d_kry, c->d_w, c->d_x, c->d_scal, c->d_partial, c->d_counter, c->d_barrier, c->d_stage, c->d_lusgsYZ, c->d_lusgsHint, c->d_sliceRange,
-                    c->d_faceRecon, c->d_gradE, c->d_visc, c->d_mrfFace, c->d_mrfOmega, c->d_transport, c->d_bfNbrPos, c->d_patchRot, c->d_bfAmiStart, c->d_amiAllSrc, c->d_amiAllW, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_blkTab, c->d_blkIdx, c->d_blkInfo, c->d_blkStage, c->d_blkFlag, c->d_blkProf, c->d_blkTrace, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
+                    c->d_faceRecon, c->d_gradE, c->d_visc, c->d_mrfFace, c->d_mrfOmega, c->d_transport, c->d_bfNbrPos, c->d_patchRot, c->d_bfAmiStart, c->d_amiAllSrc, c->d_amiAllW, c->d_rowLevF, c->d_rowLevR, c->d_tileNLevF, c->d_tileNLevR, c->d_tileDescF, c->d_tileDescR, c->d_blkTab, c->d_blkIdx, c->d_blkInfo, c->d_blkStage, c->d_blkFlag, c->d_blkCol, c->d_blkProf, c->d_blkTrace, c->d_hbD, c->d_hbPeer, c->d_hbInst, c->d_hbZone, c->d_hbZonePrm, c->d_hbInv, c->d_hbWork};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& pp : c->procs) if (pp.d_sendPos) cudaFree(pp.d_sendPos);
     for (auto& am : c->amis) { cudaFree(am.d_start); cudaFree(am.d_srcPos); cudaFree(am.d_w); }
@@ -355,6 +355,8 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
     // a whole tile with shared memory, synchronising with other CTAs only once per tile.  Otherwise fall back to the
     // level order (one 32-row slice per "tile").
     std::vector<int> tileOf;  // per cell
+    std::vector<int> tileCol; // block tiles: column of a tile (tiles of a column are consecutive, chunks ascending) or empty
+    bool colMode = false;
     int nTiles = 0;
     c->tileMode = false;
     bool blkWanted = false;
@@ -444,7 +446,28 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                     const double chain8 = steps(8) * (8 * 0.6 + 4.6), chain4 = steps(4) * (4 * 0.6 + 4.6);   // us per sweep
                     const double bytesUs = (double)N * 710.0 / 5.5e6;   // us per sweep at 5.5 TB/s
                     depth = (bytesUs < chain8 && chain4 < chain8) ? 4 : 8;
-                }
+                    // Chain-bound meshes: COLUMN mode — a CTA sweeps all chunks of a column back to back and hands each chunk's last
+                    // level to the next chunk in shared memory, so only the lateral dependencies (neighbour columns) cross L2.  The
+                    // chain is then sum over cross axes of bins x (K T + 4.6 us) + chunks x T with T = depth x 0.6 us.
+                    colMode = bytesUs < chain8;
+                    if (colMode) {
+                        auto colChain = [&](int dep) {
+                            double tsum = 0.0;
+                            int sm2 = umax[sweep], nth = 0;
+                            const double T = dep * 0.6;
+                            for (int d = 0; d < 3; d++) {
+                                if (d == sweep) continue;
+                                if (umax[d] + 1 < 4) { sm2 += umax[d]; continue; }
+                                const int b2 = nth++ == 0 ? bside : bside2;
+                                tsum += (umax[d] / b2) * (((b2 - 1 + dep - 1) / dep + 1) * T + 4.6);
+                                sm2 += b2 - 1;
+                            }
+                            return tsum + (sm2 / dep + 1) * T;
+                        };
+                        depth = colChain(4) < colChain(8) ? 4 : 8;
+                    }
+                } else if (nCross == 1) colMode = true;
+                if (const char* e = getenv("ICSB200_LUSGS_COLMODE")) colMode = atoi(e) != 0;
                 depth = envInt("ICSB200_LUSGS_DEPTH", depth);
                 int bs[3] = {1, 1, 1}, nbin[3] = {1, 1, 1}, K[3] = {0, 0, 0};
                 {
@@ -494,7 +517,23 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                         }
                         std::vector<int> order;
                         for (long long t = 0; t < nbAll; t++) if (cntT[t] > 0) order.push_back((int)t);
-                        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tlT[x] != tlT[y] ? tlT[x] < tlT[y] : chT[x] > chT[y]; });
+                        // column of a tile: its key without the chunk; column mode orders the tiles by (column rank, chunk), columns
+                        // ranked by their K-weighted bin sum (every neighbour column a column waits for has a smaller one)
+                        std::vector<long long> colT(nbAll, 0);
+                        {
+                            long long mulAll = 1;
+                            for (int d = 0; d < 3; d++) if (d != sweep && !(bs[d] == 1 && nbin[d] == 1)) mulAll *= nbin[d];
+                            for (long long t = 0; t < nbAll; t++) colT[t] = (t % nb3) % mulAll + (t / nb3) * mulAll;
+                        }
+                        if (colMode)
+                            std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+                                const int ax = tlT[x] - chT[x], ay = tlT[y] - chT[y];
+                                if (ax != ay) return ax < ay;
+                                if (colT[x] != colT[y]) return colT[x] < colT[y];
+                                return chT[x] < chT[y];
+                            });
+                        else
+                            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tlT[x] != tlT[y] ? tlT[x] < tlT[y] : chT[x] > chT[y]; });
                         int maxRows = 0, maxTL = 0;
                         for (int t : order) { maxRows = std::max(maxRows, cntT[t]); maxTL = std::max(maxTL, tlT[t]); }
                         if (maxRows <= tileRowCap) {
@@ -503,6 +542,14 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                             tileOf.resize(N);
                             for (int i = 0; i < N; i++) tileOf[i] = dense[key[i]];
                             nTiles = (int)order.size();
+                            if (colMode) {
+                                tileCol.resize(nTiles);
+                                int nc = -1;
+                                for (int k = 0; k < nTiles; k++) {
+                                    if (k == 0 || colT[order[k]] != colT[order[k - 1]]) nc++;
+                                    tileCol[k] = nc;
+                                }
+                            }
                             c->tileMode = true;
                             blkWanted = true;
                             c->nTileLevels = maxTL + 1;
@@ -966,7 +1013,15 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                 tmp[sw].erase(std::unique(tmp[sw].begin(), tmp[sw].end()), tmp[sw].end());
                 if ((int)tmp[sw].size() > ICS_BLK_MH - 1) ok = false;  // the last slot of the tile's vector is the zero the absent neighbours point to
                 tls[sw].clear();
-                for (int q : tmp[sw]) tls[sw].push_back(sliceTile2[q >> 5] + (sw == 0 ? 0 : nT));  // flag index: forward t, reverse nT + t
+                // column mode: the tile swept just before this one by the same CTA (previous chunk of the column in the forward
+                // sweep, next chunk in the reverse sweep) hands its values over in shared memory — no flag to wait for
+                const int pred = sw == 0 ? t - 1 : t + 1;
+                const bool hasPred = !tileCol.empty() && pred >= 0 && pred < nT && tileCol[pred] == tileCol[t];
+                for (int q : tmp[sw]) {
+                    const int tq = sliceTile2[q >> 5];
+                    if (hasPred && tq == pred) continue;
+                    tls[sw].push_back(tq + (sw == 0 ? 0 : nT));  // flag index: forward t, reverse nT + t
+                }
                 std::sort(tls[sw].begin(), tls[sw].end());
                 tls[sw].erase(std::unique(tls[sw].begin(), tls[sw].end()), tls[sw].end());
                 if (sw == 1) tls[sw].push_back(t);  // the reverse sweep starts from the tile's own forward values
@@ -1010,7 +1065,16 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             for (int L = 0; L < nLev; L++) if (lv[L + 1] - lv[L] != regW) regW = 0;
             if (regW < 1 || regW > 32 || 32 % regW != 0 || lv.back() != t1 - t0 - ((t1 - t0) - lv.back())) regW = 0;
             if (regW && lv.back() != nLev * regW) regW = 0;
-            d[0] = t0; d[1] = t1 - t0; d[2] = regW ? (regW | (unstaged[0] ? 0 : 1 << 8) | (unstaged[1] ? 0 : 1 << 9)) : 0; d[3] = nLev;
+            (void)regW;
+            // column mode: halo entries that lie in the tile swept just before this one become -(row of that tile) - 1
+            int colBits = 0;
+            for (int sw = 0; sw < 2; sw++) {
+                const int pred = sw == 0 ? t - 1 : t + 1;
+                if (tileCol.empty() || pred < 0 || pred >= nT || tileCol[pred] != tileCol[t]) continue;
+                colBits |= 1 << sw;
+                for (int& q : tmp[sw]) if (q >= tileStart[pred] && q < tileStart[pred + 1]) q = -(q - tileStart[pred]) - 1;
+            }
+            d[0] = t0; d[1] = t1 - t0; d[2] = colBits; d[3] = nLev;
             d[4] = section(lv);
             d[5] = section(tmp[0]); d[6] = (int)tmp[0].size();
             d[7] = section(tmp[1]); d[8] = (int)tmp[1].size();
@@ -1034,6 +1098,14 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             r |= devUpload(c, &c->d_blkIdx, idx);
             r |= devUpload(c, &c->d_blkInfo, info);
             r |= devUpload(c, &c->d_blkStage, stage);
+            {
+                // columns = units of work a CTA draws: [first tile, ...) per column; without column mode every tile is its own column
+                std::vector<int> colStart;
+                for (int t = 0; t < nT; t++) if (tileCol.empty() || t == 0 || tileCol[t] != tileCol[t - 1]) colStart.push_back(t);
+                c->nBlkCols = (int)colStart.size();
+                colStart.push_back(nT);
+                r |= devUpload(c, &c->d_blkCol, colStart);
+            }
             r |= devAlloc(c, &c->d_blkFlag, (size_t)2 * nT + 2);   // + the two ticket counters (lusgs_blk.cu)
             if (!r) CUDA_TRY(c, cudaMemset(c->d_blkFlag, 0, sizeof(int) * (2 * nT + 2)));
             c->blkEpoch = 0;

@@ -1862,7 +1862,6 @@ int ics_gmres(icsb200_ctx* c, const icsb200_solver_controls* ctl, icsb200_residu
         if (nI > 1) { c->hbSInit = sInit; c->hbVInit = vInit; c->hbSFinal = sFinal; c->hbVFinal = vFinal; }
     };
     publish();
-    if (ctl->preconditioner == ICSB200_PRECOND_JACOBI) c->invDValid = c->invDValid && true;
     bool stop = false;
     do {
       if (smooth) {

@@ -368,11 +368,22 @@ def test_iterate_host_round_trip(gpu_context):
                                        ("blk", lambda: cases.onera_box(33)), ("blk", lambda: cases.bump(24, 20)),
                                        ("blk", lambda: cases.bump(60, 50)),
                                        ("blk", lambda: cases.periodic_box(9, "ROE", "vanLeer", seed=61, mu=0.05)),
+                                       ("blk-tilelevels", lambda: cases.onera_box(20)), ("blk-tilelevels", lambda: cases.bump(60, 50)),
+                                       ("blk-depth4", lambda: cases.onera_box(33)), ("blk-depth8", lambda: cases.onera_box(33)),
                                        ("level", lambda: cases.onera_box(13))])
 def test_lusgs_tile_mode_is_bit_identical(gpu_context, monkeypatch, mode, make):
     """Every LU-SGS schedule must reproduce the sequential sweeps of the oracle (lusgs.C:220-382) bit for bit:
     ICSB200_LUSGS_MODE=blk (block tiles swept in place by k_lusgs_blk — what `auto`, the default, picks on hex-like meshes),
     level (the level pipeline), tile / tile64 (the older blocked wavefront schedules)."""
+    # block tiles: "blk" lets the set-up choose (column mode on these small, chain-bound meshes: a CTA sweeps a column's chunks
+    # back to back and hands levels over in shared memory); "-tilelevels" forces the tile-level order with a flag per tile,
+    # "-depth4/8" the two tile depths
+    if mode.startswith("blk-"):
+        if mode == "blk-tilelevels":
+            monkeypatch.setenv("ICSB200_LUSGS_COLMODE", "0")
+        else:
+            monkeypatch.setenv("ICSB200_LUSGS_DEPTH", mode[-1])
+        mode = "blk"
     monkeypatch.setenv("ICSB200_LUSGS_MODE", mode)
     case = make()
     g = case.apply(gpu_context())
