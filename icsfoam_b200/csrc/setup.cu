@@ -421,8 +421,9 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                 for (int d = 0; d < 3; d++) if (umax[d] + 1 >= 4 && (sweep < 0 || umax[d] > umax[sweep])) sweep = d;
                 auto envInt = [](const char* name, int dflt) { const char* e = getenv(name); return e ? std::max(1, atoi(e)) : dflt; };
                 const int nCross = active > 0 ? active - 1 : 0;
-                // 3-D: 8 x 4 columns (32 rows = one warp per block-row component and level), 8 levels deep; 2-D: 16 wide, 16 deep
-                int bside = nCross == 2 ? 8 : (nCross == 1 ? 16 : 1);
+                // 3-D: 8 x 4 columns (32 rows = one warp per block-row component and level), 8 or 4 levels deep; 2-D: 32 wide, 8 deep
+                // (profiles/r02_lusgs_tileshape_sweep.log, r02_lusgs_colshape_sweep.log)
+                int bside = nCross == 2 ? 8 : (nCross == 1 ? 32 : 1);
                 bside = envInt("ICSB200_LUSGS_BSIDE", bside);
                 int bside2 = nCross == 2 ? 4 : bside;
                 bside2 = envInt("ICSB200_LUSGS_BSIDE2", bside2);
@@ -430,7 +431,11 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                 // 10.3 ms against 12.8 with 4); when it is bound by the chain of tile steps, the depth with the shorter chain wins
                 // (172^3: 193 steps of 4 levels, 2.68 ms, against 149 steps of 8 levels, 2.82 ms).  Model: step = depth x 0.6 us +
                 // 4.6 us (lusgs_blk_trace.py medians), bytes at 5.5 TB/s.
-                int depth = nCross == 2 ? 8 : (nCross == 1 ? 16 : 32);
+                int depth = nCross == 2 ? 8 : (nCross == 1 ? 8 : 32);
+                // COLUMN mode (default wherever there are columns): a CTA sweeps all chunks of a column back to back and hands each
+                // chunk's last level to the next chunk in shared memory, so only the lateral dependencies (neighbour columns) cross
+                // L2: 172^3 2.73 -> 1.95 ms, 344^3 10.35 -> 9.70 ms, bump-4M 7.2 -> 4.9 ms.
+                colMode = nCross >= 1;
                 if (nCross == 2) {
                     auto steps = [&](int dep) {
                         int n = 0, sm2 = umax[sweep], nth = 0;
@@ -446,11 +451,9 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                     const double chain8 = steps(8) * (8 * 0.6 + 4.6), chain4 = steps(4) * (4 * 0.6 + 4.6);   // us per sweep
                     const double bytesUs = (double)N * 710.0 / 5.5e6;   // us per sweep at 5.5 TB/s
                     depth = (bytesUs < chain8 && chain4 < chain8) ? 4 : 8;
-                    // Chain-bound meshes: COLUMN mode — a CTA sweeps all chunks of a column back to back and hands each chunk's last
-                    // level to the next chunk in shared memory, so only the lateral dependencies (neighbour columns) cross L2.  The
-                    // chain is then sum over cross axes of bins x (K T + 4.6 us) + chunks x T with T = depth x 0.6 us.
-                    colMode = bytesUs < chain8;
-                    if (colMode) {
+                    // chain-bound meshes in column mode: the chain is the sum over the cross axes of bins x (K T + 4.6 us) + chunks x T
+                    // with T = depth x 0.6 us
+                    if (bytesUs < chain8) {
                         auto colChain = [&](int dep) {
                             double tsum = 0.0;
                             int sm2 = umax[sweep], nth = 0;
@@ -466,7 +469,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                         };
                         depth = colChain(4) < colChain(8) ? 4 : 8;
                     }
-                } else if (nCross == 1) colMode = true;
+                }
                 if (const char* e = getenv("ICSB200_LUSGS_COLMODE")) colMode = atoi(e) != 0;
                 depth = envInt("ICSB200_LUSGS_DEPTH", depth);
                 int bs[3] = {1, 1, 1}, nbin[3] = {1, 1, 1}, K[3] = {0, 0, 0};
