@@ -383,12 +383,50 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             std::vector<int> u[3];
             int umax[3] = {0, 0, 0};
             for (int d = 0; d < 3; d++) u[d].assign(N, 0);
+            // Block tiles: every face constrains all three coordinates (weight 1 along its own axis, 0 along the others), forwards
+            // (u(neighbour) >= u(owner) + w) and backwards (u(owner) >= u(neighbour) - w), relaxed until nothing moves: on a
+            // logically structured mesh that is the exact index potential (i,j,k) up to a shift, whatever the shape of the
+            // sub-domain.  A forward longest path alone starts every row of a staircase-shaped partition cut (x-slabs of a curved
+            // mesh) at zero, which put several cells on one coordinate and made a y-face step back in x: three of the eight
+            // bump-4M slabs fell back to the level pipeline.  The last pass is a forward one, so every coordinate is
+            // non-decreasing across every face even where the mesh is not structured (the tile graph is checked anyway).
+            const bool legacyU = !wantBlk;   // the older tile modes keep their coordinates
+            std::vector<unsigned char> axisOf(F);
             for (int f = 0; f < F; f++) {
                 double ax = std::fabs(Sf[3 * (size_t)f]), ay = std::fabs(Sf[3 * (size_t)f + 1]), az = std::fabs(Sf[3 * (size_t)f + 2]);
-                int d = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
-                int v = u[d][owner[f]] + 1;
-                if (v > u[d][neighbour[f]]) { u[d][neighbour[f]] = v; umax[d] = std::max(umax[d], v); }
+                axisOf[f] = (unsigned char)((ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2));
             }
+            auto forwardPass = [&]() {
+                bool changed = false;
+                for (int f = 0; f < F; f++) {
+                    const int d = axisOf[f], o = owner[f], n2 = neighbour[f];
+                    for (int a2 = 0; a2 < 3; a2++) {
+                        if (legacyU && a2 != d) continue;
+                        const int v = u[a2][o] + (a2 == d ? 1 : 0);
+                        if (v > u[a2][n2]) { u[a2][n2] = v; changed = true; }
+                    }
+                }
+                return changed;
+            };
+            auto backwardPass = [&]() {
+                bool changed = false;
+                for (int f = F - 1; f >= 0; f--) {
+                    const int d = axisOf[f], o = owner[f], n2 = neighbour[f];
+                    for (int a2 = 0; a2 < 3; a2++) {
+                        const int v = u[a2][n2] - (a2 == d ? 1 : 0);
+                        if (v > u[a2][o]) { u[a2][o] = v; changed = true; }
+                    }
+                }
+                return changed;
+            };
+            forwardPass();
+            if (!legacyU)
+                for (int it = 0; it < 4; it++) {
+                    if (!backwardPass()) break;
+                    if (!forwardPass()) break;
+                }
+            for (int d = 0; d < 3; d++)
+                for (int i = 0; i < N; i++) umax[d] = std::max(umax[d], u[d][i]);
             int active = 0;
             for (int d = 0; d < 3; d++) if (umax[d] + 1 >= 4) active++;
             int side = active > 0 ? std::max(2, (int)std::lround(std::pow(tileTarget, 1.0 / active))) : (int)tileTarget;
@@ -506,7 +544,14 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                         tlOf[i] = tl2 + ch;
                     }
                     for (int f = 0; f < F && ok; f++)
-                        if (key[owner[f]] != key[neighbour[f]] && tlOf[owner[f]] >= tlOf[neighbour[f]]) ok = false;
+                        if (key[owner[f]] != key[neighbour[f]] && tlOf[owner[f]] >= tlOf[neighbour[f]]) {
+                            ok = false;
+                            if (getenv("ICSB200_LUSGS_DEBUG")) {
+                                const int o = owner[f], n2 = neighbour[f];
+                                fprintf(stderr, "icsb200: tile graph not ranked at face %d: owner %d u=(%d,%d,%d) TL %d -> neighbour %d u=(%d,%d,%d) TL %d (sweep axis %d, blocks %d %d %d, depth %d)\n",
+                                        f, o, u[0][o], u[1][o], u[2][o], tlOf[o], n2, u[0][n2], u[1][n2], u[2][n2], tlOf[n2], sweep, bs[0], bs[1], bs[2], depth);
+                            }
+                        }
                     if (ok) {
                         // tile order: by tile level; inside a level by descending chunk = ascending column index sum, so that every
                         // tile a tile waits for sits at the same or an earlier relative place of the previous level — with
@@ -539,6 +584,7 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                             std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tlT[x] != tlT[y] ? tlT[x] < tlT[y] : chT[x] > chT[y]; });
                         int maxRows = 0, maxTL = 0;
                         for (int t : order) { maxRows = std::max(maxRows, cntT[t]); maxTL = std::max(maxTL, tlT[t]); }
+                        if (maxRows > tileRowCap && getenv("ICSB200_LUSGS_DEBUG")) fprintf(stderr, "icsb200: a tile has %d rows (cap %d)\n", maxRows, tileRowCap);
                         if (maxRows <= tileRowCap) {
                             std::vector<int> dense(nbAll, -1);
                             for (size_t k = 0; k < order.size(); k++) dense[order[k]] = (int)k;

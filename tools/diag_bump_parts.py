@@ -6,9 +6,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from icsfoam_b200 import cases, capi
 from icsfoam_b200.context import Context
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+only = [int(x) for x in sys.argv[2:]]
+os.environ["ICSB200_LUSGS_DEBUG"] = "1"
 case = cases.bump(1280, 1040)
 part, meshes = case.partition(n, "x")
 for r, m in enumerate(meshes):
+    if only and r not in only:
+        continue
     for p in m.patches:
         if p["kind"] == capi.PROCESSOR:
             p["kind"] = capi.PATCH
