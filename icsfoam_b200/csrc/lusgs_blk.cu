@@ -149,12 +149,6 @@ __device__ __forceinline__ long long gtime()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ int ldRelaxed(const int* p)
-{
-    int v;
-    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void stRelease(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // what a consumer thread needs for its (row, component) of a level besides the sweep values of the neighbours
@@ -171,7 +165,7 @@ k_lusgs_blk(BlkArgs a)
     extern __shared__ __align__(128) unsigned char blkRaw[];
     BlkSmem& sm = *reinterpret_cast<BlkSmem*>(blkRaw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int G = gridDim.x, b = blockIdx.x;
+    const int b = blockIdx.x;
     if (tid == 0) {
         for (int s = 0; s < NST; s++) { mbInit(sm.full + s, 1); mbInit(sm.empty + s, NCW); }
         for (int s = 0; s < NBUF; s++) { mbInit(sm.idfull + s, 1); mbInit(sm.mfull + s, 1); mbInit(sm.mempty + s, 2); mbInit(sm.hfull + s, 1); mbInit(sm.done + s, NCW / 2); }

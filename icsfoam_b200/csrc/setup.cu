@@ -1108,13 +1108,6 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
             std::vector<int> lv(tileFLev.begin() + tileFPtr[t], tileFLev.begin() + tileFPtr[t + 1]);
             std::vector<int> so(c->h_sliceOff.begin() + t0 / 32, c->h_sliceOff.begin() + t0 / 32 + nSl), rl(sRevLo.begin() + t0 / 32, sRevLo.begin() + t0 / 32 + nSl);
             int d[16] = {0};
-            // regular tile: every level has the same width w (a divisor of 32, all rows real) — the kernel then derives rows, slices
-            // and stages from the level number alone; bit 8 / 9: the forward / reverse sweep may use that path (nothing unstaged)
-            int regW = lv[1] - lv[0];
-            for (int L = 0; L < nLev; L++) if (lv[L + 1] - lv[L] != regW) regW = 0;
-            if (regW < 1 || regW > 32 || 32 % regW != 0 || lv.back() != t1 - t0 - ((t1 - t0) - lv.back())) regW = 0;
-            if (regW && lv.back() != nLev * regW) regW = 0;
-            (void)regW;
             // column mode: halo entries that lie in the tile swept just before this one become -(row of that tile) - 1
             int colBits = 0;
             for (int sw = 0; sw < 2; sw++) {

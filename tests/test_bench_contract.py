@@ -25,3 +25,25 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_both_arms_share_one_config_object_and_the_cpu_arm_uses_every_core():
+    """The driver compares the `config` of the GPU line with that of the reference line: both come from Workload.config; the
+    sample the CPU arm really ran is stated in cpu_baseline.sample / run.sample_cells; partitions = all host cores."""
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.factor3(16) == (4, 2, 2) and bench.factor3(13) == (13, 1, 1) and bench.factor3(64) == (4, 4, 4) and bench.factor3(48) == (4, 4, 3)
+    assert bench.host_threads() >= 1
+    args = argparse.Namespace(workload="onera344", n=344, n_cpu=12, bump_nx=1280, bump_ny=1040, bump_nx_cpu=40, bump_ny_cpu=30)
+    want = bench.Workload(args).config
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-cells-per-dim", "12"],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["config"] == want and "344^3" in d["config"]["workload"] and d["config"]["cells"] == 344 ** 3
+    assert d["run"]["sample_cells"] == 12 ** 3 and "12^3" in d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["cores"] == bench.host_threads()
+    bump = bench.Workload(argparse.Namespace(workload="bump4m", n=344, n_cpu=12, bump_nx=1280, bump_ny=1040, bump_nx_cpu=40, bump_ny_cpu=30))
+    assert bump.config["cells"] == 3 * 1280 * 1040 and "Minmod" in bump.config["workload"]
