@@ -1,9 +1,10 @@
 // common.cuh — context, device layout and launch helpers of libicsb200 (sm_100a).
 //
 // Device layout (private; see DESIGN.md "Data layout in HBM"):
-//  * cells are renumbered into POSITIONS: sorted by LU-SGS forward level (longest path in the owner<neighbour
-//    DAG, lusgs.C:130-159), ties by cell id, each level padded to a multiple of 32 so a warp never straddles
-//    a level.  All cell vectors are SoA of length NPH = NP (+ halo slots + boundary-face slots).
+//  * cells are renumbered into POSITIONS in LU-SGS sweep order (setup.cu): on hex-like meshes by column, tile (chunk of
+//    hyperplanes of a column) and forward level inside the tile (lusgs_blk.cu), otherwise by forward level (longest path in
+//    the owner<neighbour DAG, lusgs.C:130-159), ties by cell id; tiles / levels are padded to a multiple of 32 so a warp never
+//    straddles one.  All cell vectors are SoA of length NPH = NP (+ halo slots + boundary-face slots).
 //  * the coupled matrix (coupledMatrix.H: 9 LDU sub-blocks) is stored row-wise as sliced-ELL with one 5x5
 //    block per face of the row (SELL-32, entry-major SoA): value (e, k, lane) at ((sliceOff[s]+j)*25+k)*32+lane.
 //    Row entries are the faces of the cell in ascending reference face id = [faces where the cell is the
