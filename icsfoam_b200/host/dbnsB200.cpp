@@ -237,6 +237,14 @@ int main(int argc, char** argv)
             throw FatalError("thermodynamics: only `Tref 0` (stated explicitly; OpenFOAM defaults to Tstd) with Hsref 0 is supported");
         // ---- solver controls (fvSolution/flowSolver): read before -parseOnly returns so that dictionary errors surface without a GPU
         const icsb200_solver_controls ctl = coupledMatrix::controlsFromDict(fvSolution.subDict("flowSolver"));
+        // ---- time scheme and run controls this driver does not implement are refused, not silently replaced (also before -parseOnly returns)
+        const std::vector<std::string>& ddt = fvSchemes.subDict("ddtSchemes").lookup("default");
+        if (ddt.at(0) != "dualTime") throw FatalError("ddtSchemes default must be 'dualTime rPseudoDeltaT <inner>' (dualTimeDdtScheme.H:103)");
+        const std::string inner = ddt.back();
+        const bool steadyState = inner == "steadyState";
+        if (!steadyState && inner != "Euler" && inner != "backward") throw FatalError("inner ddt scheme '" + inner + "' is not supported (steadyState Euler backward)");
+        if (fvSolution.subDict("pseudoTime").getSwitch("resetPseudo", false)) throw FatalError("pseudoTime/resetPseudo true (beginTimeStep.H) is not supported");
+        if (controlDict.getSwitch("adjustTimeStep", false)) throw FatalError("controlDict adjustTimeStep yes is not supported");
         if (parseOnly) {
             double pmin = 1e300, pmax = -1e300;
             for (double v : p) { pmin = std::min(pmin, v); pmax = std::max(pmax, v); }
@@ -265,14 +273,7 @@ int main(int argc, char** argv)
         const dictionary& cfs = fvSchemes.subDict("convectiveFluxScheme");
         sch.low_mach_ausm = cfs.getSwitch("lowMachAusm", true);
         sch.entropy_fix_coeff = cfs.getOrDefault<double>("entropyFixCoeff", 0.05);
-        const std::vector<std::string>& ddt = fvSchemes.subDict("ddtSchemes").lookup("default");
-        if (ddt.at(0) != "dualTime") throw FatalError("ddtSchemes default must be 'dualTime rPseudoDeltaT <inner>' (dualTimeDdtScheme.H:103)");
-        const std::string inner = ddt.back();
-        const bool steadyState = inner == "steadyState";
-        if (!steadyState && inner != "Euler" && inner != "backward") throw FatalError("inner ddt scheme '" + inner + "' is not supported (steadyState Euler backward)");
         sch.ddt_scheme = steadyState ? ICSB200_DDT_STEADY : inner == "Euler" ? ICSB200_DDT_EULER : ICSB200_DDT_BACKWARD;
-        if (pseudo.getSwitch("resetPseudo", false)) throw FatalError("pseudoTime/resetPseudo true (beginTimeStep.H) is not supported");
-        if (controlDict.getSwitch("adjustTimeStep", false)) throw FatalError("controlDict adjustTimeStep yes is not supported");
         sch.delta_t = controlDict.get<double>("deltaT");
         sch.local_timestepping = pseudo.getSwitch("localTimestepping", true);
         sch.local_timestepping_bounding = pseudo.getSwitch("localTimesteppingBounding", true);

@@ -78,3 +78,48 @@ def test_driver_refuses_an_implicit_tref_and_reads_the_smooth_solver(tmp_path):
     sol.write_text(stxt[:m.start()] + new % "GaussSeidel" + stxt[i:])
     r = run(str(case), "-parseOnly")
     assert r.returncode != 0 and "Unknown smoother type GaussSeidel" in r.stderr, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not (os.path.isdir(REF) and os.path.exists(DRIVER)), reason="reference tutorial or driver binary not present")
+def test_driver_refuses_what_it_does_not_implement(tmp_path):
+    """Settings the driver does not implement are FatalErrors, not silent substitutions: an inner ddt scheme other than
+    steadyState / Euler / backward, pseudoTime/resetPseudo, adjustTimeStep; a freestreamPressure patch takes its velocity from the
+    freestreamValue of the U patch field on the same patch (macros resolved), and needs that patch field to be `freestream`."""
+    case = tmp_path / "vki"
+    shutil.copytree(REF, case)
+
+    def edit(rel, old, new, count=1):
+        path = case / rel
+        txt = path.read_text()
+        assert len(re.findall(old, txt)) >= 1, (rel, old)
+        path.write_text(re.sub(old, new, txt, count=count))
+        return txt
+
+    keep = edit("system/fvSchemes", r"default dualTime rPseudoDeltaT steadyState;", "default dualTime rPseudoDeltaT CrankNicolson 0.9;")
+    r = run(str(case), "-parseOnly")
+    assert r.returncode != 0 and "inner ddt scheme" in r.stderr and "not supported" in r.stderr, r.stdout + r.stderr
+    (case / "system" / "fvSchemes").write_text(keep)
+
+    keep = edit("system/fvSolution", r"nPseudoCorr\s+1;", "nPseudoCorr  1;\n    resetPseudo true;")
+    r = run(str(case), "-parseOnly")
+    assert r.returncode != 0 and "resetPseudo" in r.stderr, r.stdout + r.stderr
+    (case / "system" / "fvSolution").write_text(keep)
+
+    keep = edit("system/controlDict", r"adjustTimeStep\s+no;", "adjustTimeStep  yes;")
+    r = run(str(case), "-parseOnly")
+    assert r.returncode != 0 and "adjustTimeStep" in r.stderr, r.stdout + r.stderr
+    (case / "system" / "controlDict").write_text(keep)
+
+    # freestreamPressure on the outlet while U stays pressureInletOutletVelocity: refused
+    keep_p = edit("0/p", r"outlet\s*\{\s*type\s+fixedValue;\s*value\s+uniform 82000;", "outlet\n    {\n        type freestreamPressure;\n        freestreamValue uniform 82000;")
+    r = run(str(case), "-parseOnly")
+    assert r.returncode != 0 and "freestreamPressure needs a freestream U patch field" in r.stderr, r.stdout + r.stderr
+    # ... with a freestream U patch whose freestreamValue is a macro of the file: accepted
+    edit("0/U", r"outlet\s*\{\s*type\s+pressureInletOutletVelocity;\s*tangentialVelocity\s+uniform \(0 0 0\);", "outlet\n    {\n         type freestream;\n         freestreamValue $internalField;")
+    r = run(str(case), "-parseOnly")
+    assert r.returncode == 0 and "parse ok" in r.stdout, r.stdout + r.stderr
+    # ... supersonic true: refused
+    (case / "0" / "p").write_text((case / "0" / "p").read_text().replace("freestreamValue uniform 82000;", "freestreamValue uniform 82000;\n        supersonic true;"))
+    r = run(str(case), "-parseOnly")
+    assert r.returncode != 0 and "supersonic" in r.stderr, r.stdout + r.stderr
+    (case / "0" / "p").write_text(keep_p)
