@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — Mcell-iterations/s of the ICSFoam implicit pseudo-time iteration on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload onera344|bump4m|forwardstep|vki]
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload onera344|bump4m|forwardstep|vki|vki-hb]
 
 A "step" is one outer pseudo-time iteration of dbnsFoam (outerLoop.H:51-99 + updateFields.H): gradients, flux,
 residual, local pseudo time step, Jacobian assembly, GMRES(m)/LU-SGS solve, field update.
@@ -9,7 +9,7 @@ Default workload (the configuration BASELINE.json's metric is quoted on): C4, th
 mesh of SURVEY.md §8d (the shipped OneraM6 mesh is incomplete in the reference checkout), HLLC + vanLeer, steady, Co=100,
 GMRES m=5 maxIter 10 relTol 0.1 with LU-SGS, at 344^3 = 40.7 M cells (~100 GB of HBM; --cells-per-dim to change).
 Other named meshes (`--workload`): bump4m = C3 circularArcBump refined to 3 x 1280 x 1040 cells (HLLC, Minmod, Co 200,
-m=5), forwardstep = C2 and vki = C5 (i) on the reference's own shipped meshes.
+m=5), forwardstep = C2, vki = C5 (i) and vki-hb = C5 (ii, Harmonic Balance with 3 time instances) on the reference's own shipped meshes.
 Prints ONE JSON line.  `value` = device-resident throughput (inputs in HBM), `e2e` = the same iteration through
 icsb200_iterate_host with pinned host buffers (p,U,T in and out every step).  `--impl reference` times the CPU
 restatement of the same path (the reference itself needs OpenFOAM v2112, absent here) on all host cores on a bounded
@@ -124,16 +124,19 @@ class Workload:
             self.n_total = 3 * args.bump_nx * args.bump_ny
             self.label = (f"circularArcBump transonic 3x{args.bump_nx}x{args.bump_ny} = {self.n_total} cells (C3, blockMesh-refined 2-D), "
                           f"HLLC Minmod steady Co=200, GMRES m=5 maxIter 10 relTol 1e-2, LU-SGS")
-        elif w in ("forwardstep", "vki"):
-            name = {"forwardstep": "forwardStep", "vki": "VKI-LS89"}[w]
+        elif w in ("forwardstep", "vki", "vki-hb"):
+            name = {"forwardstep": "forwardStep", "vki": "VKI-LS89", "vki-hb": "VKI-LS89"}[w]
             d = cases.tutorial_dir(name)
             if d is None:
                 raise SystemExit(f"workload {w}: tutorial {name} not found ($ICSFOAM_REF, /root/reference or cases_local/)")
             self.poly = os.path.join(d, "constant", "polyMesh")
-            self._whole = cases.forward_step(self.poly) if w == "forwardstep" else cases.vki_ls89(self.poly)
-            self.n_total = self._whole.mesh.n_cells
+            self._whole = (cases.forward_step(self.poly) if w == "forwardstep" else cases.vki_ls89(self.poly) if w == "vki"
+                           else cases.vki_hb(self.poly, 3))
+            self.n_total = self._whole.mesh.n_cells   # Harmonic Balance: the coupled cells of all time instances
             self.label = {"forwardstep": f"forwardStep Mach 3 shipped polyMesh = {self.n_total} cells (C2), HLLC Minmod, dual time (backward), GMRES m=8 maxIter 20 relTol 1e-4, LU-SGS",
-                          "vki": f"VKI-LS89 shipped polyMesh = {self.n_total} cells (C5 i, cyclic pair, laminar viscous), ROE vanLeer steady Co=10, GMRES m=8 maxIter 10 relTol 1e-3, LU-SGS"}[w]
+                          "vki": f"VKI-LS89 shipped polyMesh = {self.n_total} cells (C5 i, cyclic pair, laminar viscous), ROE vanLeer steady Co=10, GMRES m=8 maxIter 10 relTol 1e-3, LU-SGS",
+                          "vki-hb": f"VKI-LS89 Harmonic Balance, 3 time instances x 28059 cells = {self.n_total} coupled cells (C5 ii, dbnsFullyImplicitHBFoam; inlet total pressure "
+                                    f"oscillating at 2 kHz), ROE vanLeer Co=10, GMRES m=8 maxIter 10 relTol 1e-3, LU-SGS"}[w]
         else:
             raise SystemExit(f"unknown workload {w}")
         small = self.n_total * 2600 < 4 * 126e6
@@ -160,6 +163,8 @@ class Workload:
         case = self._whole_case()
         if world == 1:
             return case, None, None
+        if a.workload == "vki-hb":   # every rank holds all time instances of its own partition (HB instants are not sharded)
+            return case.partition(world, "x")[rank], None, None
         part, meshes = case.partition(world, "x", only=rank)
         return case, meshes[rank], meshes[rank].cell_global
 
@@ -170,6 +175,9 @@ class Workload:
             parts = [(c.onera_box(a.n_cpu, parts=px, rank=r), None, None) for r in range(threads)] if threads > 1 else [(c.onera_box(a.n_cpu), None, None)]
             return parts, a.n_cpu ** 3, f"onera-box {a.n_cpu}^3 ({a.n_cpu**3} cells) in {px[0]}x{px[1]}x{px[2]} blocks"
         case = self._whole_case(sample=True)
+        if a.workload == "vki-hb":
+            threads = max(1, min(threads, 8))
+            return case.partition(threads, "x"), case.mesh.n_cells, f"{case.name} {case.mesh.n_cells} coupled cells in {threads} x-slabs (all instances per slab)"
         threads = max(1, min(threads, case.mesh.n_cells // 2000))
         if threads == 1:
             return [(case, None, None)], case.mesh.n_cells, f"{case.name} {case.mesh.n_cells} cells, 1 partition"
@@ -205,6 +213,12 @@ class CpuRun:
         from oracle.pyoracle import Oracle
         parts, self.n_cells, self.sample = wl.cpu(threads)
         self.threads = len(parts)
+        self.hb = None
+        if wl.args.workload == "vki-hb":      # the reference-structured HB oracle: nO contexts per rank + the global (2 nO, nO) system
+            from oracle.pyoracle import HBWorld
+            self.controls = parts[0].controls
+            self.hb = HBWorld(parts)
+            return
         self.controls = parts[0][0].controls
         if self.threads > 1:
             self.world = apply_to_world(parts)
@@ -213,6 +227,10 @@ class CpuRun:
 
     def iterate(self, iters):
         t0 = time.perf_counter()
+        if self.hb is not None:
+            n_it = self.hb.iterate(self.controls, iters)[0]["n_iterations"]
+            dt = time.perf_counter() - t0
+            return self.n_cells * iters / dt / 1e6, dt, n_it
         if self.threads > 1:
             res = self.world.iterate(self.controls, iters)
         else:
@@ -305,7 +323,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--workload", default=os.environ.get("ICSB200_BENCH_WORKLOAD", "onera344"), choices=["onera344", "bump4m", "forwardstep", "vki"])
+    ap.add_argument("--workload", default=os.environ.get("ICSB200_BENCH_WORKLOAD", "onera344"), choices=["onera344", "bump4m", "forwardstep", "vki", "vki-hb"])
     ap.add_argument("--cells-per-dim", "--n", dest="n", type=int, default=int(os.environ.get("ICSB200_BENCH_N", "344")),
                     help="cells per direction of the 3-D mesh (use the long form under torchrun)")
     ap.add_argument("--cpu-cells-per-dim", "--n-cpu", dest="n_cpu", type=int, default=128, help="cells per direction of the bounded CPU-baseline sample")
