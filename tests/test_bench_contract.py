@@ -47,3 +47,17 @@ def test_both_arms_share_one_config_object_and_the_cpu_arm_uses_every_core():
     assert d["cpu_baseline"]["cores"] == bench.host_threads()
     bump = bench.Workload(argparse.Namespace(workload="bump4m", n=344, n_cpu=12, bump_nx=1280, bump_ny=1040, bump_nx_cpu=40, bump_ny_cpu=30))
     assert bump.config["cells"] == 3 * 1280 * 1040 and "Minmod" in bump.config["workload"]
+
+
+def test_reference_arm_runs_the_harmonic_balance_workload():
+    """--workload vki-hb (C5 ii): the CPU arm is the reference-structured HB oracle world on the shipped VKI-LS89 mesh."""
+    import pytest
+    from icsfoam_b200 import cases
+    if cases.tutorial_dir("VKI-LS89") is None:
+        pytest.skip("VKI-LS89 tutorial not found")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "vki-hb"],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["config"]["cells"] == 3 * 28059 and "Harmonic Balance" in d["config"]["workload"] and d["value"] > 0
+    assert d["run"]["sample_cells"] == 3 * 28059 and d["run"]["restarts_per_step"] >= 1
