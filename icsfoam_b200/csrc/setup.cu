@@ -505,7 +505,9 @@ extern "C" int icsb200_mesh_set(icsb200_ctx* c, int N, int F, int FT, const int*
                             }
                             return tsum + (sm2 / dep + 1) * T;
                         };
-                        depth = colChain(4) < colChain(8) ? 4 : 8;
+                        // measured: 172^3 1.95 ms (4) against 2.00 (8), 200^3 2.78 (4) against 2.58 (8), 344^3 12.5 (4) against 9.7 (8):
+                        // the shallow tiles only pay on small partitions
+                        depth = (N < 6000000 && colChain(4) < colChain(8)) ? 4 : 8;
                     }
                 }
                 if (const char* e = getenv("ICSB200_LUSGS_COLMODE")) colMode = atoi(e) != 0;
