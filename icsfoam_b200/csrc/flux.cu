@@ -276,7 +276,7 @@ __device__ __forceinline__ Flux5 faceFlux(const FaceState& s, V3 Sf, double magS
 // ------------------------------------------------------------------------------------------------ k_grad
 // gaussGrad::gradf for the NQ reconstructed scalars.  f: fields [Q_COUNT][NX]; grad: [NQ*3][NPH]
 template <int NQ>
-__global__ void __launch_bounds__(128, NQ > 4 ? 4 : 5)
+__global__ void __launch_bounds__(128, NQ > 4 ? 4 : (NQ > 1 ? 5 : 8))
 k_grad(int NP, const int* __restrict__ pos2cell, const int* __restrict__ sliceOff, const int* __restrict__ rowNAll, const int* __restrict__ col,
        const int* __restrict__ meta, const int* __restrict__ gfid, const double* __restrict__ geo, size_t NFG, const double* __restrict__ V,
        const double* __restrict__ f, size_t NX, double* __restrict__ grad, size_t NPH)
